@@ -144,3 +144,214 @@ def grid_start_for(curve_lower: float, curve_upper: float, bin_width: float) -> 
 def num_bins_for(curve_lower: float, curve_upper: float, bin_width: float) -> int:
     """R:139-140: ``length(seq(lower, upper, bw))``."""
     return int(np.floor((curve_upper - curve_lower) / bin_width + 1e-10)) + 1
+
+
+# ---------------------------------------------------------------------------------------------
+# Packed boundary (include/fgt_companion.h part 2)
+# ---------------------------------------------------------------------------------------------
+class fgt_chrom_t(C.Structure):
+    _fields_ = [("nsites", C.c_int32), ("pos", C.c_void_p), ("rate", C.c_void_p), ("labels", C.c_void_p),
+                ("labels_on_device", C.c_int32)]
+
+
+class fgt_problem_t(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("ploidy", C.c_int32), ("nsamples", C.c_int32), ("num_chrom", C.c_int32),
+                ("n_packed_inds", C.c_int32), ("label_bytes", C.c_int32), ("chrom", C.POINTER(fgt_chrom_t)),
+                ("num_inds", C.c_int32), ("ind_rows", C.c_void_p), ("num_inds_total", C.c_int32),
+                ("pair_offset", C.c_void_p), ("pairs_total", C.c_int64), ("binwidth", C.c_double),
+                ("num_bins", C.c_int32), ("grid_start", C.c_int32), ("num_donors", C.c_int32),
+                ("donor_label_vec", C.c_void_p), ("n_donor_labels", C.c_int32), ("weight_min", C.c_double),
+                ("gridweight_max_cutoff", C.c_double), ("num_surrogates", C.c_int32), ("temp_weights", C.c_void_p)]
+
+
+class fgt_stats_t(C.Structure):
+    _fields_ = [("pairs", C.c_int64), ("accepted", C.c_int64), ("chunks", C.c_int64), ("kernel_launches", C.c_int32),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("ms_chunk", C.c_float), ("ms_rand", C.c_float),
+                ("ms_accum", C.c_float), ("ms_project", C.c_float), ("ms_total", C.c_float),
+                ("accum_launches", C.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+FGT_ERRORS = {0: "ok", -1: "no CUDA device (no CPU path)", -2: "CUDA error", -3: "missing donor (-9)",
+              -4: "donor label out of range", -5: "bad argument", -6: "libc rand() state unsupported",
+              -7: "mode 3 met a target-population chunk"}
+
+
+class FgtError(RuntimeError):
+    def __init__(self, rc):
+        super().__init__(f"fgt error {rc}: {FGT_ERRORS.get(rc, '?')}")
+        self.rc = rc
+
+
+class PackedCompanion(Companion):
+    """The B200 library including its packed entry points.  ``chrom`` arguments are lists of dicts
+    with ``pos``/``rate`` (numpy float64) and ``labels`` -- a numpy array [rows, nsites] (uint16 or
+    int32; host path) or a ``(device_ptr, dtype_itemsize)`` tuple (already resident in HBM)."""
+
+    def __init__(self, path: str | None = None):
+        super().__init__(path)
+        L = self.lib
+        L.fgt_data_read_packed.argtypes = [C.POINTER(fgt_problem_t), _dp, C.POINTER(fgt_stats_t)]
+        L.fgt_data_read_packed.restype = C.c_int
+        L.fgt_count_pairs_packed.argtypes = [C.POINTER(fgt_problem_t), C.POINTER(C.c_int64)]
+        L.fgt_count_pairs_packed.restype = C.c_int
+        L.fgt_data_read_null_packed.argtypes = [C.POINTER(fgt_problem_t), _ip, _dp, C.POINTER(fgt_stats_t)]
+        L.fgt_data_read_null_packed.restype = C.c_int
+        L.fgt_get_raw_counts.argtypes = [_dp, C.c_int64]
+        L.fgt_get_raw_counts.restype = C.c_int64
+        L.fgt_set_option.argtypes = [C.c_char_p, C.c_double]
+        L.fgt_set_option.restype = C.c_int
+        L.fgt_get_option.argtypes = [C.c_char_p]
+        L.fgt_get_option.restype = C.c_double
+        L.fgt_srand.argtypes = [C.c_uint]
+        L.fgt_srand.restype = None
+        L.fgt_last_stats.argtypes = [C.POINTER(fgt_stats_t)]
+        L.fgt_last_stats.restype = None
+        L.fgt_rand_fill.argtypes = [C.c_void_p, C.c_int64]
+        L.fgt_rand_fill.restype = C.c_int
+        L.fgt_chunk_one.restype = C.c_int
+        L.fgt_version.restype = C.c_char_p
+
+    def set_option(self, key: str, value: float):
+        rc = self.lib.fgt_set_option(key.encode(), float(value))
+        if rc:
+            raise FgtError(rc)
+
+    def get_option(self, key: str) -> float:
+        return self.lib.fgt_get_option(key.encode())
+
+    def srand(self, seed: int):
+        self.lib.fgt_srand(C.c_uint(seed))
+
+    def last_stats(self) -> dict:
+        s = fgt_stats_t()
+        self.lib.fgt_last_stats(C.byref(s))
+        return s.as_dict()
+
+    def rand_fill(self, n: int) -> np.ndarray:
+        out = np.zeros(n, dtype=np.int32)
+        rc = self.lib.fgt_rand_fill(out.ctypes.data, n)
+        if rc:
+            raise FgtError(rc)
+        return out
+
+    def _problem(self, mode, ploidy, nsamples, chrom, ind_rows, bin_width, num_bins, grid_start, K, donor_label_vec,
+                 weight_min, cutoff, S, temp_weights, n_packed_inds=None, num_inds_total=0, pair_offset=None,
+                 pairs_total=0):
+        keep = []
+        n = len(chrom)
+        carr = (fgt_chrom_t * n)()
+        lb = None
+        rows = None
+        for h, c in enumerate(chrom):
+            pos = np.ascontiguousarray(c["pos"], dtype=np.float64)
+            rate = np.ascontiguousarray(c["rate"], dtype=np.float64)
+            keep += [pos, rate]
+            carr[h].nsites = pos.size
+            carr[h].pos = pos.ctypes.data
+            carr[h].rate = rate.ctypes.data
+            lab = c["labels"]
+            if isinstance(lab, tuple):
+                ptr, item, nrows = lab
+                carr[h].labels = ptr
+                carr[h].labels_on_device = 1
+                this_lb, this_rows = item, nrows
+            else:
+                lab = np.ascontiguousarray(lab)
+                keep.append(lab)
+                carr[h].labels = lab.ctypes.data
+                carr[h].labels_on_device = 0
+                this_lb, this_rows = lab.dtype.itemsize, lab.shape[0]
+            assert lb in (None, this_lb)
+            lb, rows = this_lb, this_rows
+        ids = np.ascontiguousarray(ind_rows, dtype=np.int32).ravel()
+        dl = np.ascontiguousarray(donor_label_vec, dtype=np.int32)
+        keep += [ids, dl, carr]
+        pb = fgt_problem_t()
+        pb.mode, pb.ploidy, pb.nsamples, pb.num_chrom = mode, ploidy, nsamples, n
+        pb.n_packed_inds = n_packed_inds if n_packed_inds is not None else rows // (ploidy * nsamples)
+        pb.label_bytes = lb
+        pb.chrom = carr
+        pb.num_inds = ids.size // n
+        pb.ind_rows = ids.ctypes.data
+        pb.num_inds_total = num_inds_total
+        if pair_offset is not None:
+            po = np.ascontiguousarray(pair_offset, dtype=np.int64)
+            keep.append(po)
+            pb.pair_offset = po.ctypes.data
+            pb.pairs_total = int(pairs_total)
+        pb.binwidth, pb.num_bins, pb.grid_start, pb.num_donors = bin_width, num_bins, grid_start, K
+        pb.donor_label_vec = dl.ctypes.data
+        pb.n_donor_labels = dl.size
+        pb.weight_min, pb.gridweight_max_cutoff, pb.num_surrogates = weight_min, cutoff, S
+        if temp_weights is not None:
+            tw = np.ascontiguousarray(temp_weights, dtype=np.float64).ravel()
+            keep.append(tw)
+            pb.temp_weights = tw.ctypes.data
+        return pb, keep
+
+    def data_read_packed(self, mode, ploidy, nsamples, chrom, ind_rows, bin_width, num_bins, grid_start, K,
+                         donor_label_vec, weight_min, cutoff, S, temp_weights, want_raw=False, means_init=None, **kw):
+        """Returns (means [S*S, G], raw or None, stats dict)."""
+        pb, keep = self._problem(mode, ploidy, nsamples, chrom, ind_rows, bin_width, num_bins, grid_start, K,
+                                 donor_label_vec, weight_min, cutoff, S, temp_weights, **kw)
+        means = np.zeros(S * S * num_bins, dtype=np.float64) if means_init is None else \
+            np.ascontiguousarray(means_init, dtype=np.float64).ravel().copy()
+        st = fgt_stats_t()
+        self.set_option("keep_raw", 1 if want_raw else 0)
+        rc = self.lib.fgt_data_read_packed(C.byref(pb), means.ctypes.data_as(_dp), C.byref(st))
+        del keep
+        if rc:
+            raise FgtError(rc)
+        raw = self.get_raw_counts(K, num_bins) if want_raw else None
+        return means.reshape(S * S, num_bins), raw, st.as_dict()
+
+    def count_pairs_packed(self, mode, ploidy, nsamples, chrom, ind_rows, bin_width, num_bins, grid_start, K,
+                           donor_label_vec, weight_min, cutoff, **kw) -> np.ndarray:
+        pb, keep = self._problem(mode, ploidy, nsamples, chrom, ind_rows, bin_width, num_bins, grid_start, K,
+                                 donor_label_vec, weight_min, cutoff, 1, None, **kw)
+        out = np.zeros(pb.num_chrom * pb.num_inds, dtype=np.int64)
+        rc = self.lib.fgt_count_pairs_packed(C.byref(pb), out.ctypes.data_as(C.POINTER(C.c_int64)))
+        del keep
+        if rc:
+            raise FgtError(rc)
+        return out.reshape(pb.num_chrom, pb.num_inds)
+
+    def get_raw_counts(self, K, num_bins) -> np.ndarray:
+        n = self.lib.fgt_get_raw_counts(None, 0)
+        out = np.zeros(max(n, 0), dtype=np.float64)
+        if n > 0:
+            self.lib.fgt_get_raw_counts(out.ctypes.data_as(_dp), n)
+        return out.reshape(-1, K * K, num_bins)
+
+    def data_read_null_packed(self, ploidy, nsamples, chrom, rec_rows, bin_width, num_bins, grid_start, K,
+                              donor_label_vec, weight_min, cutoff, init=None):
+        rows = np.ascontiguousarray(rec_rows, dtype=np.int32)
+        pb, keep = self._problem(1, ploidy, nsamples, chrom, np.zeros(len(chrom) * rows.size, dtype=np.int32), bin_width,
+                                 num_bins, grid_start, K, donor_label_vec, weight_min, cutoff, 1, None)
+        out = np.zeros(K * K * num_bins, dtype=np.float64) if init is None else \
+            np.ascontiguousarray(init, dtype=np.float64).ravel().copy()
+        st = fgt_stats_t()
+        rc = self.lib.fgt_data_read_null_packed(C.byref(pb), rows.ctypes.data_as(_ip), out.ctypes.data_as(_dp), C.byref(st))
+        del keep
+        if rc:
+            raise FgtError(rc)
+        return out.reshape(K * K, num_bins), st.as_dict()
+
+    def chunk_one(self, labels_row, pos, rate, weight_min, cutoff, donor_label_vec):
+        lab = np.ascontiguousarray(labels_row)
+        L = lab.size
+        p = np.ascontiguousarray(pos, dtype=np.float64)
+        r = np.ascontiguousarray(rate, dtype=np.float64)
+        dl = np.ascontiguousarray(donor_label_vec, dtype=np.int32)
+        arrs = [np.zeros(L, dtype=np.float64) for _ in range(4)]
+        pop = np.zeros(L, dtype=np.int32)
+        n = self.lib.fgt_chunk_one(C.c_void_p(lab.ctypes.data), C.c_int(lab.dtype.itemsize), C.c_int(L),
+                                   p.ctypes.data_as(_dp), r.ctypes.data_as(_dp), C.c_double(weight_min),
+                                   C.c_double(cutoff), dl.ctypes.data_as(_ip), C.c_int(dl.size),
+                                   *[a.ctypes.data_as(_dp) for a in arrs], pop.ctypes.data_as(_ip))
+        if n < 0:
+            return n, None
+        return n, {"pos": arrs[0][:n], "size": arrs[1][:n], "weight": arrs[2][:n], "end": arrs[3][:n], "pop": pop[:n]}

@@ -1,0 +1,674 @@
+// engine.cu -- host orchestration: packed paintings -> chunks -> sampling schedule -> rand() stream
+// -> ordered accumulation -> projection -> normalised curves.  One CUDA stream, grow-only device
+// buffers, no CPU compute path.
+#include "engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+namespace fgt {
+
+#define CK(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            fprintf(stderr, "fastGLOBETROTTERCompanion(B200): CUDA error %s at %s:%d: %s\n",     \
+                    cudaGetErrorName(e__), __FILE__, __LINE__, cudaGetErrorString(e__));          \
+            return FGT_ERR_CUDA;                                                                  \
+        }                                                                                         \
+    } while (0)
+
+void *DevBuf::get(size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    if (bytes <= cap) return p;
+    if (p) cudaFree(p);
+    size_t want = bytes + bytes / 8 + 256;
+    if (cudaMalloc(&p, want) != cudaSuccess) {
+        p = nullptr; cap = 0;
+        fprintf(stderr, "fastGLOBETROTTERCompanion(B200): cudaMalloc of %zu bytes failed\n", want);
+        return nullptr;
+    }
+    cap = want;
+    return p;
+}
+
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+}
+
+Engine &Engine::get() {
+    static Engine e;
+    return e;
+}
+
+int Engine::set_option(const char *key, double v) {
+    std::string k(key);
+    int iv = (int)v;
+    if (k == "device") { if (inited_ && iv != opt.device) { inited_ = false; } opt.device = iv; }
+    else if (k == "strict") opt.strict = iv;
+    else if (k == "keep_raw") opt.keep_raw = iv;
+    else if (k == "rand_libc") opt.rand_libc = iv;
+    else if (k == "slab_bins") opt.slab_bins = iv;
+    else if (k == "cache") opt.cache = iv;
+    else if (k == "threads") opt.threads = iv;
+    else if (k == "verbose") opt.verbose = iv;
+    else if (k == "reuse_prep") opt.reuse_prep = iv;
+    else return FGT_ERR_ARG;
+    return FGT_OK;
+}
+
+double Engine::get_option(const char *key) {
+    std::string k(key);
+    if (k == "device") return opt.device;
+    if (k == "strict") return opt.strict;
+    if (k == "keep_raw") return opt.keep_raw;
+    if (k == "rand_libc") return opt.rand_libc;
+    if (k == "slab_bins") return opt.slab_bins;
+    if (k == "cache") return opt.cache;
+    if (k == "threads") return opt.threads;
+    if (k == "verbose") return opt.verbose;
+    if (k == "reuse_prep") return opt.reuse_prep;
+    return NAN;
+}
+
+int Engine::ensure_init() {
+    if (inited_) return init_rc_;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        fprintf(stderr, "fastGLOBETROTTERCompanion(B200): no usable CUDA device (%s). This library has no CPU path.\n",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        cudaGetLastError();
+        return FGT_ERR_NO_DEVICE;
+    }
+    if (opt.device >= n) return FGT_ERR_ARG;
+    CK(cudaSetDevice(opt.device));
+    if (!st_) CK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+    if (level_tab_.empty()) level_tab_ = build_level_tables();
+    uint32_t *dt = d_level_tab_.as<uint32_t>(level_tab_.size());
+    if (!dt) return FGT_ERR_CUDA;
+    CK(cudaMemcpy(dt, level_tab_.data(), level_tab_.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (!d_err_.as<int>(4) || !d_accepted_.as<unsigned long long>(2)) return FGT_ERR_CUDA;
+    inited_ = true;
+    init_rc_ = FGT_OK;
+    return FGT_OK;
+}
+
+bool Engine::fetch_history(History &h) {
+    if (opt.rand_libc) return libc_snapshot(h);
+    h = private_hist_;
+    return true;
+}
+
+void Engine::store_history(const History &h) {
+    if (opt.rand_libc) libc_store(h);
+    else private_hist_ = h;
+}
+
+static int err_to_code(int bits) {
+    if (bits & kErrMissingDonor) return FGT_ERR_MISSING_DONOR;
+    if (bits & kErrLabelRange) return FGT_ERR_LABEL_RANGE;
+    if (bits & kErrMode3Target) return FGT_ERR_MODE3_TARGET;
+    if (bits) return FGT_ERR_CUDA;
+    return FGT_OK;
+}
+
+// Slab table for the strict accumulation kernel.  A slab owns fine bins [b0,b1] of the full grid;
+// an update lands in bin B only if its distance d is within half a bin of B*bw, and a pair of
+// coarse bins (j,k) only produces distances in (k-j-1, k-j+1), so separations outside
+// [floor((b0-.5)bw), floor((b1+.5)bw)+1] cannot reach the slab (a superset is harmless).
+std::vector<SlabDesc> Engine::make_slabs(int G, int grid_start, double bw, int W, int N) const {
+    int sb = opt.slab_bins;
+    if (sb <= 0) {
+        // trade redundancy (each slab re-evaluates ~2 cM of separations beyond its own width)
+        // against the number of independent warps
+        const double target = 148.0 * 40.0;
+        double best = -1;
+        sb = G;
+        for (int cand = 4; cand <= std::max(G, 4); cand = cand + std::max(1, cand / 4)) {
+            int c = std::min(cand, G);
+            double slabs = std::ceil((double)G / c);
+            double tasks = slabs * N;
+            double redundancy = (c * bw + 2.0) / (c * bw);
+            double score = std::min(tasks, target) / redundancy;
+            if (score > best * 1.02) { best = score; sb = c; }
+            if (c == G) break;
+        }
+    }
+    std::vector<SlabDesc> v;
+    for (int b = 0; b < G; b += sb) {
+        SlabDesc s;
+        s.b0 = grid_start + b;
+        s.b1 = grid_start + std::min(G, b + sb) - 1;
+        double dmin = (s.b0 - 0.5) * bw - 1e-6, dmax = (s.b1 + 0.5) * bw + 1e-6;
+        s.dlo = std::max(1, (int)std::floor(dmin));
+        s.dhi = std::min(W - 1, (int)std::floor(dmax) + 1);
+        if (s.dlo <= s.dhi) v.push_back(s);
+    }
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// chunk + bin one chromosome.  rows = painting rows to encode (through rowmap_dev if given),
+// grouped rows_per_ind at a time into n_groups "individuals" (data_read) -- or, for the NULL path,
+// one row per haplotype and no binning.
+// ---------------------------------------------------------------------------------------------
+int Engine::prep_chromosome(const fgt_problem_t &pb, int h, const int32_t *rowmap_dev, int rows, int rows_per_ind,
+                            int n_groups, bool for_null, ChromState &cs, fgt_stats_t &stx) {
+    const fgt_chrom_t &c = pb.chrom[h];
+    const int L = c.nsites;
+    if (L <= 0) return FGT_ERR_ARG;
+    // cM prefix: sequential fp64 sum exactly as reference C:494 (and the increment re-used at C:501)
+    std::vector<double> cum(L), inc(L);
+    {
+        double total = 0.0;
+        cum[0] = 0.0; inc[0] = 0.0;
+        for (int j = 1; j < L; j++) {
+            double step = c.rate[j - 1] * (c.pos[j] - c.pos[j - 1]) * 100;
+            total = total + step;
+            cum[j] = total; inc[j] = step;
+        }
+    }
+    double *d_cum = d_cum_.as<double>(L), *d_inc = d_inc_.as<double>(L);
+    if (!d_cum || !d_inc) return FGT_ERR_CUDA;
+    CK(cudaMemcpyAsync(d_cum, cum.data(), L * sizeof(double), cudaMemcpyHostToDevice, st_));
+    CK(cudaMemcpyAsync(d_inc, inc.data(), L * sizeof(double), cudaMemcpyHostToDevice, st_));
+    stx.h2d_bytes += 2LL * L * sizeof(double);
+    const void *d_lab = c.labels;
+    if (!c.labels_on_device) {
+        size_t bytes = (size_t)pb.n_packed_inds * pb.ploidy * pb.nsamples * L * pb.label_bytes;
+        void *buf = d_labels_.get(bytes);
+        if (!buf) return FGT_ERR_CUDA;
+        CK(cudaMemcpyAsync(buf, c.labels, bytes, cudaMemcpyHostToDevice, st_));
+        stx.h2d_bytes += (int64_t)bytes;
+        d_lab = buf;
+    }
+    int32_t *d_counts = d_counts_.as<int32_t>(rows), *d_rowoff = d_rowoff_.as<int32_t>(rows + 1);
+    if (!d_counts || !d_rowoff) return FGT_ERR_CUDA;
+    launch_chunk_count(d_lab, rowmap_dev, pb.label_bytes, L, rows, pb.weight_min, d_counts, st_);
+    launch_exclusive_scan_i32(d_counts, d_rowoff, rows, st_);
+    launches_ += 2;
+    int32_t total_chunks = 0;
+    CK(cudaMemcpyAsync(&total_chunks, d_rowoff + rows, sizeof(int32_t), cudaMemcpyDeviceToHost, st_));
+    // the copies above read host vectors that die at scope exit: synchronise here (also yields total_chunks)
+    CK(cudaStreamSynchronize(st_));
+    stx.d2h_bytes += 4;
+    if (total_chunks <= 0) return FGT_ERR_ARG;
+    cs.n_chunks = total_chunks;
+    stx.chunks += total_chunks;
+    double *d_cstart = d_cstart_.as<double>(total_chunks), *d_cend = d_cend_.as<double>(total_chunks);
+    int32_t *d_chap = d_chap_.as<int32_t>(total_chunks);
+    if (!d_cstart || !d_cend || !d_chap) return FGT_ERR_CUDA;
+    launch_chunk_emit(d_lab, rowmap_dev, pb.label_bytes, L, rows, pb.weight_min, d_rowoff, d_cum, d_inc, d_cstart, d_cend,
+                      d_chap, st_);
+    launches_ += 1;
+    Chunk *d_sorted = cs.sorted.as<Chunk>(total_chunks);
+    if (!d_sorted) return FGT_ERR_CUDA;
+    const int K = pb.num_donors;
+    if (for_null) {
+        int32_t *d_laboff = cs.yoff.as<int32_t>((size_t)rows * (K + 2));
+        int32_t *d_base = cs.chunk_base.as<int32_t>(rows + 1);
+        if (!d_laboff || !d_base) return FGT_ERR_CUDA;
+        CK(cudaMemcpyAsync(d_base, d_rowoff, (rows + 1) * sizeof(int32_t), cudaMemcpyDeviceToDevice, st_));
+        launch_null_group(rows, d_rowoff, d_cstart, d_cend, d_chap, d_donor_.as<int32_t>(pb.n_donor_labels),
+                          pb.n_donor_labels, pb.gridweight_max_cutoff, K, d_sorted, d_laboff, d_err_.as<int>(4), st_);
+        launches_ += 1;
+        return FGT_OK;
+    }
+    // coarse binning + sampling schedule
+    const double chr_length = cum[L - 1];                    // every painting's last chunk ends here (C:57-65)
+    const int nb = (int)chr_length / 1 + 1;                  // reference C:67-68
+    const int W = (int)std::ceil(pb.binwidth * pb.num_bins) + (pb.mode == 3 ? 1 : 3);   // C:117 / C:1125
+    cs.nb = nb; cs.W = W;
+    std::vector<double> etab(W);
+    for (int d = 0; d < W; d++) etab[d] = std::exp(-0.05 * d);   // exp(-0.05*(k-j)) with the host libm, as C:129
+    double *d_etab = d_etab_.as<double>(W);
+    if (!d_etab) return FGT_ERR_CUDA;
+    CK(cudaMemcpyAsync(d_etab, etab.data(), W * sizeof(double), cudaMemcpyHostToDevice, st_));
+    int32_t *d_t = cs.t.as<int32_t>((size_t)n_groups * nb), *d_first = cs.first.as<int32_t>((size_t)n_groups * nb);
+    int32_t *d_yoff = cs.yoff.as<int32_t>((size_t)n_groups * nb * W);
+    long long *d_ro = cs.rowoff.as<long long>((size_t)n_groups * (nb + 1));
+    int32_t *d_cbase = cs.chunk_base.as<int32_t>(n_groups + 1);
+    size_t cm = (size_t)n_groups * rows_per_ind * nb;
+    int32_t *d_cnt = d_cntmat_.as<int32_t>(cm), *d_rf = d_runfirst_.as<int32_t>(cm);
+    if (!d_t || !d_first || !d_yoff || !d_ro || !d_cbase || !d_cnt || !d_rf) return FGT_ERR_CUDA;
+    CK(cudaMemsetAsync(d_cnt, 0, cm * sizeof(int32_t), st_));
+    launch_bin_sort(n_groups, rows_per_ind, d_rowoff, d_cstart, d_cend, d_chap, d_donor_.as<int32_t>(pb.n_donor_labels),
+                    pb.n_donor_labels, pb.gridweight_max_cutoff, K, pb.mode, nb, W, d_etab, pb.mode == 3 ? 8.0 : 10.0,
+                    d_sorted, d_cbase, d_t, d_first, d_yoff, d_ro, d_cnt, d_rf, d_err_.as<int>(4), st_);
+    launches_ += 1;
+    cs.totals.resize(n_groups);
+    CK(cudaMemcpy2DAsync(cs.totals.data(), sizeof(long long), d_ro + nb, (nb + 1) * sizeof(long long), sizeof(long long),
+                         n_groups, cudaMemcpyDeviceToHost, st_));
+    CK(cudaStreamSynchronize(st_));   // etab (host vector) and totals
+    stx.d2h_bytes += (int64_t)n_groups * 8;
+    return FGT_OK;
+}
+
+// The reference walks the samples file forwards (C:418-425, C:553-560): a non-positive step in the
+// id sequence re-tabulates the individual that was read last.  Returns the packed individual used
+// by each pseudo-individual of chromosome h, or false if the walk leaves the packed range.
+static bool resolve_walk(const int32_t *ids, int stride, int N, int n_packed, std::vector<int32_t> &used) {
+    used.resize(N);
+    int next_in_file = 0;
+    for (int n = 0; n < N; n++) {
+        int id = ids[(size_t)n * stride];
+        if (n == 0) { used[0] = id; next_in_file = id + 1; }
+        else {
+            int skip = id - ids[(size_t)(n - 1) * stride] - 1;
+            if (skip < 0) used[n] = used[n - 1];
+            else { used[n] = next_in_file + skip; next_in_file = used[n] + 1; }
+        }
+        if (used[n] < 0 || used[n] >= n_packed) return false;
+    }
+    return true;
+}
+
+int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t *stats, int64_t *count_only) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    if ((pb.mode != 1 && pb.mode != 3) || pb.ploidy <= 0 || pb.nsamples <= 0 || pb.num_chrom <= 0 || pb.num_inds <= 0 ||
+        pb.n_packed_inds <= 0 || (pb.label_bytes != 2 && pb.label_bytes != 4) || pb.num_bins <= 0 || pb.num_donors <= 0 ||
+        pb.num_surrogates <= 0 || !(pb.binwidth > 0))
+        return FGT_ERR_ARG;
+    CK(cudaSetDevice(opt.device));
+    fgt_stats_t stx{};
+    launches_ = 0;
+    cudaEvent_t ev[6];
+    for (auto &e : ev) CK(cudaEventCreate(&e));
+    CK(cudaEventRecord(ev[0], st_));
+
+    const int N = pb.num_inds, Cn = pb.num_chrom, K = pb.num_donors, G = pb.num_bins, S = pb.num_surrogates;
+    const int PM = pb.ploidy * pb.nsamples;
+    const int n_phys = pb.n_packed_inds;
+    int *d_err = d_err_.as<int>(4);
+    unsigned long long *d_acc = d_accepted_.as<unsigned long long>(2);
+    CK(cudaMemsetAsync(d_err, 0, 4 * sizeof(int), st_));
+    CK(cudaMemsetAsync(d_acc, 0, 2 * sizeof(unsigned long long), st_));
+    int32_t *d_donor = d_donor_.as<int32_t>(pb.n_donor_labels);
+    if (!d_donor) return FGT_ERR_CUDA;
+    CK(cudaMemcpyAsync(d_donor, pb.donor_label_vec, pb.n_donor_labels * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
+
+    // ---- pass 1: chunks, coarse bins, sampling schedule of every chromosome ---------------------
+    const bool reuse = opt.reuse_prep && (int)chroms_.size() == Cn && !chroms_.empty() && chroms_[0].nb > 0;
+    opt.reuse_prep = 0;
+    if (!reuse) {
+        chroms_.resize(Cn);
+        for (int h = 0; h < Cn; h++) {
+            rc = prep_chromosome(pb, h, nullptr, n_phys * PM, PM, n_phys, false, chroms_[h], stx);
+            if (rc) return rc;
+        }
+    }
+    CK(cudaEventRecord(ev[1], st_));
+    {
+        int herr[4];
+        CK(cudaMemcpyAsync(herr, d_err, sizeof herr, cudaMemcpyDeviceToHost, st_));
+        CK(cudaStreamSynchronize(st_));
+        if (herr[0] & (kErrMissingDonor | kErrLabelRange)) return err_to_code(herr[0]);
+    }
+
+    // ---- stream positions -----------------------------------------------------------------------
+    std::vector<std::vector<int32_t>> used(Cn);
+    std::vector<long long> pair_abs((size_t)Cn * N);     // absolute pair index (from call entry) of (h,n)
+    long long run = 0, my_pairs = 0;
+    for (int h = 0; h < Cn; h++) {
+        if (!resolve_walk(pb.ind_rows + h, Cn, N, n_phys, used[h])) {
+            fprintf(stderr, "fastGLOBETROTTERCompanion(B200): ind_id_vec walks outside the recipients of the samples file\n");
+            return FGT_ERR_ARG;
+        }
+        for (int n = 0; n < N; n++) {
+            long long cnt = chroms_[h].totals[used[h][n]];
+            if (count_only) count_only[(size_t)h * N + n] = cnt;
+            pair_abs[(size_t)h * N + n] = pb.pair_offset ? pb.pair_offset[(size_t)h * N + n] : run;
+            run += cnt;
+            my_pairs += cnt;
+        }
+    }
+    if (count_only) {
+        for (auto &e : ev) cudaEventDestroy(e);
+        return FGT_OK;
+    }
+    const long long all_pairs = pb.pair_offset ? pb.pairs_total : run;
+    stx.pairs = my_pairs;
+
+    History h0;
+    if (!fetch_history(h0)) {
+        fprintf(stderr, "fastGLOBETROTTERCompanion(B200): libc rand() is not in its default TYPE_3 state\n");
+        return FGT_ERR_RAND;
+    }
+
+    // ---- device tables for the accumulation ---------------------------------------------------------
+    const size_t P = (size_t)K * (K + 1) / 2;
+    const size_t tens_elems = (size_t)N * P * G;
+    double *d_tensor = d_tensor_.as<double>(tens_elems);
+    double *d_results = d_results_.as<double>((size_t)N * S * S * G);
+    double *d_tw = d_tw_.as<double>((size_t)K * K * S * S);
+    int32_t *d_pairkh = d_pairkh_.as<int32_t>(P);
+    if (!d_tensor || !d_results || !d_tw || !d_pairkh) return FGT_ERR_CUDA;
+    CK(cudaMemsetAsync(d_tensor, 0, tens_elems * sizeof(double), st_));
+    CK(cudaMemsetAsync(d_results, 0, (size_t)N * S * S * G * sizeof(double), st_));
+    CK(cudaMemcpyAsync(d_tw, pb.temp_weights, (size_t)K * K * S * S * sizeof(double), cudaMemcpyHostToDevice, st_));
+    stx.h2d_bytes += (int64_t)K * K * S * S * 8;
+    std::vector<int32_t> pairkh(P);
+    {
+        size_t q = 0;
+        for (int k = 0; k < K; k++)
+            for (int hh = k; hh < K; hh++) pairkh[q++] = K * k + hh;
+    }
+    CK(cudaMemcpyAsync(d_pairkh, pairkh.data(), P * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
+    const int W0 = chroms_[0].W;
+    std::vector<SlabDesc> slabs = make_slabs(G, pb.grid_start, pb.binwidth, W0, N);
+    SlabDesc *d_slabs = d_slabs_.as<SlabDesc>(slabs.size());
+    long long *d_pairbase = d_pairbase_.as<long long>((size_t)Cn * N);
+    int32_t *d_physof = d_physof_.as<int32_t>((size_t)Cn * N);
+    uint32_t *d_hist = d_hist_.as<uint32_t>((size_t)Cn * kLag);
+    if (!d_slabs || !d_pairbase || !d_physof || !d_hist) return FGT_ERR_CUDA;
+    CK(cudaMemcpyAsync(d_slabs, slabs.data(), slabs.size() * sizeof(SlabDesc), cudaMemcpyHostToDevice, st_));
+
+    // per chromosome: stream window [lo,hi) in pairs, buffer origin (in draws, multiple of 4)
+    std::vector<long long> origin(Cn), nthreads(Cn);
+    std::vector<long long> pairbase_rel((size_t)Cn * N);
+    std::vector<int32_t> physof((size_t)Cn * N);
+    std::vector<uint32_t> hists((size_t)Cn * kLag);
+    long long max_draws = 0;
+    for (int h = 0; h < Cn; h++) {
+        long long lo = -1, hi = 0;
+        for (int n = 0; n < N; n++) {
+            long long a0 = pair_abs[(size_t)h * N + n], c0 = chroms_[h].totals[used[h][n]];
+            if (lo < 0 || a0 < lo) lo = a0;
+            hi = std::max(hi, a0 + c0);
+        }
+        long long A4 = (2 * lo) & ~3LL;
+        origin[h] = A4;
+        long long nd = 2 * hi - A4;
+        nthreads[h] = (nd + kRun - 1) / kRun;
+        max_draws = std::max(max_draws, nthreads[h] * (long long)kRun);
+        History hh = apply_jump(poly_pow_E((uint64_t)A4), h0);
+        std::memcpy(&hists[(size_t)h * kLag], hh.x, sizeof hh.x);
+        for (int n = 0; n < N; n++) {
+            pairbase_rel[(size_t)h * N + n] = pair_abs[(size_t)h * N + n] - A4 / 2;
+            physof[(size_t)h * N + n] = used[h][n];
+        }
+    }
+    CK(cudaMemcpyAsync(d_pairbase, pairbase_rel.data(), pairbase_rel.size() * sizeof(long long), cudaMemcpyHostToDevice, st_));
+    CK(cudaMemcpyAsync(d_physof, physof.data(), physof.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
+    CK(cudaMemcpyAsync(d_hist, hists.data(), hists.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st_));
+    uint32_t *d_draws = d_draws_.as<uint32_t>((size_t)max_draws + 4);
+    if (!d_draws) return FGT_ERR_CUDA;
+
+    const bool want_raw = opt.keep_raw != 0;
+    raw_count_ = 0;
+    double *d_raw = nullptr;
+    if (want_raw) {
+        size_t slots = (pb.mode == 1) ? (size_t)N : (size_t)N * Cn;
+        d_raw = d_raw_.as<double>(slots * K * K * G);
+        if (!d_raw) return FGT_ERR_CUDA;
+        raw_count_ = (int64_t)slots * K * K * G;
+    }
+
+    CK(cudaEventRecord(ev[2], st_));
+    float ms_rand = 0.f, ms_accum = 0.f, ms_proj = 0.f;
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&]() { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st_); tev.push_back(e); };
+    for (int h = 0; h < Cn; h++) {
+        ChromState &cs = chroms_[h];
+        mark();
+        launch_rand_fill(d_hist + (size_t)h * kLag, d_level_tab_.as<uint32_t>(level_tab_.size()), d_draws, nthreads[h], st_);
+        launches_ += 1;
+        mark();
+        AccumArgs a{};
+        a.cp.nb = cs.nb; a.cp.W = cs.W; a.cp.n_phys = n_phys;
+        a.cp.chunks = (const Chunk *)cs.sorted.p; a.cp.chunk_base = (const int32_t *)cs.chunk_base.p;
+        a.cp.t = (const int32_t *)cs.t.p; a.cp.first = (const int32_t *)cs.first.p;
+        a.cp.yoff = (const int32_t *)cs.yoff.p; a.cp.rowoff = (const long long *)cs.rowoff.p;
+        a.draws = (const uint2 *)d_draws;
+        a.pair_base = d_pairbase + (size_t)h * N;
+        a.phys_of = d_physof + (size_t)h * N;
+        a.tensor = d_tensor;
+        a.N = N; a.K = K; a.G = G; a.grid_start = pb.grid_start; a.mode = pb.mode;
+        a.bw = pb.binwidth; a.half_bw = pb.binwidth / 2.0;
+        a.slabs = d_slabs; a.n_slabs = (int)slabs.size();
+        a.accepted = d_acc; a.err = d_err;
+        launch_accum_strict(a, st_);
+        launches_ += 1;
+        stx.accum_launches += 1;
+        mark();
+        if (pb.mode == 3) {
+            if (want_raw) { launch_expand_raw(d_tensor, N, K, G, d_raw + (size_t)h * N * K * K * G, st_); launches_++; }
+            launch_project(d_tensor, N, K, G, S, d_tw, d_pairkh, d_results, st_);
+            launches_ += 1;
+            CK(cudaMemsetAsync(d_tensor, 0, tens_elems * sizeof(double), st_));
+        }
+        mark();
+    }
+    CK(cudaEventRecord(ev[3], st_));
+    if (pb.mode == 1) {
+        if (want_raw) { launch_expand_raw(d_tensor, N, K, G, d_raw, st_); launches_++; }
+        launch_project(d_tensor, N, K, G, S, d_tw, d_pairkh, d_results, st_);
+        launches_ += 1;
+    }
+    double *d_rs = d_rs_.as<double>((size_t)N * S * G), *d_ratio = d_ratio_.as<double>((size_t)N * S * S * G);
+    double *d_means = d_means_.as<double>((size_t)S * S * G);
+    if (!d_rs || !d_ratio || !d_means) return FGT_ERR_CUDA;
+    CK(cudaMemcpyAsync(d_means, means, (size_t)S * S * G * sizeof(double), cudaMemcpyHostToDevice, st_));
+    launch_normalise(d_results, N, S, G, pb.num_inds_total > 0 ? pb.num_inds_total : N, d_rs, d_ratio, st_);
+    launch_mean_accum(d_ratio, N, S, G, d_means, st_);
+    launches_ += 2;
+    CK(cudaMemcpyAsync(means, d_means, (size_t)S * S * G * sizeof(double), cudaMemcpyDeviceToHost, st_));
+    stx.h2d_bytes += (int64_t)S * S * G * 8;
+    stx.d2h_bytes += (int64_t)S * S * G * 8;
+    CK(cudaEventRecord(ev[4], st_));
+    int herr[4];
+    unsigned long long hacc[2];
+    CK(cudaMemcpyAsync(herr, d_err, sizeof herr, cudaMemcpyDeviceToHost, st_));
+    CK(cudaMemcpyAsync(hacc, d_acc, sizeof hacc, cudaMemcpyDeviceToHost, st_));
+    if (want_raw) {
+        raw_host_.resize(raw_count_);
+        CK(cudaMemcpyAsync(raw_host_.data(), d_raw, raw_count_ * sizeof(double), cudaMemcpyDeviceToHost, st_));
+    }
+    CK(cudaStreamSynchronize(st_));
+    CK(cudaGetLastError());
+    if (herr[0]) return err_to_code(herr[0]);
+
+    // the stream moves on by two draws per sampled pair of the WHOLE call (all shards), C:136-137
+    store_history(apply_jump(poly_pow_E(2ULL * (uint64_t)all_pairs), h0));
+
+    for (size_t i = 0; i + 3 < tev.size(); i += 4) {
+        float a1 = 0, a2 = 0, a3 = 0;
+        cudaEventElapsedTime(&a1, tev[i], tev[i + 1]);
+        cudaEventElapsedTime(&a2, tev[i + 1], tev[i + 2]);
+        cudaEventElapsedTime(&a3, tev[i + 2], tev[i + 3]);
+        ms_rand += a1; ms_accum += a2; ms_proj += a3;
+    }
+    for (auto e : tev) cudaEventDestroy(e);
+    float tail = 0.f;
+    cudaEventElapsedTime(&stx.ms_chunk, ev[0], ev[1]);
+    cudaEventElapsedTime(&tail, ev[3], ev[4]);
+    cudaEventElapsedTime(&stx.ms_total, ev[0], ev[4]);
+    stx.ms_rand = ms_rand; stx.ms_accum = ms_accum; stx.ms_project = ms_proj + tail;
+    stx.accepted = (int64_t)hacc[0];
+    stx.kernel_launches = launches_;
+    for (auto &e : ev) cudaEventDestroy(e);
+    last_stats = stx;
+    if (stats) *stats = stx;
+    return FGT_OK;
+}
+
+int64_t Engine::get_raw(double *out, int64_t cap) {
+    if (raw_count_ <= 0 || (int64_t)raw_host_.size() < raw_count_) return 0;
+    if (out) {
+        if (cap < raw_count_) return FGT_ERR_ARG;
+        std::memcpy(out, raw_host_.data(), raw_count_ * sizeof(double));
+    }
+    return raw_count_;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NULL-individual curves
+// ---------------------------------------------------------------------------------------------
+int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_rows, double *out, fgt_stats_t *stats) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (pb.ploidy <= 0 || pb.nsamples <= 0 || pb.num_chrom <= 0 || pb.num_inds <= 0 || pb.n_packed_inds <= 0 ||
+        (pb.label_bytes != 2 && pb.label_bytes != 4) || pb.num_bins <= 0 || pb.num_donors <= 0 || !(pb.binwidth > 0))
+        return FGT_ERR_ARG;
+    CK(cudaSetDevice(opt.device));
+    fgt_stats_t stx{};
+    launches_ = 0;
+    cudaEvent_t e0, e1, e2;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
+    CK(cudaEventRecord(e0, st_));
+    const int Nc = std::min(pb.num_inds, 100);                 // reference C:687, C:704-705
+    const int K = pb.num_donors, G = pb.num_bins, P = pb.ploidy;
+    const int n_haps = Nc * P;
+    int *d_err = d_err_.as<int>(4);
+    unsigned long long *d_acc = d_accepted_.as<unsigned long long>(2);
+    CK(cudaMemsetAsync(d_err, 0, 4 * sizeof(int), st_));
+    CK(cudaMemsetAsync(d_acc, 0, 2 * sizeof(unsigned long long), st_));
+    int32_t *d_donor = d_donor_.as<int32_t>(pb.n_donor_labels);
+    if (!d_donor) return FGT_ERR_CUDA;
+    CK(cudaMemcpyAsync(d_donor, pb.donor_label_vec, pb.n_donor_labels * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
+    std::vector<int32_t> rowmap(n_haps);
+    for (int n = 0; n < Nc; n++) {
+        if (rec_rows[n] < 0 || rec_rows[n] >= pb.n_packed_inds) return FGT_ERR_ARG;
+        for (int p = 0; p < P; p++) rowmap[n * P + p] = (rec_rows[n] * P + p) * pb.nsamples + 0;   // first sample only, C:748
+    }
+    int32_t *d_rowmap = d_rowmap_.as<int32_t>(n_haps);
+    if (!d_rowmap) return FGT_ERR_CUDA;
+    CK(cudaMemcpyAsync(d_rowmap, rowmap.data(), n_haps * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
+    double *d_out = d_tensor_.as<double>((size_t)K * K * G);
+    if (!d_out) return FGT_ERR_CUDA;
+    CK(cudaMemcpyAsync(d_out, out, (size_t)K * K * G * sizeof(double), cudaMemcpyHostToDevice, st_));
+    CK(cudaEventRecord(e1, st_));
+    ChromState cs;
+    long long evals = 0;
+    for (int h = 0; h < pb.num_chrom; h++) {
+        rc = prep_chromosome(pb, h, d_rowmap, n_haps, 1, n_haps, true, cs, stx);
+        if (rc) { cs.sorted.release(); cs.yoff.release(); cs.chunk_base.release(); return rc; }
+        if (Nc >= 2) {
+            NullArgs a{};
+            a.chunks = (const Chunk *)cs.sorted.p; a.hap_base = (const int32_t *)cs.chunk_base.p;
+            a.lab_off = (const int32_t *)cs.yoff.p;
+            a.n_inds = Nc; a.ploidy = P; a.K = K; a.G = G; a.grid_start = pb.grid_start;
+            a.bw = pb.binwidth; a.half_bw = pb.binwidth / 2.0; a.out = d_out; a.accepted = d_acc;
+            launch_null_strict(a, st_);
+            launches_ += 1;
+            stx.accum_launches += 1;
+            // evaluated pairs (reference loop count): sum over hap pairs of |A|*|B|
+            std::vector<int32_t> ro(n_haps + 1);
+            CK(cudaMemcpyAsync(ro.data(), cs.chunk_base.p, (n_haps + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st_));
+            CK(cudaStreamSynchronize(st_));
+            std::vector<long long> suffix(Nc + 1, 0);
+            for (int n = Nc - 1; n >= 0; n--) {
+                long long c = 0;
+                for (int p = 0; p < P; p++) c += ro[n * P + p + 1] - ro[n * P + p];
+                suffix[n] = suffix[n + 1] + c;
+            }
+            for (int n = 0; n < Nc - 1; n++) {
+                long long c = 0;
+                for (int p = 0; p < P; p++) c += ro[n * P + p + 1] - ro[n * P + p];
+                evals += c * suffix[n + 1];
+            }
+        }
+    }
+    CK(cudaEventRecord(e2, st_));
+    CK(cudaMemcpyAsync(out, d_out, (size_t)K * K * G * sizeof(double), cudaMemcpyDeviceToHost, st_));
+    int herr[4];
+    unsigned long long hacc[2];
+    CK(cudaMemcpyAsync(herr, d_err, sizeof herr, cudaMemcpyDeviceToHost, st_));
+    CK(cudaMemcpyAsync(hacc, d_acc, sizeof hacc, cudaMemcpyDeviceToHost, st_));
+    CK(cudaStreamSynchronize(st_));
+    CK(cudaGetLastError());
+    cs.sorted.release(); cs.yoff.release(); cs.chunk_base.release();
+    if ((herr[0] & kErrMissingDonor) && Nc >= 2) return FGT_ERR_MISSING_DONOR;
+    stx.pairs = evals;
+    stx.accepted = (int64_t)hacc[0];
+    stx.kernel_launches = launches_;
+    stx.h2d_bytes += (int64_t)K * K * G * 8;
+    stx.d2h_bytes += (int64_t)K * K * G * 8;
+    cudaEventElapsedTime(&stx.ms_chunk, e0, e1);
+    cudaEventElapsedTime(&stx.ms_accum, e1, e2);
+    cudaEventElapsedTime(&stx.ms_total, e0, e2);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    last_stats = stx;
+    if (stats) *stats = stx;
+    return FGT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small self-test entry points
+// ---------------------------------------------------------------------------------------------
+int Engine::rand_fill_host(int32_t *out, int64_t n) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (n <= 0) return FGT_OK;
+    History h0;
+    if (!fetch_history(h0)) return FGT_ERR_RAND;
+    long long nthreads = (n + kRun - 1) / kRun;
+    uint32_t *d = d_draws_.as<uint32_t>((size_t)nthreads * kRun);
+    uint32_t *dh = d_hist_.as<uint32_t>(kLag);
+    if (!d || !dh) return FGT_ERR_CUDA;
+    CK(cudaMemcpyAsync(dh, h0.x, sizeof h0.x, cudaMemcpyHostToDevice, st_));
+    launch_rand_fill(dh, d_level_tab_.as<uint32_t>(level_tab_.size()), d, nthreads, st_);
+    CK(cudaMemcpyAsync(out, d, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st_));
+    CK(cudaStreamSynchronize(st_));
+    CK(cudaGetLastError());
+    store_history(apply_jump(poly_pow_E((uint64_t)n), h0));
+    return FGT_OK;
+}
+
+int Engine::outer_weights(double *tempweights, const double *weights_mat, int S, int K) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (S <= 0 || K <= 0) return FGT_ERR_ARG;
+    CK(cudaSetDevice(opt.device));
+    double *dw = d_rs_.as<double>((size_t)S * K), *dout = d_tw_.as<double>((size_t)S * S * K * K);
+    if (!dw || !dout) return FGT_ERR_CUDA;
+    CK(cudaMemcpyAsync(dw, weights_mat, (size_t)S * K * sizeof(double), cudaMemcpyHostToDevice, st_));
+    launch_outer_weights(dw, S, K, dout, st_);
+    CK(cudaMemcpyAsync(tempweights, dout, (size_t)S * S * K * K * sizeof(double), cudaMemcpyDeviceToHost, st_));
+    CK(cudaStreamSynchronize(st_));
+    CK(cudaGetLastError());
+    return FGT_OK;
+}
+
+int Engine::chunk_one(const void *labels, int label_bytes, int nsites, const double *pos, const double *rate,
+                      double weight_min, double cutoff, const int32_t *donor_label_vec, int n_donor_labels, double *cpos,
+                      double *csize, double *cweight, double *cend, int32_t *cpop) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    fgt_problem_t pb{};
+    fgt_chrom_t c{};
+    c.nsites = nsites; c.pos = pos; c.rate = rate; c.labels = labels; c.labels_on_device = 0;
+    pb.mode = 1; pb.ploidy = 1; pb.nsamples = 1; pb.num_chrom = 1; pb.n_packed_inds = 1; pb.label_bytes = label_bytes;
+    pb.chrom = &c; pb.num_inds = 1; pb.binwidth = 0.1; pb.num_bins = 10; pb.grid_start = 10; pb.num_donors = 1 << 30;
+    pb.donor_label_vec = donor_label_vec; pb.n_donor_labels = n_donor_labels; pb.weight_min = weight_min;
+    pb.gridweight_max_cutoff = cutoff; pb.num_surrogates = 1;
+    int32_t *d_donor = d_donor_.as<int32_t>(n_donor_labels);
+    int *d_err = d_err_.as<int>(4);
+    CK(cudaMemsetAsync(d_err, 0, 4 * sizeof(int), st_));
+    CK(cudaMemcpyAsync(d_donor, donor_label_vec, n_donor_labels * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
+    ChromState cs;
+    fgt_stats_t stx{};
+    rc = prep_chromosome(pb, 0, nullptr, 1, 1, 1, false, cs, stx);
+    if (rc) return rc;
+    int n = (int)cs.n_chunks;
+    std::vector<Chunk> hc(n);
+    int herr[4];
+    CK(cudaMemcpy(hc.data(), cs.sorted.p, n * sizeof(Chunk), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(herr, d_err, sizeof herr, cudaMemcpyDeviceToHost));
+    // one painting: its chunks are position sorted, so the coarse-bin stable sort is the identity
+    std::vector<double> hend(n);
+    CK(cudaMemcpy(hend.data(), d_cend_.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++) {
+        cpos[i] = hc[i].pos; csize[i] = hc[i].size; cweight[i] = hc[i].w; cpop[i] = hc[i].pop; cend[i] = hend[i];
+    }
+    cs.sorted.release(); cs.chunk_base.release(); cs.t.release(); cs.first.release(); cs.yoff.release(); cs.rowoff.release();
+    if (herr[0] & kErrMissingDonor) return FGT_ERR_MISSING_DONOR;
+    return n;
+}
+
+}  // namespace fgt

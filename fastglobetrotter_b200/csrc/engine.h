@@ -1,0 +1,85 @@
+// engine.h -- host orchestration of the device pipeline (internal C++ API behind the C ABI).
+#pragma once
+#include <cstdint>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/fgt_companion.h"
+#include "glibc_rand.h"
+#include "kernels.cuh"
+
+namespace fgt {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    void *get(size_t bytes);   // grow-only; contents undefined after growth
+    void release();
+    template <typename T> T *as(size_t n) { return static_cast<T *>(get(n * sizeof(T))); }
+};
+
+struct ChromState {            // per chromosome device state that must outlive the prep pass
+    DevBuf sorted, chunk_base, t, first, yoff, rowoff;
+    int nb = 0, W = 0;
+    std::vector<long long> totals;   // [n_phys] pairs each packed individual samples on this chromosome
+    long long n_chunks = 0;
+};
+
+struct Options {
+    int device = 0;
+    int strict = 1;
+    int keep_raw = 0;
+    int rand_libc = 1;
+    int slab_bins = 0;      // 0 = automatic
+    int cache = 1;
+    int threads = 0;        // 0 = hardware concurrency
+    int verbose = 0;
+    int reuse_prep = 0;     // one-shot: next packed call may reuse the chunk/bin tables of the previous one
+};
+
+class Engine {
+  public:
+    static Engine &get();
+    Options opt;
+    int set_option(const char *key, double v);
+    double get_option(const char *key);
+    void srand_private(unsigned seed) { private_hist_ = seeded_history(seed); }
+
+    int data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t *stats, int64_t *count_only);
+    int data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_rows, double *out, fgt_stats_t *stats);
+    int64_t get_raw(double *out, int64_t cap);
+    int rand_fill_host(int32_t *out, int64_t n);
+    int outer_weights(double *tempweights, const double *weights_mat, int S, int K);
+    int chunk_one(const void *labels, int label_bytes, int nsites, const double *pos, const double *rate,
+                  double weight_min, double cutoff, const int32_t *donor_label_vec, int n_donor_labels, double *cpos,
+                  double *csize, double *cweight, double *cend, int32_t *cpop);
+    fgt_stats_t last_stats{};
+
+  private:
+    Engine() = default;
+    int ensure_init();
+    bool fetch_history(History &h);          // current stream state (libc-coupled or private)
+    void store_history(const History &h);
+    int prep_chromosome(const fgt_problem_t &pb, int h, const int32_t *rowmap_dev, int rows, int rows_per_ind,
+                        int n_groups, bool for_null, ChromState &cs, fgt_stats_t &stx);
+    std::vector<SlabDesc> make_slabs(int G, int grid_start, double bw, int W, int N) const;
+
+    bool inited_ = false;
+    int init_rc_ = 0;
+    cudaStream_t st_ = nullptr;
+    History private_hist_ = seeded_history(1);
+    std::vector<uint32_t> level_tab_;
+    DevBuf d_level_tab_, d_err_, d_accepted_;
+    // scratch shared by all chromosomes (stream ordered)
+    DevBuf d_labels_, d_cum_, d_inc_, d_counts_, d_rowoff_, d_cstart_, d_cend_, d_chap_, d_cntmat_, d_runfirst_,
+        d_donor_, d_etab_, d_rowmap_;
+    DevBuf d_draws_, d_hist_, d_tensor_, d_results_, d_tw_, d_pairkh_, d_slabs_, d_pairbase_, d_physof_, d_rs_,
+        d_ratio_, d_means_, d_raw_, d_totals_;
+    std::vector<ChromState> chroms_;
+    std::vector<double> raw_host_;
+    int64_t raw_count_ = 0;
+    int launches_ = 0;
+};
+
+}  // namespace fgt

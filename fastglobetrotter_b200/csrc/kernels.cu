@@ -1,0 +1,836 @@
+// kernels.cu -- sm_100a kernels of the coancestry-curve path.
+//
+// Every floating-point operation whose result feeds a value that must match the reference
+// bit-for-bit is written with the round-to-nearest intrinsics (__dadd_rn, __dmul_rn, __ddiv_rn):
+// they are never contracted into FMAs (the reference x86-64 binary has none) and the file is
+// additionally compiled with --fmad=false.
+#include "kernels.cuh"
+#include "glibc_rand.h"
+
+#include <algorithm>
+
+namespace fgt {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+// block-wide exclusive prefix of a per-thread flag (0/1); returns the exclusive prefix and the
+// block total through `total`.  blockDim.x <= 1024, smem: 32 ints.
+__device__ __forceinline__ int block_flag_scan(bool flag, int *warp_tot, int &total) {
+    unsigned m = __ballot_sync(kFull, flag);
+    int lane = lane_id(), w = warp_id(), nw = (blockDim.x + 31) >> 5;
+    int excl = __popc(m & ((1u << lane) - 1));
+    if (lane == 0) warp_tot[w] = __popc(m);
+    __syncthreads();
+    int base = 0, tot = 0;
+    for (int i = 0; i < nw; i++) {
+        int c = warp_tot[i];
+        if (i < w) base += c;
+        tot += c;
+    }
+    __syncthreads();
+    total = tot;
+    return base + excl;
+}
+
+// =============================================================================================
+// 1. Chunk builder: run-length encoding of a painting against the cM prefix of the chromosome.
+//    reference C:446-455 (count), C:487-510 (locate), same code in mode 3 and the NULL path.
+//    Fast path (weight_min < 1): every label change opens a chunk.
+// =============================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) k_chunk_count(const T *__restrict__ labels, const int32_t *__restrict__ rowmap, int L,
+                                                     int rows, int32_t *__restrict__ counts) {
+    __shared__ int wtot[8];
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const T *lab = labels + (size_t)(rowmap ? rowmap[row] : row) * L;
+        int c = 0;
+        for (int j = 1 + threadIdx.x; j < L; j += blockDim.x) c += (lab[j] != lab[j - 1]);
+        c = warp_sum(c);
+        if (lane_id() == 0) wtot[warp_id()] = c;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int s = 1;
+            for (int i = 0; i < (int)(blockDim.x >> 5); i++) s += wtot[i];
+            counts[row] = s;
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_chunk_emit(const T *__restrict__ labels, const int32_t *__restrict__ rowmap, int L,
+                                                    int rows, const int32_t *__restrict__ row_off, const double *__restrict__ cum,
+                                                    const double *__restrict__ inc, double *__restrict__ cstart,
+                                                    double *__restrict__ cend, int32_t *__restrict__ chap) {
+    __shared__ int wtot[32];
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const T *lab = labels + (size_t)(rowmap ? rowmap[row] : row) * L;
+        const int base = row_off[row];
+        if (threadIdx.x == 0) {
+            cstart[base] = 0.0;
+            chap[base] = (int32_t)lab[0];
+            cend[row_off[row + 1] - 1] = cum[L - 1];
+        }
+        int running = 0;
+        for (int t0 = 1; t0 < L; t0 += blockDim.x) {
+            int j = t0 + threadIdx.x;
+            T cur = 0;
+            bool flag = false;
+            if (j < L) { cur = lab[j]; flag = cur != lab[j - 1]; }
+            int tot;
+            int ex = block_flag_scan(flag, wtot, tot);
+            if (flag) {
+                int c = base + running + ex + 1;
+                double cj = cum[j];
+                cstart[c] = cj;
+                chap[c] = (int32_t)cur;
+                cend[c - 1] = __dsub_rn(cj, inc[j]);   // reference C:501: cursor minus the same increment
+            }
+            running += tot;
+        }
+        __syncthreads();
+    }
+}
+
+// General path (weight_min >= 1, never used by the R driver which passes 0, R:52): a label change
+// opens a chunk only if the run that just ended is longer than weight_min SNPs.  One thread per row.
+template <typename T, bool EMIT>
+__global__ void k_chunk_seq(const T *__restrict__ labels, const int32_t *__restrict__ rowmap, int L, int rows, double weight_min,
+                            int32_t *__restrict__ counts, const int32_t *__restrict__ row_off,
+                            const double *__restrict__ cum, const double *__restrict__ inc, double *__restrict__ cstart,
+                            double *__restrict__ cend, int32_t *__restrict__ chap) {
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    const T *lab = labels + (size_t)(rowmap ? rowmap[row] : row) * L;
+    int c = 0, base = EMIT ? row_off[row] : 0;
+    if (EMIT) { cstart[base] = 0.0; chap[base] = (int32_t)lab[0]; }
+    double run = 1;
+    T prev = lab[0];
+    for (int j = 1; j < L; j++) {
+        T cur = lab[j];
+        if (cur == prev) run = run + 1;
+        else {
+            if (run > weight_min) {
+                c++;
+                if (EMIT) {
+                    double cj = cum[j];
+                    cstart[base + c] = cj;
+                    chap[base + c] = (int32_t)cur;
+                    cend[base + c - 1] = __dsub_rn(cj, inc[j]);
+                }
+            }
+            run = 1;
+        }
+        prev = cur;
+    }
+    if (EMIT) cend[base + c] = cum[L - 1];
+    else counts[row] = c + 1;
+}
+
+void launch_chunk_count(const void *labels, const int32_t *rowmap, int label_bytes, int nsites, int rows, double weight_min,
+                        int32_t *counts, cudaStream_t st) {
+    if (weight_min < 1.0) {
+        int grid = rows < 148 * 64 ? rows : 148 * 64;
+        if (label_bytes == 2) k_chunk_count<uint16_t><<<grid, 256, 0, st>>>((const uint16_t *)labels, rowmap, nsites, rows, counts);
+        else k_chunk_count<int32_t><<<grid, 256, 0, st>>>((const int32_t *)labels, rowmap, nsites, rows, counts);
+    } else {
+        int grid = (rows + 127) / 128;
+        if (label_bytes == 2)
+            k_chunk_seq<uint16_t, false><<<grid, 128, 0, st>>>((const uint16_t *)labels, rowmap, nsites, rows, weight_min, counts,
+                                                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+        else
+            k_chunk_seq<int32_t, false><<<grid, 128, 0, st>>>((const int32_t *)labels, rowmap, nsites, rows, weight_min, counts,
+                                                             nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    }
+}
+
+void launch_chunk_emit(const void *labels, const int32_t *rowmap, int label_bytes, int nsites, int rows, double weight_min,
+                       const int32_t *row_off, const double *cum, const double *inc, double *cstart, double *cend,
+                       int32_t *chap, cudaStream_t st) {
+    if (weight_min < 1.0) {
+        int grid = rows < 148 * 64 ? rows : 148 * 64;
+        if (label_bytes == 2)
+            k_chunk_emit<uint16_t><<<grid, 256, 0, st>>>((const uint16_t *)labels, rowmap, nsites, rows, row_off, cum, inc, cstart, cend, chap);
+        else
+            k_chunk_emit<int32_t><<<grid, 256, 0, st>>>((const int32_t *)labels, rowmap, nsites, rows, row_off, cum, inc, cstart, cend, chap);
+    } else {
+        int grid = (rows + 127) / 128;
+        if (label_bytes == 2)
+            k_chunk_seq<uint16_t, true><<<grid, 128, 0, st>>>((const uint16_t *)labels, rowmap, nsites, rows, weight_min, nullptr,
+                                                             row_off, cum, inc, cstart, cend, chap);
+        else
+            k_chunk_seq<int32_t, true><<<grid, 128, 0, st>>>((const int32_t *)labels, rowmap, nsites, rows, weight_min, nullptr,
+                                                            row_off, cum, inc, cstart, cend, chap);
+    }
+}
+
+// exclusive scan of int32 counts -> out[0..n] (single block; n is "rows", at most a few 10^5)
+__global__ void __launch_bounds__(1024) k_exclusive_scan_i32(const int32_t *__restrict__ in, int32_t *__restrict__ out, int n) {
+    __shared__ int wtot[32];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int t0 = 0; t0 < n; t0 += blockDim.x) {
+        int i = t0 + threadIdx.x;
+        int v = i < n ? in[i] : 0;
+        int x = v;   // inclusive warp scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(kFull, x, o);
+            if (lane_id() >= o) x += y;
+        }
+        if (lane_id() == 31) wtot[warp_id()] = x;
+        __syncthreads();
+        int base = carry_s;
+        for (int w = 0; w < warp_id(); w++) base += wtot[w];
+        if (i < n) out[i] = base + x - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry_s = base + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = carry_s;
+}
+
+void launch_exclusive_scan_i32(const int32_t *in, int32_t *out, int n, cudaStream_t st) {
+    k_exclusive_scan_i32<<<1, 1024, 0, st>>>(in, out, n);
+}
+
+// =============================================================================================
+// 2. Per-individual coarse binning (reference C:57-111): finish the chunk records, stable-sort
+//    them by 1-cM bin, and tabulate how many pairs every (j,k) bin pair will sample
+//    (reference C:121-131 / C:1128-1140) so that rand() stream offsets are a prefix sum.
+//    One CTA per packed individual.
+// =============================================================================================
+__device__ __forceinline__ int pairs_to_sample(int t1, int t2, double e, double divisor) {
+    // Y_i = (int) t_1*t_2*exp(-0.05*(k-j))/divisor ; if (t_1>0 && t_2>0 && Y_i==0) Y_i=1
+    int prod = (int)((unsigned)t1 * (unsigned)t2);
+    double y = __ddiv_rn(__dmul_rn((double)prod, e), divisor);
+    int Y = __double2int_rz(y);
+    if (t1 > 0 && t2 > 0 && Y == 0) Y = 1;
+    return Y < 0 ? 0 : Y;
+}
+
+__global__ void __launch_bounds__(256)
+k_bin_sort(int rows_per_ind, const int32_t *__restrict__ row_off, const double *__restrict__ cstart,
+           const double *__restrict__ cend, const int32_t *__restrict__ chap, const int32_t *__restrict__ donor_label,
+           int n_donor_labels, double cutoff, int K, int mode, int nb, int W, const double *__restrict__ Etab,
+           double divisor, Chunk *__restrict__ sorted, int32_t *__restrict__ chunk_base, int32_t *__restrict__ t_out,
+           int32_t *__restrict__ first_out, int32_t *__restrict__ yoff, long long *__restrict__ rowoff,
+           int32_t *__restrict__ cntmat, int32_t *__restrict__ runfirst, int *__restrict__ err) {
+    const int p = blockIdx.x;
+    const int r0 = p * rows_per_ind;
+    const int c0 = row_off[r0];
+    int32_t *cnt = cntmat + (size_t)p * rows_per_ind * nb;      // zero on entry
+    int32_t *rf = runfirst + (size_t)p * rows_per_ind * nb;
+    int32_t *t = t_out + (size_t)p * nb;
+    int32_t *first = first_out + (size_t)p * nb;
+    if (threadIdx.x == 0) {
+        chunk_base[p] = c0;
+        if (p == gridDim.x - 1) chunk_base[p + 1] = row_off[r0 + rows_per_ind];
+    }
+    // phase 1: occupancy of (painting, coarse bin); first chunk of each run
+    for (int r = 0; r < rows_per_ind; r++) {
+        const int a = row_off[r0 + r], b = row_off[r0 + r + 1];
+        for (int i = a + threadIdx.x; i < b; i += blockDim.x) {
+            double pos = __dmul_rn(__dadd_rn(cstart[i], cend[i]), 0.5);
+            int bin = __double2int_rz(pos);
+            bin = bin < 0 ? 0 : (bin >= nb ? nb - 1 : bin);
+            atomicAdd(&cnt[r * nb + bin], 1);
+            bool is_first = (i == a);
+            if (!is_first) {
+                double pp = __dmul_rn(__dadd_rn(cstart[i - 1], cend[i - 1]), 0.5);
+                int pb = __double2int_rz(pp);
+                pb = pb < 0 ? 0 : (pb >= nb ? nb - 1 : pb);
+                is_first = pb != bin;
+            }
+            if (is_first) rf[r * nb + bin] = i;
+        }
+    }
+    __syncthreads();
+    // phase 2: per bin, turn the per-painting counts into exclusive prefixes; t[bin] = total
+    for (int bin = threadIdx.x; bin < nb; bin += blockDim.x) {
+        int s = 0;
+        for (int r = 0; r < rows_per_ind; r++) {
+            int c = cnt[r * nb + bin];
+            cnt[r * nb + bin] = s;
+            s += c;
+        }
+        t[bin] = s;
+    }
+    __syncthreads();
+    // phase 3: start_bin
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int bin = 0; bin < nb; bin++) { first[bin] = s; s += t[bin]; }
+    }
+    __syncthreads();
+    // phase 4: stable placement + finished records
+    int bad = 0;
+    for (int r = 0; r < rows_per_ind; r++) {
+        const int a = row_off[r0 + r], b = row_off[r0 + r + 1];
+        for (int i = a + threadIdx.x; i < b; i += blockDim.x) {
+            double s = cstart[i], e = cend[i];
+            double pos = __dmul_rn(__dadd_rn(s, e), 0.5);
+            int bin = __double2int_rz(pos);
+            bin = bin < 0 ? 0 : (bin >= nb ? nb - 1 : bin);
+            int dest = c0 + first[bin] + cnt[r * nb + bin] + (i - rf[r * nb + bin]);
+            double len = __dsub_rn(e, s);
+            int hap = chap[i];
+            int pop = (hap >= 1 && hap <= n_donor_labels) ? donor_label[hap - 1] : -9;
+            if (pop == -9) bad |= kErrMissingDonor;                 // reference C:517-522
+            if (mode == 1 && pop > K) bad |= kErrLabelRange;        // reference C:102-107
+            if (mode == 3 && (pop > K)) bad |= kErrLabelRange;      // (would index out of bounds in the reference)
+            Chunk c;
+            c.pos = pos; c.size = len; c.w = (len > cutoff) ? cutoff : len; c.pop = pop; c.hapid = hap;
+            sorted[dest] = c;
+        }
+    }
+    if (bad) atomicOr(err, bad);
+    // phase 5: pairs per row of the (j,k) sampling schedule
+    for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+        int32_t *yo = yoff + ((size_t)p * nb + j) * W;
+        int t1 = t[j];
+        int acc = 0;
+        yo[0] = 0;
+        for (int d = 1; d < W; d++) {
+            int k = j + d;
+            if (j < nb - 1 && k < nb) acc += pairs_to_sample(t1, t[k], Etab[d], divisor);
+            yo[d] = acc;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long s = 0;
+        long long *ro = rowoff + (size_t)p * (nb + 1);
+        for (int j = 0; j < nb; j++) { ro[j] = s; s += yoff[((size_t)p * nb + j) * W + (W - 1)]; }
+        ro[nb] = s;
+    }
+}
+
+void launch_bin_sort(int n_phys, int rows_per_ind, const int32_t *row_off, const double *cstart, const double *cend,
+                     const int32_t *chap, const int32_t *donor_label, int n_donor_labels, double cutoff, int K, int mode,
+                     int nb, int W, const double *Etab, double divisor, Chunk *sorted, int32_t *chunk_base, int32_t *t,
+                     int32_t *first, int32_t *yoff, long long *rowoff, int32_t *cntmat, int32_t *runfirst, int *err,
+                     cudaStream_t st) {
+    k_bin_sort<<<n_phys, 256, 0, st>>>(rows_per_ind, row_off, cstart, cend, chap, donor_label, n_donor_labels, cutoff, K,
+                                      mode, nb, W, Etab, divisor, sorted, chunk_base, t, first, yoff, rowoff, cntmat,
+                                      runfirst, err);
+}
+
+// =============================================================================================
+// 3. glibc rand() stream, generated in bulk.  Thread t produces draws [t*kRun, (t+1)*kRun) of the
+//    buffer; its start state is the buffer's base history advanced by the base-256 digits of t
+//    (level tables from glibc_rand.h).  x[n] = x[n-31] + x[n-3]; output x[n] >> 1.
+// =============================================================================================
+__device__ __forceinline__ void block_apply_level(uint32_t *y /*smem[61]*/, const uint32_t *__restrict__ tab, int level,
+                                                  int digit) {
+    // y[0..30] holds a history; replace it by the history `digit * kRun * 256^level` draws later
+    if (threadIdx.x == 0)
+        for (int m = 0; m < kLag - 1; m++) y[kLag + m] = y[m] + y[m + kTap];
+    __syncthreads();
+    uint32_t s = 0;
+    if (threadIdx.x < kLag) {
+        for (int i = 0; i < kLag; i++) s += tab[((size_t)level * kLag + i) * 256 + digit] * y[i + threadIdx.x];
+    }
+    __syncthreads();
+    if (threadIdx.x < kLag) y[threadIdx.x] = s;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+k_rand_fill(const uint32_t *__restrict__ base_hist, const uint32_t *__restrict__ tab, uint32_t *__restrict__ out,
+            long long n_threads) {
+    __shared__ uint32_t y[2 * kLag - 1];
+    if (threadIdx.x < kLag) y[threadIdx.x] = base_hist[threadIdx.x];
+    __syncthreads();
+    unsigned long long blk = blockIdx.x;
+#pragma unroll 1
+    for (int lv = 1; lv < kLevels; lv++) {
+        int digit = (int)((blk >> (8 * (lv - 1))) & 255);
+        if (digit) block_apply_level(y, tab, lv, digit);
+    }
+    if (threadIdx.x == 0)
+        for (int m = 0; m < kLag - 1; m++) y[kLag + m] = y[m] + y[m + kTap];
+    __syncthreads();
+    long long tglob = (long long)blk * 256 + threadIdx.x;
+    if (tglob >= n_threads) return;
+    uint32_t yy[2 * kLag - 1];
+#pragma unroll
+    for (int i = 0; i < 2 * kLag - 1; i++) yy[i] = y[i];
+    uint32_t s[kLag];
+#pragma unroll
+    for (int j = 0; j < kLag; j++) s[j] = 0;
+#pragma unroll
+    for (int i = 0; i < kLag; i++) {
+        uint32_t c = tab[(size_t)i * 256 + threadIdx.x];     // level 0, digit = threadIdx.x
+#pragma unroll
+        for (int j = 0; j < kLag; j++) s[j] += c * yy[i + j];
+    }
+    uint4 *dst = reinterpret_cast<uint4 *>(out + tglob * (long long)kRun);
+#pragma unroll 1
+    for (int it = 0; it < kRun / (4 * kLag); it++) {
+#pragma unroll
+        for (int v = 0; v < kLag; v++) {          // 31 x 4 draws: the rotating index returns to 0
+            uint32_t o[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int i = (4 * v + r) % kLag;
+                s[i] += s[(i + kTap) % kLag];
+                o[r] = s[i] >> 1;
+            }
+            dst[v] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        dst += kLag;
+    }
+}
+
+void launch_rand_fill(const uint32_t *base_hist, const uint32_t *level_tab, uint32_t *out, long long n_threads,
+                      cudaStream_t st) {
+    if (n_threads <= 0) return;
+    long long blocks = (n_threads + 255) / 256;
+    k_rand_fill<<<(unsigned)blocks, 256, 0, st>>>(base_hist, level_tab, out, n_threads);
+}
+
+// =============================================================================================
+// 4. Sampled pair accumulation, strict (order-preserving) mode.
+//    reference tabulate_chunks C:121-168 / tabulate_chunks_mode3 C:1128-1177.
+//
+//    One warp owns one (pseudo-individual, slab of fine bins) and is the ONLY writer of those
+//    cells, so it may fold updates in the reference's order without atomics: it walks the
+//    sampling schedule (j ascending, k ascending, draw ascending) restricted to the coarse
+//    separations that can land in its slab, evaluates 32 consecutive sampled pairs per step,
+//    and commits them in lane order; lanes that hit the same cell are chained through
+//    shuffles so the additions happen in sequence order.
+// =============================================================================================
+__device__ __forceinline__ int tri_row(int lo, int hi, int K) { return lo * K - ((lo * (lo - 1)) >> 1) + (hi - lo); }
+
+__global__ void __launch_bounds__(128) k_accum_strict(const AccumArgs a) {
+    const int lane = lane_id();
+    const int task = blockIdx.x * (blockDim.x >> 5) + warp_id();
+    if (task >= a.N * a.n_slabs) return;
+    const int slab_i = task / a.N;      // slab-major: the heavy (small separation) slabs start first
+    const int n = task - slab_i * a.N;
+    const SlabDesc sl = a.slabs[slab_i];
+    const int phys = a.phys_of[n];
+    const ChromPrep &cp = a.cp;
+    const int nb = cp.nb, W = cp.W;
+    const int32_t *T = cp.t + (size_t)phys * nb;
+    const int32_t *F = cp.first + (size_t)phys * nb;
+    const long long *RO = cp.rowoff + (size_t)phys * (nb + 1);
+    const Chunk *ch = cp.chunks + cp.chunk_base[phys];
+    const uint2 *dr = a.draws + a.pair_base[n];
+    const int G = a.G, K = a.K;
+    double *tens = a.tensor + (size_t)n * ((size_t)K * (K + 1) / 2) * G;
+    const double bw = a.bw, half_bw = a.half_bw;
+    unsigned long long n_acc = 0;
+    int bad = 0;
+
+    for (int j = 0; j < nb - 1; j++) {
+        const int t1 = T[j];
+        if (t1 <= 0) continue;
+        int dmax = W - 1;
+        if (nb - 1 - j < dmax) dmax = nb - 1 - j;
+        const int dlo = sl.dlo, dhi = sl.dhi < dmax ? sl.dhi : dmax;
+        if (dlo > dhi) continue;
+        const int32_t *yo = cp.yoff + ((size_t)phys * nb + j) * W;
+        const int o_lo = yo[dlo - 1], o_hi = yo[dhi];
+        const int R = o_hi - o_lo;
+        if (R <= 0) continue;
+        const uint2 *drow = dr + RO[j] + o_lo;
+        const int f1 = F[j];
+        for (int base = 0; base < R; base += 32) {
+            const int q = base + lane;
+            bool valid = q < R;
+            int cell = -1;
+            double val = 0.0;
+            if (valid) {
+                // which separation does draw q belong to: smallest d with q + o_lo < yo[d]
+                int lo = dlo, hi = dhi;
+                const int target = q + o_lo;
+                while (lo < hi) {
+                    int mid = (lo + hi) >> 1;
+                    if (target < yo[mid]) hi = mid; else lo = mid + 1;
+                }
+                const int k = j + lo;
+                const int t2 = T[k];
+                const uint2 r = drow[q];
+                const int c1 = f1 + (int)(r.x % (unsigned)t1);
+                const int c2 = F[k] + (int)(r.y % (unsigned)t2);
+                const Chunk A = ch[c1], B = ch[c2];
+                bool live = true;
+                if (a.mode == 1) live = (A.pop != 0) && (B.pop != 0);          // reference C:138-142
+                else if (A.pop == 0 || B.pop == 0) { bad |= kErrMode3Target; live = false; }
+                if (live) {
+                    const double d = fabs(__dsub_rn(A.pos, B.pos));             // pow(pow(x,2),0.5), reference C:143
+                    const double qd = __ddiv_rn(d, bw);
+                    const double fl = floor(qd);
+                    const double frac = __dmul_rn(__dsub_rn(qd, fl), bw);       // reference C:144-145
+                    int bfull = __double2int_rz(fl);
+                    bool ok = true;
+                    if (frac <= half_bw) { /* floor */ }
+                    else if (frac > half_bw) bfull += 1;
+                    else ok = false;                                             // NaN: the reference keeps a stale bin
+                    const double mind = __dadd_rn(__dmul_rn(A.size, 0.5), __dmul_rn(B.size, 0.5));
+                    if (ok && bfull >= sl.b0 && bfull <= sl.b1 && d >= mind) {
+                        const int l1 = A.pop - 1, l2 = B.pop - 1;
+                        const int lo_l = l1 < l2 ? l1 : l2, hi_l = l1 < l2 ? l2 : l1;
+                        cell = tri_row(lo_l, hi_l, K) * G + (bfull - a.grid_start);
+                        val = __dmul_rn(A.w, B.w);
+                    }
+                }
+            }
+            // ---- ordered commit -------------------------------------------------------------
+            const unsigned key = cell >= 0 ? (unsigned)cell : (0x80000000u | (unsigned)lane);
+            const unsigned grp = __match_any_sync(kFull, key);
+            const bool leader = (cell >= 0) && ((grp & ((1u << lane) - 1)) == 0);
+            double acc = 0.0;
+            if (leader) acc = tens[cell];
+            unsigned rest = leader ? (grp & ~(1u << lane)) : 0u;
+            acc = __dadd_rn(acc, val);
+            while (__any_sync(kFull, rest != 0)) {
+                const int src = rest ? (__ffs(rest) - 1) : lane;
+                const double v = __shfl_sync(kFull, val, src);
+                if (rest) { acc = __dadd_rn(acc, v); rest &= rest - 1; }
+            }
+            if (leader) tens[cell] = acc;
+            n_acc += (cell >= 0);
+            __syncwarp();
+        }
+    }
+    n_acc = warp_sum_u64(n_acc);
+    if (lane == 0 && n_acc) atomicAdd(a.accepted, n_acc);
+    if (bad) atomicOr(a.err, bad);
+}
+
+void launch_accum_strict(const AccumArgs &a, cudaStream_t st) {
+    long long tasks = (long long)a.N * a.n_slabs;
+    if (tasks <= 0) return;
+    const int wpb = 4;
+    unsigned grid = (unsigned)((tasks + wpb - 1) / wpb);
+    k_accum_strict<<<grid, wpb * 32, 0, st>>>(a);
+}
+
+void launch_accum_relaxed(const AccumArgs &, long long, const long long *, cudaStream_t) {}
+
+// =============================================================================================
+// 5. Projection onto surrogate pairs (reference C:578-595, mode 3: C:1190-1203):
+//    results[n][mn][i] += sum over upper-triangle rows (k<=h, in that order) of
+//    temp_weights[(K*k+h)*S*S + mn] * counts[n][(k,h)][i]; multiply and add rounded separately,
+//    summed in the reference's order, so the result is bit-identical.
+// =============================================================================================
+constexpr int PT = 64, PKK = 16;
+__global__ void __launch_bounds__(256)
+k_project(const double *__restrict__ tensor, int K, int G, int S, const double *__restrict__ tw,
+          const int32_t *__restrict__ pair_kh, double *__restrict__ results) {
+    const int n = blockIdx.z;
+    const int SS = S * S, P = K * (K + 1) / 2;
+    const int i0 = blockIdx.x * PT, m0 = blockIdx.y * PT;
+    const double *B = tensor + (size_t)n * P * G;
+    double *out = results + (size_t)n * SS * G;
+    __shared__ double sA[PKK][PT + 1];   // [pair][mn]
+    __shared__ double sB[PKK][PT + 1];   // [pair][i]
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double acc[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            int mn = m0 + ty + 16 * u, i = i0 + tx + 16 * v;
+            acc[u][v] = (mn < SS && i < G) ? out[(size_t)mn * G + i] : 0.0;
+        }
+    for (int p0 = 0; p0 < P; p0 += PKK) {
+        for (int e = threadIdx.x; e < PKK * PT; e += 256) {
+            int pr = e / PT, c = e % PT;
+            int p = p0 + pr;
+            double va = 0.0, vb = 0.0;
+            if (p < P) {
+                if (m0 + c < SS) va = tw[(size_t)pair_kh[p] * SS + m0 + c];
+                if (i0 + c < G) vb = B[(size_t)p * G + i0 + c];
+            }
+            sA[pr][c] = va;
+            sB[pr][c] = vb;
+        }
+        __syncthreads();
+        const int lim = (P - p0) < PKK ? (P - p0) : PKK;
+        for (int pr = 0; pr < lim; pr++) {
+            double av[4], bv[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) av[u] = sA[pr][ty + 16 * u];
+#pragma unroll
+            for (int v = 0; v < 4; v++) bv[v] = sB[pr][tx + 16 * v];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+                for (int v = 0; v < 4; v++) acc[u][v] = __dadd_rn(acc[u][v], __dmul_rn(av[u], bv[v]));
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            int mn = m0 + ty + 16 * u, i = i0 + tx + 16 * v;
+            if (mn < SS && i < G) out[(size_t)mn * G + i] = acc[u][v];
+        }
+}
+
+void launch_project(const double *tensor, int N, int K, int G, int S, const double *tw, const int32_t *pair_kh,
+                    double *results, cudaStream_t st) {
+    if (N <= 0) return;
+    dim3 grid((G + PT - 1) / PT, (S * S + PT - 1) / PT, N);
+    k_project<<<grid, 256, 0, st>>>(tensor, K, G, S, tw, pair_kh, results);
+}
+
+// =============================================================================================
+// 6. Symmetrise, divide by expectation (reference C:603-648), then mean over individuals in
+//    individual order.
+// =============================================================================================
+__global__ void __launch_bounds__(128)
+k_normalise(const double *__restrict__ results, int N, int S, int G, int N_total, double *__restrict__ rsbuf,
+            double *__restrict__ ratio) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = blockIdx.y;
+    if (i >= G) return;
+    const double *R = results + (size_t)n * S * S * G + i;
+    double *rs = rsbuf + (size_t)n * S * G + i;
+    double *out = ratio + (size_t)n * S * S * G + i;
+    double tot = 0.0;
+    for (int k = 0; k < S; k++) {
+        double s = 0.0;
+        for (int h = 0; h < S; h++) {
+            // symmetrised entry: for k<=h the reference forms (R[k,h]+R[h,k])/2 and mirrors it (C:610-615)
+            int a = k <= h ? k : h, b = k <= h ? h : k;
+            double sym = __dmul_rn(__dadd_rn(R[(size_t)(a * S + b) * G], R[(size_t)(b * S + a) * G]), 0.5);
+            s = __dadd_rn(s, sym);
+        }
+        rs[(size_t)k * G] = s;
+        tot = __dadd_rn(tot, s);
+    }
+    const double dN = (double)N_total;
+    for (int k = 0; k < S; k++)
+        for (int h = 0; h < S; h++) {
+            int a = k <= h ? k : h, b = k <= h ? h : k;
+            double sym = __dmul_rn(__dadd_rn(R[(size_t)(a * S + b) * G], R[(size_t)(b * S + a) * G]), 0.5);
+            double e_ab = __ddiv_rn(__dmul_rn(rs[(size_t)a * G], rs[(size_t)b * G]), tot);
+            double e_ba = __ddiv_rn(__dmul_rn(rs[(size_t)b * G], rs[(size_t)a * G]), tot);
+            double ex = __dmul_rn(__dadd_rn(e_ab, e_ba), 0.5);                       // C:628-638
+            out[(size_t)(k * S + h) * G] = __ddiv_rn(__ddiv_rn(sym, ex), dN);        // C:644
+        }
+}
+
+__global__ void __launch_bounds__(128)
+k_mean_accum(const double *__restrict__ ratio, int N, int SS, int G, double *__restrict__ means) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int kh = blockIdx.y;
+    if (i >= G) return;
+    double m = means[(size_t)kh * G + i];
+    for (int n = 0; n < N; n++) m = __dadd_rn(m, ratio[((size_t)n * SS + kh) * G + i]);
+    means[(size_t)kh * G + i] = m;
+}
+
+void launch_normalise(double *results, int N, int S, int G, int N_total, double *rsbuf, double *ratio, cudaStream_t st) {
+    if (N <= 0) return;
+    dim3 grid((G + 127) / 128, N);
+    k_normalise<<<grid, 128, 0, st>>>(results, N, S, G, N_total, rsbuf, ratio);
+}
+
+void launch_mean_accum(const double *ratio, int N, int S, int G, double *means, cudaStream_t st) {
+    dim3 grid((G + 127) / 128, S * S);
+    k_mean_accum<<<grid, 128, 0, st>>>(ratio, N, S * S, G, means);
+}
+
+// reference mutiply_temp_weight C:15-23: out[(m*S+n)*K*K + k*K + l] = w[k*S+m] * w[l*S+n]
+__global__ void __launch_bounds__(256) k_outer_weights(const double *__restrict__ w, int S, int K, double *__restrict__ out) {
+    const size_t KK = (size_t)K * K;
+    const size_t total = (size_t)S * S * KK;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int mn = (int)(idx / KK), kl = (int)(idx % KK);
+        const int m = mn / S, n = mn % S, k = kl / K, l = kl % K;
+        out[idx] = __dmul_rn(w[(size_t)k * S + m], w[(size_t)l * S + n]);
+    }
+}
+
+void launch_outer_weights(const double *w, int S, int K, double *out, cudaStream_t st) {
+    size_t total = (size_t)S * S * K * K;
+    unsigned grid = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
+    k_outer_weights<<<grid ? grid : 1, 256, 0, st>>>(w, S, K, out);
+}
+
+// upper-triangle tensor -> the reference's full [K*K][G] layout (lower triangle stays zero)
+__global__ void k_expand_raw(const double *__restrict__ tensor, int K, int G, double *__restrict__ out) {
+    const int n = blockIdx.z, lo = blockIdx.y / K, hi = blockIdx.y % K;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G) return;
+    const int P = K * (K + 1) / 2;
+    double v = 0.0;
+    if (lo <= hi) v = tensor[((size_t)n * P + tri_row(lo, hi, K)) * G + i];
+    out[((size_t)n * K * K + (size_t)lo * K + hi) * G + i] = v;
+}
+
+void launch_expand_raw(const double *tensor, int N, int K, int G, double *out_full, cudaStream_t st) {
+    if (N <= 0) return;
+    dim3 grid((G + 127) / 128, K * K, N);
+    k_expand_raw<<<grid, 128, 0, st>>>(tensor, K, G, out_full);
+}
+
+// =============================================================================================
+// 7. NULL-individual curves (reference C:916-1042): exhaustive chunk x chunk between haplotypes
+//    of different individuals, full K x K x G tensor, one global sequential fold.
+//    Strict mode: one warp owns one (label of A, label of B) pair = G cells held in shared
+//    memory; it enumerates, in the reference's order, only the chunk pairs with those labels
+//    (haplotype chunks are pre-grouped by label, stably), 32 candidates per step.
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+k_null_group(const int32_t *__restrict__ row_off, const double *__restrict__ cstart, const double *__restrict__ cend,
+             const int32_t *__restrict__ chap, const int32_t *__restrict__ donor_label, int n_donor_labels,
+             double cutoff, int K, Chunk *__restrict__ grouped, int32_t *__restrict__ lab_off, int *__restrict__ err) {
+    // one CTA per haplotype; stable counting sort of its chunks by label (labels 1..K; label 0 and
+    // out-of-range labels are dropped: they never contribute, reference C:1020)
+    extern __shared__ int32_t sm[];       // [K+1] counts -> offsets
+    const int hap = blockIdx.x;
+    const int a = row_off[hap], b = row_off[hap + 1];
+    int32_t *off = lab_off + (size_t)hap * (K + 2);
+    for (int l = threadIdx.x; l <= K + 1; l += blockDim.x) sm[l] = 0;
+    __syncthreads();
+    int bad = 0;
+    for (int i = a + threadIdx.x; i < b; i += blockDim.x) {
+        int h = chap[i];
+        int pop = (h >= 1 && h <= n_donor_labels) ? donor_label[h - 1] : -9;
+        if (pop == -9) bad |= kErrMissingDonor;
+        if (pop >= 1 && pop <= K) atomicAdd(&sm[pop], 1);
+    }
+    if (bad) atomicOr(err, bad);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int l = 1; l <= K; l++) { int c = sm[l]; sm[l] = s; off[l - 1] = s; s += c; }
+        off[K] = s;
+        off[K + 1] = b - a;
+    }
+    __syncthreads();
+    // stable placement: chunk i goes after all earlier chunks with the same label.  Chunks per
+    // haplotype are few hundred..tens of thousands: rank by a block-wide pass per tile.
+    for (int t0 = a; t0 < b; t0 += blockDim.x) {
+        int i = t0 + threadIdx.x;
+        int pop = 0;
+        if (i < b) {
+            int h = chap[i];
+            pop = (h >= 1 && h <= n_donor_labels) ? donor_label[h - 1] : -9;
+            if (pop < 1 || pop > K) pop = 0;
+        }
+        // rank among same-label lanes in this tile, in thread order
+        unsigned peers = __match_any_sync(kFull, pop);
+        int rank_in_warp = __popc(peers & ((1u << lane_id()) - 1));
+        int cnt_in_warp = __popc(peers);
+        // serialise warps of the tile: warp w adds after warps < w
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) {
+            if (warp_id() == w && pop > 0) {
+                int basep = sm[pop];
+                if (i < b) {
+                    double s = cstart[i], e = cend[i];
+                    double len = __dsub_rn(e, s);
+                    Chunk c;
+                    c.pos = __dmul_rn(__dadd_rn(s, e), 0.5); c.size = len; c.w = (len > cutoff) ? cutoff : len;
+                    c.pop = pop; c.hapid = chap[i];
+                    grouped[a + basep + rank_in_warp] = c;
+                }
+                __syncwarp(peers);
+                if (rank_in_warp == 0) sm[pop] = basep + cnt_in_warp;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+void launch_null_group(int n_haps, const int32_t *row_off, const double *cstart, const double *cend, const int32_t *chap,
+                       const int32_t *donor_label, int n_donor_labels, double cutoff, int K, Chunk *grouped,
+                       int32_t *lab_off, int *err, cudaStream_t st) {
+    k_null_group<<<n_haps, 256, (K + 2) * sizeof(int32_t), st>>>(row_off, cstart, cend, chap, donor_label, n_donor_labels,
+                                                                cutoff, K, grouped, lab_off, err);
+}
+
+__global__ void __launch_bounds__(32) k_null_strict(const NullArgs a) {
+    extern __shared__ double tile[];      // [G]
+    const int lane = lane_id();
+    const int K = a.K, G = a.G;
+    const int lA = blockIdx.x / K, lB = blockIdx.x % K;   // 0-based labels
+    double *gout = a.out + ((size_t)lA * K + lB) * G;
+    for (int i = lane; i < G; i += 32) tile[i] = gout[i];
+    __syncwarp();
+    const int P = a.ploidy, NH = a.n_inds * P;
+    const double bw = a.bw, half_bw = a.half_bw;
+    unsigned long long n_acc = 0;
+    for (int hA = 0; hA < (a.n_inds - 1) * P; hA++) {
+        const int nA = hA / P;
+        const int32_t *oA = a.lab_off + (size_t)hA * (K + 2);
+        const int a0 = oA[lA], cntA = oA[lA + 1] - a0;
+        if (cntA == 0) continue;
+        const Chunk *CA = a.chunks + a.hap_base[hA] + a0;
+        for (int hB = (nA + 1) * P; hB < NH; hB++) {
+            const int32_t *oB = a.lab_off + (size_t)hB * (K + 2);
+            const int b0 = oB[lB], cntB = oB[lB + 1] - b0;
+            if (cntB == 0) continue;
+            const Chunk *CB = a.chunks + a.hap_base[hB] + b0;
+            const int tot = cntA * cntB;
+            for (int base = 0; base < tot; base += 32) {
+                const int q = base + lane;
+                int cell = -1;
+                double val = 0.0;
+                if (q < tot) {
+                    const int ia = q / cntB, jb = q - ia * cntB;
+                    const Chunk A = CA[ia], B = CB[jb];
+                    const double d = fabs(__dsub_rn(A.pos, B.pos));
+                    const double qd = __ddiv_rn(d, bw);
+                    const double fl = floor(qd);
+                    const double frac = __dmul_rn(__dsub_rn(qd, fl), bw);
+                    int bfull = __double2int_rz(fl);
+                    bool ok = true;
+                    if (frac <= half_bw) {}
+                    else if (frac > half_bw) bfull += 1;
+                    else ok = false;
+                    const int bb = bfull - a.grid_start;
+                    const double mind = __dadd_rn(__dmul_rn(A.size, 0.5), __dmul_rn(B.size, 0.5));
+                    if (ok && bb >= 0 && bb < G && d >= mind) { cell = bb; val = __dmul_rn(A.w, B.w); }
+                }
+                const unsigned key = cell >= 0 ? (unsigned)cell : (0x80000000u | (unsigned)lane);
+                const unsigned grp = __match_any_sync(kFull, key);
+                const bool leader = (cell >= 0) && ((grp & ((1u << lane) - 1)) == 0);
+                double acc = leader ? tile[cell] : 0.0;
+                unsigned rest = leader ? (grp & ~(1u << lane)) : 0u;
+                acc = __dadd_rn(acc, val);
+                while (__any_sync(kFull, rest != 0)) {
+                    const int src = rest ? (__ffs(rest) - 1) : lane;
+                    const double v = __shfl_sync(kFull, val, src);
+                    if (rest) { acc = __dadd_rn(acc, v); rest &= rest - 1; }
+                }
+                if (leader) tile[cell] = acc;
+                n_acc += (cell >= 0);
+                __syncwarp();
+            }
+        }
+    }
+    for (int i = lane; i < G; i += 32) gout[i] = tile[i];
+    n_acc = warp_sum_u64(n_acc);
+    if (lane == 0 && n_acc) atomicAdd(a.accepted, n_acc);
+}
+
+void launch_null_strict(const NullArgs &a, cudaStream_t st) {
+    k_null_strict<<<a.K * a.K, 32, a.G * sizeof(double), st>>>(a);
+}
+
+}  // namespace fgt

@@ -1,0 +1,90 @@
+// kernels.cuh -- device data layouts and launch wrappers of the coancestry-curve path.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace fgt {
+
+// One chunk of a painting after run-length encoding (reference C:514-527), 32 bytes = one
+// L2 sector so that a random gather of a chunk costs exactly one sector.
+struct __align__(32) Chunk {
+    double pos;     // (start+end)/2 in cM
+    double size;    // end-start (grid_size)
+    double w;       // min(size, gridweightMAX_cutoff)
+    int32_t pop;    // donor population label (0 = target population)
+    int32_t hapid;  // donor haplotype id (kept for debugging / NULL path grouping)
+};
+
+// error bits raised by kernels (mapped to FGT_ERR_* on the host)
+enum : int { kErrMissingDonor = 1, kErrLabelRange = 2, kErrMode3Target = 4, kErrInternal = 8 };
+
+struct SlabDesc {   // one accumulation task column: a contiguous range of fine bins
+    int32_t b0, b1; // owned fine bins [b0, b1] on the FULL grid (before subtracting grid_start)
+    int32_t dlo, dhi; // coarse-bin separations (k-j) that can produce those bins (superset)
+};
+
+struct ChromPrep {  // per chromosome, per call: everything the accumulation kernel reads
+    int32_t nb;             // coarse (1 cM) bins = (int)chr_length + 1   (reference C:67-68)
+    int32_t W;              // window_size (reference C:117 / C:1125)
+    int32_t n_phys;         // packed individuals
+    const Chunk *chunks;    // coarse-bin-sorted chunks of all individuals
+    const int32_t *chunk_base; // [n_phys+1] first chunk of each individual
+    const int32_t *t;       // [n_phys][nb] chunks per coarse bin          (numchunckinbin)
+    const int32_t *first;   // [n_phys][nb] exclusive prefix of t          (start_bin)
+    const int32_t *yoff;    // [n_phys][nb][W]: yoff[..][d] = sum_{delta=1..d} Y(j, j+delta)
+    const long long *rowoff; // [n_phys][nb+1] exclusive prefix over j of the row totals
+};
+
+struct AccumArgs {
+    ChromPrep cp;
+    const uint2 *draws;         // draws[p] = the two rand() outputs of sampled pair p (buffer-relative)
+    const long long *pair_base; // [N] first pair (buffer-relative) of pseudo-individual n on this chromosome
+    const int32_t *phys_of;     // [N] packed individual whose chunks pseudo-individual n uses
+    double *tensor;             // [N][K(K+1)/2][G] upper-triangle rows, fp64
+    int32_t N, K, G, grid_start, mode;
+    double bw, half_bw;
+    const SlabDesc *slabs;
+    int32_t n_slabs;
+    unsigned long long *accepted;
+    int *err;
+};
+
+// ---- launch wrappers (all asynchronous on `st`) ---------------------------------------------
+void launch_chunk_count(const void *labels, const int32_t *rowmap, int label_bytes, int nsites, int rows, double weight_min,
+                        int32_t *counts, cudaStream_t st);
+void launch_exclusive_scan_i32(const int32_t *in, int32_t *out /*[n+1]*/, int n, cudaStream_t st);
+void launch_chunk_emit(const void *labels, const int32_t *rowmap, int label_bytes, int nsites, int rows, double weight_min,
+                       const int32_t *row_off, const double *cum, const double *inc, double *cstart, double *cend,
+                       int32_t *chap, cudaStream_t st);
+void launch_bin_sort(int n_phys, int rows_per_ind, const int32_t *row_off, const double *cstart, const double *cend,
+                     const int32_t *chap, const int32_t *donor_label, int n_donor_labels, double cutoff, int K, int mode,
+                     int nb, int W, const double *Etab, double divisor, Chunk *sorted, int32_t *chunk_base, int32_t *t,
+                     int32_t *first, int32_t *yoff, long long *rowoff, int32_t *cntmat, int32_t *runfirst, int *err,
+                     cudaStream_t st);
+void launch_rand_fill(const uint32_t *base_hist, const uint32_t *level_tab, uint32_t *out, long long n_threads,
+                      cudaStream_t st);
+void launch_accum_strict(const AccumArgs &a, cudaStream_t st);
+void launch_accum_relaxed(const AccumArgs &a, long long total_pairs, const long long *task_prefix, cudaStream_t st);
+void launch_project(const double *tensor, int N, int K, int G, int S, const double *tw, const int32_t *pair_kh,
+                    double *results, cudaStream_t st);
+void launch_normalise(double *results, int N, int S, int G, int N_total, double *rsbuf, double *ratio, cudaStream_t st);
+void launch_mean_accum(const double *ratio, int N, int S, int G, double *means, cudaStream_t st);
+void launch_outer_weights(const double *w, int S, int K, double *out, cudaStream_t st);
+void launch_expand_raw(const double *tensor, int N, int K, int G, double *out_full, cudaStream_t st);
+
+// NULL-individual path
+struct NullArgs {
+    const Chunk *chunks;        // per haplotype, grouped by population label (stable), see k_null_group
+    const int32_t *hap_base;    // [n_haps+1]
+    const int32_t *lab_off;     // [n_haps][K+1] offsets (relative to hap_base) of each label group (labels 1..K)
+    int32_t n_inds, ploidy, K, G, grid_start;
+    double bw, half_bw;
+    double *out;                // [K][K][G]
+    unsigned long long *accepted;
+};
+void launch_null_group(int n_haps, const int32_t *row_off /*[n_haps+1]*/, const double *cstart, const double *cend,
+                       const int32_t *chap, const int32_t *donor_label, int n_donor_labels, double cutoff, int K,
+                       Chunk *grouped, int32_t *lab_off, int *err, cudaStream_t st);
+void launch_null_strict(const NullArgs &a, cudaStream_t st);
+
+}  // namespace fgt

@@ -1,0 +1,162 @@
+/*
+ * fgt_companion.h -- C ABI of the B200-native fastGLOBETROTTER companion library
+ * (fastglobetrotter_b200/fastGLOBETROTTERCompanion.so).
+ *
+ * Part 1 is the drop-in boundary: the four symbols fastGLOBETROTTER.R binds with
+ * .C() after dyn.load("fastGLOBETROTTERCompanion.so") (reference fastGLOBETROTTER.R:154,
+ * R:199-232).  Names (including the typo), argument order, pointer-only calling convention,
+ * "add into the caller-zeroed output" and "printf + exit(1) on error" are those of the
+ * reference C file.  No R headers are involved on either side (reference C:1-7).
+ *
+ * Part 2 is the packed boundary used by benchmarks, multi-GPU sharding and the parity
+ * tests: the same computation on already-decoded paintings (host or device resident).
+ *
+ * There is no CPU implementation behind any of these entry points: a machine without a
+ * usable CUDA device makes every compute entry point fail loudly (exit(1) for the .C
+ * symbols, a negative return code for the fgt_* ones).
+ */
+#ifndef FGT_COMPANION_H
+#define FGT_COMPANION_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------
+ * Part 1 -- R-callable entry points (replace the same-named functions of the reference)
+ * ------------------------------------------------------------------------------------ */
+
+/* replaces fastGLOBETROTTERCompanion.c:15-23; bound at fastGLOBETROTTER.R:217.
+ * tempweights[(m*S+n)*K*K + k*K + l] = weights_mat[k*S+m] * weights_mat[l*S+n]. */
+void mutiply_temp_weight(double *tempweights, double *weights_mat, int *num_surrogates, int *num_donors);
+
+/* replaces fastGLOBETROTTERCompanion.c:183-683 (modes 1 and 2); bound at fastGLOBETROTTER.R:210.
+ * means (S*S*num_bins doubles, row-major [(k*S+h)*num_bins + i]) is added into. */
+void data_read(int *ploidy, int *ind_id_vec, char **filenameSAMPread, char **filenameRECOMread, double *binwidth,
+               int *num_bins, int *grid_start, int *num_donors, int *donor_label_vec, int *num_inds_rec,
+               char **recipient_label_vec, double *weight_min, double *gridweightMAX_cutoff, int *num_surrogates,
+               double *temp_weights, double *means);
+
+/* replaces fastGLOBETROTTERCompanion.c:1211-1621 (mode 3); bound at fastGLOBETROTTER.R:202. */
+void data_read_mode3(int *ploidy, int *ind_id_vec, char **filenameSAMPread, char **filenameRECOMread,
+                     double *binwidth, int *num_bins, int *grid_start, int *num_donors, int *donor_label_vec,
+                     int *num_inds_rec, char **recipient_label_vec, double *weight_min,
+                     double *gridweightMAX_cutoff, int *num_surrogates, double *temp_weights, double *means);
+
+/* replaces fastGLOBETROTTERCompanion.c:685-1056 (NULL-individual curves); bound at fastGLOBETROTTER.R:224.
+ * chrom_ind_res (K*K*num_bins doubles, [(lA*K + lB)*num_bins + b]) is added into. */
+void data_read_null(int *ploidy, char **filenameSAMPread, char **filenameRECOMread, double *binwidth, int *num_bins,
+                    int *grid_start, int *num_donors, int *donor_label_vec, int *num_inds_rec,
+                    char **recipient_label_vec, double *weight_min, double *gridweightMAX_cutoff,
+                    double *chrom_ind_res);
+
+/* ------------------------------------------------------------------------------------
+ * Part 2 -- packed boundary
+ * ------------------------------------------------------------------------------------ */
+
+#define FGT_OK 0
+#define FGT_ERR_NO_DEVICE (-1)   /* no CUDA device / driver: there is no CPU fallback            */
+#define FGT_ERR_CUDA (-2)        /* a CUDA call failed (message on stderr)                        */
+#define FGT_ERR_MISSING_DONOR (-3) /* a chunk's donor haplotype has label -9 (reference C:517-522) */
+#define FGT_ERR_LABEL_RANGE (-4) /* donor label > num_donors (reference C:102-107)                */
+#define FGT_ERR_ARG (-5)         /* malformed problem description                                 */
+#define FGT_ERR_RAND (-6)        /* libc rand() state is not the TYPE_3 generator                 */
+#define FGT_ERR_MODE3_TARGET (-7) /* mode 3 met a target-population chunk (undefined behaviour in
+                                     the reference, C:1159-1166 index with label-1 = -1)           */
+
+/* one chromosome of decoded paintings */
+typedef struct fgt_chrom_t {
+    int32_t nsites;          /* SNPs = rows of the recombination map (reference C:357-364)               */
+    const double *pos;       /* host, [nsites] basepair positions                                         */
+    const double *rate;      /* host, [nsites] recombination rate per bp (Morgans)                        */
+    const void *labels;      /* [n_packed_inds*ploidy*nsamples][nsites] donor haplotype ids (1-based),    */
+                             /* row (ind*ploidy + p)*nsamples + s; uint16 or int32, host or device memory */
+    int32_t labels_on_device;
+} fgt_chrom_t;
+
+typedef struct fgt_problem_t {
+    int32_t mode;            /* 1 = data_read constants, 3 = data_read_mode3 constants                    */
+    int32_t ploidy, nsamples, num_chrom;
+    int32_t n_packed_inds;   /* individuals present in every labels matrix                                */
+    int32_t label_bytes;     /* 2 or 4                                                                    */
+    const fgt_chrom_t *chrom;
+    int32_t num_inds;        /* pseudo-individuals handled by THIS call (this rank's shard)               */
+    const int32_t *ind_rows; /* [i*num_chrom + h] packed individual used for pseudo-individual i          */
+    int32_t num_inds_total;  /* divisor of the mean over individuals (= num_inds unless sharded)          */
+    const int64_t *pair_offset; /* optional [h*num_inds + i]: position (in sampled pairs, from the rand()
+                                state at call entry) at which (h,i) starts drawing; NULL = this call owns
+                                the whole stream and offsets are the running sum in (h,i) order          */
+    int64_t pairs_total;     /* with pair_offset: pairs drawn by ALL shards (state advance); else ignored */
+    double binwidth;
+    int32_t num_bins, grid_start, num_donors;
+    const int32_t *donor_label_vec;
+    int32_t n_donor_labels;
+    double weight_min, gridweight_max_cutoff;
+    int32_t num_surrogates;
+    const double *temp_weights;   /* host, laid out as data_read expects it (reference C:590)            */
+} fgt_problem_t;
+
+typedef struct fgt_stats_t {
+    int64_t pairs;           /* sampled chunk pairs evaluated by this call (sum of Y) / NULL path: (i,j) pairs */
+    int64_t accepted;        /* pairs that updated a cell                                                 */
+    int64_t chunks;          /* chunks built                                                              */
+    int32_t kernel_launches; /* kernels launched by this call                                             */
+    int64_t h2d_bytes, d2h_bytes;
+    float ms_chunk, ms_rand, ms_accum, ms_project, ms_total; /* CUDA-event times on the library stream  */
+    int32_t accum_launches;  /* launches of the accumulation kernel included in ms_accum                  */
+} fgt_stats_t;
+
+/* sampled-pair curves (data_read / data_read_mode3 semantics) from packed paintings.
+ * means: host, S*S*num_bins doubles, added into. */
+int fgt_data_read_packed(const fgt_problem_t *prob, double *means, fgt_stats_t *stats);
+
+/* pairs each (h,i) of the problem will draw: out[h*num_inds + i].  Lets shards exchange counts
+ * (one all-gather) and derive pair_offset. */
+int fgt_count_pairs_packed(const fgt_problem_t *prob, int64_t *out);
+
+/* NULL-individual curves (data_read_null semantics): uses the first min(num_inds,100) entries of
+ * rec_rows (packed individual of each recipient) and the first painting sample only. */
+int fgt_data_read_null_packed(const fgt_problem_t *prob, const int32_t *rec_rows, double *chrom_ind_res,
+                              fgt_stats_t *stats);
+
+/* raw per-individual co-copying tensor of the last fgt_data_read_packed / data_read call
+ * (needs option "keep_raw"=1 before the call).  mode 1: [num_inds][K*K][num_bins] as
+ * total_counts_mat_all stands before reference C:578; mode 3: [num_chrom*num_inds][K*K][num_bins]
+ * in tabulate call order.  Returns the number of doubles (or a negative error). */
+int64_t fgt_get_raw_counts(double *out, int64_t capacity);
+
+/* options: "device" (ordinal), "strict" (1 = order-preserving fp64 fold, bit-exact; 0 = fp64
+ * atomics), "keep_raw", "rand_libc" (1 = draw from / advance the process' libc rand() state like
+ * the reference does; 0 = private stream seeded by fgt_srand), "slab_bins", "cache" (parsed-file cache),
+ * "threads" (parser threads), "verbose". */
+int fgt_set_option(const char *key, double value);
+double fgt_get_option(const char *key);
+
+/* seed of the private glibc-compatible stream (rand_libc = 0); same sequence as srand(seed). */
+void fgt_srand(unsigned seed);
+
+/* stats of the most recent .C-style call (data_read, data_read_mode3, data_read_null) */
+void fgt_last_stats(fgt_stats_t *out);
+
+/* glibc rand() emulator self-test helpers (host): fill out[n] with the next n draws of the
+ * stream (private or libc-coupled) generated ON THE DEVICE, advancing it. */
+int fgt_rand_fill(int32_t *out, int64_t n);
+
+/* chunk builder alone (device): chunks of one painting row; arrays sized >= nsites.
+ * Returns the number of chunks or a negative error. */
+int fgt_chunk_one(const void *labels, int label_bytes, int nsites, const double *pos, const double *rate,
+                  double weight_min, double cutoff, const int32_t *donor_label_vec, int n_donor_labels,
+                  double *cpos, double *csize, double *cweight, double *cend, int32_t *cpop);
+
+/* host-only self-test of the jump-ahead arithmetic: the 31-word history (oldest first) of the
+ * glibc stream n_draws after srand(seed). */
+int fgt_rand_host_jump(unsigned seed, uint64_t n_draws, uint32_t *hist_out);
+
+const char *fgt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FGT_COMPANION_H */

@@ -1,0 +1,61 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def _have_gpu() -> bool:
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    if _have_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device here")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def built():
+    """Build (if stale) and return the path of the product library."""
+    from fastglobetrotter_b200 import build as b
+    return b.build()
+
+
+@pytest.fixture(scope="session")
+def lib(built):
+    from fastglobetrotter_b200.companion import PackedCompanion
+    return PackedCompanion(built)
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle.oracle import Oracle
+    return Oracle()
+
+
+@pytest.fixture(scope="session")
+def ref_libs():
+    """(pristine, hooked) compiled reference, built here if /root/reference exists."""
+    from oracle import build_ref
+    ok = build_ref.build()
+    if not ok:
+        pytest.skip("compiled reference unavailable")
+    from helpers import REF_LIB, REF_HOOKED
+    from fastglobetrotter_b200.companion import Companion
+    return Companion(REF_LIB), Companion(REF_HOOKED)

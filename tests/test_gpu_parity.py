@@ -1,0 +1,262 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle
+(oracle/companion_oracle.c, itself pinned to the compiled reference) and, where oracle/_ref
+travelled to this box, against the compiled reference driven through the .C entry points.
+
+Bar: bit-exact for the raw fp64 co-copying tensors AND for `means` / the NULL tensor on one GPU
+(the additions are performed in the reference's order).  Sizes are chosen so that the oracle
+finishes in seconds."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from helpers import (REF_HOOKED, REF_LIB, bootstrap_ids, have_ref, ind_id_matrix, libc_rand, srand)
+from fastglobetrotter_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def packed_chrom(data):
+    sp = data.spec
+    per = sp.ploidy * sp.nsamples
+    out = []
+    for c in data.chrom:
+        rows = np.concatenate([np.arange(s * per, (s + 1) * per) for s in data.rec_file_index])
+        out.append({"pos": c["pos"], "rate": c["rate"], "labels": np.ascontiguousarray(c["labels"][rows])})
+    return out
+
+
+@pytest.fixture(scope="module")
+def small(tmp_path_factory):
+    spec = synth.SynthSpec(n_chrom=2, n_inds=6, n_snps=4000, K=7, nsamples=5, self_copy_frac=0.04, n_extra_inds=2,
+                           rate=3e-7, name="small")
+    d = tmp_path_factory.mktemp("small")
+    return synth.write_dataset(spec, str(d))
+
+
+# ---------------------------------------------------------------------------------------------
+def test_rand_stream_matches_libc(lib):
+    """device-generated glibc stream == libc rand(), private and libc-coupled modes, across the
+    run boundaries of the generator (1984 draws/thread, 256 threads/block)."""
+    lib.set_option("rand_libc", 0)
+    for seed, n in ((1, 5000), (12345, 1984 * 256 * 3 + 77)):
+        lib.srand(seed)
+        got = lib.rand_fill(n)
+        srand(seed)
+        want = np.array([libc_rand() for _ in range(min(n, 20000))], dtype=np.int32)
+        assert np.array_equal(got[:want.size], want)
+        if n > 20000:
+            # tail: continue the private stream and compare with libc after skipping
+            srand(seed)
+            for _ in range(n):
+                libc_rand()
+            nxt = lib.rand_fill(100)
+            assert np.array_equal(nxt, np.array([libc_rand() for _ in range(100)], dtype=np.int32))
+    # coupled: consume from libc's own state and leave it advanced
+    lib.set_option("rand_libc", 1)
+    srand(99)
+    a = [libc_rand() for _ in range(10)]
+    got = lib.rand_fill(3000)
+    after = [libc_rand() for _ in range(5)]
+    srand(99)
+    want = np.array([libc_rand() for _ in range(10 + 3000 + 5)], dtype=np.int32)
+    assert a == want[:10].tolist()
+    assert np.array_equal(got, want[10:3010])
+    assert after == want[3010:].tolist()
+
+
+@pytest.mark.parametrize("weight_min", [0.0, 3.0])
+def test_chunk_builder(lib, oracle, weight_min):
+    spec = synth.SynthSpec(n_chrom=1, n_inds=1, n_snps=5000, K=5, nsamples=3, rate=3e-7, seed=7)
+    pos, rate, labels = synth.make_chromosome(spec, 0)
+    dl = spec.donor_label_vec()
+    for r in range(labels.shape[0]):
+        n_o, o = oracle.chunk_one(labels[r], pos, rate, weight_min, 1.0, dl)
+        n_g, g = lib.chunk_one(labels[r], pos, rate, weight_min, 1.0, dl)
+        assert n_o == n_g
+        for k in ("pos", "size", "weight", "end", "pop"):
+            assert np.array_equal(o[k], g[k]), k
+    # 32-bit labels, single-SNP and single-chunk edge cases
+    lab32 = labels[0].astype(np.int32)
+    assert oracle.chunk_one(lab32, pos, rate, weight_min, 1.0, dl)[0] == lib.chunk_one(lab32, pos, rate, weight_min, 1.0, dl)[0]
+    const = np.full(spec.n_snps, 3, dtype=np.uint16)
+    n_g, g = lib.chunk_one(const, pos, rate, weight_min, 1.0, dl)
+    n_o, o = oracle.chunk_one(const, pos, rate, weight_min, 1.0, dl)
+    assert n_g == n_o == 1 and np.array_equal(g["pos"], o["pos"]) and np.array_equal(g["weight"], o["weight"])
+
+
+def test_missing_donor_is_an_error(lib):
+    spec = synth.SynthSpec(n_chrom=1, n_inds=1, n_snps=500, K=3, nsamples=1, rate=3e-6)
+    pos, rate, labels = synth.make_chromosome(spec, 0)
+    dl = spec.donor_label_vec().copy()
+    dl[int(labels[0][0]) - 1] = -9
+    n, _ = lib.chunk_one(labels[0], pos, rate, 0.0, 1.0, dl)
+    assert n == -3
+
+
+@pytest.mark.parametrize("mode", [1, 3])
+@pytest.mark.parametrize("ids_kind", ["identity", "bootstrap"])
+def test_data_read_packed_bit_exact(lib, oracle, small, mode, ids_kind):
+    sp = small.spec
+    if mode == 3:   # mode 3 has undefined behaviour on target-label chunks: use a data set without them
+        sp = synth.SynthSpec(n_chrom=2, n_inds=6, n_snps=4000, K=7, nsamples=5, rate=3e-7, name="m3")
+        chrom = []
+        for h in range(sp.n_chrom):
+            pos, rate, labels = synth.make_chromosome(sp, h)
+            chrom.append({"pos": pos, "rate": rate, "labels": labels})
+        dl = sp.donor_label_vec()
+    else:
+        chrom, dl = packed_chrom(small), small.donor_label_vec
+    K, S, G, bw, gs = sp.K, 4, 120, 0.1, 10
+    W = synth.random_weights(K, S)
+    tw = oracle.mutiply_temp_weight(K, S, W.ravel(order="F")).reshape(S * S, K * K).ravel(order="F")
+    ids = ind_id_matrix(sp.n_inds, sp.n_chrom) if ids_kind == "identity" else bootstrap_ids(sp.n_inds, sp.n_chrom, 3)
+    oracle.srand(2024)
+    m_o, raw_o, pairs_o = oracle.data_read_packed(mode, sp.ploidy, sp.nsamples, chrom, ids, bw, G, gs, K, dl, 0.0, 1.0, S,
+                                                  tw, want_raw=True)
+    lib.set_option("rand_libc", 0)
+    lib.srand(2024)
+    m_g, raw_g, st = lib.data_read_packed(mode, sp.ploidy, sp.nsamples, chrom, ids, bw, G, gs, K, dl, 0.0, 1.0, S, tw,
+                                          want_raw=True)
+    assert st["pairs"] == pairs_o
+    assert raw_g.shape == raw_o.shape
+    assert np.array_equal(raw_g, raw_o), f"raw tensor differs in {(raw_g != raw_o).sum()} cells"
+    assert np.array_equal(m_g, m_o), f"means differ, max rel {np.max(np.abs(m_g - m_o) / np.abs(m_o))}"
+    # the private stream advanced by exactly two draws per sampled pair
+    nxt = lib.rand_fill(3)
+    oracle_next = np.array([oracle.rand() for _ in range(3)], dtype=np.int32)
+    assert np.array_equal(nxt, oracle_next)
+
+
+@pytest.mark.parametrize("slab_bins", [5, 17, 1000])
+def test_slab_partition_does_not_change_results(lib, oracle, small, slab_bins):
+    sp = small.spec
+    chrom, dl = packed_chrom(small), small.donor_label_vec
+    K, S, G, bw, gs = sp.K, 3, 95, 0.1, 10
+    tw = np.random.default_rng(0).random(K * K * S * S)
+    ids = ind_id_matrix(sp.n_inds, sp.n_chrom)
+    oracle.srand(5)
+    m_o, raw_o, _ = oracle.data_read_packed(1, sp.ploidy, sp.nsamples, chrom, ids, bw, G, gs, K, dl, 0.0, 1.0, S, tw, want_raw=True)
+    lib.set_option("rand_libc", 0)
+    lib.set_option("slab_bins", slab_bins)
+    try:
+        lib.srand(5)
+        m_g, raw_g, _ = lib.data_read_packed(1, sp.ploidy, sp.nsamples, chrom, ids, bw, G, gs, K, dl, 0.0, 1.0, S, tw, want_raw=True)
+    finally:
+        lib.set_option("slab_bins", 0)
+    assert np.array_equal(raw_g, raw_o) and np.array_equal(m_g, m_o)
+
+
+def test_odd_grids(lib, oracle, small):
+    """bin widths / grid starts that are not 0.1 / 10, and weight_min > 0."""
+    sp = small.spec
+    chrom, dl = packed_chrom(small), small.donor_label_vec
+    K, S = sp.K, 2
+    tw = np.random.default_rng(1).random(K * K * S * S)
+    ids = ind_id_matrix(sp.n_inds, sp.n_chrom)
+    for (bw, G, gs, wmin, cutoff) in ((0.25, 40, 4, 0.0, 1.0), (0.07, 150, 0, 2.0, 0.5), (1.0, 12, 1, 0.0, 1.0)):
+        oracle.srand(11)
+        m_o, raw_o, _ = oracle.data_read_packed(1, sp.ploidy, sp.nsamples, chrom, ids, bw, G, gs, K, dl, wmin, cutoff, S, tw, want_raw=True)
+        lib.set_option("rand_libc", 0)
+        lib.srand(11)
+        m_g, raw_g, _ = lib.data_read_packed(1, sp.ploidy, sp.nsamples, chrom, ids, bw, G, gs, K, dl, wmin, cutoff, S, tw, want_raw=True)
+        assert np.array_equal(raw_g, raw_o), (bw, G, gs)
+        assert np.array_equal(m_g, m_o, equal_nan=True), (bw, G, gs)
+
+
+def test_null_packed_bit_exact(lib, oracle, small):
+    sp = small.spec
+    chrom, dl = packed_chrom(small), small.donor_label_vec
+    K, G, bw, gs = sp.K, 120, 0.1, 10
+    rows = np.arange(sp.n_inds)
+    n_o, ev_o = oracle.data_read_null_packed(sp.ploidy, sp.nsamples, chrom, rows, bw, G, gs, K, dl, 0.0, 1.0)
+    n_g, st = lib.data_read_null_packed(sp.ploidy, sp.nsamples, chrom, rows, bw, G, gs, K, dl, 0.0, 1.0)
+    assert st["pairs"] == ev_o
+    assert np.array_equal(n_g, n_o), f"{(n_g != n_o).sum()} cells differ"
+    # adds into the caller's buffer
+    init = np.random.default_rng(2).random(K * K * G)
+    n_g2, _ = lib.data_read_null_packed(sp.ploidy, sp.nsamples, chrom, rows, bw, G, gs, K, dl, 0.0, 1.0, init=init)
+    assert not np.array_equal(n_g2, n_g)
+
+
+def test_mutiply_temp_weight(lib, oracle):
+    K, S = 9, 4
+    W = synth.random_weights(K, S)
+    got = lib.mutiply_temp_weight(K, S, W)
+    want = oracle.mutiply_temp_weight(K, S, W.ravel(order="F"))
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.skipif(not have_ref(), reason="compiled reference (oracle/_ref) not present")
+@pytest.mark.parametrize("mode", [1, 3])
+def test_file_entry_points_vs_compiled_reference(lib, ref_libs, small, tmp_path, mode):
+    """data_read / data_read_mode3 / data_read_null through the R-style .C marshalling on the same
+    text files, same libc srand(): bit-identical outputs, and libc rand() left in the same state."""
+    ref, ref_hooked = ref_libs
+    if mode == 3:
+        sp = synth.SynthSpec(n_chrom=2, n_inds=5, n_snps=3000, K=6, nsamples=4, rate=4e-7, n_extra_inds=1, name="m3f")
+        data = synth.write_dataset(sp, str(tmp_path))
+    else:
+        data, sp = small, small.spec
+    K, S, G, bw, gs = sp.K, 3, 100, 0.1, 10
+    W = synth.random_weights(K, S)
+    tw_ref = ref.temp_weights_for_data_read(K, S, W)
+    tw_lib = lib.temp_weights_for_data_read(K, S, W)
+    assert np.array_equal(tw_ref, tw_lib)
+    ids = bootstrap_ids(sp.n_inds, sp.n_chrom, 8)
+    f_ref = ref.coancestry_curves if mode == 1 else ref.coancestry_curves_mode3
+    f_lib = lib.coancestry_curves if mode == 1 else lib.coancestry_curves_mode3
+    args = (sp.ploidy, ids, data.samples_list, data.recom_list, bw, G, gs, K, data.donor_label_vec, data.rec_labels, 0.0, 1.0)
+    lib.set_option("rand_libc", 1)
+    srand(31337)
+    m_ref = f_ref(*args, tw_ref, S)
+    after_ref = [libc_rand() for _ in range(4)]
+    srand(31337)
+    m_lib = f_lib(*args, tw_lib, S)
+    after_lib = [libc_rand() for _ in range(4)]
+    assert np.array_equal(m_ref, m_lib)
+    assert after_ref == after_lib
+    # second call in the same process continues the stream (the R driver makes ~100 calls)
+    srand(4)
+    a1 = f_ref(*args, tw_ref, S); a2 = f_ref(*args, tw_ref, S)
+    srand(4)
+    b1 = f_lib(*args, tw_lib, S); b2 = f_lib(*args, tw_lib, S)
+    assert np.array_equal(a1, b1) and np.array_equal(a2, b2) and not np.array_equal(a1, a2)
+    if mode == 1:
+        n_ref = ref.coancestry_curves_null(sp.ploidy, data.samples_list, data.recom_list, bw, G, gs, K,
+                                           data.donor_label_vec, data.rec_labels, 0.0, 1.0)
+        n_lib = lib.coancestry_curves_null(sp.ploidy, data.samples_list, data.recom_list, bw, G, gs, K,
+                                           data.donor_label_vec, data.rec_labels, 0.0, 1.0)
+        assert np.array_equal(n_ref, n_lib)
+
+
+def test_sharded_offsets_reproduce_single_call(lib, oracle, small):
+    """two 'ranks' (emulated sequentially on one GPU) with exchanged pair counts reproduce the raw
+    tensors of the unsharded call bit-for-bit; means agree to 1e-12 (different summation order over
+    individuals across ranks)."""
+    sp = small.spec
+    chrom, dl = packed_chrom(small), small.donor_label_vec
+    K, S, G, bw, gs = sp.K, 3, 100, 0.1, 10
+    tw = np.random.default_rng(3).random(K * K * S * S)
+    N, Cn = sp.n_inds, sp.n_chrom
+    ids = ind_id_matrix(N, Cn)
+    lib.set_option("rand_libc", 0)
+    lib.srand(77)
+    m_all, raw_all, st_all = lib.data_read_packed(1, sp.ploidy, sp.nsamples, chrom, ids, bw, G, gs, K, dl, 0.0, 1.0, S, tw, want_raw=True)
+    counts = lib.count_pairs_packed(1, sp.ploidy, sp.nsamples, chrom, ids, bw, G, gs, K, dl, 0.0, 1.0)  # [Cn, N]
+    assert counts.sum() == st_all["pairs"]
+    offs = np.concatenate([[0], np.cumsum(counts.ravel())])[:-1].reshape(Cn, N)
+    halves = [np.arange(0, N // 2), np.arange(N // 2, N)]
+    m_sum = np.zeros_like(m_all)
+    raws = []
+    for part in halves:
+        lib.srand(77)
+        ids_p = ids.reshape(N, Cn)[part].ravel()
+        m_p, raw_p, _ = lib.data_read_packed(1, sp.ploidy, sp.nsamples, chrom, ids_p, bw, G, gs, K, dl, 0.0, 1.0, S, tw,
+                                             want_raw=True, num_inds_total=N, pair_offset=offs[:, part],
+                                             pairs_total=int(counts.sum()))
+        m_sum += m_p
+        raws.append(raw_p)
+    assert np.array_equal(np.concatenate(raws), raw_all)
+    assert np.allclose(m_sum, m_all, rtol=1e-12, atol=0)
