@@ -1,0 +1,351 @@
+#!/usr/bin/env python3
+"""bench.py -- coancestry-curve hot path throughput on B200 (see DESIGN.md "Measurement").
+
+One "step" = one full `data_read` pass (chunk paintings -> sampling schedule -> glibc rand stream ->
+order-preserving fp64 accumulation -> projection -> normalised curves) over the synthetic workload
+of BASELINE.json configs[1]: 1 chromosome, 200 target haplotypes (100 diploid individuals) x 10
+painting samples, 100k SNPs, K = 30 donor groups, 500 bins of 0.1 cM, per GPU (weak scaling).
+
+  value : sampled chunk-pair updates per second, inputs (decoded paintings) resident in HBM
+  e2e   : the same through the packed C ABI with HOST (pinned) paintings: H2D of the labels and D2H
+          of the curves inside the timed region
+  --impl reference : the compiled reference companion (oracle/_ref) on host cores, bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "coancestry_chunk_pair_updates_per_sec"
+UNIT = "pair-updates/s"
+
+WORK = dict(n_chrom=1, n_inds=100, ploidy=2, nsamples=10, n_snps=100_000, K=30, G=500, bw=0.1, grid_start=10, S=10,
+            haps_per_pop=20, weight_min=0.0, cutoff=1.0, mode=1)
+WORKLOAD_NAME = ("configs[1]: synthetic 1 chromosome, 200 target haps (100 diploid inds) x 10 samples, 100k SNPs, "
+                 "K=30 donor groups, 500 x 0.1 cM bins, S=10 surrogates, data_read (mode 1) semantics, per GPU")
+
+
+def spec_for(n_inds, seed=20261019 + 2):
+    from fastglobetrotter_b200 import synth
+    return synth.SynthSpec(n_chrom=WORK["n_chrom"], n_inds=n_inds, ploidy=WORK["ploidy"], nsamples=WORK["nsamples"],
+                           n_snps=WORK["n_snps"], K=WORK["K"], haps_per_pop=WORK["haps_per_pop"], seed=seed, name="cfg2")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                          str(self.index), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.rows.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from fastglobetrotter_b200 import build as fbuild
+    from fastglobetrotter_b200 import synth
+    from fastglobetrotter_b200.companion import PackedCompanion
+    from fastglobetrotter_b200.synth_torch import make_chromosome_device
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = PackedCompanion(fbuild.build())
+    lib.set_option("device", local)
+    lib.set_option("rand_libc", 0)
+    lib.srand(1)
+
+    W = WORK
+    spec = spec_for(W["n_inds"])
+    K, S, G = W["K"], W["S"], W["G"]
+    chrom_dev, chrom_host, keep = [], [], []
+    for h in range(W["n_chrom"]):
+        pos, rate, lab = make_chromosome_device(spec, h, dev, ind_offset=rank * W["n_inds"])
+        keep.append(lab)
+        chrom_dev.append({"pos": pos, "rate": rate, "labels": (lab.data_ptr(), 2, lab.shape[0])})
+        hl = torch.empty(lab.shape, dtype=torch.int16, pin_memory=True)
+        hl.copy_(lab)
+        keep.append(hl)
+        chrom_host.append({"pos": pos, "rate": rate, "labels": hl.numpy().view(np.uint16)})
+    torch.cuda.synchronize()
+    dl = spec.donor_label_vec()
+    weights = synth.random_weights(K, S)
+    tw = lib.temp_weights_for_data_read(K, S, weights)
+    N = W["n_inds"]
+    ids = np.repeat(np.arange(N, dtype=np.int32), W["n_chrom"])
+    common = (W["mode"], W["ploidy"], W["nsamples"])
+    tail = (ids, W["bw"], G, W["grid_start"], K, dl, W["weight_min"], W["cutoff"])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def one_step(chrom):
+        """one data_read pass of this rank's shard; returns (means partial, stats)"""
+        if world == 1:
+            m, _, st = lib.data_read_packed(*common, chrom, *tail, S, tw)
+            return m, st
+        cnt = lib.count_pairs_packed(*common, chrom, *tail)                        # [Cn, N] local
+        allc = [torch.zeros(cnt.size, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(allc, torch.from_numpy(cnt.ravel()).to(dev))                # the one exchange of draw counts
+        allc = torch.stack(allc).cpu().numpy().reshape(world, W["n_chrom"], N)
+        # reference order: chromosome-major, individual-minor; ranks own consecutive blocks of individuals
+        flat = allc.transpose(1, 0, 2).reshape(W["n_chrom"], world * N)
+        offs = np.concatenate([[0], np.cumsum(flat.ravel())])[:-1].reshape(W["n_chrom"], world * N)
+        mine = offs[:, rank * N:(rank + 1) * N]
+        lib.set_option("reuse_prep", 1)
+        m, _, st = lib.data_read_packed(*common, chrom, *tail, S, tw, num_inds_total=world * N, pair_offset=mine,
+                                        pairs_total=int(flat.sum()))
+        mt = torch.from_numpy(m).to(dev)
+        dist.all_reduce(mt)                                                          # S^2 x G fp64 curves
+        return mt.cpu().numpy(), st
+
+    def timed(chrom, steps, warmup):
+        for _ in range(warmup):
+            one_step(chrom)
+        barrier()
+        t0 = time.perf_counter()
+        agg = {"pairs": 0, "accepted": 0, "ms_accum": 0.0, "accum_launches": 0, "kernel_launches": 0, "chunks": 0,
+               "h2d_bytes": 0, "d2h_bytes": 0, "ms_total": 0.0, "ms_rand": 0.0, "ms_chunk": 0.0, "ms_project": 0.0}
+        for _ in range(steps):
+            m, st = one_step(chrom)
+            for k in agg:
+                agg[k] += st[k]
+        barrier()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt, float(agg["pairs"])], dtype=torch.float64, device=dev)
+        if world > 1:
+            tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            dt, total_pairs = float(tmax[0]), float(tsum[1])
+        else:
+            total_pairs = float(agg["pairs"])
+        return dt, total_pairs, agg, m
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    dt, total_pairs, agg, means = timed(chrom_dev, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    e_steps = max(1, min(args.steps, 5))
+    dt_e, pairs_e, agg_e, _ = timed(chrom_host, e_steps, 1)
+
+    out = None
+    if rank == 0:
+        peak, peak_src = peaks()
+        P = K * (K + 1) // 2
+        launches = max(1, agg["accum_launches"])
+        per_launch_pairs = agg["pairs"] / launches
+        per_launch_chunks = agg["chunks"] / launches
+        alg_bytes = 16.0 * per_launch_pairs + 32.0 * per_launch_chunks + 8.0 * P * G * N
+        kern_s = (agg["ms_accum"] / launches) * 1e-3
+        achieved = alg_bytes / kern_s / 1e9 if kern_s > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "accum_dram_bytes.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        out = {
+            "metric": METRIC, "value": total_pairs / dt, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic (device-generated paintings, seed 20261021)",
+            "config": {"workload": WORKLOAD_NAME, "pairs_per_step_per_gpu": agg["pairs"] / args.steps,
+                       "accepted_fraction": agg["accepted"] / max(1, agg["pairs"]),
+                       "accumulation": "strict (order-preserving fp64 fold, bit-exact vs reference)",
+                       "l2": "inputs > L2: 400 MB of paintings and a fresh 1.3 GB rand stream are re-read every step"},
+            "e2e": {"value": pairs_e / dt_e, "unit": UNIT, "h2d_bytes_per_step": agg_e["h2d_bytes"] / e_steps,
+                    "d2h_bytes_per_step": agg_e["d2h_bytes"] / e_steps, "steps": e_steps,
+                    "ms_per_step": dt_e / e_steps * 1e3, "api": "fgt_data_read_packed (host pinned paintings)"},
+            "gpu_launches": int(agg["kernel_launches"]),
+            "roofline": {"bound": "hbm", "kernel": "k_accum_strict", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_s * 1e3},
+            "device_ms_per_step": {k: agg[k] / args.steps for k in ("ms_total", "ms_chunk", "ms_rand", "ms_accum", "ms_project")},
+            "clocks": clocks,
+            "means_checksum": float(np.nansum(means)),
+        }
+        if not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_baseline(sample_inds=args.cpu_sample_inds, procs=1)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if out is not None:
+        print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------
+def _ref_worker(argtuple):
+    """one process: compiled reference data_read on its own sample files; returns (pairs, seconds)"""
+    lib_path, sl, rl, n_inds, rec_labels, steps = argtuple
+    import ctypes as C
+    sys.path.insert(0, ROOT)
+    from fastglobetrotter_b200.companion import Companion
+    from fastglobetrotter_b200 import synth
+    W = WORK
+    ref = Companion(lib_path)
+    K, S, G = W["K"], W["S"], W["G"]
+    weights = synth.random_weights(K, S)
+    tw = ref.temp_weights_for_data_read(K, S, weights)
+    ids = np.repeat(np.arange(n_inds, dtype=np.int32), W["n_chrom"])
+    dl = spec_for(n_inds).donor_label_vec()
+    pairs = None
+    try:
+        pairs = C.c_long.in_dll(ref.lib, "REF_DUMP_pairs")
+    except ValueError:
+        pass
+    C.CDLL(None).srand(1)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        ref.coancestry_curves(W["ploidy"], ids, sl, rl, W["bw"], G, W["grid_start"], K, dl, rec_labels, W["weight_min"],
+                              W["cutoff"], tw, S)
+        times.append(time.perf_counter() - t0)
+    return (pairs.value if pairs is not None else 0), times
+
+
+def _make_sample_files(tmp, n_inds, tag, seed_shift=0):
+    from fastglobetrotter_b200 import synth
+    spec = spec_for(n_inds, seed=20261019 + 2 + seed_shift)
+    spec.name = f"cfg2_{tag}"
+    data = synth.write_dataset(spec, tmp)
+    return data.samples_list, data.recom_list, data.rec_labels
+
+
+def cpu_baseline(sample_inds=12, procs=1, steps=1):
+    """the compiled reference companion (hooked build, for its pair counter) on host cores."""
+    from oracle import build_ref
+    import multiprocessing as mp
+    if not build_ref.build():
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "compiled reference unavailable"}
+    libp = build_ref.HOOKED
+    with tempfile.TemporaryDirectory() as tmp:
+        jobs = []
+        for p in range(procs):
+            sl, rl, rec = _make_sample_files(os.path.join(tmp, f"p{p}"), sample_inds, f"p{p}", seed_shift=p)
+            jobs.append((libp, sl, rl, sample_inds, rec, steps))
+        ctx = mp.get_context("spawn")
+        t0 = time.perf_counter()
+        if procs == 1:
+            res = [_ref_worker(jobs[0])]
+        else:
+            with ctx.Pool(procs) as pool:
+                res = pool.map(_ref_worker, jobs)
+        wall = time.perf_counter() - t0
+    pairs = sum(r[0] for r in res)
+    busy = max(sum(r[1]) for r in res)
+    return {"value": pairs / busy, "unit": UNIT, "cores": procs, "kind": "reference",
+            "sample": f"{procs} process(es) x {steps} data_read call(s) over {sample_inds} individuals each of the same "
+                      f"workload (text .gz inputs, parse included); {pairs} pairs in {busy:.2f} s (wall {wall:.2f} s)",
+            "pairs": pairs, "seconds": busy}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    procs = max(1, min(os.cpu_count() or 1, 32))
+    t_all = []
+    total_pairs = 0
+    # each step: every process runs one bounded data_read
+    r = cpu_baseline(sample_inds=args.cpu_sample_inds, procs=procs, steps=args.steps + args.warmup)
+    if r["value"] is None:
+        print(json.dumps({"impl": "reference", "unavailable": r["sample"]}))
+        return
+    frac = args.steps / (args.steps + args.warmup)
+    value = r["value"]
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": r["seconds"] / (args.steps + args.warmup) * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic (same generator, text .gz files)",
+           "config": {"workload": WORKLOAD_NAME, "sample": r["sample"]},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "reference", "sample": r["sample"]},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-inds", type=int, default=8)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
