@@ -56,6 +56,7 @@ int Engine::set_option(const char *key, double v) {
     else if (k == "threads") opt.threads = iv;
     else if (k == "verbose") opt.verbose = iv;
     else if (k == "reuse_prep") opt.reuse_prep = iv;
+    else if (k == "accum_impl") opt.accum_impl = iv;
     else return FGT_ERR_ARG;
     return FGT_OK;
 }
@@ -71,6 +72,7 @@ double Engine::get_option(const char *key) {
     if (k == "threads") return opt.threads;
     if (k == "verbose") return opt.verbose;
     if (k == "reuse_prep") return opt.reuse_prep;
+    if (k == "accum_impl") return opt.accum_impl;
     return NAN;
 }
 
@@ -149,6 +151,55 @@ std::vector<SlabDesc> Engine::make_slabs(int G, int grid_start, double bw, int W
         if (s.dlo <= s.dhi) v.push_back(s);
     }
     return v;
+}
+
+// fine bin of a distance, literally the reference's rule (C:144-147) -- used on the host only to
+// bound which bins a coarse-bin separation can reach (the rule is monotone in the distance)
+static int host_fine_bin(double d, double bw) {
+    double q = d / bw;
+    double fl = std::floor(q);
+    double frac = (q - fl) * bw;
+    int b = (int)fl;
+    if (frac > bw / 2.0) b += 1;
+    return b;
+}
+
+// Slab plan of the two-phase accumulation: fixed-width slabs of fine bins; for every separation d
+// the contiguous range of slabs it can reach (distances in [d-1, d+1]); n_slots = widest reach.
+Engine::SlabPlan Engine::make_slab_plan(int G, int grid_start, double bw, int W, int N) const {
+    SlabPlan p;
+    int sb = opt.slab_bins;
+    if (sb <= 0) {
+        sb = std::max(1, (int)std::lround(1.0 / bw));          // 1 cM of bins: a separation reaches 3 slabs
+        while ((long long)((G + sb - 1) / sb) * N < 2000 && sb > 4) sb = (sb + 1) / 2;
+    }
+    auto plan_for = [&](int width) {
+        SlabPlan q;
+        q.slab_of.resize(G);
+        for (int b = 0; b < G; b++) q.slab_of[b] = b / width;
+        int n_slabs = (G + width - 1) / width;
+        q.slabs.resize(n_slabs);
+        for (int s = 0; s < n_slabs; s++) {
+            q.slabs[s].b0 = grid_start + s * width;
+            q.slabs[s].b1 = grid_start + std::min(G, (s + 1) * width) - 1;
+            q.slabs[s].dlo = W; q.slabs[s].dhi = 0;
+        }
+        q.first_slab.assign(W, 0);
+        q.n_slots = 1;
+        for (int d = 1; d < W; d++) {
+            int blo = host_fine_bin((double)(d - 1), bw) - grid_start, bhi = host_fine_bin((double)(d + 1), bw) - grid_start;
+            if (bhi < 0 || blo >= G) { q.first_slab[d] = 0; continue; }
+            blo = std::max(blo, 0); bhi = std::min(bhi, G - 1);
+            int s0 = q.slab_of[blo], s1 = q.slab_of[bhi];
+            q.first_slab[d] = s0;
+            q.n_slots = std::max(q.n_slots, s1 - s0 + 1);
+            for (int s = s0; s <= s1; s++) { q.slabs[s].dlo = std::min(q.slabs[s].dlo, d); q.slabs[s].dhi = std::max(q.slabs[s].dhi, d); }
+        }
+        return q;
+    };
+    p = plan_for(sb);
+    while (p.n_slots > kMaxSlots) { sb *= 2; p = plan_for(sb); }   // wider slabs -> fewer regions per segment
+    return p;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -360,8 +411,18 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
     }
     CK(cudaMemcpyAsync(d_pairkh, pairkh.data(), P * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
     const int W0 = chroms_[0].W;
-    std::vector<SlabDesc> slabs = make_slabs(G, pb.grid_start, pb.binwidth, W0, N);
+    SlabPlan plan;
+    std::vector<SlabDesc> slabs;
+    if (opt.accum_impl == 1) slabs = make_slabs(G, pb.grid_start, pb.binwidth, W0, N);
+    else { plan = make_slab_plan(G, pb.grid_start, pb.binwidth, W0, N); slabs = plan.slabs; }
     SlabDesc *d_slabs = d_slabs_.as<SlabDesc>(slabs.size());
+    int32_t *d_slabof = nullptr, *d_firstslab = nullptr;
+    if (opt.accum_impl != 1) {
+        d_slabof = d_slabof_.as<int32_t>(G); d_firstslab = d_firstslab_.as<int32_t>(W0);
+        if (!d_slabof || !d_firstslab) return FGT_ERR_CUDA;
+        CK(cudaMemcpyAsync(d_slabof, plan.slab_of.data(), G * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
+        CK(cudaMemcpyAsync(d_firstslab, plan.first_slab.data(), W0 * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
+    }
     long long *d_pairbase = d_pairbase_.as<long long>((size_t)Cn * N);
     int32_t *d_physof = d_physof_.as<int32_t>((size_t)Cn * N);
     uint32_t *d_hist = d_hist_.as<uint32_t>((size_t)Cn * kLag);
@@ -419,22 +480,47 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
         launch_rand_fill(d_hist + (size_t)h * kLag, d_level_tab_.as<uint32_t>(level_tab_.size()), d_draws, nthreads[h], st_);
         launches_ += 1;
         mark();
-        AccumArgs a{};
-        a.cp.nb = cs.nb; a.cp.W = cs.W; a.cp.n_phys = n_phys;
-        a.cp.chunks = (const Chunk *)cs.sorted.p; a.cp.chunk_base = (const int32_t *)cs.chunk_base.p;
-        a.cp.t = (const int32_t *)cs.t.p; a.cp.first = (const int32_t *)cs.first.p;
-        a.cp.yoff = (const int32_t *)cs.yoff.p; a.cp.rowoff = (const long long *)cs.rowoff.p;
-        a.draws = (const uint2 *)d_draws;
-        a.pair_base = d_pairbase + (size_t)h * N;
-        a.phys_of = d_physof + (size_t)h * N;
-        a.tensor = d_tensor;
-        a.N = N; a.K = K; a.G = G; a.grid_start = pb.grid_start; a.mode = pb.mode;
-        a.bw = pb.binwidth; a.half_bw = pb.binwidth / 2.0;
-        a.slabs = d_slabs; a.n_slabs = (int)slabs.size();
-        a.accepted = d_acc; a.err = d_err;
-        launch_accum_strict(a, st_);
-        launches_ += 1;
-        stx.accum_launches += 1;
+        ChromPrep cpd{};
+        cpd.nb = cs.nb; cpd.W = cs.W; cpd.n_phys = n_phys;
+        cpd.chunks = (const Chunk *)cs.sorted.p; cpd.chunk_base = (const int32_t *)cs.chunk_base.p;
+        cpd.t = (const int32_t *)cs.t.p; cpd.first = (const int32_t *)cs.first.p;
+        cpd.yoff = (const int32_t *)cs.yoff.p; cpd.rowoff = (const long long *)cs.rowoff.p;
+        if (opt.accum_impl == 1) {
+            AccumArgs a{};
+            a.cp = cpd;
+            a.draws = (const uint2 *)d_draws;
+            a.pair_base = d_pairbase + (size_t)h * N;
+            a.phys_of = d_physof + (size_t)h * N;
+            a.tensor = d_tensor;
+            a.N = N; a.K = K; a.G = G; a.grid_start = pb.grid_start; a.mode = pb.mode;
+            a.bw = pb.binwidth; a.half_bw = pb.binwidth / 2.0;
+            a.slabs = d_slabs; a.n_slabs = (int)slabs.size();
+            a.accepted = d_acc; a.err = d_err;
+            launch_accum_strict(a, st_);
+            launches_ += 1;
+            stx.accum_launches += 1;
+        } else {
+            size_t cnt_elems = (size_t)N * cs.nb * cs.W * plan.n_slots;
+            int32_t *d_cnt = d_cnt_.as<int32_t>(cnt_elems);
+            UpdateRec *d_recs = d_recs_.as<UpdateRec>((size_t)(nthreads[h] * (long long)kRun / 2 + 2) * plan.n_slots);
+            if (!d_cnt || !d_recs) return FGT_ERR_CUDA;
+            CK(cudaMemsetAsync(d_cnt, 0, cnt_elems * sizeof(int32_t), st_));
+            EvalArgs ea{};
+            ea.cp = cpd; ea.draws = (const uint2 *)d_draws;
+            ea.pair_base = d_pairbase + (size_t)h * N; ea.phys_of = d_physof + (size_t)h * N;
+            ea.N = N; ea.K = K; ea.G = G; ea.grid_start = pb.grid_start; ea.mode = pb.mode; ea.n_slots = plan.n_slots;
+            ea.bw = pb.binwidth; ea.half_bw = pb.binwidth / 2.0;
+            ea.slab_of = d_slabof; ea.first_slab = d_firstslab; ea.recs = d_recs; ea.cnt = d_cnt; ea.err = d_err;
+            launch_eval_pairs(ea, st_);
+            CommitArgs ca{};
+            ca.cp = cpd; ca.pair_base = ea.pair_base; ca.phys_of = ea.phys_of;
+            ca.N = N; ca.K = K; ca.G = G; ca.n_slots = plan.n_slots; ca.n_slabs = (int)plan.slabs.size();
+            ca.slabs = d_slabs; ca.first_slab = d_firstslab; ca.recs = d_recs; ca.cnt = d_cnt; ca.tensor = d_tensor;
+            ca.accepted = d_acc;
+            launch_commit_ordered(ca, st_);
+            launches_ += 2;
+            stx.accum_launches += 1;
+        }
         mark();
         if (pb.mode == 3) {
             if (want_raw) { launch_expand_raw(d_tensor, N, K, G, d_raw + (size_t)h * N * K * K * G, st_); launches_++; }

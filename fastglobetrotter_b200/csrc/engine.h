@@ -35,7 +35,8 @@ struct Options {
     int cache = 1;
     int threads = 0;        // 0 = hardware concurrency
     int verbose = 0;
-    int reuse_prep = 0;     // one-shot: next packed call may reuse the chunk/bin tables of the previous one
+    int reuse_prep = 0;
+    int accum_impl = 2;     // 2 = two-phase (evaluate once, ordered commit); 1 = single-phase slab warps     // one-shot: next packed call may reuse the chunk/bin tables of the previous one
 };
 
 class Engine {
@@ -64,6 +65,8 @@ class Engine {
     int prep_chromosome(const fgt_problem_t &pb, int h, const int32_t *rowmap_dev, int rows, int rows_per_ind,
                         int n_groups, bool for_null, ChromState &cs, fgt_stats_t &stx);
     std::vector<SlabDesc> make_slabs(int G, int grid_start, double bw, int W, int N) const;
+    struct SlabPlan { std::vector<SlabDesc> slabs; std::vector<int32_t> slab_of, first_slab; int n_slots = 0; };
+    SlabPlan make_slab_plan(int G, int grid_start, double bw, int W, int N) const;
 
     bool inited_ = false;
     int init_rc_ = 0;
@@ -75,7 +78,7 @@ class Engine {
     DevBuf d_labels_, d_cum_, d_inc_, d_counts_, d_rowoff_, d_cstart_, d_cend_, d_chap_, d_cntmat_, d_runfirst_,
         d_donor_, d_etab_, d_rowmap_;
     DevBuf d_draws_, d_hist_, d_tensor_, d_results_, d_tw_, d_pairkh_, d_slabs_, d_pairbase_, d_physof_, d_rs_,
-        d_ratio_, d_means_, d_raw_, d_totals_;
+        d_ratio_, d_means_, d_raw_, d_totals_, d_recs_, d_cnt_, d_slabof_, d_firstslab_;
     std::vector<ChromState> chroms_;
     std::vector<double> raw_host_;
     int64_t raw_count_ = 0;

@@ -525,6 +525,187 @@ void launch_accum_strict(const AccumArgs &a, cudaStream_t st) {
     k_accum_strict<<<grid, wpb * 32, 0, st>>>(a);
 }
 
+// =============================================================================================
+// 4b. Two-phase strict accumulation.
+// =============================================================================================
+__device__ __forceinline__ unsigned fastmod_u32(unsigned a, unsigned d, double inv_d) {
+    // a < 2^31: trunc(a * RN(1/d)) is floor(a/d) or, for exact multiples only, one less
+    unsigned q = __double2uint_rz(__dmul_rn((double)a, inv_d));
+    unsigned r = a - q * d;
+    return r >= d ? r - d : r;
+}
+
+// Phase 1: one warp per (pseudo-individual, coarse bin j); walks k = j+1.. in order, 32 sampled pairs
+// per step.  Everything of reference C:136-162 except the "+=" happens here.
+__global__ void __launch_bounds__(128) k_eval_pairs(const EvalArgs a) {
+    const int lane = lane_id();
+    const ChromPrep &cp = a.cp;
+    const int nb = cp.nb, W = cp.W;
+    const long long task = (long long)blockIdx.x * (blockDim.x >> 5) + warp_id();
+    if (task >= (long long)a.N * (nb - 1)) return;
+    const int n = (int)(task / (nb - 1));
+    const int j = (int)(task - (long long)n * (nb - 1));
+    const int phys = a.phys_of[n];
+    const int32_t *T = cp.t + (size_t)phys * nb;
+    const int t1 = T[j];
+    if (t1 <= 0) return;
+    const int32_t *F = cp.first + (size_t)phys * nb;
+    const int32_t *yo = cp.yoff + ((size_t)phys * nb + j) * W;
+    const Chunk *ch = cp.chunks + cp.chunk_base[phys];
+    const long long row_pair0 = a.pair_base[n] + cp.rowoff[(size_t)phys * (nb + 1) + j];
+    const int f1 = F[j];
+    const double inv1 = __ddiv_rn(1.0, (double)t1);
+    const int G = a.G, K = a.K, ns = a.n_slots;
+    const double bw = a.bw, half_bw = a.half_bw;
+    int dmax = W - 1;
+    if (nb - 1 - j < dmax) dmax = nb - 1 - j;
+    int bad = 0;
+    const unsigned lt = (1u << lane) - 1;
+    for (int d = 1; d <= dmax; d++) {
+        const int y0 = yo[d - 1];
+        const int Y = yo[d] - y0;
+        if (Y <= 0) continue;
+        const int k = j + d;
+        const int t2 = T[k], f2 = F[k];
+        const double inv2 = __ddiv_rn(1.0, (double)t2);
+        const long long seg = row_pair0 + y0;
+        const uint2 *dr = a.draws + seg;
+        UpdateRec *reg = a.recs + seg * ns;
+        const int slab0 = a.first_slab[d];
+        int c[kMaxSlots] = {0, 0, 0, 0};
+        for (int base = 0; base < Y; base += 32) {
+            const int q = base + lane;
+            int cell = -1, slot = -1;
+            double val = 0.0;
+            if (q < Y) {
+                const uint2 r = dr[q];
+                const int c1 = f1 + (int)fastmod_u32(r.x, (unsigned)t1, inv1);
+                const int c2 = f2 + (int)fastmod_u32(r.y, (unsigned)t2, inv2);
+                const Chunk A = ch[c1], B = ch[c2];
+                bool live = true;
+                if (a.mode == 1) live = (A.pop != 0) && (B.pop != 0);          // reference C:138-142
+                else if (A.pop == 0 || B.pop == 0) { bad |= kErrMode3Target; live = false; }
+                if (live) {
+                    const double dist = fabs(__dsub_rn(A.pos, B.pos));          // reference C:143
+                    const double qd = __ddiv_rn(dist, bw);
+                    const double fl = floor(qd);
+                    const double frac = __dmul_rn(__dsub_rn(qd, fl), bw);       // reference C:144-145
+                    int bfull = __double2int_rz(fl);
+                    bool ok = true;
+                    if (frac <= half_bw) {}
+                    else if (frac > half_bw) bfull += 1;
+                    else ok = false;
+                    const int bb = bfull - a.grid_start;
+                    const double mind = __dadd_rn(__dmul_rn(A.size, 0.5), __dmul_rn(B.size, 0.5));
+                    if (ok && bb >= 0 && bb < G && dist >= mind) {
+                        const int l1 = A.pop - 1, l2 = B.pop - 1;
+                        const int lo_l = l1 < l2 ? l1 : l2, hi_l = l1 < l2 ? l2 : l1;
+                        cell = tri_row(lo_l, hi_l, K) * G + bb;
+                        val = __dmul_rn(A.w, B.w);
+                        slot = a.slab_of[bb] - slab0;
+                        if (slot < 0 || slot >= ns) { bad |= kErrInternal; slot = -1; cell = -1; }
+                    }
+                }
+            }
+            // ordered partition of this step's updates into the segment's slab regions
+            int pos = 0;
+#pragma unroll
+            for (int s = 0; s < kMaxSlots; s++) {
+                if (s < ns) {
+                    const unsigned m = __ballot_sync(kFull, slot == s);
+                    if (slot == s) pos = c[s] + __popc(m & lt);
+                    c[s] += __popc(m);
+                }
+            }
+            if (slot >= 0) {
+                UpdateRec rec;
+                rec.cell = cell; rec.pad = 0; rec.val = val;
+                reg[(long long)slot * Y + pos] = rec;
+            }
+        }
+        if (lane < ns) {
+            int v = c[0];
+#pragma unroll
+            for (int s = 1; s < kMaxSlots; s++) if (lane == s) v = c[s];
+            a.cnt[(((size_t)n * nb + j) * W + d) * ns + lane] = v;
+        }
+    }
+    if (bad) atomicOr(a.err, bad);
+}
+
+void launch_eval_pairs(const EvalArgs &a, cudaStream_t st) {
+    long long tasks = (long long)a.N * (a.cp.nb - 1);
+    if (tasks <= 0) return;
+    const int wpb = 4;
+    k_eval_pairs<<<(unsigned)((tasks + wpb - 1) / wpb), wpb * 32, 0, st>>>(a);
+}
+
+// Phase 2: one warp per (pseudo-individual, slab) folds the slab's records in sequence order
+// (j ascending, k ascending, draw ascending): the "+=" of reference C:155 / C:161.
+__global__ void __launch_bounds__(128) k_commit_ordered(const CommitArgs a) {
+    const int lane = lane_id();
+    const int task = blockIdx.x * (blockDim.x >> 5) + warp_id();
+    if (task >= a.N * a.n_slabs) return;
+    const int slab_i = task / a.N;
+    const int n = task - slab_i * a.N;
+    const SlabDesc sl = a.slabs[slab_i];
+    const int phys = a.phys_of[n];
+    const ChromPrep &cp = a.cp;
+    const int nb = cp.nb, W = cp.W, ns = a.n_slots;
+    const int32_t *T = cp.t + (size_t)phys * nb;
+    const long long *RO = cp.rowoff + (size_t)phys * (nb + 1);
+    double *tens = a.tensor + (size_t)n * ((size_t)a.K * (a.K + 1) / 2) * a.G;
+    const long long pb = a.pair_base[n];
+    unsigned long long n_acc = 0;
+    for (int j = 0; j < nb - 1; j++) {
+        if (T[j] <= 0) continue;
+        int dmax = W - 1;
+        if (nb - 1 - j < dmax) dmax = nb - 1 - j;
+        const int dhi = sl.dhi < dmax ? sl.dhi : dmax;
+        const int32_t *yo = cp.yoff + ((size_t)phys * nb + j) * W;
+        const int32_t *cn = a.cnt + ((size_t)n * nb + j) * W * ns;
+        const long long row0 = pb + RO[j];
+        for (int d = sl.dlo; d <= dhi; d++) {
+            const int y0 = yo[d - 1];
+            const int Y = yo[d] - y0;
+            if (Y <= 0) continue;
+            const int slot = slab_i - a.first_slab[d];
+            const int c = cn[d * ns + slot];
+            if (c <= 0) continue;
+            const UpdateRec *reg = a.recs + (row0 + y0) * ns + (long long)slot * Y;
+            for (int base = 0; base < c; base += 32) {
+                const int q = base + lane;
+                int cell = -1;
+                double val = 0.0;
+                if (q < c) { const UpdateRec r = reg[q]; cell = r.cell; val = r.val; }
+                const unsigned key = cell >= 0 ? (unsigned)cell : (0x80000000u | (unsigned)lane);
+                const unsigned grp = __match_any_sync(kFull, key);
+                const bool leader = (cell >= 0) && ((grp & ((1u << lane) - 1)) == 0);
+                double acc = 0.0;
+                if (leader) acc = tens[cell];
+                unsigned rest = leader ? (grp & ~(1u << lane)) : 0u;
+                acc = __dadd_rn(acc, val);
+                while (__any_sync(kFull, rest != 0)) {
+                    const int src = rest ? (__ffs(rest) - 1) : lane;
+                    const double v = __shfl_sync(kFull, val, src);
+                    if (rest) { acc = __dadd_rn(acc, v); rest &= rest - 1; }
+                }
+                if (leader) tens[cell] = acc;
+                __syncwarp();
+            }
+            n_acc += (unsigned long long)c;
+        }
+    }
+    if (lane == 0 && n_acc) atomicAdd(a.accepted, n_acc);
+}
+
+void launch_commit_ordered(const CommitArgs &a, cudaStream_t st) {
+    long long tasks = (long long)a.N * a.n_slabs;
+    if (tasks <= 0) return;
+    const int wpb = 4;
+    k_commit_ordered<<<(unsigned)((tasks + wpb - 1) / wpb), wpb * 32, 0, st>>>(a);
+}
+
 void launch_accum_relaxed(const AccumArgs &, long long, const long long *, cudaStream_t) {}
 
 // =============================================================================================

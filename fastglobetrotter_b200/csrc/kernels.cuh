@@ -49,6 +49,43 @@ struct AccumArgs {
     int *err;
 };
 
+// ---- two-phase strict accumulation (v2) -------------------------------------------------------
+// Phase 1 evaluates every sampled pair once (no ordering constraint, full occupancy) and files the
+// accepted updates, in sequence order, into per-(segment, slab) record regions; phase 2 lets one warp
+// per (individual, slab) fold the records of its slab in the reference's order.
+struct __align__(16) UpdateRec { int32_t cell; int32_t pad; double val; };
+
+constexpr int kMaxSlots = 4;   // slabs a coarse-bin separation can reach (regions per segment)
+
+struct EvalArgs {
+    ChromPrep cp;
+    const uint2 *draws;
+    const long long *pair_base;   // [N]
+    const int32_t *phys_of;       // [N]
+    int32_t N, K, G, grid_start, mode, n_slots;
+    double bw, half_bw;
+    const int32_t *slab_of;       // [G] slab index of every fine bin (relative to grid_start)
+    const int32_t *first_slab;    // [W] first slab reachable from separation d
+    UpdateRec *recs;              // [(pairs) * n_slots]: segment (n,j,d) owns n_slots regions of Y records each
+    int32_t *cnt;                 // [N][nb][W][n_slots] records filed per region
+    int *err;
+};
+
+struct CommitArgs {
+    ChromPrep cp;
+    const long long *pair_base;
+    const int32_t *phys_of;
+    int32_t N, K, G, n_slots, n_slabs;
+    const SlabDesc *slabs;        // dlo/dhi = separations whose reach includes the slab
+    const int32_t *first_slab;
+    const UpdateRec *recs;
+    const int32_t *cnt;
+    double *tensor;
+    unsigned long long *accepted;
+};
+void launch_eval_pairs(const EvalArgs &a, cudaStream_t st);
+void launch_commit_ordered(const CommitArgs &a, cudaStream_t st);
+
 // ---- launch wrappers (all asynchronous on `st`) ---------------------------------------------
 void launch_chunk_count(const void *labels, const int32_t *rowmap, int label_bytes, int nsites, int rows, double weight_min,
                         int32_t *counts, cudaStream_t st);

@@ -260,3 +260,22 @@ def test_sharded_offsets_reproduce_single_call(lib, oracle, small):
         raws.append(raw_p)
     assert np.array_equal(np.concatenate(raws), raw_all)
     assert np.allclose(m_sum, m_all, rtol=1e-12, atol=0)
+
+
+def test_single_phase_kernel_still_exact(lib, oracle, small):
+    """accum_impl=1 (one-phase slab warps, kept for A/B profiling) gives the same bits as the default."""
+    sp = small.spec
+    chrom, dl = packed_chrom(small), small.donor_label_vec
+    K, S, G, bw, gs = sp.K, 3, 110, 0.1, 10
+    tw = np.random.default_rng(9).random(K * K * S * S)
+    ids = bootstrap_ids(sp.n_inds, sp.n_chrom, 1)
+    oracle.srand(8)
+    m_o, raw_o, _ = oracle.data_read_packed(1, sp.ploidy, sp.nsamples, chrom, ids, bw, G, gs, K, dl, 0.0, 1.0, S, tw, want_raw=True)
+    lib.set_option("rand_libc", 0)
+    lib.set_option("accum_impl", 1)
+    try:
+        lib.srand(8)
+        m_g, raw_g, _ = lib.data_read_packed(1, sp.ploidy, sp.nsamples, chrom, ids, bw, G, gs, K, dl, 0.0, 1.0, S, tw, want_raw=True)
+    finally:
+        lib.set_option("accum_impl", 2)
+    assert np.array_equal(raw_g, raw_o) and np.array_equal(m_g, m_o)
