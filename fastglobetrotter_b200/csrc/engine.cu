@@ -198,7 +198,7 @@ Engine::SlabPlan Engine::make_slab_plan(int G, int grid_start, double bw, int W,
         return q;
     };
     p = plan_for(sb);
-    while (p.n_slots > kMaxSlots) { sb *= 2; p = plan_for(sb); }   // wider slabs -> fewer regions per segment
+    while (p.n_slots > kMaxSlots && sb < G) { sb *= 2; p = plan_for(sb); }   // wider slabs -> fewer regions per segment
     return p;
 }
 
@@ -413,15 +413,32 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
     const int W0 = chroms_[0].W;
     SlabPlan plan;
     std::vector<SlabDesc> slabs;
-    if (opt.accum_impl == 1) slabs = make_slabs(G, pb.grid_start, pb.binwidth, W0, N);
-    else { plan = make_slab_plan(G, pb.grid_start, pb.binwidth, W0, N); slabs = plan.slabs; }
+    int impl = opt.accum_impl;
+    if (impl != 1) {
+        plan = make_slab_plan(G, pb.grid_start, pb.binwidth, W0, N);
+        slabs = plan.slabs;
+        for (const SlabDesc &s : slabs)
+            if (s.dhi - s.dlo + 1 > 32) impl = 1;      // the commit kernel keeps one separation per lane
+        if (plan.n_slots > kMaxSlots) impl = 1;
+    }
+    if (impl == 1) slabs = make_slabs(G, pb.grid_start, pb.binwidth, W0, N);
     SlabDesc *d_slabs = d_slabs_.as<SlabDesc>(slabs.size());
-    int32_t *d_slabof = nullptr, *d_firstslab = nullptr;
-    if (opt.accum_impl != 1) {
+    int32_t *d_slabof = nullptr, *d_firstslab = nullptr, *d_slabw = nullptr, *d_slabb0 = nullptr;
+    int plan_max_w = 1;
+    if (impl != 1) {
         d_slabof = d_slabof_.as<int32_t>(G); d_firstslab = d_firstslab_.as<int32_t>(W0);
         if (!d_slabof || !d_firstslab) return FGT_ERR_CUDA;
         CK(cudaMemcpyAsync(d_slabof, plan.slab_of.data(), G * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
         CK(cudaMemcpyAsync(d_firstslab, plan.first_slab.data(), W0 * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
+        std::vector<int32_t> sw(slabs.size()), sb0(slabs.size());
+        for (size_t s = 0; s < slabs.size(); s++) {
+            sw[s] = slabs[s].b1 - slabs[s].b0 + 1; sb0[s] = slabs[s].b0 - pb.grid_start;
+            plan_max_w = std::max(plan_max_w, sw[s]);
+        }
+        d_slabw = d_slabw_.as<int32_t>(slabs.size()); d_slabb0 = d_slabb0_.as<int32_t>(slabs.size());
+        if (!d_slabw || !d_slabb0) return FGT_ERR_CUDA;
+        CK(cudaMemcpyAsync(d_slabw, sw.data(), sw.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
+        CK(cudaMemcpyAsync(d_slabb0, sb0.data(), sb0.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
     }
     long long *d_pairbase = d_pairbase_.as<long long>((size_t)Cn * N);
     int32_t *d_physof = d_physof_.as<int32_t>((size_t)Cn * N);
@@ -485,7 +502,7 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
         cpd.chunks = (const Chunk *)cs.sorted.p; cpd.chunk_base = (const int32_t *)cs.chunk_base.p;
         cpd.t = (const int32_t *)cs.t.p; cpd.first = (const int32_t *)cs.first.p;
         cpd.yoff = (const int32_t *)cs.yoff.p; cpd.rowoff = (const long long *)cs.rowoff.p;
-        if (opt.accum_impl == 1) {
+        if (impl == 1) {
             AccumArgs a{};
             a.cp = cpd;
             a.draws = (const uint2 *)d_draws;
@@ -510,14 +527,15 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
             ea.pair_base = d_pairbase + (size_t)h * N; ea.phys_of = d_physof + (size_t)h * N;
             ea.N = N; ea.K = K; ea.G = G; ea.grid_start = pb.grid_start; ea.mode = pb.mode; ea.n_slots = plan.n_slots;
             ea.bw = pb.binwidth; ea.half_bw = pb.binwidth / 2.0;
-            ea.slab_of = d_slabof; ea.first_slab = d_firstslab; ea.recs = d_recs; ea.cnt = d_cnt; ea.err = d_err;
+            ea.slab_of = d_slabof; ea.first_slab = d_firstslab; ea.slab_w = d_slabw; ea.slab_b0 = d_slabb0;
+            ea.recs = d_recs; ea.cnt = d_cnt; ea.err = d_err;
             launch_eval_pairs(ea, st_);
             CommitArgs ca{};
             ca.cp = cpd; ca.pair_base = ea.pair_base; ca.phys_of = ea.phys_of;
-            ca.N = N; ca.K = K; ca.G = G; ca.n_slots = plan.n_slots; ca.n_slabs = (int)plan.slabs.size();
+            ca.N = N; ca.K = K; ca.G = G; ca.grid_start = pb.grid_start; ca.n_slots = plan.n_slots; ca.n_slabs = (int)plan.slabs.size();
             ca.slabs = d_slabs; ca.first_slab = d_firstslab; ca.recs = d_recs; ca.cnt = d_cnt; ca.tensor = d_tensor;
             ca.accepted = d_acc;
-            launch_commit_ordered(ca, st_);
+            launch_commit_ordered(ca, plan_max_w, st_);
             launches_ += 2;
             stx.accum_launches += 1;
         }

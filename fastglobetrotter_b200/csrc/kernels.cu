@@ -575,7 +575,7 @@ __global__ void __launch_bounds__(128) k_eval_pairs(const EvalArgs a) {
         int c[kMaxSlots] = {0, 0, 0, 0};
         for (int base = 0; base < Y; base += 32) {
             const int q = base + lane;
-            int cell = -1, slot = -1;
+            int cell = -1, slot = -1, local = 0;
             double val = 0.0;
             if (q < Y) {
                 const uint2 r = dr[q];
@@ -602,7 +602,9 @@ __global__ void __launch_bounds__(128) k_eval_pairs(const EvalArgs a) {
                         const int lo_l = l1 < l2 ? l1 : l2, hi_l = l1 < l2 ? l2 : l1;
                         cell = tri_row(lo_l, hi_l, K) * G + bb;
                         val = __dmul_rn(A.w, B.w);
-                        slot = a.slab_of[bb] - slab0;
+                        const int slab = a.slab_of[bb];
+                        slot = slab - slab0;
+                        local = tri_row(lo_l, hi_l, K) * a.slab_w[slab] + (bb - a.slab_b0[slab]);
                         if (slot < 0 || slot >= ns) { bad |= kErrInternal; slot = -1; cell = -1; }
                     }
                 }
@@ -619,7 +621,7 @@ __global__ void __launch_bounds__(128) k_eval_pairs(const EvalArgs a) {
             }
             if (slot >= 0) {
                 UpdateRec rec;
-                rec.cell = cell; rec.pad = 0; rec.val = val;
+                rec.cell = cell; rec.pad = local; rec.val = val;
                 reg[(long long)slot * Y + pos] = rec;
             }
         }
@@ -640,49 +642,162 @@ void launch_eval_pairs(const EvalArgs &a, cudaStream_t st) {
     k_eval_pairs<<<(unsigned)((tasks + wpb - 1) / wpb), wpb * 32, 0, st>>>(a);
 }
 
-// Phase 2: one warp per (pseudo-individual, slab) folds the slab's records in sequence order
+// Phase 2: one CTA per (pseudo-individual, slab) folds the slab's records in sequence order
 // (j ascending, k ascending, draw ascending): the "+=" of reference C:155 / C:161.
-__global__ void __launch_bounds__(128) k_commit_ordered(const CommitArgs a) {
+//
+// Warp-specialised, Blackwell style: warp 1 is the producer -- it walks the record regions of the
+// slab in order and streams them into a shared-memory ring with TMA bulk copies
+// (cp.async.bulk + mbarrier complete_tx); warp 0 is the consumer -- it folds 32 records per step into
+// the slab tile, which lives in shared memory when it fits (TILE_SMEM), so the ordered
+// read-modify-write chain runs at shared-memory latency and global latency is off the critical path.
+constexpr int kStages = 6;        // ring depth
+constexpr int kStageRecs = 64;    // records per ring stage (two consumer steps)
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <bool TILE_SMEM>
+__global__ void __launch_bounds__(64) k_commit_ordered(const CommitArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    UpdateRec *ring = reinterpret_cast<UpdateRec *>(smem_raw);                         // [kStages][kStageRecs]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kStages * kStageRecs * sizeof(UpdateRec));
+    uint64_t *empty = full + kStages;
+    int *stage_cnt = reinterpret_cast<int *>(empty + kStages);                         // [kStages]
+    int *meta_c = stage_cnt + kStages;                                                 // [32]
+    long long *meta_base = reinterpret_cast<long long *>(meta_c + 32 + 2);             // [32] (8-byte aligned)
+    double *tile = reinterpret_cast<double *>(smem_raw + 6144 + 1024);                 // ring 6 KB + 1 KB control
     const int lane = lane_id();
-    const int task = blockIdx.x * (blockDim.x >> 5) + warp_id();
-    if (task >= a.N * a.n_slabs) return;
+    const int wid = warp_id();
+    const int task = blockIdx.x;
     const int slab_i = task / a.N;
     const int n = task - slab_i * a.N;
     const SlabDesc sl = a.slabs[slab_i];
-    const int phys = a.phys_of[n];
-    const ChromPrep &cp = a.cp;
-    const int nb = cp.nb, W = cp.W, ns = a.n_slots;
-    const int32_t *T = cp.t + (size_t)phys * nb;
-    const long long *RO = cp.rowoff + (size_t)phys * (nb + 1);
-    double *tens = a.tensor + (size_t)n * ((size_t)a.K * (a.K + 1) / 2) * a.G;
-    const long long pb = a.pair_base[n];
-    unsigned long long n_acc = 0;
-    for (int j = 0; j < nb - 1; j++) {
-        if (T[j] <= 0) continue;
-        int dmax = W - 1;
-        if (nb - 1 - j < dmax) dmax = nb - 1 - j;
-        const int dhi = sl.dhi < dmax ? sl.dhi : dmax;
-        const int32_t *yo = cp.yoff + ((size_t)phys * nb + j) * W;
-        const int32_t *cn = a.cnt + ((size_t)n * nb + j) * W * ns;
-        const long long row0 = pb + RO[j];
-        for (int d = sl.dlo; d <= dhi; d++) {
-            const int y0 = yo[d - 1];
-            const int Y = yo[d] - y0;
-            if (Y <= 0) continue;
-            const int slot = slab_i - a.first_slab[d];
-            const int c = cn[d * ns + slot];
-            if (c <= 0) continue;
-            const UpdateRec *reg = a.recs + (row0 + y0) * ns + (long long)slot * Y;
-            for (int base = 0; base < c; base += 32) {
-                const int q = base + lane;
+    const int G = a.G;
+    const int P = a.K * (a.K + 1) / 2;
+    double *tens = a.tensor + (size_t)n * (size_t)P * G;
+    const int sbw = sl.b1 - sl.b0 + 1;
+    const int boff = sl.b0 - a.grid_start;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (TILE_SMEM) {
+        for (int idx = threadIdx.x; idx < P * sbw; idx += blockDim.x) {
+            const int row = idx / sbw, off = idx - row * sbw;
+            tile[idx] = tens[(size_t)row * G + boff + off];
+        }
+    }
+    __syncthreads();
+
+    if (wid == 1) {
+        // ------------------------------ producer ------------------------------
+        const int phys = a.phys_of[n];
+        const ChromPrep &cp = a.cp;
+        const int nb = cp.nb, W = cp.W, ns = a.n_slots;
+        const int32_t *T = cp.t + (size_t)phys * nb;
+        const long long *RO = cp.rowoff + (size_t)phys * (nb + 1);
+        const long long pb = a.pair_base[n];
+        const int nd = sl.dhi - sl.dlo + 1;                    // <= 32 (engine guarantees)
+        const int my_d = sl.dlo + lane;
+        const int my_slot = (lane < nd) ? slab_i - a.first_slab[my_d] : 0;
+        auto load_row = [&](int j, int &c, long long &base) {
+            c = 0; base = 0;
+            if (j < nb - 1 && lane < nd) {
+                const int t1 = T[j];
+                int dmax = W - 1;
+                if (nb - 1 - j < dmax) dmax = nb - 1 - j;
+                if (t1 > 0 && my_d <= dmax) {
+                    const int32_t *yo = cp.yoff + ((size_t)phys * nb + j) * W;
+                    const int y0 = yo[my_d - 1], Y = yo[my_d] - y0;
+                    if (Y > 0) {
+                        c = a.cnt[(((size_t)n * nb + j) * W + my_d) * ns + my_slot];
+                        base = (pb + RO[j] + y0) * ns + (long long)my_slot * Y;
+                    }
+                }
+            }
+        };
+        int stage = 0;
+        unsigned phase = 0;
+        int c_cur, c_nxt;
+        long long b_cur, b_nxt;
+        load_row(0, c_cur, b_cur);
+        for (int j = 0; j < nb - 1; j++) {
+            load_row(j + 1, c_nxt, b_nxt);                 // in flight while row j is being issued
+            if (__any_sync(kFull, c_cur > 0)) {
+                meta_c[lane] = c_cur;
+                meta_base[lane] = b_cur;
+                __syncwarp();
+                if (lane == 0) {
+                    for (int i = 0; i < nd; i++) {
+                        const int c = meta_c[i];
+                        const long long base = meta_base[i];
+                        for (int off = 0; off < c; off += kStageRecs) {
+                            const int cnt_here = c - off < kStageRecs ? c - off : kStageRecs;
+                            mbar_wait(&empty[stage], phase ^ 1);
+                            stage_cnt[stage] = cnt_here;
+                            mbar_arrive_expect_tx(&full[stage], (unsigned)cnt_here * (unsigned)sizeof(UpdateRec));
+                            bulk_g2s(&ring[stage * kStageRecs], a.recs + base + off, (unsigned)cnt_here * (unsigned)sizeof(UpdateRec),
+                                     &full[stage]);
+                            if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            c_cur = c_nxt; b_cur = b_nxt;
+        }
+        if (lane == 0) {                                   // end marker
+            mbar_wait(&empty[stage], phase ^ 1);
+            stage_cnt[stage] = -1;
+            mbar_arrive(&full[stage]);
+        }
+    } else {
+        // ------------------------------ consumer ------------------------------
+        int stage = 0;
+        unsigned phase = 0;
+        unsigned long long n_acc = 0;
+        while (true) {
+            mbar_wait(&full[stage], phase);
+            const int c = stage_cnt[stage];
+            if (c < 0) break;
+            for (int off = 0; off < c; off += 32) {
                 int cell = -1;
                 double val = 0.0;
-                if (q < c) { const UpdateRec r = reg[q]; cell = r.cell; val = r.val; }
+                if (off + lane < c) {
+                    const UpdateRec r = ring[stage * kStageRecs + off + lane];
+                    cell = TILE_SMEM ? r.pad : r.cell;
+                    val = r.val;
+                }
                 const unsigned key = cell >= 0 ? (unsigned)cell : (0x80000000u | (unsigned)lane);
                 const unsigned grp = __match_any_sync(kFull, key);
                 const bool leader = (cell >= 0) && ((grp & ((1u << lane) - 1)) == 0);
                 double acc = 0.0;
-                if (leader) acc = tens[cell];
+                if (leader) acc = TILE_SMEM ? tile[cell] : tens[cell];
                 unsigned rest = leader ? (grp & ~(1u << lane)) : 0u;
                 acc = __dadd_rn(acc, val);
                 while (__any_sync(kFull, rest != 0)) {
@@ -690,20 +805,42 @@ __global__ void __launch_bounds__(128) k_commit_ordered(const CommitArgs a) {
                     const double v = __shfl_sync(kFull, val, src);
                     if (rest) { acc = __dadd_rn(acc, v); rest &= rest - 1; }
                 }
-                if (leader) tens[cell] = acc;
+                if (leader) { if (TILE_SMEM) tile[cell] = acc; else tens[cell] = acc; }
                 __syncwarp();
             }
             n_acc += (unsigned long long)c;
+            if (lane == 0) mbar_arrive(&empty[stage]);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if (lane == 0 && n_acc) atomicAdd(a.accepted, n_acc);
+    }
+    __syncthreads();
+    if (TILE_SMEM) {
+        for (int idx = threadIdx.x; idx < P * sbw; idx += blockDim.x) {
+            const int row = idx / sbw, o2 = idx - row * sbw;
+            tens[(size_t)row * G + boff + o2] = tile[idx];
         }
     }
-    if (lane == 0 && n_acc) atomicAdd(a.accepted, n_acc);
 }
 
-void launch_commit_ordered(const CommitArgs &a, cudaStream_t st) {
+size_t commit_tile_bytes(int K, int slab_width) { return (size_t)K * (K + 1) / 2 * slab_width * sizeof(double); }
+
+void launch_commit_ordered(const CommitArgs &a, int max_slab_width, cudaStream_t st) {
     long long tasks = (long long)a.N * a.n_slabs;
     if (tasks <= 0) return;
-    const int wpb = 4;
-    k_commit_ordered<<<(unsigned)((tasks + wpb - 1) / wpb), wpb * 32, 0, st>>>(a);
+    const size_t ctrl_bytes = 6144 + 1024;
+    static_assert(kStages * kStageRecs * sizeof(UpdateRec) == 6144, "ring size");
+    const size_t tile_bytes = commit_tile_bytes(a.K, max_slab_width);
+    static bool attr_set = false;
+    if (tile_bytes + ctrl_bytes <= 200 * 1024) {
+        if (!attr_set) {
+            cudaFuncSetAttribute(k_commit_ordered<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            attr_set = true;
+        }
+        k_commit_ordered<true><<<(unsigned)tasks, 64, ctrl_bytes + tile_bytes, st>>>(a);
+    } else {
+        k_commit_ordered<false><<<(unsigned)tasks, 64, ctrl_bytes, st>>>(a);
+    }
 }
 
 void launch_accum_relaxed(const AccumArgs &, long long, const long long *, cudaStream_t) {}

@@ -53,7 +53,7 @@ struct AccumArgs {
 // Phase 1 evaluates every sampled pair once (no ordering constraint, full occupancy) and files the
 // accepted updates, in sequence order, into per-(segment, slab) record regions; phase 2 lets one warp
 // per (individual, slab) fold the records of its slab in the reference's order.
-struct __align__(16) UpdateRec { int32_t cell; int32_t pad; double val; };
+struct __align__(16) UpdateRec { int32_t cell; int32_t pad; double val; };   // cell: index in the individual's tensor; pad: index in the slab tile
 
 constexpr int kMaxSlots = 4;   // slabs a coarse-bin separation can reach (regions per segment)
 
@@ -66,6 +66,8 @@ struct EvalArgs {
     double bw, half_bw;
     const int32_t *slab_of;       // [G] slab index of every fine bin (relative to grid_start)
     const int32_t *first_slab;    // [W] first slab reachable from separation d
+    const int32_t *slab_w;        // [n_slabs] width of each slab in bins
+    const int32_t *slab_b0;       // [n_slabs] first bin (relative to grid_start) of each slab
     UpdateRec *recs;              // [(pairs) * n_slots]: segment (n,j,d) owns n_slots regions of Y records each
     int32_t *cnt;                 // [N][nb][W][n_slots] records filed per region
     int *err;
@@ -75,7 +77,7 @@ struct CommitArgs {
     ChromPrep cp;
     const long long *pair_base;
     const int32_t *phys_of;
-    int32_t N, K, G, n_slots, n_slabs;
+    int32_t N, K, G, grid_start, n_slots, n_slabs;
     const SlabDesc *slabs;        // dlo/dhi = separations whose reach includes the slab
     const int32_t *first_slab;
     const UpdateRec *recs;
@@ -84,7 +86,8 @@ struct CommitArgs {
     unsigned long long *accepted;
 };
 void launch_eval_pairs(const EvalArgs &a, cudaStream_t st);
-void launch_commit_ordered(const CommitArgs &a, cudaStream_t st);
+void launch_commit_ordered(const CommitArgs &a, int max_slab_width, cudaStream_t st);
+size_t commit_tile_bytes(int K, int slab_width);
 
 // ---- launch wrappers (all asynchronous on `st`) ---------------------------------------------
 void launch_chunk_count(const void *labels, const int32_t *rowmap, int label_bytes, int nsites, int rows, double weight_min,
