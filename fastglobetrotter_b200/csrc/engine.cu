@@ -399,7 +399,7 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
     double *d_tw = d_tw_.as<double>((size_t)K * K * S * S);
     int32_t *d_pairkh = d_pairkh_.as<int32_t>(P);
     if (!d_tensor || !d_results || !d_tw || !d_pairkh) return FGT_ERR_CUDA;
-    CK(cudaMemsetAsync(d_tensor, 0, tens_elems * sizeof(double), st_));
+    bool tensor_zero = true;      // the commit kernel then starts from zero tiles and overwrites every cell
     CK(cudaMemsetAsync(d_results, 0, (size_t)N * S * S * G * sizeof(double), st_));
     CK(cudaMemcpyAsync(d_tw, pb.temp_weights, (size_t)K * K * S * S * sizeof(double), cudaMemcpyHostToDevice, st_));
     stx.h2d_bytes += (int64_t)K * K * S * S * 8;
@@ -422,6 +422,14 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
         if (plan.n_slots > kMaxSlots) impl = 1;
     }
     if (impl == 1) slabs = make_slabs(G, pb.grid_start, pb.binwidth, W0, N);
+    bool tile_in_smem = false;
+    if (impl != 1) {
+        int mw = 1;
+        for (const SlabDesc &s : slabs) mw = std::max(mw, s.b1 - s.b0 + 1);
+        tile_in_smem = commit_tile_bytes(K, mw) + 7168 <= 200 * 1024;
+    }
+    const bool memset_tensor = !tile_in_smem;     // smem tiles start from zero and overwrite every cell
+    if (memset_tensor) CK(cudaMemsetAsync(d_tensor, 0, tens_elems * sizeof(double), st_));
     SlabDesc *d_slabs = d_slabs_.as<SlabDesc>(slabs.size());
     int32_t *d_slabof = nullptr, *d_firstslab = nullptr, *d_slabw = nullptr, *d_slabb0 = nullptr;
     int plan_max_w = 1;
@@ -517,25 +525,31 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
             launches_ += 1;
             stx.accum_launches += 1;
         } else {
-            size_t cnt_elems = (size_t)N * cs.nb * cs.W * plan.n_slots;
-            int32_t *d_cnt = d_cnt_.as<int32_t>(cnt_elems);
+            int nd_max = 1;
+            for (const SlabDesc &s : slabs) nd_max = std::max(nd_max, s.dhi - s.dlo + 1);
+            size_t n_ent = (size_t)N * slabs.size() * (cs.nb - 1) * nd_max;
+            RegionEnt *d_regions = d_cnt_.as<RegionEnt>(n_ent);
             UpdateRec *d_recs = d_recs_.as<UpdateRec>((size_t)(nthreads[h] * (long long)kRun / 2 + 2) * plan.n_slots);
-            if (!d_cnt || !d_recs) return FGT_ERR_CUDA;
-            CK(cudaMemsetAsync(d_cnt, 0, cnt_elems * sizeof(int32_t), st_));
+            if (!d_regions || !d_recs) return FGT_ERR_CUDA;
+            CK(cudaMemsetAsync(d_regions, 0, n_ent * sizeof(RegionEnt), st_));
             EvalArgs ea{};
             ea.cp = cpd; ea.draws = (const uint2 *)d_draws;
             ea.pair_base = d_pairbase + (size_t)h * N; ea.phys_of = d_physof + (size_t)h * N;
             ea.N = N; ea.K = K; ea.G = G; ea.grid_start = pb.grid_start; ea.mode = pb.mode; ea.n_slots = plan.n_slots;
             ea.bw = pb.binwidth; ea.half_bw = pb.binwidth / 2.0;
             ea.slab_of = d_slabof; ea.first_slab = d_firstslab; ea.slab_w = d_slabw; ea.slab_b0 = d_slabb0;
-            ea.recs = d_recs; ea.cnt = d_cnt; ea.err = d_err;
+            ea.recs = d_recs; ea.regions = d_regions; ea.slabs = d_slabs; ea.n_slabs = (int)slabs.size(); ea.nd_max = nd_max;
+            ea.err = d_err;
             launch_eval_pairs(ea, st_);
             CommitArgs ca{};
             ca.cp = cpd; ca.pair_base = ea.pair_base; ca.phys_of = ea.phys_of;
-            ca.N = N; ca.K = K; ca.G = G; ca.grid_start = pb.grid_start; ca.n_slots = plan.n_slots; ca.n_slabs = (int)plan.slabs.size();
-            ca.slabs = d_slabs; ca.first_slab = d_firstslab; ca.recs = d_recs; ca.cnt = d_cnt; ca.tensor = d_tensor;
-            ca.accepted = d_acc;
+            ca.N = N; ca.K = K; ca.G = G; ca.grid_start = pb.grid_start; ca.n_slots = plan.n_slots;
+            ca.n_slabs = (int)slabs.size();
+            ca.slabs = d_slabs; ca.recs = d_recs; ca.regions = d_regions; ca.nd_max = nd_max;
+            ca.tensor_is_zero = (tensor_zero && tile_in_smem) ? 1 : 0;
+            ca.tensor = d_tensor; ca.accepted = d_acc;
             launch_commit_ordered(ca, plan_max_w, st_);
+            tensor_zero = false;
             launches_ += 2;
             stx.accum_launches += 1;
         }
@@ -544,7 +558,8 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
             if (want_raw) { launch_expand_raw(d_tensor, N, K, G, d_raw + (size_t)h * N * K * K * G, st_); launches_++; }
             launch_project(d_tensor, N, K, G, S, d_tw, d_pairkh, d_results, st_);
             launches_ += 1;
-            CK(cudaMemsetAsync(d_tensor, 0, tens_elems * sizeof(double), st_));
+            if (memset_tensor) CK(cudaMemsetAsync(d_tensor, 0, tens_elems * sizeof(double), st_));
+            tensor_zero = true;
         }
         mark();
     }

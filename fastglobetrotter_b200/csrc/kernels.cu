@@ -535,8 +535,49 @@ __device__ __forceinline__ unsigned fastmod_u32(unsigned a, unsigned d, double i
     return r >= d ? r - d : r;
 }
 
-// Phase 1: one warp per (pseudo-individual, coarse bin j); walks k = j+1.. in order, 32 sampled pairs
-// per step.  Everything of reference C:136-162 except the "+=" happens here.
+// Phase 1: one warp per (pseudo-individual, coarse bin j); walks k = j+1.. in order, 64 sampled pairs
+// (two per lane, for memory-level parallelism) per iteration.  Everything of reference C:136-162
+// except the "+=" happens here.
+struct PairEval { int cell, local, slot; double val; };
+
+__device__ __forceinline__ PairEval eval_pair(bool in_range, uint2 r, int f1, int t1, double inv1, int f2, int t2, double inv2,
+                                              const Chunk *__restrict__ ch, const EvalArgs &a, int slab0, int &bad) {
+    PairEval o;
+    o.cell = -1; o.local = 0; o.slot = -1; o.val = 0.0;
+    if (!in_range) return o;
+    const int c1 = f1 + (int)fastmod_u32(r.x, (unsigned)t1, inv1);
+    const int c2 = f2 + (int)fastmod_u32(r.y, (unsigned)t2, inv2);
+    const Chunk A = ch[c1], B = ch[c2];
+    bool live = true;
+    if (a.mode == 1) live = (A.pop != 0) && (B.pop != 0);                  // reference C:138-142
+    else if (A.pop == 0 || B.pop == 0) { bad |= kErrMode3Target; live = false; }
+    if (!live) return o;
+    const double dist = fabs(__dsub_rn(A.pos, B.pos));                      // reference C:143
+    const double qd = __ddiv_rn(dist, a.bw);
+    const double fl = floor(qd);
+    const double frac = __dmul_rn(__dsub_rn(qd, fl), a.bw);                 // reference C:144-145
+    int bfull = __double2int_rz(fl);
+    bool ok = true;
+    if (frac <= a.half_bw) {}
+    else if (frac > a.half_bw) bfull += 1;
+    else ok = false;
+    const int bb = bfull - a.grid_start;
+    const double mind = __dadd_rn(__dmul_rn(A.size, 0.5), __dmul_rn(B.size, 0.5));
+    if (ok && bb >= 0 && bb < a.G && dist >= mind) {
+        const int l1 = A.pop - 1, l2 = B.pop - 1;
+        const int lo_l = l1 < l2 ? l1 : l2, hi_l = l1 < l2 ? l2 : l1;
+        const int row = tri_row(lo_l, hi_l, a.K);
+        const int slab = a.slab_of[bb];
+        const int slot = slab - slab0;
+        if (slot < 0 || slot >= a.n_slots) { bad |= kErrInternal; return o; }
+        o.cell = row * a.G + bb;
+        o.local = row * a.slab_w[slab] + (bb - a.slab_b0[slab]);
+        o.slot = slot;
+        o.val = __dmul_rn(A.w, B.w);
+    }
+    return o;
+}
+
 __global__ void __launch_bounds__(128) k_eval_pairs(const EvalArgs a) {
     const int lane = lane_id();
     const ChromPrep &cp = a.cp;
@@ -555,8 +596,7 @@ __global__ void __launch_bounds__(128) k_eval_pairs(const EvalArgs a) {
     const long long row_pair0 = a.pair_base[n] + cp.rowoff[(size_t)phys * (nb + 1) + j];
     const int f1 = F[j];
     const double inv1 = __ddiv_rn(1.0, (double)t1);
-    const int G = a.G, K = a.K, ns = a.n_slots;
-    const double bw = a.bw, half_bw = a.half_bw;
+    const int ns = a.n_slots;
     int dmax = W - 1;
     if (nb - 1 - j < dmax) dmax = nb - 1 - j;
     int bad = 0;
@@ -573,63 +613,45 @@ __global__ void __launch_bounds__(128) k_eval_pairs(const EvalArgs a) {
         UpdateRec *reg = a.recs + seg * ns;
         const int slab0 = a.first_slab[d];
         int c[kMaxSlots] = {0, 0, 0, 0};
-        for (int base = 0; base < Y; base += 32) {
-            const int q = base + lane;
-            int cell = -1, slot = -1, local = 0;
-            double val = 0.0;
-            if (q < Y) {
-                const uint2 r = dr[q];
-                const int c1 = f1 + (int)fastmod_u32(r.x, (unsigned)t1, inv1);
-                const int c2 = f2 + (int)fastmod_u32(r.y, (unsigned)t2, inv2);
-                const Chunk A = ch[c1], B = ch[c2];
-                bool live = true;
-                if (a.mode == 1) live = (A.pop != 0) && (B.pop != 0);          // reference C:138-142
-                else if (A.pop == 0 || B.pop == 0) { bad |= kErrMode3Target; live = false; }
-                if (live) {
-                    const double dist = fabs(__dsub_rn(A.pos, B.pos));          // reference C:143
-                    const double qd = __ddiv_rn(dist, bw);
-                    const double fl = floor(qd);
-                    const double frac = __dmul_rn(__dsub_rn(qd, fl), bw);       // reference C:144-145
-                    int bfull = __double2int_rz(fl);
-                    bool ok = true;
-                    if (frac <= half_bw) {}
-                    else if (frac > half_bw) bfull += 1;
-                    else ok = false;
-                    const int bb = bfull - a.grid_start;
-                    const double mind = __dadd_rn(__dmul_rn(A.size, 0.5), __dmul_rn(B.size, 0.5));
-                    if (ok && bb >= 0 && bb < G && dist >= mind) {
-                        const int l1 = A.pop - 1, l2 = B.pop - 1;
-                        const int lo_l = l1 < l2 ? l1 : l2, hi_l = l1 < l2 ? l2 : l1;
-                        cell = tri_row(lo_l, hi_l, K) * G + bb;
-                        val = __dmul_rn(A.w, B.w);
-                        const int slab = a.slab_of[bb];
-                        slot = slab - slab0;
-                        local = tri_row(lo_l, hi_l, K) * a.slab_w[slab] + (bb - a.slab_b0[slab]);
-                        if (slot < 0 || slot >= ns) { bad |= kErrInternal; slot = -1; cell = -1; }
+        for (int base = 0; base < Y; base += 64) {
+            const int q0 = base + lane, q1 = base + 32 + lane;
+            uint2 r0 = make_uint2(0, 0), r1 = make_uint2(0, 0);
+            if (q0 < Y) r0 = dr[q0];
+            if (q1 < Y) r1 = dr[q1];
+            PairEval e[2];
+            e[0] = eval_pair(q0 < Y, r0, f1, t1, inv1, f2, t2, inv2, ch, a, slab0, bad);
+            e[1] = eval_pair(q1 < Y, r1, f1, t1, inv1, f2, t2, inv2, ch, a, slab0, bad);
+            // ordered partition of the two steps' updates into the segment's slab regions
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                int pos = 0;
+#pragma unroll
+                for (int s = 0; s < kMaxSlots; s++) {
+                    if (s < ns) {
+                        const unsigned m = __ballot_sync(kFull, e[h].slot == s);
+                        if (e[h].slot == s) pos = c[s] + __popc(m & lt);
+                        c[s] += __popc(m);
                     }
                 }
-            }
-            // ordered partition of this step's updates into the segment's slab regions
-            int pos = 0;
-#pragma unroll
-            for (int s = 0; s < kMaxSlots; s++) {
-                if (s < ns) {
-                    const unsigned m = __ballot_sync(kFull, slot == s);
-                    if (slot == s) pos = c[s] + __popc(m & lt);
-                    c[s] += __popc(m);
+                if (e[h].slot >= 0) {
+                    UpdateRec rec;
+                    rec.cell = e[h].cell; rec.pad = e[h].local; rec.val = e[h].val;
+                    reg[(long long)e[h].slot * Y + pos] = rec;
                 }
-            }
-            if (slot >= 0) {
-                UpdateRec rec;
-                rec.cell = cell; rec.pad = local; rec.val = val;
-                reg[(long long)slot * Y + pos] = rec;
             }
         }
         if (lane < ns) {
             int v = c[0];
 #pragma unroll
             for (int s = 1; s < kMaxSlots; s++) if (lane == s) v = c[s];
-            a.cnt[(((size_t)n * nb + j) * W + d) * ns + lane] = v;
+            const int slab = slab0 + lane;
+            if (v > 0 && slab < a.n_slabs) {
+                // region directory of task (n, slab): entry (j, d - dlo(slab)); empty entries stay zero
+                RegionEnt ent;
+                ent.base = seg * ns + (long long)lane * Y;
+                ent.cnt = v; ent.pad = 0;
+                a.regions[(((size_t)n * a.n_slabs + slab) * (nb - 1) + j) * a.nd_max + (d - a.slabs[slab].dlo)] = ent;
+            }
         }
     }
     if (bad) atomicOr(a.err, bad);
@@ -688,8 +710,7 @@ __global__ void __launch_bounds__(64) k_commit_ordered(const CommitArgs a) {
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kStages * kStageRecs * sizeof(UpdateRec));
     uint64_t *empty = full + kStages;
     int *stage_cnt = reinterpret_cast<int *>(empty + kStages);                         // [kStages]
-    int *meta_c = stage_cnt + kStages;                                                 // [32]
-    long long *meta_base = reinterpret_cast<long long *>(meta_c + 32 + 2);             // [32] (8-byte aligned)
+    RegionEnt *dir = reinterpret_cast<RegionEnt *>(smem_raw + 6144 + 256);              // [32] staged directory entries
     double *tile = reinterpret_cast<double *>(smem_raw + 6144 + 1024);                 // ring 6 KB + 1 KB control
     const int lane = lane_id();
     const int wid = warp_id();
@@ -707,61 +728,46 @@ __global__ void __launch_bounds__(64) k_commit_ordered(const CommitArgs a) {
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (TILE_SMEM) {
-        for (int idx = threadIdx.x; idx < P * sbw; idx += blockDim.x) {
-            const int row = idx / sbw, off = idx - row * sbw;
-            tile[idx] = tens[(size_t)row * G + boff + off];
+        if (a.tensor_is_zero) {
+            for (int idx = threadIdx.x; idx < P * sbw; idx += blockDim.x) tile[idx] = 0.0;
+        } else {
+            for (int idx = threadIdx.x; idx < P * sbw; idx += blockDim.x) {
+                const int row = idx / sbw, off = idx - row * sbw;
+                tile[idx] = tens[(size_t)row * G + boff + off];
+            }
         }
     }
     __syncthreads();
 
     if (wid == 1) {
         // ------------------------------ producer ------------------------------
-        const int phys = a.phys_of[n];
-        const ChromPrep &cp = a.cp;
-        const int nb = cp.nb, W = cp.W, ns = a.n_slots;
-        const int32_t *T = cp.t + (size_t)phys * nb;
-        const long long *RO = cp.rowoff + (size_t)phys * (nb + 1);
-        const long long pb = a.pair_base[n];
-        const int nd = sl.dhi - sl.dlo + 1;                    // <= 32 (engine guarantees)
-        const int my_d = sl.dlo + lane;
-        const int my_slot = (lane < nd) ? slab_i - a.first_slab[my_d] : 0;
-        auto load_row = [&](int j, int &c, long long &base) {
-            c = 0; base = 0;
-            if (j < nb - 1 && lane < nd) {
-                const int t1 = T[j];
-                int dmax = W - 1;
-                if (nb - 1 - j < dmax) dmax = nb - 1 - j;
-                if (t1 > 0 && my_d <= dmax) {
-                    const int32_t *yo = cp.yoff + ((size_t)phys * nb + j) * W;
-                    const int y0 = yo[my_d - 1], Y = yo[my_d] - y0;
-                    if (Y > 0) {
-                        c = a.cnt[(((size_t)n * nb + j) * W + my_d) * ns + my_slot];
-                        base = (pb + RO[j] + y0) * ns + (long long)my_slot * Y;
-                    }
-                }
-            }
-        };
+        const long long n_ent = (long long)(a.cp.nb - 1) * a.nd_max;
+        const RegionEnt *ents = a.regions + ((size_t)n * a.n_slabs + slab_i) * n_ent;
         int stage = 0;
         unsigned phase = 0;
-        int c_cur, c_nxt;
-        long long b_cur, b_nxt;
-        load_row(0, c_cur, b_cur);
-        for (int j = 0; j < nb - 1; j++) {
-            load_row(j + 1, c_nxt, b_nxt);                 // in flight while row j is being issued
-            if (__any_sync(kFull, c_cur > 0)) {
-                meta_c[lane] = c_cur;
-                meta_base[lane] = b_cur;
+        RegionEnt cur, nxt;
+        cur.base = 0; cur.cnt = 0; cur.pad = 0;
+        if (lane < n_ent) cur = ents[lane];
+        for (long long e0 = 0; e0 < n_ent; e0 += 32) {
+            nxt.base = 0; nxt.cnt = 0; nxt.pad = 0;
+            if (e0 + 32 + lane < n_ent) nxt = ents[e0 + 32 + lane];     // in flight while this batch is issued
+            const unsigned live = __ballot_sync(kFull, cur.cnt > 0);
+            if (live) {
+                dir[lane] = cur;
                 __syncwarp();
                 if (lane == 0) {
-                    for (int i = 0; i < nd; i++) {
-                        const int c = meta_c[i];
-                        const long long base = meta_base[i];
+                    unsigned m = live;
+                    while (m) {
+                        const int i = __ffs(m) - 1;
+                        m &= m - 1;
+                        const int c = dir[i].cnt;
+                        const UpdateRec *src = a.recs + dir[i].base;
                         for (int off = 0; off < c; off += kStageRecs) {
                             const int cnt_here = c - off < kStageRecs ? c - off : kStageRecs;
                             mbar_wait(&empty[stage], phase ^ 1);
                             stage_cnt[stage] = cnt_here;
                             mbar_arrive_expect_tx(&full[stage], (unsigned)cnt_here * (unsigned)sizeof(UpdateRec));
-                            bulk_g2s(&ring[stage * kStageRecs], a.recs + base + off, (unsigned)cnt_here * (unsigned)sizeof(UpdateRec),
+                            bulk_g2s(&ring[stage * kStageRecs], src + off, (unsigned)cnt_here * (unsigned)sizeof(UpdateRec),
                                      &full[stage]);
                             if (++stage == kStages) { stage = 0; phase ^= 1; }
                         }
@@ -769,7 +775,7 @@ __global__ void __launch_bounds__(64) k_commit_ordered(const CommitArgs a) {
                 }
                 __syncwarp();
             }
-            c_cur = c_nxt; b_cur = b_nxt;
+            cur = nxt;
         }
         if (lane == 0) {                                   // end marker
             mbar_wait(&empty[stage], phase ^ 1);
@@ -781,21 +787,28 @@ __global__ void __launch_bounds__(64) k_commit_ordered(const CommitArgs a) {
         int stage = 0;
         unsigned phase = 0;
         unsigned long long n_acc = 0;
+        const unsigned lt = (1u << lane) - 1;
         while (true) {
             mbar_wait(&full[stage], phase);
             const int c = stage_cnt[stage];
             if (c < 0) break;
-            for (int off = 0; off < c; off += 32) {
-                int cell = -1;
-                double val = 0.0;
-                if (off + lane < c) {
-                    const UpdateRec r = ring[stage * kStageRecs + off + lane];
-                    cell = TILE_SMEM ? r.pad : r.cell;
-                    val = r.val;
-                }
-                const unsigned key = cell >= 0 ? (unsigned)cell : (0x80000000u | (unsigned)lane);
-                const unsigned grp = __match_any_sync(kFull, key);
-                const bool leader = (cell >= 0) && ((grp & ((1u << lane) - 1)) == 0);
+            // a stage holds up to two steps of 32 records: stage both, match both, then fold in order
+            int cell0 = -1, cell1 = -1;
+            double val0 = 0.0, val1 = 0.0;
+            const UpdateRec *rg = ring + stage * kStageRecs;
+            if (lane < c) { const UpdateRec r = rg[lane]; cell0 = TILE_SMEM ? r.pad : r.cell; val0 = r.val; }
+            if (32 + lane < c) { const UpdateRec r = rg[32 + lane]; cell1 = TILE_SMEM ? r.pad : r.cell; val1 = r.val; }
+            const unsigned g0 = __match_any_sync(kFull, cell0 >= 0 ? (unsigned)cell0 : (0x80000000u | (unsigned)lane));
+            const unsigned g1 = __match_any_sync(kFull, cell1 >= 0 ? (unsigned)cell1 : (0x80000000u | (unsigned)lane));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);     // records are in registers: the stage can be refilled
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int cell = h ? cell1 : cell0;
+                const double val = h ? val1 : val0;
+                const unsigned grp = h ? g1 : g0;
+                if (h == 1 && c <= 32) break;
+                const bool leader = (cell >= 0) && ((grp & lt) == 0);
                 double acc = 0.0;
                 if (leader) acc = TILE_SMEM ? tile[cell] : tens[cell];
                 unsigned rest = leader ? (grp & ~(1u << lane)) : 0u;
@@ -809,7 +822,6 @@ __global__ void __launch_bounds__(64) k_commit_ordered(const CommitArgs a) {
                 __syncwarp();
             }
             n_acc += (unsigned long long)c;
-            if (lane == 0) mbar_arrive(&empty[stage]);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         if (lane == 0 && n_acc) atomicAdd(a.accepted, n_acc);

@@ -55,6 +55,8 @@ struct AccumArgs {
 // per (individual, slab) fold the records of its slab in the reference's order.
 struct __align__(16) UpdateRec { int32_t cell; int32_t pad; double val; };   // cell: index in the individual's tensor; pad: index in the slab tile
 
+struct __align__(16) RegionEnt { long long base; int32_t cnt; int32_t pad; };   // one record region: first record, count
+
 constexpr int kMaxSlots = 4;   // slabs a coarse-bin separation can reach (regions per segment)
 
 struct EvalArgs {
@@ -69,7 +71,9 @@ struct EvalArgs {
     const int32_t *slab_w;        // [n_slabs] width of each slab in bins
     const int32_t *slab_b0;       // [n_slabs] first bin (relative to grid_start) of each slab
     UpdateRec *recs;              // [(pairs) * n_slots]: segment (n,j,d) owns n_slots regions of Y records each
-    int32_t *cnt;                 // [N][nb][W][n_slots] records filed per region
+    RegionEnt *regions;           // [N*n_slabs][nb-1][nd_max] region directory, slab-major (zero = empty)
+    const SlabDesc *slabs;
+    int32_t n_slabs, nd_max;
     int *err;
 };
 
@@ -79,9 +83,9 @@ struct CommitArgs {
     const int32_t *phys_of;
     int32_t N, K, G, grid_start, n_slots, n_slabs;
     const SlabDesc *slabs;        // dlo/dhi = separations whose reach includes the slab
-    const int32_t *first_slab;
     const UpdateRec *recs;
-    const int32_t *cnt;
+    const RegionEnt *regions;
+    int32_t nd_max, tensor_is_zero;
     double *tensor;
     unsigned long long *accepted;
 };
