@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 namespace fgt {
 
@@ -548,6 +549,7 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
             ca.slabs = d_slabs; ca.recs = d_recs; ca.regions = d_regions; ca.nd_max = nd_max;
             ca.tensor_is_zero = (tensor_zero && tile_in_smem) ? 1 : 0;
             ca.tensor = d_tensor; ca.accepted = d_acc;
+            ca.dbg = getenv("FGT_COMMIT_DBG") ? atoi(getenv("FGT_COMMIT_DBG")) : 0;   // timing experiments only
             launch_commit_ordered(ca, plan_max_w, st_);
             tensor_zero = false;
             launches_ += 2;

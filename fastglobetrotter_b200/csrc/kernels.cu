@@ -52,14 +52,52 @@ __device__ __forceinline__ int block_flag_scan(bool flag, int *warp_tot, int &to
 //    reference C:446-455 (count), C:487-510 (locate), same code in mode 3 and the NULL path.
 //    Fast path (weight_min < 1): every label change opens a chunk.
 // =============================================================================================
+// Eight consecutive labels per thread.  For 16-bit labels the eight come from one 16-byte load of
+// the flat label matrix (groups are aligned in the flat index space, rows may start anywhere).
+template <typename T> struct Lab8 { T v[8]; };
+
+template <typename T>
+__device__ __forceinline__ void load8(const T *__restrict__ flat, long long g0, long long lo, long long hi, Lab8<T> &out) {
+    // elements [g0, g0+8) of the flat matrix, clipped to the row [lo, hi)
+    if (sizeof(T) == 2 && g0 >= lo && g0 + 8 <= hi) {
+        const uint4 w = *reinterpret_cast<const uint4 *>(flat + g0);
+        const unsigned ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int e = 0; e < 8; e++) out.v[e] = (T)((ww[e >> 1] >> ((e & 1) * 16)) & 0xffffu);
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; e++) out.v[e] = (g0 + e >= lo && g0 + e < hi) ? flat[g0 + e] : (T)0;
+    }
+}
+
+// bit e of the result: element g0+e is inside the row, is not its first element, and differs from its predecessor
+template <typename T>
+__device__ __forceinline__ unsigned change_mask(const T *__restrict__ flat, long long g0, long long lo, long long hi,
+                                                const Lab8<T> &x) {
+    unsigned m = 0;
+    T prev = (g0 - 1 >= lo && g0 - 1 < hi) ? flat[g0 - 1] : (T)0;
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        const long long g = g0 + e;
+        if (g > lo && g < hi && x.v[e] != prev) m |= 1u << e;
+        prev = x.v[e];
+    }
+    return m;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) k_chunk_count(const T *__restrict__ labels, const int32_t *__restrict__ rowmap, int L,
                                                      int rows, int32_t *__restrict__ counts) {
     __shared__ int wtot[8];
     for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-        const T *lab = labels + (size_t)(rowmap ? rowmap[row] : row) * L;
+        const long long lo = (long long)(rowmap ? rowmap[row] : row) * L, hi = lo + L;
+        const long long a0 = lo & ~7LL;
         int c = 0;
-        for (int j = 1 + threadIdx.x; j < L; j += blockDim.x) c += (lab[j] != lab[j - 1]);
+        for (long long g0 = a0 + 8LL * threadIdx.x; g0 < hi; g0 += 8LL * blockDim.x) {
+            Lab8<T> x;
+            load8(labels, g0, lo, hi, x);
+            c += __popc(change_mask(labels, g0, lo, hi, x));
+        }
         c = warp_sum(c);
         if (lane_id() == 0) wtot[warp_id()] = c;
         __syncthreads();
@@ -77,33 +115,50 @@ __global__ void __launch_bounds__(256) k_chunk_emit(const T *__restrict__ labels
                                                     int rows, const int32_t *__restrict__ row_off, const double *__restrict__ cum,
                                                     const double *__restrict__ inc, double *__restrict__ cstart,
                                                     double *__restrict__ cend, int32_t *__restrict__ chap) {
-    __shared__ int wtot[32];
+    __shared__ int wtot[8];
+    __shared__ int running_s;
     for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-        const T *lab = labels + (size_t)(rowmap ? rowmap[row] : row) * L;
+        const long long lo = (long long)(rowmap ? rowmap[row] : row) * L, hi = lo + L;
+        const long long a0 = lo & ~7LL;
         const int base = row_off[row];
         if (threadIdx.x == 0) {
             cstart[base] = 0.0;
-            chap[base] = (int32_t)lab[0];
+            chap[base] = (int32_t)labels[lo];
             cend[row_off[row + 1] - 1] = cum[L - 1];
-        }
-        int running = 0;
-        for (int t0 = 1; t0 < L; t0 += blockDim.x) {
-            int j = t0 + threadIdx.x;
-            T cur = 0;
-            bool flag = false;
-            if (j < L) { cur = lab[j]; flag = cur != lab[j - 1]; }
-            int tot;
-            int ex = block_flag_scan(flag, wtot, tot);
-            if (flag) {
-                int c = base + running + ex + 1;
-                double cj = cum[j];
-                cstart[c] = cj;
-                chap[c] = (int32_t)cur;
-                cend[c - 1] = __dsub_rn(cj, inc[j]);   // reference C:501: cursor minus the same increment
-            }
-            running += tot;
+            running_s = 0;
         }
         __syncthreads();
+        for (long long t0 = a0; t0 < hi; t0 += 8LL * blockDim.x) {
+            const long long g0 = t0 + 8LL * threadIdx.x;
+            Lab8<T> x;
+            unsigned m = 0;
+            if (g0 < hi) { load8(labels, g0, lo, hi, x); m = change_mask(labels, g0, lo, hi, x); }
+            const int mine = __popc(m);
+            int inc_scan = mine;                           // inclusive warp scan of per-thread boundary counts
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int y = __shfl_up_sync(kFull, inc_scan, o);
+                if (lane_id() >= o) inc_scan += y;
+            }
+            if (lane_id() == 31) wtot[warp_id()] = inc_scan;
+            __syncthreads();
+            int wbase = running_s, tot = 0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); w++) { if (w < warp_id()) wbase += wtot[w]; tot += wtot[w]; }
+            int c = base + wbase + inc_scan - mine;        // chunks opened before this thread's first boundary
+            while (m) {
+                const int e = __ffs(m) - 1;
+                m &= m - 1;
+                c++;
+                const int j = (int)(g0 + e - lo);
+                const double cj = cum[j];
+                cstart[c] = cj;
+                chap[c] = (int32_t)x.v[e];
+                cend[c - 1] = __dsub_rn(cj, inc[j]);       // reference C:501: cursor minus the same increment
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) running_s += tot;
+            __syncthreads();
+        }
     }
 }
 
@@ -367,8 +422,6 @@ k_rand_fill(const uint32_t *__restrict__ base_hist, const uint32_t *__restrict__
     if (threadIdx.x == 0)
         for (int m = 0; m < kLag - 1; m++) y[kLag + m] = y[m] + y[m + kTap];
     __syncthreads();
-    long long tglob = (long long)blk * 256 + threadIdx.x;
-    if (tglob >= n_threads) return;
     uint32_t yy[2 * kLag - 1];
 #pragma unroll
     for (int i = 0; i < 2 * kLag - 1; i++) yy[i] = y[i];
@@ -381,21 +434,42 @@ k_rand_fill(const uint32_t *__restrict__ base_hist, const uint32_t *__restrict__
 #pragma unroll
         for (int j = 0; j < kLag; j++) s[j] += c * yy[i + j];
     }
-    uint4 *dst = reinterpret_cast<uint4 *>(out + tglob * (long long)kRun);
+    // Each thread owns a contiguous run of the stream, so its stores would be 32 scattered sectors per
+    // instruction.  Four octets (128 B) per thread are staged in shared memory (XOR-swizzled 16-byte
+    // blocks, conflict free) and flushed as whole 128-byte lines: 8 lanes per line, 4 lines per store.
+    extern __shared__ __align__(16) uint4 stage_all[];            // [warps][32 rows][8 blocks]
+    uint4 *stg = stage_all + (size_t)warp_id() * 256;
+    const int lane = lane_id();
+    uint4 *grun = reinterpret_cast<uint4 *>(out) + ((long long)blk * 256 + (threadIdx.x & ~31)) * (kRun / 4);
+    // grun: first uint4 of lane 0's run; lane r's run starts r * (kRun/4) uint4 later
+    int flushed = 0;                                               // 128-byte groups already written per thread
 #pragma unroll 1
-    for (int it = 0; it < kRun / (4 * kLag); it++) {
+    for (int it = 0; it < kRun / (8 * kLag); it++) {
 #pragma unroll
-        for (int v = 0; v < kLag; v++) {          // 31 x 4 draws: the rotating index returns to 0
-            uint32_t o[4];
+        for (int v = 0; v < kLag; v++) {                           // 31 octets: the rotating state index returns to 0
+            uint32_t o[8];
 #pragma unroll
-            for (int r = 0; r < 4; r++) {
-                const int i = (4 * v + r) % kLag;
+            for (int r = 0; r < 8; r++) {
+                const int i = (8 * v + r) % kLag;
                 s[i] += s[(i + kTap) % kLag];
                 o[r] = s[i] >> 1;
             }
-            dst[v] = make_uint4(o[0], o[1], o[2], o[3]);
+            const int oct = (it * kLag + v) & 3;                   // position of this octet inside the 128-byte group
+            stg[lane * 8 + ((2 * oct) ^ (lane & 7))] = make_uint4(o[0], o[1], o[2], o[3]);
+            stg[lane * 8 + ((2 * oct + 1) ^ (lane & 7))] = make_uint4(o[4], o[5], o[6], o[7]);
+            if (oct == 3) {
+                __syncwarp();
+#pragma unroll
+                for (int i4 = 0; i4 < 8; i4++) {
+                    const int row = 4 * i4 + (lane >> 3), cb = lane & 7;
+                    const uint4 w = stg[row * 8 + (cb ^ (row & 7))];
+                    if ((long long)blk * 256 + (threadIdx.x & ~31) + row < n_threads)
+                        grun[(long long)row * (kRun / 4) + flushed * 8 + cb] = w;
+                }
+                flushed++;
+                __syncwarp();
+            }
         }
-        dst += kLag;
     }
 }
 
@@ -403,7 +477,7 @@ void launch_rand_fill(const uint32_t *base_hist, const uint32_t *level_tab, uint
                       cudaStream_t st) {
     if (n_threads <= 0) return;
     long long blocks = (n_threads + 255) / 256;
-    k_rand_fill<<<(unsigned)blocks, 256, 0, st>>>(base_hist, level_tab, out, n_threads);
+    k_rand_fill<<<(unsigned)blocks, 256, 8 * 256 * sizeof(uint4), st>>>(base_hist, level_tab, out, n_threads);
 }
 
 // =============================================================================================
@@ -798,12 +872,16 @@ __global__ void __launch_bounds__(64) k_commit_ordered(const CommitArgs a) {
             const UpdateRec *rg = ring + stage * kStageRecs;
             if (lane < c) { const UpdateRec r = rg[lane]; cell0 = TILE_SMEM ? r.pad : r.cell; val0 = r.val; }
             if (32 + lane < c) { const UpdateRec r = rg[32 + lane]; cell1 = TILE_SMEM ? r.pad : r.cell; val1 = r.val; }
-            const unsigned g0 = __match_any_sync(kFull, cell0 >= 0 ? (unsigned)cell0 : (0x80000000u | (unsigned)lane));
-            const unsigned g1 = __match_any_sync(kFull, cell1 >= 0 ? (unsigned)cell1 : (0x80000000u | (unsigned)lane));
+            unsigned g0 = 1u << lane, g1 = 1u << lane;
+            if (!(a.dbg & 2)) {
+                g0 = __match_any_sync(kFull, cell0 >= 0 ? (unsigned)cell0 : (0x80000000u | (unsigned)lane));
+                g1 = __match_any_sync(kFull, cell1 >= 0 ? (unsigned)cell1 : (0x80000000u | (unsigned)lane));
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[stage]);     // records are in registers: the stage can be refilled
 #pragma unroll
             for (int h = 0; h < 2; h++) {
+                if (a.dbg & 1) break;
                 const int cell = h ? cell1 : cell0;
                 const double val = h ? val1 : val0;
                 const unsigned grp = h ? g1 : g0;

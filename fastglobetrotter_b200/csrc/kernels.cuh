@@ -85,7 +85,7 @@ struct CommitArgs {
     const SlabDesc *slabs;        // dlo/dhi = separations whose reach includes the slab
     const UpdateRec *recs;
     const RegionEnt *regions;
-    int32_t nd_max, tensor_is_zero;
+    int32_t nd_max, tensor_is_zero, dbg;
     double *tensor;
     unsigned long long *accepted;
 };
