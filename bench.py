@@ -102,7 +102,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from fastglobetrotter_b200 import build as fbuild
-    from fastglobetrotter_b200 import synth
+    from fastglobetrotter_b200 import shard, synth
     from fastglobetrotter_b200.companion import PackedCompanion
     from fastglobetrotter_b200.synth_torch import make_chromosome_device
 
@@ -155,14 +155,12 @@ def run_ours(args):
         cnt = lib.count_pairs_packed(*common, chrom, *tail)                        # [Cn, N] local
         allc = [torch.zeros(cnt.size, dtype=torch.int64, device=dev) for _ in range(world)]
         dist.all_gather(allc, torch.from_numpy(cnt.ravel()).to(dev))                # the one exchange of draw counts
-        allc = torch.stack(allc).cpu().numpy().reshape(world, W["n_chrom"], N)
+        by_rank = [c.cpu().numpy().reshape(W["n_chrom"], N) for c in allc]
         # reference order: chromosome-major, individual-minor; ranks own consecutive blocks of individuals
-        flat = allc.transpose(1, 0, 2).reshape(W["n_chrom"], world * N)
-        offs = np.concatenate([[0], np.cumsum(flat.ravel())])[:-1].reshape(W["n_chrom"], world * N)
-        mine = offs[:, rank * N:(rank + 1) * N]
+        offs, total = shard.stream_offsets(by_rank)
         lib.set_option("reuse_prep", 1)
-        m, _, st = lib.data_read_packed(*common, chrom, *tail, S, tw, num_inds_total=world * N, pair_offset=mine,
-                                        pairs_total=int(flat.sum()))
+        m, _, st = lib.data_read_packed(*common, chrom, *tail, S, tw, num_inds_total=world * N, pair_offset=offs[rank],
+                                        pairs_total=total)
         mt = torch.from_numpy(m).to(dev)
         dist.all_reduce(mt)                                                          # S^2 x G fp64 curves
         return mt.cpu().numpy(), st
@@ -234,7 +232,7 @@ def run_ours(args):
             "means_checksum": float(np.nansum(means)),
         }
         if not args.no_cpu_baseline and world == 1:
-            out["cpu_baseline"] = cpu_baseline(sample_inds=args.cpu_sample_inds, procs=1)
+            out["cpu_baseline"] = cpu_baseline(sample_inds=args.cpu_sample_inds, procs=1, steps=3)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -339,7 +337,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-inds", type=int, default=8)
+    ap.add_argument("--cpu-sample-inds", type=int, default=16)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

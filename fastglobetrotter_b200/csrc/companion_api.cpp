@@ -555,6 +555,38 @@ int fgt_chunk_one(const void *labels, int label_bytes, int nsites, const double 
                                    n_donor_labels, cpos, csize, cweight, cend, cpop);
 }
 
+int fgt_parse_probe(const char *samples_list, const char *recom_list, int ploidy, int n_rec, char **rec_labels,
+                    int32_t *num_chrom, int32_t *nsamples, int32_t *nsites /*[num_chrom]*/, int32_t *rec_index /*[n_rec]*/,
+                    int32_t *label_bytes, uint64_t *label_sum /*[num_chrom]*/, void **labels_out /*[num_chrom] or NULL*/,
+                    double *pos_out /*concatenated or NULL*/, double *rate_out) {
+    // host-only: run the text layer (list files, recombination maps, multithreaded gz decode) and report
+    // what it decoded.  Lets the CPU test suite check the parser without a GPU.
+    if (!samples_list || !recom_list || !num_chrom) return FGT_ERR_ARG;
+    char *sl = const_cast<char *>(samples_list), *rl = const_cast<char *>(recom_list);
+    Loaded L = load_inputs(ploidy, &sl, &rl, n_rec, rec_labels, n_rec);
+    *num_chrom = L.num_chrom;
+    if (nsamples) *nsamples = L.nsamples;
+    if (rec_index) for (int i = 0; i < n_rec; i++) rec_index[i] = L.rec_index[i];
+    size_t off = 0;
+    for (int h = 0; h < L.num_chrom; h++) {
+        PackedFile &pf = *L.files[h];
+        if (nsites) nsites[h] = pf.nsites;
+        if (label_bytes) *label_bytes = pf.label_bytes;
+        uint64_t sum = 0;
+        if (pf.label_bytes == 2) for (uint16_t v : pf.lab16) sum += v;
+        else for (int32_t v : pf.lab32) sum += (uint64_t)(uint32_t)v;
+        if (label_sum) label_sum[h] = sum;
+        if (labels_out && labels_out[h]) {
+            if (pf.label_bytes == 2) std::memcpy(labels_out[h], pf.lab16.data(), pf.lab16.size() * 2);
+            else std::memcpy(labels_out[h], pf.lab32.data(), pf.lab32.size() * 4);
+        }
+        if (pos_out) std::memcpy(pos_out + off, L.maps[h].pos.data(), pf.nsites * sizeof(double));
+        if (rate_out) std::memcpy(rate_out + off, L.maps[h].rate.data(), pf.nsites * sizeof(double));
+        off += pf.nsites;
+    }
+    return FGT_OK;
+}
+
 int fgt_rand_host_jump(unsigned seed, uint64_t n_draws, uint32_t *hist_out) {
     // host-only: history (oldest first) of the glibc stream `n_draws` after srand(seed), by polynomial jump-ahead
     if (!hist_out) return FGT_ERR_ARG;

@@ -150,6 +150,13 @@ int fgt_chunk_one(const void *labels, int label_bytes, int nsites, const double 
                   double weight_min, double cutoff, const int32_t *donor_label_vec, int n_donor_labels,
                   double *cpos, double *csize, double *cweight, double *cend, int32_t *cpop);
 
+/* host-only: run the file layer of the .C entry points (list files, recombination maps, multithreaded
+ * gz decode of the recipients' paintings; reference C:201-275, C:341-445) and report what it decoded.
+ * Fatal input errors exit(1) exactly like data_read.  Output pointers may be NULL. */
+int fgt_parse_probe(const char *samples_list, const char *recom_list, int ploidy, int n_rec, char **rec_labels,
+                    int32_t *num_chrom, int32_t *nsamples, int32_t *nsites, int32_t *rec_index, int32_t *label_bytes,
+                    uint64_t *label_sum, void **labels_out, double *pos_out, double *rate_out);
+
 /* host-only self-test of the jump-ahead arithmetic: the 31-word history (oldest first) of the
  * glibc stream n_draws after srand(seed). */
 int fgt_rand_host_jump(unsigned seed, uint64_t n_draws, uint32_t *hist_out);

@@ -279,3 +279,32 @@ def test_single_phase_kernel_still_exact(lib, oracle, small):
     finally:
         lib.set_option("accum_impl", 2)
     assert np.array_equal(raw_g, raw_o) and np.array_equal(m_g, m_o)
+
+
+def test_golden_vectors_from_the_compiled_reference(lib):
+    """the committed fixtures (tests/golden, generated from the compiled reference with the script next to
+    them): tutorial subset, modes 1 and 3, NULL; synthetic bootstrap case."""
+    import golden_util as gu
+    g = gu.load("tutorial_subset.npz")
+    chrom = gu.tutorial_chrom(g)
+    K, S, G, bw, gs, N = int(g["K"]), int(g["S"]), int(g["G"]), float(g["bw"]), int(g["gs"]), int(g["N"])
+    lib.set_option("rand_libc", 0)
+    for mode in (1, 3):
+        lib.srand(int(g["seed"]))
+        m, raw, st = lib.data_read_packed(mode, 2, 10, chrom, g["ids"], bw, G, gs, K, g["donor_label_vec"], 0.0, 1.0, S,
+                                          g["tw"], want_raw=True)
+        assert st["pairs"] == int(g[f"pairs{mode}"])
+        assert np.array_equal(m, g[f"means{mode}"])
+        gu.assert_matches(g, f"raw{mode}", raw)
+    null, _ = lib.data_read_null_packed(2, 10, chrom, np.arange(N), bw, G, gs, K, g["donor_label_vec"], 0.0, 1.0)
+    gu.assert_matches(g, "null", null)
+    g = gu.load("synth_a.npz")
+    spec, chrom, dl = gu.synth_a_packed()
+    K, S, G, bw, gs = int(g["K"]), int(g["S"]), int(g["G"]), float(g["bw"]), int(g["gs"])
+    lib.srand(int(g["seed"]))
+    m, raw, st = lib.data_read_packed(1, spec.ploidy, spec.nsamples, chrom, g["ids"], bw, G, gs, K, dl, 0.0, 1.0, S, g["tw"],
+                                      want_raw=True)
+    assert st["pairs"] == int(g["pairs1"]) and np.array_equal(m, g["means1"])
+    gu.assert_matches(g, "raw1", raw)
+    null, _ = lib.data_read_null_packed(spec.ploidy, spec.nsamples, chrom, np.arange(spec.n_inds), bw, G, gs, K, dl, 0.0, 1.0)
+    gu.assert_matches(g, "null", null)
