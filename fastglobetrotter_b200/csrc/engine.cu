@@ -58,6 +58,7 @@ int Engine::set_option(const char *key, double v) {
     else if (k == "verbose") opt.verbose = iv;
     else if (k == "reuse_prep") opt.reuse_prep = iv;
     else if (k == "accum_impl") opt.accum_impl = iv;
+    else if (k == "batch_pairs") opt.batch_pairs = v;
     else return FGT_ERR_ARG;
     return FGT_OK;
 }
@@ -74,6 +75,7 @@ double Engine::get_option(const char *key) {
     if (k == "verbose") return opt.verbose;
     if (k == "reuse_prep") return opt.reuse_prep;
     if (k == "accum_impl") return opt.accum_impl;
+    if (k == "batch_pairs") return opt.batch_pairs;
     return NAN;
 }
 
@@ -347,6 +349,11 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
     // ---- pass 1: chunks, coarse bins, sampling schedule of every chromosome ---------------------
     const bool reuse = opt.reuse_prep && (int)chroms_.size() == Cn && !chroms_.empty() && chroms_[0].nb > 0;
     opt.reuse_prep = 0;
+    if (reuse && !count_only) {
+        stx.h2d_bytes += carry_.h2d_bytes; stx.d2h_bytes += carry_.d2h_bytes; stx.chunks += carry_.chunks;
+        launches_ += carry_.kernel_launches;
+    }
+    carry_ = fgt_stats_t{};
     if (!reuse) {
         chroms_.resize(Cn);
         for (int h = 0; h < Cn; h++) {
@@ -381,6 +388,8 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
     }
     if (count_only) {
         for (auto &e : ev) cudaEventDestroy(e);
+        carry_ = stx;                       // a following reuse_prep call accounts for this pass
+        carry_.kernel_launches = launches_;
         return FGT_OK;
     }
     const long long all_pairs = pb.pair_offset ? pb.pairs_total : run;
@@ -400,7 +409,6 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
     double *d_tw = d_tw_.as<double>((size_t)K * K * S * S);
     int32_t *d_pairkh = d_pairkh_.as<int32_t>(P);
     if (!d_tensor || !d_results || !d_tw || !d_pairkh) return FGT_ERR_CUDA;
-    bool tensor_zero = true;      // the commit kernel then starts from zero tiles and overwrites every cell
     CK(cudaMemsetAsync(d_results, 0, (size_t)N * S * S * G * sizeof(double), st_));
     CK(cudaMemcpyAsync(d_tw, pb.temp_weights, (size_t)K * K * S * S * sizeof(double), cudaMemcpyHostToDevice, st_));
     stx.h2d_bytes += (int64_t)K * K * S * S * 8;
@@ -451,40 +459,74 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
     }
     long long *d_pairbase = d_pairbase_.as<long long>((size_t)Cn * N);
     int32_t *d_physof = d_physof_.as<int32_t>((size_t)Cn * N);
-    uint32_t *d_hist = d_hist_.as<uint32_t>((size_t)Cn * kLag);
-    if (!d_slabs || !d_pairbase || !d_physof || !d_hist) return FGT_ERR_CUDA;
+    if (!d_slabs || !d_pairbase || !d_physof) return FGT_ERR_CUDA;
     CK(cudaMemcpyAsync(d_slabs, slabs.data(), slabs.size() * sizeof(SlabDesc), cudaMemcpyHostToDevice, st_));
 
-    // per chromosome: stream window [lo,hi) in pairs, buffer origin (in draws, multiple of 4)
-    std::vector<long long> origin(Cn), nthreads(Cn);
+    // Batches: a chromosome's individuals are processed in blocks whose rand() window and update records
+    // fit a memory budget (the records need 16 B x n_slots per sampled pair).  Individuals of a block are
+    // consecutive in the stream, so one generator launch covers the block.
+    struct Batch { int h, n0, n1; long long nthreads; };
+    std::vector<Batch> batches;
+    const int ns_rec = (impl == 1) ? 0 : plan.n_slots;
+    long long budget_pairs = (long long)opt.batch_pairs;
+    if (budget_pairs <= 0) {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        free_b += d_draws_.cap + d_recs_.cap;                    // our own grow-only buffers are reusable
+        double use = std::min((double)free_b * 0.6, 64e9);
+        budget_pairs = (long long)(use / (8.0 + 16.0 * ns_rec));
+    }
     std::vector<long long> pairbase_rel((size_t)Cn * N);
     std::vector<int32_t> physof((size_t)Cn * N);
-    std::vector<uint32_t> hists((size_t)Cn * kLag);
-    long long max_draws = 0;
+    std::vector<uint32_t> hists;
+    long long max_threads = 0;
+    int max_batch_n = 0;
     for (int h = 0; h < Cn; h++) {
-        long long lo = -1, hi = 0;
-        for (int n = 0; n < N; n++) {
-            long long a0 = pair_abs[(size_t)h * N + n], c0 = chroms_[h].totals[used[h][n]];
-            if (lo < 0 || a0 < lo) lo = a0;
-            hi = std::max(hi, a0 + c0);
-        }
-        long long A4 = (2 * lo) & ~3LL;
-        origin[h] = A4;
-        long long nd = 2 * hi - A4;
-        nthreads[h] = (nd + kRun - 1) / kRun;
-        max_draws = std::max(max_draws, nthreads[h] * (long long)kRun);
-        History hh = apply_jump(poly_pow_E((uint64_t)A4), h0);
-        std::memcpy(&hists[(size_t)h * kLag], hh.x, sizeof hh.x);
-        for (int n = 0; n < N; n++) {
-            pairbase_rel[(size_t)h * N + n] = pair_abs[(size_t)h * N + n] - A4 / 2;
-            physof[(size_t)h * N + n] = used[h][n];
+        int n = 0;
+        while (n < N) {
+            const int n0 = n;
+            long long lo = pair_abs[(size_t)h * N + n0], hi = lo, acc_pairs = 0;
+            while (n < N) {
+                const long long a0 = pair_abs[(size_t)h * N + n], c0 = chroms_[h].totals[used[h][n]];
+                if (n > n0 && acc_pairs + c0 > budget_pairs) break;
+                lo = std::min(lo, a0); hi = std::max(hi, a0 + c0);
+                acc_pairs += c0;
+                n++;
+            }
+            const long long A4 = (2 * lo) & ~3LL;
+            const long long nd = 2 * hi - A4;
+            Batch b{h, n0, n, (nd + kRun - 1) / kRun};
+            batches.push_back(b);
+            max_threads = std::max(max_threads, b.nthreads);
+            max_batch_n = std::max(max_batch_n, n - n0);
+            History hh = apply_jump(poly_pow_E((uint64_t)A4), h0);
+            hists.insert(hists.end(), hh.x, hh.x + kLag);
+            for (int m = n0; m < n; m++) {
+                pairbase_rel[(size_t)h * N + m] = pair_abs[(size_t)h * N + m] - A4 / 2;
+                physof[(size_t)h * N + m] = used[h][m];
+            }
         }
     }
+    uint32_t *d_hist = d_hist_.as<uint32_t>(hists.size());
+    if (!d_hist) return FGT_ERR_CUDA;
     CK(cudaMemcpyAsync(d_pairbase, pairbase_rel.data(), pairbase_rel.size() * sizeof(long long), cudaMemcpyHostToDevice, st_));
     CK(cudaMemcpyAsync(d_physof, physof.data(), physof.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
     CK(cudaMemcpyAsync(d_hist, hists.data(), hists.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st_));
-    uint32_t *d_draws = d_draws_.as<uint32_t>((size_t)max_draws + 4);
+    uint32_t *d_draws = d_draws_.as<uint32_t>((size_t)max_threads * kRun + 4);
     if (!d_draws) return FGT_ERR_CUDA;
+    int nd_max = 1;
+    for (const SlabDesc &s : slabs) nd_max = std::max(nd_max, s.dhi - s.dlo + 1);
+    UpdateRec *d_recs = nullptr;
+    RegionEnt *d_regions = nullptr;
+    size_t max_ent = 0;
+    if (impl != 1) {
+        int max_nb = 0;
+        for (int h = 0; h < Cn; h++) max_nb = std::max(max_nb, chroms_[h].nb);
+        max_ent = (size_t)max_batch_n * slabs.size() * (size_t)std::max(1, max_nb - 1) * nd_max;
+        d_regions = d_cnt_.as<RegionEnt>(max_ent);
+        d_recs = d_recs_.as<UpdateRec>((size_t)(max_threads * (long long)kRun / 2 + 2) * plan.n_slots);
+        if (!d_regions || !d_recs) return FGT_ERR_CUDA;
+    }
 
     const bool want_raw = opt.keep_raw != 0;
     raw_count_ = 0;
@@ -498,72 +540,75 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
 
     CK(cudaEventRecord(ev[2], st_));
     float ms_rand = 0.f, ms_accum = 0.f, ms_proj = 0.f;
-    std::vector<cudaEvent_t> tev;
-    auto mark = [&]() { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st_); tev.push_back(e); };
-    for (int h = 0; h < Cn; h++) {
+    struct Span { cudaEvent_t a, b; int kind; };
+    std::vector<Span> spans;
+    auto span_begin = [&](int kind) { Span s; cudaEventCreate(&s.a); cudaEventCreate(&s.b); s.kind = kind; cudaEventRecord(s.a, st_); spans.push_back(s); };
+    auto span_end = [&]() { cudaEventRecord(spans.back().b, st_); };
+    const size_t tens_per_ind = P * (size_t)G;
+    const int dbg = getenv("FGT_COMMIT_DBG") ? atoi(getenv("FGT_COMMIT_DBG")) : 0;   // timing experiments only
+    for (size_t bi = 0; bi < batches.size(); bi++) {
+        const Batch &b = batches[bi];
+        const int h = b.h, n0 = b.n0, Nb = b.n1 - b.n0;
         ChromState &cs = chroms_[h];
-        mark();
-        launch_rand_fill(d_hist + (size_t)h * kLag, d_level_tab_.as<uint32_t>(level_tab_.size()), d_draws, nthreads[h], st_);
+        span_begin(0);
+        launch_rand_fill(d_hist + bi * kLag, d_level_tab_.as<uint32_t>(level_tab_.size()), d_draws, b.nthreads, st_);
         launches_ += 1;
-        mark();
+        span_end();
+        span_begin(1);
         ChromPrep cpd{};
         cpd.nb = cs.nb; cpd.W = cs.W; cpd.n_phys = n_phys;
         cpd.chunks = (const Chunk *)cs.sorted.p; cpd.chunk_base = (const int32_t *)cs.chunk_base.p;
         cpd.t = (const int32_t *)cs.t.p; cpd.first = (const int32_t *)cs.first.p;
         cpd.yoff = (const int32_t *)cs.yoff.p; cpd.rowoff = (const long long *)cs.rowoff.p;
+        const long long *pbase = d_pairbase + (size_t)h * N + n0;
+        const int32_t *pphys = d_physof + (size_t)h * N + n0;
+        double *tens_b = d_tensor + (size_t)n0 * tens_per_ind;
         if (impl == 1) {
             AccumArgs a{};
             a.cp = cpd;
             a.draws = (const uint2 *)d_draws;
-            a.pair_base = d_pairbase + (size_t)h * N;
-            a.phys_of = d_physof + (size_t)h * N;
-            a.tensor = d_tensor;
-            a.N = N; a.K = K; a.G = G; a.grid_start = pb.grid_start; a.mode = pb.mode;
+            a.pair_base = pbase; a.phys_of = pphys;
+            a.tensor = tens_b;
+            a.N = Nb; a.K = K; a.G = G; a.grid_start = pb.grid_start; a.mode = pb.mode;
             a.bw = pb.binwidth; a.half_bw = pb.binwidth / 2.0;
             a.slabs = d_slabs; a.n_slabs = (int)slabs.size();
             a.accepted = d_acc; a.err = d_err;
             launch_accum_strict(a, st_);
             launches_ += 1;
-            stx.accum_launches += 1;
         } else {
-            int nd_max = 1;
-            for (const SlabDesc &s : slabs) nd_max = std::max(nd_max, s.dhi - s.dlo + 1);
-            size_t n_ent = (size_t)N * slabs.size() * (cs.nb - 1) * nd_max;
-            RegionEnt *d_regions = d_cnt_.as<RegionEnt>(n_ent);
-            UpdateRec *d_recs = d_recs_.as<UpdateRec>((size_t)(nthreads[h] * (long long)kRun / 2 + 2) * plan.n_slots);
-            if (!d_regions || !d_recs) return FGT_ERR_CUDA;
+            const size_t n_ent = (size_t)Nb * slabs.size() * (cs.nb - 1) * nd_max;
             CK(cudaMemsetAsync(d_regions, 0, n_ent * sizeof(RegionEnt), st_));
             EvalArgs ea{};
             ea.cp = cpd; ea.draws = (const uint2 *)d_draws;
-            ea.pair_base = d_pairbase + (size_t)h * N; ea.phys_of = d_physof + (size_t)h * N;
-            ea.N = N; ea.K = K; ea.G = G; ea.grid_start = pb.grid_start; ea.mode = pb.mode; ea.n_slots = plan.n_slots;
+            ea.pair_base = pbase; ea.phys_of = pphys;
+            ea.N = Nb; ea.K = K; ea.G = G; ea.grid_start = pb.grid_start; ea.mode = pb.mode; ea.n_slots = plan.n_slots;
             ea.bw = pb.binwidth; ea.half_bw = pb.binwidth / 2.0;
             ea.slab_of = d_slabof; ea.first_slab = d_firstslab; ea.slab_w = d_slabw; ea.slab_b0 = d_slabb0;
             ea.recs = d_recs; ea.regions = d_regions; ea.slabs = d_slabs; ea.n_slabs = (int)slabs.size(); ea.nd_max = nd_max;
             ea.err = d_err;
             launch_eval_pairs(ea, st_);
             CommitArgs ca{};
-            ca.cp = cpd; ca.pair_base = ea.pair_base; ca.phys_of = ea.phys_of;
-            ca.N = N; ca.K = K; ca.G = G; ca.grid_start = pb.grid_start; ca.n_slots = plan.n_slots;
+            ca.cp = cpd; ca.pair_base = pbase; ca.phys_of = pphys;
+            ca.N = Nb; ca.K = K; ca.G = G; ca.grid_start = pb.grid_start; ca.n_slots = plan.n_slots;
             ca.n_slabs = (int)slabs.size();
             ca.slabs = d_slabs; ca.recs = d_recs; ca.regions = d_regions; ca.nd_max = nd_max;
-            ca.tensor_is_zero = (tensor_zero && tile_in_smem) ? 1 : 0;
-            ca.tensor = d_tensor; ca.accepted = d_acc;
-            ca.dbg = getenv("FGT_COMMIT_DBG") ? atoi(getenv("FGT_COMMIT_DBG")) : 0;   // timing experiments only
+            ca.tensor_is_zero = (tile_in_smem && (pb.mode == 3 || h == 0)) ? 1 : 0;
+            ca.tensor = tens_b; ca.accepted = d_acc;
+            ca.dbg = dbg;
             launch_commit_ordered(ca, plan_max_w, st_);
-            tensor_zero = false;
             launches_ += 2;
-            stx.accum_launches += 1;
         }
-        mark();
-        if (pb.mode == 3) {
+        stx.accum_launches += 1;
+        span_end();
+        const bool last_of_chrom = (bi + 1 == batches.size()) || (batches[bi + 1].h != h);
+        if (pb.mode == 3 && last_of_chrom) {
+            span_begin(2);
             if (want_raw) { launch_expand_raw(d_tensor, N, K, G, d_raw + (size_t)h * N * K * K * G, st_); launches_++; }
             launch_project(d_tensor, N, K, G, S, d_tw, d_pairkh, d_results, st_);
             launches_ += 1;
             if (memset_tensor) CK(cudaMemsetAsync(d_tensor, 0, tens_elems * sizeof(double), st_));
-            tensor_zero = true;
+            span_end();
         }
-        mark();
     }
     CK(cudaEventRecord(ev[3], st_));
     if (pb.mode == 1) {
@@ -597,14 +642,12 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
     // the stream moves on by two draws per sampled pair of the WHOLE call (all shards), C:136-137
     store_history(apply_jump(poly_pow_E(2ULL * (uint64_t)all_pairs), h0));
 
-    for (size_t i = 0; i + 3 < tev.size(); i += 4) {
-        float a1 = 0, a2 = 0, a3 = 0;
-        cudaEventElapsedTime(&a1, tev[i], tev[i + 1]);
-        cudaEventElapsedTime(&a2, tev[i + 1], tev[i + 2]);
-        cudaEventElapsedTime(&a3, tev[i + 2], tev[i + 3]);
-        ms_rand += a1; ms_accum += a2; ms_proj += a3;
+    for (Span &s : spans) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, s.a, s.b);
+        if (s.kind == 0) ms_rand += t; else if (s.kind == 1) ms_accum += t; else ms_proj += t;
+        cudaEventDestroy(s.a); cudaEventDestroy(s.b);
     }
-    for (auto e : tev) cudaEventDestroy(e);
     float tail = 0.f;
     cudaEventElapsedTime(&stx.ms_chunk, ev[0], ev[1]);
     cudaEventElapsedTime(&tail, ev[3], ev[4]);

@@ -36,6 +36,7 @@ struct Options {
     int threads = 0;        // 0 = hardware concurrency
     int verbose = 0;
     int reuse_prep = 0;
+    double batch_pairs = 0; // sampled pairs per batch of individuals (0 = from free device memory)
     int accum_impl = 2;     // 2 = two-phase (evaluate once, ordered commit); 1 = single-phase slab warps     // one-shot: next packed call may reuse the chunk/bin tables of the previous one
 };
 
@@ -83,6 +84,7 @@ class Engine {
     std::vector<double> raw_host_;
     int64_t raw_count_ = 0;
     int launches_ = 0;
+    fgt_stats_t carry_{};
 };
 
 }  // namespace fgt

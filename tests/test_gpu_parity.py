@@ -308,3 +308,27 @@ def test_golden_vectors_from_the_compiled_reference(lib):
     gu.assert_matches(g, "raw1", raw)
     null, _ = lib.data_read_null_packed(spec.ploidy, spec.nsamples, chrom, np.arange(spec.n_inds), bw, G, gs, K, dl, 0.0, 1.0)
     gu.assert_matches(g, "null", null)
+
+
+def test_batched_individuals_match_unbatched(lib, oracle, small):
+    """a tiny pair budget forces several batches of individuals per chromosome (the path that bounds the
+    record memory at biobank scale); results must not change."""
+    sp = small.spec
+    chrom, dl = packed_chrom(small), small.donor_label_vec
+    K, S, G, bw, gs = sp.K, 3, 100, 0.1, 10
+    tw = np.random.default_rng(4).random(K * K * S * S)
+    ids = bootstrap_ids(sp.n_inds, sp.n_chrom, 12)
+    for mode in (1,):
+        oracle.srand(19)
+        m_o, raw_o, pairs = oracle.data_read_packed(mode, sp.ploidy, sp.nsamples, chrom, ids, bw, G, gs, K, dl, 0.0, 1.0, S, tw,
+                                                    want_raw=True)
+        lib.set_option("rand_libc", 0)
+        lib.set_option("batch_pairs", max(1000, pairs // 7))
+        try:
+            lib.srand(19)
+            m_g, raw_g, st = lib.data_read_packed(mode, sp.ploidy, sp.nsamples, chrom, ids, bw, G, gs, K, dl, 0.0, 1.0, S, tw,
+                                                  want_raw=True)
+        finally:
+            lib.set_option("batch_pairs", 0)
+        assert st["accum_launches"] > sp.n_chrom
+        assert np.array_equal(raw_g, raw_o) and np.array_equal(m_g, m_o)
