@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <cstdlib>
 
@@ -59,6 +60,9 @@ int Engine::set_option(const char *key, double v) {
     else if (k == "reuse_prep") opt.reuse_prep = iv;
     else if (k == "accum_impl") opt.accum_impl = iv;
     else if (k == "batch_pairs") opt.batch_pairs = v;
+    else if (k == "blocks") opt.blocks = iv;
+    else if (k == "ranges") opt.ranges = iv;
+    else if (k == "split_ready") opt.split_ready = iv;
     else return FGT_ERR_ARG;
     return FGT_OK;
 }
@@ -76,6 +80,9 @@ double Engine::get_option(const char *key) {
     if (k == "reuse_prep") return opt.reuse_prep;
     if (k == "accum_impl") return opt.accum_impl;
     if (k == "batch_pairs") return opt.batch_pairs;
+    if (k == "blocks") return opt.blocks;
+    if (k == "ranges") return opt.ranges;
+    if (k == "split_ready") return opt.split_ready;
     return NAN;
 }
 
@@ -92,6 +99,9 @@ int Engine::ensure_init() {
     if (opt.device >= n) return FGT_ERR_ARG;
     CK(cudaSetDevice(opt.device));
     if (!st_) CK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+    if (!st_prep_) CK(cudaStreamCreateWithFlags(&st_prep_, cudaStreamNonBlocking));
+    if (!st_copy_) CK(cudaStreamCreateWithFlags(&st_copy_, cudaStreamNonBlocking));
+    if (!st_acc2_) CK(cudaStreamCreateWithFlags(&st_acc2_, cudaStreamNonBlocking));
     if (level_tab_.empty()) level_tab_ = build_level_tables();
     uint32_t *dt = d_level_tab_.as<uint32_t>(level_tab_.size());
     if (!dt) return FGT_ERR_CUDA;
@@ -285,7 +295,7 @@ int Engine::prep_chromosome(const fgt_problem_t &pb, int h, const int32_t *rowma
     int32_t *d_t = cs.t.as<int32_t>((size_t)n_groups * nb), *d_first = cs.first.as<int32_t>((size_t)n_groups * nb);
     int32_t *d_yoff = cs.yoff.as<int32_t>((size_t)n_groups * nb * W);
     long long *d_ro = cs.rowoff.as<long long>((size_t)n_groups * (nb + 1));
-    int32_t *d_cbase = cs.chunk_base.as<int32_t>(n_groups + 1);
+    const Chunk **d_cbase = cs.chunk_ptr.as<const Chunk *>(n_groups + 1);
     size_t cm = (size_t)n_groups * rows_per_ind * nb;
     int32_t *d_cnt = d_cntmat_.as<int32_t>(cm), *d_rf = d_runfirst_.as<int32_t>(cm);
     if (!d_t || !d_first || !d_yoff || !d_ro || !d_cbase || !d_cnt || !d_rf) return FGT_ERR_CUDA;
@@ -321,6 +331,91 @@ static bool resolve_walk(const int32_t *ids, int stride, int N, int n_packed, st
     return true;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Chunk + bin the packed individuals [p0, p1) of chromosome h (data_read path).  Runs on the prep
+// stream; waits for the block's label copy if the paintings come from the host.  Leaves the block's
+// sorted chunks in its own buffer (per-individual pointers in cs.chunk_ptr) and the per-individual
+// pair totals in cs.totals.
+// ---------------------------------------------------------------------------------------------
+int Engine::prep_block(const fgt_problem_t &pb, int h, int p0, int p1, int blk, const void *d_lab, cudaEvent_t copy_done,
+                       ChromState &cs, fgt_stats_t &stx) {
+    const int L = pb.chrom[h].nsites;
+    const int PM = pb.ploidy * pb.nsamples;
+    const int np = p1 - p0, rows = np * PM;
+    const int K = pb.num_donors;
+    cudaStream_t sp = st_prep_;
+    if (copy_done) CK(cudaStreamWaitEvent(sp, copy_done, 0));
+    const char *lab_blk = (const char *)d_lab + (size_t)p0 * PM * L * pb.label_bytes;
+    int32_t *d_counts = d_counts_.as<int32_t>(rows), *d_rowoff = d_rowoff_.as<int32_t>(rows + 1);
+    if (!d_counts || !d_rowoff) return FGT_ERR_CUDA;
+    launch_chunk_count(lab_blk, nullptr, pb.label_bytes, L, rows, pb.weight_min, d_counts, sp);
+    launch_exclusive_scan_i32(d_counts, d_rowoff, rows, sp);
+    launches_ += 2;
+    int32_t total_chunks = 0;
+    CK(cudaMemcpyAsync(&total_chunks, d_rowoff + rows, sizeof(int32_t), cudaMemcpyDeviceToHost, sp));
+    CK(cudaStreamSynchronize(sp));
+    stx.d2h_bytes += 4;
+    if (total_chunks <= 0) return FGT_ERR_ARG;
+    cs.n_chunks += total_chunks;
+    stx.chunks += total_chunks;
+    double *d_cstart = d_cstart_.as<double>(total_chunks), *d_cend = d_cend_.as<double>(total_chunks);
+    int32_t *d_chap = d_chap_.as<int32_t>(total_chunks);
+    if ((int)cs.sorted_blocks.size() <= blk) cs.sorted_blocks.resize(blk + 1);
+    Chunk *d_sorted = cs.sorted_blocks[blk].as<Chunk>(total_chunks);
+    if (!d_cstart || !d_cend || !d_chap || !d_sorted) return FGT_ERR_CUDA;
+    launch_chunk_emit(lab_blk, nullptr, pb.label_bytes, L, rows, pb.weight_min, d_rowoff, (const double *)cs.cum.p,
+                      (const double *)cs.inc.p, d_cstart, d_cend, d_chap, sp);
+    const int nb = cs.nb, W = cs.W;
+    size_t cm = (size_t)np * PM * nb;
+    int32_t *d_cnt = d_cntmat_.as<int32_t>(cm), *d_rf = d_runfirst_.as<int32_t>(cm);
+    if (!d_cnt || !d_rf) return FGT_ERR_CUDA;
+    CK(cudaMemsetAsync(d_cnt, 0, cm * sizeof(int32_t), sp));
+    launch_bin_sort(np, PM, d_rowoff, d_cstart, d_cend, d_chap, (const int32_t *)d_donor_.p, pb.n_donor_labels,
+                    pb.gridweight_max_cutoff, K, pb.mode, nb, W, (const double *)cs.etab.p, pb.mode == 3 ? 8.0 : 10.0, d_sorted,
+                    (const Chunk **)cs.chunk_ptr.p + p0, (int32_t *)cs.t.p + (size_t)p0 * nb, (int32_t *)cs.first.p + (size_t)p0 * nb,
+                    (int32_t *)cs.yoff.p + (size_t)p0 * nb * W, (long long *)cs.rowoff.p + (size_t)p0 * (nb + 1), d_cnt, d_rf,
+                    (int *)d_err_.p, sp);
+    launches_ += 2;
+    CK(cudaMemcpy2DAsync(cs.totals.data() + p0, sizeof(long long), (long long *)cs.rowoff.p + (size_t)p0 * (nb + 1) + nb,
+                         (nb + 1) * sizeof(long long), sizeof(long long), np, cudaMemcpyDeviceToHost, sp));
+    CK(cudaStreamSynchronize(sp));
+    stx.d2h_bytes += (int64_t)np * 8;
+    return FGT_OK;
+}
+
+// per-chromosome tables that do not depend on the paintings: cM prefix, exp table, schedule buffers
+int Engine::setup_chromosome(const fgt_problem_t &pb, int h, ChromState &cs, fgt_stats_t &stx) {
+    const fgt_chrom_t &c = pb.chrom[h];
+    const int L = c.nsites, n_phys = pb.n_packed_inds;
+    if (L <= 0) return FGT_ERR_ARG;
+    std::vector<double> cum(L), inc(L);
+    double total = 0.0;                       // sequential fp64 sum exactly as reference C:494 (increment re-used at C:501)
+    cum[0] = 0.0; inc[0] = 0.0;
+    for (int j = 1; j < L; j++) {
+        double step = c.rate[j - 1] * (c.pos[j] - c.pos[j - 1]) * 100;
+        total = total + step;
+        cum[j] = total; inc[j] = step;
+    }
+    const int nb = (int)cum[L - 1] / 1 + 1;                  // every painting's last chunk ends at cum[L-1] (C:57-68)
+    const int W = (int)std::ceil(pb.binwidth * pb.num_bins) + (pb.mode == 3 ? 1 : 3);   // C:117 / C:1125
+    cs.nb = nb; cs.W = W; cs.n_chunks = 0;
+    std::vector<double> etab(W);
+    for (int d = 0; d < W; d++) etab[d] = std::exp(-0.05 * d);   // exp(-0.05*(k-j)) with the host libm, as C:129
+    double *d_cum = cs.cum.as<double>(L), *d_inc = cs.inc.as<double>(L), *d_etab = cs.etab.as<double>(W);
+    if (!d_cum || !d_inc || !d_etab) return FGT_ERR_CUDA;
+    if (!cs.t.as<int32_t>((size_t)n_phys * nb) || !cs.first.as<int32_t>((size_t)n_phys * nb) ||
+        !cs.yoff.as<int32_t>((size_t)n_phys * nb * W) || !cs.rowoff.as<long long>((size_t)n_phys * (nb + 1)) ||
+        !cs.chunk_ptr.as<const Chunk *>(n_phys))
+        return FGT_ERR_CUDA;
+    cs.totals.assign(n_phys, 0);
+    CK(cudaMemcpyAsync(d_cum, cum.data(), L * sizeof(double), cudaMemcpyHostToDevice, st_prep_));
+    CK(cudaMemcpyAsync(d_inc, inc.data(), L * sizeof(double), cudaMemcpyHostToDevice, st_prep_));
+    CK(cudaMemcpyAsync(d_etab, etab.data(), W * sizeof(double), cudaMemcpyHostToDevice, st_prep_));
+    CK(cudaStreamSynchronize(st_prep_));     // the host vectors die here
+    stx.h2d_bytes += 2LL * L * sizeof(double);
+    return FGT_OK;
+}
+
 int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t *stats, int64_t *count_only) {
     int rc = ensure_init();
     if (rc) return rc;
@@ -331,10 +426,14 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
     CK(cudaSetDevice(opt.device));
     fgt_stats_t stx{};
     launches_ = 0;
-    cudaEvent_t ev[6];
+    cudaEvent_t ev[4];
     for (auto &e : ev) CK(cudaEventCreate(&e));
     CK(cudaEventRecord(ev[0], st_));
 
+    const auto t_start = std::chrono::steady_clock::now();
+    auto tick = [&](const char *what) {
+        if (opt.verbose) fprintf(stderr, "[fgt] %8.3f ms  %s\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(), what);
+    };
     const int N = pb.num_inds, Cn = pb.num_chrom, K = pb.num_donors, G = pb.num_bins, S = pb.num_surrogates;
     const int PM = pb.ploidy * pb.nsamples;
     const int n_phys = pb.n_packed_inds;
@@ -345,263 +444,338 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
     int32_t *d_donor = d_donor_.as<int32_t>(pb.n_donor_labels);
     if (!d_donor) return FGT_ERR_CUDA;
     CK(cudaMemcpyAsync(d_donor, pb.donor_label_vec, pb.n_donor_labels * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
+    CK(cudaStreamSynchronize(st_));       // donor labels / cleared flags are visible to the other streams
+    tick("donor labels up");
 
-    // ---- pass 1: chunks, coarse bins, sampling schedule of every chromosome ---------------------
-    const bool reuse = opt.reuse_prep && (int)chroms_.size() == Cn && !chroms_.empty() && chroms_[0].nb > 0;
+    const bool reuse = opt.reuse_prep && (int)chroms_.size() == Cn && !chroms_.empty() && chroms_[0].nb > 0 &&
+                       (int)chroms_[0].totals.size() == n_phys;
     opt.reuse_prep = 0;
     if (reuse && !count_only) {
         stx.h2d_bytes += carry_.h2d_bytes; stx.d2h_bytes += carry_.d2h_bytes; stx.chunks += carry_.chunks;
         launches_ += carry_.kernel_launches;
     }
     carry_ = fgt_stats_t{};
-    if (!reuse) {
-        chroms_.resize(Cn);
-        for (int h = 0; h < Cn; h++) {
-            rc = prep_chromosome(pb, h, nullptr, n_phys * PM, PM, n_phys, false, chroms_[h], stx);
-            if (rc) return rc;
-        }
-    }
-    CK(cudaEventRecord(ev[1], st_));
-    {
-        int herr[4];
-        CK(cudaMemcpyAsync(herr, d_err, sizeof herr, cudaMemcpyDeviceToHost, st_));
-        CK(cudaStreamSynchronize(st_));
-        if (herr[0] & (kErrMissingDonor | kErrLabelRange)) return err_to_code(herr[0]);
-    }
+    if (!reuse) chroms_.resize(Cn);
 
-    // ---- stream positions -----------------------------------------------------------------------
+    // the walk of every chromosome (which packed individual each pseudo-individual uses)
     std::vector<std::vector<int32_t>> used(Cn);
-    std::vector<long long> pair_abs((size_t)Cn * N);     // absolute pair index (from call entry) of (h,n)
-    long long run = 0, my_pairs = 0;
+    std::vector<char> monotone(Cn, 1);
     for (int h = 0; h < Cn; h++) {
         if (!resolve_walk(pb.ind_rows + h, Cn, N, n_phys, used[h])) {
             fprintf(stderr, "fastGLOBETROTTERCompanion(B200): ind_id_vec walks outside the recipients of the samples file\n");
             return FGT_ERR_ARG;
         }
-        for (int n = 0; n < N; n++) {
-            long long cnt = chroms_[h].totals[used[h][n]];
-            if (count_only) count_only[(size_t)h * N + n] = cnt;
-            pair_abs[(size_t)h * N + n] = pb.pair_offset ? pb.pair_offset[(size_t)h * N + n] : run;
-            run += cnt;
-            my_pairs += cnt;
-        }
+        for (int n = 1; n < N; n++) if (used[h][n] < used[h][n - 1]) monotone[h] = 0;
     }
-    if (count_only) {
-        for (auto &e : ev) cudaEventDestroy(e);
-        carry_ = stx;                       // a following reuse_prep call accounts for this pass
-        carry_.kernel_launches = launches_;
-        return FGT_OK;
-    }
-    const long long all_pairs = pb.pair_offset ? pb.pairs_total : run;
-    stx.pairs = my_pairs;
 
     History h0;
-    if (!fetch_history(h0)) {
+    if (!count_only && !fetch_history(h0)) {
         fprintf(stderr, "fastGLOBETROTTERCompanion(B200): libc rand() is not in its default TYPE_3 state\n");
         return FGT_ERR_RAND;
     }
 
-    // ---- device tables for the accumulation ---------------------------------------------------------
+    tick("walk + rand state");
+    // ---- tables of the accumulation that do not depend on the paintings ---------------------------
     const size_t P = (size_t)K * (K + 1) / 2;
-    const size_t tens_elems = (size_t)N * P * G;
-    double *d_tensor = d_tensor_.as<double>(tens_elems);
-    double *d_results = d_results_.as<double>((size_t)N * S * S * G);
-    double *d_tw = d_tw_.as<double>((size_t)K * K * S * S);
-    int32_t *d_pairkh = d_pairkh_.as<int32_t>(P);
-    if (!d_tensor || !d_results || !d_tw || !d_pairkh) return FGT_ERR_CUDA;
-    CK(cudaMemsetAsync(d_results, 0, (size_t)N * S * S * G * sizeof(double), st_));
-    CK(cudaMemcpyAsync(d_tw, pb.temp_weights, (size_t)K * K * S * S * sizeof(double), cudaMemcpyHostToDevice, st_));
-    stx.h2d_bytes += (int64_t)K * K * S * S * 8;
-    std::vector<int32_t> pairkh(P);
-    {
-        size_t q = 0;
-        for (int k = 0; k < K; k++)
-            for (int hh = k; hh < K; hh++) pairkh[q++] = K * k + hh;
-    }
-    CK(cudaMemcpyAsync(d_pairkh, pairkh.data(), P * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
-    const int W0 = chroms_[0].W;
+    const size_t tens_per_ind = P * (size_t)G;
+    const size_t tens_elems = (size_t)N * tens_per_ind;
+    const int W0 = (int)std::ceil(pb.binwidth * pb.num_bins) + (pb.mode == 3 ? 1 : 3);
     SlabPlan plan;
     std::vector<SlabDesc> slabs;
     int impl = opt.accum_impl;
-    if (impl != 1) {
-        plan = make_slab_plan(G, pb.grid_start, pb.binwidth, W0, N);
-        slabs = plan.slabs;
-        for (const SlabDesc &s : slabs)
-            if (s.dhi - s.dlo + 1 > 32) impl = 1;      // the commit kernel keeps one separation per lane
-        if (plan.n_slots > kMaxSlots) impl = 1;
-    }
-    if (impl == 1) slabs = make_slabs(G, pb.grid_start, pb.binwidth, W0, N);
-    bool tile_in_smem = false;
-    if (impl != 1) {
-        int mw = 1;
-        for (const SlabDesc &s : slabs) mw = std::max(mw, s.b1 - s.b0 + 1);
-        tile_in_smem = commit_tile_bytes(K, mw) + 7168 <= 200 * 1024;
-    }
-    const bool memset_tensor = !tile_in_smem;     // smem tiles start from zero and overwrite every cell
-    if (memset_tensor) CK(cudaMemsetAsync(d_tensor, 0, tens_elems * sizeof(double), st_));
-    SlabDesc *d_slabs = d_slabs_.as<SlabDesc>(slabs.size());
-    int32_t *d_slabof = nullptr, *d_firstslab = nullptr, *d_slabw = nullptr, *d_slabb0 = nullptr;
-    int plan_max_w = 1;
-    if (impl != 1) {
-        d_slabof = d_slabof_.as<int32_t>(G); d_firstslab = d_firstslab_.as<int32_t>(W0);
-        if (!d_slabof || !d_firstslab) return FGT_ERR_CUDA;
-        CK(cudaMemcpyAsync(d_slabof, plan.slab_of.data(), G * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
-        CK(cudaMemcpyAsync(d_firstslab, plan.first_slab.data(), W0 * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
-        std::vector<int32_t> sw(slabs.size()), sb0(slabs.size());
-        for (size_t s = 0; s < slabs.size(); s++) {
-            sw[s] = slabs[s].b1 - slabs[s].b0 + 1; sb0[s] = slabs[s].b0 - pb.grid_start;
-            plan_max_w = std::max(plan_max_w, sw[s]);
-        }
-        d_slabw = d_slabw_.as<int32_t>(slabs.size()); d_slabb0 = d_slabb0_.as<int32_t>(slabs.size());
-        if (!d_slabw || !d_slabb0) return FGT_ERR_CUDA;
-        CK(cudaMemcpyAsync(d_slabw, sw.data(), sw.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
-        CK(cudaMemcpyAsync(d_slabb0, sb0.data(), sb0.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
-    }
-    long long *d_pairbase = d_pairbase_.as<long long>((size_t)Cn * N);
-    int32_t *d_physof = d_physof_.as<int32_t>((size_t)Cn * N);
-    if (!d_slabs || !d_pairbase || !d_physof) return FGT_ERR_CUDA;
-    CK(cudaMemcpyAsync(d_slabs, slabs.data(), slabs.size() * sizeof(SlabDesc), cudaMemcpyHostToDevice, st_));
-
-    // Batches: a chromosome's individuals are processed in blocks whose rand() window and update records
-    // fit a memory budget (the records need 16 B x n_slots per sampled pair).  Individuals of a block are
-    // consecutive in the stream, so one generator launch covers the block.
-    struct Batch { int h, n0, n1; long long nthreads; };
-    std::vector<Batch> batches;
-    const int ns_rec = (impl == 1) ? 0 : plan.n_slots;
-    long long budget_pairs = (long long)opt.batch_pairs;
-    if (budget_pairs <= 0) {
-        size_t free_b = 0, total_b = 0;
-        cudaMemGetInfo(&free_b, &total_b);
-        free_b += d_draws_.cap + d_recs_.cap;                    // our own grow-only buffers are reusable
-        double use = std::min((double)free_b * 0.6, 64e9);
-        budget_pairs = (long long)(use / (8.0 + 16.0 * ns_rec));
-    }
-    std::vector<long long> pairbase_rel((size_t)Cn * N);
-    std::vector<int32_t> physof((size_t)Cn * N);
-    std::vector<uint32_t> hists;
-    long long max_threads = 0;
-    int max_batch_n = 0;
-    for (int h = 0; h < Cn; h++) {
-        int n = 0;
-        while (n < N) {
-            const int n0 = n;
-            long long lo = pair_abs[(size_t)h * N + n0], hi = lo, acc_pairs = 0;
-            while (n < N) {
-                const long long a0 = pair_abs[(size_t)h * N + n], c0 = chroms_[h].totals[used[h][n]];
-                if (n > n0 && acc_pairs + c0 > budget_pairs) break;
-                lo = std::min(lo, a0); hi = std::max(hi, a0 + c0);
-                acc_pairs += c0;
-                n++;
-            }
-            const long long A4 = (2 * lo) & ~3LL;
-            const long long nd = 2 * hi - A4;
-            Batch b{h, n0, n, (nd + kRun - 1) / kRun};
-            batches.push_back(b);
-            max_threads = std::max(max_threads, b.nthreads);
-            max_batch_n = std::max(max_batch_n, n - n0);
-            History hh = apply_jump(poly_pow_E((uint64_t)A4), h0);
-            hists.insert(hists.end(), hh.x, hh.x + kLag);
-            for (int m = n0; m < n; m++) {
-                pairbase_rel[(size_t)h * N + m] = pair_abs[(size_t)h * N + m] - A4 / 2;
-                physof[(size_t)h * N + m] = used[h][m];
-            }
-        }
-    }
-    uint32_t *d_hist = d_hist_.as<uint32_t>(hists.size());
-    if (!d_hist) return FGT_ERR_CUDA;
-    CK(cudaMemcpyAsync(d_pairbase, pairbase_rel.data(), pairbase_rel.size() * sizeof(long long), cudaMemcpyHostToDevice, st_));
-    CK(cudaMemcpyAsync(d_physof, physof.data(), physof.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
-    CK(cudaMemcpyAsync(d_hist, hists.data(), hists.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st_));
-    uint32_t *d_draws = d_draws_.as<uint32_t>((size_t)max_threads * kRun + 4);
-    if (!d_draws) return FGT_ERR_CUDA;
-    int nd_max = 1;
-    for (const SlabDesc &s : slabs) nd_max = std::max(nd_max, s.dhi - s.dlo + 1);
-    UpdateRec *d_recs = nullptr;
-    RegionEnt *d_regions = nullptr;
-    size_t max_ent = 0;
-    if (impl != 1) {
-        int max_nb = 0;
-        for (int h = 0; h < Cn; h++) max_nb = std::max(max_nb, chroms_[h].nb);
-        max_ent = (size_t)max_batch_n * slabs.size() * (size_t)std::max(1, max_nb - 1) * nd_max;
-        d_regions = d_cnt_.as<RegionEnt>(max_ent);
-        d_recs = d_recs_.as<UpdateRec>((size_t)(max_threads * (long long)kRun / 2 + 2) * plan.n_slots);
-        if (!d_regions || !d_recs) return FGT_ERR_CUDA;
-    }
-
+    double *d_tensor = nullptr, *d_results = nullptr, *d_tw = nullptr, *d_raw = nullptr;
+    int32_t *d_pairkh = nullptr, *d_slabof = nullptr, *d_firstslab = nullptr, *d_slabw = nullptr, *d_slabb0 = nullptr;
+    SlabDesc *d_slabs = nullptr;
+    long long *d_pairbase = nullptr;
+    int32_t *d_physof = nullptr;
+    uint32_t *d_hist = nullptr;
+    bool tile_in_smem = false, memset_tensor = true;
+    int plan_max_w = 1, nd_max = 1;
     const bool want_raw = opt.keep_raw != 0;
     raw_count_ = 0;
-    double *d_raw = nullptr;
-    if (want_raw) {
-        size_t slots = (pb.mode == 1) ? (size_t)N : (size_t)N * Cn;
-        d_raw = d_raw_.as<double>(slots * K * K * G);
-        if (!d_raw) return FGT_ERR_CUDA;
-        raw_count_ = (int64_t)slots * K * K * G;
+    if (!count_only) {
+        d_tensor = d_tensor_.as<double>(tens_elems);
+        d_results = d_results_.as<double>((size_t)N * S * S * G);
+        d_tw = d_tw_.as<double>((size_t)K * K * S * S);
+        d_pairkh = d_pairkh_.as<int32_t>(P);
+        if (!d_tensor || !d_results || !d_tw || !d_pairkh) return FGT_ERR_CUDA;
+        CK(cudaMemsetAsync(d_results, 0, (size_t)N * S * S * G * sizeof(double), st_));
+        CK(cudaMemcpyAsync(d_tw, pb.temp_weights, (size_t)K * K * S * S * sizeof(double), cudaMemcpyHostToDevice, st_));
+        stx.h2d_bytes += (int64_t)K * K * S * S * 8;
+        std::vector<int32_t> pairkh(P);
+        size_t q = 0;
+        for (int k = 0; k < K; k++)
+            for (int hh = k; hh < K; hh++) pairkh[q++] = K * k + hh;
+        CK(cudaMemcpyAsync(d_pairkh, pairkh.data(), P * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
+        if (impl != 1) {
+            plan = make_slab_plan(G, pb.grid_start, pb.binwidth, W0, N);
+            slabs = plan.slabs;
+            for (const SlabDesc &s : slabs)
+                if (s.dhi - s.dlo + 1 > 32) impl = 1;      // the commit kernel keeps one separation per lane
+            if (plan.n_slots > kMaxSlots) impl = 1;
+        }
+        if (impl == 1) slabs = make_slabs(G, pb.grid_start, pb.binwidth, W0, N);
+        for (const SlabDesc &s : slabs) {
+            plan_max_w = std::max(plan_max_w, s.b1 - s.b0 + 1);
+            nd_max = std::max(nd_max, s.dhi - s.dlo + 1);
+        }
+        if (impl != 1) tile_in_smem = commit_tile_bytes(K, plan_max_w) + 7168 <= 200 * 1024;
+        memset_tensor = !tile_in_smem;            // smem tiles start from zero and overwrite every cell
+        if (memset_tensor) CK(cudaMemsetAsync(d_tensor, 0, tens_elems * sizeof(double), st_));
+        d_slabs = d_slabs_.as<SlabDesc>(slabs.size());
+        d_pairbase = d_pairbase_.as<long long>((size_t)Cn * N);
+        d_physof = d_physof_.as<int32_t>((size_t)Cn * N);
+        d_hist = d_hist_.as<uint32_t>(((size_t)Cn * N + 1) * kLag);
+        if (!d_slabs || !d_pairbase || !d_physof || !d_hist) return FGT_ERR_CUDA;
+        CK(cudaMemcpyAsync(d_slabs, slabs.data(), slabs.size() * sizeof(SlabDesc), cudaMemcpyHostToDevice, st_));
+        if (impl != 1) {
+            d_slabof = d_slabof_.as<int32_t>(G); d_firstslab = d_firstslab_.as<int32_t>(W0);
+            d_slabw = d_slabw_.as<int32_t>(slabs.size()); d_slabb0 = d_slabb0_.as<int32_t>(slabs.size());
+            if (!d_slabof || !d_firstslab || !d_slabw || !d_slabb0) return FGT_ERR_CUDA;
+            std::vector<int32_t> sw(slabs.size()), sb0(slabs.size());
+            for (size_t s = 0; s < slabs.size(); s++) { sw[s] = slabs[s].b1 - slabs[s].b0 + 1; sb0[s] = slabs[s].b0 - pb.grid_start; }
+            CK(cudaMemcpyAsync(d_slabof, plan.slab_of.data(), G * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
+            CK(cudaMemcpyAsync(d_firstslab, plan.first_slab.data(), W0 * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
+            CK(cudaMemcpyAsync(d_slabw, sw.data(), sw.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
+            CK(cudaMemcpyAsync(d_slabb0, sb0.data(), sb0.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
+        }
+        if (want_raw) {
+            size_t slots = (pb.mode == 1) ? (size_t)N : (size_t)N * Cn;
+            d_raw = d_raw_.as<double>(slots * K * K * G);
+            if (!d_raw) return FGT_ERR_CUDA;
+            raw_count_ = (int64_t)slots * K * K * G;
+        }
     }
+    cudaEvent_t tables_ready = nullptr;
+    if (!count_only) { cudaEventCreateWithFlags(&tables_ready, cudaEventDisableTiming); CK(cudaEventRecord(tables_ready, st_)); }
+    tick("tables uploaded");
+    const int ns_rec = (impl == 1) ? 0 : plan.n_slots;
+    long long budget_pairs = (long long)opt.batch_pairs;
+    if (budget_pairs <= 0 && !count_only) {
+        if (mem_budget_bytes_ <= 0) {                            // cudaMemGetInfo costs milliseconds: ask once
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            free_b += d_draws_.cap + d_recs_.cap;                // our own grow-only buffers are reusable
+            mem_budget_bytes_ = std::min((double)free_b * 0.6, 64e9);
+        }
+        budget_pairs = (long long)(mem_budget_bytes_ / 2 / (8.0 + 16.0 * ns_rec));   // two lanes hold a batch each
+    }
+    const int dbg = getenv("FGT_COMMIT_DBG") ? atoi(getenv("FGT_COMMIT_DBG")) : 0;   // timing experiments only
+    tick("tables ready");
 
-    CK(cudaEventRecord(ev[2], st_));
+    // timing spans on the accumulation stream
     float ms_rand = 0.f, ms_accum = 0.f, ms_proj = 0.f;
     struct Span { cudaEvent_t a, b; int kind; };
     std::vector<Span> spans;
     auto span_begin = [&](int kind) { Span s; cudaEventCreate(&s.a); cudaEventCreate(&s.b); s.kind = kind; cudaEventRecord(s.a, st_); spans.push_back(s); };
     auto span_end = [&]() { cudaEventRecord(spans.back().b, st_); };
-    const size_t tens_per_ind = P * (size_t)G;
-    const int dbg = getenv("FGT_COMMIT_DBG") ? atoi(getenv("FGT_COMMIT_DBG")) : 0;   // timing experiments only
-    for (size_t bi = 0; bi < batches.size(); bi++) {
-        const Batch &b = batches[bi];
-        const int h = b.h, n0 = b.n0, Nb = b.n1 - b.n0;
+
+    // ---- launch the accumulation of pseudo-individuals [n0, n1) of chromosome h -------------------
+    long long run = 0, my_pairs = 0;             // running stream position / pairs of this call
+    size_t hist_used = 0;
+    // per-range tables go through pinned staging (a pageable async copy would make the host wait for the stream)
+    const size_t stage_need = (size_t)Cn * N * (sizeof(long long) + sizeof(int32_t)) + ((size_t)Cn * N + 1) * kLag * sizeof(uint32_t);
+    if (!count_only && pinned_cap_ < stage_need) {
+        if (pinned_) cudaFreeHost(pinned_);
+        pinned_ = nullptr; pinned_cap_ = 0;
+        if (cudaHostAlloc(&pinned_, stage_need + 256, cudaHostAllocDefault) != cudaSuccess) return FGT_ERR_CUDA;
+        pinned_cap_ = stage_need;
+    }
+    long long *pin_pairbase = (long long *)pinned_;
+    int32_t *pin_physof = (int32_t *)(pin_pairbase + (size_t)Cn * N);
+    uint32_t *pin_hist = (uint32_t *)(pin_physof + (size_t)Cn * N);
+    const bool project_per_range = !memset_tensor;   // (a global-memory tensor in mode 3 is cleared per chromosome instead)
+    int lane_rr = 0;                               // ranges alternate between two accumulation lanes (stream + buffers)
+    bool lane_used[2] = {false, false};
+    auto launch_range = [&](int h, int n0, int n1, cudaEvent_t ready) -> int {
         ChromState &cs = chroms_[h];
-        span_begin(0);
-        launch_rand_fill(d_hist + bi * kLag, d_level_tab_.as<uint32_t>(level_tab_.size()), d_draws, b.nthreads, st_);
-        launches_ += 1;
-        span_end();
-        span_begin(1);
-        ChromPrep cpd{};
-        cpd.nb = cs.nb; cpd.W = cs.W; cpd.n_phys = n_phys;
-        cpd.chunks = (const Chunk *)cs.sorted.p; cpd.chunk_base = (const int32_t *)cs.chunk_base.p;
-        cpd.t = (const int32_t *)cs.t.p; cpd.first = (const int32_t *)cs.first.p;
-        cpd.yoff = (const int32_t *)cs.yoff.p; cpd.rowoff = (const long long *)cs.rowoff.p;
-        const long long *pbase = d_pairbase + (size_t)h * N + n0;
-        const int32_t *pphys = d_physof + (size_t)h * N + n0;
-        double *tens_b = d_tensor + (size_t)n0 * tens_per_ind;
-        if (impl == 1) {
-            AccumArgs a{};
-            a.cp = cpd;
-            a.draws = (const uint2 *)d_draws;
-            a.pair_base = pbase; a.phys_of = pphys;
-            a.tensor = tens_b;
-            a.N = Nb; a.K = K; a.G = G; a.grid_start = pb.grid_start; a.mode = pb.mode;
-            a.bw = pb.binwidth; a.half_bw = pb.binwidth / 2.0;
-            a.slabs = d_slabs; a.n_slabs = (int)slabs.size();
-            a.accepted = d_acc; a.err = d_err;
-            launch_accum_strict(a, st_);
+        const int ln = lane_rr;
+        lane_rr ^= 1;
+        lane_used[ln] = true;
+        cudaStream_t st_ = ln ? this->st_acc2_ : this->st_;      // shadows the member inside this lambda
+        DevBuf &d_draws_ = ln ? this->d_draws2_ : this->d_draws_;
+        DevBuf &d_recs_ = ln ? this->d_recs2_ : this->d_recs_;
+        DevBuf &d_cnt_ = ln ? this->d_cnt2_ : this->d_cnt_;
+        auto span_begin = [&](int kind) { Span s; cudaEventCreate(&s.a); cudaEventCreate(&s.b); s.kind = kind; cudaEventRecord(s.a, st_); spans.push_back(s); };
+        auto span_end = [&]() { cudaEventRecord(spans.back().b, st_); };
+        if (ready) CK(cudaStreamWaitEvent(st_, ready, 0));
+        if (tables_ready) CK(cudaStreamWaitEvent(st_, tables_ready, 0));
+        int n = n0;
+        while (n < n1) {
+            const int b0 = n;
+            long long lo = -1, hi = 0, acc_pairs = 0;
+            std::vector<long long> abs_off;
+            while (n < n1) {
+                const long long c0 = cs.totals[used[h][n]];
+                if (n > b0 && acc_pairs + c0 > budget_pairs) break;
+                const long long a0 = pb.pair_offset ? pb.pair_offset[(size_t)h * N + n] : run;
+                run += c0; my_pairs += c0;
+                abs_off.push_back(a0);
+                lo = (lo < 0) ? a0 : std::min(lo, a0);
+                hi = std::max(hi, a0 + c0);
+                acc_pairs += c0;
+                n++;
+            }
+            const int Nb = n - b0;
+            const long long A4 = (2 * lo) & ~3LL;
+            const long long nthreads = (2 * hi - A4 + kRun - 1) / kRun;
+            long long *hp = pin_pairbase + (size_t)h * N + b0;
+            int32_t *hq = pin_physof + (size_t)h * N + b0;
+            for (int m = 0; m < Nb; m++) { hp[m] = abs_off[m] - A4 / 2; hq[m] = used[h][b0 + m]; }
+            History hh = apply_jump(poly_pow_E((uint64_t)A4), h0);
+            uint32_t *dh = d_hist + hist_used * kLag;
+            std::memcpy(pin_hist + hist_used * kLag, hh.x, sizeof hh.x);
+            CK(cudaMemcpyAsync(dh, pin_hist + hist_used * kLag, sizeof hh.x, cudaMemcpyHostToDevice, st_));
+            hist_used++;
+            CK(cudaMemcpyAsync(d_pairbase + (size_t)h * N + b0, hp, Nb * sizeof(long long), cudaMemcpyHostToDevice, st_));
+            CK(cudaMemcpyAsync(d_physof + (size_t)h * N + b0, hq, Nb * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
+            uint32_t *d_draws = d_draws_.as<uint32_t>((size_t)nthreads * kRun + 4);
+            if (!d_draws) return FGT_ERR_CUDA;
+            span_begin(0);
+            launch_rand_fill(dh, (const uint32_t *)d_level_tab_.p, d_draws, nthreads, st_);
             launches_ += 1;
-        } else {
-            const size_t n_ent = (size_t)Nb * slabs.size() * (cs.nb - 1) * nd_max;
-            CK(cudaMemsetAsync(d_regions, 0, n_ent * sizeof(RegionEnt), st_));
-            EvalArgs ea{};
-            ea.cp = cpd; ea.draws = (const uint2 *)d_draws;
-            ea.pair_base = pbase; ea.phys_of = pphys;
-            ea.N = Nb; ea.K = K; ea.G = G; ea.grid_start = pb.grid_start; ea.mode = pb.mode; ea.n_slots = plan.n_slots;
-            ea.bw = pb.binwidth; ea.half_bw = pb.binwidth / 2.0;
-            ea.slab_of = d_slabof; ea.first_slab = d_firstslab; ea.slab_w = d_slabw; ea.slab_b0 = d_slabb0;
-            ea.recs = d_recs; ea.regions = d_regions; ea.slabs = d_slabs; ea.n_slabs = (int)slabs.size(); ea.nd_max = nd_max;
-            ea.err = d_err;
-            launch_eval_pairs(ea, st_);
-            CommitArgs ca{};
-            ca.cp = cpd; ca.pair_base = pbase; ca.phys_of = pphys;
-            ca.N = Nb; ca.K = K; ca.G = G; ca.grid_start = pb.grid_start; ca.n_slots = plan.n_slots;
-            ca.n_slabs = (int)slabs.size();
-            ca.slabs = d_slabs; ca.recs = d_recs; ca.regions = d_regions; ca.nd_max = nd_max;
-            ca.tensor_is_zero = (tile_in_smem && (pb.mode == 3 || h == 0)) ? 1 : 0;
-            ca.tensor = tens_b; ca.accepted = d_acc;
-            ca.dbg = dbg;
-            launch_commit_ordered(ca, plan_max_w, st_);
-            launches_ += 2;
+            span_end();
+            span_begin(1);
+            ChromPrep cpd{};
+            cpd.nb = cs.nb; cpd.W = cs.W; cpd.n_phys = n_phys;
+            cpd.chunk_ptr = (const Chunk *const *)cs.chunk_ptr.p;
+            cpd.t = (const int32_t *)cs.t.p; cpd.first = (const int32_t *)cs.first.p;
+            cpd.yoff = (const int32_t *)cs.yoff.p; cpd.rowoff = (const long long *)cs.rowoff.p;
+            const long long *pbase = d_pairbase + (size_t)h * N + b0;
+            const int32_t *pphys = d_physof + (size_t)h * N + b0;
+            double *tens_b = d_tensor + (size_t)b0 * tens_per_ind;
+            if (impl == 1) {
+                AccumArgs a{};
+                a.cp = cpd;
+                a.draws = (const uint2 *)d_draws;
+                a.pair_base = pbase; a.phys_of = pphys;
+                a.tensor = tens_b;
+                a.N = Nb; a.K = K; a.G = G; a.grid_start = pb.grid_start; a.mode = pb.mode;
+                a.bw = pb.binwidth; a.half_bw = pb.binwidth / 2.0;
+                a.slabs = d_slabs; a.n_slabs = (int)slabs.size();
+                a.accepted = d_acc; a.err = d_err;
+                launch_accum_strict(a, st_);
+                launches_ += 1;
+            } else {
+                const size_t n_ent = (size_t)Nb * slabs.size() * (cs.nb - 1) * nd_max;
+                RegionEnt *d_regions = d_cnt_.as<RegionEnt>(n_ent);
+                UpdateRec *d_recs = d_recs_.as<UpdateRec>((size_t)(nthreads * (long long)kRun / 2 + 2) * plan.n_slots);
+                if (!d_regions || !d_recs) return FGT_ERR_CUDA;
+                CK(cudaMemsetAsync(d_regions, 0, n_ent * sizeof(RegionEnt), st_));
+                EvalArgs ea{};
+                ea.cp = cpd; ea.draws = (const uint2 *)d_draws;
+                ea.pair_base = pbase; ea.phys_of = pphys;
+                ea.N = Nb; ea.K = K; ea.G = G; ea.grid_start = pb.grid_start; ea.mode = pb.mode; ea.n_slots = plan.n_slots;
+                ea.bw = pb.binwidth; ea.half_bw = pb.binwidth / 2.0;
+                ea.slab_of = d_slabof; ea.first_slab = d_firstslab; ea.slab_w = d_slabw; ea.slab_b0 = d_slabb0;
+                ea.recs = d_recs; ea.regions = d_regions; ea.slabs = d_slabs; ea.n_slabs = (int)slabs.size(); ea.nd_max = nd_max;
+                ea.err = d_err;
+                launch_eval_pairs(ea, st_);
+                CommitArgs ca{};
+                ca.cp = cpd; ca.pair_base = pbase; ca.phys_of = pphys;
+                ca.N = Nb; ca.K = K; ca.G = G; ca.grid_start = pb.grid_start; ca.n_slots = plan.n_slots;
+                ca.n_slabs = (int)slabs.size();
+                ca.slabs = d_slabs; ca.recs = d_recs; ca.regions = d_regions; ca.nd_max = nd_max;
+                ca.tensor_is_zero = (tile_in_smem && (pb.mode == 3 || h == 0)) ? 1 : 0;
+                ca.tensor = tens_b; ca.accepted = d_acc;
+                ca.dbg = dbg;
+                launch_commit_ordered(ca, plan_max_w, st_);
+                launches_ += 2;
+            }
+            stx.accum_launches += 1;
+            span_end();
+            if (project_per_range && (pb.mode == 3 || h == Cn - 1) && !want_raw) {
+                // these individuals' tensors are final: project them now, off the tail of the call
+                span_begin(2);
+                launch_project(tens_b, Nb, K, G, S, d_tw, d_pairkh, d_results + (size_t)b0 * S * S * G, st_);
+                launches_ += 1;
+                span_end();
+            }
         }
-        stx.accum_launches += 1;
-        span_end();
-        const bool last_of_chrom = (bi + 1 == batches.size()) || (batches[bi + 1].h != h);
-        if (pb.mode == 3 && last_of_chrom) {
+        return FGT_OK;
+    };
+
+    // ---- chromosomes: blocks of packed individuals flow  copy -> chunk/bin -> accumulate -------------
+    std::vector<cudaEvent_t> evs;
+    auto new_event = [&]() { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); evs.push_back(e); return e; };
+    cudaEvent_t labels_free = nullptr;            // last chunk kernel that read the shared label staging buffer
+    float ms_prep_host = 0.f;
+    for (int h = 0; h < Cn; h++) {
+        ChromState &cs = chroms_[h];
+        if (!reuse) {
+            rc = setup_chromosome(pb, h, cs, stx);
+            if (rc) return rc;
+        }
+        const fgt_chrom_t &c = pb.chrom[h];
+        const size_t bytes_per_ind = (size_t)PM * c.nsites * pb.label_bytes;
+        int n_blocks = 1;
+        if (!reuse) {
+            if (!c.labels_on_device) n_blocks = (int)std::min<size_t>(n_phys, std::max<size_t>(1, (bytes_per_ind * n_phys) / (48u << 20)));
+            else n_blocks = 1;
+            if (opt.blocks > 0) n_blocks = std::min(n_phys, opt.blocks);
+        }
+        const void *d_lab = c.labels;
+        std::vector<cudaEvent_t> copy_done(n_blocks, nullptr);
+        auto blk_lo = [&](int b) { return (int)((long long)n_phys * b / n_blocks); };
+        if (!reuse && !c.labels_on_device) {
+            void *buf = d_labels_.get(bytes_per_ind * n_phys);
+            if (!buf) return FGT_ERR_CUDA;
+            d_lab = buf;
+            if (labels_free) CK(cudaStreamWaitEvent(st_copy_, labels_free, 0));
+            for (int b = 0; b < n_blocks; b++) {
+                const int p0 = blk_lo(b), p1 = blk_lo(b + 1);
+                CK(cudaMemcpyAsync((char *)buf + bytes_per_ind * p0, (const char *)c.labels + bytes_per_ind * p0,
+                                   bytes_per_ind * (p1 - p0), cudaMemcpyHostToDevice, st_copy_));
+                copy_done[b] = new_event();
+                CK(cudaEventRecord(copy_done[b], st_copy_));
+            }
+            stx.h2d_bytes += (int64_t)(bytes_per_ind * n_phys);
+        }
+        int next_n = 0;
+        for (int b = 0; b < n_blocks; b++) {
+            const int p0 = blk_lo(b), p1 = blk_lo(b + 1);
+            cudaEvent_t ready = nullptr;
+            if (!reuse) {
+                rc = prep_block(pb, h, p0, p1, b, d_lab, copy_done[b], cs, stx);
+                if (rc) return rc;
+                tick("block prepared");
+                ready = new_event();
+                CK(cudaEventRecord(ready, st_prep_));
+                if (b == n_blocks - 1) labels_free = ready;
+            }
+            if (count_only) continue;
+            // pseudo-individuals whose packed individual (and all earlier ones in stream order) are ready
+            int n_end = next_n;
+            if (b == n_blocks - 1) n_end = N;
+            else if (monotone[h]) while (n_end < N && used[h][n_end] < p1) n_end++;
+            const int min_range = std::max(1, (N + opt.ranges - 1) / std::max(1, opt.ranges));
+            if (n_end > next_n && (b == n_blocks - 1 || n_end - next_n >= min_range)) {
+                // with everything prepared at once (device-resident paintings) still launch two ranges on the two
+                // lanes: the evaluation of one overlaps the latency-bound ordered commit of the other
+                const int parts = (n_blocks == 1 && opt.split_ready > 1) ? std::min(opt.split_ready, n_end - next_n) : 1;
+                for (int q = 0; q < parts; q++) {
+                    const int a0 = next_n + (int)((long long)(n_end - next_n) * q / parts);
+                    const int a1 = next_n + (int)((long long)(n_end - next_n) * (q + 1) / parts);
+                    rc = launch_range(h, a0, a1, ready);
+                    if (rc) return rc;
+                }
+                tick("range launched");
+                next_n = n_end;
+            }
+        }
+        if (count_only) {
+            for (int n = 0; n < N; n++) count_only[(size_t)h * N + n] = cs.totals[used[h][n]];
+            continue;
+        }
+        if (lane_used[1]) {                      // everything of this chromosome must be in before projecting / moving on
+            cudaEvent_t j = new_event();
+            CK(cudaEventRecord(j, st_acc2_));
+            CK(cudaStreamWaitEvent(st_, j, 0));
+            cudaEvent_t j2 = new_event();
+            CK(cudaEventRecord(j2, st_));
+            CK(cudaStreamWaitEvent(st_acc2_, j2, 0));
+        }
+        if (pb.mode == 3 && !(project_per_range && !want_raw)) {
             span_begin(2);
             if (want_raw) { launch_expand_raw(d_tensor, N, K, G, d_raw + (size_t)h * N * K * K * G, st_); launches_++; }
             launch_project(d_tensor, N, K, G, S, d_tw, d_pairkh, d_results, st_);
@@ -610,8 +784,27 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
             span_end();
         }
     }
-    CK(cudaEventRecord(ev[3], st_));
-    if (pb.mode == 1) {
+    {
+        int herr[4];
+        CK(cudaStreamSynchronize(st_prep_));
+        CK(cudaMemcpy(herr, d_err, sizeof herr, cudaMemcpyDeviceToHost));
+        if (count_only || (herr[0] & (kErrMissingDonor | kErrLabelRange))) {
+            if (count_only) { carry_ = stx; carry_.kernel_launches = launches_; }
+            CK(cudaStreamSynchronize(st_));
+            CK(cudaStreamSynchronize(st_acc2_));
+            for (auto e2 : evs) cudaEventDestroy(e2);
+            for (auto &e2 : ev) cudaEventDestroy(e2);
+            for (Span &s : spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+            if (herr[0]) return err_to_code(herr[0]);
+            return FGT_OK;
+        }
+    }
+    (void)ms_prep_host;
+    const long long all_pairs = pb.pair_offset ? pb.pairs_total : run;
+    stx.pairs = my_pairs;
+
+    CK(cudaEventRecord(ev[1], st_));
+    if (pb.mode == 1 && !(project_per_range && !want_raw)) {
         if (want_raw) { launch_expand_raw(d_tensor, N, K, G, d_raw, st_); launches_++; }
         launch_project(d_tensor, N, K, G, S, d_tw, d_pairkh, d_results, st_);
         launches_ += 1;
@@ -626,7 +819,7 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
     CK(cudaMemcpyAsync(means, d_means, (size_t)S * S * G * sizeof(double), cudaMemcpyDeviceToHost, st_));
     stx.h2d_bytes += (int64_t)S * S * G * 8;
     stx.d2h_bytes += (int64_t)S * S * G * 8;
-    CK(cudaEventRecord(ev[4], st_));
+    CK(cudaEventRecord(ev[2], st_));
     int herr[4];
     unsigned long long hacc[2];
     CK(cudaMemcpyAsync(herr, d_err, sizeof herr, cudaMemcpyDeviceToHost, st_));
@@ -636,7 +829,10 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
         CK(cudaMemcpyAsync(raw_host_.data(), d_raw, raw_count_ * sizeof(double), cudaMemcpyDeviceToHost, st_));
     }
     CK(cudaStreamSynchronize(st_));
+    tick("all done");
     CK(cudaGetLastError());
+    for (auto e2 : evs) cudaEventDestroy(e2);
+    if (tables_ready) cudaEventDestroy(tables_ready);
     if (herr[0]) return err_to_code(herr[0]);
 
     // the stream moves on by two draws per sampled pair of the WHOLE call (all shards), C:136-137
@@ -649,13 +845,13 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
         cudaEventDestroy(s.a); cudaEventDestroy(s.b);
     }
     float tail = 0.f;
-    cudaEventElapsedTime(&stx.ms_chunk, ev[0], ev[1]);
-    cudaEventElapsedTime(&tail, ev[3], ev[4]);
-    cudaEventElapsedTime(&stx.ms_total, ev[0], ev[4]);
+    cudaEventElapsedTime(&tail, ev[1], ev[2]);
+    cudaEventElapsedTime(&stx.ms_total, ev[0], ev[2]);
     stx.ms_rand = ms_rand; stx.ms_accum = ms_accum; stx.ms_project = ms_proj + tail;
+    stx.ms_chunk = stx.ms_total - ms_rand - ms_accum - stx.ms_project;   // what is left: chunking/binning not hidden behind the accumulation
     stx.accepted = (int64_t)hacc[0];
     stx.kernel_launches = launches_;
-    for (auto &e : ev) cudaEventDestroy(e);
+    for (auto &e2 : ev) cudaEventDestroy(e2);
     last_stats = stx;
     if (stats) *stats = stx;
     return FGT_OK;

@@ -20,7 +20,8 @@ struct DevBuf {
 };
 
 struct ChromState {            // per chromosome device state that must outlive the prep pass
-    DevBuf sorted, chunk_base, t, first, yoff, rowoff;
+    DevBuf sorted, chunk_base, t, first, yoff, rowoff, cum, inc, etab, chunk_ptr;
+    std::vector<DevBuf> sorted_blocks;   // data_read path: one sorted-chunk buffer per block of individuals
     int nb = 0, W = 0;
     std::vector<long long> totals;   // [n_phys] pairs each packed individual samples on this chromosome
     long long n_chunks = 0;
@@ -37,6 +38,9 @@ struct Options {
     int verbose = 0;
     int reuse_prep = 0;
     double batch_pairs = 0; // sampled pairs per batch of individuals (0 = from free device memory)
+    int split_ready = 1;    // ranges launched at once when all paintings are already prepared (two lanes overlap)
+    int ranges = 8;         // accumulation launches per chromosome when the paintings stream in from the host
+    int blocks = 0;         // blocks of individuals per chromosome in the copy/chunk/accumulate pipeline (0 = automatic)
     int accum_impl = 2;     // 2 = two-phase (evaluate once, ordered commit); 1 = single-phase slab warps     // one-shot: next packed call may reuse the chunk/bin tables of the previous one
 };
 
@@ -63,6 +67,9 @@ class Engine {
     int ensure_init();
     bool fetch_history(History &h);          // current stream state (libc-coupled or private)
     void store_history(const History &h);
+    int setup_chromosome(const fgt_problem_t &pb, int h, ChromState &cs, fgt_stats_t &stx);
+    int prep_block(const fgt_problem_t &pb, int h, int p0, int p1, int blk, const void *d_lab, cudaEvent_t copy_done,
+                   ChromState &cs, fgt_stats_t &stx);
     int prep_chromosome(const fgt_problem_t &pb, int h, const int32_t *rowmap_dev, int rows, int rows_per_ind,
                         int n_groups, bool for_null, ChromState &cs, fgt_stats_t &stx);
     std::vector<SlabDesc> make_slabs(int G, int grid_start, double bw, int W, int N) const;
@@ -71,7 +78,7 @@ class Engine {
 
     bool inited_ = false;
     int init_rc_ = 0;
-    cudaStream_t st_ = nullptr;
+    cudaStream_t st_ = nullptr, st_prep_ = nullptr, st_copy_ = nullptr, st_acc2_ = nullptr;
     History private_hist_ = seeded_history(1);
     std::vector<uint32_t> level_tab_;
     DevBuf d_level_tab_, d_err_, d_accepted_;
@@ -79,12 +86,15 @@ class Engine {
     DevBuf d_labels_, d_cum_, d_inc_, d_counts_, d_rowoff_, d_cstart_, d_cend_, d_chap_, d_cntmat_, d_runfirst_,
         d_donor_, d_etab_, d_rowmap_;
     DevBuf d_draws_, d_hist_, d_tensor_, d_results_, d_tw_, d_pairkh_, d_slabs_, d_pairbase_, d_physof_, d_rs_,
-        d_ratio_, d_means_, d_raw_, d_totals_, d_recs_, d_cnt_, d_slabof_, d_firstslab_, d_slabw_, d_slabb0_;
+        d_ratio_, d_means_, d_raw_, d_totals_, d_recs_, d_cnt_, d_draws2_, d_recs2_, d_cnt2_, d_slabof_, d_firstslab_, d_slabw_, d_slabb0_;
     std::vector<ChromState> chroms_;
     std::vector<double> raw_host_;
     int64_t raw_count_ = 0;
     int launches_ = 0;
     fgt_stats_t carry_{};
+    double mem_budget_bytes_ = 0;
+    void *pinned_ = nullptr;
+    size_t pinned_cap_ = 0;
 };
 
 }  // namespace fgt

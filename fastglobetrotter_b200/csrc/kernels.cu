@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(256)
 k_bin_sort(int rows_per_ind, const int32_t *__restrict__ row_off, const double *__restrict__ cstart,
            const double *__restrict__ cend, const int32_t *__restrict__ chap, const int32_t *__restrict__ donor_label,
            int n_donor_labels, double cutoff, int K, int mode, int nb, int W, const double *__restrict__ Etab,
-           double divisor, Chunk *__restrict__ sorted, int32_t *__restrict__ chunk_base, int32_t *__restrict__ t_out,
+           double divisor, Chunk *__restrict__ sorted, const Chunk **__restrict__ chunk_ptr, int32_t *__restrict__ t_out,
            int32_t *__restrict__ first_out, int32_t *__restrict__ yoff, long long *__restrict__ rowoff,
            int32_t *__restrict__ cntmat, int32_t *__restrict__ runfirst, int *__restrict__ err) {
     const int p = blockIdx.x;
@@ -294,10 +294,7 @@ k_bin_sort(int rows_per_ind, const int32_t *__restrict__ row_off, const double *
     int32_t *rf = runfirst + (size_t)p * rows_per_ind * nb;
     int32_t *t = t_out + (size_t)p * nb;
     int32_t *first = first_out + (size_t)p * nb;
-    if (threadIdx.x == 0) {
-        chunk_base[p] = c0;
-        if (p == gridDim.x - 1) chunk_base[p + 1] = row_off[r0 + rows_per_ind];
-    }
+    if (threadIdx.x == 0) chunk_ptr[p] = sorted + c0;
     // phase 1: occupancy of (painting, coarse bin); first chunk of each run
     for (int r = 0; r < rows_per_ind; r++) {
         const int a = row_off[r0 + r], b = row_off[r0 + r + 1];
@@ -379,11 +376,11 @@ k_bin_sort(int rows_per_ind, const int32_t *__restrict__ row_off, const double *
 
 void launch_bin_sort(int n_phys, int rows_per_ind, const int32_t *row_off, const double *cstart, const double *cend,
                      const int32_t *chap, const int32_t *donor_label, int n_donor_labels, double cutoff, int K, int mode,
-                     int nb, int W, const double *Etab, double divisor, Chunk *sorted, int32_t *chunk_base, int32_t *t,
+                     int nb, int W, const double *Etab, double divisor, Chunk *sorted, const Chunk **chunk_ptr, int32_t *t,
                      int32_t *first, int32_t *yoff, long long *rowoff, int32_t *cntmat, int32_t *runfirst, int *err,
                      cudaStream_t st) {
     k_bin_sort<<<n_phys, 256, 0, st>>>(rows_per_ind, row_off, cstart, cend, chap, donor_label, n_donor_labels, cutoff, K,
-                                      mode, nb, W, Etab, divisor, sorted, chunk_base, t, first, yoff, rowoff, cntmat,
+                                      mode, nb, W, Etab, divisor, sorted, chunk_ptr, t, first, yoff, rowoff, cntmat,
                                       runfirst, err);
 }
 
@@ -506,7 +503,7 @@ __global__ void __launch_bounds__(128) k_accum_strict(const AccumArgs a) {
     const int32_t *T = cp.t + (size_t)phys * nb;
     const int32_t *F = cp.first + (size_t)phys * nb;
     const long long *RO = cp.rowoff + (size_t)phys * (nb + 1);
-    const Chunk *ch = cp.chunks + cp.chunk_base[phys];
+    const Chunk *ch = cp.chunk_ptr[phys];
     const uint2 *dr = a.draws + a.pair_base[n];
     const int G = a.G, K = a.K;
     double *tens = a.tensor + (size_t)n * ((size_t)K * (K + 1) / 2) * G;
@@ -666,7 +663,7 @@ __global__ void __launch_bounds__(128, 8) k_eval_pairs(const EvalArgs a) {
     if (t1 <= 0) return;
     const int32_t *F = cp.first + (size_t)phys * nb;
     const int32_t *yo = cp.yoff + ((size_t)phys * nb + j) * W;
-    const Chunk *ch = cp.chunks + cp.chunk_base[phys];
+    const Chunk *ch = cp.chunk_ptr[phys];
     const long long row_pair0 = a.pair_base[n] + cp.rowoff[(size_t)phys * (nb + 1) + j];
     const int f1 = F[j];
     const double inv1 = __ddiv_rn(1.0, (double)t1);

@@ -27,8 +27,7 @@ struct ChromPrep {  // per chromosome, per call: everything the accumulation ker
     int32_t nb;             // coarse (1 cM) bins = (int)chr_length + 1   (reference C:67-68)
     int32_t W;              // window_size (reference C:117 / C:1125)
     int32_t n_phys;         // packed individuals
-    const Chunk *chunks;    // coarse-bin-sorted chunks of all individuals
-    const int32_t *chunk_base; // [n_phys+1] first chunk of each individual
+    const Chunk *const *chunk_ptr; // [n_phys] coarse-bin-sorted chunks of each packed individual
     const int32_t *t;       // [n_phys][nb] chunks per coarse bin          (numchunckinbin)
     const int32_t *first;   // [n_phys][nb] exclusive prefix of t          (start_bin)
     const int32_t *yoff;    // [n_phys][nb][W]: yoff[..][d] = sum_{delta=1..d} Y(j, j+delta)
@@ -102,7 +101,7 @@ void launch_chunk_emit(const void *labels, const int32_t *rowmap, int label_byte
                        int32_t *chap, cudaStream_t st);
 void launch_bin_sort(int n_phys, int rows_per_ind, const int32_t *row_off, const double *cstart, const double *cend,
                      const int32_t *chap, const int32_t *donor_label, int n_donor_labels, double cutoff, int K, int mode,
-                     int nb, int W, const double *Etab, double divisor, Chunk *sorted, int32_t *chunk_base, int32_t *t,
+                     int nb, int W, const double *Etab, double divisor, Chunk *sorted, const Chunk **chunk_ptr, int32_t *t,
                      int32_t *first, int32_t *yoff, long long *rowoff, int32_t *cntmat, int32_t *runfirst, int *err,
                      cudaStream_t st);
 void launch_rand_fill(const uint32_t *base_hist, const uint32_t *level_tab, uint32_t *out, long long n_threads,
