@@ -62,6 +62,7 @@ int Engine::set_option(const char *key, double v) {
     else if (k == "batch_pairs") opt.batch_pairs = v;
     else if (k == "blocks") opt.blocks = iv;
     else if (k == "ranges") opt.ranges = iv;
+    else if (k == "null_slab_bins") opt.null_slab_bins = iv;
     else if (k == "split_ready") opt.split_ready = iv;
     else return FGT_ERR_ARG;
     return FGT_OK;
@@ -82,6 +83,7 @@ double Engine::get_option(const char *key) {
     if (k == "batch_pairs") return opt.batch_pairs;
     if (k == "blocks") return opt.blocks;
     if (k == "ranges") return opt.ranges;
+    if (k == "null_slab_bins") return opt.null_slab_bins;
     if (k == "split_ready") return opt.split_ready;
     return NAN;
 }
@@ -767,13 +769,13 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
             for (int n = 0; n < N; n++) count_only[(size_t)h * N + n] = cs.totals[used[h][n]];
             continue;
         }
-        if (lane_used[1]) {                      // everything of this chromosome must be in before projecting / moving on
-            cudaEvent_t j = new_event();
-            CK(cudaEventRecord(j, st_acc2_));
-            CK(cudaStreamWaitEvent(st_, j, 0));
-            cudaEvent_t j2 = new_event();
-            CK(cudaEventRecord(j2, st_));
-            CK(cudaStreamWaitEvent(st_acc2_, j2, 0));
+        {   // chromosomes are folded in order into the same cells: both lanes must have finished this chromosome
+            // before either starts the next one (or the projection)
+            cudaEvent_t ja = new_event(), jb = new_event();
+            CK(cudaEventRecord(ja, st_));
+            CK(cudaEventRecord(jb, st_acc2_));
+            CK(cudaStreamWaitEvent(st_, jb, 0));
+            CK(cudaStreamWaitEvent(st_acc2_, ja, 0));
         }
         if (pb.mode == 3 && !(project_per_range && !want_raw)) {
             span_begin(2);
@@ -914,6 +916,8 @@ int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_ro
             a.lab_off = (const int32_t *)cs.yoff.p;
             a.n_inds = Nc; a.ploidy = P; a.K = K; a.G = G; a.grid_start = pb.grid_start;
             a.bw = pb.binwidth; a.half_bw = pb.binwidth / 2.0; a.out = d_out; a.accepted = d_acc;
+            a.slab_bins = opt.null_slab_bins > 0 ? opt.null_slab_bins : std::max(8, (G + 7) / 8);
+            a.n_slabs = (G + a.slab_bins - 1) / a.slab_bins;
             launch_null_strict(a, st_);
             launches_ += 1;
             stx.accum_launches += 1;

@@ -39,6 +39,7 @@ struct Options {
     int reuse_prep = 0;
     double batch_pairs = 0; // sampled pairs per batch of individuals (0 = from free device memory)
     int split_ready = 1;    // ranges launched at once when all paintings are already prepared (two lanes overlap)
+    int null_slab_bins = 0; // NULL path: bins per slab (0 = G/16)
     int ranges = 8;         // accumulation launches per chromosome when the paintings stream in from the host
     int blocks = 0;         // blocks of individuals per chromosome in the copy/chunk/accumulate pipeline (0 = automatic)
     int accum_impl = 2;     // 2 = two-phase (evaluate once, ordered commit); 1 = single-phase slab warps     // one-shot: next packed call may reuse the chunk/bin tables of the previous one

@@ -1182,17 +1182,84 @@ void launch_null_group(int n_haps, const int32_t *row_off, const double *cstart,
                                                                 cutoff, K, grouped, lab_off, err);
 }
 
-__global__ void __launch_bounds__(32) k_null_strict(const NullArgs a) {
-    extern __shared__ double tile[];      // [G]
-    const int lane = lane_id();
+// One warp per (label of A, label of B, slab of fine bins).  It walks, in the reference's loop order
+// (haplotype pairs, then chunk i of A, then chunk j of B), the chunk pairs that carry its two labels:
+// the B group is staged in shared memory once per haplotype pair, a step compares one A chunk with 32
+// consecutive B chunks (one subtraction and three compares per pair: distance window of the slab and the
+// minimum-distance rule), survivors are queued FIFO in shared memory, and every 32 queued pairs get their
+// exact bin (the reference's rounding rule) and are folded, in order, into the slab's cells.  Splitting each
+// label pair over narrow slabs gives K*K*n_slabs independent ordered folds; since a slab has few cells the
+// fold lets each cell's first lane add its group's values straight from the queue, in lane order.
+constexpr int kNullQ = 64;
+constexpr int kNullStage = 256;   // B chunks staged per haplotype pair (larger groups are read from global memory)
+
+__global__ void __launch_bounds__(128) k_null_strict(const NullArgs a) {
+    extern __shared__ __align__(16) unsigned char nsm[];
+    const int lane = lane_id(), wid = warp_id();
+    const int wpb = blockDim.x >> 5;
     const int K = a.K, G = a.G;
-    const int lA = blockIdx.x / K, lB = blockIdx.x % K;   // 0-based labels
-    double *gout = a.out + ((size_t)lA * K + lB) * G;
-    for (int i = lane; i < G; i += 32) tile[i] = gout[i];
+    const long long task = (long long)blockIdx.x * wpb + wid;
+    const int n_slabs = a.n_slabs;
+    if (task >= (long long)K * K * n_slabs) return;
+    const int slab = (int)(task % n_slabs);
+    const int lab = (int)(task / n_slabs);
+    const int lA = lab / K, lB = lab % K;                  // 0-based labels
+    const int b_lo = slab * a.slab_bins, b_hi = min(G, b_lo + a.slab_bins);   // owned bins (relative to grid_start)
+    const int sbw = b_hi - b_lo;
+    const int per_warp = 3 * kNullStage + 2 * kNullQ + a.slab_bins;            // doubles
+    double *sposB = reinterpret_cast<double *>(nsm) + (size_t)wid * per_warp;
+    double *shalfB = sposB + kNullStage;
+    double *swB = shalfB + kNullStage;
+    double *qdist = swB + kNullStage;
+    double *qval = qdist + kNullQ;
+    double *tile = qval + kNullQ;
+    double *gout = a.out + ((size_t)lA * K + lB) * G + b_lo;
+    for (int i = lane; i < sbw; i += 32) tile[i] = gout[i];
     __syncwarp();
+    // distances that can land in [b_lo, b_hi): a safe superset window for the prefilter
+    const double dwin_lo = ((double)(a.grid_start + b_lo) - 0.5) * a.bw - 1e-9 - a.bw * 1e-6;
+    const double dwin_hi = ((double)(a.grid_start + b_hi - 1) + 0.5) * a.bw + 1e-9 + a.bw * 1e-6;
     const int P = a.ploidy, NH = a.n_inds * P;
     const double bw = a.bw, half_bw = a.half_bw;
+    const unsigned lt = (1u << lane) - 1;
     unsigned long long n_acc = 0;
+    int qn = 0;                                             // queued pairs (uniform)
+    auto fold32 = [&](int cnt) {                           // exact bin + ordered fold of the first cnt (<= 32) queued pairs
+        int cell = -1;
+        double val = 0.0;
+        if (lane < cnt) {
+            const double dist = qdist[lane];
+            const double qd = __ddiv_rn(dist, bw);
+            const double fl = floor(qd);
+            const double frac = __dmul_rn(__dsub_rn(qd, fl), bw);    // reference C:1016-1017
+            int bfull = __double2int_rz(fl);
+            bool ok = true;
+            if (frac <= half_bw) {}
+            else if (frac > half_bw) bfull += 1;
+            else ok = false;
+            const int bb = bfull - a.grid_start;
+            if (ok && bb >= b_lo && bb < b_hi) { cell = bb - b_lo; val = qval[lane]; }
+        }
+        const unsigned grp = __match_any_sync(kFull, cell >= 0 ? (unsigned)cell : (0x80000000u | (unsigned)lane));
+        if (cell >= 0 && (grp & lt) == 0) {                // first lane of the cell: add the group's values in lane order
+            double acc = __dadd_rn(tile[cell], val);
+            unsigned rest = grp & ~(1u << lane);
+            while (rest) {
+                const int src = __ffs(rest) - 1;
+                rest &= rest - 1;
+                acc = __dadd_rn(acc, qval[src]);
+            }
+            tile[cell] = acc;
+        }
+        n_acc += __popc(__ballot_sync(kFull, cell >= 0));
+        __syncwarp();
+        int have = qn - 32;                                // shift the remainder of the queue to the front
+        double md = 0.0, mv = 0.0;
+        if (lane < have) { md = qdist[lane + 32]; mv = qval[lane + 32]; }
+        __syncwarp();
+        if (lane < have) { qdist[lane] = md; qval[lane] = mv; }
+        __syncwarp();
+    };
     for (int hA = 0; hA < (a.n_inds - 1) * P; hA++) {
         const int nA = hA / P;
         const int32_t *oA = a.lab_off + (size_t)hA * (K + 2);
@@ -1204,51 +1271,52 @@ __global__ void __launch_bounds__(32) k_null_strict(const NullArgs a) {
             const int b0 = oB[lB], cntB = oB[lB + 1] - b0;
             if (cntB == 0) continue;
             const Chunk *CB = a.chunks + a.hap_base[hB] + b0;
-            const int tot = cntA * cntB;
-            for (int base = 0; base < tot; base += 32) {
-                const int q = base + lane;
-                int cell = -1;
-                double val = 0.0;
-                if (q < tot) {
-                    const int ia = q / cntB, jb = q - ia * cntB;
-                    const Chunk A = CA[ia], B = CB[jb];
-                    const double d = fabs(__dsub_rn(A.pos, B.pos));
-                    const double qd = __ddiv_rn(d, bw);
-                    const double fl = floor(qd);
-                    const double frac = __dmul_rn(__dsub_rn(qd, fl), bw);
-                    int bfull = __double2int_rz(fl);
-                    bool ok = true;
-                    if (frac <= half_bw) {}
-                    else if (frac > half_bw) bfull += 1;
-                    else ok = false;
-                    const int bb = bfull - a.grid_start;
-                    const double mind = __dadd_rn(__dmul_rn(A.size, 0.5), __dmul_rn(B.size, 0.5));
-                    if (ok && bb >= 0 && bb < G && d >= mind) { cell = bb; val = __dmul_rn(A.w, B.w); }
-                }
-                const unsigned key = cell >= 0 ? (unsigned)cell : (0x80000000u | (unsigned)lane);
-                const unsigned grp = __match_any_sync(kFull, key);
-                const bool leader = (cell >= 0) && ((grp & ((1u << lane) - 1)) == 0);
-                double acc = leader ? tile[cell] : 0.0;
-                unsigned rest = leader ? (grp & ~(1u << lane)) : 0u;
-                acc = __dadd_rn(acc, val);
-                while (__any_sync(kFull, rest != 0)) {
-                    const int src = rest ? (__ffs(rest) - 1) : lane;
-                    const double v = __shfl_sync(kFull, val, src);
-                    if (rest) { acc = __dadd_rn(acc, v); rest &= rest - 1; }
-                }
-                if (leader) tile[cell] = acc;
-                n_acc += (cell >= 0);
+            const bool staged = cntB <= kNullStage;
+            if (staged) {
                 __syncwarp();
+                for (int j = lane; j < cntB; j += 32) {
+                    const Chunk B = CB[j];
+                    sposB[j] = B.pos; shalfB[j] = __dmul_rn(B.size, 0.5); swB[j] = B.w;
+                }
+                __syncwarp();
+            }
+            for (int ia = 0; ia < cntA; ia++) {
+                const Chunk A = CA[ia];                    // same address in every lane: one broadcast load
+                const double halfA = __dmul_rn(A.size, 0.5);
+                for (int jb0 = 0; jb0 < cntB; jb0 += 32) {
+                    const int jb = jb0 + lane;
+                    bool surv = false;
+                    double dist = 0.0, val = 0.0;
+                    if (jb < cntB) {
+                        double pbv, hb, wb;
+                        if (staged) { pbv = sposB[jb]; hb = shalfB[jb]; wb = swB[jb]; }
+                        else { const Chunk B = CB[jb]; pbv = B.pos; hb = __dmul_rn(B.size, 0.5); wb = B.w; }
+                        dist = fabs(__dsub_rn(A.pos, pbv));            // reference C:1015
+                        // C:1019-1020: dist >= size_A/2 + size_B/2 ; and the slab's distance window
+                        surv = dist >= dwin_lo && dist <= dwin_hi && dist >= __dadd_rn(halfA, hb);
+                        val = __dmul_rn(A.w, wb);
+                    }
+                    const unsigned m = __ballot_sync(kFull, surv);
+                    if (m) {
+                        if (surv) { const int pos = qn + __popc(m & lt); qdist[pos] = dist; qval[pos] = val; }
+                        qn += __popc(m);
+                        __syncwarp();
+                        if (qn >= 32) { fold32(32); qn -= 32; }
+                    }
+                }
             }
         }
     }
-    for (int i = lane; i < G; i += 32) gout[i] = tile[i];
-    n_acc = warp_sum_u64(n_acc);
+    if (qn > 0) { fold32(qn); qn = 0; }
+    for (int i = lane; i < sbw; i += 32) gout[i] = tile[i];
     if (lane == 0 && n_acc) atomicAdd(a.accepted, n_acc);
 }
 
 void launch_null_strict(const NullArgs &a, cudaStream_t st) {
-    k_null_strict<<<a.K * a.K, 32, a.G * sizeof(double), st>>>(a);
+    const int wpb = 4;
+    long long tasks = (long long)a.K * a.K * a.n_slabs;
+    size_t smem = (size_t)wpb * (3 * kNullStage + 2 * kNullQ + a.slab_bins) * sizeof(double);
+    k_null_strict<<<(unsigned)((tasks + wpb - 1) / wpb), wpb * 32, smem, st>>>(a);
 }
 
 }  // namespace fgt

@@ -121,6 +121,7 @@ struct NullArgs {
     const int32_t *hap_base;    // [n_haps+1]
     const int32_t *lab_off;     // [n_haps][K+1] offsets (relative to hap_base) of each label group (labels 1..K)
     int32_t n_inds, ploidy, K, G, grid_start;
+    int32_t n_slabs, slab_bins; // every label pair is split over slabs of fine bins (independent ordered folds)
     double bw, half_bw;
     double *out;                // [K][K][G]
     unsigned long long *accepted;

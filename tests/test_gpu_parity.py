@@ -332,3 +332,33 @@ def test_batched_individuals_match_unbatched(lib, oracle, small):
             lib.set_option("batch_pairs", 0)
         assert st["accum_launches"] > sp.n_chrom
         assert np.array_equal(raw_g, raw_o) and np.array_equal(m_g, m_o)
+
+
+def test_pipeline_options_do_not_change_results(lib, oracle, small):
+    """host-resident paintings flow through the copy -> chunk -> accumulate pipeline in blocks; many small
+    blocks/ranges (both accumulation lanes, cross-chromosome ordering) must give the same bits, run twice."""
+    sp = small.spec
+    chrom, dl = packed_chrom(small), small.donor_label_vec
+    K, S, G, bw, gs = sp.K, 3, 100, 0.1, 10
+    tw = np.random.default_rng(6).random(K * K * S * S)
+    ids = ind_id_matrix(sp.n_inds, sp.n_chrom)
+    oracle.srand(23)
+    m_o, raw_o, _ = oracle.data_read_packed(1, sp.ploidy, sp.nsamples, chrom, ids, bw, G, gs, K, dl, 0.0, 1.0, S, tw, want_raw=True)
+    oracle.srand(23)
+    m3_o, _, _ = oracle.data_read_packed(3, sp.ploidy, sp.nsamples, [c for c in chrom], ids, bw, G, gs, K,
+                                         np.where(dl == 0, 1, dl), 0.0, 1.0, S, tw)
+    lib.set_option("rand_libc", 0)
+    try:
+        for blocks, ranges, split in ((6, 6, 1), (3, 2, 1), (1, 1, 3)):
+            lib.set_option("blocks", blocks); lib.set_option("ranges", ranges); lib.set_option("split_ready", split)
+            for rep in range(2):
+                lib.srand(23)
+                m_g, raw_g, st = lib.data_read_packed(1, sp.ploidy, sp.nsamples, chrom, ids, bw, G, gs, K, dl, 0.0, 1.0, S, tw,
+                                                      want_raw=True)
+                assert np.array_equal(raw_g, raw_o) and np.array_equal(m_g, m_o), (blocks, ranges, split, rep)
+                lib.srand(23)
+                m3_g, _, _ = lib.data_read_packed(3, sp.ploidy, sp.nsamples, chrom, ids, bw, G, gs, K, np.where(dl == 0, 1, dl),
+                                                  0.0, 1.0, S, tw)          # no raw: per-range projection path
+                assert np.array_equal(m3_g, m3_o), (blocks, ranges, split, rep, "mode3")
+    finally:
+        lib.set_option("blocks", 0); lib.set_option("ranges", 8); lib.set_option("split_ready", 1)
