@@ -233,6 +233,7 @@ def run_ours(args):
         }
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(sample_inds=args.cpu_sample_inds, procs=1, steps=3)
+            out["file_e2e"] = file_e2e(lib)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -304,6 +305,39 @@ def cpu_baseline(sample_inds=12, procs=1, steps=1):
             "sample": f"{procs} process(es) x {steps} data_read call(s) over {sample_inds} individuals each of the same "
                       f"workload (text .gz inputs, parse included); {pairs} pairs in {busy:.2f} s (wall {wall:.2f} s)",
             "pairs": pairs, "seconds": busy}
+
+
+def file_e2e(lib, n_inds=24):
+    """end-to-end wall time of the R-facing entry point on text/gz inputs of the tutorial's shape (2 chromosomes
+    x 7,000 SNPs, 10 samples, K=26, 291 bins): first call (inflate + tokenise + upload + compute), cached calls,
+    and the compiled reference on the same files."""
+    from fastglobetrotter_b200 import synth
+    from fastglobetrotter_b200.companion import Companion
+    from oracle import build_ref
+    spec = synth.SynthSpec(n_chrom=2, n_inds=n_inds, n_snps=7000, K=26, nsamples=10, rate=60.0 / 7000 / 1000 / 100,
+                           seed=20261019 + 1, name="tut_shape")
+    K, S, G = 26, 7, 291
+    with tempfile.TemporaryDirectory() as tmp:
+        data = synth.write_dataset(spec, tmp)
+        tw = lib.temp_weights_for_data_read(K, S, synth.random_weights(K, S))
+        ids = np.repeat(np.arange(n_inds, dtype=np.int32), 2)
+        args = (2, ids, data.samples_list, data.recom_list, 0.1, G, 10, K, data.donor_label_vec, data.rec_labels, 0.0, 1.0, tw, S)
+        lib.set_option("rand_libc", 1)
+        t0 = time.perf_counter(); lib.coancestry_curves(*args); cold = time.perf_counter() - t0
+        pairs = lib.last_stats()["pairs"]
+        warm = []
+        for _ in range(3):
+            t0 = time.perf_counter(); lib.coancestry_curves(*args); warm.append(time.perf_counter() - t0)
+        t0 = time.perf_counter(); lib.coancestry_curves_null(*args[:1], *args[2:12]); null_s = time.perf_counter() - t0
+        out = {"shape": f"{n_inds} inds x 10 samples, 2 chr x 7000 SNPs, K=26, 291 bins (text .gz)", "pairs_per_call": pairs,
+               "data_read_first_call_ms": cold * 1e3, "data_read_cached_ms": float(np.median(warm)) * 1e3,
+               "data_read_null_ms": null_s * 1e3}
+        if build_ref.build():
+            ref = Companion(build_ref.PRISTINE)
+            t0 = time.perf_counter(); ref.coancestry_curves(*args); out["reference_data_read_ms"] = (time.perf_counter() - t0) * 1e3
+            t0 = time.perf_counter(); ref.coancestry_curves_null(*args[:1], *args[2:12]); out["reference_data_read_null_ms"] = (time.perf_counter() - t0) * 1e3
+        lib.set_option("rand_libc", 0)
+    return out
 
 
 def run_reference(args):
