@@ -103,7 +103,11 @@ int Engine::ensure_init() {
     if (!st_) CK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
     if (!st_prep_) CK(cudaStreamCreateWithFlags(&st_prep_, cudaStreamNonBlocking));
     if (!st_copy_) CK(cudaStreamCreateWithFlags(&st_copy_, cudaStreamNonBlocking));
-    if (!st_acc2_) CK(cudaStreamCreateWithFlags(&st_acc2_, cudaStreamNonBlocking));
+    if (!st_commit_) {
+        int lo_p = 0, hi_p = 0;
+        cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
+        CK(cudaStreamCreateWithPriority(&st_commit_, cudaStreamNonBlocking, hi_p));
+    }
     if (level_tab_.empty()) level_tab_ = build_level_tables();
     uint32_t *dt = d_level_tab_.as<uint32_t>(level_tab_.size());
     if (!dt) return FGT_ERR_CUDA;
@@ -550,6 +554,7 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
     }
     cudaEvent_t tables_ready = nullptr;
     if (!count_only) { cudaEventCreateWithFlags(&tables_ready, cudaEventDisableTiming); CK(cudaEventRecord(tables_ready, st_)); }
+    if (tables_ready) CK(cudaStreamWaitEvent(st_commit_, tables_ready, 0));
     tick("tables uploaded");
     const int ns_rec = (impl == 1) ? 0 : plan.n_slots;
     long long budget_pairs = (long long)opt.batch_pairs;
@@ -569,9 +574,6 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
     float ms_rand = 0.f, ms_accum = 0.f, ms_proj = 0.f;
     struct Span { cudaEvent_t a, b; int kind; };
     std::vector<Span> spans;
-    auto span_begin = [&](int kind) { Span s; cudaEventCreate(&s.a); cudaEventCreate(&s.b); s.kind = kind; cudaEventRecord(s.a, st_); spans.push_back(s); };
-    auto span_end = [&]() { cudaEventRecord(spans.back().b, st_); };
-
     // ---- launch the accumulation of pseudo-individuals [n0, n1) of chromosome h -------------------
     long long run = 0, my_pairs = 0;             // running stream position / pairs of this call
     size_t hist_used = 0;
@@ -586,22 +588,27 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
     long long *pin_pairbase = (long long *)pinned_;
     int32_t *pin_physof = (int32_t *)(pin_pairbase + (size_t)Cn * N);
     uint32_t *pin_hist = (uint32_t *)(pin_physof + (size_t)Cn * N);
+    std::vector<cudaEvent_t> evs;
+    auto new_event = [&]() { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); evs.push_back(e); return e; };
+    auto new_timed_event = [&]() { cudaEvent_t e; cudaEventCreate(&e); evs.push_back(e); return e; };
     const bool project_per_range = !memset_tensor;   // (a global-memory tensor in mode 3 is cleared per chromosome instead)
-    int lane_rr = 0;                               // ranges alternate between two accumulation lanes (stream + buffers)
-    bool lane_used[2] = {false, false};
+    // Two streams: the evaluation stream (rand stream + phase 1) and the high-priority commit stream (phase 2,
+    // projection -- everything that touches the tensors, so chromosomes stay ordered).  Ranges alternate between
+    // two sets of record buffers, so the evaluation of range r+1 overlaps the latency-bound ordered commit of
+    // range r; the commit kernel is persistent (no waiting blocks), which lets the two kernels share the SMs.
+    cudaStream_t sc = st_commit_;
+    auto span_begin = [&](int kind, cudaStream_t s) { Span sp; cudaEventCreate(&sp.a); cudaEventCreate(&sp.b); sp.kind = kind; cudaEventRecord(sp.a, s); spans.push_back(sp); };
+    auto span_end = [&](cudaStream_t s) { cudaEventRecord(spans.back().b, s); };
+    cudaEvent_t commit_done[2] = {nullptr, nullptr};
+    cudaEvent_t first_eval = nullptr, last_commit = nullptr;
+    int batch_seq = 0;
+    int *d_taskctr = d_taskctr_.as<int>((size_t)Cn * N + 2);
+    if (!count_only) {
+        if (!d_taskctr) return FGT_ERR_CUDA;
+        CK(cudaMemsetAsync(d_taskctr, 0, ((size_t)Cn * N + 2) * sizeof(int), st_));
+    }
     auto launch_range = [&](int h, int n0, int n1, cudaEvent_t ready) -> int {
         ChromState &cs = chroms_[h];
-        const int ln = lane_rr;
-        lane_rr ^= 1;
-        lane_used[ln] = true;
-        cudaStream_t st_ = ln ? this->st_acc2_ : this->st_;      // shadows the member inside this lambda
-        DevBuf &d_draws_ = ln ? this->d_draws2_ : this->d_draws_;
-        DevBuf &d_recs_ = ln ? this->d_recs2_ : this->d_recs_;
-        DevBuf &d_cnt_ = ln ? this->d_cnt2_ : this->d_cnt_;
-        auto span_begin = [&](int kind) { Span s; cudaEventCreate(&s.a); cudaEventCreate(&s.b); s.kind = kind; cudaEventRecord(s.a, st_); spans.push_back(s); };
-        auto span_end = [&]() { cudaEventRecord(spans.back().b, st_); };
-        if (ready) CK(cudaStreamWaitEvent(st_, ready, 0));
-        if (tables_ready) CK(cudaStreamWaitEvent(st_, tables_ready, 0));
         int n = n0;
         while (n < n1) {
             const int b0 = n;
@@ -619,6 +626,10 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
                 n++;
             }
             const int Nb = n - b0;
+            const int bi = batch_seq & 1;
+            DevBuf &draws_buf = bi ? d_draws2_ : d_draws_;
+            DevBuf &recs_buf = bi ? d_recs2_ : d_recs_;
+            DevBuf &reg_buf = bi ? d_cnt2_ : d_cnt_;
             const long long A4 = (2 * lo) & ~3LL;
             const long long nthreads = (2 * hi - A4 + kRun - 1) / kRun;
             long long *hp = pin_pairbase + (size_t)h * N + b0;
@@ -627,17 +638,20 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
             History hh = apply_jump(poly_pow_E((uint64_t)A4), h0);
             uint32_t *dh = d_hist + hist_used * kLag;
             std::memcpy(pin_hist + hist_used * kLag, hh.x, sizeof hh.x);
+            // ---- evaluation stream ----
+            if (ready) CK(cudaStreamWaitEvent(st_, ready, 0));
+            if (commit_done[bi]) CK(cudaStreamWaitEvent(st_, commit_done[bi], 0));     // this buffer set is free again
             CK(cudaMemcpyAsync(dh, pin_hist + hist_used * kLag, sizeof hh.x, cudaMemcpyHostToDevice, st_));
             hist_used++;
             CK(cudaMemcpyAsync(d_pairbase + (size_t)h * N + b0, hp, Nb * sizeof(long long), cudaMemcpyHostToDevice, st_));
             CK(cudaMemcpyAsync(d_physof + (size_t)h * N + b0, hq, Nb * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
-            uint32_t *d_draws = d_draws_.as<uint32_t>((size_t)nthreads * kRun + 4);
+            uint32_t *d_draws = draws_buf.as<uint32_t>((size_t)nthreads * kRun + 4);
             if (!d_draws) return FGT_ERR_CUDA;
-            span_begin(0);
+            if (!first_eval) { first_eval = new_timed_event(); CK(cudaEventRecord(first_eval, st_)); }
+            span_begin(0, st_);
             launch_rand_fill(dh, (const uint32_t *)d_level_tab_.p, d_draws, nthreads, st_);
             launches_ += 1;
-            span_end();
-            span_begin(1);
+            span_end(st_);
             ChromPrep cpd{};
             cpd.nb = cs.nb; cpd.W = cs.W; cpd.n_phys = n_phys;
             cpd.chunk_ptr = (const Chunk *const *)cs.chunk_ptr.p;
@@ -646,7 +660,11 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
             const long long *pbase = d_pairbase + (size_t)h * N + b0;
             const int32_t *pphys = d_physof + (size_t)h * N + b0;
             double *tens_b = d_tensor + (size_t)b0 * tens_per_ind;
+            cudaEvent_t eval_done = new_event();
             if (impl == 1) {
+                CK(cudaEventRecord(eval_done, st_));
+                CK(cudaStreamWaitEvent(sc, eval_done, 0));
+                span_begin(1, sc);
                 AccumArgs a{};
                 a.cp = cpd;
                 a.draws = (const uint2 *)d_draws;
@@ -656,13 +674,15 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
                 a.bw = pb.binwidth; a.half_bw = pb.binwidth / 2.0;
                 a.slabs = d_slabs; a.n_slabs = (int)slabs.size();
                 a.accepted = d_acc; a.err = d_err;
-                launch_accum_strict(a, st_);
+                launch_accum_strict(a, sc);
                 launches_ += 1;
+                span_end(sc);
             } else {
                 const size_t n_ent = (size_t)Nb * slabs.size() * (cs.nb - 1) * nd_max;
-                RegionEnt *d_regions = d_cnt_.as<RegionEnt>(n_ent);
-                UpdateRec *d_recs = d_recs_.as<UpdateRec>((size_t)(nthreads * (long long)kRun / 2 + 2) * plan.n_slots);
+                RegionEnt *d_regions = reg_buf.as<RegionEnt>(n_ent);
+                UpdateRec *d_recs = recs_buf.as<UpdateRec>((size_t)(nthreads * (long long)kRun / 2 + 2) * plan.n_slots);
                 if (!d_regions || !d_recs) return FGT_ERR_CUDA;
+                span_begin(3, st_);
                 CK(cudaMemsetAsync(d_regions, 0, n_ent * sizeof(RegionEnt), st_));
                 EvalArgs ea{};
                 ea.cp = cpd; ea.draws = (const uint2 *)d_draws;
@@ -673,6 +693,10 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
                 ea.recs = d_recs; ea.regions = d_regions; ea.slabs = d_slabs; ea.n_slabs = (int)slabs.size(); ea.nd_max = nd_max;
                 ea.err = d_err;
                 launch_eval_pairs(ea, st_);
+                span_end(st_);
+                CK(cudaEventRecord(eval_done, st_));
+                CK(cudaStreamWaitEvent(sc, eval_done, 0));
+                span_begin(1, sc);
                 CommitArgs ca{};
                 ca.cp = cpd; ca.pair_base = pbase; ca.phys_of = pphys;
                 ca.N = Nb; ca.K = K; ca.G = G; ca.grid_start = pb.grid_start; ca.n_slots = plan.n_slots;
@@ -680,26 +704,28 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
                 ca.slabs = d_slabs; ca.recs = d_recs; ca.regions = d_regions; ca.nd_max = nd_max;
                 ca.tensor_is_zero = (tile_in_smem && (pb.mode == 3 || h == 0)) ? 1 : 0;
                 ca.tensor = tens_b; ca.accepted = d_acc;
+                ca.task_counter = d_taskctr + batch_seq;
                 ca.dbg = dbg;
-                launch_commit_ordered(ca, plan_max_w, st_);
+                launch_commit_ordered(ca, plan_max_w, sc);
                 launches_ += 2;
+                span_end(sc);
             }
             stx.accum_launches += 1;
-            span_end();
             if (project_per_range && (pb.mode == 3 || h == Cn - 1) && !want_raw) {
                 // these individuals' tensors are final: project them now, off the tail of the call
-                span_begin(2);
-                launch_project(tens_b, Nb, K, G, S, d_tw, d_pairkh, d_results + (size_t)b0 * S * S * G, st_);
+                span_begin(2, sc);
+                launch_project(tens_b, Nb, K, G, S, d_tw, d_pairkh, d_results + (size_t)b0 * S * S * G, sc);
                 launches_ += 1;
-                span_end();
+                span_end(sc);
             }
+            commit_done[bi] = new_event();
+            CK(cudaEventRecord(commit_done[bi], sc));
+            batch_seq++;
         }
         return FGT_OK;
     };
 
     // ---- chromosomes: blocks of packed individuals flow  copy -> chunk/bin -> accumulate -------------
-    std::vector<cudaEvent_t> evs;
-    auto new_event = [&]() { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); evs.push_back(e); return e; };
     cudaEvent_t labels_free = nullptr;            // last chunk kernel that read the shared label staging buffer
     float ms_prep_host = 0.f;
     for (int h = 0; h < Cn; h++) {
@@ -752,8 +778,8 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
             else if (monotone[h]) while (n_end < N && used[h][n_end] < p1) n_end++;
             const int min_range = std::max(1, (N + opt.ranges - 1) / std::max(1, opt.ranges));
             if (n_end > next_n && (b == n_blocks - 1 || n_end - next_n >= min_range)) {
-                // with everything prepared at once (device-resident paintings) still launch two ranges on the two
-                // lanes: the evaluation of one overlaps the latency-bound ordered commit of the other
+                // with everything prepared at once (device-resident paintings) still launch several ranges:
+                // the evaluation of one overlaps the latency-bound ordered commit of the previous one
                 const int parts = (n_blocks == 1 && opt.split_ready > 1) ? std::min(opt.split_ready, n_end - next_n) : 1;
                 for (int q = 0; q < parts; q++) {
                     const int a0 = next_n + (int)((long long)(n_end - next_n) * q / parts);
@@ -769,21 +795,13 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
             for (int n = 0; n < N; n++) count_only[(size_t)h * N + n] = cs.totals[used[h][n]];
             continue;
         }
-        {   // chromosomes are folded in order into the same cells: both lanes must have finished this chromosome
-            // before either starts the next one (or the projection)
-            cudaEvent_t ja = new_event(), jb = new_event();
-            CK(cudaEventRecord(ja, st_));
-            CK(cudaEventRecord(jb, st_acc2_));
-            CK(cudaStreamWaitEvent(st_, jb, 0));
-            CK(cudaStreamWaitEvent(st_acc2_, ja, 0));
-        }
         if (pb.mode == 3 && !(project_per_range && !want_raw)) {
-            span_begin(2);
-            if (want_raw) { launch_expand_raw(d_tensor, N, K, G, d_raw + (size_t)h * N * K * K * G, st_); launches_++; }
-            launch_project(d_tensor, N, K, G, S, d_tw, d_pairkh, d_results, st_);
+            span_begin(2, sc);
+            if (want_raw) { launch_expand_raw(d_tensor, N, K, G, d_raw + (size_t)h * N * K * K * G, sc); launches_++; }
+            launch_project(d_tensor, N, K, G, S, d_tw, d_pairkh, d_results, sc);
             launches_ += 1;
-            if (memset_tensor) CK(cudaMemsetAsync(d_tensor, 0, tens_elems * sizeof(double), st_));
-            span_end();
+            if (memset_tensor) CK(cudaMemsetAsync(d_tensor, 0, tens_elems * sizeof(double), sc));
+            span_end(sc);
         }
     }
     {
@@ -793,7 +811,7 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
         if (count_only || (herr[0] & (kErrMissingDonor | kErrLabelRange))) {
             if (count_only) { carry_ = stx; carry_.kernel_launches = launches_; }
             CK(cudaStreamSynchronize(st_));
-            CK(cudaStreamSynchronize(st_acc2_));
+            CK(cudaStreamSynchronize(st_commit_));
             for (auto e2 : evs) cudaEventDestroy(e2);
             for (auto &e2 : ev) cudaEventDestroy(e2);
             for (Span &s : spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
@@ -805,54 +823,62 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
     const long long all_pairs = pb.pair_offset ? pb.pairs_total : run;
     stx.pairs = my_pairs;
 
-    CK(cudaEventRecord(ev[1], st_));
+    if (!count_only) { last_commit = new_timed_event(); CK(cudaEventRecord(last_commit, sc)); }
+    CK(cudaEventRecord(ev[1], sc));
     if (pb.mode == 1 && !(project_per_range && !want_raw)) {
-        if (want_raw) { launch_expand_raw(d_tensor, N, K, G, d_raw, st_); launches_++; }
-        launch_project(d_tensor, N, K, G, S, d_tw, d_pairkh, d_results, st_);
+        if (want_raw) { launch_expand_raw(d_tensor, N, K, G, d_raw, sc); launches_++; }
+        launch_project(d_tensor, N, K, G, S, d_tw, d_pairkh, d_results, sc);
         launches_ += 1;
     }
     double *d_rs = d_rs_.as<double>((size_t)N * S * G), *d_ratio = d_ratio_.as<double>((size_t)N * S * S * G);
     double *d_means = d_means_.as<double>((size_t)S * S * G);
     if (!d_rs || !d_ratio || !d_means) return FGT_ERR_CUDA;
-    CK(cudaMemcpyAsync(d_means, means, (size_t)S * S * G * sizeof(double), cudaMemcpyHostToDevice, st_));
-    launch_normalise(d_results, N, S, G, pb.num_inds_total > 0 ? pb.num_inds_total : N, d_rs, d_ratio, st_);
-    launch_mean_accum(d_ratio, N, S, G, d_means, st_);
+    CK(cudaMemcpyAsync(d_means, means, (size_t)S * S * G * sizeof(double), cudaMemcpyHostToDevice, sc));
+    launch_normalise(d_results, N, S, G, pb.num_inds_total > 0 ? pb.num_inds_total : N, d_rs, d_ratio, sc);
+    launch_mean_accum(d_ratio, N, S, G, d_means, sc);
     launches_ += 2;
-    CK(cudaMemcpyAsync(means, d_means, (size_t)S * S * G * sizeof(double), cudaMemcpyDeviceToHost, st_));
+    CK(cudaMemcpyAsync(means, d_means, (size_t)S * S * G * sizeof(double), cudaMemcpyDeviceToHost, sc));
     stx.h2d_bytes += (int64_t)S * S * G * 8;
     stx.d2h_bytes += (int64_t)S * S * G * 8;
-    CK(cudaEventRecord(ev[2], st_));
+    CK(cudaEventRecord(ev[2], sc));
     int herr[4];
     unsigned long long hacc[2];
-    CK(cudaMemcpyAsync(herr, d_err, sizeof herr, cudaMemcpyDeviceToHost, st_));
-    CK(cudaMemcpyAsync(hacc, d_acc, sizeof hacc, cudaMemcpyDeviceToHost, st_));
+    CK(cudaMemcpyAsync(herr, d_err, sizeof herr, cudaMemcpyDeviceToHost, sc));
+    CK(cudaMemcpyAsync(hacc, d_acc, sizeof hacc, cudaMemcpyDeviceToHost, sc));
     if (want_raw) {
         raw_host_.resize(raw_count_);
-        CK(cudaMemcpyAsync(raw_host_.data(), d_raw, raw_count_ * sizeof(double), cudaMemcpyDeviceToHost, st_));
+        CK(cudaMemcpyAsync(raw_host_.data(), d_raw, raw_count_ * sizeof(double), cudaMemcpyDeviceToHost, sc));
     }
+    CK(cudaStreamSynchronize(sc));
     CK(cudaStreamSynchronize(st_));
     tick("all done");
     CK(cudaGetLastError());
-    for (auto e2 : evs) cudaEventDestroy(e2);
     if (tables_ready) cudaEventDestroy(tables_ready);
-    if (herr[0]) return err_to_code(herr[0]);
+    if (herr[0]) { for (auto e2 : evs) cudaEventDestroy(e2); return err_to_code(herr[0]); }
 
     // the stream moves on by two draws per sampled pair of the WHOLE call (all shards), C:136-137
     store_history(apply_jump(poly_pow_E(2ULL * (uint64_t)all_pairs), h0));
 
+    float ms_eval = 0.f, ms_commit = 0.f;
     for (Span &s : spans) {
         float t = 0.f;
         cudaEventElapsedTime(&t, s.a, s.b);
-        if (s.kind == 0) ms_rand += t; else if (s.kind == 1) ms_accum += t; else ms_proj += t;
+        if (s.kind == 0) ms_rand += t; else if (s.kind == 1) ms_commit += t; else if (s.kind == 3) ms_eval += t; else ms_proj += t;
         cudaEventDestroy(s.a); cudaEventDestroy(s.b);
     }
+    // accumulation = from the first evaluation launch to the end of the last commit (the two phases of
+    // consecutive ranges overlap, so their individual spans add up to more than this)
+    if (first_eval && last_commit) cudaEventElapsedTime(&ms_accum, first_eval, last_commit);
+    ms_accum = std::max(0.f, ms_accum - ms_rand - ms_proj);
+    (void)ms_eval; (void)ms_commit;
     float tail = 0.f;
     cudaEventElapsedTime(&tail, ev[1], ev[2]);
     cudaEventElapsedTime(&stx.ms_total, ev[0], ev[2]);
     stx.ms_rand = ms_rand; stx.ms_accum = ms_accum; stx.ms_project = ms_proj + tail;
-    stx.ms_chunk = stx.ms_total - ms_rand - ms_accum - stx.ms_project;   // what is left: chunking/binning not hidden behind the accumulation
+    stx.ms_chunk = std::max(0.f, stx.ms_total - ms_rand - ms_accum - stx.ms_project);   // chunking/binning not hidden behind the accumulation
     stx.accepted = (int64_t)hacc[0];
     stx.kernel_launches = launches_;
+    for (auto e2 : evs) cudaEventDestroy(e2);
     for (auto &e2 : ev) cudaEventDestroy(e2);
     last_stats = stx;
     if (stats) *stats = stx;

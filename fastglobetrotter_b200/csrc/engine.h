@@ -79,7 +79,7 @@ class Engine {
 
     bool inited_ = false;
     int init_rc_ = 0;
-    cudaStream_t st_ = nullptr, st_prep_ = nullptr, st_copy_ = nullptr, st_acc2_ = nullptr;
+    cudaStream_t st_ = nullptr, st_prep_ = nullptr, st_copy_ = nullptr, st_commit_ = nullptr;
     History private_hist_ = seeded_history(1);
     std::vector<uint32_t> level_tab_;
     DevBuf d_level_tab_, d_err_, d_accepted_;
@@ -87,7 +87,7 @@ class Engine {
     DevBuf d_labels_, d_cum_, d_inc_, d_counts_, d_rowoff_, d_cstart_, d_cend_, d_chap_, d_cntmat_, d_runfirst_,
         d_donor_, d_etab_, d_rowmap_;
     DevBuf d_draws_, d_hist_, d_tensor_, d_results_, d_tw_, d_pairkh_, d_slabs_, d_pairbase_, d_physof_, d_rs_,
-        d_ratio_, d_means_, d_raw_, d_totals_, d_recs_, d_cnt_, d_draws2_, d_recs2_, d_cnt2_, d_slabof_, d_firstslab_, d_slabw_, d_slabb0_;
+        d_ratio_, d_means_, d_raw_, d_totals_, d_recs_, d_cnt_, d_draws2_, d_recs2_, d_cnt2_, d_taskctr_, d_slabof_, d_firstslab_, d_slabw_, d_slabb0_;
     std::vector<ChromState> chroms_;
     std::vector<double> raw_host_;
     int64_t raw_count_ = 0;

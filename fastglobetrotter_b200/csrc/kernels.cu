@@ -606,19 +606,32 @@ __device__ __forceinline__ unsigned fastmod_u32(unsigned a, unsigned d, double i
     return r >= d ? r - d : r;
 }
 
+// One 256-bit load per chunk record (LDG.E.256): a random gather of a 32-byte record then costs one L1
+// wavefront per lane instead of two (the evaluation kernel is L1-wavefront bound on these gathers).
+__device__ __forceinline__ Chunk ldg_chunk(const Chunk *p) {
+    unsigned long long a, b, c, d;
+    asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];\n" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+    Chunk o;
+    o.pos = __longlong_as_double((long long)a);
+    o.size = __longlong_as_double((long long)b);
+    o.w = __longlong_as_double((long long)c);
+    o.pop = (int32_t)(d & 0xffffffffull);
+    o.hapid = (int32_t)(d >> 32);
+    return o;
+}
+
 // Phase 1: one warp per (pseudo-individual, coarse bin j); walks k = j+1.. in order, 64 sampled pairs
 // (two per lane, for memory-level parallelism) per iteration.  Everything of reference C:136-162
 // except the "+=" happens here.
 struct PairEval { int cell, local, slot; double val; };
 
-__device__ __forceinline__ PairEval eval_pair(bool in_range, uint2 r, int f1, int t1, double inv1, int f2, int t2, double inv2,
-                                              const Chunk *__restrict__ ch, const EvalArgs &a, int slab0, int &bad) {
+__device__ __forceinline__ PairEval eval_pair(bool in_range, uint2 r, int t1, double inv1, int t2, double inv2,
+                                              const Chunk *binA, const Chunk *binB, const EvalArgs &a, int slab0, int &bad) {
     PairEval o;
     o.cell = -1; o.local = 0; o.slot = -1; o.val = 0.0;
     if (!in_range) return o;
-    const int c1 = f1 + (int)fastmod_u32(r.x, (unsigned)t1, inv1);
-    const int c2 = f2 + (int)fastmod_u32(r.y, (unsigned)t2, inv2);
-    const Chunk A = ch[c1], B = ch[c2];
+    // reference C:136-137: chunk1 = start_bin[j] + rand() % t_1 ; chunk2 = start_bin[k] + rand() % t_2
+    const Chunk A = ldg_chunk(binA + fastmod_u32(r.x, (unsigned)t1, inv1)), B = ldg_chunk(binB + fastmod_u32(r.y, (unsigned)t2, inv2));
     bool live = true;
     if (a.mode == 1) live = (A.pop != 0) && (B.pop != 0);                  // reference C:138-142
     else if (A.pop == 0 || B.pop == 0) { bad |= kErrMode3Target; live = false; }
@@ -668,6 +681,7 @@ __global__ void __launch_bounds__(128, 8) k_eval_pairs(const EvalArgs a) {
     const int f1 = F[j];
     const double inv1 = __ddiv_rn(1.0, (double)t1);
     const int ns = a.n_slots;
+    const Chunk *binA = ch + f1;
     int dmax = W - 1;
     if (nb - 1 - j < dmax) dmax = nb - 1 - j;
     int bad = 0;
@@ -683,6 +697,7 @@ __global__ void __launch_bounds__(128, 8) k_eval_pairs(const EvalArgs a) {
         const uint2 *dr = a.draws + seg;
         UpdateRec *reg = a.recs + seg * ns;
         const int slab0 = a.first_slab[d];
+        const Chunk *binB = ch + f2;
         int c[kMaxSlots] = {0, 0, 0, 0};
         for (int base = 0; base < Y; base += 64) {
             const int q0 = base + lane, q1 = base + 32 + lane;
@@ -690,8 +705,8 @@ __global__ void __launch_bounds__(128, 8) k_eval_pairs(const EvalArgs a) {
             if (q0 < Y) r0 = dr[q0];
             if (q1 < Y) r1 = dr[q1];
             PairEval e[2];
-            e[0] = eval_pair(q0 < Y, r0, f1, t1, inv1, f2, t2, inv2, ch, a, slab0, bad);
-            e[1] = eval_pair(q1 < Y, r1, f1, t1, inv1, f2, t2, inv2, ch, a, slab0, bad);
+            e[0] = eval_pair(q0 < Y, r0, t1, inv1, t2, inv2, binA, binB, a, slab0, bad);
+            e[1] = eval_pair(q1 < Y, r1, t1, inv1, t2, inv2, binA, binB, a, slab0, bad);
             // ordered partition of the two steps' updates into the segment's slab regions
 #pragma unroll
             for (int h = 0; h < 2; h++) {
@@ -743,8 +758,9 @@ void launch_eval_pairs(const EvalArgs &a, cudaStream_t st) {
 // (cp.async.bulk + mbarrier complete_tx); warp 0 is the consumer -- it folds 32 records per step into
 // the slab tile, which lives in shared memory when it fits (TILE_SMEM), so the ordered
 // read-modify-write chain runs at shared-memory latency and global latency is off the critical path.
-constexpr int kStages = 6;        // ring depth
-constexpr int kStageRecs = 64;    // records per ring stage (two consumer steps)
+constexpr int kStages = 3;        // ring depth
+constexpr int kStageRecs = 128;   // records per ring stage (four consumer steps); stages are packed across regions
+constexpr int kStageSteps = kStageRecs / 32;
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
@@ -752,6 +768,9 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -781,146 +800,176 @@ __global__ void __launch_bounds__(64) k_commit_ordered(const CommitArgs a) {
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kStages * kStageRecs * sizeof(UpdateRec));
     uint64_t *empty = full + kStages;
     int *stage_cnt = reinterpret_cast<int *>(empty + kStages);                         // [kStages]
+    int *task_slot = stage_cnt + kStages;                                              // [1] task broadcast
     RegionEnt *dir = reinterpret_cast<RegionEnt *>(smem_raw + 6144 + 256);              // [32] staged directory entries
     double *tile = reinterpret_cast<double *>(smem_raw + 6144 + 1024);                 // ring 6 KB + 1 KB control
     const int lane = lane_id();
     const int wid = warp_id();
-    const int task = blockIdx.x;
-    const int slab_i = task / a.N;
-    const int n = task - slab_i * a.N;
-    const SlabDesc sl = a.slabs[slab_i];
     const int G = a.G;
     const int P = a.K * (a.K + 1) / 2;
-    double *tens = a.tensor + (size_t)n * (size_t)P * G;
-    const int sbw = sl.b1 - sl.b0 + 1;
-    const int boff = sl.b0 - a.grid_start;
+    const int total_tasks = a.N * a.n_slabs;
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    if (TILE_SMEM) {
-        if (a.tensor_is_zero) {
-            for (int idx = threadIdx.x; idx < P * sbw; idx += blockDim.x) tile[idx] = 0.0;
-        } else {
-            for (int idx = threadIdx.x; idx < P * sbw; idx += blockDim.x) {
-                const int row = idx / sbw, off = idx - row * sbw;
-                tile[idx] = tens[(size_t)row * G + boff + off];
+    // ring position: carried across tasks (the end marker of a task occupies a stage like any other)
+    int stage = 0;
+    unsigned phase = 0;
+    unsigned long long n_acc = 0;
+    const unsigned lt = (1u << lane) - 1;
+
+    // Persistent CTA: tasks (heavy slabs first) are claimed from a global counter, so the grid never has
+    // blocks waiting and kernels of other streams (the next range's evaluation) can share the SMs.
+    while (true) {
+        __syncthreads();                                   // previous task fully retired (tile stored, ring drained)
+        if (threadIdx.x == 0) *task_slot = atomicAdd(a.task_counter, 1);
+        __syncthreads();
+        const int task = *task_slot;
+        if (task >= total_tasks) break;
+        const int slab_i = task / a.N;
+        const int n = task - slab_i * a.N;
+        const SlabDesc sl = a.slabs[slab_i];
+        double *tens = a.tensor + (size_t)n * (size_t)P * G;
+        const int sbw = sl.b1 - sl.b0 + 1;
+        const int boff = sl.b0 - a.grid_start;
+        if (TILE_SMEM) {
+            if (a.tensor_is_zero) {
+                for (int idx = threadIdx.x; idx < P * sbw; idx += blockDim.x) tile[idx] = 0.0;
+            } else {
+                for (int idx = threadIdx.x; idx < P * sbw; idx += blockDim.x) {
+                    const int row = idx / sbw, off = idx - row * sbw;
+                    tile[idx] = tens[(size_t)row * G + boff + off];
+                }
             }
         }
-    }
-    __syncthreads();
+        __syncthreads();
 
-    if (wid == 1) {
-        // ------------------------------ producer ------------------------------
-        const long long n_ent = (long long)(a.cp.nb - 1) * a.nd_max;
-        const RegionEnt *ents = a.regions + ((size_t)n * a.n_slabs + slab_i) * n_ent;
-        int stage = 0;
-        unsigned phase = 0;
-        RegionEnt cur, nxt;
-        cur.base = 0; cur.cnt = 0; cur.pad = 0;
-        if (lane < n_ent) cur = ents[lane];
-        for (long long e0 = 0; e0 < n_ent; e0 += 32) {
-            nxt.base = 0; nxt.cnt = 0; nxt.pad = 0;
-            if (e0 + 32 + lane < n_ent) nxt = ents[e0 + 32 + lane];     // in flight while this batch is issued
-            const unsigned live = __ballot_sync(kFull, cur.cnt > 0);
-            if (live) {
-                dir[lane] = cur;
-                __syncwarp();
-                if (lane == 0) {
-                    unsigned m = live;
-                    while (m) {
-                        const int i = __ffs(m) - 1;
-                        m &= m - 1;
-                        const int c = dir[i].cnt;
-                        const UpdateRec *src = a.recs + dir[i].base;
-                        for (int off = 0; off < c; off += kStageRecs) {
-                            const int cnt_here = c - off < kStageRecs ? c - off : kStageRecs;
-                            mbar_wait(&empty[stage], phase ^ 1);
-                            stage_cnt[stage] = cnt_here;
-                            mbar_arrive_expect_tx(&full[stage], (unsigned)cnt_here * (unsigned)sizeof(UpdateRec));
-                            bulk_g2s(&ring[stage * kStageRecs], src + off, (unsigned)cnt_here * (unsigned)sizeof(UpdateRec),
-                                     &full[stage]);
-                            if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (wid == 1) {
+            // ------------------------------ producer ------------------------------
+            const long long n_ent = (long long)(a.cp.nb - 1) * a.nd_max;
+            const RegionEnt *ents = a.regions + ((size_t)n * a.n_slabs + slab_i) * n_ent;
+            RegionEnt cur, nxt;
+            cur.base = 0; cur.cnt = 0; cur.pad = 0;
+            if (lane < n_ent) cur = ents[lane];
+            int fill = 0;                                  // records already placed in the open stage (lane 0's view)
+            bool open = false;
+            for (long long e0 = 0; e0 < n_ent; e0 += 32) {
+                nxt.base = 0; nxt.cnt = 0; nxt.pad = 0;
+                if (e0 + 32 + lane < n_ent) nxt = ents[e0 + 32 + lane];     // in flight while this batch is issued
+                const unsigned live = __ballot_sync(kFull, cur.cnt > 0);
+                if (live) {
+                    dir[lane] = cur;
+                    __syncwarp();
+                    if (lane == 0) {
+                        unsigned m = live;
+                        while (m) {
+                            const int i = __ffs(m) - 1;
+                            m &= m - 1;
+                            const int c = dir[i].cnt;
+                            const UpdateRec *src = a.recs + dir[i].base;
+                            int off = 0;
+                            while (off < c) {              // stages are packed: a stage takes pieces of consecutive regions
+                                if (!open) { mbar_wait(&empty[stage], phase ^ 1); open = true; fill = 0; }
+                                const int piece = min(c - off, kStageRecs - fill);
+                                const unsigned bytes = (unsigned)piece * (unsigned)sizeof(UpdateRec);
+                                mbar_expect_tx(&full[stage], bytes);
+                                bulk_g2s(&ring[stage * kStageRecs + fill], src + off, bytes, &full[stage]);
+                                fill += piece; off += piece;
+                                if (fill == kStageRecs) {
+                                    stage_cnt[stage] = fill;
+                                    mbar_arrive(&full[stage]);
+                                    open = false;
+                                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                                }
+                            }
                         }
                     }
+                    __syncwarp();
                 }
-                __syncwarp();
+                cur = nxt;
             }
-            cur = nxt;
-        }
-        if (lane == 0) {                                   // end marker
-            mbar_wait(&empty[stage], phase ^ 1);
-            stage_cnt[stage] = -1;
-            mbar_arrive(&full[stage]);
-        }
-    } else {
-        // ------------------------------ consumer ------------------------------
-        // software pipeline: the records (and match.any masks) of stage s+1 are fetched before stage s is
-        // folded, so barrier / shared-memory / match latency overlaps the ordered read-modify-write chain
-        int stage = 0;
-        unsigned phase = 0;
-        unsigned long long n_acc = 0;
-        const unsigned lt = (1u << lane) - 1;
-        // Lanes that share a cell must add in lane order, so every step needs, per lane, the set of lanes with
-        // the same cell: match.any.  (Measured alternatives, both slower on B200: one ballot per index bit --
-        // 13 votes cost more than one match.any; stamping the tile with lane ids to detect collisions first --
-        // duplicates occur in most steps of this workload, so the slow path is the common path.)
-        auto same_cell_mask = [&](int cell) -> unsigned {
-            return __match_any_sync(kFull, cell >= 0 ? (unsigned)cell : (0x80000000u | (unsigned)lane));
-        };
-        struct Staged { int c, cell0, cell1; double val0, val1; unsigned g0, g1; };
-        auto fetch = [&]() -> Staged {
-            Staged s;
-            mbar_wait(&full[stage], phase);
-            s.c = stage_cnt[stage];
-            s.cell0 = -1; s.cell1 = -1; s.val0 = 0.0; s.val1 = 0.0; s.g0 = 0; s.g1 = 0;
-            if (s.c >= 0) {
-                const UpdateRec *rg = ring + stage * kStageRecs;
-                if (lane < s.c) { const UpdateRec r = rg[lane]; s.cell0 = TILE_SMEM ? r.pad : r.cell; s.val0 = r.val; }
-                if (32 + lane < s.c) { const UpdateRec r = rg[32 + lane]; s.cell1 = TILE_SMEM ? r.pad : r.cell; s.val1 = r.val; }
+            if (lane == 0) {
+                if (open) {                                // last, partially filled stage
+                    stage_cnt[stage] = fill;
+                    mbar_arrive(&full[stage]);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                mbar_wait(&empty[stage], phase ^ 1);       // end marker: occupies one stage
+                stage_cnt[stage] = -1;
+                mbar_arrive(&full[stage]);
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+            stage = __shfl_sync(kFull, stage, 0);
+            phase = __shfl_sync(kFull, phase, 0);
+        } else {
+            // ------------------------------ consumer ------------------------------
+            // software pipeline: the records (and match.any masks) of stage s+1 are fetched before stage s is
+            // folded, so barrier / shared-memory / match latency overlaps the ordered read-modify-write chain.
+            // Lanes that share a cell must add in lane order, so every step needs, per lane, the set of lanes with
+            // the same cell: match.any.  (Measured alternatives, both slower on B200: one ballot per index bit --
+            // 13 votes cost more than one match.any; stamping the tile with lane ids to detect collisions first --
+            // duplicates occur in about half the steps of this workload, so the slow path is the common path.)
+            auto same_cell_mask = [&](int cell) -> unsigned {
+                return __match_any_sync(kFull, cell >= 0 ? (unsigned)cell : (0x80000000u | (unsigned)lane));
+            };
+            struct Staged { int c; int cell[kStageSteps]; double val[kStageSteps]; unsigned g[kStageSteps]; };
+            auto fetch = [&]() -> Staged {
+                Staged s;
+                mbar_wait(&full[stage], phase);
+                s.c = stage_cnt[stage];
+#pragma unroll
+                for (int h = 0; h < kStageSteps; h++) { s.cell[h] = -1; s.val[h] = 0.0; s.g[h] = 0; }
+                if (s.c >= 0) {
+                    const UpdateRec *rg = ring + stage * kStageRecs;
+#pragma unroll
+                    for (int h = 0; h < kStageSteps; h++)
+                        if (32 * h + lane < s.c) { const UpdateRec r = rg[32 * h + lane]; s.cell[h] = TILE_SMEM ? r.pad : r.cell; s.val[h] = r.val; }
+                }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[stage]);     // records are in registers: the stage can be refilled
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
-                if (!(a.dbg & 2)) {
-                    s.g0 = same_cell_mask(s.cell0);
-                    if (s.c > 32) s.g1 = same_cell_mask(s.cell1);
+                if (s.c >= 0 && !(a.dbg & 2)) {
+#pragma unroll
+                    for (int h = 0; h < kStageSteps; h++)
+                        if (32 * h < s.c) s.g[h] = same_cell_mask(s.cell[h]);
                 }
+                return s;
+            };
+            auto fold = [&](int cell, double val, unsigned grp) {
+                const bool leader = (cell >= 0) && ((grp & lt) == 0);
+                double acc = 0.0;
+                if (leader) acc = TILE_SMEM ? tile[cell] : tens[cell];
+                unsigned rest = leader ? (grp & ~(1u << lane)) : 0u;
+                acc = __dadd_rn(acc, val);
+                while (__any_sync(kFull, rest != 0)) {
+                    const int src = rest ? (__ffs(rest) - 1) : lane;
+                    const double v = __shfl_sync(kFull, val, src);
+                    if (rest) { acc = __dadd_rn(acc, v); rest &= rest - 1; }
+                }
+                if (leader) { if (TILE_SMEM) tile[cell] = acc; else tens[cell] = acc; }
+                __syncwarp();
+            };
+            Staged cur = fetch();
+            while (cur.c >= 0) {
+                const Staged nxt = fetch();
+                if (!(a.dbg & 1)) {
+#pragma unroll
+                    for (int h = 0; h < kStageSteps; h++)
+                        if (32 * h < cur.c) fold(cur.cell[h], cur.val[h], cur.g[h]);
+                }
+                n_acc += (unsigned long long)cur.c;
+                cur = nxt;
             }
-            return s;
-        };
-        auto fold = [&](int cell, double val, unsigned grp) {
-            const bool leader = (cell >= 0) && ((grp & lt) == 0);
-            double acc = 0.0;
-            if (leader) acc = TILE_SMEM ? tile[cell] : tens[cell];
-            unsigned rest = leader ? (grp & ~(1u << lane)) : 0u;
-            acc = __dadd_rn(acc, val);
-            while (__any_sync(kFull, rest != 0)) {
-                const int src = rest ? (__ffs(rest) - 1) : lane;
-                const double v = __shfl_sync(kFull, val, src);
-                if (rest) { acc = __dadd_rn(acc, v); rest &= rest - 1; }
-            }
-            if (leader) { if (TILE_SMEM) tile[cell] = acc; else tens[cell] = acc; }
-            __syncwarp();
-        };
-        Staged cur = fetch();
-        while (cur.c >= 0) {
-            const Staged nxt = fetch();
-            if (!(a.dbg & 1)) {
-                fold(cur.cell0, cur.val0, cur.g0);
-                if (cur.c > 32) fold(cur.cell1, cur.val1, cur.g1);
-            }
-            n_acc += (unsigned long long)cur.c;
-            cur = nxt;
         }
-        if (lane == 0 && n_acc) atomicAdd(a.accepted, n_acc);
-    }
-    __syncthreads();
-    if (TILE_SMEM) {
-        for (int idx = threadIdx.x; idx < P * sbw; idx += blockDim.x) {
-            const int row = idx / sbw, o2 = idx - row * sbw;
-            tens[(size_t)row * G + boff + o2] = tile[idx];
+        __syncthreads();
+        if (TILE_SMEM) {
+            for (int idx = threadIdx.x; idx < P * sbw; idx += blockDim.x) {
+                const int row = idx / sbw, o2 = idx - row * sbw;
+                tens[(size_t)row * G + boff + o2] = tile[idx];
+            }
         }
     }
+    if (wid == 0 && lane == 0 && n_acc) atomicAdd(a.accepted, n_acc);
 }
 
 size_t commit_tile_bytes(int K, int slab_width) { return (size_t)K * (K + 1) / 2 * slab_width * sizeof(double); }
@@ -937,9 +986,12 @@ void launch_commit_ordered(const CommitArgs &a, int max_slab_width, cudaStream_t
             cudaFuncSetAttribute(k_commit_ordered<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             attr_set = true;
         }
-        k_commit_ordered<true><<<(unsigned)tasks, 64, ctrl_bytes + tile_bytes, st>>>(a);
+        const long long per_sm = std::max<long long>(1, (227 * 1024) / (long long)(ctrl_bytes + tile_bytes + 1024));
+        const long long grid = std::min<long long>(tasks, 148 * std::min<long long>(per_sm, 32));
+        k_commit_ordered<true><<<(unsigned)grid, 64, ctrl_bytes + tile_bytes, st>>>(a);
     } else {
-        k_commit_ordered<false><<<(unsigned)tasks, 64, ctrl_bytes, st>>>(a);
+        const long long grid = std::min<long long>(tasks, 148 * 16);
+        k_commit_ordered<false><<<(unsigned)grid, 64, ctrl_bytes, st>>>(a);
     }
 }
 

@@ -87,6 +87,7 @@ struct CommitArgs {
     int32_t nd_max, tensor_is_zero, dbg;
     double *tensor;
     unsigned long long *accepted;
+    int *task_counter;            // zeroed before the launch: persistent CTAs claim (individual, slab) tasks from it
 };
 void launch_eval_pairs(const EvalArgs &a, cudaStream_t st);
 void launch_commit_ordered(const CommitArgs &a, int max_slab_width, cudaStream_t st);
