@@ -224,7 +224,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": agg_e["d2h_bytes"] / e_steps, "steps": e_steps,
                     "ms_per_step": dt_e / e_steps * 1e3, "api": "fgt_data_read_packed (host pinned paintings)"},
             "gpu_launches": int(agg["kernel_launches"]),
-            "roofline": {"bound": "hbm", "kernel": "k_accum_strict", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_eval_pairs + k_commit_ordered (strict accumulation, phase 1 + phase 2)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_s * 1e3},
             "device_ms_per_step": {k: agg[k] / args.steps for k in ("ms_total", "ms_chunk", "ms_rand", "ms_accum", "ms_project")},

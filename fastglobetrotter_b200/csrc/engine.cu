@@ -308,7 +308,7 @@ int Engine::prep_chromosome(const fgt_problem_t &pb, int h, const int32_t *rowma
     CK(cudaMemsetAsync(d_cnt, 0, cm * sizeof(int32_t), st_));
     launch_bin_sort(n_groups, rows_per_ind, d_rowoff, d_cstart, d_cend, d_chap, d_donor_.as<int32_t>(pb.n_donor_labels),
                     pb.n_donor_labels, pb.gridweight_max_cutoff, K, pb.mode, nb, W, d_etab, pb.mode == 3 ? 8.0 : 10.0,
-                    d_sorted, d_cbase, d_t, d_first, d_yoff, d_ro, d_cnt, d_rf, d_err_.as<int>(4), st_);
+                    d_sorted, d_cbase, d_t, d_first, d_yoff, d_ro, d_cnt, d_rf, d_err_.as<int>(4), nullptr, st_);
     launches_ += 1;
     cs.totals.resize(n_groups);
     CK(cudaMemcpy2DAsync(cs.totals.data(), sizeof(long long), d_ro + nb, (nb + 1) * sizeof(long long), sizeof(long long),
@@ -375,15 +375,16 @@ int Engine::prep_block(const fgt_problem_t &pb, int h, int p0, int p1, int blk, 
     size_t cm = (size_t)np * PM * nb;
     int32_t *d_cnt = d_cntmat_.as<int32_t>(cm), *d_rf = d_runfirst_.as<int32_t>(cm);
     if (!d_cnt || !d_rf) return FGT_ERR_CUDA;
+    long long *d_tot = d_totals_.as<long long>(np);
+    if (!d_tot) return FGT_ERR_CUDA;
     CK(cudaMemsetAsync(d_cnt, 0, cm * sizeof(int32_t), sp));
     launch_bin_sort(np, PM, d_rowoff, d_cstart, d_cend, d_chap, (const int32_t *)d_donor_.p, pb.n_donor_labels,
                     pb.gridweight_max_cutoff, K, pb.mode, nb, W, (const double *)cs.etab.p, pb.mode == 3 ? 8.0 : 10.0, d_sorted,
                     (const Chunk **)cs.chunk_ptr.p + p0, (int32_t *)cs.t.p + (size_t)p0 * nb, (int32_t *)cs.first.p + (size_t)p0 * nb,
                     (int32_t *)cs.yoff.p + (size_t)p0 * nb * W, (long long *)cs.rowoff.p + (size_t)p0 * (nb + 1), d_cnt, d_rf,
-                    (int *)d_err_.p, sp);
+                    (int *)d_err_.p, d_tot, sp);
     launches_ += 2;
-    CK(cudaMemcpy2DAsync(cs.totals.data() + p0, sizeof(long long), (long long *)cs.rowoff.p + (size_t)p0 * (nb + 1) + nb,
-                         (nb + 1) * sizeof(long long), sizeof(long long), np, cudaMemcpyDeviceToHost, sp));
+    CK(cudaMemcpyAsync(cs.totals.data() + p0, d_tot, np * sizeof(long long), cudaMemcpyDeviceToHost, sp));
     CK(cudaStreamSynchronize(sp));
     stx.d2h_bytes += (int64_t)np * 8;
     return FGT_OK;

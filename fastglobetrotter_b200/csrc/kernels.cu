@@ -286,7 +286,7 @@ k_bin_sort(int rows_per_ind, const int32_t *__restrict__ row_off, const double *
            int n_donor_labels, double cutoff, int K, int mode, int nb, int W, const double *__restrict__ Etab,
            double divisor, Chunk *__restrict__ sorted, const Chunk **__restrict__ chunk_ptr, int32_t *__restrict__ t_out,
            int32_t *__restrict__ first_out, int32_t *__restrict__ yoff, long long *__restrict__ rowoff,
-           int32_t *__restrict__ cntmat, int32_t *__restrict__ runfirst, int *__restrict__ err) {
+           int32_t *__restrict__ cntmat, int32_t *__restrict__ runfirst, int *__restrict__ err, long long *__restrict__ totals) {
     const int p = blockIdx.x;
     const int r0 = p * rows_per_ind;
     const int c0 = row_off[r0];
@@ -371,6 +371,7 @@ k_bin_sort(int rows_per_ind, const int32_t *__restrict__ row_off, const double *
         long long *ro = rowoff + (size_t)p * (nb + 1);
         for (int j = 0; j < nb; j++) { ro[j] = s; s += yoff[((size_t)p * nb + j) * W + (W - 1)]; }
         ro[nb] = s;
+        if (totals) totals[p] = s;
     }
 }
 
@@ -378,10 +379,10 @@ void launch_bin_sort(int n_phys, int rows_per_ind, const int32_t *row_off, const
                      const int32_t *chap, const int32_t *donor_label, int n_donor_labels, double cutoff, int K, int mode,
                      int nb, int W, const double *Etab, double divisor, Chunk *sorted, const Chunk **chunk_ptr, int32_t *t,
                      int32_t *first, int32_t *yoff, long long *rowoff, int32_t *cntmat, int32_t *runfirst, int *err,
-                     cudaStream_t st) {
+                     long long *totals, cudaStream_t st) {
     k_bin_sort<<<n_phys, 256, 0, st>>>(rows_per_ind, row_off, cstart, cend, chap, donor_label, n_donor_labels, cutoff, K,
                                       mode, nb, W, Etab, divisor, sorted, chunk_ptr, t, first, yoff, rowoff, cntmat,
-                                      runfirst, err);
+                                      runfirst, err, totals);
 }
 
 // =============================================================================================

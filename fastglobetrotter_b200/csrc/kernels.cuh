@@ -104,7 +104,7 @@ void launch_bin_sort(int n_phys, int rows_per_ind, const int32_t *row_off, const
                      const int32_t *chap, const int32_t *donor_label, int n_donor_labels, double cutoff, int K, int mode,
                      int nb, int W, const double *Etab, double divisor, Chunk *sorted, const Chunk **chunk_ptr, int32_t *t,
                      int32_t *first, int32_t *yoff, long long *rowoff, int32_t *cntmat, int32_t *runfirst, int *err,
-                     cudaStream_t st);
+                     long long *totals, cudaStream_t st);
 void launch_rand_fill(const uint32_t *base_hist, const uint32_t *level_tab, uint32_t *out, long long n_threads,
                       cudaStream_t st);
 void launch_accum_strict(const AccumArgs &a, cudaStream_t st);
