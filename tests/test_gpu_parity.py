@@ -390,3 +390,76 @@ def test_large_K_uses_the_global_tensor_path(lib, oracle):
         lib.srand(3)
         m_g2, _, _ = lib.data_read_packed(1, spec.ploidy, spec.nsamples, chrom, ids, bw, G, gs, K, dl, 0.0, 1.0, S, tw)
         assert np.array_equal(m_g2, m_o), K          # per-range projection path (no raw requested)
+
+
+def _run_both(lib, oracle, mode, ploidy, nsamples, chrom, ids, bw, G, gs, K, dl, wmin, cutoff, S, tw, seed=7):
+    oracle.srand(seed)
+    m_o, raw_o, pairs = oracle.data_read_packed(mode, ploidy, nsamples, chrom, ids, bw, G, gs, K, dl, wmin, cutoff, S, tw, want_raw=True)
+    lib.set_option("rand_libc", 0)
+    lib.srand(seed)
+    m_g, raw_g, st = lib.data_read_packed(mode, ploidy, nsamples, chrom, ids, bw, G, gs, K, dl, wmin, cutoff, S, tw, want_raw=True)
+    assert st["pairs"] == pairs
+    assert np.array_equal(raw_g, raw_o)
+    assert np.array_equal(m_g, m_o, equal_nan=True)
+    return pairs
+
+
+def test_edge_shapes(lib, oracle):
+    """haploid, one sample, one individual; chromosomes shorter than the window, a single chunk per painting,
+    flat stretches of the map (coincident cM positions), tiny and empty coarse bins, two SNPs."""
+    rng = np.random.default_rng(0)
+    K, S = 4, 2
+    tw = rng.random(K * K * S * S)
+    # (a) haploid, one sample, one individual, short chromosome (3 cM << 13 cM window)
+    spec = synth.SynthSpec(n_chrom=1, n_inds=1, ploidy=1, nsamples=1, n_snps=300, K=K, rate=1e-6, mean_chunk_cm=0.2, seed=3)
+    pos, rate, labels = synth.make_chromosome(spec, 0)
+    dl = spec.donor_label_vec()
+    _run_both(lib, oracle, 1, 1, 1, [{"pos": pos, "rate": rate, "labels": labels}], [0], 0.1, 100, 10, K, dl, 0.0, 1.0, S, tw)
+    # (b) every painting is a single chunk (one label) -> one chunk per coarse bin 75, nothing can be sampled across bins
+    one = np.full((6, 2000), 5, dtype=np.uint16)
+    spec = synth.SynthSpec(n_chrom=1, n_inds=3, ploidy=2, nsamples=1, n_snps=2000, K=K, rate=7.5e-7)
+    pos, rate = synth.recomb_map(spec, 0)
+    p = _run_both(lib, oracle, 1, 2, 1, [{"pos": pos, "rate": rate, "labels": one}], [0, 1, 2], 0.1, 60, 10, K, dl, 0.0, 1.0, S, tw)
+    assert p == 0
+    # (c) flat map stretches: many SNPs share a cM position, chunks of zero length, sparse coarse bins (gaps with t = 0)
+    spec = synth.SynthSpec(n_chrom=2, n_inds=3, ploidy=2, nsamples=2, n_snps=1500, K=K, rate=2e-6, mean_chunk_cm=1.5, seed=11)
+    chrom = []
+    for h in range(2):
+        pos, rate, labels = synth.make_chromosome(spec, h)
+        rate = rate.copy()
+        rate[100:400] = 0.0
+        rate[900:1100] = 0.0
+        chrom.append({"pos": pos, "rate": rate, "labels": labels})
+    for mode in (1, 3):
+        _run_both(lib, oracle, mode, 2, 2, chrom, ind_id_matrix(3, 2), 0.1, 120, 10, K, dl, 0.0, 1.0, S, tw)
+    # (d) two SNPs only; grid starting at bin 0; bin width 0.5
+    lab2 = np.array([[3, 9], [9, 9], [1, 2], [2, 2]], dtype=np.uint16)
+    pos2, rate2 = np.array([1000.0, 9_000_000.0]), np.array([3e-7, 0.0])
+    _run_both(lib, oracle, 1, 2, 1, [{"pos": pos2, "rate": rate2, "labels": lab2}], [0, 1], 0.5, 12, 0, K, dl, 0.0, 1.0, S, tw)
+    # (e) 32-bit labels
+    spec = synth.SynthSpec(n_chrom=1, n_inds=2, ploidy=2, nsamples=2, n_snps=2500, K=K, rate=5e-7, seed=5)
+    pos, rate, labels = synth.make_chromosome(spec, 0)
+    _run_both(lib, oracle, 1, 2, 2, [{"pos": pos, "rate": rate, "labels": labels.astype(np.int32)}], [0, 1], 0.1, 90, 10, K, dl, 0.0, 1.0,
+              S, tw)
+
+
+def test_null_edge_shapes(lib, oracle):
+    K = 4
+    spec = synth.SynthSpec(n_chrom=2, n_inds=3, ploidy=1, nsamples=2, n_snps=1200, K=K, rate=1.5e-6, self_copy_frac=0.1, seed=2)
+    chrom = []
+    for h in range(2):
+        pos, rate, labels = synth.make_chromosome(spec, h)
+        chrom.append({"pos": pos, "rate": rate, "labels": labels})
+    dl = spec.donor_label_vec()
+    for (bw, G, gs) in ((0.1, 80, 10), (0.5, 10, 0), (0.1, 7, 3)):
+        n_o, ev = oracle.data_read_null_packed(1, 2, chrom, np.arange(3), bw, G, gs, K, dl, 0.0, 1.0)
+        n_g, st = lib.data_read_null_packed(1, 2, chrom, np.arange(3), bw, G, gs, K, dl, 0.0, 1.0)
+        assert st["pairs"] == ev and np.array_equal(n_g, n_o), (bw, G, gs)
+    # a single recipient: nothing to compare, output untouched
+    n_g, st = lib.data_read_null_packed(1, 2, chrom, np.arange(1), 0.1, 50, 10, K, dl, 0.0, 1.0)
+    assert st["pairs"] == 0 and not n_g.any()
+    # reordered recipients
+    rows = np.array([2, 0, 1])
+    n_o, _ = oracle.data_read_null_packed(1, 2, chrom, rows, 0.1, 60, 10, K, dl, 0.0, 1.0)
+    n_g, _ = lib.data_read_null_packed(1, 2, chrom, rows, 0.1, 60, 10, K, dl, 0.0, 1.0)
+    assert np.array_equal(n_g, n_o)
