@@ -30,6 +30,8 @@ using namespace fgt;
 
 namespace {
 
+std::mutex g_api_mu;   // the engine is a per-process singleton; R calls serially, other hosts are serialised here
+
 [[noreturn]] void die(const char *fmt, ...) __attribute__((format(printf, 1, 2)));
 void die(const char *fmt, ...) {
     // reference convention: printf(message); exit(1) -- this ends the R session (SURVEY 8b "Errors")
@@ -431,6 +433,7 @@ void fatal_rc(int rc) {
 void curves_from_files(int mode, int *ploidy, int *ind_id_vec, char **samp, char **recom, double *binwidth, int *num_bins,
                        int *grid_start, int *num_donors, int *donor_label_vec, int *num_inds_rec, char **rec_labels,
                        double *weight_min, double *cutoff, int *num_surrogates, double *temp_weights, double *means) {
+    std::lock_guard<std::mutex> lk(g_api_mu);
     const int N = *num_inds_rec;
     Loaded L = load_inputs(*ploidy, samp, recom, N, rec_labels, N);
     std::vector<fgt_chrom_t> ch(L.num_chrom);
@@ -497,6 +500,7 @@ void data_read_mode3(int *ploidy, int *ind_id_vec, char **filenameSAMPread, char
 void data_read_null(int *ploidy, char **filenameSAMPread, char **filenameRECOMread, double *binwidth, int *num_bins,
                     int *grid_start, int *num_donors, int *donor_label_vec, int *num_inds_rec, char **recipient_label_vec,
                     double *weight_min, double *gridweightMAX_cutoff, double *chrom_ind_res) {
+    std::lock_guard<std::mutex> lk(g_api_mu);
     const int N = *num_inds_rec;
     const int Nc = std::min(N, 100);
     Loaded L = load_inputs(*ploidy, filenameSAMPread, filenameRECOMread, N, recipient_label_vec, Nc);
@@ -527,16 +531,19 @@ void data_read_null(int *ploidy, char **filenameSAMPread, char **filenameRECOMre
 
 int fgt_data_read_packed(const fgt_problem_t *prob, double *means, fgt_stats_t *stats) {
     if (!prob || !means) return FGT_ERR_ARG;
+    std::lock_guard<std::mutex> lk(g_api_mu);
     return Engine::get().data_read_packed(*prob, means, stats, nullptr);
 }
 
 int fgt_count_pairs_packed(const fgt_problem_t *prob, int64_t *out) {
     if (!prob || !out) return FGT_ERR_ARG;
+    std::lock_guard<std::mutex> lk(g_api_mu);
     return Engine::get().data_read_packed(*prob, nullptr, nullptr, out);
 }
 
 int fgt_data_read_null_packed(const fgt_problem_t *prob, const int32_t *rec_rows, double *chrom_ind_res, fgt_stats_t *stats) {
     if (!prob || !rec_rows || !chrom_ind_res) return FGT_ERR_ARG;
+    std::lock_guard<std::mutex> lk(g_api_mu);
     return Engine::get().data_read_null_packed(*prob, rec_rows, chrom_ind_res, stats);
 }
 

@@ -49,7 +49,10 @@ Engine &Engine::get() {
 int Engine::set_option(const char *key, double v) {
     std::string k(key);
     int iv = (int)v;
-    if (k == "device") { if (inited_ && iv != opt.device) { inited_ = false; } opt.device = iv; }
+    if (k == "device") {
+        if (inited_ && iv != opt.device) return FGT_ERR_ARG;   // buffers live on the device chosen before the first call
+        opt.device = iv;
+    }
     else if (k == "strict") opt.strict = iv;
     else if (k == "keep_raw") opt.keep_raw = iv;
     else if (k == "rand_libc") opt.rand_libc = iv;

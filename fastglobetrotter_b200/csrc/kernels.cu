@@ -996,7 +996,6 @@ void launch_commit_ordered(const CommitArgs &a, int max_slab_width, cudaStream_t
     }
 }
 
-void launch_accum_relaxed(const AccumArgs &, long long, const long long *, cudaStream_t) {}
 
 // =============================================================================================
 // 5. Projection onto surrogate pairs (reference C:578-595, mode 3: C:1190-1203):

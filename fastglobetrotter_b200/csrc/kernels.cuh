@@ -108,7 +108,6 @@ void launch_bin_sort(int n_phys, int rows_per_ind, const int32_t *row_off, const
 void launch_rand_fill(const uint32_t *base_hist, const uint32_t *level_tab, uint32_t *out, long long n_threads,
                       cudaStream_t st);
 void launch_accum_strict(const AccumArgs &a, cudaStream_t st);
-void launch_accum_relaxed(const AccumArgs &a, long long total_pairs, const long long *task_prefix, cudaStream_t st);
 void launch_project(const double *tensor, int N, int K, int G, int S, const double *tw, const int32_t *pair_kh,
                     double *results, cudaStream_t st);
 void launch_normalise(double *results, int N, int S, int G, int N_total, double *rsbuf, double *ratio, cudaStream_t st);
