@@ -946,8 +946,40 @@ int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_ro
             a.lab_off = (const int32_t *)cs.yoff.p;
             a.n_inds = Nc; a.ploidy = P; a.K = K; a.G = G; a.grid_start = pb.grid_start;
             a.bw = pb.binwidth; a.half_bw = pb.binwidth / 2.0; a.out = d_out; a.accepted = d_acc;
-            a.slab_bins = opt.null_slab_bins > 0 ? opt.null_slab_bins : std::max(8, (G + 7) / 8);
-            a.n_slabs = (G + a.slab_bins - 1) / a.slab_bins;
+            // task table: per label pair, estimate from the per-haplotype label counts how many chunk pairs it
+            // scans and accepts, and split it over as many slabs as keeps a task's fold work near a target
+            std::vector<int32_t> laboff((size_t)n_haps * (K + 2));
+            CK(cudaMemcpyAsync(laboff.data(), cs.yoff.p, laboff.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st_));
+            CK(cudaStreamSynchronize(st_));
+            std::vector<double> cnt_mean(K, 0.0);
+            for (int hp = 0; hp < n_haps; hp++)
+                for (int l = 0; l < K; l++) cnt_mean[l] += (double)(laboff[(size_t)hp * (K + 2) + l + 1] - laboff[(size_t)hp * (K + 2) + l]) / n_haps;
+            struct Cost { double c; NullTask t; };
+            std::vector<Cost> tl;
+            int max_w = 1;
+            for (int la = 0; la < K; la++)
+                for (int lb = 0; lb < K; lb++) {
+                    const double ca = cnt_mean[la], cb = cnt_mean[lb];
+                    if (ca <= 0 || cb <= 0) continue;
+                    const double scan = ca * std::ceil(std::max(cb, 1.0) / 32.0);          // steps per haplotype pair
+                    const double recs = ca * cb * 0.7;                                      // accepted pairs per haplotype pair
+                    int ns = opt.null_slab_bins > 0 ? (G + opt.null_slab_bins - 1) / opt.null_slab_bins
+                                                    : (int)std::lround(recs / 48.0);
+                    ns = std::max(1, std::min(ns, std::min(G, 64)));
+                    const int w = (G + ns - 1) / ns;
+                    for (int b = 0; b < G; b += w) {
+                        NullTask t{la, lb, b, std::min(G, b + w)};
+                        tl.push_back({scan * 40.0 + recs / ns / 32.0 * 300.0, t});
+                        max_w = std::max(max_w, t.b_hi - t.b_lo);
+                    }
+                }
+            std::stable_sort(tl.begin(), tl.end(), [](const Cost &x, const Cost &y) { return x.c > y.c; });
+            std::vector<NullTask> tasks(tl.size());
+            for (size_t q = 0; q < tl.size(); q++) tasks[q] = tl[q].t;
+            NullTask *d_tasks = d_slabs_.as<NullTask>(tasks.size() + 1);
+            if (!d_tasks) return FGT_ERR_CUDA;
+            CK(cudaMemcpyAsync(d_tasks, tasks.data(), tasks.size() * sizeof(NullTask), cudaMemcpyHostToDevice, st_));
+            a.tasks = d_tasks; a.n_tasks = (int)tasks.size(); a.max_slab_bins = max_w;
             launch_null_strict(a, st_);
             launches_ += 1;
             stx.accum_launches += 1;

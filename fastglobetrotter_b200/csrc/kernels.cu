@@ -1251,20 +1251,20 @@ __global__ void __launch_bounds__(128) k_null_strict(const NullArgs a) {
     const int wpb = blockDim.x >> 5;
     const int K = a.K, G = a.G;
     const long long task = (long long)blockIdx.x * wpb + wid;
-    const int n_slabs = a.n_slabs;
-    if (task >= (long long)K * K * n_slabs) return;
-    const int slab = (int)(task % n_slabs);
-    const int lab = (int)(task / n_slabs);
-    const int lA = lab / K, lB = lab % K;                  // 0-based labels
-    const int b_lo = slab * a.slab_bins, b_hi = min(G, b_lo + a.slab_bins);   // owned bins (relative to grid_start)
+    if (task >= a.n_tasks) return;
+    // task table (built on the host from the label counts): costliest first; hot label pairs are split
+    // over many narrow slabs, cold ones over few wide ones (every slab of a pair re-walks the pair's chunk pairs)
+    const NullTask tk = a.tasks[task];
+    const int lA = tk.lA, lB = tk.lB;                      // 0-based labels
+    const int b_lo = tk.b_lo, b_hi = tk.b_hi;              // owned bins (relative to grid_start)
     const int sbw = b_hi - b_lo;
-    const int per_warp = 3 * kNullStage + 2 * kNullQ + a.slab_bins;            // doubles
-    double *sposB = reinterpret_cast<double *>(nsm) + (size_t)wid * per_warp;
-    double *shalfB = sposB + kNullStage;
-    double *swB = shalfB + kNullStage;
-    double *qdist = swB + kNullStage;
-    double *qval = qdist + kNullQ;
-    double *tile = qval + kNullQ;
+    const int per_warp = 3 * kNullStage + 2 * kNullQ + a.max_slab_bins;         // doubles
+    double *__restrict__ sposB = reinterpret_cast<double *>(nsm) + (size_t)wid * per_warp;
+    double *__restrict__ shalfB = sposB + kNullStage;
+    double *__restrict__ swB = shalfB + kNullStage;
+    double *__restrict__ qdist = swB + kNullStage;
+    double *__restrict__ qval = qdist + kNullQ;
+    double *__restrict__ tile = qval + kNullQ;
     double *gout = a.out + ((size_t)lA * K + lB) * G + b_lo;
     for (int i = lane; i < sbw; i += 32) tile[i] = gout[i];
     __syncwarp();
@@ -1332,29 +1332,53 @@ __global__ void __launch_bounds__(128) k_null_strict(const NullArgs a) {
                 }
                 __syncwarp();
             }
-            for (int ia = 0; ia < cntA; ia++) {
+            auto push = [&](bool surv, double dist, double val) {      // ordered append of one step's survivors
+                const unsigned m = __ballot_sync(kFull, surv);
+                if (m) {
+                    if (surv) { const int pos = qn + __popc(m & lt); qdist[pos] = dist; qval[pos] = val; }
+                    qn += __popc(m);
+                    __syncwarp();
+                    if (qn >= 32) { fold32(32); qn -= 32; }
+                }
+            };
+            auto test = [&](const Chunk &A, double halfA, int jb, bool &surv, double &dist, double &val) {
+                surv = false; dist = 0.0; val = 0.0;
+                if (jb < cntB) {
+                    double pbv, hb, wb;
+                    if (staged) { pbv = sposB[jb]; hb = shalfB[jb]; wb = swB[jb]; }
+                    else { const Chunk B = CB[jb]; pbv = B.pos; hb = __dmul_rn(B.size, 0.5); wb = B.w; }
+                    dist = fabs(__dsub_rn(A.pos, pbv));            // reference C:1015
+                    // C:1019-1020: dist >= size_A/2 + size_B/2 ; and the slab's distance window
+                    surv = dist >= dwin_lo && dist <= dwin_hi && dist >= __dadd_rn(halfA, hb);
+                    val = __dmul_rn(A.w, wb);
+                }
+            };
+            int ia = 0;
+            if (cntB <= 32) {
+                // the whole B group is one step: evaluate four A chunks at once (independent), queue in order
+                for (; ia + 4 <= cntA; ia += 4) {
+                    bool s[4]; double d[4], v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) { const Chunk A = CA[ia + u]; test(A, __dmul_rn(A.size, 0.5), lane, s[u], d[u], v[u]); }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) push(s[u], d[u], v[u]);
+                }
+            }
+            for (; ia < cntA; ia++) {
                 const Chunk A = CA[ia];                    // same address in every lane: one broadcast load
                 const double halfA = __dmul_rn(A.size, 0.5);
-                for (int jb0 = 0; jb0 < cntB; jb0 += 32) {
-                    const int jb = jb0 + lane;
-                    bool surv = false;
-                    double dist = 0.0, val = 0.0;
-                    if (jb < cntB) {
-                        double pbv, hb, wb;
-                        if (staged) { pbv = sposB[jb]; hb = shalfB[jb]; wb = swB[jb]; }
-                        else { const Chunk B = CB[jb]; pbv = B.pos; hb = __dmul_rn(B.size, 0.5); wb = B.w; }
-                        dist = fabs(__dsub_rn(A.pos, pbv));            // reference C:1015
-                        // C:1019-1020: dist >= size_A/2 + size_B/2 ; and the slab's distance window
-                        surv = dist >= dwin_lo && dist <= dwin_hi && dist >= __dadd_rn(halfA, hb);
-                        val = __dmul_rn(A.w, wb);
-                    }
-                    const unsigned m = __ballot_sync(kFull, surv);
-                    if (m) {
-                        if (surv) { const int pos = qn + __popc(m & lt); qdist[pos] = dist; qval[pos] = val; }
-                        qn += __popc(m);
-                        __syncwarp();
-                        if (qn >= 32) { fold32(32); qn -= 32; }
-                    }
+                int jb0 = 0;
+                for (; jb0 + 64 <= cntB + 31 && jb0 + 32 < cntB; jb0 += 64) {      // two steps at a time
+                    bool s0, s1; double d0, d1, v0, v1;
+                    test(A, halfA, jb0 + lane, s0, d0, v0);
+                    test(A, halfA, jb0 + 32 + lane, s1, d1, v1);
+                    push(s0, d0, v0);
+                    push(s1, d1, v1);
+                }
+                for (; jb0 < cntB; jb0 += 32) {
+                    bool s0; double d0, v0;
+                    test(A, halfA, jb0 + lane, s0, d0, v0);
+                    push(s0, d0, v0);
                 }
             }
         }
@@ -1366,8 +1390,9 @@ __global__ void __launch_bounds__(128) k_null_strict(const NullArgs a) {
 
 void launch_null_strict(const NullArgs &a, cudaStream_t st) {
     const int wpb = 4;
-    long long tasks = (long long)a.K * a.K * a.n_slabs;
-    size_t smem = (size_t)wpb * (3 * kNullStage + 2 * kNullQ + a.slab_bins) * sizeof(double);
+    long long tasks = a.n_tasks;
+    if (tasks <= 0) return;
+    size_t smem = (size_t)wpb * (3 * kNullStage + 2 * kNullQ + a.max_slab_bins) * sizeof(double);
     k_null_strict<<<(unsigned)((tasks + wpb - 1) / wpb), wpb * 32, smem, st>>>(a);
 }
 

@@ -116,12 +116,14 @@ void launch_outer_weights(const double *w, int S, int K, double *out, cudaStream
 void launch_expand_raw(const double *tensor, int N, int K, int G, double *out_full, cudaStream_t st);
 
 // NULL-individual path
+struct NullTask { int32_t lA, lB, b_lo, b_hi; };   // one ordered fold: label pair x range of fine bins
 struct NullArgs {
     const Chunk *chunks;        // per haplotype, grouped by population label (stable), see k_null_group
     const int32_t *hap_base;    // [n_haps+1]
     const int32_t *lab_off;     // [n_haps][K+1] offsets (relative to hap_base) of each label group (labels 1..K)
     int32_t n_inds, ploidy, K, G, grid_start;
-    int32_t n_slabs, slab_bins; // every label pair is split over slabs of fine bins (independent ordered folds)
+    const NullTask *tasks;      // costliest first
+    int32_t n_tasks, max_slab_bins;
     double bw, half_bw;
     double *out;                // [K][K][G]
     unsigned long long *accepted;
