@@ -794,6 +794,8 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
                  : "memory");
 }
 
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
 template <bool TILE_SMEM>
 __global__ void __launch_bounds__(64) k_commit_ordered(const CommitArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -870,7 +872,7 @@ __global__ void __launch_bounds__(64) k_commit_ordered(const CommitArgs a) {
                             const UpdateRec *src = a.recs + dir[i].base;
                             int off = 0;
                             while (off < c) {              // stages are packed: a stage takes pieces of consecutive regions
-                                if (!open) { mbar_wait(&empty[stage], phase ^ 1); open = true; fill = 0; }
+                                if (!open) { mbar_wait(&empty[stage], phase ^ 1); fence_proxy_async_smem(); open = true; fill = 0; }
                                 const int piece = min(c - off, kStageRecs - fill);
                                 const unsigned bytes = (unsigned)piece * (unsigned)sizeof(UpdateRec);
                                 mbar_expect_tx(&full[stage], bytes);
@@ -926,6 +928,10 @@ __global__ void __launch_bounds__(64) k_commit_ordered(const CommitArgs a) {
                     for (int h = 0; h < kStageSteps; h++)
                         if (32 * h + lane < s.c) { const UpdateRec r = rg[32 * h + lane]; s.cell[h] = TILE_SMEM ? r.pad : r.cell; s.val[h] = r.val; }
                 }
+                // The refill of this stage is a TMA write (async proxy); the reads above are generic-proxy reads.
+                // Without the cross-proxy fence the bulk copy can land before these loads have sampled the
+                // ring (seen on B200 as a few wrong cells whenever another kernel shares the GPU).
+                fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[stage]);     // records are in registers: the stage can be refilled
                 if (++stage == kStages) { stage = 0; phase ^= 1; }

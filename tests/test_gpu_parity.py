@@ -463,3 +463,54 @@ def test_null_edge_shapes(lib, oracle):
     n_o, _ = oracle.data_read_null_packed(1, 2, chrom, rows, 0.1, 60, 10, K, dl, 0.0, 1.0)
     n_g, _ = lib.data_read_null_packed(1, 2, chrom, rows, 0.1, 60, 10, K, dl, 0.0, 1.0)
     assert np.array_equal(n_g, n_o)
+
+
+def test_repeatable_at_scale_with_other_kernels_on_the_gpu(lib):
+    """Regression: the ordered commit streams records through a TMA ring; its refill used to race with the
+    consumer's shared-memory reads whenever the timing was disturbed (a second chromosome's evaluation, or
+    any foreign kernel, running beside the commit).  Two chromosomes x several batches of individuals at
+    benchmark-like size, repeated, with a noisy neighbour on another stream: every repeat must give the
+    bits of the single-phase kernel (which the small-size tests pin to the oracle)."""
+    import torch
+    from fastglobetrotter_b200.synth_torch import make_chromosome_device
+    dev = torch.device("cuda", 0)
+    N, L, K, G, S, nchr = 60, 60_000, 20, 300, 4, 2
+    spec = synth.SynthSpec(n_chrom=nchr, n_inds=N, n_snps=L, K=K, nsamples=10, seed=77)
+    chrom, keep = [], []
+    for h in range(nchr):
+        pos, rate, lab = make_chromosome_device(spec, h, dev)
+        keep.append(lab)
+        chrom.append({"pos": pos, "rate": rate, "labels": (lab.data_ptr(), 2, lab.shape[0])})
+    torch.cuda.synchronize()
+    dl = spec.donor_label_vec()
+    tw = np.random.default_rng(0).random(K * K * S * S)
+    ids = np.repeat(np.arange(N), nchr).astype(np.int32)
+    x = torch.empty(1 << 27, dtype=torch.float32, device=dev)
+    y = torch.empty_like(x)
+    side = torch.cuda.Stream()
+    lib.set_option("rand_libc", 0)
+    try:
+        lib.set_option("accum_impl", 1)
+        lib.srand(11)
+        m_ref, raw_ref, st_ref = lib.data_read_packed(1, 2, 10, chrom, ids, 0.1, G, 10, K, dl, 0.0, 1.0, S, tw, want_raw=True)
+        raw_ref = raw_ref.copy()
+        lib.set_option("accum_impl", 2)
+        for bp in (0, st_ref["pairs"] // 5):
+            lib.set_option("batch_pairs", float(bp))
+            for rep in range(4):
+                if rep >= 2:
+                    with torch.cuda.stream(side):
+                        for _ in range(30):
+                            y.copy_(x)
+                lib.srand(11)
+                m, raw, st = lib.data_read_packed(1, 2, 10, chrom, ids, 0.1, G, 10, K, dl, 0.0, 1.0, S, tw, want_raw=True)
+                torch.cuda.synchronize()
+                assert st["pairs"] == st_ref["pairs"]
+                if bp:
+                    assert st["accum_launches"] > nchr
+                bad = np.where((raw != raw_ref).reshape(raw.shape[0], -1).any(axis=1))[0]
+                assert bad.size == 0, (bp, rep, bad[:10])
+                assert np.array_equal(m, m_ref), (bp, rep)
+    finally:
+        lib.set_option("batch_pairs", 0)
+        lib.set_option("accum_impl", 2)
