@@ -689,7 +689,7 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
                 span_begin(3, st_);
                 CK(cudaMemsetAsync(d_regions, 0, n_ent * sizeof(RegionEnt), st_));
                 EvalArgs ea{};
-                ea.cp = cpd; ea.draws = (const uint2 *)d_draws;
+                ea.cp = cpd; ea.draws = (const uint2 *)d_draws; ea.draws_limit = nthreads * (long long)kRun / 2;
                 ea.pair_base = pbase; ea.phys_of = pphys;
                 ea.N = Nb; ea.K = K; ea.G = G; ea.grid_start = pb.grid_start; ea.mode = pb.mode; ea.n_slots = plan.n_slots;
                 ea.bw = pb.binwidth; ea.half_bw = pb.binwidth / 2.0;

@@ -687,6 +687,14 @@ __global__ void __launch_bounds__(128, 8) k_eval_pairs(const EvalArgs a) {
     if (nb - 1 - j < dmax) dmax = nb - 1 - j;
     int bad = 0;
     const unsigned lt = (1u << lane) - 1;
+    // The row's draws are consumed strictly front to back (segment d+1 starts where segment d ends), so the 64
+    // draws of the next iteration are fetched while the current one waits for its chunk gathers.
+    uint2 nr0, nr1;
+    auto prefetch = [&](long long p) {
+        nr0 = (p + lane < a.draws_limit) ? a.draws[p + lane] : make_uint2(0, 0);
+        nr1 = (p + 32 + lane < a.draws_limit) ? a.draws[p + 32 + lane] : make_uint2(0, 0);
+    };
+    prefetch(row_pair0 + yo[0]);
     for (int d = 1; d <= dmax; d++) {
         const int y0 = yo[d - 1];
         const int Y = yo[d] - y0;
@@ -695,16 +703,14 @@ __global__ void __launch_bounds__(128, 8) k_eval_pairs(const EvalArgs a) {
         const int t2 = T[k], f2 = F[k];
         const double inv2 = __ddiv_rn(1.0, (double)t2);
         const long long seg = row_pair0 + y0;
-        const uint2 *dr = a.draws + seg;
         UpdateRec *reg = a.recs + seg * ns;
         const int slab0 = a.first_slab[d];
         const Chunk *binB = ch + f2;
         int c[kMaxSlots] = {0, 0, 0, 0};
         for (int base = 0; base < Y; base += 64) {
             const int q0 = base + lane, q1 = base + 32 + lane;
-            uint2 r0 = make_uint2(0, 0), r1 = make_uint2(0, 0);
-            if (q0 < Y) r0 = dr[q0];
-            if (q1 < Y) r1 = dr[q1];
+            const uint2 r0 = nr0, r1 = nr1;
+            prefetch(seg + min(base + 64, Y));
             PairEval e[2];
             e[0] = eval_pair(q0 < Y, r0, t1, inv1, t2, inv2, binA, binB, a, slab0, bad);
             e[1] = eval_pair(q1 < Y, r1, t1, inv1, t2, inv2, binA, binB, a, slab0, bad);
@@ -762,6 +768,7 @@ void launch_eval_pairs(const EvalArgs &a, cudaStream_t st) {
 constexpr int kStages = 3;        // ring depth
 constexpr int kStageRecs = 128;   // records per ring stage (four consumer steps); stages are packed across regions
 constexpr int kStageSteps = kStageRecs / 32;
+constexpr int kConsumers = 2;     // consumer warps per CTA; each owns the tile cells with local % kConsumers == warp
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
@@ -797,7 +804,7 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 template <bool TILE_SMEM>
-__global__ void __launch_bounds__(64) k_commit_ordered(const CommitArgs a) {
+__global__ void __launch_bounds__(32 * (kConsumers + 1)) k_commit_ordered(const CommitArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     UpdateRec *ring = reinterpret_cast<UpdateRec *>(smem_raw);                         // [kStages][kStageRecs]
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kStages * kStageRecs * sizeof(UpdateRec));
@@ -812,7 +819,7 @@ __global__ void __launch_bounds__(64) k_commit_ordered(const CommitArgs a) {
     const int P = a.K * (a.K + 1) / 2;
     const int total_tasks = a.N * a.n_slabs;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < kStages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], kConsumers); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     // ring position: carried across tasks (the end marker of a task occupies a stage like any other)
@@ -847,7 +854,7 @@ __global__ void __launch_bounds__(64) k_commit_ordered(const CommitArgs a) {
         }
         __syncthreads();
 
-        if (wid == 1) {
+        if (wid == kConsumers) {
             // ------------------------------ producer ------------------------------
             const long long n_ent = (long long)(a.cp.nb - 1) * a.nd_max;
             const RegionEnt *ents = a.regions + ((size_t)n * a.n_slabs + slab_i) * n_ent;
@@ -912,8 +919,11 @@ __global__ void __launch_bounds__(64) k_commit_ordered(const CommitArgs a) {
             // the same cell: match.any.  (Measured alternatives, both slower on B200: one ballot per index bit --
             // 13 votes cost more than one match.any; stamping the tile with lane ids to detect collisions first --
             // duplicates occur in about half the steps of this workload, so the slow path is the common path.)
+            // Several consumer warps read every stage; each folds only the cells it owns, so a cell's additions
+            // stay in stream order.  Records of other warps share one sentinel key: match.any's cost grows with
+            // the number of distinct keys, so every warp's vote gets cheaper as well.
             auto same_cell_mask = [&](int cell) -> unsigned {
-                return __match_any_sync(kFull, cell >= 0 ? (unsigned)cell : (0x80000000u | (unsigned)lane));
+                return __match_any_sync(kFull, cell >= 0 ? (unsigned)cell : 0x80000000u);
             };
             struct Staged { int c; int cell[kStageSteps]; double val[kStageSteps]; unsigned g[kStageSteps]; };
             auto fetch = [&]() -> Staged {
@@ -926,7 +936,10 @@ __global__ void __launch_bounds__(64) k_commit_ordered(const CommitArgs a) {
                     const UpdateRec *rg = ring + stage * kStageRecs;
 #pragma unroll
                     for (int h = 0; h < kStageSteps; h++)
-                        if (32 * h + lane < s.c) { const UpdateRec r = rg[32 * h + lane]; s.cell[h] = TILE_SMEM ? r.pad : r.cell; s.val[h] = r.val; }
+                        if (32 * h + lane < s.c) {
+                            const UpdateRec r = rg[32 * h + lane];
+                            if ((unsigned)r.pad % kConsumers == (unsigned)wid) { s.cell[h] = TILE_SMEM ? r.pad : r.cell; s.val[h] = r.val; }
+                        }
                 }
                 // The refill of this stage is a TMA write (async proxy); the reads above are generic-proxy reads.
                 // Without the cross-proxy fence the bulk copy can land before these loads have sampled the
@@ -964,7 +977,7 @@ __global__ void __launch_bounds__(64) k_commit_ordered(const CommitArgs a) {
                     for (int h = 0; h < kStageSteps; h++)
                         if (32 * h < cur.c) fold(cur.cell[h], cur.val[h], cur.g[h]);
                 }
-                n_acc += (unsigned long long)cur.c;
+                if (wid == 0) n_acc += (unsigned long long)cur.c;
                 cur = nxt;
             }
         }
@@ -995,10 +1008,10 @@ void launch_commit_ordered(const CommitArgs &a, int max_slab_width, cudaStream_t
         }
         const long long per_sm = std::max<long long>(1, (227 * 1024) / (long long)(ctrl_bytes + tile_bytes + 1024));
         const long long grid = std::min<long long>(tasks, 148 * std::min<long long>(per_sm, 32));
-        k_commit_ordered<true><<<(unsigned)grid, 64, ctrl_bytes + tile_bytes, st>>>(a);
+        k_commit_ordered<true><<<(unsigned)grid, 32 * (kConsumers + 1), ctrl_bytes + tile_bytes, st>>>(a);
     } else {
         const long long grid = std::min<long long>(tasks, 148 * 16);
-        k_commit_ordered<false><<<(unsigned)grid, 64, ctrl_bytes, st>>>(a);
+        k_commit_ordered<false><<<(unsigned)grid, 32 * (kConsumers + 1), ctrl_bytes, st>>>(a);
     }
 }
 

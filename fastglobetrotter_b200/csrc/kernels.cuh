@@ -61,6 +61,7 @@ constexpr int kMaxSlots = 4;   // slabs a coarse-bin separation can reach (regio
 struct EvalArgs {
     ChromPrep cp;
     const uint2 *draws;
+    long long draws_limit;        // pairs of draws in `draws` (prefetches are clamped to it)
     const long long *pair_base;   // [N]
     const int32_t *phys_of;       // [N]
     int32_t N, K, G, grid_start, mode, n_slots;

@@ -66,6 +66,29 @@ def test_rand_stream_matches_libc(lib):
     assert after == want[3010:].tolist()
 
 
+def test_rand_stream_far_into_a_launch(lib, oracle):
+    """blocks >= 256 of one k_rand_fill launch take their start state through the level-2 jump table (the
+    benchmark workload uses ~600 blocks per launch): compare windows around the table boundaries with the
+    host polynomial jump-ahead (itself pinned to libc stepping in the CPU suite) + the oracle's stepping."""
+    per_block = 1984 * 256
+    n = per_block * 520 + 12345
+    lib.set_option("rand_libc", 0)
+    lib.srand(4242)
+    got = lib.rand_fill(n)
+    hist = np.zeros(31, dtype=np.uint32)
+    for at in (0, per_block * 255 + 1984 * 200, per_block * 256 - 40, per_block * 256, per_block * 257 + 11, per_block * 511 + 1984 * 255 - 3,
+               per_block * 512 - 1, n - 3000):
+        assert lib.lib.fgt_rand_host_jump(C.c_uint(4242), C.c_uint64(at), hist.ctypes.data_as(C.c_void_p)) == 0
+        oracle.set_history(hist)
+        m = min(2500, n - at)
+        want = np.array([oracle.rand() for _ in range(m)], dtype=np.int32)
+        assert np.array_equal(got[at:at + m], want), at
+    # the stream position after the launch
+    assert lib.lib.fgt_rand_host_jump(C.c_uint(4242), C.c_uint64(n), hist.ctypes.data_as(C.c_void_p)) == 0
+    oracle.set_history(hist)
+    assert np.array_equal(lib.rand_fill(64), np.array([oracle.rand() for _ in range(64)], dtype=np.int32))
+
+
 @pytest.mark.parametrize("weight_min", [0.0, 3.0])
 def test_chunk_builder(lib, oracle, weight_min):
     spec = synth.SynthSpec(n_chrom=1, n_inds=1, n_snps=5000, K=5, nsamples=3, rate=3e-7, seed=7)
