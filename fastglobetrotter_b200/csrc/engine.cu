@@ -62,6 +62,7 @@ int Engine::set_option(const char *key, double v) {
     else if (k == "verbose") opt.verbose = iv;
     else if (k == "reuse_prep") opt.reuse_prep = iv;
     else if (k == "accum_impl") opt.accum_impl = iv;
+    else if (k == "spec_rand") opt.spec_rand = iv;
     else if (k == "batch_pairs") opt.batch_pairs = v;
     else if (k == "blocks") opt.blocks = iv;
     else if (k == "ranges") opt.ranges = iv;
@@ -83,6 +84,7 @@ double Engine::get_option(const char *key) {
     if (k == "verbose") return opt.verbose;
     if (k == "reuse_prep") return opt.reuse_prep;
     if (k == "accum_impl") return opt.accum_impl;
+    if (k == "spec_rand") return opt.spec_rand;
     if (k == "batch_pairs") return opt.batch_pairs;
     if (k == "blocks") return opt.blocks;
     if (k == "ranges") return opt.ranges;
@@ -106,6 +108,7 @@ int Engine::ensure_init() {
     if (!st_) CK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
     if (!st_prep_) CK(cudaStreamCreateWithFlags(&st_prep_, cudaStreamNonBlocking));
     if (!st_copy_) CK(cudaStreamCreateWithFlags(&st_copy_, cudaStreamNonBlocking));
+    if (!st_aux_) CK(cudaStreamCreateWithFlags(&st_aux_, cudaStreamNonBlocking));
     if (!st_commit_) {
         int lo_p = 0, hi_p = 0;
         cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
@@ -259,11 +262,12 @@ int Engine::prep_chromosome(const fgt_problem_t &pb, int h, const int32_t *rowma
         stx.h2d_bytes += (int64_t)bytes;
         d_lab = buf;
     }
-    int32_t *d_counts = d_counts_.as<int32_t>(rows), *d_rowoff = d_rowoff_.as<int32_t>(rows + 1);
-    if (!d_counts || !d_rowoff) return FGT_ERR_CUDA;
+    int32_t *d_counts = d_counts_.as<int32_t>((size_t)rows * kChunkSegs), *d_rowoff = d_rowoff_.as<int32_t>(rows + 1);
+    int32_t *d_segoff = d_segoff_.as<int32_t>((size_t)rows * kChunkSegs + 1);
+    if (!d_counts || !d_rowoff || !d_segoff) return FGT_ERR_CUDA;
     launch_chunk_count(d_lab, rowmap_dev, pb.label_bytes, L, rows, pb.weight_min, d_counts, st_);
-    launch_exclusive_scan_i32(d_counts, d_rowoff, rows, st_);
-    launches_ += 2;
+    launch_chunk_scan(d_counts, d_segoff, d_rowoff, rows, st_);
+    launches_ += 3;
     int32_t total_chunks = 0;
     CK(cudaMemcpyAsync(&total_chunks, d_rowoff + rows, sizeof(int32_t), cudaMemcpyDeviceToHost, st_));
     // the copies above read host vectors that die at scope exit: synchronise here (also yields total_chunks)
@@ -275,7 +279,7 @@ int Engine::prep_chromosome(const fgt_problem_t &pb, int h, const int32_t *rowma
     double *d_cstart = d_cstart_.as<double>(total_chunks), *d_cend = d_cend_.as<double>(total_chunks);
     int32_t *d_chap = d_chap_.as<int32_t>(total_chunks);
     if (!d_cstart || !d_cend || !d_chap) return FGT_ERR_CUDA;
-    launch_chunk_emit(d_lab, rowmap_dev, pb.label_bytes, L, rows, pb.weight_min, d_rowoff, d_cum, d_inc, d_cstart, d_cend,
+    launch_chunk_emit(d_lab, rowmap_dev, pb.label_bytes, L, rows, pb.weight_min, d_segoff, d_cum, d_inc, d_cstart, d_cend,
                       d_chap, st_);
     launches_ += 1;
     Chunk *d_sorted = cs.sorted.as<Chunk>(total_chunks);
@@ -353,16 +357,15 @@ int Engine::prep_block(const fgt_problem_t &pb, int h, int p0, int p1, int blk, 
     const int np = p1 - p0, rows = np * PM;
     const int K = pb.num_donors;
     cudaStream_t sp = st_prep_;
-    if (copy_done) CK(cudaStreamWaitEvent(sp, copy_done, 0));
     const char *lab_blk = (const char *)d_lab + (size_t)p0 * PM * L * pb.label_bytes;
-    int32_t *d_counts = d_counts_.as<int32_t>(rows), *d_rowoff = d_rowoff_.as<int32_t>(rows + 1);
-    if (!d_counts || !d_rowoff) return FGT_ERR_CUDA;
-    launch_chunk_count(lab_blk, nullptr, pb.label_bytes, L, rows, pb.weight_min, d_counts, sp);
-    launch_exclusive_scan_i32(d_counts, d_rowoff, rows, sp);
-    launches_ += 2;
-    int32_t total_chunks = 0;
-    CK(cudaMemcpyAsync(&total_chunks, d_rowoff + rows, sizeof(int32_t), cudaMemcpyDeviceToHost, sp));
+    if (!(count_pending_ && count_key_[0] == h && count_key_[1] == p0 && count_key_[2] == p1)) {
+        int rc = prep_count(pb, h, p0, p1, d_lab, copy_done);
+        if (rc) return rc;
+    }
+    count_pending_ = false;
+    int32_t *d_rowoff = (int32_t *)d_rowoff_.p, *d_segoff = (int32_t *)d_segoff_.p;
     CK(cudaStreamSynchronize(sp));
+    const int32_t total_chunks = *pin_small_;
     stx.d2h_bytes += 4;
     if (total_chunks <= 0) return FGT_ERR_ARG;
     cs.n_chunks += total_chunks;
@@ -372,7 +375,7 @@ int Engine::prep_block(const fgt_problem_t &pb, int h, int p0, int p1, int blk, 
     if ((int)cs.sorted_blocks.size() <= blk) cs.sorted_blocks.resize(blk + 1);
     Chunk *d_sorted = cs.sorted_blocks[blk].as<Chunk>(total_chunks);
     if (!d_cstart || !d_cend || !d_chap || !d_sorted) return FGT_ERR_CUDA;
-    launch_chunk_emit(lab_blk, nullptr, pb.label_bytes, L, rows, pb.weight_min, d_rowoff, (const double *)cs.cum.p,
+    launch_chunk_emit(lab_blk, nullptr, pb.label_bytes, L, rows, pb.weight_min, d_segoff, (const double *)cs.cum.p,
                       (const double *)cs.inc.p, d_cstart, d_cend, d_chap, sp);
     const int nb = cs.nb, W = cs.W;
     size_t cm = (size_t)np * PM * nb;
@@ -390,6 +393,28 @@ int Engine::prep_block(const fgt_problem_t &pb, int h, int p0, int p1, int blk, 
     CK(cudaMemcpyAsync(cs.totals.data() + p0, d_tot, np * sizeof(long long), cudaMemcpyDeviceToHost, sp));
     CK(cudaStreamSynchronize(sp));
     stx.d2h_bytes += (int64_t)np * 8;
+    return FGT_OK;
+}
+
+// First step of prep_block, separately launchable: count the chunks of the block's rows, scan, and start the
+// read-back of the total (pinned), so that host-side work can run while the labels stream through the count kernel.
+int Engine::prep_count(const fgt_problem_t &pb, int h, int p0, int p1, const void *d_lab, cudaEvent_t copy_done) {
+    const int L = pb.chrom[h].nsites;
+    const int PM = pb.ploidy * pb.nsamples;
+    const int rows = (p1 - p0) * PM;
+    cudaStream_t sp = st_prep_;
+    if (!pin_small_ && cudaHostAlloc((void **)&pin_small_, 64, cudaHostAllocDefault) != cudaSuccess) return FGT_ERR_CUDA;
+    if (copy_done) CK(cudaStreamWaitEvent(sp, copy_done, 0));
+    const char *lab_blk = (const char *)d_lab + (size_t)p0 * PM * L * pb.label_bytes;
+    int32_t *d_counts = d_counts_.as<int32_t>((size_t)rows * kChunkSegs), *d_rowoff = d_rowoff_.as<int32_t>(rows + 1);
+    int32_t *d_segoff = d_segoff_.as<int32_t>((size_t)rows * kChunkSegs + 1);
+    if (!d_counts || !d_rowoff || !d_segoff) return FGT_ERR_CUDA;
+    launch_chunk_count(lab_blk, nullptr, pb.label_bytes, L, rows, pb.weight_min, d_counts, sp);
+    launch_chunk_scan(d_counts, d_segoff, d_rowoff, rows, sp);
+    launches_ += 3;
+    CK(cudaMemcpyAsync(pin_small_, d_rowoff + rows, sizeof(int32_t), cudaMemcpyDeviceToHost, sp));
+    count_pending_ = true;
+    count_key_[0] = h; count_key_[1] = p0; count_key_[2] = p1;
     return FGT_OK;
 }
 
@@ -418,10 +443,11 @@ int Engine::setup_chromosome(const fgt_problem_t &pb, int h, ChromState &cs, fgt
         !cs.chunk_ptr.as<const Chunk *>(n_phys))
         return FGT_ERR_CUDA;
     cs.totals.assign(n_phys, 0);
-    CK(cudaMemcpyAsync(d_cum, cum.data(), L * sizeof(double), cudaMemcpyHostToDevice, st_prep_));
-    CK(cudaMemcpyAsync(d_inc, inc.data(), L * sizeof(double), cudaMemcpyHostToDevice, st_prep_));
-    CK(cudaMemcpyAsync(d_etab, etab.data(), W * sizeof(double), cudaMemcpyHostToDevice, st_prep_));
-    CK(cudaStreamSynchronize(st_prep_));     // the host vectors die here
+    // on their own stream: the prep stream may already be streaming labels through the chunk count
+    CK(cudaMemcpyAsync(d_cum, cum.data(), L * sizeof(double), cudaMemcpyHostToDevice, st_aux_));
+    CK(cudaMemcpyAsync(d_inc, inc.data(), L * sizeof(double), cudaMemcpyHostToDevice, st_aux_));
+    CK(cudaMemcpyAsync(d_etab, etab.data(), W * sizeof(double), cudaMemcpyHostToDevice, st_aux_));
+    CK(cudaStreamSynchronize(st_aux_));      // the host vectors die here; later prep-stream work is enqueued after this
     stx.h2d_bytes += 2LL * L * sizeof(double);
     return FGT_OK;
 }
@@ -611,6 +637,30 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
         if (!d_taskctr) return FGT_ERR_CUDA;
         CK(cudaMemsetAsync(d_taskctr, 0, ((size_t)Cn * N + 2) * sizeof(int), st_));
     }
+    // ---- speculative draws: the first batch's share of the rand() stream starts at a known position, only its
+    // length depends on the chunking.  Generate as many runs as the previous call's first batch needed while the
+    // chunk/bin kernels run; the batch then tops up (or ignores the surplus).
+    long long spec_threads = 0, spec_A4 = -1;
+    uint32_t *spec_ptr = nullptr;
+    const long long shape_sig = (((((long long)N * 1000003 + pb.n_packed_inds) * 1000003 + pb.chrom[0].nsites) * 31 + pb.nsamples) * 31 +
+                                 pb.ploidy) * 1009 + pb.num_bins * 4 + pb.mode;
+    if (shape_sig != last_shape_sig_) last_first_batch_threads_ = 0;     // only repeat calls of one problem shape speculate
+    last_shape_sig_ = shape_sig;
+    if (!count_only && opt.spec_rand && last_first_batch_threads_ >= 256) {
+        const long long lo0 = pb.pair_offset ? pb.pair_offset[0] : 0;
+        spec_A4 = (2 * lo0) & ~3LL;
+        spec_threads = last_first_batch_threads_ & ~255LL;
+        spec_ptr = d_draws_.as<uint32_t>((size_t)spec_threads * kRun + 4);
+        if (!spec_ptr) return FGT_ERR_CUDA;
+        History hs = apply_jump(poly_pow_E((uint64_t)spec_A4), h0);
+        uint32_t *pin_spec = pin_hist + (size_t)Cn * N * kLag;        // the spare last slot
+        std::memcpy(pin_spec, hs.x, sizeof hs.x);
+        CK(cudaMemcpyAsync(d_hist + (size_t)Cn * N * kLag, pin_spec, sizeof hs.x, cudaMemcpyHostToDevice, st_));
+        span_begin(4, st_);
+        launch_rand_fill(d_hist + (size_t)Cn * N * kLag, (const uint32_t *)d_level_tab_.p, spec_ptr, spec_threads, st_);
+        launches_ += 1;
+        span_end(st_);
+    }
     auto launch_range = [&](int h, int n0, int n1, cudaEvent_t ready) -> int {
         ChromState &cs = chroms_[h];
         int n = n0;
@@ -652,10 +702,15 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
             uint32_t *d_draws = draws_buf.as<uint32_t>((size_t)nthreads * kRun + 4);
             if (!d_draws) return FGT_ERR_CUDA;
             if (!first_eval) { first_eval = new_timed_event(); CK(cudaEventRecord(first_eval, st_)); }
-            span_begin(0, st_);
-            launch_rand_fill(dh, (const uint32_t *)d_level_tab_.p, d_draws, nthreads, st_);
-            launches_ += 1;
-            span_end(st_);
+            long long have = 0;                       // runs already generated speculatively for this very range
+            if (batch_seq == 0 && spec_threads > 0 && A4 == spec_A4 && d_draws == spec_ptr) have = std::min(spec_threads, nthreads & ~255LL);
+            if (batch_seq == 0) last_first_batch_threads_ = nthreads;
+            if (have < nthreads) {
+                span_begin(0, st_);
+                launch_rand_fill(dh, (const uint32_t *)d_level_tab_.p, d_draws, nthreads, st_, have);
+                launches_ += 1;
+                span_end(st_);
+            }
             ChromPrep cpd{};
             cpd.nb = cs.nb; cpd.W = cs.W; cpd.n_phys = n_phys;
             cpd.chunk_ptr = (const Chunk *const *)cs.chunk_ptr.p;
@@ -734,11 +789,12 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
     float ms_prep_host = 0.f;
     for (int h = 0; h < Cn; h++) {
         ChromState &cs = chroms_[h];
-        if (!reuse) {
+        const fgt_chrom_t &c = pb.chrom[h];
+        // host-resident paintings: upload the chromosome's tables before the label copies fill the copy engine
+        if (!reuse && !c.labels_on_device) {
             rc = setup_chromosome(pb, h, cs, stx);
             if (rc) return rc;
         }
-        const fgt_chrom_t &c = pb.chrom[h];
         const size_t bytes_per_ind = (size_t)PM * c.nsites * pb.label_bytes;
         int n_blocks = 1;
         if (!reuse) {
@@ -762,6 +818,14 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
                 CK(cudaEventRecord(copy_done[b], st_copy_));
             }
             stx.h2d_bytes += (int64_t)(bytes_per_ind * n_phys);
+        }
+        count_pending_ = false;
+        if (!reuse && c.labels_on_device) {
+            // device-resident paintings: the chunk count streams the labels while the host builds the cM prefix
+            rc = prep_count(pb, h, blk_lo(0), blk_lo(1), d_lab, copy_done[0]);
+            if (rc) return rc;
+            rc = setup_chromosome(pb, h, cs, stx);
+            if (rc) return rc;
         }
         int next_n = 0;
         for (int b = 0; b < n_blocks; b++) {
@@ -863,11 +927,11 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
     // the stream moves on by two draws per sampled pair of the WHOLE call (all shards), C:136-137
     store_history(apply_jump(poly_pow_E(2ULL * (uint64_t)all_pairs), h0));
 
-    float ms_eval = 0.f, ms_commit = 0.f;
+    float ms_eval = 0.f, ms_commit = 0.f, ms_rand_spec = 0.f;
     for (Span &s : spans) {
         float t = 0.f;
         cudaEventElapsedTime(&t, s.a, s.b);
-        if (s.kind == 0) ms_rand += t; else if (s.kind == 1) ms_commit += t; else if (s.kind == 3) ms_eval += t; else ms_proj += t;
+        if (s.kind == 0) ms_rand += t; else if (s.kind == 4) ms_rand_spec += t; else if (s.kind == 1) ms_commit += t; else if (s.kind == 3) ms_eval += t; else ms_proj += t;
         cudaEventDestroy(s.a); cudaEventDestroy(s.b);
     }
     // accumulation = from the first evaluation launch to the end of the last commit (the two phases of
@@ -878,7 +942,7 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
     float tail = 0.f;
     cudaEventElapsedTime(&tail, ev[1], ev[2]);
     cudaEventElapsedTime(&stx.ms_total, ev[0], ev[2]);
-    stx.ms_rand = ms_rand; stx.ms_accum = ms_accum; stx.ms_project = ms_proj + tail;
+    stx.ms_rand = ms_rand + ms_rand_spec; stx.ms_accum = ms_accum; stx.ms_project = ms_proj + tail;
     stx.ms_chunk = std::max(0.f, stx.ms_total - ms_rand - ms_accum - stx.ms_project);   // chunking/binning not hidden behind the accumulation
     stx.accepted = (int64_t)hacc[0];
     stx.kernel_launches = launches_;

@@ -42,6 +42,7 @@ struct Options {
     int null_slab_bins = 0; // NULL path: bins per slab (0 = G/16)
     int ranges = 8;         // accumulation launches per chromosome when the paintings stream in from the host
     int blocks = 0;         // blocks of individuals per chromosome in the copy/chunk/accumulate pipeline (0 = automatic)
+    int spec_rand = 1;      // generate the first batch's draws while the chunk/bin kernels run
     int accum_impl = 2;     // 2 = two-phase (evaluate once, ordered commit); 1 = single-phase slab warps     // one-shot: next packed call may reuse the chunk/bin tables of the previous one
 };
 
@@ -69,6 +70,7 @@ class Engine {
     bool fetch_history(History &h);          // current stream state (libc-coupled or private)
     void store_history(const History &h);
     int setup_chromosome(const fgt_problem_t &pb, int h, ChromState &cs, fgt_stats_t &stx);
+    int prep_count(const fgt_problem_t &pb, int h, int p0, int p1, const void *d_lab, cudaEvent_t copy_done);
     int prep_block(const fgt_problem_t &pb, int h, int p0, int p1, int blk, const void *d_lab, cudaEvent_t copy_done,
                    ChromState &cs, fgt_stats_t &stx);
     int prep_chromosome(const fgt_problem_t &pb, int h, const int32_t *rowmap_dev, int rows, int rows_per_ind,
@@ -80,11 +82,12 @@ class Engine {
     bool inited_ = false;
     int init_rc_ = 0;
     cudaStream_t st_ = nullptr, st_prep_ = nullptr, st_copy_ = nullptr, st_commit_ = nullptr;
+    cudaStream_t st_aux_ = nullptr;   // small table uploads that must not queue behind the prep stream
     History private_hist_ = seeded_history(1);
     std::vector<uint32_t> level_tab_;
     DevBuf d_level_tab_, d_err_, d_accepted_;
     // scratch shared by all chromosomes (stream ordered)
-    DevBuf d_labels_, d_cum_, d_inc_, d_counts_, d_rowoff_, d_cstart_, d_cend_, d_chap_, d_cntmat_, d_runfirst_,
+    DevBuf d_labels_, d_cum_, d_inc_, d_counts_, d_rowoff_, d_segoff_, d_cstart_, d_cend_, d_chap_, d_cntmat_, d_runfirst_,
         d_donor_, d_etab_, d_rowmap_;
     DevBuf d_draws_, d_hist_, d_tensor_, d_results_, d_tw_, d_pairkh_, d_slabs_, d_pairbase_, d_physof_, d_rs_,
         d_ratio_, d_means_, d_raw_, d_totals_, d_recs_, d_cnt_, d_draws2_, d_recs2_, d_cnt2_, d_taskctr_, d_slabof_, d_firstslab_, d_slabw_, d_slabb0_;
@@ -94,6 +97,11 @@ class Engine {
     int launches_ = 0;
     fgt_stats_t carry_{};
     double mem_budget_bytes_ = 0;
+    long long last_shape_sig_ = -1;
+    long long last_first_batch_threads_ = 0;   // generator runs the previous call's first batch used (speculation size)
+    int32_t *pin_small_ = nullptr;   // pinned word for the chunk-count read-back
+    bool count_pending_ = false;
+    int count_key_[3] = {0, 0, 0};
     void *pinned_ = nullptr;
     size_t pinned_cap_ = 0;
 };

@@ -85,66 +85,91 @@ __device__ __forceinline__ unsigned change_mask(const T *__restrict__ flat, long
     return m;
 }
 
+// A row is split into `segs` (= warps per block, chunk_segs_for) contiguous segments, one per warp of the row's block: the count kernel leaves one
+// count per (row, segment), one scan turns them into output offsets, and the emit kernel then needs no block-wide
+// synchronisation at all -- each warp streams its segment with a warp-level prefix of the boundary counts.
+// A lane's predecessor label comes from its neighbour lane (the last label of the previous iteration for lane 0).
 template <typename T>
-__global__ void __launch_bounds__(256) k_chunk_count(const T *__restrict__ labels, const int32_t *__restrict__ rowmap, int L,
-                                                     int rows, int32_t *__restrict__ counts) {
-    __shared__ int wtot[8];
+__device__ __forceinline__ unsigned change_mask_warp(const Lab8<T> &x, T carry_prev, long long g0, long long lo, long long hi) {
+    T prev = (T)__shfl_up_sync(kFull, (unsigned)x.v[7], 1);
+    if (lane_id() == 0) prev = carry_prev;
+    unsigned m = 0;
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        const long long g = g0 + e;
+        if (g > lo && g < hi && x.v[e] != prev) m |= 1u << e;
+        prev = x.v[e];
+    }
+    return m;
+}
+
+// lane-group range [q0, q1) (groups of 8 labels, aligned in the flat index space) of segment `seg` of a row
+__device__ __forceinline__ void seg_range(long long lo, long long hi, int seg, int segs, long long &a0, long long &q0, long long &q1) {
+    a0 = lo & ~7LL;
+    const long long groups = (hi - a0 + 7) >> 3;
+    const long long per = (((groups + segs - 1) / segs) + 31) & ~31LL;     // whole warp iterations
+    q0 = per * seg;
+    q1 = q0 + per < groups ? q0 + per : groups;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512) k_chunk_count(const T *__restrict__ labels, const int32_t *__restrict__ rowmap,
+                                                                 int L, int rows, int32_t *__restrict__ counts) {
+    const int seg = warp_id(), lane = lane_id(), segs = blockDim.x >> 5;
     for (int row = blockIdx.x; row < rows; row += gridDim.x) {
         const long long lo = (long long)(rowmap ? rowmap[row] : row) * L, hi = lo + L;
-        const long long a0 = lo & ~7LL;
+        long long a0, q0, q1;
+        seg_range(lo, hi, seg, segs, a0, q0, q1);
         int c = 0;
-        for (long long g0 = a0 + 8LL * threadIdx.x; g0 < hi; g0 += 8LL * blockDim.x) {
+        T carry = (T)0;
+        if (q0 < q1) { const long long gp = a0 + 8 * q0 - 1; carry = (gp >= lo) ? labels[gp] : (T)0; }
+        for (long long q = q0; q < q1; q += 32) {
+            const long long g0 = a0 + 8 * (q + lane);
             Lab8<T> x;
-            load8(labels, g0, lo, hi, x);
-            c += __popc(change_mask(labels, g0, lo, hi, x));
+            load8(labels, g0, lo, hi, x);              // groups past the row end read as zeros and are masked out
+            c += __popc(change_mask_warp(x, carry, g0, lo, hi));
+            carry = (T)__shfl_sync(kFull, (unsigned)x.v[7], 31);
         }
         c = warp_sum(c);
-        if (lane_id() == 0) wtot[warp_id()] = c;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int s = 1;
-            for (int i = 0; i < (int)(blockDim.x >> 5); i++) s += wtot[i];
-            counts[row] = s;
-        }
-        __syncthreads();
+        if (lane == 0) counts[(size_t)row * segs + seg] = c + (seg == 0 ? 1 : 0);   // the row's first chunk
     }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) k_chunk_emit(const T *__restrict__ labels, const int32_t *__restrict__ rowmap, int L,
-                                                    int rows, const int32_t *__restrict__ row_off, const double *__restrict__ cum,
-                                                    const double *__restrict__ inc, double *__restrict__ cstart,
-                                                    double *__restrict__ cend, int32_t *__restrict__ chap) {
-    __shared__ int wtot[8];
-    __shared__ int running_s;
+__global__ void __launch_bounds__(512) k_chunk_emit(const T *__restrict__ labels, const int32_t *__restrict__ rowmap,
+                                                                int L, int rows, const int32_t *__restrict__ seg_off,
+                                                                const double *__restrict__ cum, const double *__restrict__ inc,
+                                                                double *__restrict__ cstart, double *__restrict__ cend,
+                                                                int32_t *__restrict__ chap) {
+    const int seg = warp_id(), lane = lane_id(), segs = blockDim.x >> 5;
     for (int row = blockIdx.x; row < rows; row += gridDim.x) {
         const long long lo = (long long)(rowmap ? rowmap[row] : row) * L, hi = lo + L;
-        const long long a0 = lo & ~7LL;
-        const int base = row_off[row];
-        if (threadIdx.x == 0) {
-            cstart[base] = 0.0;
-            chap[base] = (int32_t)labels[lo];
-            cend[row_off[row + 1] - 1] = cum[L - 1];
-            running_s = 0;
-        }
-        __syncthreads();
-        for (long long t0 = a0; t0 < hi; t0 += 8LL * blockDim.x) {
-            const long long g0 = t0 + 8LL * threadIdx.x;
+        long long a0, q0, q1;
+        seg_range(lo, hi, seg, segs, a0, q0, q1);
+        int running = seg_off[(size_t)row * segs + seg];          // chunks opened before this segment ...
+        if (seg == 0) {
+            if (lane == 0) {
+                cstart[running] = 0.0;
+                chap[running] = (int32_t)labels[lo];
+                cend[seg_off[(size_t)(row + 1) * segs] - 1] = cum[L - 1];
+            }
+        } else running -= 1;                                             // ... c below is the index of the open chunk
+        T carry = (T)0;
+        if (q0 < q1) { const long long gp = a0 + 8 * q0 - 1; carry = (gp >= lo) ? labels[gp] : (T)0; }
+        for (long long q = q0; q < q1; q += 32) {
+            const long long g0 = a0 + 8 * (q + lane);
             Lab8<T> x;
-            unsigned m = 0;
-            if (g0 < hi) { load8(labels, g0, lo, hi, x); m = change_mask(labels, g0, lo, hi, x); }
+            load8(labels, g0, lo, hi, x);
+            unsigned m = change_mask_warp(x, carry, g0, lo, hi);
+            carry = (T)__shfl_sync(kFull, (unsigned)x.v[7], 31);
             const int mine = __popc(m);
-            int inc_scan = mine;                           // inclusive warp scan of per-thread boundary counts
+            int inc_scan = mine;                           // inclusive warp scan of per-lane boundary counts
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 int y = __shfl_up_sync(kFull, inc_scan, o);
-                if (lane_id() >= o) inc_scan += y;
+                if (lane >= o) inc_scan += y;
             }
-            if (lane_id() == 31) wtot[warp_id()] = inc_scan;
-            __syncthreads();
-            int wbase = running_s, tot = 0;
-            for (int w = 0; w < (int)(blockDim.x >> 5); w++) { if (w < warp_id()) wbase += wtot[w]; tot += wtot[w]; }
-            int c = base + wbase + inc_scan - mine;        // chunks opened before this thread's first boundary
+            int c = running + inc_scan - mine;             // open chunk before this lane's first boundary
             while (m) {
                 const int e = __ffs(m) - 1;
                 m &= m - 1;
@@ -155,9 +180,7 @@ __global__ void __launch_bounds__(256) k_chunk_emit(const T *__restrict__ labels
                 chap[c] = (int32_t)x.v[e];
                 cend[c - 1] = __dsub_rn(cj, inc[j]);       // reference C:501: cursor minus the same increment
             }
-            __syncthreads();
-            if (threadIdx.x == 0) running_s += tot;
-            __syncthreads();
+            running += __shfl_sync(kFull, inc_scan, 31);
         }
     }
 }
@@ -165,14 +188,14 @@ __global__ void __launch_bounds__(256) k_chunk_emit(const T *__restrict__ labels
 // General path (weight_min >= 1, never used by the R driver which passes 0, R:52): a label change
 // opens a chunk only if the run that just ended is longer than weight_min SNPs.  One thread per row.
 template <typename T, bool EMIT>
-__global__ void k_chunk_seq(const T *__restrict__ labels, const int32_t *__restrict__ rowmap, int L, int rows, double weight_min,
+__global__ void k_chunk_seq(const T *__restrict__ labels, const int32_t *__restrict__ rowmap, int L, int rows, int segs, double weight_min,
                             int32_t *__restrict__ counts, const int32_t *__restrict__ row_off,
                             const double *__restrict__ cum, const double *__restrict__ inc, double *__restrict__ cstart,
                             double *__restrict__ cend, int32_t *__restrict__ chap) {
     int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows) return;
     const T *lab = labels + (size_t)(rowmap ? rowmap[row] : row) * L;
-    int c = 0, base = EMIT ? row_off[row] : 0;
+    int c = 0, base = EMIT ? row_off[(size_t)row * segs] : 0;
     if (EMIT) { cstart[base] = 0.0; chap[base] = (int32_t)lab[0]; }
     double run = 1;
     T prev = lab[0];
@@ -194,22 +217,31 @@ __global__ void k_chunk_seq(const T *__restrict__ labels, const int32_t *__restr
         prev = cur;
     }
     if (EMIT) cend[base + c] = cum[L - 1];
-    else counts[row] = c + 1;
+    else counts[(size_t)row * segs] = c + 1;       // other segments of the row stay zero (cleared by the launcher)
+}
+
+// warps per row: as many as keep the whole launch in one wave of resident warps (148 SMs x 64)
+int chunk_segs_for(int rows) {
+    int segs = 16;
+    while (segs > 1 && (long long)rows * segs > 148LL * 64) segs >>= 1;
+    return segs;
 }
 
 void launch_chunk_count(const void *labels, const int32_t *rowmap, int label_bytes, int nsites, int rows, double weight_min,
                         int32_t *counts, cudaStream_t st) {
+    const int segs = chunk_segs_for(rows);
     if (weight_min < 1.0) {
         int grid = rows < 148 * 64 ? rows : 148 * 64;
-        if (label_bytes == 2) k_chunk_count<uint16_t><<<grid, 256, 0, st>>>((const uint16_t *)labels, rowmap, nsites, rows, counts);
-        else k_chunk_count<int32_t><<<grid, 256, 0, st>>>((const int32_t *)labels, rowmap, nsites, rows, counts);
+        if (label_bytes == 2) k_chunk_count<uint16_t><<<grid, 32 * segs, 0, st>>>((const uint16_t *)labels, rowmap, nsites, rows, counts);
+        else k_chunk_count<int32_t><<<grid, 32 * segs, 0, st>>>((const int32_t *)labels, rowmap, nsites, rows, counts);
     } else {
+        cudaMemsetAsync(counts, 0, (size_t)rows * segs * sizeof(int32_t), st);
         int grid = (rows + 127) / 128;
         if (label_bytes == 2)
-            k_chunk_seq<uint16_t, false><<<grid, 128, 0, st>>>((const uint16_t *)labels, rowmap, nsites, rows, weight_min, counts,
+            k_chunk_seq<uint16_t, false><<<grid, 128, 0, st>>>((const uint16_t *)labels, rowmap, nsites, rows, segs, weight_min, counts,
                                                               nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
         else
-            k_chunk_seq<int32_t, false><<<grid, 128, 0, st>>>((const int32_t *)labels, rowmap, nsites, rows, weight_min, counts,
+            k_chunk_seq<int32_t, false><<<grid, 128, 0, st>>>((const int32_t *)labels, rowmap, nsites, rows, segs, weight_min, counts,
                                                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     }
 }
@@ -217,19 +249,20 @@ void launch_chunk_count(const void *labels, const int32_t *rowmap, int label_byt
 void launch_chunk_emit(const void *labels, const int32_t *rowmap, int label_bytes, int nsites, int rows, double weight_min,
                        const int32_t *row_off, const double *cum, const double *inc, double *cstart, double *cend,
                        int32_t *chap, cudaStream_t st) {
+    const int segs = chunk_segs_for(rows);
     if (weight_min < 1.0) {
         int grid = rows < 148 * 64 ? rows : 148 * 64;
         if (label_bytes == 2)
-            k_chunk_emit<uint16_t><<<grid, 256, 0, st>>>((const uint16_t *)labels, rowmap, nsites, rows, row_off, cum, inc, cstart, cend, chap);
+            k_chunk_emit<uint16_t><<<grid, 32 * segs, 0, st>>>((const uint16_t *)labels, rowmap, nsites, rows, row_off, cum, inc, cstart, cend, chap);
         else
-            k_chunk_emit<int32_t><<<grid, 256, 0, st>>>((const int32_t *)labels, rowmap, nsites, rows, row_off, cum, inc, cstart, cend, chap);
+            k_chunk_emit<int32_t><<<grid, 32 * segs, 0, st>>>((const int32_t *)labels, rowmap, nsites, rows, row_off, cum, inc, cstart, cend, chap);
     } else {
         int grid = (rows + 127) / 128;
         if (label_bytes == 2)
-            k_chunk_seq<uint16_t, true><<<grid, 128, 0, st>>>((const uint16_t *)labels, rowmap, nsites, rows, weight_min, nullptr,
+            k_chunk_seq<uint16_t, true><<<grid, 128, 0, st>>>((const uint16_t *)labels, rowmap, nsites, rows, segs, weight_min, nullptr,
                                                              row_off, cum, inc, cstart, cend, chap);
         else
-            k_chunk_seq<int32_t, true><<<grid, 128, 0, st>>>((const int32_t *)labels, rowmap, nsites, rows, weight_min, nullptr,
+            k_chunk_seq<int32_t, true><<<grid, 128, 0, st>>>((const int32_t *)labels, rowmap, nsites, rows, segs, weight_min, nullptr,
                                                             row_off, cum, inc, cstart, cend, chap);
     }
 }
@@ -263,6 +296,18 @@ __global__ void __launch_bounds__(1024) k_exclusive_scan_i32(const int32_t *__re
 
 void launch_exclusive_scan_i32(const int32_t *in, int32_t *out, int n, cudaStream_t st) {
     k_exclusive_scan_i32<<<1, 1024, 0, st>>>(in, out, n);
+}
+
+// row_off[r] = seg_off[r * segs], r = 0..rows
+__global__ void k_compact_row_off(const int32_t *__restrict__ seg_off, int32_t *__restrict__ row_off, int rows, int segs) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r <= rows) row_off[r] = seg_off[(size_t)r * segs];
+}
+
+void launch_chunk_scan(const int32_t *counts, int32_t *seg_off, int32_t *row_off, int rows, cudaStream_t st) {
+    const int segs = chunk_segs_for(rows);
+    k_exclusive_scan_i32<<<1, 1024, 0, st>>>(counts, seg_off, rows * segs);
+    k_compact_row_off<<<(rows + 1 + 255) / 256, 256, 0, st>>>(seg_off, row_off, rows, segs);
 }
 
 // =============================================================================================
@@ -407,11 +452,11 @@ __device__ __forceinline__ void block_apply_level(uint32_t *y /*smem[61]*/, cons
 
 __global__ void __launch_bounds__(256)
 k_rand_fill(const uint32_t *__restrict__ base_hist, const uint32_t *__restrict__ tab, uint32_t *__restrict__ out,
-            long long n_threads) {
+            long long n_threads, unsigned blk0) {
     __shared__ uint32_t y[2 * kLag - 1];
     if (threadIdx.x < kLag) y[threadIdx.x] = base_hist[threadIdx.x];
     __syncthreads();
-    unsigned long long blk = blockIdx.x;
+    unsigned long long blk = (unsigned long long)blockIdx.x + blk0;
 #pragma unroll 1
     for (int lv = 1; lv < kLevels; lv++) {
         int digit = (int)((blk >> (8 * (lv - 1))) & 255);
@@ -472,10 +517,12 @@ k_rand_fill(const uint32_t *__restrict__ base_hist, const uint32_t *__restrict__
 }
 
 void launch_rand_fill(const uint32_t *base_hist, const uint32_t *level_tab, uint32_t *out, long long n_threads,
-                      cudaStream_t st) {
-    if (n_threads <= 0) return;
-    long long blocks = (n_threads + 255) / 256;
-    k_rand_fill<<<(unsigned)blocks, 256, 8 * 256 * sizeof(uint4), st>>>(base_hist, level_tab, out, n_threads);
+                      cudaStream_t st, long long first_thread) {
+    // threads [first_thread, n_threads) of the stream that starts at base_hist; first_thread is a multiple of 256
+    if (n_threads <= first_thread) return;
+    const long long blk0 = first_thread / 256;
+    long long blocks = (n_threads + 255) / 256 - blk0;
+    k_rand_fill<<<(unsigned)blocks, 256, 8 * 256 * sizeof(uint4), st>>>(base_hist, level_tab, out, n_threads, (unsigned)blk0);
 }
 
 // =============================================================================================

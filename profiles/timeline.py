@@ -1,0 +1,20 @@
+"""Print the engine's verbose host/device timeline for one data_read on the bench workload (device-resident paintings)."""
+import sys, os
+sys.path.insert(0, os.getcwd())
+import numpy as np, torch
+from fastglobetrotter_b200 import synth, build as fbuild
+from fastglobetrotter_b200.companion import PackedCompanion
+from fastglobetrotter_b200.synth_torch import make_chromosome_device
+lib = PackedCompanion(fbuild.build()); lib.set_option("rand_libc", 0)
+dev = torch.device("cuda", 0)
+N, L, K, G, S = 100, 100_000, 30, 500, 10
+spec = synth.SynthSpec(n_chrom=1, n_inds=N, n_snps=L, K=K, nsamples=10, seed=20261021)
+pos, rate, lab = make_chromosome_device(spec, 0, dev)
+chrom = [{"pos": pos, "rate": rate, "labels": (lab.data_ptr(), 2, lab.shape[0])}]
+torch.cuda.synchronize()
+dl = spec.donor_label_vec(); tw = np.random.default_rng(0).random(K * K * S * S); ids = np.arange(N).astype(np.int32)
+for rep in range(4):
+    lib.set_option("verbose", 1 if rep == 3 else 0)
+    lib.srand(11)
+    m, _, st = lib.data_read_packed(1, 2, 10, chrom, ids, 0.1, G, 10, K, dl, 0.0, 1.0, S, tw)
+print({k: (round(v, 3) if isinstance(v, float) else v) for k, v in st.items()})
