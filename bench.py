@@ -147,23 +147,39 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    # persistent exchange buffers (pinned host <-> device) for the two collectives of a sharded call
+    if world > 1:
+        n_cnt = W["n_chrom"] * N
+        cnt_pin = torch.empty(n_cnt, dtype=torch.int64, pin_memory=True)
+        cnt_dev = torch.empty(n_cnt, dtype=torch.int64, device=dev)
+        all_dev = torch.empty(world * n_cnt, dtype=torch.int64, device=dev)
+        all_pin = torch.empty(world * n_cnt, dtype=torch.int64, pin_memory=True)
+        m_pin = torch.empty(S * S * G, dtype=torch.float64, pin_memory=True)
+        m_dev = torch.empty(S * S * G, dtype=torch.float64, device=dev)
+
     def one_step(chrom):
         """one data_read pass of this rank's shard; returns (means partial, stats)"""
         if world == 1:
             m, _, st = lib.data_read_packed(*common, chrom, *tail, S, tw)
             return m, st
         cnt = lib.count_pairs_packed(*common, chrom, *tail)                        # [Cn, N] local
-        allc = [torch.zeros(cnt.size, dtype=torch.int64, device=dev) for _ in range(world)]
-        dist.all_gather(allc, torch.from_numpy(cnt.ravel()).to(dev))                # the one exchange of draw counts
-        by_rank = [c.cpu().numpy().reshape(W["n_chrom"], N) for c in allc]
+        cnt_pin.numpy()[:] = cnt.ravel()
+        cnt_dev.copy_(cnt_pin, non_blocking=True)
+        dist.all_gather_into_tensor(all_dev, cnt_dev)                               # the one exchange of draw counts
+        all_pin.copy_(all_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        by_rank = list(all_pin.numpy().reshape(world, W["n_chrom"], N))
         # reference order: chromosome-major, individual-minor; ranks own consecutive blocks of individuals
         offs, total = shard.stream_offsets(by_rank)
         lib.set_option("reuse_prep", 1)
         m, _, st = lib.data_read_packed(*common, chrom, *tail, S, tw, num_inds_total=world * N, pair_offset=offs[rank],
                                         pairs_total=total)
-        mt = torch.from_numpy(m).to(dev)
-        dist.all_reduce(mt)                                                          # S^2 x G fp64 curves
-        return mt.cpu().numpy(), st
+        m_pin.numpy()[:] = m.ravel()
+        m_dev.copy_(m_pin, non_blocking=True)
+        dist.all_reduce(m_dev)                                                       # S^2 x G fp64 curves
+        m_pin.copy_(m_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return m_pin.numpy().reshape(m.shape).copy(), st
 
     def timed(chrom, steps, warmup):
         for _ in range(warmup):

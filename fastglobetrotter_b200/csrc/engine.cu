@@ -63,6 +63,7 @@ int Engine::set_option(const char *key, double v) {
     else if (k == "reuse_prep") opt.reuse_prep = iv;
     else if (k == "accum_impl") opt.accum_impl = iv;
     else if (k == "spec_rand") opt.spec_rand = iv;
+    else if (k == "eval_parts") opt.eval_parts = iv;
     else if (k == "batch_pairs") opt.batch_pairs = v;
     else if (k == "blocks") opt.blocks = iv;
     else if (k == "ranges") opt.ranges = iv;
@@ -85,6 +86,7 @@ double Engine::get_option(const char *key) {
     if (k == "reuse_prep") return opt.reuse_prep;
     if (k == "accum_impl") return opt.accum_impl;
     if (k == "spec_rand") return opt.spec_rand;
+    if (k == "eval_parts") return opt.eval_parts;
     if (k == "batch_pairs") return opt.batch_pairs;
     if (k == "blocks") return opt.blocks;
     if (k == "ranges") return opt.ranges;
@@ -751,6 +753,11 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
                 ea.slab_of = d_slabof; ea.first_slab = d_firstslab; ea.slab_w = d_slabw; ea.slab_b0 = d_slabb0;
                 ea.recs = d_recs; ea.regions = d_regions; ea.slabs = d_slabs; ea.n_slabs = (int)slabs.size(); ea.nd_max = nd_max;
                 ea.err = d_err;
+                {   // enough warps to fill the GPU twice over even for a small range of individuals
+                    const long long rows_jn = (long long)Nb * std::max(1, cs.nb - 1);
+                    long long ds = opt.eval_parts > 0 ? opt.eval_parts : (2 * 148 * 32 + rows_jn - 1) / rows_jn;
+                    ea.d_parts = (int)std::min<long long>(8, std::max<long long>(opt.eval_parts > 0 ? 1 : 4, ds));   // 4 also balances the tail of a full-size launch
+                }
                 launch_eval_pairs(ea, st_);
                 span_end(st_);
                 CK(cudaEventRecord(eval_done, st_));
@@ -932,6 +939,12 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
         float t = 0.f;
         cudaEventElapsedTime(&t, s.a, s.b);
         if (s.kind == 0) ms_rand += t; else if (s.kind == 4) ms_rand_spec += t; else if (s.kind == 1) ms_commit += t; else if (s.kind == 3) ms_eval += t; else ms_proj += t;
+        if (opt.verbose) {                       // device timeline of the accumulation stages, relative to the start of the call
+            static const char *names[] = {"rand", "commit", "project", "eval", "rand(spec)"};
+            float t0 = 0.f;
+            cudaEventElapsedTime(&t0, ev[0], s.a);
+            fprintf(stderr, "[fgt dev] %8.3f .. %8.3f ms  %s\n", t0, t0 + t, names[s.kind]);
+        }
         cudaEventDestroy(s.a); cudaEventDestroy(s.b);
     }
     // accumulation = from the first evaluation launch to the end of the last commit (the two phases of

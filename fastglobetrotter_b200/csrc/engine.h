@@ -42,6 +42,7 @@ struct Options {
     int null_slab_bins = 0; // NULL path: bins per slab (0 = G/16)
     int ranges = 8;         // accumulation launches per chromosome when the paintings stream in from the host
     int blocks = 0;         // blocks of individuals per chromosome in the copy/chunk/accumulate pipeline (0 = automatic)
+    int eval_parts = 0;     // warps per (individual, coarse bin) in phase 1; 0 = automatic
     int spec_rand = 1;      // generate the first batch's draws while the chunk/bin kernels run
     int accum_impl = 2;     // 2 = two-phase (evaluate once, ordered commit); 1 = single-phase slab warps     // one-shot: next packed call may reuse the chunk/bin tables of the previous one
 };

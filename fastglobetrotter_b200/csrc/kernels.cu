@@ -714,8 +714,11 @@ __global__ void __launch_bounds__(128, 8) k_eval_pairs(const EvalArgs a) {
     const int lane = lane_id();
     const ChromPrep &cp = a.cp;
     const int nb = cp.nb, W = cp.W;
-    const long long task = (long long)blockIdx.x * (blockDim.x >> 5) + warp_id();
-    if (task >= (long long)a.N * (nb - 1)) return;
+    const int DS = a.d_parts;
+    const long long wtask = (long long)blockIdx.x * (blockDim.x >> 5) + warp_id();
+    if (wtask >= (long long)a.N * (nb - 1) * DS) return;
+    const long long task = wtask / DS;
+    const int part = (int)(wtask - task * DS);
     const int n = (int)(task / (nb - 1));
     const int j = (int)(task - (long long)n * (nb - 1));
     const int phys = a.phys_of[n];
@@ -741,8 +744,25 @@ __global__ void __launch_bounds__(128, 8) k_eval_pairs(const EvalArgs a) {
         nr0 = (p + lane < a.draws_limit) ? a.draws[p + lane] : make_uint2(0, 0);
         nr1 = (p + 32 + lane < a.draws_limit) ? a.draws[p + 32 + lane] : make_uint2(0, 0);
     };
-    prefetch(row_pair0 + yo[0]);
-    for (int d = 1; d <= dmax; d++) {
+    // this warp's share of the separations: d in (d_from, d_to], cut where the row's cumulative pair count crosses
+    // part/DS of its total (small ranges of individuals would otherwise leave most of the GPU idle)
+    int d_from = 0, d_to = dmax;
+    if (DS > 1) {
+        const int y00 = yo[0];
+        const long long yrow = (long long)yo[dmax] - y00;
+        const long long thr_lo = yrow * part / DS, thr_hi = yrow * (part + 1) / DS;
+        int n_lo = 0, n_hi = 0;                   // separations d in [0, dmax] whose cumulative count is <= the threshold
+        for (int d0 = 0; d0 <= dmax; d0 += 32) {
+            const long long c = (d0 + lane <= dmax) ? (long long)yo[d0 + lane] - y00 : (1LL << 62);
+            n_lo += __popc(__ballot_sync(kFull, c <= thr_lo));
+            n_hi += __popc(__ballot_sync(kFull, c <= thr_hi));
+        }
+        d_from = n_lo - 1;
+        d_to = (part == DS - 1) ? dmax : n_hi - 1;
+        if (d_from >= d_to) return;
+    }
+    prefetch(row_pair0 + yo[d_from]);
+    for (int d = d_from + 1; d <= d_to; d++) {
         const int y0 = yo[d - 1];
         const int Y = yo[d] - y0;
         if (Y <= 0) continue;
@@ -798,7 +818,7 @@ __global__ void __launch_bounds__(128, 8) k_eval_pairs(const EvalArgs a) {
 }
 
 void launch_eval_pairs(const EvalArgs &a, cudaStream_t st) {
-    long long tasks = (long long)a.N * (a.cp.nb - 1);
+    long long tasks = (long long)a.N * (a.cp.nb - 1) * a.d_parts;
     if (tasks <= 0) return;
     const int wpb = 4;
     k_eval_pairs<<<(unsigned)((tasks + wpb - 1) / wpb), wpb * 32, 0, st>>>(a);

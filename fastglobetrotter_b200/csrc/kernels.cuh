@@ -74,6 +74,7 @@ struct EvalArgs {
     RegionEnt *regions;           // [N*n_slabs][nb-1][nd_max] region directory, slab-major (zero = empty)
     const SlabDesc *slabs;
     int32_t n_slabs, nd_max;
+    int32_t d_parts;              // warps per (individual, coarse bin): the separations are split into parts of equal pair counts
     int *err;
 };
 

@@ -11,6 +11,11 @@ N, L, K, G, S = 100, 100_000, 30, 500, 10
 spec = synth.SynthSpec(n_chrom=1, n_inds=N, n_snps=L, K=K, nsamples=10, seed=20261021)
 pos, rate, lab = make_chromosome_device(spec, 0, dev)
 chrom = [{"pos": pos, "rate": rate, "labels": (lab.data_ptr(), 2, lab.shape[0])}]
+if os.environ.get("HOST"):
+    hl = torch.empty(lab.shape, dtype=torch.int16, pin_memory=True); hl.copy_(lab)
+    chrom = [{"pos": pos, "rate": rate, "labels": hl.numpy().view(np.uint16)}]
+for k, v in [kv.split("=") for kv in os.environ.get("OPTS", "").split(",") if kv]:
+    lib.set_option(k, float(v))
 torch.cuda.synchronize()
 dl = spec.donor_label_vec(); tw = np.random.default_rng(0).random(K * K * S * S); ids = np.arange(N).astype(np.int32)
 for rep in range(4):
