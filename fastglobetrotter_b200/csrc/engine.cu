@@ -264,12 +264,12 @@ int Engine::prep_chromosome(const fgt_problem_t &pb, int h, const int32_t *rowma
         stx.h2d_bytes += (int64_t)bytes;
         d_lab = buf;
     }
-    int32_t *d_counts = d_counts_.as<int32_t>((size_t)rows * kChunkSegs), *d_rowoff = d_rowoff_.as<int32_t>(rows + 1);
-    int32_t *d_segoff = d_segoff_.as<int32_t>((size_t)rows * kChunkSegs + 1);
-    if (!d_counts || !d_rowoff || !d_segoff) return FGT_ERR_CUDA;
-    launch_chunk_count(d_lab, rowmap_dev, pb.label_bytes, L, rows, pb.weight_min, d_counts, st_);
-    launch_chunk_scan(d_counts, d_segoff, d_rowoff, rows, st_);
-    launches_ += 3;
+    int32_t *d_counts = d_counts_.as<int32_t>((size_t)rows * chunk_tiles_for(L)), *d_rowoff = d_rowoff_.as<int32_t>(rows + 1);
+    int32_t *d_rowsum = d_segoff_.as<int32_t>(rows);
+    if (!d_counts || !d_rowoff || !d_rowsum) return FGT_ERR_CUDA;
+    launch_chunk_count(d_lab, rowmap_dev, pb.label_bytes, L, rows, pb.weight_min, d_counts, d_rowsum, st_);
+    launch_chunk_scan(d_rowsum, d_rowoff, rows, st_);
+    launches_ += 2;
     int32_t total_chunks = 0;
     CK(cudaMemcpyAsync(&total_chunks, d_rowoff + rows, sizeof(int32_t), cudaMemcpyDeviceToHost, st_));
     // the copies above read host vectors that die at scope exit: synchronise here (also yields total_chunks)
@@ -281,7 +281,7 @@ int Engine::prep_chromosome(const fgt_problem_t &pb, int h, const int32_t *rowma
     double *d_cstart = d_cstart_.as<double>(total_chunks), *d_cend = d_cend_.as<double>(total_chunks);
     int32_t *d_chap = d_chap_.as<int32_t>(total_chunks);
     if (!d_cstart || !d_cend || !d_chap) return FGT_ERR_CUDA;
-    launch_chunk_emit(d_lab, rowmap_dev, pb.label_bytes, L, rows, pb.weight_min, d_segoff, d_cum, d_inc, d_cstart, d_cend,
+    launch_chunk_emit(d_lab, rowmap_dev, pb.label_bytes, L, rows, pb.weight_min, d_counts, d_rowoff, d_cum, d_inc, d_cstart, d_cend,
                       d_chap, st_);
     launches_ += 1;
     Chunk *d_sorted = cs.sorted.as<Chunk>(total_chunks);
@@ -365,7 +365,7 @@ int Engine::prep_block(const fgt_problem_t &pb, int h, int p0, int p1, int blk, 
         if (rc) return rc;
     }
     count_pending_ = false;
-    int32_t *d_rowoff = (int32_t *)d_rowoff_.p, *d_segoff = (int32_t *)d_segoff_.p;
+    int32_t *d_rowoff = (int32_t *)d_rowoff_.p, *d_counts = (int32_t *)d_counts_.p;
     CK(cudaStreamSynchronize(sp));
     const int32_t total_chunks = *pin_small_;
     stx.d2h_bytes += 4;
@@ -377,7 +377,7 @@ int Engine::prep_block(const fgt_problem_t &pb, int h, int p0, int p1, int blk, 
     if ((int)cs.sorted_blocks.size() <= blk) cs.sorted_blocks.resize(blk + 1);
     Chunk *d_sorted = cs.sorted_blocks[blk].as<Chunk>(total_chunks);
     if (!d_cstart || !d_cend || !d_chap || !d_sorted) return FGT_ERR_CUDA;
-    launch_chunk_emit(lab_blk, nullptr, pb.label_bytes, L, rows, pb.weight_min, d_segoff, (const double *)cs.cum.p,
+    launch_chunk_emit(lab_blk, nullptr, pb.label_bytes, L, rows, pb.weight_min, d_counts, d_rowoff, (const double *)cs.cum.p,
                       (const double *)cs.inc.p, d_cstart, d_cend, d_chap, sp);
     const int nb = cs.nb, W = cs.W;
     size_t cm = (size_t)np * PM * nb;
@@ -408,12 +408,12 @@ int Engine::prep_count(const fgt_problem_t &pb, int h, int p0, int p1, const voi
     if (!pin_small_ && cudaHostAlloc((void **)&pin_small_, 64, cudaHostAllocDefault) != cudaSuccess) return FGT_ERR_CUDA;
     if (copy_done) CK(cudaStreamWaitEvent(sp, copy_done, 0));
     const char *lab_blk = (const char *)d_lab + (size_t)p0 * PM * L * pb.label_bytes;
-    int32_t *d_counts = d_counts_.as<int32_t>((size_t)rows * kChunkSegs), *d_rowoff = d_rowoff_.as<int32_t>(rows + 1);
-    int32_t *d_segoff = d_segoff_.as<int32_t>((size_t)rows * kChunkSegs + 1);
-    if (!d_counts || !d_rowoff || !d_segoff) return FGT_ERR_CUDA;
-    launch_chunk_count(lab_blk, nullptr, pb.label_bytes, L, rows, pb.weight_min, d_counts, sp);
-    launch_chunk_scan(d_counts, d_segoff, d_rowoff, rows, sp);
-    launches_ += 3;
+    int32_t *d_counts = d_counts_.as<int32_t>((size_t)rows * chunk_tiles_for(L)), *d_rowoff = d_rowoff_.as<int32_t>(rows + 1);
+    int32_t *d_rowsum = d_segoff_.as<int32_t>(rows);
+    if (!d_counts || !d_rowoff || !d_rowsum) return FGT_ERR_CUDA;
+    launch_chunk_count(lab_blk, nullptr, pb.label_bytes, L, rows, pb.weight_min, d_counts, d_rowsum, sp);
+    launch_chunk_scan(d_rowsum, d_rowoff, rows, sp);
+    launches_ += 2;
     CK(cudaMemcpyAsync(pin_small_, d_rowoff + rows, sizeof(int32_t), cudaMemcpyDeviceToHost, sp));
     count_pending_ = true;
     count_key_[0] = h; count_key_[1] = p0; count_key_[2] = p1;

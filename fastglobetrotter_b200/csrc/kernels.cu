@@ -85,102 +85,171 @@ __device__ __forceinline__ unsigned change_mask(const T *__restrict__ flat, long
     return m;
 }
 
-// A row is split into `segs` (= warps per block, chunk_segs_for) contiguous segments, one per warp of the row's block: the count kernel leaves one
-// count per (row, segment), one scan turns them into output offsets, and the emit kernel then needs no block-wide
-// synchronisation at all -- each warp streams its segment with a warp-level prefix of the boundary counts.
-// A lane's predecessor label comes from its neighbour lane (the last label of the previous iteration for lane 0).
+// Streaming layout: one block per 2048-label tile of a row (256 threads x one 16-byte load), every block
+// independent -- the count kernel leaves one count per (row, tile) and adds it to the row's total; after a scan of
+// the row totals the emit kernel finds its output offset from the row offset plus the counts of the tiles before it.
+// The kernels are instruction-bound unless the per-label work is tiny, so groups that lie wholly inside the row
+// compare the eight 16-bit labels with their predecessors as four 32-bit words (funnel shift + xor).
+constexpr int kTileLabels = 2048;
+
+// first label index (<= lo, > lo - 8) of the row's first 8-label group: groups are 16-byte aligned in memory for
+// 16-bit labels whatever the row length and wherever the label block starts
 template <typename T>
-__device__ __forceinline__ unsigned change_mask_warp(const Lab8<T> &x, T carry_prev, long long g0, long long lo, long long hi) {
-    T prev = (T)__shfl_up_sync(kFull, (unsigned)x.v[7], 1);
-    if (lane_id() == 0) prev = carry_prev;
+__device__ __forceinline__ long long tile_first_group(const T *labels, long long lo) {
+    const long long off = (long long)((reinterpret_cast<uintptr_t>(labels) / sizeof(T)) & 7);
+    return ((lo + off) & ~7LL) - off;
+}
+
+template <typename T> struct Group8 {
+    Lab8<T> x;
+    __device__ __forceinline__ int label(int e) const { return (int)x.v[e]; }
+};
+template <> struct Group8<uint16_t> {
+    uint4 w;                                            // labels 0..7 = low/high halves of w.x, w.y, w.z, w.w
+    __device__ __forceinline__ int label(int e) const {
+        const unsigned ww = (e >> 1) == 0 ? w.x : (e >> 1) == 1 ? w.y : (e >> 1) == 2 ? w.z : w.w;
+        return (int)((ww >> ((e & 1) * 16)) & 0xffffu);
+    }
+};
+
+// bit e of the result: label g0+e is inside the row, is not its first label, and differs from its predecessor
+__device__ __forceinline__ unsigned tile_change_mask(const uint16_t *__restrict__ labels, long long g0, long long lo, long long hi,
+                                                     Group8<uint16_t> &g, const uint4 *pre = nullptr) {
+    const bool interior = g0 > lo && g0 + 8 <= hi;
+    if (__all_sync(kFull, interior)) {
+        g.w = pre ? *pre : *reinterpret_cast<const uint4 *>(labels + g0);
+        unsigned prev = __shfl_up_sync(kFull, g.w.w, 1) >> 16;
+        if (lane_id() == 0) prev = labels[g0 - 1];
+        const unsigned dx = g.w.x ^ ((g.w.x << 16) | prev);
+        const unsigned dy = g.w.y ^ __funnelshift_l(g.w.x, g.w.y, 16);
+        const unsigned dz = g.w.z ^ __funnelshift_l(g.w.y, g.w.z, 16);
+        const unsigned dw = g.w.w ^ __funnelshift_l(g.w.z, g.w.w, 16);
+        unsigned m = 0;
+        m |= (dx & 0xffffu) ? 1u : 0u;  m |= (dx >> 16) ? 2u : 0u;
+        m |= (dy & 0xffffu) ? 4u : 0u;  m |= (dy >> 16) ? 8u : 0u;
+        m |= (dz & 0xffffu) ? 16u : 0u; m |= (dz >> 16) ? 32u : 0u;
+        m |= (dw & 0xffffu) ? 64u : 0u; m |= (dw >> 16) ? 128u : 0u;
+        return m;
+    }
+    // a warp that touches a row end: element-wise with bounds (labels outside the row read as zeros and are masked)
+    Lab8<uint16_t> x;
+    load8(labels, g0, lo, hi, x);
+    g.w.x = x.v[0] | ((unsigned)x.v[1] << 16); g.w.y = x.v[2] | ((unsigned)x.v[3] << 16);
+    g.w.z = x.v[4] | ((unsigned)x.v[5] << 16); g.w.w = x.v[6] | ((unsigned)x.v[7] << 16);
+    uint16_t prev = (uint16_t)__shfl_up_sync(kFull, (unsigned)x.v[7], 1);
+    if (lane_id() == 0) prev = (g0 - 1 >= lo && g0 - 1 < hi) ? labels[g0 - 1] : (uint16_t)0;
     unsigned m = 0;
 #pragma unroll
     for (int e = 0; e < 8; e++) {
-        const long long g = g0 + e;
-        if (g > lo && g < hi && x.v[e] != prev) m |= 1u << e;
+        const long long q = g0 + e;
+        if (q > lo && q < hi && x.v[e] != prev) m |= 1u << e;
         prev = x.v[e];
     }
     return m;
 }
 
-// lane-group range [q0, q1) (groups of 8 labels, aligned in the flat index space) of segment `seg` of a row
-__device__ __forceinline__ void seg_range(long long lo, long long hi, int seg, int segs, long long &a0, long long &q0, long long &q1) {
-    a0 = lo & ~7LL;
-    const long long groups = (hi - a0 + 7) >> 3;
-    const long long per = (((groups + segs - 1) / segs) + 31) & ~31LL;     // whole warp iterations
-    q0 = per * seg;
-    q1 = q0 + per < groups ? q0 + per : groups;
+__device__ __forceinline__ unsigned tile_change_mask(const int32_t *__restrict__ labels, long long g0, long long lo, long long hi,
+                                                     Group8<int32_t> &g, const uint4 * = nullptr) {
+    load8(labels, g0, lo, hi, g.x);
+    int32_t prev = (int32_t)__shfl_up_sync(kFull, (unsigned)g.x.v[7], 1);
+    if (lane_id() == 0) prev = (g0 - 1 >= lo && g0 - 1 < hi) ? labels[g0 - 1] : 0;
+    unsigned m = 0;
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        const long long q = g0 + e;
+        if (q > lo && q < hi && g.x.v[e] != prev) m |= 1u << e;
+        prev = g.x.v[e];
+    }
+    return m;
 }
 
 template <typename T>
-__global__ void __launch_bounds__(512) k_chunk_count(const T *__restrict__ labels, const int32_t *__restrict__ rowmap,
-                                                                 int L, int rows, int32_t *__restrict__ counts) {
-    const int seg = warp_id(), lane = lane_id(), segs = blockDim.x >> 5;
-    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-        const long long lo = (long long)(rowmap ? rowmap[row] : row) * L, hi = lo + L;
-        long long a0, q0, q1;
-        seg_range(lo, hi, seg, segs, a0, q0, q1);
-        int c = 0;
-        T carry = (T)0;
-        if (q0 < q1) { const long long gp = a0 + 8 * q0 - 1; carry = (gp >= lo) ? labels[gp] : (T)0; }
-        for (long long q = q0; q < q1; q += 32) {
-            const long long g0 = a0 + 8 * (q + lane);
-            Lab8<T> x;
-            load8(labels, g0, lo, hi, x);              // groups past the row end read as zeros and are masked out
-            c += __popc(change_mask_warp(x, carry, g0, lo, hi));
-            carry = (T)__shfl_sync(kFull, (unsigned)x.v[7], 31);
-        }
-        c = warp_sum(c);
-        if (lane == 0) counts[(size_t)row * segs + seg] = c + (seg == 0 ? 1 : 0);   // the row's first chunk
+__global__ void __launch_bounds__(256, 8) k_chunk_count(const T *__restrict__ labels, const int32_t *__restrict__ rowmap, int L,
+                                                        int rows, int tiles, int32_t *__restrict__ counts,
+                                                        int32_t *__restrict__ rowsum) {
+    __shared__ int wtot[8];
+    const int row = blockIdx.x / tiles, t = blockIdx.x - row * tiles;       // one tile per block (32-bit index arithmetic)
+    const long long lo = (long long)(rowmap ? rowmap[row] : row) * L, hi = lo + L;
+    const long long g0 = tile_first_group(labels, lo) + ((long long)t * 256 + threadIdx.x) * 8;
+    Group8<T> g;
+    int c = __popc(tile_change_mask(labels, g0, lo, hi, g));
+    c = warp_sum(c);
+    if (lane_id() == 0) wtot[warp_id()] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = (t == 0) ? 1 : 0;                       // the row's first chunk
+#pragma unroll
+        for (int i = 0; i < 8; i++) s += wtot[i];
+        counts[blockIdx.x] = s;
+        if (s) atomicAdd(&rowsum[row], s);
     }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(512) k_chunk_emit(const T *__restrict__ labels, const int32_t *__restrict__ rowmap,
-                                                                int L, int rows, const int32_t *__restrict__ seg_off,
-                                                                const double *__restrict__ cum, const double *__restrict__ inc,
-                                                                double *__restrict__ cstart, double *__restrict__ cend,
-                                                                int32_t *__restrict__ chap) {
-    const int seg = warp_id(), lane = lane_id(), segs = blockDim.x >> 5;
-    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+__global__ void __launch_bounds__(256, 8) k_chunk_emit(const T *__restrict__ labels, const int32_t *__restrict__ rowmap, int L,
+                                                       int rows, int tiles, const int32_t *__restrict__ counts,
+                                                       const int32_t *__restrict__ row_off, const double *__restrict__ cum,
+                                                       const double *__restrict__ inc, double *__restrict__ cstart,
+                                                       double *__restrict__ cend, int32_t *__restrict__ chap) {
+    __shared__ int wtot[8];
+    __shared__ int open_s;
+    __shared__ int2 blist[kTileLabels];                // (SNP index in the row, label) of every boundary of the tile
+    const int lane = lane_id(), w = warp_id();
+    {
+        const int row = blockIdx.x / tiles, t = blockIdx.x - row * tiles;   // one tile per block (32-bit index arithmetic)
         const long long lo = (long long)(rowmap ? rowmap[row] : row) * L, hi = lo + L;
-        long long a0, q0, q1;
-        seg_range(lo, hi, seg, segs, a0, q0, q1);
-        int running = seg_off[(size_t)row * segs + seg];          // chunks opened before this segment ...
-        if (seg == 0) {
-            if (lane == 0) {
-                cstart[running] = 0.0;
-                chap[running] = (int32_t)labels[lo];
-                cend[seg_off[(size_t)(row + 1) * segs] - 1] = cum[L - 1];
-            }
-        } else running -= 1;                                             // ... c below is the index of the open chunk
-        T carry = (T)0;
-        if (q0 < q1) { const long long gp = a0 + 8 * q0 - 1; carry = (gp >= lo) ? labels[gp] : (T)0; }
-        for (long long q = q0; q < q1; q += 32) {
-            const long long g0 = a0 + 8 * (q + lane);
-            Lab8<T> x;
-            load8(labels, g0, lo, hi, x);
-            unsigned m = change_mask_warp(x, carry, g0, lo, hi);
-            carry = (T)__shfl_sync(kFull, (unsigned)x.v[7], 31);
-            const int mine = __popc(m);
-            int inc_scan = mine;                           // inclusive warp scan of per-lane boundary counts
+        const long long g0 = tile_first_group(labels, lo) + ((long long)t * 256 + threadIdx.x) * 8;
+        // warp 0 also sums the counts of the row's earlier tiles
+        int before = 0;
+        if (w == 0)
+            for (int i = lane; i < t; i += 32) before += counts[(size_t)row * tiles + i];
+        const int base = (threadIdx.x == 0) ? row_off[row] : 0;
+        Group8<T> g;
+        const unsigned m = tile_change_mask(labels, g0, lo, hi, g);
+        const int mine = __popc(m);
+        int inc_scan = mine;                           // inclusive warp scan of per-thread boundary counts
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int y = __shfl_up_sync(kFull, inc_scan, o);
-                if (lane >= o) inc_scan += y;
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(kFull, inc_scan, o);
+            if (lane >= o) inc_scan += y;
+        }
+        if (lane == 31) wtot[w] = inc_scan;
+        if (w == 0) {
+            // index of the chunk that is open when this tile starts: the row's first chunk plus the boundaries before it
+            before = warp_sum(before);
+            if (lane == 0) {
+                open_s = base + (t == 0 ? 0 : before - 1);
+                if (t == 0) {
+                    cstart[base] = 0.0;
+                    chap[base] = (int32_t)labels[lo];
+                    cend[row_off[row + 1] - 1] = cum[L - 1];
+                }
             }
-            int c = running + inc_scan - mine;             // open chunk before this lane's first boundary
-            while (m) {
-                const int e = __ffs(m) - 1;
-                m &= m - 1;
-                c++;
-                const int j = (int)(g0 + e - lo);
-                const double cj = cum[j];
-                cstart[c] = cj;
-                chap[c] = (int32_t)x.v[e];
-                cend[c - 1] = __dsub_rn(cj, inc[j]);       // reference C:501: cursor minus the same increment
-            }
-            running += __shfl_sync(kFull, inc_scan, 31);
+        }
+        __syncthreads();
+        // The tile's boundaries are first listed in shared memory in label order; consecutive threads then write
+        // consecutive chunks (a thread emitting its own boundaries directly costs eight sparsely populated rounds
+        // of scattered loads and stores per warp).
+        int r = inc_scan - mine, tot = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int wt = wtot[i];
+            if (i < w) r += wt;
+            tot += wt;
+        }
+        const int j0 = (int)(g0 - lo);
+#pragma unroll
+        for (int e = 0; e < 8; e++) {                  // static indices keep the labels in registers
+            if ((m >> e) & 1u) blist[r++] = make_int2(j0 + e, g.label(e));
+        }
+        __syncthreads();
+        const int c0 = open_s;
+        for (int k = threadIdx.x; k < tot; k += 256) {
+            const int2 b = blist[k];
+            const double cj = cum[b.x];
+            cstart[c0 + k + 1] = cj;
+            chap[c0 + k + 1] = b.y;
+            cend[c0 + k] = __dsub_rn(cj, inc[b.x]);    // reference C:501: cursor minus the same increment
         }
     }
 }
@@ -188,14 +257,14 @@ __global__ void __launch_bounds__(512) k_chunk_emit(const T *__restrict__ labels
 // General path (weight_min >= 1, never used by the R driver which passes 0, R:52): a label change
 // opens a chunk only if the run that just ended is longer than weight_min SNPs.  One thread per row.
 template <typename T, bool EMIT>
-__global__ void k_chunk_seq(const T *__restrict__ labels, const int32_t *__restrict__ rowmap, int L, int rows, int segs, double weight_min,
+__global__ void k_chunk_seq(const T *__restrict__ labels, const int32_t *__restrict__ rowmap, int L, int rows, double weight_min,
                             int32_t *__restrict__ counts, const int32_t *__restrict__ row_off,
                             const double *__restrict__ cum, const double *__restrict__ inc, double *__restrict__ cstart,
                             double *__restrict__ cend, int32_t *__restrict__ chap) {
     int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows) return;
     const T *lab = labels + (size_t)(rowmap ? rowmap[row] : row) * L;
-    int c = 0, base = EMIT ? row_off[(size_t)row * segs] : 0;
+    int c = 0, base = EMIT ? row_off[row] : 0;
     if (EMIT) { cstart[base] = 0.0; chap[base] = (int32_t)lab[0]; }
     double run = 1;
     T prev = lab[0];
@@ -217,52 +286,49 @@ __global__ void k_chunk_seq(const T *__restrict__ labels, const int32_t *__restr
         prev = cur;
     }
     if (EMIT) cend[base + c] = cum[L - 1];
-    else counts[(size_t)row * segs] = c + 1;       // other segments of the row stay zero (cleared by the launcher)
+    else counts[row] = c + 1;
 }
 
-// warps per row: as many as keep the whole launch in one wave of resident warps (148 SMs x 64)
-int chunk_segs_for(int rows) {
-    int segs = 16;
-    while (segs > 1 && (long long)rows * segs > 148LL * 64) segs >>= 1;
-    return segs;
-}
+int chunk_tiles_for(int nsites) { return (nsites + 7 + kTileLabels - 1) / kTileLabels; }   // +7: rows start anywhere in an aligned group
 
 void launch_chunk_count(const void *labels, const int32_t *rowmap, int label_bytes, int nsites, int rows, double weight_min,
-                        int32_t *counts, cudaStream_t st) {
-    const int segs = chunk_segs_for(rows);
+                        int32_t *counts, int32_t *rowsum, cudaStream_t st) {
     if (weight_min < 1.0) {
-        int grid = rows < 148 * 64 ? rows : 148 * 64;
-        if (label_bytes == 2) k_chunk_count<uint16_t><<<grid, 32 * segs, 0, st>>>((const uint16_t *)labels, rowmap, nsites, rows, counts);
-        else k_chunk_count<int32_t><<<grid, 32 * segs, 0, st>>>((const int32_t *)labels, rowmap, nsites, rows, counts);
+        const int tiles = chunk_tiles_for(nsites);
+        cudaMemsetAsync(rowsum, 0, (size_t)rows * sizeof(int32_t), st);
+        // one tile per block: 8 resident blocks per SM at different stages hide the latency better than a persistent
+        // loop with a one-tile-ahead prefetch (measured: 131 vs 235 us for 400 MB of labels); rows*tiles < 2^31
+        const unsigned grid = (unsigned)((long long)rows * tiles);
+        if (label_bytes == 2) k_chunk_count<uint16_t><<<grid, 256, 0, st>>>((const uint16_t *)labels, rowmap, nsites, rows, tiles, counts, rowsum);
+        else k_chunk_count<int32_t><<<grid, 256, 0, st>>>((const int32_t *)labels, rowmap, nsites, rows, tiles, counts, rowsum);
     } else {
-        cudaMemsetAsync(counts, 0, (size_t)rows * segs * sizeof(int32_t), st);
         int grid = (rows + 127) / 128;
         if (label_bytes == 2)
-            k_chunk_seq<uint16_t, false><<<grid, 128, 0, st>>>((const uint16_t *)labels, rowmap, nsites, rows, segs, weight_min, counts,
+            k_chunk_seq<uint16_t, false><<<grid, 128, 0, st>>>((const uint16_t *)labels, rowmap, nsites, rows, weight_min, rowsum,
                                                               nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
         else
-            k_chunk_seq<int32_t, false><<<grid, 128, 0, st>>>((const int32_t *)labels, rowmap, nsites, rows, segs, weight_min, counts,
+            k_chunk_seq<int32_t, false><<<grid, 128, 0, st>>>((const int32_t *)labels, rowmap, nsites, rows, weight_min, rowsum,
                                                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     }
 }
 
 void launch_chunk_emit(const void *labels, const int32_t *rowmap, int label_bytes, int nsites, int rows, double weight_min,
-                       const int32_t *row_off, const double *cum, const double *inc, double *cstart, double *cend,
-                       int32_t *chap, cudaStream_t st) {
-    const int segs = chunk_segs_for(rows);
+                       const int32_t *counts, const int32_t *row_off, const double *cum, const double *inc, double *cstart,
+                       double *cend, int32_t *chap, cudaStream_t st) {
     if (weight_min < 1.0) {
-        int grid = rows < 148 * 64 ? rows : 148 * 64;
+        const int tiles = chunk_tiles_for(nsites);
+        const unsigned grid = (unsigned)((long long)rows * tiles);
         if (label_bytes == 2)
-            k_chunk_emit<uint16_t><<<grid, 32 * segs, 0, st>>>((const uint16_t *)labels, rowmap, nsites, rows, row_off, cum, inc, cstart, cend, chap);
+            k_chunk_emit<uint16_t><<<grid, 256, 0, st>>>((const uint16_t *)labels, rowmap, nsites, rows, tiles, counts, row_off, cum, inc, cstart, cend, chap);
         else
-            k_chunk_emit<int32_t><<<grid, 32 * segs, 0, st>>>((const int32_t *)labels, rowmap, nsites, rows, row_off, cum, inc, cstart, cend, chap);
+            k_chunk_emit<int32_t><<<grid, 256, 0, st>>>((const int32_t *)labels, rowmap, nsites, rows, tiles, counts, row_off, cum, inc, cstart, cend, chap);
     } else {
         int grid = (rows + 127) / 128;
         if (label_bytes == 2)
-            k_chunk_seq<uint16_t, true><<<grid, 128, 0, st>>>((const uint16_t *)labels, rowmap, nsites, rows, segs, weight_min, nullptr,
+            k_chunk_seq<uint16_t, true><<<grid, 128, 0, st>>>((const uint16_t *)labels, rowmap, nsites, rows, weight_min, nullptr,
                                                              row_off, cum, inc, cstart, cend, chap);
         else
-            k_chunk_seq<int32_t, true><<<grid, 128, 0, st>>>((const int32_t *)labels, rowmap, nsites, rows, segs, weight_min, nullptr,
+            k_chunk_seq<int32_t, true><<<grid, 128, 0, st>>>((const int32_t *)labels, rowmap, nsites, rows, weight_min, nullptr,
                                                             row_off, cum, inc, cstart, cend, chap);
     }
 }
@@ -298,16 +364,8 @@ void launch_exclusive_scan_i32(const int32_t *in, int32_t *out, int n, cudaStrea
     k_exclusive_scan_i32<<<1, 1024, 0, st>>>(in, out, n);
 }
 
-// row_off[r] = seg_off[r * segs], r = 0..rows
-__global__ void k_compact_row_off(const int32_t *__restrict__ seg_off, int32_t *__restrict__ row_off, int rows, int segs) {
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r <= rows) row_off[r] = seg_off[(size_t)r * segs];
-}
-
-void launch_chunk_scan(const int32_t *counts, int32_t *seg_off, int32_t *row_off, int rows, cudaStream_t st) {
-    const int segs = chunk_segs_for(rows);
-    k_exclusive_scan_i32<<<1, 1024, 0, st>>>(counts, seg_off, rows * segs);
-    k_compact_row_off<<<(rows + 1 + 255) / 256, 256, 0, st>>>(seg_off, row_off, rows, segs);
+void launch_chunk_scan(const int32_t *rowsum, int32_t *row_off, int rows, cudaStream_t st) {
+    k_exclusive_scan_i32<<<1, 1024, 0, st>>>(rowsum, row_off, rows);
 }
 
 // =============================================================================================

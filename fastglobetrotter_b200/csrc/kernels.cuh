@@ -96,16 +96,14 @@ void launch_commit_ordered(const CommitArgs &a, int max_slab_width, cudaStream_t
 size_t commit_tile_bytes(int K, int slab_width);
 
 // ---- launch wrappers (all asynchronous on `st`) ---------------------------------------------
-constexpr int kChunkSegs = 16;  // most segments (warps) a painting row is split into by the chunk kernels (buffer sizing)
-int chunk_segs_for(int rows);   // segments actually used for a launch over `rows` rows
+int chunk_tiles_for(int nsites);   // 2048-label tiles per painting row (sizes the per-tile count buffer)
 void launch_chunk_count(const void *labels, const int32_t *rowmap, int label_bytes, int nsites, int rows, double weight_min,
-                        int32_t *counts /*[rows*chunk_segs_for(rows)]*/, cudaStream_t st);
-// seg_off[rows*segs+1] = exclusive scan of counts; row_off[rows+1] = its per-row entries
-void launch_chunk_scan(const int32_t *counts, int32_t *seg_off, int32_t *row_off, int rows, cudaStream_t st);
+                        int32_t *counts /*[rows*chunk_tiles_for(nsites)]*/, int32_t *rowsum /*[rows]*/, cudaStream_t st);
+void launch_chunk_scan(const int32_t *rowsum, int32_t *row_off /*[rows+1]*/, int rows, cudaStream_t st);
 void launch_exclusive_scan_i32(const int32_t *in, int32_t *out /*[n+1]*/, int n, cudaStream_t st);
 void launch_chunk_emit(const void *labels, const int32_t *rowmap, int label_bytes, int nsites, int rows, double weight_min,
-                       const int32_t *seg_off, const double *cum, const double *inc, double *cstart, double *cend,
-                       int32_t *chap, cudaStream_t st);
+                       const int32_t *counts, const int32_t *row_off, const double *cum, const double *inc, double *cstart,
+                       double *cend, int32_t *chap, cudaStream_t st);
 void launch_bin_sort(int n_phys, int rows_per_ind, const int32_t *row_off, const double *cstart, const double *cend,
                      const int32_t *chap, const int32_t *donor_label, int n_donor_labels, double cutoff, int K, int mode,
                      int nb, int W, const double *Etab, double divisor, Chunk *sorted, const Chunk **chunk_ptr, int32_t *t,

@@ -537,3 +537,26 @@ def test_repeatable_at_scale_with_other_kernels_on_the_gpu(lib):
     finally:
         lib.set_option("batch_pairs", 0)
         lib.set_option("accum_impl", 2)
+
+
+def test_odd_row_lengths_and_label_block_offsets(lib, oracle):
+    """the chunk kernels read 16-bit labels as aligned 16-byte groups: odd row lengths, blocks of individuals that start
+    at any byte offset (host path, several blocks), a row-mapped NULL call and 32-bit labels must all chunk identically."""
+    K, S = 5, 2
+    tw = np.random.default_rng(2).random(K * K * S * S)
+    for L in (2501, 4099, 3333):
+        spec = synth.SynthSpec(n_chrom=1, n_inds=5, ploidy=2, nsamples=3, n_snps=L, K=K, rate=6e-7, seed=L)
+        pos, rate, labels = synth.make_chromosome(spec, 0)
+        dl = spec.donor_label_vec()
+        chrom = [{"pos": pos, "rate": rate, "labels": labels}]
+        for blocks in (0, 5, 2):
+            lib.set_option("blocks", blocks)
+            try:
+                _run_both(lib, oracle, 1, 2, 3, chrom, np.arange(5), 0.1, 80, 10, K, dl, 0.0, 1.0, S, tw, seed=L + blocks)
+            finally:
+                lib.set_option("blocks", 0)
+        _run_both(lib, oracle, 1, 2, 3, [{"pos": pos, "rate": rate, "labels": labels.astype(np.int32)}], np.arange(5), 0.1, 80, 10,
+                  K, dl, 0.0, 1.0, S, tw, seed=5)
+        n_o, ev = oracle.data_read_null_packed(2, 3, chrom, np.array([3, 1, 4]), 0.1, 60, 10, K, dl, 0.0, 1.0)
+        n_g, st = lib.data_read_null_packed(2, 3, chrom, np.array([3, 1, 4]), 0.1, 60, 10, K, dl, 0.0, 1.0)
+        assert st["pairs"] == ev and np.array_equal(n_g, n_o), L
