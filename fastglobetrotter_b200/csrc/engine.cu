@@ -202,6 +202,7 @@ Engine::SlabPlan Engine::make_slab_plan(int G, int grid_start, double bw, int W,
     }
     auto plan_for = [&](int width) {
         SlabPlan q;
+        q.slab_width = width;
         q.slab_of.resize(G);
         for (int b = 0; b < G; b++) q.slab_of[b] = b / width;
         int n_slabs = (G + width - 1) / width;
@@ -317,7 +318,7 @@ int Engine::prep_chromosome(const fgt_problem_t &pb, int h, const int32_t *rowma
     CK(cudaMemsetAsync(d_cnt, 0, cm * sizeof(int32_t), st_));
     launch_bin_sort(n_groups, rows_per_ind, d_rowoff, d_cstart, d_cend, d_chap, d_donor_.as<int32_t>(pb.n_donor_labels),
                     pb.n_donor_labels, pb.gridweight_max_cutoff, K, pb.mode, nb, W, d_etab, pb.mode == 3 ? 8.0 : 10.0,
-                    d_sorted, d_cbase, d_t, d_first, d_yoff, d_ro, d_cnt, d_rf, d_err_.as<int>(4), nullptr, st_);
+                    d_sorted, total_chunks, d_cbase, nullptr, nullptr, d_t, d_first, d_yoff, d_ro, d_cnt, d_rf, d_err_.as<int>(4), nullptr, st_);
     launches_ += 1;
     cs.totals.resize(n_groups);
     CK(cudaMemcpy2DAsync(cs.totals.data(), sizeof(long long), d_ro + nb, (nb + 1) * sizeof(long long), sizeof(long long),
@@ -375,7 +376,8 @@ int Engine::prep_block(const fgt_problem_t &pb, int h, int p0, int p1, int blk, 
     double *d_cstart = d_cstart_.as<double>(total_chunks), *d_cend = d_cend_.as<double>(total_chunks);
     int32_t *d_chap = d_chap_.as<int32_t>(total_chunks);
     if ((int)cs.sorted_blocks.size() <= blk) cs.sorted_blocks.resize(blk + 1);
-    Chunk *d_sorted = cs.sorted_blocks[blk].as<Chunk>(total_chunks);
+    // 32-byte records, then the compact (pos, size) / label copies phase 1 gathers from (k_bin_sort)
+    Chunk *d_sorted = (Chunk *)cs.sorted_blocks[blk].get((size_t)total_chunks * (sizeof(Chunk) + sizeof(double2) + sizeof(int32_t)));
     if (!d_cstart || !d_cend || !d_chap || !d_sorted) return FGT_ERR_CUDA;
     launch_chunk_emit(lab_blk, nullptr, pb.label_bytes, L, rows, pb.weight_min, d_counts, d_rowoff, (const double *)cs.cum.p,
                       (const double *)cs.inc.p, d_cstart, d_cend, d_chap, sp);
@@ -388,7 +390,8 @@ int Engine::prep_block(const fgt_problem_t &pb, int h, int p0, int p1, int blk, 
     CK(cudaMemsetAsync(d_cnt, 0, cm * sizeof(int32_t), sp));
     launch_bin_sort(np, PM, d_rowoff, d_cstart, d_cend, d_chap, (const int32_t *)d_donor_.p, pb.n_donor_labels,
                     pb.gridweight_max_cutoff, K, pb.mode, nb, W, (const double *)cs.etab.p, pb.mode == 3 ? 8.0 : 10.0, d_sorted,
-                    (const Chunk **)cs.chunk_ptr.p + p0, (int32_t *)cs.t.p + (size_t)p0 * nb, (int32_t *)cs.first.p + (size_t)p0 * nb,
+                    total_chunks, (const Chunk **)cs.chunk_ptr.p + p0, (const double2 **)cs.ps_ptr.p + p0,
+                    (const int32_t **)cs.pop_ptr.p + p0, (int32_t *)cs.t.p + (size_t)p0 * nb, (int32_t *)cs.first.p + (size_t)p0 * nb,
                     (int32_t *)cs.yoff.p + (size_t)p0 * nb * W, (long long *)cs.rowoff.p + (size_t)p0 * (nb + 1), d_cnt, d_rf,
                     (int *)d_err_.p, d_tot, sp);
     launches_ += 2;
@@ -442,7 +445,7 @@ int Engine::setup_chromosome(const fgt_problem_t &pb, int h, ChromState &cs, fgt
     if (!d_cum || !d_inc || !d_etab) return FGT_ERR_CUDA;
     if (!cs.t.as<int32_t>((size_t)n_phys * nb) || !cs.first.as<int32_t>((size_t)n_phys * nb) ||
         !cs.yoff.as<int32_t>((size_t)n_phys * nb * W) || !cs.rowoff.as<long long>((size_t)n_phys * (nb + 1)) ||
-        !cs.chunk_ptr.as<const Chunk *>(n_phys))
+        !cs.chunk_ptr.as<const Chunk *>(n_phys) || !cs.ps_ptr.as<const double2 *>(n_phys) || !cs.pop_ptr.as<const int32_t *>(n_phys))
         return FGT_ERR_CUDA;
     cs.totals.assign(n_phys, 0);
     // on their own stream: the prep stream may already be streaming labels through the chunk count
@@ -545,6 +548,7 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
         for (int k = 0; k < K; k++)
             for (int hh = k; hh < K; hh++) pairkh[q++] = K * k + hh;
         CK(cudaMemcpyAsync(d_pairkh, pairkh.data(), P * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
+        if (impl != 1 && G >= 65536) impl = 1;       // phase 1 divides bin indices with a 16-bit reciprocal
         if (impl != 1) {
             plan = make_slab_plan(G, pb.grid_start, pb.binwidth, W0, N);
             slabs = plan.slabs;
@@ -716,6 +720,7 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
             ChromPrep cpd{};
             cpd.nb = cs.nb; cpd.W = cs.W; cpd.n_phys = n_phys;
             cpd.chunk_ptr = (const Chunk *const *)cs.chunk_ptr.p;
+            cpd.ps_ptr = (const double2 *const *)cs.ps_ptr.p; cpd.pop_ptr = (const int32_t *const *)cs.pop_ptr.p;
             cpd.t = (const int32_t *)cs.t.p; cpd.first = (const int32_t *)cs.first.p;
             cpd.yoff = (const int32_t *)cs.yoff.p; cpd.rowoff = (const long long *)cs.rowoff.p;
             const long long *pbase = d_pairbase + (size_t)h * N + b0;
@@ -749,8 +754,10 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
                 ea.cp = cpd; ea.draws = (const uint2 *)d_draws; ea.draws_limit = nthreads * (long long)kRun / 2;
                 ea.pair_base = pbase; ea.phys_of = pphys;
                 ea.N = Nb; ea.K = K; ea.G = G; ea.grid_start = pb.grid_start; ea.mode = pb.mode; ea.n_slots = plan.n_slots;
-                ea.bw = pb.binwidth; ea.half_bw = pb.binwidth / 2.0;
+                ea.bw = pb.binwidth; ea.half_bw = pb.binwidth / 2.0; ea.cutoff = pb.gridweight_max_cutoff;
                 ea.slab_of = d_slabof; ea.first_slab = d_firstslab; ea.slab_w = d_slabw; ea.slab_b0 = d_slabb0;
+                ea.slab_width = plan.slab_width;
+                ea.slab_magic = plan.slab_width > 1 ? (uint32_t)(((1ULL << 32) + plan.slab_width - 1) / plan.slab_width) : 0u;
                 ea.recs = d_recs; ea.regions = d_regions; ea.slabs = d_slabs; ea.n_slabs = (int)slabs.size(); ea.nd_max = nd_max;
                 ea.err = d_err;
                 {   // enough warps to fill the GPU twice over even for a small range of individuals

@@ -20,7 +20,7 @@ struct DevBuf {
 };
 
 struct ChromState {            // per chromosome device state that must outlive the prep pass
-    DevBuf sorted, chunk_base, t, first, yoff, rowoff, cum, inc, etab, chunk_ptr;
+    DevBuf sorted, chunk_base, t, first, yoff, rowoff, cum, inc, etab, chunk_ptr, ps_ptr, pop_ptr;
     std::vector<DevBuf> sorted_blocks;   // data_read path: one sorted-chunk buffer per block of individuals
     int nb = 0, W = 0;
     std::vector<long long> totals;   // [n_phys] pairs each packed individual samples on this chromosome
@@ -77,7 +77,7 @@ class Engine {
     int prep_chromosome(const fgt_problem_t &pb, int h, const int32_t *rowmap_dev, int rows, int rows_per_ind,
                         int n_groups, bool for_null, ChromState &cs, fgt_stats_t &stx);
     std::vector<SlabDesc> make_slabs(int G, int grid_start, double bw, int W, int N) const;
-    struct SlabPlan { std::vector<SlabDesc> slabs; std::vector<int32_t> slab_of, first_slab; int n_slots = 0; };
+    struct SlabPlan { std::vector<SlabDesc> slabs; std::vector<int32_t> slab_of, first_slab; int n_slots = 0, slab_width = 1; };
     SlabPlan make_slab_plan(int G, int grid_start, double bw, int W, int N) const;
 
     bool inited_ = false;

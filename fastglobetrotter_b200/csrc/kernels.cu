@@ -387,7 +387,8 @@ __global__ void __launch_bounds__(256)
 k_bin_sort(int rows_per_ind, const int32_t *__restrict__ row_off, const double *__restrict__ cstart,
            const double *__restrict__ cend, const int32_t *__restrict__ chap, const int32_t *__restrict__ donor_label,
            int n_donor_labels, double cutoff, int K, int mode, int nb, int W, const double *__restrict__ Etab,
-           double divisor, Chunk *__restrict__ sorted, const Chunk **__restrict__ chunk_ptr, int32_t *__restrict__ t_out,
+           double divisor, Chunk *__restrict__ sorted, long long n_sorted, const Chunk **__restrict__ chunk_ptr,
+           const double2 **__restrict__ ps_ptr, const int32_t **__restrict__ pop_ptr, int32_t *__restrict__ t_out,
            int32_t *__restrict__ first_out, int32_t *__restrict__ yoff, long long *__restrict__ rowoff,
            int32_t *__restrict__ cntmat, int32_t *__restrict__ runfirst, int *__restrict__ err, long long *__restrict__ totals) {
     const int p = blockIdx.x;
@@ -397,7 +398,13 @@ k_bin_sort(int rows_per_ind, const int32_t *__restrict__ row_off, const double *
     int32_t *rf = runfirst + (size_t)p * rows_per_ind * nb;
     int32_t *t = t_out + (size_t)p * nb;
     int32_t *first = first_out + (size_t)p * nb;
-    if (threadIdx.x == 0) chunk_ptr[p] = sorted + c0;
+    // compact copies for phase 1 live behind the 32-byte records of the same buffer: (pos, size) pairs, then labels
+    double2 *ps = reinterpret_cast<double2 *>(sorted + n_sorted);
+    int32_t *pops = reinterpret_cast<int32_t *>(ps + n_sorted);
+    if (threadIdx.x == 0) {
+        chunk_ptr[p] = sorted + c0;
+        if (ps_ptr) { ps_ptr[p] = ps + c0; pop_ptr[p] = pops + c0; }
+    }
     // phase 1: occupancy of (painting, coarse bin); first chunk of each run
     for (int r = 0; r < rows_per_ind; r++) {
         const int a = row_off[r0 + r], b = row_off[r0 + r + 1];
@@ -453,6 +460,7 @@ k_bin_sort(int rows_per_ind, const int32_t *__restrict__ row_off, const double *
             Chunk c;
             c.pos = pos; c.size = len; c.w = (len > cutoff) ? cutoff : len; c.pop = pop; c.hapid = hap;
             sorted[dest] = c;
+            if (ps_ptr) { ps[dest] = make_double2(pos, len); pops[dest] = pop; }
         }
     }
     if (bad) atomicOr(err, bad);
@@ -480,11 +488,12 @@ k_bin_sort(int rows_per_ind, const int32_t *__restrict__ row_off, const double *
 
 void launch_bin_sort(int n_phys, int rows_per_ind, const int32_t *row_off, const double *cstart, const double *cend,
                      const int32_t *chap, const int32_t *donor_label, int n_donor_labels, double cutoff, int K, int mode,
-                     int nb, int W, const double *Etab, double divisor, Chunk *sorted, const Chunk **chunk_ptr, int32_t *t,
+                     int nb, int W, const double *Etab, double divisor, Chunk *sorted, long long n_sorted, const Chunk **chunk_ptr,
+                     const double2 **ps_ptr, const int32_t **pop_ptr, int32_t *t,
                      int32_t *first, int32_t *yoff, long long *rowoff, int32_t *cntmat, int32_t *runfirst, int *err,
                      long long *totals, cudaStream_t st) {
     k_bin_sort<<<n_phys, 256, 0, st>>>(rows_per_ind, row_off, cstart, cend, chap, donor_label, n_donor_labels, cutoff, K,
-                                      mode, nb, W, Etab, divisor, sorted, chunk_ptr, t, first, yoff, rowoff, cntmat,
+                                      mode, nb, W, Etab, divisor, sorted, n_sorted, chunk_ptr, ps_ptr, pop_ptr, t, first, yoff, rowoff, cntmat,
                                       runfirst, err, totals);
 }
 
@@ -731,13 +740,25 @@ __device__ __forceinline__ Chunk ldg_chunk(const Chunk *p) {
 // except the "+=" happens here.
 struct PairEval { int cell, local, slot; double val; };
 
+// Phase 1 gathers the compact copy of a chunk: one 16-byte (pos, size) pair -- 8 per cache line instead of 4 -- and its
+// label (32 per line): the kernel is bound by the L1 wavefronts of these scattered gathers.
+struct PairChunk { double pos, size; int pop; };
+struct BinRef { const double2 *ps; const int32_t *pop; };
+__device__ __forceinline__ PairChunk ldg_pair_chunk(const double2 *ps, const int32_t *pop) {
+    PairChunk c;
+    const double2 v = __ldg(ps);
+    c.pos = v.x; c.size = v.y; c.pop = __ldg(pop);
+    return c;
+}
+
 __device__ __forceinline__ PairEval eval_pair(bool in_range, uint2 r, int t1, double inv1, int t2, double inv2,
-                                              const Chunk *binA, const Chunk *binB, const EvalArgs &a, int slab0, int &bad) {
+                                              const BinRef binA, const BinRef binB, const EvalArgs &a, int slab0, int &bad) {
     PairEval o;
     o.cell = -1; o.local = 0; o.slot = -1; o.val = 0.0;
     if (!in_range) return o;
     // reference C:136-137: chunk1 = start_bin[j] + rand() % t_1 ; chunk2 = start_bin[k] + rand() % t_2
-    const Chunk A = ldg_chunk(binA + fastmod_u32(r.x, (unsigned)t1, inv1)), B = ldg_chunk(binB + fastmod_u32(r.y, (unsigned)t2, inv2));
+    const unsigned ia = fastmod_u32(r.x, (unsigned)t1, inv1), ib = fastmod_u32(r.y, (unsigned)t2, inv2);
+    const PairChunk A = ldg_pair_chunk(binA.ps + ia, binA.pop + ia), B = ldg_pair_chunk(binB.ps + ib, binB.pop + ib);
     bool live = true;
     if (a.mode == 1) live = (A.pop != 0) && (B.pop != 0);                  // reference C:138-142
     else if (A.pop == 0 || B.pop == 0) { bad |= kErrMode3Target; live = false; }
@@ -757,13 +778,16 @@ __device__ __forceinline__ PairEval eval_pair(bool in_range, uint2 r, int t1, do
         const int l1 = A.pop - 1, l2 = B.pop - 1;
         const int lo_l = l1 < l2 ? l1 : l2, hi_l = l1 < l2 ? l2 : l1;
         const int row = tri_row(lo_l, hi_l, a.K);
-        const int slab = a.slab_of[bb];
+        const int slab = a.slab_magic ? (int)__umulhi((unsigned)bb, a.slab_magic) : bb;   // bb / slab_width (exact: both < 2^16; 0 = width 1)
         const int slot = slab - slab0;
         if (slot < 0 || slot >= a.n_slots) { bad |= kErrInternal; return o; }
         o.cell = row * a.G + bb;
-        o.local = row * a.slab_w[slab] + (bb - a.slab_b0[slab]);
+        const int sb0 = slab * a.slab_width;
+        const int sw = min(a.slab_width, a.G - sb0);                          // the last slab may be narrower
+        o.local = row * sw + (bb - sb0);
         o.slot = slot;
-        o.val = __dmul_rn(A.w, B.w);
+        // gridweight = min(size, cutoff), as stored by the chunk builder (reference C:527)
+        o.val = __dmul_rn(A.size > a.cutoff ? a.cutoff : A.size, B.size > a.cutoff ? a.cutoff : B.size);
     }
     return o;
 }
@@ -785,12 +809,13 @@ __global__ void __launch_bounds__(128, 8) k_eval_pairs(const EvalArgs a) {
     if (t1 <= 0) return;
     const int32_t *F = cp.first + (size_t)phys * nb;
     const int32_t *yo = cp.yoff + ((size_t)phys * nb + j) * W;
-    const Chunk *ch = cp.chunk_ptr[phys];
+    const double2 *chps = cp.ps_ptr[phys];
+    const int32_t *chpop = cp.pop_ptr[phys];
     const long long row_pair0 = a.pair_base[n] + cp.rowoff[(size_t)phys * (nb + 1) + j];
     const int f1 = F[j];
     const double inv1 = __ddiv_rn(1.0, (double)t1);
     const int ns = a.n_slots;
-    const Chunk *binA = ch + f1;
+    const BinRef binA{chps + f1, chpop + f1};
     int dmax = W - 1;
     if (nb - 1 - j < dmax) dmax = nb - 1 - j;
     int bad = 0;
@@ -830,7 +855,7 @@ __global__ void __launch_bounds__(128, 8) k_eval_pairs(const EvalArgs a) {
         const long long seg = row_pair0 + y0;
         UpdateRec *reg = a.recs + seg * ns;
         const int slab0 = a.first_slab[d];
-        const Chunk *binB = ch + f2;
+        const BinRef binB{chps + f2, chpop + f2};
         int c[kMaxSlots] = {0, 0, 0, 0};
         for (int base = 0; base < Y; base += 64) {
             const int q0 = base + lane, q1 = base + 32 + lane;

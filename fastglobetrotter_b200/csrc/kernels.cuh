@@ -28,6 +28,8 @@ struct ChromPrep {  // per chromosome, per call: everything the accumulation ker
     int32_t W;              // window_size (reference C:117 / C:1125)
     int32_t n_phys;         // packed individuals
     const Chunk *const *chunk_ptr; // [n_phys] coarse-bin-sorted chunks of each packed individual
+    const double2 *const *ps_ptr;  // [n_phys] the same chunks as (pos, size) pairs -- 16-byte gathers for phase 1
+    const int32_t *const *pop_ptr; // [n_phys] ... and their population labels
     const int32_t *t;       // [n_phys][nb] chunks per coarse bin          (numchunckinbin)
     const int32_t *first;   // [n_phys][nb] exclusive prefix of t          (start_bin)
     const int32_t *yoff;    // [n_phys][nb][W]: yoff[..][d] = sum_{delta=1..d} Y(j, j+delta)
@@ -65,7 +67,7 @@ struct EvalArgs {
     const long long *pair_base;   // [N]
     const int32_t *phys_of;       // [N]
     int32_t N, K, G, grid_start, mode, n_slots;
-    double bw, half_bw;
+    double bw, half_bw, cutoff;
     const int32_t *slab_of;       // [G] slab index of every fine bin (relative to grid_start)
     const int32_t *first_slab;    // [W] first slab reachable from separation d
     const int32_t *slab_w;        // [n_slabs] width of each slab in bins
@@ -74,6 +76,8 @@ struct EvalArgs {
     RegionEnt *regions;           // [N*n_slabs][nb-1][nd_max] region directory, slab-major (zero = empty)
     const SlabDesc *slabs;
     int32_t n_slabs, nd_max;
+    int32_t slab_width;           // bins per slab (all slabs but the last); slab_magic = ceil(2^32 / slab_width)
+    uint32_t slab_magic;
     int32_t d_parts;              // warps per (individual, coarse bin): the separations are split into parts of equal pair counts
     int *err;
 };
@@ -106,7 +110,8 @@ void launch_chunk_emit(const void *labels, const int32_t *rowmap, int label_byte
                        double *cend, int32_t *chap, cudaStream_t st);
 void launch_bin_sort(int n_phys, int rows_per_ind, const int32_t *row_off, const double *cstart, const double *cend,
                      const int32_t *chap, const int32_t *donor_label, int n_donor_labels, double cutoff, int K, int mode,
-                     int nb, int W, const double *Etab, double divisor, Chunk *sorted, const Chunk **chunk_ptr, int32_t *t,
+                     int nb, int W, const double *Etab, double divisor, Chunk *sorted, long long n_sorted, const Chunk **chunk_ptr,
+                     const double2 **ps_ptr, const int32_t **pop_ptr, int32_t *t,
                      int32_t *first, int32_t *yoff, long long *rowoff, int32_t *cntmat, int32_t *runfirst, int *err,
                      long long *totals, cudaStream_t st);
 void launch_rand_fill(const uint32_t *base_hist, const uint32_t *level_tab, uint32_t *out, long long n_threads,
