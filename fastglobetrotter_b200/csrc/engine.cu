@@ -367,7 +367,9 @@ int Engine::prep_block(const fgt_problem_t &pb, int h, int p0, int p1, int blk, 
     }
     count_pending_ = false;
     int32_t *d_rowoff = (int32_t *)d_rowoff_.p, *d_counts = (int32_t *)d_counts_.p;
+    vtick("  prep: waiting for the chunk count");
     CK(cudaStreamSynchronize(sp));
+    vtick("  prep: chunk count known");
     const int32_t total_chunks = *pin_small_;
     stx.d2h_bytes += 4;
     if (total_chunks <= 0) return FGT_ERR_ARG;
@@ -396,9 +398,16 @@ int Engine::prep_block(const fgt_problem_t &pb, int h, int p0, int p1, int blk, 
                     (int *)d_err_.p, d_tot, sp);
     launches_ += 2;
     CK(cudaMemcpyAsync(cs.totals.data() + p0, d_tot, np * sizeof(long long), cudaMemcpyDeviceToHost, sp));
+    vtick("  prep: emit + bin sort enqueued");
     CK(cudaStreamSynchronize(sp));
     stx.d2h_bytes += (int64_t)np * 8;
     return FGT_OK;
+}
+
+void Engine::vtick(const char *what) const {
+    if (opt.verbose)
+        fprintf(stderr, "[fgt] %8.3f ms  %s\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call_start_).count(), what);
 }
 
 // First step of prep_block, separately launchable: count the chunks of the block's rows, scan, and start the
@@ -428,7 +437,18 @@ int Engine::setup_chromosome(const fgt_problem_t &pb, int h, ChromState &cs, fgt
     const fgt_chrom_t &c = pb.chrom[h];
     const int L = c.nsites, n_phys = pb.n_packed_inds;
     if (L <= 0) return FGT_ERR_ARG;
-    std::vector<double> cum(L), inc(L);
+    const int W = (int)std::ceil(pb.binwidth * pb.num_bins) + (pb.mode == 3 ? 1 : 3);   // C:117 / C:1125
+    // the tables are built straight into pinned memory and uploaded without a host wait (the previous chromosome's
+    // upload from the same staging area has to be over first)
+    const size_t need = ((size_t)2 * L + W) * sizeof(double);
+    CK(cudaStreamSynchronize(st_aux_));
+    if (pin_tab_cap_ < need) {
+        if (pin_tab_) cudaFreeHost(pin_tab_);
+        pin_tab_ = nullptr; pin_tab_cap_ = 0;
+        if (cudaHostAlloc((void **)&pin_tab_, need + need / 4, cudaHostAllocDefault) != cudaSuccess) return FGT_ERR_CUDA;
+        pin_tab_cap_ = need + need / 4;
+    }
+    double *cum = pin_tab_, *inc = pin_tab_ + L, *etab = pin_tab_ + 2 * (size_t)L;
     double total = 0.0;                       // sequential fp64 sum exactly as reference C:494 (increment re-used at C:501)
     cum[0] = 0.0; inc[0] = 0.0;
     for (int j = 1; j < L; j++) {
@@ -437,9 +457,7 @@ int Engine::setup_chromosome(const fgt_problem_t &pb, int h, ChromState &cs, fgt
         cum[j] = total; inc[j] = step;
     }
     const int nb = (int)cum[L - 1] / 1 + 1;                  // every painting's last chunk ends at cum[L-1] (C:57-68)
-    const int W = (int)std::ceil(pb.binwidth * pb.num_bins) + (pb.mode == 3 ? 1 : 3);   // C:117 / C:1125
     cs.nb = nb; cs.W = W; cs.n_chunks = 0;
-    std::vector<double> etab(W);
     for (int d = 0; d < W; d++) etab[d] = std::exp(-0.05 * d);   // exp(-0.05*(k-j)) with the host libm, as C:129
     double *d_cum = cs.cum.as<double>(L), *d_inc = cs.inc.as<double>(L), *d_etab = cs.etab.as<double>(W);
     if (!d_cum || !d_inc || !d_etab) return FGT_ERR_CUDA;
@@ -449,10 +467,12 @@ int Engine::setup_chromosome(const fgt_problem_t &pb, int h, ChromState &cs, fgt
         return FGT_ERR_CUDA;
     cs.totals.assign(n_phys, 0);
     // on their own stream: the prep stream may already be streaming labels through the chunk count
-    CK(cudaMemcpyAsync(d_cum, cum.data(), L * sizeof(double), cudaMemcpyHostToDevice, st_aux_));
-    CK(cudaMemcpyAsync(d_inc, inc.data(), L * sizeof(double), cudaMemcpyHostToDevice, st_aux_));
-    CK(cudaMemcpyAsync(d_etab, etab.data(), W * sizeof(double), cudaMemcpyHostToDevice, st_aux_));
-    CK(cudaStreamSynchronize(st_aux_));      // the host vectors die here; later prep-stream work is enqueued after this
+    CK(cudaMemcpyAsync(d_cum, cum, L * sizeof(double), cudaMemcpyHostToDevice, st_aux_));
+    CK(cudaMemcpyAsync(d_inc, inc, L * sizeof(double), cudaMemcpyHostToDevice, st_aux_));
+    CK(cudaMemcpyAsync(d_etab, etab, W * sizeof(double), cudaMemcpyHostToDevice, st_aux_));
+    if (!tab_ready_) CK(cudaEventCreateWithFlags(&tab_ready_, cudaEventDisableTiming));
+    CK(cudaEventRecord(tab_ready_, st_aux_));
+    CK(cudaStreamWaitEvent(st_prep_, tab_ready_, 0));        // chunk emit / bin sort of this chromosome come after this
     stx.h2d_bytes += 2LL * L * sizeof(double);
     return FGT_OK;
 }
@@ -472,9 +492,8 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
     CK(cudaEventRecord(ev[0], st_));
 
     const auto t_start = std::chrono::steady_clock::now();
-    auto tick = [&](const char *what) {
-        if (opt.verbose) fprintf(stderr, "[fgt] %8.3f ms  %s\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(), what);
-    };
+    t_call_start_ = t_start;
+    auto tick = [&](const char *what) { vtick(what); };
     const int N = pb.num_inds, Cn = pb.num_chrom, K = pb.num_donors, G = pb.num_bins, S = pb.num_surrogates;
     const int PM = pb.ploidy * pb.nsamples;
     const int n_phys = pb.n_packed_inds;
@@ -491,6 +510,14 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
     const bool reuse = opt.reuse_prep && (int)chroms_.size() == Cn && !chroms_.empty() && chroms_[0].nb > 0 &&
                        (int)chroms_[0].totals.size() == n_phys;
     opt.reuse_prep = 0;
+    // device-resident paintings: the first chromosome's chunk count needs nothing but the labels -- start it before
+    // the per-call tables are built and uploaded
+    count_pending_ = false;
+    if (!reuse && pb.chrom[0].labels_on_device && pb.chrom[0].nsites > 0) {
+        const int nb0 = opt.blocks > 0 ? std::min(n_phys, opt.blocks) : 1;
+        rc = prep_count(pb, 0, 0, (int)((long long)n_phys * 1 / nb0), pb.chrom[0].labels, nullptr);
+        if (rc) return rc;
+    }
     if (reuse && !count_only) {
         stx.h2d_bytes += carry_.h2d_bytes; stx.d2h_bytes += carry_.d2h_bytes; stx.chunks += carry_.chunks;
         launches_ += carry_.kernel_launches;
@@ -833,11 +860,12 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
             }
             stx.h2d_bytes += (int64_t)(bytes_per_ind * n_phys);
         }
-        count_pending_ = false;
         if (!reuse && c.labels_on_device) {
             // device-resident paintings: the chunk count streams the labels while the host builds the cM prefix
-            rc = prep_count(pb, h, blk_lo(0), blk_lo(1), d_lab, copy_done[0]);
-            if (rc) return rc;
+            if (!(count_pending_ && count_key_[0] == h && count_key_[1] == blk_lo(0) && count_key_[2] == blk_lo(1))) {
+                rc = prep_count(pb, h, blk_lo(0), blk_lo(1), d_lab, copy_done[0]);
+                if (rc) return rc;
+            }
             rc = setup_chromosome(pb, h, cs, stx);
             if (rc) return rc;
         }

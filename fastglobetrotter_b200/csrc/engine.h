@@ -3,6 +3,7 @@
 #include <cstdint>
 #include <map>
 #include <string>
+#include <chrono>
 #include <vector>
 
 #include "../../include/fgt_companion.h"
@@ -71,6 +72,8 @@ class Engine {
     bool fetch_history(History &h);          // current stream state (libc-coupled or private)
     void store_history(const History &h);
     int setup_chromosome(const fgt_problem_t &pb, int h, ChromState &cs, fgt_stats_t &stx);
+    void vtick(const char *what) const;
+    std::chrono::steady_clock::time_point t_call_start_;
     int prep_count(const fgt_problem_t &pb, int h, int p0, int p1, const void *d_lab, cudaEvent_t copy_done);
     int prep_block(const fgt_problem_t &pb, int h, int p0, int p1, int blk, const void *d_lab, cudaEvent_t copy_done,
                    ChromState &cs, fgt_stats_t &stx);
@@ -100,6 +103,9 @@ class Engine {
     double mem_budget_bytes_ = 0;
     long long last_shape_sig_ = -1;
     long long last_first_batch_threads_ = 0;   // generator runs the previous call's first batch used (speculation size)
+    double *pin_tab_ = nullptr;       // pinned staging of a chromosome's cM prefix / increments / exp table
+    size_t pin_tab_cap_ = 0;
+    cudaEvent_t tab_ready_ = nullptr;
     int32_t *pin_small_ = nullptr;   // pinned word for the chunk-count read-back
     bool count_pending_ = false;
     int count_key_[3] = {0, 0, 0};

@@ -1172,44 +1172,44 @@ void launch_commit_ordered(const CommitArgs &a, int max_slab_width, cudaStream_t
 //    temp_weights[(K*k+h)*S*S + mn] * counts[n][(k,h)][i]; multiply and add rounded separately,
 //    summed in the reference's order, so the result is bit-identical.
 // =============================================================================================
-constexpr int PT = 64, PKK = 16;
-__global__ void __launch_bounds__(256)
+constexpr int PT = 64, PKK = 16, PTM_MAX = 100;      // bins per tile, pairs per slice, most surrogate pairs per tile
+__global__ void __launch_bounds__(16 * (PTM_MAX / 4))
 k_project(const double *__restrict__ tensor, int K, int G, int S, const double *__restrict__ tw,
           const int32_t *__restrict__ pair_kh, double *__restrict__ results) {
     const int n = blockIdx.z;
     const int SS = S * S, P = K * (K + 1) / 2;
-    const int i0 = blockIdx.x * PT, m0 = blockIdx.y * PT;
+    const int TY = blockDim.x >> 4, PTM = 4 * TY;       // the tile is PTM surrogate pairs x PT bins; 4 x 4 outputs per thread
+    const int i0 = blockIdx.x * PT, m0 = blockIdx.y * PTM;
     const double *B = tensor + (size_t)n * P * G;
     double *out = results + (size_t)n * SS * G;
-    __shared__ double sA[PKK][PT + 1];   // [pair][mn]
-    __shared__ double sB[PKK][PT + 1];   // [pair][i]
+    __shared__ double sA[PKK][PTM_MAX + 1];   // [pair][mn]
+    __shared__ double sB[PKK][PT + 1];        // [pair][i]
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     double acc[4][4];
 #pragma unroll
     for (int u = 0; u < 4; u++)
 #pragma unroll
         for (int v = 0; v < 4; v++) {
-            int mn = m0 + ty + 16 * u, i = i0 + tx + 16 * v;
+            int mn = m0 + ty + TY * u, i = i0 + tx + 16 * v;
             acc[u][v] = (mn < SS && i < G) ? out[(size_t)mn * G + i] : 0.0;
         }
     for (int p0 = 0; p0 < P; p0 += PKK) {
-        for (int e = threadIdx.x; e < PKK * PT; e += 256) {
-            int pr = e / PT, c = e % PT;
-            int p = p0 + pr;
-            double va = 0.0, vb = 0.0;
-            if (p < P) {
-                if (m0 + c < SS) va = tw[(size_t)pair_kh[p] * SS + m0 + c];
-                if (i0 + c < G) vb = B[(size_t)p * G + i0 + c];
-            }
-            sA[pr][c] = va;
-            sB[pr][c] = vb;
+        for (int e = threadIdx.x; e < PKK * PTM; e += blockDim.x) {
+            const int pr = e / PTM, c = e - pr * PTM;
+            const int p = p0 + pr;
+            sA[pr][c] = (p < P && m0 + c < SS) ? tw[(size_t)pair_kh[p] * SS + m0 + c] : 0.0;
+        }
+        for (int e = threadIdx.x; e < PKK * PT; e += blockDim.x) {
+            const int pr = e / PT, c = e % PT;
+            const int p = p0 + pr;
+            sB[pr][c] = (p < P && i0 + c < G) ? B[(size_t)p * G + i0 + c] : 0.0;
         }
         __syncthreads();
         const int lim = (P - p0) < PKK ? (P - p0) : PKK;
         for (int pr = 0; pr < lim; pr++) {
             double av[4], bv[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) av[u] = sA[pr][ty + 16 * u];
+            for (int u = 0; u < 4; u++) av[u] = sA[pr][ty + TY * u];
 #pragma unroll
             for (int v = 0; v < 4; v++) bv[v] = sB[pr][tx + 16 * v];
 #pragma unroll
@@ -1223,7 +1223,7 @@ k_project(const double *__restrict__ tensor, int K, int G, int S, const double *
     for (int u = 0; u < 4; u++)
 #pragma unroll
         for (int v = 0; v < 4; v++) {
-            int mn = m0 + ty + 16 * u, i = i0 + tx + 16 * v;
+            int mn = m0 + ty + TY * u, i = i0 + tx + 16 * v;
             if (mn < SS && i < G) out[(size_t)mn * G + i] = acc[u][v];
         }
 }
@@ -1231,8 +1231,12 @@ k_project(const double *__restrict__ tensor, int K, int G, int S, const double *
 void launch_project(const double *tensor, int N, int K, int G, int S, const double *tw, const int32_t *pair_kh,
                     double *results, cudaStream_t st) {
     if (N <= 0) return;
-    dim3 grid((G + PT - 1) / PT, (S * S + PT - 1) / PT, N);
-    k_project<<<grid, 256, 0, st>>>(tensor, K, G, S, tw, pair_kh, results);
+    // rows (surrogate pairs) per tile: the fewest tiles of at most PTM_MAX rows, split evenly (S=10: one tile of 100 rows)
+    const int SS = S * S;
+    const int tiles_m = (SS + PTM_MAX - 1) / PTM_MAX;
+    const int TY = std::max(1, ((SS + tiles_m - 1) / tiles_m + 3) / 4);
+    dim3 grid((G + PT - 1) / PT, (SS + 4 * TY - 1) / (4 * TY), N);
+    k_project<<<grid, 16 * TY, 0, st>>>(tensor, K, G, S, tw, pair_kh, results);
 }
 
 // =============================================================================================
