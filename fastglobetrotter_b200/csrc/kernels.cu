@@ -383,7 +383,7 @@ __device__ __forceinline__ int pairs_to_sample(int t1, int t2, double e, double 
     return Y < 0 ? 0 : Y;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_bin_sort(int rows_per_ind, const int32_t *__restrict__ row_off, const double *__restrict__ cstart,
            const double *__restrict__ cend, const int32_t *__restrict__ chap, const int32_t *__restrict__ donor_label,
            int n_donor_labels, double cutoff, int K, int mode, int nb, int W, const double *__restrict__ Etab,
@@ -405,23 +405,32 @@ k_bin_sort(int rows_per_ind, const int32_t *__restrict__ row_off, const double *
         chunk_ptr[p] = sorted + c0;
         if (ps_ptr) { ps_ptr[p] = ps + c0; pop_ptr[p] = pops + c0; }
     }
-    // phase 1: occupancy of (painting, coarse bin); first chunk of each run
-    for (int r = 0; r < rows_per_ind; r++) {
-        const int a = row_off[r0 + r], b = row_off[r0 + r + 1];
-        for (int i = a + threadIdx.x; i < b; i += blockDim.x) {
-            double pos = __dmul_rn(__dadd_rn(cstart[i], cend[i]), 0.5);
-            int bin = __double2int_rz(pos);
-            bin = bin < 0 ? 0 : (bin >= nb ? nb - 1 : bin);
-            atomicAdd(&cnt[r * nb + bin], 1);
-            bool is_first = (i == a);
-            if (!is_first) {
-                double pp = __dmul_rn(__dadd_rn(cstart[i - 1], cend[i - 1]), 0.5);
-                int pb = __double2int_rz(pp);
-                pb = pb < 0 ? 0 : (pb >= nb ? nb - 1 : pb);
-                is_first = pb != bin;
-            }
-            if (is_first) rf[r * nb + bin] = i;
+    // phase 1: occupancy of (painting, coarse bin); first chunk of each run.  The individual's chunks are one
+    // contiguous range; a thread finds the painting of its chunk by bisecting the row offsets.
+    const int c_end = row_off[r0 + rows_per_ind];
+    auto row_of = [&](int i) {
+        int lo = 0, hi = rows_per_ind - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (row_off[r0 + mid] <= i) lo = mid; else hi = mid - 1;
         }
+        return lo;
+    };
+    for (int i = c0 + threadIdx.x; i < c_end; i += blockDim.x) {
+        const int r = row_of(i);
+        const int a = row_off[r0 + r];
+        double pos = __dmul_rn(__dadd_rn(cstart[i], cend[i]), 0.5);
+        int bin = __double2int_rz(pos);
+        bin = bin < 0 ? 0 : (bin >= nb ? nb - 1 : bin);
+        atomicAdd(&cnt[r * nb + bin], 1);
+        bool is_first = (i == a);
+        if (!is_first) {
+            double pp = __dmul_rn(__dadd_rn(cstart[i - 1], cend[i - 1]), 0.5);
+            int pb = __double2int_rz(pp);
+            pb = pb < 0 ? 0 : (pb >= nb ? nb - 1 : pb);
+            is_first = pb != bin;
+        }
+        if (is_first) rf[r * nb + bin] = i;
     }
     __syncthreads();
     // phase 2: per bin, turn the per-painting counts into exclusive prefixes; t[bin] = total
@@ -435,33 +444,42 @@ k_bin_sort(int rows_per_ind, const int32_t *__restrict__ row_off, const double *
         t[bin] = s;
     }
     __syncthreads();
-    // phase 3: start_bin
-    if (threadIdx.x == 0) {
-        int s = 0;
-        for (int bin = 0; bin < nb; bin++) { first[bin] = s; s += t[bin]; }
+    // phase 3: start_bin = exclusive prefix of t (one warp, 32 bins per step)
+    if (threadIdx.x < 32) {
+        int carry = 0;
+        for (int b0 = 0; b0 < nb; b0 += 32) {
+            const int bin = b0 + (int)threadIdx.x;
+            const int v = bin < nb ? t[bin] : 0;
+            int x = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(kFull, x, o);
+                if ((int)threadIdx.x >= o) x += y;
+            }
+            if (bin < nb) first[bin] = carry + x - v;
+            carry += __shfl_sync(kFull, x, 31);
+        }
     }
     __syncthreads();
     // phase 4: stable placement + finished records
     int bad = 0;
-    for (int r = 0; r < rows_per_ind; r++) {
-        const int a = row_off[r0 + r], b = row_off[r0 + r + 1];
-        for (int i = a + threadIdx.x; i < b; i += blockDim.x) {
-            double s = cstart[i], e = cend[i];
-            double pos = __dmul_rn(__dadd_rn(s, e), 0.5);
-            int bin = __double2int_rz(pos);
-            bin = bin < 0 ? 0 : (bin >= nb ? nb - 1 : bin);
-            int dest = c0 + first[bin] + cnt[r * nb + bin] + (i - rf[r * nb + bin]);
-            double len = __dsub_rn(e, s);
-            int hap = chap[i];
-            int pop = (hap >= 1 && hap <= n_donor_labels) ? donor_label[hap - 1] : -9;
-            if (pop == -9) bad |= kErrMissingDonor;                 // reference C:517-522
-            if (mode == 1 && pop > K) bad |= kErrLabelRange;        // reference C:102-107
-            if (mode == 3 && (pop > K)) bad |= kErrLabelRange;      // (would index out of bounds in the reference)
-            Chunk c;
-            c.pos = pos; c.size = len; c.w = (len > cutoff) ? cutoff : len; c.pop = pop; c.hapid = hap;
-            sorted[dest] = c;
-            if (ps_ptr) { ps[dest] = make_double2(pos, len); pops[dest] = pop; }
-        }
+    for (int i = c0 + threadIdx.x; i < c_end; i += blockDim.x) {
+        const int r = row_of(i);
+        double s = cstart[i], e = cend[i];
+        double pos = __dmul_rn(__dadd_rn(s, e), 0.5);
+        int bin = __double2int_rz(pos);
+        bin = bin < 0 ? 0 : (bin >= nb ? nb - 1 : bin);
+        int dest = c0 + first[bin] + cnt[r * nb + bin] + (i - rf[r * nb + bin]);
+        double len = __dsub_rn(e, s);
+        int hap = chap[i];
+        int pop = (hap >= 1 && hap <= n_donor_labels) ? donor_label[hap - 1] : -9;
+        if (pop == -9) bad |= kErrMissingDonor;                 // reference C:517-522
+        if (mode == 1 && pop > K) bad |= kErrLabelRange;        // reference C:102-107
+        if (mode == 3 && (pop > K)) bad |= kErrLabelRange;      // (would index out of bounds in the reference)
+        Chunk c;
+        c.pos = pos; c.size = len; c.w = (len > cutoff) ? cutoff : len; c.pop = pop; c.hapid = hap;
+        sorted[dest] = c;
+        if (ps_ptr) { ps[dest] = make_double2(pos, len); pops[dest] = pop; }
     }
     if (bad) atomicOr(err, bad);
     // phase 5: pairs per row of the (j,k) sampling schedule
@@ -477,12 +495,25 @@ k_bin_sort(int rows_per_ind, const int32_t *__restrict__ row_off, const double *
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        long long s = 0;
+    if (threadIdx.x < 32) {                             // exclusive prefix over j of the row totals (one warp)
+        long long carry = 0;
         long long *ro = rowoff + (size_t)p * (nb + 1);
-        for (int j = 0; j < nb; j++) { ro[j] = s; s += yoff[((size_t)p * nb + j) * W + (W - 1)]; }
-        ro[nb] = s;
-        if (totals) totals[p] = s;
+        for (int j0 = 0; j0 < nb; j0 += 32) {
+            const int j = j0 + (int)threadIdx.x;
+            const long long v = j < nb ? (long long)yoff[((size_t)p * nb + j) * W + (W - 1)] : 0;
+            long long x = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long y = __shfl_up_sync(kFull, x, o);
+                if ((int)threadIdx.x >= o) x += y;
+            }
+            if (j < nb) ro[j] = carry + x - v;
+            carry += __shfl_sync(kFull, x, 31);
+        }
+        if (threadIdx.x == 0) {
+            ro[nb] = carry;
+            if (totals) totals[p] = carry;
+        }
     }
 }
 
@@ -492,7 +523,7 @@ void launch_bin_sort(int n_phys, int rows_per_ind, const int32_t *row_off, const
                      const double2 **ps_ptr, const int32_t **pop_ptr, int32_t *t,
                      int32_t *first, int32_t *yoff, long long *rowoff, int32_t *cntmat, int32_t *runfirst, int *err,
                      long long *totals, cudaStream_t st) {
-    k_bin_sort<<<n_phys, 256, 0, st>>>(rows_per_ind, row_off, cstart, cend, chap, donor_label, n_donor_labels, cutoff, K,
+    k_bin_sort<<<n_phys, 1024, 0, st>>>(rows_per_ind, row_off, cstart, cend, chap, donor_label, n_donor_labels, cutoff, K,
                                       mode, nb, W, Etab, divisor, sorted, n_sorted, chunk_ptr, ps_ptr, pop_ptr, t, first, yoff, rowoff, cntmat,
                                       runfirst, err, totals);
 }
