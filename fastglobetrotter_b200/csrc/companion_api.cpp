@@ -20,6 +20,7 @@
 #include <mutex>
 #include <string>
 #include <sys/stat.h>
+#include <unistd.h>
 #include <thread>
 #include <unordered_map>
 #include <vector>
@@ -317,6 +318,112 @@ std::string cache_key(const std::string &path, long long size, long long mt, int
     return path + buf;
 }
 
+// ---- optional on-disk cache of decoded paintings --------------------------------------------------
+// With FGT_PACK_CACHE_DIR set, every decoded samples file (and what the scan of the first file learnt) is also
+// written there as a binary file keyed by source path, size, mtime and recipient set; a later process reads it back
+// instead of inflating and tokenising the text.  Off by default: the reference library writes no files.
+const char *pack_dir() {
+    const char *d = getenv("FGT_PACK_CACHE_DIR");
+    return (d && *d) ? d : nullptr;
+}
+
+std::string pack_path(const char *dir, const std::string &key, const char *ext) {
+    unsigned long long h = 1469598103934665603ULL;
+    for (unsigned char c : key) { h ^= c; h *= 1099511628211ULL; }
+    char buf[64];
+    snprintf(buf, sizeof buf, "/%016llx.%s", h, ext);
+    return std::string(dir) + buf;
+}
+
+struct PackHdr {
+    char magic[8];
+    uint32_t key_len, label_bytes;
+    int32_t nsites, nsamples, ploidy, max_label;
+    uint64_t n_rec, n_labels;
+};
+
+bool write_all(FILE *f, const void *p, size_t n) { return n == 0 || fwrite(p, 1, n, f) == n; }
+bool read_all(FILE *f, void *p, size_t n) { return n == 0 || fread(p, 1, n, f) == n; }
+
+void disk_store(const char *dir, const std::string &key, const PackedFile &pf) {
+    const std::string path = pack_path(dir, key, "fgtpack"), tmp = path + ".tmp" + std::to_string((long long)getpid());
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) return;                                   // the cache is best effort: failures never reach the caller
+    PackHdr h{};
+    memcpy(h.magic, "FGTPACK1", 8);
+    h.key_len = (uint32_t)key.size(); h.label_bytes = (uint32_t)pf.label_bytes;
+    h.nsites = pf.nsites; h.nsamples = pf.nsamples; h.ploidy = pf.ploidy; h.max_label = pf.max_label;
+    h.n_rec = pf.rec_index.size();
+    h.n_labels = pf.label_bytes == 2 ? pf.lab16.size() : pf.lab32.size();
+    const void *lab = pf.label_bytes == 2 ? (const void *)pf.lab16.data() : (const void *)pf.lab32.data();
+    bool ok = write_all(f, &h, sizeof h) && write_all(f, key.data(), key.size()) &&
+              write_all(f, pf.rec_index.data(), pf.rec_index.size() * sizeof(int)) &&
+              write_all(f, lab, (size_t)h.n_labels * pf.label_bytes);
+    ok = (fclose(f) == 0) && ok;
+    if (!ok || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());
+}
+
+bool disk_load(const char *dir, const std::string &key, const std::string &src_path, PackedFile &pf) {
+    FILE *f = fopen(pack_path(dir, key, "fgtpack").c_str(), "rb");
+    if (!f) return false;
+    PackHdr h{};
+    bool ok = read_all(f, &h, sizeof h) && memcmp(h.magic, "FGTPACK1", 8) == 0 && h.key_len == key.size() &&
+              (h.label_bytes == 2 || h.label_bytes == 4) && h.n_rec < (1u << 28) && h.nsites > 0;
+    if (ok) {
+        std::string k(h.key_len, '\0');
+        ok = read_all(f, &k[0], k.size()) && k == key;     // the key holds path, size, mtime, ploidy, sites, recipients
+    }
+    if (ok) {
+        pf.rec_index.resize(h.n_rec);
+        ok = read_all(f, pf.rec_index.data(), h.n_rec * sizeof(int)) &&
+             h.n_labels == (uint64_t)h.n_rec * h.ploidy * h.nsamples * h.nsites;
+    }
+    if (ok) {
+        if (h.label_bytes == 2) { pf.lab16.resize(h.n_labels); ok = read_all(f, pf.lab16.data(), h.n_labels * 2); }
+        else { pf.lab32.resize(h.n_labels); ok = read_all(f, pf.lab32.data(), h.n_labels * 4); }
+        char extra;
+        ok = ok && fread(&extra, 1, 1, f) == 0;            // nothing may follow
+    }
+    fclose(f);
+    if (!ok) { pf = PackedFile(); return false; }
+    pf.label_bytes = (int)h.label_bytes; pf.nsites = h.nsites; pf.nsamples = h.nsamples; pf.ploidy = h.ploidy;
+    pf.max_label = h.max_label; pf.path = src_path;
+    return true;
+}
+
+void disk_store_meta(const char *dir, const std::string &key, const SamplesMeta &m) {
+    const std::string path = pack_path(dir, key, "fgtmeta"), tmp = path + ".tmp" + std::to_string((long long)getpid());
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) return;
+    const uint64_t hdr[4] = {0x315441544d544746ULL /* "FGTMETA1" */, key.size(), (uint64_t)m.rec_first_index.size(), (uint64_t)m.nsamples};
+    const long long cnt = m.count;
+    bool ok = write_all(f, hdr, sizeof hdr) && write_all(f, &cnt, sizeof cnt) && write_all(f, key.data(), key.size()) &&
+              write_all(f, m.rec_first_index.data(), m.rec_first_index.size() * sizeof(int));
+    ok = (fclose(f) == 0) && ok;
+    if (!ok || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());
+}
+
+bool disk_load_meta(const char *dir, const std::string &key, SamplesMeta &m) {
+    FILE *f = fopen(pack_path(dir, key, "fgtmeta").c_str(), "rb");
+    if (!f) return false;
+    uint64_t hdr[4];
+    long long cnt = 0;
+    bool ok = read_all(f, hdr, sizeof hdr) && hdr[0] == 0x315441544d544746ULL && hdr[1] == key.size() && hdr[2] < (1u << 28) &&
+              read_all(f, &cnt, sizeof cnt);
+    if (ok) {
+        std::string k(hdr[1], '\0');
+        ok = read_all(f, &k[0], k.size()) && k == key;
+    }
+    if (ok) {
+        m.rec_first_index.resize(hdr[2]);
+        ok = read_all(f, m.rec_first_index.data(), hdr[2] * sizeof(int));
+    }
+    fclose(f);
+    if (!ok) { m = SamplesMeta(); return false; }
+    m.nsamples = (int)hdr[3]; m.count = (long)cnt;
+    return true;
+}
+
 struct Loaded {                 // everything a .C call needs, decoded
     int num_chrom = 0, nsamples = 0;
     std::vector<RecombMap> maps;
@@ -349,12 +456,14 @@ Loaded load_inputs(int ploidy, char **samp_list, char **recom_list, int n_rec, c
             auto it = meta_cache.find(mk);
             if (it != meta_cache.end()) { meta = it->second; hit = true; }
         }
+        if (!hit && pack_dir() && disk_load_meta(pack_dir(), mk, meta) && (int)meta.rec_first_index.size() == n_rec) hit = true;
         if (!hit) {
             first_text = std::make_shared<SamplesText>();
             if (!inflate_file(sfiles[0], *first_text)) die("error opening %s\n", sfiles[0].c_str());
             meta = scan_first_file(*first_text, sfiles[0], ploidy, n_rec, rec_labels);
-            if (use_cache) { std::lock_guard<std::mutex> lk(mu); meta_cache[mk] = meta; }
+            if (pack_dir()) disk_store_meta(pack_dir(), mk, meta);
         }
+        if (use_cache) { std::lock_guard<std::mutex> lk(mu); meta_cache[mk] = meta; }
     }
     L.nsamples = meta.nsamples;
     L.rec_index = meta.rec_first_index;
@@ -383,6 +492,14 @@ Loaded load_inputs(int ploidy, char **samp_list, char **recom_list, int n_rec, c
             auto it = g_cache.find(keys[h]);
             if (it != g_cache.end()) { L.files[h] = it->second; cached[h] = 1; }
         }
+        if (!cached[h] && pack_dir()) {
+            auto pf = std::make_shared<PackedFile>();
+            if (disk_load(pack_dir(), keys[h], sfiles[h], *pf) && pf->nsamples == meta.nsamples && pf->rec_index == need) {
+                pf->fsize = sz; pf->mtime_ns = mt;
+                L.files[h] = pf; cached[h] = 1;
+                if (use_cache) { std::lock_guard<std::mutex> lk(g_cache_mu); g_cache[keys[h]] = pf; }
+            }
+        }
     }
     auto next_uncached = [&](int from) { for (int h = from; h < L.num_chrom; h++) if (!cached[h]) return h; return -1; };
     int cur = next_uncached(0);
@@ -398,6 +515,7 @@ Loaded load_inputs(int ploidy, char **samp_list, char **recom_list, int n_rec, c
         auto pf = std::make_shared<PackedFile>();
         pack_file(*cur_text, sfiles[cur], ploidy, meta.nsamples, (int)L.maps[cur].pos.size(), need, *pf);
         L.files[cur] = pf;
+        if (pack_dir()) disk_store(pack_dir(), keys[cur], *pf);
         if (use_cache) { std::lock_guard<std::mutex> lk(g_cache_mu); g_cache[keys[cur]] = pf; }
         cur_text.reset();
         if (nxt >= 0) cur_text = next.get();

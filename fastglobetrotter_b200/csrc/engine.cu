@@ -63,6 +63,7 @@ int Engine::set_option(const char *key, double v) {
     else if (k == "reuse_prep") opt.reuse_prep = iv;
     else if (k == "accum_impl") opt.accum_impl = iv;
     else if (k == "spec_rand") opt.spec_rand = iv;
+    else if (k == "copy_streams") opt.copy_streams = iv;
     else if (k == "eval_parts") opt.eval_parts = iv;
     else if (k == "batch_pairs") opt.batch_pairs = v;
     else if (k == "blocks") opt.blocks = iv;
@@ -86,6 +87,7 @@ double Engine::get_option(const char *key) {
     if (k == "reuse_prep") return opt.reuse_prep;
     if (k == "accum_impl") return opt.accum_impl;
     if (k == "spec_rand") return opt.spec_rand;
+    if (k == "copy_streams") return opt.copy_streams;
     if (k == "eval_parts") return opt.eval_parts;
     if (k == "batch_pairs") return opt.batch_pairs;
     if (k == "blocks") return opt.blocks;
@@ -110,6 +112,7 @@ int Engine::ensure_init() {
     if (!st_) CK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
     if (!st_prep_) CK(cudaStreamCreateWithFlags(&st_prep_, cudaStreamNonBlocking));
     if (!st_copy_) CK(cudaStreamCreateWithFlags(&st_copy_, cudaStreamNonBlocking));
+    if (!st_copy2_) CK(cudaStreamCreateWithFlags(&st_copy2_, cudaStreamNonBlocking));
     if (!st_aux_) CK(cudaStreamCreateWithFlags(&st_aux_, cudaStreamNonBlocking));
     if (!st_commit_) {
         int lo_p = 0, hi_p = 0;
@@ -850,13 +853,14 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
             void *buf = d_labels_.get(bytes_per_ind * n_phys);
             if (!buf) return FGT_ERR_CUDA;
             d_lab = buf;
-            if (labels_free) CK(cudaStreamWaitEvent(st_copy_, labels_free, 0));
+            if (labels_free) { CK(cudaStreamWaitEvent(st_copy_, labels_free, 0)); CK(cudaStreamWaitEvent(st_copy2_, labels_free, 0)); }
             for (int b = 0; b < n_blocks; b++) {
                 const int p0 = blk_lo(b), p1 = blk_lo(b + 1);
+                cudaStream_t cstream = (opt.copy_streams > 1 && (b & 1)) ? st_copy2_ : st_copy_;   // two DMA engines
                 CK(cudaMemcpyAsync((char *)buf + bytes_per_ind * p0, (const char *)c.labels + bytes_per_ind * p0,
-                                   bytes_per_ind * (p1 - p0), cudaMemcpyHostToDevice, st_copy_));
+                                   bytes_per_ind * (p1 - p0), cudaMemcpyHostToDevice, cstream));
                 copy_done[b] = new_event();
-                CK(cudaEventRecord(copy_done[b], st_copy_));
+                CK(cudaEventRecord(copy_done[b], cstream));
             }
             stx.h2d_bytes += (int64_t)(bytes_per_ind * n_phys);
         }

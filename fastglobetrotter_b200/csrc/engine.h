@@ -44,6 +44,7 @@ struct Options {
     int ranges = 8;         // accumulation launches per chromosome when the paintings stream in from the host
     int blocks = 0;         // blocks of individuals per chromosome in the copy/chunk/accumulate pipeline (0 = automatic)
     int eval_parts = 0;     // warps per (individual, coarse bin) in phase 1; 0 = automatic
+    int copy_streams = 1;   // 2 = alternate the label block copies between two streams (two DMA engines)
     int spec_rand = 1;      // generate the first batch's draws while the chunk/bin kernels run
     int accum_impl = 2;     // 2 = two-phase (evaluate once, ordered commit); 1 = single-phase slab warps     // one-shot: next packed call may reuse the chunk/bin tables of the previous one
 };
@@ -86,6 +87,7 @@ class Engine {
     bool inited_ = false;
     int init_rc_ = 0;
     cudaStream_t st_ = nullptr, st_prep_ = nullptr, st_copy_ = nullptr, st_commit_ = nullptr;
+    cudaStream_t st_copy2_ = nullptr;
     cudaStream_t st_aux_ = nullptr;   // small table uploads that must not queue behind the prep stream
     History private_hist_ = seeded_history(1);
     std::vector<uint32_t> level_tab_;

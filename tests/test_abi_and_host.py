@@ -148,3 +148,48 @@ def test_fatal_input_errors_exit_like_the_reference(lib, tmp_path):
     nofile = base % (ROOT, "b'Target1', b'Target2'", "/nonexistent/list.txt", data.recom_list)
     p = subprocess.run([sys.executable, "-c", nofile], capture_output=True, text=True)
     assert p.returncode == 1 and "error opening" in p.stdout
+
+
+def test_on_disk_pack_cache_round_trip(lib, tmp_path, monkeypatch):
+    """FGT_PACK_CACHE_DIR: decoded paintings are written as binary files and a later reader (no in-process cache,
+    even with the text gone stale in memory) gets the identical arrays without inflating; a changed source file,
+    a different recipient set or a damaged cache file fall back to parsing the text."""
+    spec = synth.SynthSpec(n_chrom=2, n_inds=3, n_snps=900, K=4, nsamples=3, n_extra_inds=2, rate=6e-7, name="pack")
+    data = synth.write_dataset(spec, str(tmp_path / "data"))
+    cache = tmp_path / "cache"
+    cache.mkdir()
+    monkeypatch.setenv("FGT_PACK_CACHE_DIR", str(cache))
+    lib.set_option("cache", 0)                       # take the per-process cache out of the picture
+    try:
+        first = _probe(lib, data)
+        packs = sorted(p.name for p in cache.iterdir())
+        assert sum(n.endswith(".fgtpack") for n in packs) == 2 and sum(n.endswith(".fgtmeta") for n in packs) == 1
+        assert not any(".tmp" in n for n in packs)
+        # served from disk: make the text unreadable as paintings but keep size and mtime, so only the cache can answer
+        import gzip
+        sfile = open(data.samples_list).read().split()[0]
+        st = os.stat(sfile)
+        raw = open(sfile, "rb").read()
+        open(sfile, "wb").write(b"\0" * len(raw))
+        os.utime(sfile, ns=(st.st_atime_ns, st.st_mtime_ns))
+        second = _probe(lib, data)
+        assert second[:5] == first[:5]
+        for a, b in zip(first[5], second[5]):
+            assert np.array_equal(a, b)
+        # restore the text with a new mtime: the stale cache entry is ignored and a fresh one is written
+        open(sfile, "wb").write(raw)
+        os.utime(sfile, ns=(st.st_atime_ns, st.st_mtime_ns + 5_000_000_000))
+        third = _probe(lib, data)
+        for a, b in zip(first[5], third[5]):
+            assert np.array_equal(a, b)
+        assert sum(p.name.endswith(".fgtpack") for p in cache.iterdir()) == 3
+        # a truncated cache file is rejected
+        for p in cache.iterdir():
+            if p.name.endswith(".fgtpack"):
+                b = p.read_bytes()
+                p.write_bytes(b[: len(b) // 2])
+        fourth = _probe(lib, data)
+        for a, b in zip(first[5], fourth[5]):
+            assert np.array_equal(a, b)
+    finally:
+        lib.set_option("cache", 1)
