@@ -63,6 +63,7 @@ int Engine::set_option(const char *key, double v) {
     else if (k == "reuse_prep") opt.reuse_prep = iv;
     else if (k == "accum_impl") opt.accum_impl = iv;
     else if (k == "spec_rand") opt.spec_rand = iv;
+    else if (k == "project_impl") opt.project_impl = iv;
     else if (k == "copy_streams") opt.copy_streams = iv;
     else if (k == "eval_parts") opt.eval_parts = iv;
     else if (k == "batch_pairs") opt.batch_pairs = v;
@@ -87,6 +88,7 @@ double Engine::get_option(const char *key) {
     if (k == "reuse_prep") return opt.reuse_prep;
     if (k == "accum_impl") return opt.accum_impl;
     if (k == "spec_rand") return opt.spec_rand;
+    if (k == "project_impl") return opt.project_impl;
     if (k == "copy_streams") return opt.copy_streams;
     if (k == "eval_parts") return opt.eval_parts;
     if (k == "batch_pairs") return opt.batch_pairs;
@@ -817,7 +819,7 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
             if (project_per_range && (pb.mode == 3 || h == Cn - 1) && !want_raw) {
                 // these individuals' tensors are final: project them now, off the tail of the call
                 span_begin(2, sc);
-                launch_project(tens_b, Nb, K, G, S, d_tw, d_pairkh, d_results + (size_t)b0 * S * S * G, sc);
+                (opt.project_impl == 1 ? launch_project_tensor : launch_project)(tens_b, Nb, K, G, S, d_tw, d_pairkh, d_results + (size_t)b0 * S * S * G, sc);
                 launches_ += 1;
                 span_end(sc);
             }
@@ -912,7 +914,7 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
         if (pb.mode == 3 && !(project_per_range && !want_raw)) {
             span_begin(2, sc);
             if (want_raw) { launch_expand_raw(d_tensor, N, K, G, d_raw + (size_t)h * N * K * K * G, sc); launches_++; }
-            launch_project(d_tensor, N, K, G, S, d_tw, d_pairkh, d_results, sc);
+            (opt.project_impl == 1 ? launch_project_tensor : launch_project)(d_tensor, N, K, G, S, d_tw, d_pairkh, d_results, sc);
             launches_ += 1;
             if (memset_tensor) CK(cudaMemsetAsync(d_tensor, 0, tens_elems * sizeof(double), sc));
             span_end(sc);
@@ -941,7 +943,7 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
     CK(cudaEventRecord(ev[1], sc));
     if (pb.mode == 1 && !(project_per_range && !want_raw)) {
         if (want_raw) { launch_expand_raw(d_tensor, N, K, G, d_raw, sc); launches_++; }
-        launch_project(d_tensor, N, K, G, S, d_tw, d_pairkh, d_results, sc);
+        (opt.project_impl == 1 ? launch_project_tensor : launch_project)(d_tensor, N, K, G, S, d_tw, d_pairkh, d_results, sc);
         launches_ += 1;
     }
     double *d_rs = d_rs_.as<double>((size_t)N * S * G), *d_ratio = d_ratio_.as<double>((size_t)N * S * S * G);

@@ -887,7 +887,7 @@ __global__ void __launch_bounds__(128, 8) k_eval_pairs(const EvalArgs a) {
         UpdateRec *reg = a.recs + seg * ns;
         const int slab0 = a.first_slab[d];
         const BinRef binB{chps + f2, chpop + f2};
-        int c[kMaxSlots] = {0, 0, 0, 0};
+        int c[kMaxSlots] = {};
         for (int base = 0; base < Y; base += 64) {
             const int q0 = base + lane, q1 = base + 32 + lane;
             const uint2 r0 = nr0, r1 = nr1;
@@ -1257,6 +1257,77 @@ k_project(const double *__restrict__ tensor, int K, int G, int S, const double *
             int mn = m0 + ty + TY * u, i = i0 + tx + 16 * v;
             if (mn < SS && i < G) out[(size_t)mn * G + i] = acc[u][v];
         }
+}
+
+// Tensor-core variant (opt-in, `project_impl` = 1): the same contraction on the FP64 tensor pipe
+// (mma.sync m8n8k4, SASS DMMA).  Each product is fused into the running sum, so `results` -- and only `results`,
+// the raw tensors are untouched -- agree with the reference to ~1e-14 relative instead of bit for bit; north_star
+// allows 1e-12 on the curves.  Worth it when K and S are large: the contraction grows like S^2 K^2 G per individual
+// and chromosome (4.5 GFLOP at K=150, S=20) and then dwarfs the accumulation.
+constexpr int DM = 64, DN = 64, DK = 16, DPAD = 8;     // block tile (surrogate pairs x bins), k-slice; row stride 72 doubles
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(128)
+k_project_dmma(const double *__restrict__ tensor, int K, int G, int S, const double *__restrict__ tw,
+               const int32_t *__restrict__ pair_kh, double *__restrict__ results) {
+    const int n = blockIdx.z;
+    const int SS = S * S, P = K * (K + 1) / 2;
+    const int g0 = blockIdx.x * DN, m0 = blockIdx.y * DM;
+    const double *B = tensor + (size_t)n * P * G;
+    double *out = results + (size_t)n * SS * G;
+    __shared__ double sA[DK][DM + DPAD];      // [pair][surrogate pair]
+    __shared__ double sB[DK][DN + DPAD];      // [pair][bin]
+    const int lane = lane_id(), w = warp_id();
+    const int wm = (w >> 1) * 32, wn = (w & 1) * 32;            // this warp's 32 x 32 corner of the block tile
+    const int grp = lane >> 2, tig = lane & 3;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int mn = m0 + wm + 8 * i + grp, g = g0 + wn + 8 * j + 2 * tig;
+            acc[i][j][0] = (mn < SS && g < G) ? out[(size_t)mn * G + g] : 0.0;
+            acc[i][j][1] = (mn < SS && g + 1 < G) ? out[(size_t)mn * G + g + 1] : 0.0;
+        }
+    for (int p0 = 0; p0 < P; p0 += DK) {
+        for (int e = threadIdx.x; e < DK * DM; e += 128) {
+            const int pr = e / DM, c = e % DM;
+            const int p = p0 + pr;
+            sA[pr][c] = (p < P && m0 + c < SS) ? tw[(size_t)pair_kh[p] * SS + m0 + c] : 0.0;
+            sB[pr][c] = (p < P && g0 + c < G) ? B[(size_t)p * G + g0 + c] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < DK; kk += 4) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[i] = sA[kk + tig][wm + 8 * i + grp];     // A fragment: row grp, column tig
+#pragma unroll
+            for (int j = 0; j < 4; j++) b[j] = sB[kk + tig][wn + 8 * j + grp];     // B fragment: row tig, column grp
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int mn = m0 + wm + 8 * i + grp, g = g0 + wn + 8 * j + 2 * tig;
+            if (mn < SS && g < G) out[(size_t)mn * G + g] = acc[i][j][0];
+            if (mn < SS && g + 1 < G) out[(size_t)mn * G + g + 1] = acc[i][j][1];
+        }
+}
+
+void launch_project_tensor(const double *tensor, int N, int K, int G, int S, const double *tw, const int32_t *pair_kh,
+                           double *results, cudaStream_t st) {
+    if (N <= 0) return;
+    dim3 grid((G + DN - 1) / DN, (S * S + DM - 1) / DM, N);
+    k_project_dmma<<<grid, 128, 0, st>>>(tensor, K, G, S, tw, pair_kh, results);
 }
 
 void launch_project(const double *tensor, int N, int K, int G, int S, const double *tw, const int32_t *pair_kh,

@@ -119,6 +119,8 @@ void launch_rand_fill(const uint32_t *base_hist, const uint32_t *level_tab, uint
 void launch_accum_strict(const AccumArgs &a, cudaStream_t st);
 void launch_project(const double *tensor, int N, int K, int G, int S, const double *tw, const int32_t *pair_kh,
                     double *results, cudaStream_t st);
+void launch_project_tensor(const double *tensor, int N, int K, int G, int S, const double *tw, const int32_t *pair_kh,
+                           double *results, cudaStream_t st);   // FP64 tensor cores; results to ~1e-14, not bit-exact
 void launch_normalise(double *results, int N, int S, int G, int N_total, double *rsbuf, double *ratio, cudaStream_t st);
 void launch_mean_accum(const double *ratio, int N, int S, int G, double *means, cudaStream_t st);
 void launch_outer_weights(const double *w, int S, int K, double *out, cudaStream_t st);

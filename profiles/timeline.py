@@ -8,6 +8,8 @@ from fastglobetrotter_b200.synth_torch import make_chromosome_device
 lib = PackedCompanion(fbuild.build()); lib.set_option("rand_libc", 0)
 dev = torch.device("cuda", 0)
 N, L, K, G, S = 100, 100_000, 30, 500, 10
+N, L, K, G, S = [int(os.environ.get(k, v)) for k, v in (('N', N), ('L', L), ('K', K), ('G', G), ('S', S))]
+MODE = int(os.environ.get('MODE', 1))
 spec = synth.SynthSpec(n_chrom=1, n_inds=N, n_snps=L, K=K, nsamples=10, seed=20261021)
 pos, rate, lab = make_chromosome_device(spec, 0, dev)
 chrom = [{"pos": pos, "rate": rate, "labels": (lab.data_ptr(), 2, lab.shape[0])}]
@@ -21,5 +23,5 @@ dl = spec.donor_label_vec(); tw = np.random.default_rng(0).random(K * K * S * S)
 for rep in range(4):
     lib.set_option("verbose", 1 if rep == 3 else 0)
     lib.srand(11)
-    m, _, st = lib.data_read_packed(1, 2, 10, chrom, ids, 0.1, G, 10, K, dl, 0.0, 1.0, S, tw)
+    m, _, st = lib.data_read_packed(MODE, 2, 10, chrom, ids, 0.1, G, 10, K, dl, 0.0, 1.0, S, tw)
 print({k: (round(v, 3) if isinstance(v, float) else v) for k, v in st.items()})

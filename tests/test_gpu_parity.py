@@ -560,3 +560,32 @@ def test_odd_row_lengths_and_label_block_offsets(lib, oracle):
         n_o, ev = oracle.data_read_null_packed(2, 3, chrom, np.array([3, 1, 4]), 0.1, 60, 10, K, dl, 0.0, 1.0)
         n_g, st = lib.data_read_null_packed(2, 3, chrom, np.array([3, 1, 4]), 0.1, 60, 10, K, dl, 0.0, 1.0)
         assert st["pairs"] == ev and np.array_equal(n_g, n_o), L
+
+
+@pytest.mark.parametrize("mode", [1, 3])
+def test_tensor_core_projection_within_tolerance(lib, oracle, small, mode):
+    """project_impl=1 runs the surrogate projection on the FP64 tensor pipe (DMMA): raw tensors stay bit-exact, the
+    curves agree with the oracle to 1e-12 relative (north_star's tolerance for normalised curves), not bit for bit."""
+    sp = small.spec
+    chrom = packed_chrom(small)
+    dl = small.donor_label_vec if mode == 1 else np.where(small.donor_label_vec == 0, 1, small.donor_label_vec)
+    K, S, G, bw, gs = sp.K, 5, 130, 0.1, 10
+    tw = np.random.default_rng(8).random(K * K * S * S)
+    ids = ind_id_matrix(sp.n_inds, sp.n_chrom)
+    oracle.srand(31)
+    m_o, raw_o, _ = oracle.data_read_packed(mode, sp.ploidy, sp.nsamples, chrom, ids, bw, G, gs, K, dl, 0.0, 1.0, S, tw, want_raw=True)
+    lib.set_option("rand_libc", 0)
+    lib.set_option("project_impl", 1)
+    try:
+        for want_raw in (True, False):
+            lib.srand(31)
+            m_g, raw_g, _ = lib.data_read_packed(mode, sp.ploidy, sp.nsamples, chrom, ids, bw, G, gs, K, dl, 0.0, 1.0, S, tw,
+                                                 want_raw=want_raw)
+            if want_raw:
+                assert np.array_equal(raw_g, raw_o)
+            ok = np.isfinite(m_o)
+            assert np.array_equal(np.isfinite(m_g), ok)
+            rel = np.abs(m_g[ok] - m_o[ok]) / np.maximum(np.abs(m_o[ok]), 1e-300)
+            assert rel.max() <= 1e-12, rel.max()
+    finally:
+        lib.set_option("project_impl", 0)
