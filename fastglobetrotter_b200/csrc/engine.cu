@@ -9,6 +9,7 @@
 #include <chrono>
 #include <cstring>
 #include <cstdlib>
+#include <future>
 
 namespace fgt {
 
@@ -557,6 +558,9 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
     std::vector<SlabDesc> slabs;
     int impl = opt.accum_impl;
     double *d_tensor = nullptr, *d_results = nullptr, *d_tw = nullptr, *d_raw = nullptr;
+    size_t tw_bytes = 0;
+    bool tw_pending = false;
+    std::future<void> tw_stage;
     int32_t *d_pairkh = nullptr, *d_slabof = nullptr, *d_firstslab = nullptr, *d_slabw = nullptr, *d_slabb0 = nullptr;
     SlabDesc *d_slabs = nullptr;
     long long *d_pairbase = nullptr;
@@ -573,7 +577,25 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
         d_pairkh = d_pairkh_.as<int32_t>(P);
         if (!d_tensor || !d_results || !d_tw || !d_pairkh) return FGT_ERR_CUDA;
         CK(cudaMemsetAsync(d_results, 0, (size_t)N * S * S * G * sizeof(double), st_));
-        CK(cudaMemcpyAsync(d_tw, pb.temp_weights, (size_t)K * K * S * S * sizeof(double), cudaMemcpyHostToDevice, st_));
+        // The surrogate weights are only needed by the projection.  A large table (72 MB at K=150, S=20) is staged into
+        // pinned memory by a helper thread and uploaded just before the first projection, instead of holding the host
+        // (and with it the whole pipeline) for a pageable copy at the start of the call.
+        tw_bytes = (size_t)K * K * S * S * sizeof(double);
+        if (tw_bytes >= (4u << 20)) {
+            if (pin_tw_cap_ < tw_bytes) {
+                if (pin_tw_) cudaFreeHost(pin_tw_);
+                pin_tw_ = nullptr; pin_tw_cap_ = 0;
+                if (cudaHostAlloc((void **)&pin_tw_, tw_bytes, cudaHostAllocDefault) != cudaSuccess) return FGT_ERR_CUDA;
+                pin_tw_cap_ = tw_bytes;
+            }
+            double *dst = pin_tw_;
+            const double *src = pb.temp_weights;
+            const size_t nbytes = tw_bytes;
+            tw_stage = std::async(std::launch::async, [dst, src, nbytes]() { std::memcpy(dst, src, nbytes); });
+            tw_pending = true;
+        } else {
+            CK(cudaMemcpyAsync(d_tw, pb.temp_weights, tw_bytes, cudaMemcpyHostToDevice, st_));
+        }
         stx.h2d_bytes += (int64_t)K * K * S * S * 8;
         std::vector<int32_t> pairkh(P);
         size_t q = 0;
@@ -819,6 +841,7 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
             if (project_per_range && (pb.mode == 3 || h == Cn - 1) && !want_raw) {
                 // these individuals' tensors are final: project them now, off the tail of the call
                 span_begin(2, sc);
+                if (tw_pending) { tw_stage.get(); CK(cudaMemcpyAsync(d_tw, pin_tw_, tw_bytes, cudaMemcpyHostToDevice, sc)); tw_pending = false; }
                 (opt.project_impl == 1 ? launch_project_tensor : launch_project)(tens_b, Nb, K, G, S, d_tw, d_pairkh, d_results + (size_t)b0 * S * S * G, sc);
                 launches_ += 1;
                 span_end(sc);
@@ -914,6 +937,7 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
         if (pb.mode == 3 && !(project_per_range && !want_raw)) {
             span_begin(2, sc);
             if (want_raw) { launch_expand_raw(d_tensor, N, K, G, d_raw + (size_t)h * N * K * K * G, sc); launches_++; }
+            if (tw_pending) { tw_stage.get(); CK(cudaMemcpyAsync(d_tw, pin_tw_, tw_bytes, cudaMemcpyHostToDevice, sc)); tw_pending = false; }
             (opt.project_impl == 1 ? launch_project_tensor : launch_project)(d_tensor, N, K, G, S, d_tw, d_pairkh, d_results, sc);
             launches_ += 1;
             if (memset_tensor) CK(cudaMemsetAsync(d_tensor, 0, tens_elems * sizeof(double), sc));
@@ -943,6 +967,7 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
     CK(cudaEventRecord(ev[1], sc));
     if (pb.mode == 1 && !(project_per_range && !want_raw)) {
         if (want_raw) { launch_expand_raw(d_tensor, N, K, G, d_raw, sc); launches_++; }
+        if (tw_pending) { tw_stage.get(); CK(cudaMemcpyAsync(d_tw, pin_tw_, tw_bytes, cudaMemcpyHostToDevice, sc)); tw_pending = false; }
         (opt.project_impl == 1 ? launch_project_tensor : launch_project)(d_tensor, N, K, G, S, d_tw, d_pairkh, d_results, sc);
         launches_ += 1;
     }

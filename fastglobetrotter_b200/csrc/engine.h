@@ -106,6 +106,8 @@ class Engine {
     double mem_budget_bytes_ = 0;
     long long last_shape_sig_ = -1;
     long long last_first_batch_threads_ = 0;   // generator runs the previous call's first batch used (speculation size)
+    double *pin_tw_ = nullptr;        // pinned staging of a large surrogate-weight table
+    size_t pin_tw_cap_ = 0;
     double *pin_tab_ = nullptr;       // pinned staging of a chromosome's cM prefix / increments / exp table
     size_t pin_tab_cap_ = 0;
     cudaEvent_t tab_ready_ = nullptr;
