@@ -809,6 +809,13 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
                 ea.pair_base = pbase; ea.phys_of = pphys;
                 ea.N = Nb; ea.K = K; ea.G = G; ea.grid_start = pb.grid_start; ea.mode = pb.mode; ea.n_slots = plan.n_slots;
                 ea.bw = pb.binwidth; ea.half_bw = pb.binwidth / 2.0; ea.cutoff = pb.gridweight_max_cutoff;
+                {
+                    uint64_t bits;
+                    std::memcpy(&bits, &pb.binwidth, sizeof bits);
+                    const bool all_ones = (bits & 0xFFFFFFFFFFFFFULL) == 0xFFFFFFFFFFFFFULL;
+                    const bool normal = std::isnormal(pb.binwidth) && pb.binwidth > 1e-100 && pb.binwidth < 1e100;
+                    ea.inv_bw = (!all_ones && normal) ? 1.0 / pb.binwidth : 0.0;
+                }
                 ea.slab_of = d_slabof; ea.first_slab = d_firstslab; ea.slab_w = d_slabw; ea.slab_b0 = d_slabb0;
                 ea.slab_width = plan.slab_width;
                 ea.slab_magic = plan.slab_width > 1 ? (uint32_t)(((1ULL << 32) + plan.slab_width - 1) / plan.slab_width) : 0u;
