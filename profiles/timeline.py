@@ -19,7 +19,7 @@ if os.environ.get("HOST"):
 for k, v in [kv.split("=") for kv in os.environ.get("OPTS", "").split(",") if kv]:
     lib.set_option(k, float(v))
 torch.cuda.synchronize()
-dl = spec.donor_label_vec(); tw = np.random.default_rng(0).random(K * K * S * S); ids = np.arange(N).astype(np.int32)
+dl = spec.donor_label_vec(); tw = lib.temp_weights_for_data_read(K, S, synth.random_weights(K, S)); ids = np.arange(N).astype(np.int32)
 for rep in range(4):
     lib.set_option("verbose", 1 if rep == 3 else 0)
     lib.srand(11)
