@@ -589,3 +589,38 @@ def test_tensor_core_projection_within_tolerance(lib, oracle, small, mode):
             assert rel.max() <= 1e-12, rel.max()
     finally:
         lib.set_option("project_impl", 0)
+
+
+def test_surrogate_counts_and_kernel_variants(lib, oracle, small):
+    """projection tiles for many surrogate counts (S*S = 1 ... 400: one partial tile up to four full ones), phase 1
+    with 1/2/3/8 warps per (individual, bin) row, draws generated speculatively or not across repeated calls of one
+    shape: all bit-identical to the oracle."""
+    sp = small.spec
+    chrom, dl = packed_chrom(small), small.donor_label_vec
+    K, G, bw, gs = sp.K, 70, 0.1, 10
+    ids = bootstrap_ids(sp.n_inds, sp.n_chrom, 5)
+    lib.set_option("rand_libc", 0)
+    for S in (1, 7, 10, 11, 20):
+        tw = np.random.default_rng(S).random(K * K * S * S)
+        oracle.srand(77)
+        m_o, _, _ = oracle.data_read_packed(1, sp.ploidy, sp.nsamples, chrom, ids, bw, G, gs, K, dl, 0.0, 1.0, S, tw)
+        lib.srand(77)
+        m_g, _, _ = lib.data_read_packed(1, sp.ploidy, sp.nsamples, chrom, ids, bw, G, gs, K, dl, 0.0, 1.0, S, tw)
+        assert np.array_equal(m_g, m_o, equal_nan=True), S
+    S = 3
+    tw = np.random.default_rng(3).random(K * K * S * S)
+    oracle.srand(78)
+    m_o, raw_o, _ = oracle.data_read_packed(1, sp.ploidy, sp.nsamples, chrom, ids, bw, G, gs, K, dl, 0.0, 1.0, S, tw, want_raw=True)
+    try:
+        for parts in (1, 2, 3, 8):
+            for spec in (0, 1):
+                lib.set_option("eval_parts", parts)
+                lib.set_option("spec_rand", spec)
+                for rep in range(3):                     # the second and third call of a shape may use speculative draws
+                    lib.srand(78)
+                    m_g, raw_g, _ = lib.data_read_packed(1, sp.ploidy, sp.nsamples, chrom, ids, bw, G, gs, K, dl, 0.0, 1.0, S, tw,
+                                                         want_raw=True)
+                    assert np.array_equal(raw_g, raw_o) and np.array_equal(m_g, m_o), (parts, spec, rep)
+    finally:
+        lib.set_option("eval_parts", 0)
+        lib.set_option("spec_rand", 1)
