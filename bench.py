@@ -247,6 +247,8 @@ def run_ours(args):
             "clocks": clocks,
             "means_checksum": float(np.nansum(means)),
         }
+        if world == 1:
+            out["other_paths"] = other_paths(lib, chrom_dev, common, tail, S, tw, N, dl, K, G, W)
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(sample_inds=args.cpu_sample_inds, procs=1, steps=3)
             out["file_e2e"] = file_e2e(lib)
@@ -321,6 +323,36 @@ def cpu_baseline(sample_inds=12, procs=1, steps=1):
             "sample": f"{procs} process(es) x {steps} data_read call(s) over {sample_inds} individuals each of the same "
                       f"workload (text .gz inputs, parse included); {pairs} pairs in {busy:.2f} s (wall {wall:.2f} s)",
             "pairs": pairs, "seconds": busy}
+
+
+def other_paths(lib, chrom_dev, common, tail, S, tw, N, dl, K, G, W, steps=3, null_inds=40):
+    """the two other entry points of the path on the same device-resident synthetic paintings (outside the timed region of
+    the headline): data_read_mode3 (window +1, Y/8, no target-label skip, projection per chromosome) in the headline's
+    unit, and data_read_null (exhaustive chunk x chunk across the first `null_inds` individuals) in chunk-pair
+    evaluations per second."""
+    import torch
+    res = {}
+    m3 = (3,) + tuple(common[1:])
+    dl3 = np.where(dl == 0, 1, dl).astype(np.int32)          # mode 3 never sees the target population label
+    tail3 = tail[:5] + (dl3,) + tail[6:]
+    lib.data_read_packed(*m3, chrom_dev, *tail3, S, tw)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    pairs = 0
+    for _ in range(steps):
+        _, _, st = lib.data_read_packed(*m3, chrom_dev, *tail3, S, tw)
+        pairs += st["pairs"]
+    dt = time.perf_counter() - t0
+    res["data_read_mode3"] = {"value": pairs / dt, "unit": UNIT, "ms_per_step": dt / steps * 1e3, "pairs_per_step": pairs / steps}
+    rows = np.arange(min(null_inds, N), dtype=np.int32)
+    lib.data_read_null_packed(W["ploidy"], W["nsamples"], chrom_dev, rows, W["bw"], G, W["grid_start"], K, dl, W["weight_min"], W["cutoff"])
+    t0 = time.perf_counter()
+    _, st = lib.data_read_null_packed(W["ploidy"], W["nsamples"], chrom_dev, rows, W["bw"], G, W["grid_start"], K, dl, W["weight_min"],
+                                      W["cutoff"])
+    dt = time.perf_counter() - t0
+    res["data_read_null"] = {"value": st["pairs"] / dt, "unit": "chunk-pair evaluations/s", "ms": dt * 1e3, "individuals": int(rows.size),
+                             "pair_evaluations": st["pairs"]}
+    return res
 
 
 def file_e2e(lib, n_inds=24):
