@@ -624,3 +624,27 @@ def test_surrogate_counts_and_kernel_variants(lib, oracle, small):
     finally:
         lib.set_option("eval_parts", 0)
         lib.set_option("spec_rand", 1)
+
+
+@pytest.mark.parametrize("mode", [1, 3])
+def test_twenty_two_chromosomes_bootstrap(lib, oracle, mode):
+    """the autosome count of configs 3-5: 22 chromosomes of different lengths, a chromosome-bootstrap id matrix (R:2058),
+    host-resident paintings flowing through the block pipeline; raw tensors and curves bit-identical to the oracle."""
+    K, S, G = 6, 3, 120
+    spec = synth.SynthSpec(n_chrom=22, n_inds=5, ploidy=2, nsamples=3, n_snps=1800, K=K, rate=9e-7, seed=22)
+    chrom = []
+    for h in range(spec.n_chrom):
+        pos, rate, labels = synth.make_chromosome(spec, h)
+        keep = 1800 - 60 * h                                  # shorter and shorter chromosomes
+        chrom.append({"pos": pos[:keep].copy(), "rate": rate[:keep].copy(), "labels": np.ascontiguousarray(labels[:, :keep])})
+    dl = spec.donor_label_vec()
+    if mode == 3:
+        dl = np.where(dl == 0, 1, dl)
+    tw = np.random.default_rng(22).random(K * K * S * S)
+    ids = bootstrap_ids(spec.n_inds, spec.n_chrom, 9)
+    _run_both(lib, oracle, mode, 2, 3, chrom, ids, 0.1, G, 10, K, dl, 0.0, 1.0, S, tw, seed=220 + mode)
+    lib.set_option("blocks", 3)
+    try:
+        _run_both(lib, oracle, mode, 2, 3, chrom, ids, 0.1, G, 10, K, dl, 0.0, 1.0, S, tw, seed=230 + mode)
+    finally:
+        lib.set_option("blocks", 0)
