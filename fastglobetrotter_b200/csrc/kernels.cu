@@ -745,11 +745,14 @@ void launch_accum_strict(const AccumArgs &a, cudaStream_t st) {
 // =============================================================================================
 // 4b. Two-phase strict accumulation.
 // =============================================================================================
-__device__ __forceinline__ unsigned fastmod_u32(unsigned a, unsigned d, double inv_d) {
-    // a < 2^31: trunc(a * RN(1/d)) is floor(a/d) or, for exact multiples only, one less
-    unsigned q = __double2uint_rz(__dmul_rn((double)a, inv_d));
-    unsigned r = a - q * d;
-    return r >= d ? r - d : r;
+// a % d for a < 2^31 (a rand() draw) and small d: with M = floor((2^32 - 1) / d) + 1 >= 2^32 / d the estimate
+// q = floor(a * M / 2^32) is floor(a / d) or one more (the excess a * (M * d - 2^32) / (d * 2^32) is below 1/2), so one
+// correction of a negative remainder makes it exact.  M == 0 encodes d == 1.
+__device__ __forceinline__ unsigned mod_magic(unsigned d) { return d > 1 ? 0xFFFFFFFFu / d + 1u : 0u; }
+__device__ __forceinline__ unsigned fastmod_u32(unsigned a, unsigned d, unsigned magic) {
+    const unsigned q = __umulhi(a, magic);
+    const int r = (int)(a - q * d);
+    return magic ? (unsigned)(r < 0 ? r + (int)d : r) : 0u;
 }
 
 // One 256-bit load per chunk record (LDG.E.256): a random gather of a 32-byte record then costs one L1
@@ -782,7 +785,7 @@ __device__ __forceinline__ PairChunk ldg_pair_chunk(const double2 *ps, const int
     return c;
 }
 
-__device__ __forceinline__ PairEval eval_pair(bool in_range, uint2 r, int t1, double inv1, int t2, double inv2,
+__device__ __forceinline__ PairEval eval_pair(bool in_range, uint2 r, int t1, unsigned inv1, int t2, unsigned inv2,
                                               const BinRef binA, const BinRef binB, const EvalArgs &a, int slab0, int &bad) {
     PairEval o;
     o.cell = -1; o.local = 0; o.slot = -1; o.val = 0.0;
@@ -812,20 +815,20 @@ __device__ __forceinline__ PairEval eval_pair(bool in_range, uint2 r, int t1, do
     else ok = false;
     const int bb = bfull - a.grid_start;
     const double mind = __dadd_rn(__dmul_rn(A.size, 0.5), __dmul_rn(B.size, 0.5));
-    if (ok && bb >= 0 && bb < a.G && dist >= mind) {
+    if (ok && (unsigned)bb < (unsigned)a.G && dist >= mind) {
         const int l1 = A.pop - 1, l2 = B.pop - 1;
         const int lo_l = l1 < l2 ? l1 : l2, hi_l = l1 < l2 ? l2 : l1;
         const int row = tri_row(lo_l, hi_l, a.K);
         const int slab = a.slab_magic ? (int)__umulhi((unsigned)bb, a.slab_magic) : bb;   // bb / slab_width (exact: both < 2^16; 0 = width 1)
         const int slot = slab - slab0;
-        if (slot < 0 || slot >= a.n_slots) { bad |= kErrInternal; return o; }
+        if ((unsigned)slot >= (unsigned)a.n_slots) { bad |= kErrInternal; return o; }
         o.cell = row * a.G + bb;
         const int sb0 = slab * a.slab_width;
         const int sw = min(a.slab_width, a.G - sb0);                          // the last slab may be narrower
         o.local = row * sw + (bb - sb0);
         o.slot = slot;
         // gridweight = min(size, cutoff), as stored by the chunk builder (reference C:527)
-        o.val = __dmul_rn(A.size > a.cutoff ? a.cutoff : A.size, B.size > a.cutoff ? a.cutoff : B.size);
+        o.val = __dmul_rn(fmin(A.size, a.cutoff), fmin(B.size, a.cutoff));     // sizes are never NaN: fmin == (size > cutoff ? cutoff : size)
     }
     return o;
 }
@@ -851,7 +854,7 @@ __global__ void __launch_bounds__(128, 8) k_eval_pairs(const EvalArgs a) {
     const int32_t *chpop = cp.pop_ptr[phys];
     const long long row_pair0 = a.pair_base[n] + cp.rowoff[(size_t)phys * (nb + 1) + j];
     const int f1 = F[j];
-    const double inv1 = __ddiv_rn(1.0, (double)t1);
+    const unsigned inv1 = mod_magic((unsigned)t1);
     const int ns = a.n_slots;
     const BinRef binA{chps + f1, chpop + f1};
     int dmax = W - 1;
@@ -889,7 +892,7 @@ __global__ void __launch_bounds__(128, 8) k_eval_pairs(const EvalArgs a) {
         if (Y <= 0) continue;
         const int k = j + d;
         const int t2 = T[k], f2 = F[k];
-        const double inv2 = __ddiv_rn(1.0, (double)t2);
+        const unsigned inv2 = mod_magic((unsigned)t2);
         const long long seg = row_pair0 + y0;
         UpdateRec *reg = a.recs + seg * ns;
         const int slab0 = a.first_slab[d];
