@@ -64,6 +64,8 @@ int Engine::set_option(const char *key, double v) {
     else if (k == "reuse_prep") opt.reuse_prep = iv;
     else if (k == "accum_impl") opt.accum_impl = iv;
     else if (k == "spec_rand") opt.spec_rand = iv;
+    else if (k == "null_world") opt.null_world = std::max(1, iv);
+    else if (k == "null_rank") opt.null_rank = std::max(0, iv);
     else if (k == "project_impl") opt.project_impl = iv;
     else if (k == "copy_streams") opt.copy_streams = iv;
     else if (k == "eval_parts") opt.eval_parts = iv;
@@ -89,6 +91,8 @@ double Engine::get_option(const char *key) {
     if (k == "reuse_prep") return opt.reuse_prep;
     if (k == "accum_impl") return opt.accum_impl;
     if (k == "spec_rand") return opt.spec_rand;
+    if (k == "null_world") return opt.null_world;
+    if (k == "null_rank") return opt.null_rank;
     if (k == "project_impl") return opt.project_impl;
     if (k == "copy_streams") return opt.copy_streams;
     if (k == "eval_parts") return opt.eval_parts;
@@ -1083,7 +1087,20 @@ int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_ro
     CK(cudaMemcpyAsync(d_rowmap, rowmap.data(), n_haps * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
     double *d_out = d_tensor_.as<double>((size_t)K * K * G);
     if (!d_out) return FGT_ERR_CUDA;
-    CK(cudaMemcpyAsync(d_out, out, (size_t)K * K * G * sizeof(double), cudaMemcpyHostToDevice, st_));
+    std::vector<double> own_init;
+    const double *init_src = out;
+    if (opt.null_world > 1) {
+        // sharded run: this rank returns only the label pairs it owns (continuing from the caller's values there), zeros
+        // elsewhere, so that the ranks' outputs have disjoint supports and their sum is exact
+        own_init.assign(out, out + (size_t)K * K * G);
+        for (int la = 0; la < K; la++)
+            for (int lb = 0; lb < K; lb++)
+                if ((la * 31 + lb * 17) % opt.null_world != opt.null_rank)
+                    std::fill(own_init.begin() + ((size_t)la * K + lb) * G, own_init.begin() + ((size_t)la * K + lb + 1) * G, 0.0);
+        init_src = own_init.data();
+    }
+    CK(cudaMemcpyAsync(d_out, init_src, (size_t)K * K * G * sizeof(double), cudaMemcpyHostToDevice, st_));
+    if (opt.null_world > 1) CK(cudaStreamSynchronize(st_));      // own_init is a local
     CK(cudaEventRecord(e1, st_));
     ChromState cs;
     long long evals = 0;
@@ -1111,6 +1128,10 @@ int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_ro
                 for (int lb = 0; lb < K; lb++) {
                     const double ca = cnt_mean[la], cb = cnt_mean[lb];
                     if (ca <= 0 || cb <= 0) continue;
+                    // sharded NULL run: a rank folds the label pairs it owns, on every chromosome (the owner of a cell must
+                    // not change between chromosomes, or its additions would be re-associated); the ranks' outputs have
+                    // disjoint supports, so their sum is exact
+                    if (opt.null_world > 1 && (la * 31 + lb * 17) % opt.null_world != opt.null_rank) continue;
                     const double scan = ca * std::ceil(std::max(cb, 1.0) / 32.0);          // steps per haplotype pair
                     const double recs = ca * cb * 0.7;                                      // accepted pairs per haplotype pair
                     int ns = opt.null_slab_bins > 0 ? (G + opt.null_slab_bins - 1) / opt.null_slab_bins

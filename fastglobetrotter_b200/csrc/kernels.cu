@@ -1529,6 +1529,7 @@ void launch_null_group(int n_haps, const int32_t *row_off, const double *cstart,
 // fold lets each cell's first lane add its group's values straight from the queue, in lane order.
 constexpr int kNullQ = 64;
 constexpr int kNullStage = 256;   // B chunks staged per haplotype pair (larger groups are read from global memory)
+constexpr int kNullGroup = 3 * 32 + (5 * 32 + 2) / 2 + 1;   // doubles per warp for the staged group of A chunks
 
 __global__ void __launch_bounds__(128) k_null_strict(const NullArgs a) {
     extern __shared__ __align__(16) unsigned char nsm[];
@@ -1543,13 +1544,17 @@ __global__ void __launch_bounds__(128) k_null_strict(const NullArgs a) {
     const int lA = tk.lA, lB = tk.lB;                      // 0-based labels
     const int b_lo = tk.b_lo, b_hi = tk.b_hi;              // owned bins (relative to grid_start)
     const int sbw = b_hi - b_lo;
-    const int per_warp = 3 * kNullStage + 2 * kNullQ + a.max_slab_bins;         // doubles
+    const int per_warp = 3 * kNullStage + 2 * kNullQ + kNullGroup + a.max_slab_bins;         // doubles
     double *__restrict__ sposB = reinterpret_cast<double *>(nsm) + (size_t)wid * per_warp;
     double *__restrict__ shalfB = sposB + kNullStage;
     double *__restrict__ swB = shalfB + kNullStage;
     double *__restrict__ qdist = swB + kNullStage;
     double *__restrict__ qval = qdist + kNullQ;
-    double *__restrict__ tile = qval + kNullQ;
+    double *__restrict__ sApos = qval + kNullQ;          // [32] the current group of A chunks: position, half size, weight
+    double *__restrict__ sAhalf = sApos + 32;
+    double *__restrict__ sAw = sAhalf + 32;
+    int *__restrict__ sAi = reinterpret_cast<int *>(sAw + 32);        // [4][32] window starts / sizes, [33] candidate offsets
+    double *__restrict__ tile = qval + kNullQ + kNullGroup;
     double *gout = a.out + ((size_t)lA * K + lB) * G + b_lo;
     for (int i = lane; i < sbw; i += 32) tile[i] = gout[i];
     __syncwarp();
@@ -1639,14 +1644,66 @@ __global__ void __launch_bounds__(128) k_null_strict(const NullArgs a) {
                 }
             };
             int ia = 0;
-            if (cntB <= 32) {
-                // the whole B group is one step: evaluate four A chunks at once (independent), queue in order
-                for (; ia + 4 <= cntA; ia += 4) {
-                    bool s[4]; double d[4], v[4];
+            if (staged) {
+                // Windowed enumeration.  The B group is sorted by position, and only B chunks at a distance inside the slab's
+                // window [dwin_lo, dwin_hi] from an A chunk can land in the owned bins: 32 A chunks at a time, every lane
+                // bisects the (at most two) index ranges of its A chunk, a warp scan numbers the candidates in (A, B) order,
+                // and the steps below evaluate 32 candidates each -- instead of stepping through the whole B group per A chunk.
+                int *sL0 = sAi, *snl = sAi + 32, *sR0 = sAi + 64, *snr = sAi + 96, *soff = sAi + 128;
+                for (; ia < cntA; ia += 32) {
+                    const int my = ia + lane;
+                    int L0 = 0, nl = 0, R0 = 0, nr = 0;
+                    __syncwarp();
+                    if (my < cntA) {
+                        const Chunk A = CA[my];
+                        sApos[lane] = A.pos; sAhalf[lane] = __dmul_rn(A.size, 0.5); sAw[lane] = A.w;
+                        auto lower = [&](double x) {          // first index with pos >= x
+                            int lo = 0, hi = cntB;
+                            while (lo < hi) { const int mid = (lo + hi) >> 1; if (sposB[mid] < x) lo = mid + 1; else hi = mid; }
+                            return lo;
+                        };
+                        auto upper = [&](double x) {          // first index with pos > x
+                            int lo = 0, hi = cntB;
+                            while (lo < hi) { const int mid = (lo + hi) >> 1; if (sposB[mid] <= x) lo = mid + 1; else hi = mid; }
+                            return lo;
+                        };
+                        const double slack = 1e-9;            // rounding of pos +- window; the exact tests follow
+                        L0 = lower(A.pos - dwin_hi - slack);
+                        int L1 = upper(A.pos - dwin_lo + slack);
+                        R0 = lower(A.pos + dwin_lo - slack);
+                        const int R1 = upper(A.pos + dwin_hi + slack);
+                        if (L1 > R0) { L1 = R1; R0 = R1; }   // the windows touch (the slab holds distance ~0): one range
+                        nl = L1 - L0; nr = R1 - R0;
+                        if (nl < 0) nl = 0;
+                        if (nr < 0) nr = 0;
+                    }
+                    const int mine = nl + nr;
+                    int incl = mine;
 #pragma unroll
-                    for (int u = 0; u < 4; u++) { const Chunk A = CA[ia + u]; test(A, __dmul_rn(A.size, 0.5), lane, s[u], d[u], v[u]); }
-#pragma unroll
-                    for (int u = 0; u < 4; u++) push(s[u], d[u], v[u]);
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int y = __shfl_up_sync(kFull, incl, o);
+                        if (lane >= o) incl += y;
+                    }
+                    const int T = __shfl_sync(kFull, incl, 31);
+                    sL0[lane] = L0; snl[lane] = nl; sR0[lane] = R0; snr[lane] = nr; soff[lane] = incl - mine;
+                    if (lane == 0) soff[32] = T;
+                    __syncwarp();
+                    for (int t0 = 0; t0 < T; t0 += 32) {
+                        const int t = t0 + lane;
+                        bool surv = false;
+                        double dist = 0.0, val = 0.0;
+                        if (t < T) {
+                            int lo = 0, hi = 31;                 // owner: the last A chunk whose first candidate is <= t
+                            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (soff[mid] <= t) lo = mid; else hi = mid - 1; }
+                            const int u = lo;
+                            const int k = t - soff[u];
+                            const int jb = k < snl[u] ? sL0[u] + k : sR0[u] + (k - snl[u]);
+                            dist = fabs(__dsub_rn(sApos[u], sposB[jb]));                       // reference C:1015
+                            surv = dist >= dwin_lo && dist <= dwin_hi && dist >= __dadd_rn(sAhalf[u], shalfB[jb]);   // C:1019-1020
+                            val = __dmul_rn(sAw[u], swB[jb]);
+                        }
+                        push(surv, dist, val);
+                    }
                 }
             }
             for (; ia < cntA; ia++) {
@@ -1677,7 +1734,9 @@ void launch_null_strict(const NullArgs &a, cudaStream_t st) {
     const int wpb = 4;
     long long tasks = a.n_tasks;
     if (tasks <= 0) return;
-    size_t smem = (size_t)wpb * (3 * kNullStage + 2 * kNullQ + a.max_slab_bins) * sizeof(double);
+    size_t smem = (size_t)wpb * (3 * kNullStage + 2 * kNullQ + kNullGroup + a.max_slab_bins) * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k_null_strict, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
     k_null_strict<<<(unsigned)((tasks + wpb - 1) / wpb), wpb * 32, smem, st>>>(a);
 }
 

@@ -130,7 +130,13 @@ int64_t fgt_get_raw_counts(double *out, int64_t capacity);
 /* options: "device" (ordinal), "strict" (1 = order-preserving fp64 fold, bit-exact; 0 = fp64
  * atomics), "keep_raw", "rand_libc" (1 = draw from / advance the process' libc rand() state like
  * the reference does; 0 = private stream seeded by fgt_srand), "slab_bins", "cache" (parsed-file cache),
- * "threads" (parser threads), "verbose". */
+ * "threads" (parser threads), "verbose".  Tuning / test hooks (defaults are the measured optimum): "accum_impl"
+ * (2 = two-phase, 1 = single-phase), "batch_pairs", "blocks", "ranges", "split_ready", "eval_parts", "spec_rand",
+ * "copy_streams", "null_slab_bins", "reuse_prep" (one-shot).  "project_impl": 0 = exact projection (bit-identical curves,
+ * default), 1 = FP64 tensor cores (curves to ~1e-14).  "null_world" / "null_rank": sharded data_read_null -- this
+ * process folds only the label pairs it owns and returns zeros elsewhere (every rank is given the caller's initial
+ * buffer and keeps its own cells of it); the outputs have disjoint supports, so their sum (one all-reduce) is
+ * bit-identical to the single-process result. */
 int fgt_set_option(const char *key, double value);
 double fgt_get_option(const char *key);
 

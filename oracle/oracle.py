@@ -90,11 +90,13 @@ class Oracle:
         return means.reshape(S * S, num_bins), raw, int(pairs)
 
     def data_read_null_packed(self, ploidy, nsamples, chrom, rec_rows, bin_width, num_bins, grid_start, K,
-                              donor_label_vec, weight_min, cutoff):
+                              donor_label_vec, weight_min, cutoff, init=None):
         nsites, pp, rp, lp, lb, keep = self._chrom_arrays(chrom)
         rows = np.ascontiguousarray(rec_rows, dtype=np.int32)
         dl = np.ascontiguousarray(donor_label_vec, dtype=np.int32)
-        out = np.zeros(K * K * num_bins, dtype=np.float64)
+        # the reference adds into the caller's buffer (C:1020); `init` is that buffer's content on entry
+        out = np.zeros(K * K * num_bins, dtype=np.float64) if init is None else \
+            np.ascontiguousarray(init, dtype=np.float64).ravel().copy()
         evals = self.lib.orc_data_read_null_packed(
             C.c_int(ploidy), C.c_int(nsamples), C.c_int(len(chrom)), C.c_int(rows.size), rows.ctypes.data_as(_ip),
             nsites.ctypes.data_as(_ip), pp, rp, lp, C.c_int(lb), C.c_double(bin_width), C.c_int(num_bins),

@@ -648,3 +648,29 @@ def test_twenty_two_chromosomes_bootstrap(lib, oracle, mode):
         _run_both(lib, oracle, mode, 2, 3, chrom, ids, 0.1, G, 10, K, dl, 0.0, 1.0, S, tw, seed=230 + mode)
     finally:
         lib.set_option("blocks", 0)
+
+
+def test_null_sharded_by_label_pair_is_exact(lib, oracle, small):
+    """data_read_null over `world` ranks: each folds the label pairs it owns (the same owner on every chromosome), the
+    partial tensors have disjoint supports and their sum is the oracle's tensor bit for bit -- also when the caller's
+    buffer starts non-zero (every rank gets it and keeps only its own cells of it)."""
+    sp = small.spec
+    chrom, dl = packed_chrom(small), small.donor_label_vec
+    K, G, bw, gs = sp.K, 90, 0.1, 10
+    rows = np.arange(sp.n_inds)
+    init = np.random.default_rng(3).random(K * K * G)
+    n_o, ev = oracle.data_read_null_packed(sp.ploidy, sp.nsamples, chrom, rows, bw, G, gs, K, dl, 0.0, 1.0, init=init)
+    try:
+        for world in (2, 3):
+            total = np.zeros_like(n_o)
+            for rank in range(world):
+                lib.set_option("null_world", world)
+                lib.set_option("null_rank", rank)
+                part, st = lib.data_read_null_packed(sp.ploidy, sp.nsamples, chrom, rows, bw, G, gs, K, dl, 0.0, 1.0, init=init)
+                assert st["pairs"] == ev
+                assert not np.any((part != 0) & (total != 0))          # disjoint supports
+                total = total + part
+            assert np.array_equal(total, n_o), world
+    finally:
+        lib.set_option("null_world", 1)
+        lib.set_option("null_rank", 0)
