@@ -64,6 +64,7 @@ int Engine::set_option(const char *key, double v) {
     else if (k == "reuse_prep") opt.reuse_prep = iv;
     else if (k == "accum_impl") opt.accum_impl = iv;
     else if (k == "spec_rand") opt.spec_rand = iv;
+    else if (k == "null_target") opt.null_target = iv;
     else if (k == "null_world") opt.null_world = std::max(1, iv);
     else if (k == "null_rank") opt.null_rank = std::max(0, iv);
     else if (k == "project_impl") opt.project_impl = iv;
@@ -1135,7 +1136,7 @@ int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_ro
                     const double scan = ca * std::ceil(std::max(cb, 1.0) / 32.0);          // steps per haplotype pair
                     const double recs = ca * cb * 0.7;                                      // accepted pairs per haplotype pair
                     int ns = opt.null_slab_bins > 0 ? (G + opt.null_slab_bins - 1) / opt.null_slab_bins
-                                                    : (int)std::lround(recs / 48.0);
+                                                    : (int)std::lround(recs / (opt.null_target > 0 ? (double)opt.null_target : 96.0));
                     ns = std::max(1, std::min(ns, std::min(G, 64)));
                     const int w = (G + ns - 1) / ns;
                     for (int b = 0; b < G; b += w) {

@@ -46,6 +46,7 @@ struct Options {
     int eval_parts = 0;     // warps per (individual, coarse bin) in phase 1; 0 = automatic
     int copy_streams = 1;   // 2 = alternate the label block copies between two streams (two DMA engines)
     int project_impl = 0;   // 0 = exact (separately rounded multiply and add, bit-identical curves); 1 = FP64 tensor cores (~1e-14)
+    int null_target = 0;    // NULL task table: accepted pairs per (haplotype pair, slab) a task aims at; 0 = default
     int null_world = 1, null_rank = 0;   // sharded NULL run: this rank folds the label pairs it owns (sum of the ranks = exact)
     int spec_rand = 1;      // generate the first batch's draws while the chunk/bin kernels run
     int accum_impl = 2;     // 2 = two-phase (evaluate once, ordered commit); 1 = single-phase slab warps     // one-shot: next packed call may reuse the chunk/bin tables of the previous one
