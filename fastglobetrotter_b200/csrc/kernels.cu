@@ -1394,12 +1394,62 @@ k_mean_accum(const double *__restrict__ ratio, int N, int SS, int G, double *__r
     const int kh = blockIdx.y;
     if (i >= G) return;
     double m = means[(size_t)kh * G + i];
-    for (int n = 0; n < N; n++) m = __dadd_rn(m, ratio[((size_t)n * SS + kh) * G + i]);
+    const double *r = ratio + (size_t)kh * G + i;
+    const size_t stride = (size_t)SS * G;
+    int n = 0;
+    for (; n + 8 <= N; n += 8) {                         // eight loads in flight, added in individual order
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = r[(size_t)(n + u) * stride];
+#pragma unroll
+        for (int u = 0; u < 8; u++) m = __dadd_rn(m, v[u]);
+    }
+    for (; n < N; n++) m = __dadd_rn(m, r[(size_t)n * stride]);
     means[(size_t)kh * G + i] = m;
+}
+
+// the same arithmetic with one thread per (individual, surrogate row k, bin): 32 bins x S rows per block, the row sums
+// exchanged through shared memory, every thread adding them up in row order for the total (reference order)
+__global__ void __launch_bounds__(1024)
+k_normalise_rows(const double *__restrict__ results, int S, int G, int N_total, double *__restrict__ rsbuf,
+                 double *__restrict__ ratio) {
+    __shared__ double srs[32][33];
+    const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
+    const int n = blockIdx.y;
+    const bool live = i < G;
+    const double *R = results + (size_t)n * S * S * G + (live ? i : 0);
+    double s = 0.0;
+    for (int h = 0; h < S; h++) {
+        const int a = k <= h ? k : h, b = k <= h ? h : k;
+        const double sym = __dmul_rn(__dadd_rn(R[(size_t)(a * S + b) * G], R[(size_t)(b * S + a) * G]), 0.5);   // C:610-615
+        s = __dadd_rn(s, sym);
+    }
+    srs[k][lane] = s;
+    if (live) rsbuf[((size_t)n * S + k) * G + i] = s;
+    __syncthreads();
+    double tot = 0.0;
+    for (int q = 0; q < S; q++) tot = __dadd_rn(tot, srs[q][lane]);
+    if (!live) return;
+    const double dN = (double)N_total;
+    double *out = ratio + (size_t)n * S * S * G + i;
+    for (int h = 0; h < S; h++) {
+        const int a = k <= h ? k : h, b = k <= h ? h : k;
+        const double sym = __dmul_rn(__dadd_rn(R[(size_t)(a * S + b) * G], R[(size_t)(b * S + a) * G]), 0.5);
+        const double e_ab = __ddiv_rn(__dmul_rn(srs[a][lane], srs[b][lane]), tot);
+        const double e_ba = __ddiv_rn(__dmul_rn(srs[b][lane], srs[a][lane]), tot);
+        const double ex = __dmul_rn(__dadd_rn(e_ab, e_ba), 0.5);                     // C:628-638
+        out[(size_t)(k * S + h) * G] = __ddiv_rn(__ddiv_rn(sym, ex), dN);            // C:644
+    }
 }
 
 void launch_normalise(double *results, int N, int S, int G, int N_total, double *rsbuf, double *ratio, cudaStream_t st) {
     if (N <= 0) return;
+    if (S <= 32) {
+        dim3 grid2((G + 31) / 32, N);
+        k_normalise_rows<<<grid2, 32 * S, 0, st>>>(results, S, G, N_total, rsbuf, ratio);
+        return;
+    }
     dim3 grid((G + 127) / 128, N);
     k_normalise<<<grid, 128, 0, st>>>(results, N, S, G, N_total, rsbuf, ratio);
 }
