@@ -674,3 +674,23 @@ def test_null_sharded_by_label_pair_is_exact(lib, oracle, small):
     finally:
         lib.set_option("null_world", 1)
         lib.set_option("null_rank", 0)
+
+
+def test_weight_min_general_chunking_through_data_read(lib, oracle, small):
+    """weight_min >= 1 (a label change only opens a chunk after a run longer than weight_min SNPs, C:446-455) takes the
+    sequential chunk kernels; the whole data_read and data_read_null must still match the oracle bit for bit."""
+    sp = small.spec
+    chrom, dl = packed_chrom(small), small.donor_label_vec
+    K, S, G, bw, gs = sp.K, 3, 100, 0.1, 10
+    tw = np.random.default_rng(12).random(K * K * S * S)
+    ids = ind_id_matrix(sp.n_inds, sp.n_chrom)
+    for wmin in (1.0, 2.0, 5.0):
+        _run_both(lib, oracle, 1, sp.ploidy, sp.nsamples, chrom, ids, bw, G, gs, K, dl, wmin, 1.0, S, tw, seed=int(90 + wmin))
+        lib.set_option("blocks", 3)
+        try:
+            _run_both(lib, oracle, 1, sp.ploidy, sp.nsamples, chrom, ids, bw, G, gs, K, dl, wmin, 0.8, S, tw, seed=int(95 + wmin))
+        finally:
+            lib.set_option("blocks", 0)
+        n_o, ev = oracle.data_read_null_packed(sp.ploidy, sp.nsamples, chrom, np.arange(sp.n_inds), bw, G, gs, K, dl, wmin, 1.0)
+        n_g, st = lib.data_read_null_packed(sp.ploidy, sp.nsamples, chrom, np.arange(sp.n_inds), bw, G, gs, K, dl, wmin, 1.0)
+        assert st["pairs"] == ev and np.array_equal(n_g, n_o), wmin
