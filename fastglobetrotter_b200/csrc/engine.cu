@@ -566,7 +566,7 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
     size_t tw_bytes = 0;
     bool tw_pending = false;
     std::future<void> tw_stage;
-    int32_t *d_pairkh = nullptr, *d_slabof = nullptr, *d_firstslab = nullptr, *d_slabw = nullptr, *d_slabb0 = nullptr;
+    int32_t *d_pairkh = nullptr, *d_firstslab = nullptr;
     SlabDesc *d_slabs = nullptr;
     long long *d_pairbase = nullptr;
     int32_t *d_physof = nullptr;
@@ -630,15 +630,9 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
         if (!d_slabs || !d_pairbase || !d_physof || !d_hist) return FGT_ERR_CUDA;
         CK(cudaMemcpyAsync(d_slabs, slabs.data(), slabs.size() * sizeof(SlabDesc), cudaMemcpyHostToDevice, st_));
         if (impl != 1) {
-            d_slabof = d_slabof_.as<int32_t>(G); d_firstslab = d_firstslab_.as<int32_t>(W0);
-            d_slabw = d_slabw_.as<int32_t>(slabs.size()); d_slabb0 = d_slabb0_.as<int32_t>(slabs.size());
-            if (!d_slabof || !d_firstslab || !d_slabw || !d_slabb0) return FGT_ERR_CUDA;
-            std::vector<int32_t> sw(slabs.size()), sb0(slabs.size());
-            for (size_t s = 0; s < slabs.size(); s++) { sw[s] = slabs[s].b1 - slabs[s].b0 + 1; sb0[s] = slabs[s].b0 - pb.grid_start; }
-            CK(cudaMemcpyAsync(d_slabof, plan.slab_of.data(), G * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
+            d_firstslab = d_firstslab_.as<int32_t>(W0);
+            if (!d_firstslab) return FGT_ERR_CUDA;
             CK(cudaMemcpyAsync(d_firstslab, plan.first_slab.data(), W0 * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
-            CK(cudaMemcpyAsync(d_slabw, sw.data(), sw.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
-            CK(cudaMemcpyAsync(d_slabb0, sb0.data(), sb0.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
         }
         if (want_raw) {
             size_t slots = (pb.mode == 1) ? (size_t)N : (size_t)N * Cn;
@@ -821,7 +815,7 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
                     const bool normal = std::isnormal(pb.binwidth) && pb.binwidth > 1e-100 && pb.binwidth < 1e100;
                     ea.inv_bw = (!all_ones && normal) ? 1.0 / pb.binwidth : 0.0;
                 }
-                ea.slab_of = d_slabof; ea.first_slab = d_firstslab; ea.slab_w = d_slabw; ea.slab_b0 = d_slabb0;
+                ea.first_slab = d_firstslab;
                 ea.slab_width = plan.slab_width;
                 ea.slab_magic = plan.slab_width > 1 ? (uint32_t)(((1ULL << 32) + plan.slab_width - 1) / plan.slab_width) : 0u;
                 ea.recs = d_recs; ea.regions = d_regions; ea.slabs = d_slabs; ea.n_slabs = (int)slabs.size(); ea.nd_max = nd_max;

@@ -99,7 +99,7 @@ class Engine {
     DevBuf d_labels_, d_cum_, d_inc_, d_counts_, d_rowoff_, d_segoff_, d_cstart_, d_cend_, d_chap_, d_cntmat_, d_runfirst_,
         d_donor_, d_etab_, d_rowmap_;
     DevBuf d_draws_, d_hist_, d_tensor_, d_results_, d_tw_, d_pairkh_, d_slabs_, d_pairbase_, d_physof_, d_rs_,
-        d_ratio_, d_means_, d_raw_, d_totals_, d_recs_, d_cnt_, d_draws2_, d_recs2_, d_cnt2_, d_taskctr_, d_slabof_, d_firstslab_, d_slabw_, d_slabb0_;
+        d_ratio_, d_means_, d_raw_, d_totals_, d_recs_, d_cnt_, d_draws2_, d_recs2_, d_cnt2_, d_taskctr_, d_firstslab_;
     std::vector<ChromState> chroms_;
     std::vector<double> raw_host_;
     int64_t raw_count_ = 0;

@@ -69,10 +69,7 @@ struct EvalArgs {
     int32_t N, K, G, grid_start, mode, n_slots;
     double bw, half_bw, cutoff;
     double inv_bw;                // RN(1/bw), or 0 when the two-FMA division below is not provably exact for this bw
-    const int32_t *slab_of;       // [G] slab index of every fine bin (relative to grid_start)
     const int32_t *first_slab;    // [W] first slab reachable from separation d
-    const int32_t *slab_w;        // [n_slabs] width of each slab in bins
-    const int32_t *slab_b0;       // [n_slabs] first bin (relative to grid_start) of each slab
     UpdateRec *recs;              // [(pairs) * n_slots]: segment (n,j,d) owns n_slots regions of Y records each
     RegionEnt *regions;           // [N*n_slabs][nb-1][nd_max] region directory, slab-major (zero = empty)
     const SlabDesc *slabs;
