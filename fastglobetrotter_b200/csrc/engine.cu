@@ -598,7 +598,10 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
             const size_t nbytes = tw_bytes;
             tw_stage = std::async(std::launch::async, [dst, src, nbytes]() { std::memcpy(dst, src, nbytes); });
             tw_pending = true;
+        } else if (pb.chrom[0].labels_on_device) {
+            tw_pending = true;                 // small table: copied straight from the caller's buffer, also just before the projection
         } else {
+            // host-resident paintings: now, before the label copies occupy the host-to-device copy engine
             CK(cudaMemcpyAsync(d_tw, pb.temp_weights, tw_bytes, cudaMemcpyHostToDevice, st_));
         }
         stx.h2d_bytes += (int64_t)K * K * S * S * 8;
@@ -847,7 +850,12 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
             if (project_per_range && (pb.mode == 3 || h == Cn - 1) && !want_raw) {
                 // these individuals' tensors are final: project them now, off the tail of the call
                 span_begin(2, sc);
-                if (tw_pending) { tw_stage.get(); CK(cudaMemcpyAsync(d_tw, pin_tw_, tw_bytes, cudaMemcpyHostToDevice, sc)); tw_pending = false; }
+                if (tw_pending) {
+                    const double *tw_src = pb.temp_weights;
+                    if (tw_stage.valid()) { tw_stage.get(); tw_src = pin_tw_; }
+                    CK(cudaMemcpyAsync(d_tw, tw_src, tw_bytes, cudaMemcpyHostToDevice, sc));
+                    tw_pending = false;
+                }
                 (opt.project_impl == 1 ? launch_project_tensor : launch_project)(tens_b, Nb, K, G, S, d_tw, d_pairkh, d_results + (size_t)b0 * S * S * G, sc);
                 launches_ += 1;
                 span_end(sc);
@@ -943,7 +951,12 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
         if (pb.mode == 3 && !(project_per_range && !want_raw)) {
             span_begin(2, sc);
             if (want_raw) { launch_expand_raw(d_tensor, N, K, G, d_raw + (size_t)h * N * K * K * G, sc); launches_++; }
-            if (tw_pending) { tw_stage.get(); CK(cudaMemcpyAsync(d_tw, pin_tw_, tw_bytes, cudaMemcpyHostToDevice, sc)); tw_pending = false; }
+            if (tw_pending) {
+                    const double *tw_src = pb.temp_weights;
+                    if (tw_stage.valid()) { tw_stage.get(); tw_src = pin_tw_; }
+                    CK(cudaMemcpyAsync(d_tw, tw_src, tw_bytes, cudaMemcpyHostToDevice, sc));
+                    tw_pending = false;
+                }
             (opt.project_impl == 1 ? launch_project_tensor : launch_project)(d_tensor, N, K, G, S, d_tw, d_pairkh, d_results, sc);
             launches_ += 1;
             if (memset_tensor) CK(cudaMemsetAsync(d_tensor, 0, tens_elems * sizeof(double), sc));
@@ -973,7 +986,12 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
     CK(cudaEventRecord(ev[1], sc));
     if (pb.mode == 1 && !(project_per_range && !want_raw)) {
         if (want_raw) { launch_expand_raw(d_tensor, N, K, G, d_raw, sc); launches_++; }
-        if (tw_pending) { tw_stage.get(); CK(cudaMemcpyAsync(d_tw, pin_tw_, tw_bytes, cudaMemcpyHostToDevice, sc)); tw_pending = false; }
+        if (tw_pending) {
+                    const double *tw_src = pb.temp_weights;
+                    if (tw_stage.valid()) { tw_stage.get(); tw_src = pin_tw_; }
+                    CK(cudaMemcpyAsync(d_tw, tw_src, tw_bytes, cudaMemcpyHostToDevice, sc));
+                    tw_pending = false;
+                }
         (opt.project_impl == 1 ? launch_project_tensor : launch_project)(d_tensor, N, K, G, S, d_tw, d_pairkh, d_results, sc);
         launches_ += 1;
     }
