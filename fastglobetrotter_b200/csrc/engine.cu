@@ -1115,11 +1115,11 @@ int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_ro
     CK(cudaMemcpyAsync(d_out, init_src, (size_t)K * K * G * sizeof(double), cudaMemcpyHostToDevice, st_));
     if (opt.null_world > 1) CK(cudaStreamSynchronize(st_));      // own_init is a local
     CK(cudaEventRecord(e1, st_));
-    ChromState cs;
+    ChromState &cs = null_cs_;                   // grow-only buffers kept between calls (no cudaMalloc/cudaFree per call)
     long long evals = 0;
     for (int h = 0; h < pb.num_chrom; h++) {
         rc = prep_chromosome(pb, h, d_rowmap, n_haps, 1, n_haps, true, cs, stx);
-        if (rc) { cs.sorted.release(); cs.yoff.release(); cs.chunk_base.release(); return rc; }
+        if (rc) return rc;
         if (Nc >= 2) {
             NullArgs a{};
             a.chunks = (const Chunk *)cs.sorted.p; a.hap_base = (const int32_t *)cs.chunk_base.p;
@@ -1192,7 +1192,6 @@ int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_ro
     CK(cudaMemcpyAsync(hacc, d_acc, sizeof hacc, cudaMemcpyDeviceToHost, st_));
     CK(cudaStreamSynchronize(st_));
     CK(cudaGetLastError());
-    cs.sorted.release(); cs.yoff.release(); cs.chunk_base.release();
     if ((herr[0] & kErrMissingDonor) && Nc >= 2) return FGT_ERR_MISSING_DONOR;
     stx.pairs = evals;
     stx.accepted = (int64_t)hacc[0];

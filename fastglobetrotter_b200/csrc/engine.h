@@ -101,6 +101,7 @@ class Engine {
     DevBuf d_draws_, d_hist_, d_tensor_, d_results_, d_tw_, d_pairkh_, d_slabs_, d_pairbase_, d_physof_, d_rs_,
         d_ratio_, d_means_, d_raw_, d_totals_, d_recs_, d_cnt_, d_draws2_, d_recs2_, d_cnt2_, d_taskctr_, d_firstslab_;
     std::vector<ChromState> chroms_;
+    ChromState null_cs_;              // NULL path: chunk buffers of the chromosome being folded
     std::vector<double> raw_host_;
     int64_t raw_count_ = 0;
     int launches_ = 0;

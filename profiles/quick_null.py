@@ -20,5 +20,6 @@ for sb in [int(x) for x in os.environ.get("SB", "0,2,4,8,16,32,64").split(",")]:
     out, st = lib.data_read_null_packed(2, 10, chrom, rows, 0.1, G, 10, K, dl, 0.0, 1.0)
     dt = time.perf_counter() - t0
     if ref is None: ref = out
-    print(f"null_slab_bins={sb:3d}: {dt*1e3:8.1f} ms  {st['pairs']/dt/1e9:6.1f} G evals/s  same={np.array_equal(out, ref)}")
+    print(f"{os.environ.get('KEY', 'null_slab_bins')}={sb:3d}: {dt*1e3:8.1f} ms (device {st['ms_total']:.1f}, chunking {st['ms_chunk']:.1f}, kernel {st['ms_accum']:.1f})  "
+          f"{st['pairs']/dt/1e9:6.1f} G evals/s  same={np.array_equal(out, ref)}")
 lib.set_option(os.environ.get("KEY", "null_slab_bins"), 0)
