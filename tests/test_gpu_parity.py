@@ -694,3 +694,52 @@ def test_weight_min_general_chunking_through_data_read(lib, oracle, small):
         n_o, ev = oracle.data_read_null_packed(sp.ploidy, sp.nsamples, chrom, np.arange(sp.n_inds), bw, G, gs, K, dl, wmin, 1.0)
         n_g, st = lib.data_read_null_packed(sp.ploidy, sp.nsamples, chrom, np.arange(sp.n_inds), bw, G, gs, K, dl, wmin, 1.0)
         assert st["pairs"] == ev and np.array_equal(n_g, n_o), wmin
+
+
+def test_randomized_shapes_against_the_oracle(lib, oracle):
+    """differential fuzz: 36 random problem shapes (ploidy, samples, individuals, chromosomes, SNPs, map rate, K, S,
+    bins, bin width, grid start, cutoff, weight_min, mode, id pattern, self-copying, block pipeline) -- raw tensors,
+    curves and the NULL tensor bit-identical to the oracle in every one."""
+    rng = np.random.default_rng(int(os.environ.get("FGT_FUZZ_SEED", "20261020")))     # other seeds: FGT_FUZZ_SEED=...
+    lib.set_option("rand_libc", 0)
+    for case in range(36):
+        ploidy = int(rng.choice([1, 2]))
+        nsamples = int(rng.integers(1, 5))
+        n_inds = int(rng.integers(1, 7))
+        n_chrom = int(rng.integers(1, 4))
+        n_snps = int(rng.integers(40, 2600))
+        K = int(rng.integers(1, 9))
+        S = int(rng.integers(1, 5))
+        bw = float(rng.choice([0.05, 0.1, 0.2, 0.25, 0.5, 1.0]))
+        G = int(rng.integers(3, 160))
+        gs = int(rng.integers(0, 14))
+        cutoff = float(rng.choice([0.3, 1.0, 5.0]))
+        wmin = float(rng.choice([0.0, 0.0, 0.0, 1.0, 3.0]))
+        mode = int(rng.choice([1, 1, 3]))
+        rate = float(rng.choice([2e-7, 6e-7, 2e-6, 8e-6]))
+        selfc = 0.0 if mode == 3 else float(rng.choice([0.0, 0.05, 0.3]))
+        spec = synth.SynthSpec(n_chrom=n_chrom, n_inds=n_inds, ploidy=ploidy, nsamples=nsamples, n_snps=n_snps, K=K,
+                               haps_per_pop=int(rng.integers(1, 6)), rate=rate, mean_chunk_cm=float(rng.choice([0.05, 0.25, 1.5])),
+                               self_copy_frac=selfc, seed=1000 + case)
+        chrom = []
+        for h in range(n_chrom):
+            pos, rt, labels = synth.make_chromosome(spec, h)
+            chrom.append({"pos": pos, "rate": rt, "labels": labels})
+        dl = spec.donor_label_vec()
+        if mode == 3:
+            dl = np.where(dl == 0, 1, dl)
+        tw = rng.random(K * K * S * S)
+        ids = bootstrap_ids(n_inds, n_chrom, case) if rng.random() < 0.5 else ind_id_matrix(n_inds, n_chrom)
+        blocks = int(rng.choice([0, 0, 2, 5]))
+        lib.set_option("blocks", blocks)
+        try:
+            _run_both(lib, oracle, mode, ploidy, nsamples, chrom, ids, bw, G, gs, K, dl, wmin, cutoff, S, tw, seed=500 + case)
+        except AssertionError as e:
+            raise AssertionError(f"case {case}: ploidy={ploidy} nsamples={nsamples} N={n_inds} chr={n_chrom} L={n_snps} K={K} S={S} "
+                                 f"bw={bw} G={G} gs={gs} cutoff={cutoff} wmin={wmin} mode={mode} rate={rate} blocks={blocks}") from e
+        finally:
+            lib.set_option("blocks", 0)
+        if n_inds >= 2:
+            n_o, ev = oracle.data_read_null_packed(ploidy, nsamples, chrom, np.arange(n_inds), bw, G, gs, K, dl, wmin, cutoff)
+            n_g, st = lib.data_read_null_packed(ploidy, nsamples, chrom, np.arange(n_inds), bw, G, gs, K, dl, wmin, cutoff)
+            assert st["pairs"] == ev and np.array_equal(n_g, n_o), f"null case {case}"
