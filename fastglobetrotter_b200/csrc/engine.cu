@@ -659,7 +659,6 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
         }
         budget_pairs = (long long)(mem_budget_bytes_ / 2 / (8.0 + 16.0 * ns_rec));   // two lanes hold a batch each
     }
-    const int dbg = getenv("FGT_COMMIT_DBG") ? atoi(getenv("FGT_COMMIT_DBG")) : 0;   // timing experiments only
     tick("tables ready");
 
     // timing spans on the accumulation stream
@@ -841,7 +840,6 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
                 ca.tensor_is_zero = (tile_in_smem && (pb.mode == 3 || h == 0)) ? 1 : 0;
                 ca.tensor = tens_b; ca.accepted = d_acc;
                 ca.task_counter = d_taskctr + batch_seq;
-                ca.dbg = dbg;
                 launch_commit_ordered(ca, plan_max_w, sc);
                 launches_ += 2;
                 span_end(sc);

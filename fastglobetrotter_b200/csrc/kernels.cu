@@ -1139,7 +1139,7 @@ __global__ void __launch_bounds__(32 * (kConsumers + 1)) k_commit_ordered(const 
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[stage]);     // records are in registers: the stage can be refilled
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
-                if (s.c >= 0 && !(a.dbg & 2)) {
+                if (s.c >= 0) {
 #pragma unroll
                     for (int h = 0; h < kStageSteps; h++)
                         if (32 * h < s.c) s.g[h] = same_cell_mask(s.cell[h]);
@@ -1163,11 +1163,9 @@ __global__ void __launch_bounds__(32 * (kConsumers + 1)) k_commit_ordered(const 
             Staged cur = fetch();
             while (cur.c >= 0) {
                 const Staged nxt = fetch();
-                if (!(a.dbg & 1)) {
 #pragma unroll
-                    for (int h = 0; h < kStageSteps; h++)
-                        if (32 * h < cur.c) fold(cur.cell[h], cur.val[h], cur.g[h]);
-                }
+                for (int h = 0; h < kStageSteps; h++)
+                    if (32 * h < cur.c) fold(cur.cell[h], cur.val[h], cur.g[h]);
                 if (wid == 0) n_acc += (unsigned long long)cur.c;
                 cur = nxt;
             }

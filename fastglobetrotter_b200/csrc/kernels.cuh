@@ -88,7 +88,7 @@ struct CommitArgs {
     const SlabDesc *slabs;        // dlo/dhi = separations whose reach includes the slab
     const UpdateRec *recs;
     const RegionEnt *regions;
-    int32_t nd_max, tensor_is_zero, dbg;
+    int32_t nd_max, tensor_is_zero;
     double *tensor;
     unsigned long long *accepted;
     int *task_counter;            // zeroed before the launch: persistent CTAs claim (individual, slab) tasks from it
