@@ -711,7 +711,7 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
         const long long lo0 = pb.pair_offset ? pb.pair_offset[0] : 0;
         spec_A4 = (2 * lo0) & ~3LL;
         spec_threads = last_first_batch_threads_ & ~255LL;
-        spec_ptr = d_draws_.as<uint32_t>((size_t)spec_threads * kRun + 4);
+        spec_ptr = d_draws_.as<uint32_t>((size_t)spec_threads * kRun + 4 + kDrawSlack);
         if (!spec_ptr) return FGT_ERR_CUDA;
         History hs = apply_jump(poly_pow_E((uint64_t)spec_A4), h0);
         uint32_t *pin_spec = pin_hist + (size_t)Cn * N * kLag;        // the spare last slot
@@ -760,7 +760,7 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
             hist_used++;
             CK(cudaMemcpyAsync(d_pairbase + (size_t)h * N + b0, hp, Nb * sizeof(long long), cudaMemcpyHostToDevice, st_));
             CK(cudaMemcpyAsync(d_physof + (size_t)h * N + b0, hq, Nb * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
-            uint32_t *d_draws = draws_buf.as<uint32_t>((size_t)nthreads * kRun + 4);
+            uint32_t *d_draws = draws_buf.as<uint32_t>((size_t)nthreads * kRun + 4 + kDrawSlack);
             if (!d_draws) return FGT_ERR_CUDA;
             if (!first_eval) { first_eval = new_timed_event(); CK(cudaEventRecord(first_eval, st_)); }
             long long have = 0;                       // runs already generated speculatively for this very range
@@ -806,7 +806,7 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
                 span_begin(3, st_);
                 CK(cudaMemsetAsync(d_regions, 0, n_ent * sizeof(RegionEnt), st_));
                 EvalArgs ea{};
-                ea.cp = cpd; ea.draws = (const uint2 *)d_draws; ea.draws_limit = nthreads * (long long)kRun / 2;
+                ea.cp = cpd; ea.draws = (const uint2 *)d_draws;
                 ea.pair_base = pbase; ea.phys_of = pphys;
                 ea.N = Nb; ea.K = K; ea.G = G; ea.grid_start = pb.grid_start; ea.mode = pb.mode; ea.n_slots = plan.n_slots;
                 ea.bw = pb.binwidth; ea.half_bw = pb.binwidth / 2.0; ea.cutoff = pb.gridweight_max_cutoff;

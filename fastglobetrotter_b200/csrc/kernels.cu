@@ -865,8 +865,8 @@ __global__ void __launch_bounds__(128, 8) k_eval_pairs(const EvalArgs a) {
     // draws of the next iteration are fetched while the current one waits for its chunk gathers.
     uint2 nr0, nr1;
     auto prefetch = [&](long long p) {
-        nr0 = (p + lane < a.draws_limit) ? a.draws[p + lane] : make_uint2(0, 0);
-        nr1 = (p + 32 + lane < a.draws_limit) ? a.draws[p + 32 + lane] : make_uint2(0, 0);
+        nr0 = a.draws[p + lane];                         // may run up to 127 pairs past the batch: the buffer has kDrawSlack
+        nr1 = a.draws[p + 32 + lane];
     };
     // this warp's share of the separations: d in (d_from, d_to], cut where the row's cumulative pair count crosses
     // part/DS of its total (small ranges of individuals would otherwise leave most of the GPU idle)

@@ -58,12 +58,12 @@ struct __align__(16) UpdateRec { int32_t cell; int32_t pad; double val; };   // 
 
 struct __align__(16) RegionEnt { long long base; int32_t cnt; int32_t pad; };   // one record region: first record, count
 
+constexpr int kDrawSlack = 256;   // uint32 of slack behind the draws of a batch: phase 1 prefetches up to 127 pairs past the end
 constexpr int kMaxSlots = 4;   // slabs a coarse-bin separation can reach (regions per segment)
 
 struct EvalArgs {
     ChromPrep cp;
     const uint2 *draws;
-    long long draws_limit;        // pairs of draws in `draws` (prefetches are clamped to it)
     const long long *pair_base;   // [N]
     const int32_t *phys_of;       // [N]
     int32_t N, K, G, grid_start, mode, n_slots;
