@@ -1211,6 +1211,7 @@ void launch_commit_ordered(const CommitArgs &a, int max_slab_width, cudaStream_t
 //    temp_weights[(K*k+h)*S*S + mn] * counts[n][(k,h)][i]; multiply and add rounded separately,
 //    summed in the reference's order, so the result is bit-identical.
 // =============================================================================================
+constexpr int kMaxGridZ = 32768;                      // individuals per launch where they index grid.y / grid.z
 constexpr int PT = 64, PKK = 16, PTM_MAX = 100;      // bins per tile, pairs per slice, most surrogate pairs per tile
 __global__ void __launch_bounds__(16 * (PTM_MAX / 4))
 k_project(const double *__restrict__ tensor, int K, int G, int S, const double *__restrict__ tw,
@@ -1334,8 +1335,12 @@ k_project_dmma(const double *__restrict__ tensor, int K, int G, int S, const dou
 void launch_project_tensor(const double *tensor, int N, int K, int G, int S, const double *tw, const int32_t *pair_kh,
                            double *results, cudaStream_t st) {
     if (N <= 0) return;
-    dim3 grid((G + DN - 1) / DN, (S * S + DM - 1) / DM, N);
-    k_project_dmma<<<grid, 128, 0, st>>>(tensor, K, G, S, tw, pair_kh, results);
+    const size_t P = (size_t)K * (K + 1) / 2;
+    for (int n0 = 0; n0 < N; n0 += kMaxGridZ) {
+        const int nn = std::min(kMaxGridZ, N - n0);
+        dim3 grid((G + DN - 1) / DN, (S * S + DM - 1) / DM, nn);
+        k_project_dmma<<<grid, 128, 0, st>>>(tensor + (size_t)n0 * P * G, K, G, S, tw, pair_kh, results + (size_t)n0 * S * S * G);
+    }
 }
 
 void launch_project(const double *tensor, int N, int K, int G, int S, const double *tw, const int32_t *pair_kh,
@@ -1345,8 +1350,12 @@ void launch_project(const double *tensor, int N, int K, int G, int S, const doub
     const int SS = S * S;
     const int tiles_m = (SS + PTM_MAX - 1) / PTM_MAX;
     const int TY = std::max(1, ((SS + tiles_m - 1) / tiles_m + 3) / 4);
-    dim3 grid((G + PT - 1) / PT, (SS + 4 * TY - 1) / (4 * TY), N);
-    k_project<<<grid, 16 * TY, 0, st>>>(tensor, K, G, S, tw, pair_kh, results);
+    const size_t P = (size_t)K * (K + 1) / 2;
+    for (int n0 = 0; n0 < N; n0 += kMaxGridZ) {          // grid.z is limited to 65535 individuals per launch
+        const int nn = std::min(kMaxGridZ, N - n0);
+        dim3 grid((G + PT - 1) / PT, (SS + 4 * TY - 1) / (4 * TY), nn);
+        k_project<<<grid, 16 * TY, 0, st>>>(tensor + (size_t)n0 * P * G, K, G, S, tw, pair_kh, results + (size_t)n0 * SS * G);
+    }
 }
 
 // =============================================================================================
@@ -1444,12 +1453,20 @@ k_normalise_rows(const double *__restrict__ results, int S, int G, int N_total, 
 void launch_normalise(double *results, int N, int S, int G, int N_total, double *rsbuf, double *ratio, cudaStream_t st) {
     if (N <= 0) return;
     if (S <= 32) {
-        dim3 grid2((G + 31) / 32, N);
-        k_normalise_rows<<<grid2, 32 * S, 0, st>>>(results, S, G, N_total, rsbuf, ratio);
+        for (int n0 = 0; n0 < N; n0 += kMaxGridZ) {      // grid.y is limited to 65535 individuals per launch
+            const int nn = std::min(kMaxGridZ, N - n0);
+            dim3 grid2((G + 31) / 32, nn);
+            k_normalise_rows<<<grid2, 32 * S, 0, st>>>(results + (size_t)n0 * S * S * G, S, G, N_total, rsbuf + (size_t)n0 * S * G,
+                                                        ratio + (size_t)n0 * S * S * G);
+        }
         return;
     }
-    dim3 grid((G + 127) / 128, N);
-    k_normalise<<<grid, 128, 0, st>>>(results, N, S, G, N_total, rsbuf, ratio);
+    for (int n0 = 0; n0 < N; n0 += kMaxGridZ) {
+        const int nn = std::min(kMaxGridZ, N - n0);
+        dim3 grid((G + 127) / 128, nn);
+        k_normalise<<<grid, 128, 0, st>>>(results + (size_t)n0 * S * S * G, nn, S, G, N_total, rsbuf + (size_t)n0 * S * G,
+                                          ratio + (size_t)n0 * S * S * G);
+    }
 }
 
 void launch_mean_accum(const double *ratio, int N, int S, int G, double *means, cudaStream_t st) {
@@ -1487,8 +1504,12 @@ __global__ void k_expand_raw(const double *__restrict__ tensor, int K, int G, do
 
 void launch_expand_raw(const double *tensor, int N, int K, int G, double *out_full, cudaStream_t st) {
     if (N <= 0) return;
-    dim3 grid((G + 127) / 128, K * K, N);
-    k_expand_raw<<<grid, 128, 0, st>>>(tensor, K, G, out_full);
+    const size_t P = (size_t)K * (K + 1) / 2;
+    for (int n0 = 0; n0 < N; n0 += kMaxGridZ) {
+        const int nn = std::min(kMaxGridZ, N - n0);
+        dim3 grid((G + 127) / 128, K * K, nn);
+        k_expand_raw<<<grid, 128, 0, st>>>(tensor + (size_t)n0 * P * G, K, G, out_full + (size_t)n0 * K * K * G);
+    }
 }
 
 // =============================================================================================
