@@ -440,6 +440,17 @@ Loaded load_inputs(int ploidy, char **samp_list, char **recom_list, int n_rec, c
     L.num_chrom = (int)sfiles.size();
     const bool use_cache = Engine::get().opt.cache != 0;
 
+    using TextFuture = std::future<std::shared_ptr<SamplesText>>;
+    auto start_inflate = [&](int h) {
+        return std::async(std::launch::async, [&, h]() {
+            auto t = std::make_shared<SamplesText>();
+            if (!inflate_file(sfiles[h], *t)) return std::shared_ptr<SamplesText>();
+            return t;
+        });
+    };
+    auto inflate_window = [&]() { return std::max(1, std::min(n_threads(), 4)); };   // files being inflated / held as text at once
+    std::map<int, TextFuture> early;            // inflates in flight, by chromosome
+
     // first file: learn nsamples and which file individuals are the recipients (C:230-297)
     std::shared_ptr<SamplesText> first_text;
     SamplesMeta meta;
@@ -458,6 +469,10 @@ Loaded load_inputs(int ploidy, char **samp_list, char **recom_list, int n_rec, c
         }
         if (!hit && pack_dir() && disk_load_meta(pack_dir(), mk, meta) && (int)meta.rec_first_index.size() == n_rec) hit = true;
         if (!hit) {
+            // cold start: nothing of this data set is decoded yet, so the next files start inflating right away (zlib is
+            // sequential per file; several files at once is the only parallelism the format offers) while the first one
+            // is inflated here and scanned
+            for (int h = 1; h < L.num_chrom && (int)early.size() < inflate_window() - 1; h++) early[h] = start_inflate(h);
             first_text = std::make_shared<SamplesText>();
             if (!inflate_file(sfiles[0], *first_text)) die("error opening %s\n", sfiles[0].c_str());
             meta = scan_first_file(*first_text, sfiles[0], ploidy, n_rec, rec_labels);
@@ -472,15 +487,6 @@ Loaded load_inputs(int ploidy, char **samp_list, char **recom_list, int n_rec, c
     L.maps.resize(L.num_chrom);
     L.files.resize(L.num_chrom);
     for (int h = 0; h < L.num_chrom; h++) L.maps[h] = read_recomb(rfiles[h]);
-    // inflate file h+1 while file h is being tokenised
-    std::future<std::shared_ptr<SamplesText>> next;
-    auto start_inflate = [&](int h) {
-        return std::async(std::launch::async, [&, h]() {
-            auto t = std::make_shared<SamplesText>();
-            if (!inflate_file(sfiles[h], *t)) return std::shared_ptr<SamplesText>();
-            return t;
-        });
-    };
     std::vector<std::string> keys(L.num_chrom);
     std::vector<char> cached(L.num_chrom, 0);
     for (int h = 0; h < L.num_chrom; h++) {
@@ -501,26 +507,36 @@ Loaded load_inputs(int ploidy, char **samp_list, char **recom_list, int n_rec, c
             }
         }
     }
-    auto next_uncached = [&](int from) { for (int h = from; h < L.num_chrom; h++) if (!cached[h]) return h; return -1; };
-    int cur = next_uncached(0);
-    std::shared_ptr<SamplesText> cur_text;
-    if (cur >= 0) {
-        if (cur == 0 && first_text) cur_text = first_text;
-        else cur_text = start_inflate(cur).get();
+    // tokenise the files in order; up to inflate_window() later files are being inflated meanwhile
+    std::vector<int> todo;
+    for (int h = 0; h < L.num_chrom; h++) if (!cached[h]) todo.push_back(h);
+    for (auto it = early.begin(); it != early.end();) {         // a speculative inflate of a file that turned out cached
+        if (cached[it->first]) { it->second.wait(); it = early.erase(it); } else ++it;
     }
-    while (cur >= 0) {
-        int nxt = next_uncached(cur + 1);
-        if (nxt >= 0) next = start_inflate(nxt);
+    size_t issued = 0;                                           // todo[0..issued) have an inflate started or a text in hand
+    auto top_up = [&](size_t done) {
+        while (issued < todo.size() && issued < done + (size_t)inflate_window()) {
+            const int h = todo[issued++];
+            if (h == 0 && first_text) continue;
+            if (!early.count(h)) early[h] = start_inflate(h);
+        }
+    };
+    for (size_t q = 0; q < todo.size(); q++) {
+        top_up(q);
+        const int cur = todo[q];
+        std::shared_ptr<SamplesText> cur_text;
+        if (cur == 0 && first_text) cur_text = first_text;
+        else { cur_text = early[cur].get(); early.erase(cur); }
         if (!cur_text) die("error opening %s\n", sfiles[cur].c_str());
+        top_up(q + 1);                                           // this text is about to be released: one more file may start
         auto pf = std::make_shared<PackedFile>();
         pack_file(*cur_text, sfiles[cur], ploidy, meta.nsamples, (int)L.maps[cur].pos.size(), need, *pf);
         L.files[cur] = pf;
         if (pack_dir()) disk_store(pack_dir(), keys[cur], *pf);
         if (use_cache) { std::lock_guard<std::mutex> lk(g_cache_mu); g_cache[keys[cur]] = pf; }
-        cur_text.reset();
-        if (nxt >= 0) cur_text = next.get();
-        cur = nxt;
+        if (cur == 0) first_text.reset();
     }
+    for (auto &kv : early) kv.second.wait();
     first_text.reset();
     return L;
 }
