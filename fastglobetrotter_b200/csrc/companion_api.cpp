@@ -448,7 +448,15 @@ Loaded load_inputs(int ploidy, char **samp_list, char **recom_list, int n_rec, c
             return t;
         });
     };
-    auto inflate_window = [&]() { return std::max(1, std::min(n_threads(), 4)); };   // files being inflated / held as text at once
+    // files being inflated / held as text at once: up to four, fewer when the texts are large (painting text inflates
+    // about 30x; at most ~16 GB of it is kept in memory)
+    long long first_size = 0, first_mtime = 0;
+    file_identity(sfiles[0], first_size, first_mtime);
+    auto inflate_window = [&]() {
+        const long long est = std::max<long long>(1, first_size * 32);
+        const long long fit = std::max<long long>(1, (16LL << 30) / est);
+        return (int)std::max<long long>(1, std::min<long long>({(long long)n_threads(), 4LL, fit}));
+    };
     std::map<int, TextFuture> early;            // inflates in flight, by chromosome
 
     // first file: learn nsamples and which file individuals are the recipients (C:230-297)
