@@ -151,7 +151,12 @@ def num_bins_for(curve_lower: float, curve_upper: float, bin_width: float) -> in
 # ---------------------------------------------------------------------------------------------
 class fgt_chrom_t(C.Structure):
     _fields_ = [("nsites", C.c_int32), ("pos", C.c_void_p), ("rate", C.c_void_p), ("labels", C.c_void_p),
-                ("labels_on_device", C.c_int32)]
+                ("labels_on_device", C.c_int32), ("runs_on_device", C.c_int32), ("run_off", C.c_void_p),
+                ("runs", C.c_void_p)]
+
+
+#: numpy view of fgt_run_t: (start SNP, donor haplotype id)
+RUN_DTYPE = np.dtype([("start", np.uint32), ("hap", np.uint32)])
 
 
 class fgt_problem_t(C.Structure):
@@ -190,9 +195,17 @@ class PackedCompanion(Companion):
     with ``pos``/``rate`` (numpy float64) and ``labels`` -- a numpy array [rows, nsites] (uint16 or
     int32; host path) or a ``(device_ptr, dtype_itemsize)`` tuple (already resident in HBM)."""
 
-    def __init__(self, path: str | None = None):
+    def __init__(self, path: str | None = None, encode: str = "rle"):
+        """``encode``: how dense numpy label matrices handed to the packed calls reach the library -- "rle" (default:
+        run-length encoded on the host first, the library's preferred painting format) or "dense" (as they are)."""
         super().__init__(path)
+        assert encode in ("rle", "dense")
+        self.encode = encode
         L = self.lib
+        L.fgt_rle_encode.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
+        L.fgt_rle_encode.restype = C.c_int
+        L.fgt_pack_samples.argtypes = [C.c_char_p, C.c_int, C.c_char_p]
+        L.fgt_pack_samples.restype = C.c_int64
         L.fgt_data_read_packed.argtypes = [C.POINTER(fgt_problem_t), _dp, C.POINTER(fgt_stats_t)]
         L.fgt_data_read_packed.restype = C.c_int
         L.fgt_count_pairs_packed.argtypes = [C.POINTER(fgt_problem_t), C.POINTER(C.c_int64)]
@@ -237,6 +250,26 @@ class PackedCompanion(Companion):
             raise FgtError(rc)
         return out
 
+    def rle_encode(self, labels):
+        """dense [rows, nsites] uint16/int32 label matrix -> (run_off int64 [rows+1], runs RUN_DTYPE [n_runs])"""
+        lab = np.ascontiguousarray(labels)
+        assert lab.ndim == 2 and lab.dtype.itemsize in (2, 4)
+        rows, L = lab.shape
+        off = np.zeros(rows + 1, dtype=np.int64)
+        n = self.lib.fgt_rle_encode(lab.ctypes.data, lab.dtype.itemsize, rows, L, off.ctypes.data, None, 0)
+        if n < 0:
+            raise FgtError(n)
+        runs = np.zeros(n, dtype=RUN_DTYPE)
+        n2 = self.lib.fgt_rle_encode(lab.ctypes.data, lab.dtype.itemsize, rows, L, off.ctypes.data, runs.ctypes.data, n)
+        assert n2 == n
+        return off, runs
+
+    def pack_samples(self, samples_path: str, nsites: int, out_path: str) -> int:
+        n = self.lib.fgt_pack_samples(samples_path.encode(), nsites, out_path.encode())
+        if n < 0:
+            raise FgtError(int(n))
+        return int(n)
+
     def _problem(self, mode, ploidy, nsamples, chrom, ind_rows, bin_width, num_bins, grid_start, K, donor_label_vec,
                  weight_min, cutoff, S, temp_weights, n_packed_inds=None, num_inds_total=0, pair_offset=None,
                  pairs_total=0):
@@ -252,8 +285,27 @@ class PackedCompanion(Companion):
             carr[h].nsites = pos.size
             carr[h].pos = pos.ctypes.data
             carr[h].rate = rate.ctypes.data
-            lab = c["labels"]
-            if isinstance(lab, tuple):
+            lab = c.get("labels")
+            runs = c.get("runs")
+            if runs is None and lab is not None and not isinstance(lab, tuple) and self.encode == "rle":
+                runs = self.rle_encode(lab)
+            if runs is not None:
+                # (run_off int64 [rows+1], runs): runs a RUN_DTYPE array (host) or a device pointer (int)
+                off, rr = runs
+                off = np.ascontiguousarray(off, dtype=np.int64)
+                keep.append(off)
+                carr[h].run_off = off.ctypes.data
+                if isinstance(rr, (int, np.integer)):
+                    carr[h].runs = int(rr)
+                    carr[h].runs_on_device = 1
+                else:
+                    rr = np.ascontiguousarray(rr)
+                    assert rr.dtype.itemsize == 8
+                    keep.append(rr)
+                    carr[h].runs = rr.ctypes.data
+                    carr[h].runs_on_device = 0
+                this_lb, this_rows = 4, off.size - 1
+            elif isinstance(lab, tuple):
                 ptr, item, nrows = lab
                 carr[h].labels = ptr
                 carr[h].labels_on_device = 1
@@ -264,15 +316,17 @@ class PackedCompanion(Companion):
                 carr[h].labels = lab.ctypes.data
                 carr[h].labels_on_device = 0
                 this_lb, this_rows = lab.dtype.itemsize, lab.shape[0]
-            assert lb in (None, this_lb)
-            lb, rows = this_lb, this_rows
+            if runs is None:
+                assert lb in (None, this_lb)
+                lb = this_lb
+            rows = this_rows
         ids = np.ascontiguousarray(ind_rows, dtype=np.int32).ravel()
         dl = np.ascontiguousarray(donor_label_vec, dtype=np.int32)
         keep += [ids, dl, carr]
         pb = fgt_problem_t()
         pb.mode, pb.ploidy, pb.nsamples, pb.num_chrom = mode, ploidy, nsamples, n
         pb.n_packed_inds = n_packed_inds if n_packed_inds is not None else rows // (ploidy * nsamples)
-        pb.label_bytes = lb
+        pb.label_bytes = lb if lb is not None else 4
         pb.chrom = carr
         pb.num_inds = ids.size // n
         pb.ind_rows = ids.ctypes.data

@@ -75,6 +75,9 @@ int Engine::set_option(const char *key, double v) {
     else if (k == "ranges") opt.ranges = iv;
     else if (k == "null_slab_bins") opt.null_slab_bins = iv;
     else if (k == "split_ready") opt.split_ready = iv;
+    else if (k == "rand_impl") opt.rand_impl = iv;
+    else if (k == "match_impl") opt.match_impl = iv;
+    else if (k == "cache_mb") opt.cache_mb = v;
     else return FGT_ERR_ARG;
     return FGT_OK;
 }
@@ -102,6 +105,9 @@ double Engine::get_option(const char *key) {
     if (k == "ranges") return opt.ranges;
     if (k == "null_slab_bins") return opt.null_slab_bins;
     if (k == "split_ready") return opt.split_ready;
+    if (k == "rand_impl") return opt.rand_impl;
+    if (k == "match_impl") return opt.match_impl;
+    if (k == "cache_mb") return opt.cache_mb;
     return NAN;
 }
 
@@ -131,6 +137,10 @@ int Engine::ensure_init() {
     uint32_t *dt = d_level_tab_.as<uint32_t>(level_tab_.size());
     if (!dt) return FGT_ERR_CUDA;
     CK(cudaMemcpy(dt, level_tab_.data(), level_tab_.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (jump_tab_.empty()) jump_tab_ = build_jump_table();
+    uint32_t *dj = d_jump_tab_.as<uint32_t>(jump_tab_.size());
+    if (!dj) return FGT_ERR_CUDA;
+    CK(cudaMemcpy(dj, jump_tab_.data(), jump_tab_.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     if (!d_err_.as<int>(4) || !d_accepted_.as<unsigned long long>(2)) return FGT_ERR_CUDA;
     inited_ = true;
     init_rc_ = FGT_OK;
@@ -152,6 +162,7 @@ static int err_to_code(int bits) {
     if (bits & kErrMissingDonor) return FGT_ERR_MISSING_DONOR;
     if (bits & kErrLabelRange) return FGT_ERR_LABEL_RANGE;
     if (bits & kErrMode3Target) return FGT_ERR_MODE3_TARGET;
+    if (bits & kErrBadRuns) return FGT_ERR_ARG;
     if (bits) return FGT_ERR_CUDA;
     return FGT_OK;
 }
@@ -246,8 +257,8 @@ Engine::SlabPlan Engine::make_slab_plan(int G, int grid_start, double bw, int W,
 // grouped rows_per_ind at a time into n_groups "individuals" (data_read) -- or, for the NULL path,
 // one row per haplotype and no binning.
 // ---------------------------------------------------------------------------------------------
-int Engine::prep_chromosome(const fgt_problem_t &pb, int h, const int32_t *rowmap_dev, int rows, int rows_per_ind,
-                            int n_groups, bool for_null, ChromState &cs, fgt_stats_t &stx) {
+int Engine::prep_chromosome(const fgt_problem_t &pb, int h, const int32_t *rowmap_dev, const int32_t *rowmap_host, int rows,
+                            int rows_per_ind, int n_groups, bool for_null, ChromState &cs, fgt_stats_t &stx) {
     const fgt_chrom_t &c = pb.chrom[h];
     const int L = c.nsites;
     if (L <= 0) return FGT_ERR_ARG;
@@ -267,35 +278,101 @@ int Engine::prep_chromosome(const fgt_problem_t &pb, int h, const int32_t *rowma
     CK(cudaMemcpyAsync(d_cum, cum.data(), L * sizeof(double), cudaMemcpyHostToDevice, st_));
     CK(cudaMemcpyAsync(d_inc, inc.data(), L * sizeof(double), cudaMemcpyHostToDevice, st_));
     stx.h2d_bytes += 2LL * L * sizeof(double);
-    const void *d_lab = c.labels;
-    if (!c.labels_on_device) {
-        size_t bytes = (size_t)pb.n_packed_inds * pb.ploidy * pb.nsamples * L * pb.label_bytes;
-        void *buf = d_labels_.get(bytes);
-        if (!buf) return FGT_ERR_CUDA;
-        CK(cudaMemcpyAsync(buf, c.labels, bytes, cudaMemcpyHostToDevice, st_));
-        stx.h2d_bytes += (int64_t)bytes;
-        d_lab = buf;
-    }
-    int32_t *d_counts = d_counts_.as<int32_t>((size_t)rows * chunk_tiles_for(L)), *d_rowoff = d_rowoff_.as<int32_t>(rows + 1);
+    int32_t *d_rowoff = d_rowoff_.as<int32_t>(rows + 1);
     int32_t *d_rowsum = d_segoff_.as<int32_t>(rows);
-    if (!d_counts || !d_rowoff || !d_rowsum) return FGT_ERR_CUDA;
-    launch_chunk_count(d_lab, rowmap_dev, pb.label_bytes, L, rows, pb.weight_min, d_counts, d_rowsum, st_);
-    launch_chunk_scan(d_rowsum, d_rowoff, rows, st_);
-    launches_ += 2;
+    if (!d_rowoff || !d_rowsum) return FGT_ERR_CUDA;
     int32_t total_chunks = 0;
-    CK(cudaMemcpyAsync(&total_chunks, d_rowoff + rows, sizeof(int32_t), cudaMemcpyDeviceToHost, st_));
-    // the copies above read host vectors that die at scope exit: synchronise here (also yields total_chunks)
-    CK(cudaStreamSynchronize(st_));
-    stx.d2h_bytes += 4;
-    if (total_chunks <= 0) return FGT_ERR_ARG;
+    double *d_cstart = nullptr, *d_cend = nullptr;
+    int32_t *d_chap = nullptr;
+    if (c.runs) {
+        // run-length-encoded paintings: gather the selected rows' runs (host rows are compacted into one upload)
+        if (!c.run_off) return FGT_ERR_ARG;
+        const long long rows_all = (long long)pb.n_packed_inds * pb.ploidy * pb.nsamples;
+        std::vector<long long> src(rows);
+        std::vector<int32_t> cnt(rows), roff(rows + 1);
+        std::vector<fgt_run_t> stage;
+        long long acc = 0;
+        roff[0] = 0;
+        for (int r = 0; r < rows; r++) {
+            const long long rr = rowmap_host ? rowmap_host[r] : r;
+            if (rr < 0 || rr >= rows_all) return FGT_ERR_ARG;
+            const long long b0 = c.run_off[rr], e0 = c.run_off[rr + 1];
+            if (e0 <= b0 || b0 < 0) return FGT_ERR_ARG;
+            cnt[r] = (int32_t)(e0 - b0);
+            if (c.runs_on_device) src[r] = b0;
+            else { src[r] = (long long)stage.size(); stage.insert(stage.end(), c.runs + b0, c.runs + e0); }
+            acc += e0 - b0;
+            if (acc > 0x7fffffffLL) return FGT_ERR_ARG;
+            roff[r + 1] = (int32_t)acc;
+        }
+        long long *d_src = cs.run_src.as<long long>(rows);
+        int32_t *d_cnt = cs.run_cnt.as<int32_t>(rows);
+        if (!d_src || !d_cnt) return FGT_ERR_CUDA;
+        const fgt_run_t *d_runs = c.runs;
+        if (!c.runs_on_device) {
+            void *buf = d_labels_.get(stage.size() * sizeof(fgt_run_t));
+            if (!buf) return FGT_ERR_CUDA;
+            CK(cudaMemcpyAsync(buf, stage.data(), stage.size() * sizeof(fgt_run_t), cudaMemcpyHostToDevice, st_));
+            stx.h2d_bytes += (int64_t)(stage.size() * sizeof(fgt_run_t));
+            d_runs = (const fgt_run_t *)buf;
+        }
+        CK(cudaMemcpyAsync(d_src, src.data(), rows * sizeof(long long), cudaMemcpyHostToDevice, st_));
+        CK(cudaMemcpyAsync(d_cnt, cnt.data(), rows * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
+        stx.h2d_bytes += (int64_t)rows * 12;
+        const bool simple = pb.weight_min < 1.0;
+        if (simple) {
+            CK(cudaMemcpyAsync(d_rowoff, roff.data(), (rows + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
+            total_chunks = (int32_t)acc;
+        } else {
+            launch_chunk_seq_runs(false, d_runs, d_src, d_cnt, rows, L, pb.weight_min, d_rowsum, nullptr, nullptr, nullptr, nullptr,
+                                  nullptr, nullptr, d_err_.as<int>(4), st_);
+            launch_chunk_scan(d_rowsum, d_rowoff, rows, st_);
+            launches_ += 2;
+            CK(cudaMemcpyAsync(&total_chunks, d_rowoff + rows, sizeof(int32_t), cudaMemcpyDeviceToHost, st_));
+            stx.d2h_bytes += 4;
+        }
+        CK(cudaStreamSynchronize(st_));                 // the staging vectors die at scope exit
+        if (total_chunks <= 0) return FGT_ERR_ARG;
+        d_cstart = d_cstart_.as<double>(total_chunks); d_cend = d_cend_.as<double>(total_chunks);
+        d_chap = d_chap_.as<int32_t>(total_chunks);
+        if (!d_cstart || !d_cend || !d_chap) return FGT_ERR_CUDA;
+        if (simple)
+            launch_chunks_from_runs(d_runs, d_src, d_rowoff, rows, total_chunks, L, d_cum, d_inc, d_cstart, d_cend, d_chap,
+                                    d_err_.as<int>(4), st_);
+        else
+            launch_chunk_seq_runs(true, d_runs, d_src, d_cnt, rows, L, pb.weight_min, nullptr, d_rowoff, d_cum, d_inc, d_cstart,
+                                  d_cend, d_chap, d_err_.as<int>(4), st_);
+        launches_ += 1;
+    } else {
+        const void *d_lab = c.labels;
+        if (!d_lab) return FGT_ERR_ARG;
+        if (!c.labels_on_device) {
+            size_t bytes = (size_t)pb.n_packed_inds * pb.ploidy * pb.nsamples * L * pb.label_bytes;
+            void *buf = d_labels_.get(bytes);
+            if (!buf) return FGT_ERR_CUDA;
+            CK(cudaMemcpyAsync(buf, c.labels, bytes, cudaMemcpyHostToDevice, st_));
+            stx.h2d_bytes += (int64_t)bytes;
+            d_lab = buf;
+        }
+        int32_t *d_counts = d_counts_.as<int32_t>((size_t)rows * chunk_tiles_for(L));
+        if (!d_counts) return FGT_ERR_CUDA;
+        launch_chunk_count(d_lab, rowmap_dev, pb.label_bytes, L, rows, pb.weight_min, d_counts, d_rowsum, st_);
+        launch_chunk_scan(d_rowsum, d_rowoff, rows, st_);
+        launches_ += 2;
+        CK(cudaMemcpyAsync(&total_chunks, d_rowoff + rows, sizeof(int32_t), cudaMemcpyDeviceToHost, st_));
+        // the copies above read host vectors that die at scope exit: synchronise here (also yields total_chunks)
+        CK(cudaStreamSynchronize(st_));
+        stx.d2h_bytes += 4;
+        if (total_chunks <= 0) return FGT_ERR_ARG;
+        d_cstart = d_cstart_.as<double>(total_chunks); d_cend = d_cend_.as<double>(total_chunks);
+        d_chap = d_chap_.as<int32_t>(total_chunks);
+        if (!d_cstart || !d_cend || !d_chap) return FGT_ERR_CUDA;
+        launch_chunk_emit(d_lab, rowmap_dev, pb.label_bytes, L, rows, pb.weight_min, d_counts, d_rowoff, d_cum, d_inc, d_cstart, d_cend,
+                          d_chap, st_);
+        launches_ += 1;
+    }
     cs.n_chunks = total_chunks;
     stx.chunks += total_chunks;
-    double *d_cstart = d_cstart_.as<double>(total_chunks), *d_cend = d_cend_.as<double>(total_chunks);
-    int32_t *d_chap = d_chap_.as<int32_t>(total_chunks);
-    if (!d_cstart || !d_cend || !d_chap) return FGT_ERR_CUDA;
-    launch_chunk_emit(d_lab, rowmap_dev, pb.label_bytes, L, rows, pb.weight_min, d_counts, d_rowoff, d_cum, d_inc, d_cstart, d_cend,
-                      d_chap, st_);
-    launches_ += 1;
     Chunk *d_sorted = cs.sorted.as<Chunk>(total_chunks);
     if (!d_sorted) return FGT_ERR_CUDA;
     const int K = pb.num_donors;
@@ -366,23 +443,35 @@ static bool resolve_walk(const int32_t *ids, int stride, int N, int n_packed, st
 // ---------------------------------------------------------------------------------------------
 int Engine::prep_block(const fgt_problem_t &pb, int h, int p0, int p1, int blk, const void *d_lab, cudaEvent_t copy_done,
                        ChromState &cs, fgt_stats_t &stx) {
-    const int L = pb.chrom[h].nsites;
+    const fgt_chrom_t &c = pb.chrom[h];
+    const int L = c.nsites;
     const int PM = pb.ploidy * pb.nsamples;
     const int np = p1 - p0, rows = np * PM;
     const int K = pb.num_donors;
     cudaStream_t sp = st_prep_;
-    const char *lab_blk = (const char *)d_lab + (size_t)p0 * PM * L * pb.label_bytes;
-    if (!(count_pending_ && count_key_[0] == h && count_key_[1] == p0 && count_key_[2] == p1)) {
-        int rc = prep_count(pb, h, p0, p1, d_lab, copy_done);
-        if (rc) return rc;
+    const bool use_runs = c.runs != nullptr;
+    const bool simple_runs = use_runs && pb.weight_min < 1.0;     // chunk == run: offsets and totals are known on the host
+    const size_t r0 = (size_t)p0 * PM;
+    const int32_t *row_off_dev = nullptr;
+    int32_t total_chunks = 0;
+    if (!pin_small_ && cudaHostAlloc((void **)&pin_small_, 64, cudaHostAllocDefault) != cudaSuccess) return FGT_ERR_CUDA;
+    if (simple_runs) {
+        if (copy_done) CK(cudaStreamWaitEvent(sp, copy_done, 0));
+        total_chunks = (int32_t)(c.run_off[r0 + rows] - c.run_off[r0]);
+        row_off_dev = (const int32_t *)cs.run_rowoff.p + r0 + blk;
+    } else {
+        if (!(count_pending_ && count_key_[0] == h && count_key_[1] == p0 && count_key_[2] == p1)) {
+            int rc = prep_count(pb, h, p0, p1, d_lab, copy_done);
+            if (rc) return rc;
+        }
+        count_pending_ = false;
+        vtick("  prep: waiting for the chunk count");
+        CK(cudaStreamSynchronize(sp));
+        vtick("  prep: chunk count known");
+        total_chunks = *pin_small_;
+        stx.d2h_bytes += 4;
+        row_off_dev = (const int32_t *)d_rowoff_.p;
     }
-    count_pending_ = false;
-    int32_t *d_rowoff = (int32_t *)d_rowoff_.p, *d_counts = (int32_t *)d_counts_.p;
-    vtick("  prep: waiting for the chunk count");
-    CK(cudaStreamSynchronize(sp));
-    vtick("  prep: chunk count known");
-    const int32_t total_chunks = *pin_small_;
-    stx.d2h_bytes += 4;
     if (total_chunks <= 0) return FGT_ERR_ARG;
     cs.n_chunks += total_chunks;
     stx.chunks += total_chunks;
@@ -392,8 +481,20 @@ int Engine::prep_block(const fgt_problem_t &pb, int h, int p0, int p1, int blk, 
     // 32-byte records, then the compact (pos, size) / label copies phase 1 gathers from (k_bin_sort)
     Chunk *d_sorted = (Chunk *)cs.sorted_blocks[blk].get((size_t)total_chunks * (sizeof(Chunk) + sizeof(double2) + sizeof(int32_t)));
     if (!d_cstart || !d_cend || !d_chap || !d_sorted) return FGT_ERR_CUDA;
-    launch_chunk_emit(lab_blk, nullptr, pb.label_bytes, L, rows, pb.weight_min, d_counts, d_rowoff, (const double *)cs.cum.p,
-                      (const double *)cs.inc.p, d_cstart, d_cend, d_chap, sp);
+    if (use_runs) {
+        const fgt_run_t *d_runs = (const fgt_run_t *)d_lab;
+        const long long *d_src = (const long long *)cs.run_src.p + r0;
+        if (simple_runs)
+            launch_chunks_from_runs(d_runs, d_src, row_off_dev, rows, total_chunks, L, (const double *)cs.cum.p, (const double *)cs.inc.p,
+                                    d_cstart, d_cend, d_chap, (int *)d_err_.p, sp);
+        else
+            launch_chunk_seq_runs(true, d_runs, d_src, (const int32_t *)cs.run_cnt.p + r0, rows, L, pb.weight_min, nullptr, row_off_dev,
+                                  (const double *)cs.cum.p, (const double *)cs.inc.p, d_cstart, d_cend, d_chap, (int *)d_err_.p, sp);
+    } else {
+        const char *lab_blk = (const char *)d_lab + (size_t)p0 * PM * L * pb.label_bytes;
+        launch_chunk_emit(lab_blk, nullptr, pb.label_bytes, L, rows, pb.weight_min, (const int32_t *)d_counts_.p, row_off_dev,
+                          (const double *)cs.cum.p, (const double *)cs.inc.p, d_cstart, d_cend, d_chap, sp);
+    }
     const int nb = cs.nb, W = cs.W;
     size_t cm = (size_t)np * PM * nb;
     int32_t *d_cnt = d_cntmat_.as<int32_t>(cm), *d_rf = d_runfirst_.as<int32_t>(cm);
@@ -401,7 +502,7 @@ int Engine::prep_block(const fgt_problem_t &pb, int h, int p0, int p1, int blk, 
     long long *d_tot = d_totals_.as<long long>(np);
     if (!d_tot) return FGT_ERR_CUDA;
     CK(cudaMemsetAsync(d_cnt, 0, cm * sizeof(int32_t), sp));
-    launch_bin_sort(np, PM, d_rowoff, d_cstart, d_cend, d_chap, (const int32_t *)d_donor_.p, pb.n_donor_labels,
+    launch_bin_sort(np, PM, row_off_dev, d_cstart, d_cend, d_chap, (const int32_t *)d_donor_.p, pb.n_donor_labels,
                     pb.gridweight_max_cutoff, K, pb.mode, nb, W, (const double *)cs.etab.p, pb.mode == 3 ? 8.0 : 10.0, d_sorted,
                     total_chunks, (const Chunk **)cs.chunk_ptr.p + p0, (const double2 **)cs.ps_ptr.p + p0,
                     (const int32_t **)cs.pop_ptr.p + p0, (int32_t *)cs.t.p + (size_t)p0 * nb, (int32_t *)cs.first.p + (size_t)p0 * nb,
@@ -409,9 +510,59 @@ int Engine::prep_block(const fgt_problem_t &pb, int h, int p0, int p1, int blk, 
                     (int *)d_err_.p, d_tot, sp);
     launches_ += 2;
     CK(cudaMemcpyAsync(cs.totals.data() + p0, d_tot, np * sizeof(long long), cudaMemcpyDeviceToHost, sp));
+    if (use_runs) CK(cudaMemcpyAsync(pin_small_ + 1, d_err_.p, sizeof(int), cudaMemcpyDeviceToHost, sp));
     vtick("  prep: emit + bin sort enqueued");
     CK(cudaStreamSynchronize(sp));
     stx.d2h_bytes += (int64_t)np * 8;
+    if (use_runs && (pin_small_[1] & kErrBadRuns)) return FGT_ERR_ARG;     // malformed runs: nothing is accumulated
+    return FGT_OK;
+}
+
+// Per-row tables of a run-length-encoded chromosome, built in pinned memory and uploaded once: where each row's runs
+// start, how many it has, and -- per block of individuals -- the chunk offsets of its rows (for weight_min < 1 a chunk
+// is a run, so nothing has to be counted on the device).
+int Engine::setup_runs(const fgt_problem_t &pb, int h, int n_blocks, ChromState &cs) {
+    const fgt_chrom_t &c = pb.chrom[h];
+    const int PM = pb.ploidy * pb.nsamples, n_phys = pb.n_packed_inds;
+    const size_t rows = (size_t)n_phys * PM;
+    if (!c.run_off || n_blocks <= 0) return FGT_ERR_ARG;
+    const size_t need = rows * sizeof(long long) + (rows + n_blocks) * sizeof(int32_t) + rows * sizeof(int32_t);
+    CK(cudaStreamSynchronize(st_aux_));                      // the previous chromosome's upload from this staging area
+    if (pin_rows_cap_ < need) {
+        if (pin_rows_) cudaFreeHost(pin_rows_);
+        pin_rows_ = nullptr; pin_rows_cap_ = 0;
+        if (cudaHostAlloc(&pin_rows_, need + need / 4 + 64, cudaHostAllocDefault) != cudaSuccess) return FGT_ERR_CUDA;
+        pin_rows_cap_ = need + need / 4;
+    }
+    long long *src = (long long *)pin_rows_;
+    int32_t *roff = (int32_t *)(src + rows);
+    int32_t *cnt = roff + rows + n_blocks;
+    for (size_t r = 0; r < rows; r++) {
+        const long long b0 = c.run_off[r], e0 = c.run_off[r + 1];
+        if (b0 < 0 || e0 <= b0 || e0 - b0 > (long long)c.nsites) return FGT_ERR_ARG;
+        src[r] = b0;
+        cnt[r] = (int32_t)(e0 - b0);
+    }
+    for (int b = 0; b < n_blocks; b++) {
+        const size_t r0 = (size_t)((long long)n_phys * b / n_blocks) * PM, r1 = (size_t)((long long)n_phys * (b + 1) / n_blocks) * PM;
+        int32_t *base = roff + r0 + b;
+        long long acc = 0;
+        base[0] = 0;
+        for (size_t r = r0; r < r1; r++) {
+            acc += cnt[r];
+            if (acc > 0x7fffffffLL) return FGT_ERR_ARG;
+            base[r - r0 + 1] = (int32_t)acc;
+        }
+    }
+    long long *d_src = cs.run_src.as<long long>(rows);
+    int32_t *d_roff = cs.run_rowoff.as<int32_t>(rows + n_blocks), *d_cnt = cs.run_cnt.as<int32_t>(rows);
+    if (!d_src || !d_roff || !d_cnt) return FGT_ERR_CUDA;
+    CK(cudaMemcpyAsync(d_src, src, rows * sizeof(long long), cudaMemcpyHostToDevice, st_aux_));
+    CK(cudaMemcpyAsync(d_roff, roff, (rows + n_blocks) * sizeof(int32_t), cudaMemcpyHostToDevice, st_aux_));
+    CK(cudaMemcpyAsync(d_cnt, cnt, rows * sizeof(int32_t), cudaMemcpyHostToDevice, st_aux_));
+    if (!rows_ready_) CK(cudaEventCreateWithFlags(&rows_ready_, cudaEventDisableTiming));
+    CK(cudaEventRecord(rows_ready_, st_aux_));
+    CK(cudaStreamWaitEvent(st_prep_, rows_ready_, 0));
     return FGT_OK;
 }
 
@@ -424,17 +575,28 @@ void Engine::vtick(const char *what) const {
 // First step of prep_block, separately launchable: count the chunks of the block's rows, scan, and start the
 // read-back of the total (pinned), so that host-side work can run while the labels stream through the count kernel.
 int Engine::prep_count(const fgt_problem_t &pb, int h, int p0, int p1, const void *d_lab, cudaEvent_t copy_done) {
-    const int L = pb.chrom[h].nsites;
+    const fgt_chrom_t &c = pb.chrom[h];
+    const int L = c.nsites;
     const int PM = pb.ploidy * pb.nsamples;
     const int rows = (p1 - p0) * PM;
     cudaStream_t sp = st_prep_;
     if (!pin_small_ && cudaHostAlloc((void **)&pin_small_, 64, cudaHostAllocDefault) != cudaSuccess) return FGT_ERR_CUDA;
     if (copy_done) CK(cudaStreamWaitEvent(sp, copy_done, 0));
-    const char *lab_blk = (const char *)d_lab + (size_t)p0 * PM * L * pb.label_bytes;
-    int32_t *d_counts = d_counts_.as<int32_t>((size_t)rows * chunk_tiles_for(L)), *d_rowoff = d_rowoff_.as<int32_t>(rows + 1);
+    int32_t *d_rowoff = d_rowoff_.as<int32_t>(rows + 1);
     int32_t *d_rowsum = d_segoff_.as<int32_t>(rows);
-    if (!d_counts || !d_rowoff || !d_rowsum) return FGT_ERR_CUDA;
-    launch_chunk_count(lab_blk, nullptr, pb.label_bytes, L, rows, pb.weight_min, d_counts, d_rowsum, sp);
+    if (!d_rowoff || !d_rowsum) return FGT_ERR_CUDA;
+    if (c.runs) {
+        // general weight_min rule on run-length-encoded rows (needs the per-row tables of setup_runs)
+        const size_t r0 = (size_t)p0 * PM;
+        launch_chunk_seq_runs(false, (const fgt_run_t *)d_lab, (const long long *)chroms_[h].run_src.p + r0,
+                              (const int32_t *)chroms_[h].run_cnt.p + r0, rows, L, pb.weight_min, d_rowsum, nullptr, nullptr, nullptr,
+                              nullptr, nullptr, nullptr, (int *)d_err_.p, sp);
+    } else {
+        const char *lab_blk = (const char *)d_lab + (size_t)p0 * PM * L * pb.label_bytes;
+        int32_t *d_counts = d_counts_.as<int32_t>((size_t)rows * chunk_tiles_for(L));
+        if (!d_counts) return FGT_ERR_CUDA;
+        launch_chunk_count(lab_blk, nullptr, pb.label_bytes, L, rows, pb.weight_min, d_counts, d_rowsum, sp);
+    }
     launch_chunk_scan(d_rowsum, d_rowoff, rows, sp);
     launches_ += 2;
     CK(cudaMemcpyAsync(pin_small_, d_rowoff + rows, sizeof(int32_t), cudaMemcpyDeviceToHost, sp));
@@ -488,13 +650,46 @@ int Engine::setup_chromosome(const fgt_problem_t &pb, int h, ChromState &cs, fgt
     return FGT_OK;
 }
 
+// everything the kept chunk/bin tables depend on (reuse_prep): paintings, map, mode constants, chunking options
+long long Engine::prep_sig(const fgt_problem_t &pb) const {
+    unsigned long long hsh = 1469598103934665603ULL;
+    auto mix = [&](unsigned long long v) { hsh ^= v; hsh *= 1099511628211ULL; };
+    auto mixd = [&](double d) { unsigned long long b; std::memcpy(&b, &d, sizeof b); mix(b); };
+    mix((unsigned long long)pb.mode); mix((unsigned long long)pb.ploidy); mix((unsigned long long)pb.nsamples);
+    mix((unsigned long long)pb.num_chrom); mix((unsigned long long)pb.n_packed_inds); mix((unsigned long long)pb.label_bytes);
+    mix((unsigned long long)pb.num_bins); mix((unsigned long long)pb.num_donors); mix((unsigned long long)pb.n_donor_labels);
+    mixd(pb.binwidth); mixd(pb.weight_min); mixd(pb.gridweight_max_cutoff);
+    for (int i = 0; i < pb.n_donor_labels; i++) mix((unsigned long long)(unsigned)pb.donor_label_vec[i]);
+    for (int h = 0; h < pb.num_chrom; h++) {
+        const fgt_chrom_t &c = pb.chrom[h];
+        mix((unsigned long long)c.nsites); mix((unsigned long long)(uintptr_t)c.labels); mix((unsigned long long)(uintptr_t)c.runs);
+        mix((unsigned long long)(uintptr_t)c.run_off); mix((unsigned long long)(uintptr_t)c.pos); mix((unsigned long long)(uintptr_t)c.rate);
+        if (c.nsites > 0 && c.pos && c.rate) { mixd(c.pos[0]); mixd(c.pos[c.nsites - 1]); mixd(c.rate[0]); mixd(c.rate[c.nsites / 2]); }
+    }
+    return (long long)(hsh | 1ULL);
+}
+
 int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t *stats, int64_t *count_only) {
+    const int rc = data_read_packed_impl(pb, means, stats, count_only);
+    if (rc != FGT_OK && rc != FGT_ERR_NO_DEVICE) {
+        // an error return may leave work of earlier blocks in flight on the library's streams: drain it before the
+        // caller (or the next call) touches the buffers again
+        cudaDeviceSynchronize();
+        cudaGetLastError();
+    }
+    return rc;
+}
+
+int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_stats_t *stats, int64_t *count_only) {
     int rc = ensure_init();
     if (rc) return rc;
     if ((pb.mode != 1 && pb.mode != 3) || pb.ploidy <= 0 || pb.nsamples <= 0 || pb.num_chrom <= 0 || pb.num_inds <= 0 ||
-        pb.n_packed_inds <= 0 || (pb.label_bytes != 2 && pb.label_bytes != 4) || pb.num_bins <= 0 || pb.num_donors <= 0 ||
-        pb.num_surrogates <= 0 || !(pb.binwidth > 0))
+        pb.n_packed_inds <= 0 || pb.num_bins <= 0 || pb.num_donors <= 0 || pb.num_surrogates <= 0 || !(pb.binwidth > 0) || !pb.chrom)
         return FGT_ERR_ARG;
+    for (int h = 0; h < pb.num_chrom; h++) {
+        const fgt_chrom_t &c = pb.chrom[h];
+        if (c.runs ? !c.run_off : (!c.labels || (pb.label_bytes != 2 && pb.label_bytes != 4))) return FGT_ERR_ARG;
+    }
     CK(cudaSetDevice(opt.device));
     fgt_stats_t stx{};
     launches_ = 0;
@@ -518,13 +713,17 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
     CK(cudaStreamSynchronize(st_));       // donor labels / cleared flags are visible to the other streams
     tick("donor labels up");
 
+    // reuse_prep (one-shot): keep the chunk/bin tables of the previous call -- only if this call describes the very same
+    // paintings and sampling schedule (otherwise fall back to a full preparation)
+    const long long sig = prep_sig(pb);
     const bool reuse = opt.reuse_prep && (int)chroms_.size() == Cn && !chroms_.empty() && chroms_[0].nb > 0 &&
-                       (int)chroms_[0].totals.size() == n_phys;
+                       (int)chroms_[0].totals.size() == n_phys && sig == prep_sig_;
     opt.reuse_prep = 0;
+    prep_sig_ = sig;
     // device-resident paintings: the first chromosome's chunk count needs nothing but the labels -- start it before
     // the per-call tables are built and uploaded
     count_pending_ = false;
-    if (!reuse && pb.chrom[0].labels_on_device && pb.chrom[0].nsites > 0) {
+    if (!reuse && !pb.chrom[0].runs && pb.chrom[0].labels && pb.chrom[0].labels_on_device && pb.chrom[0].nsites > 0) {
         const int nb0 = opt.blocks > 0 ? std::min(n_phys, opt.blocks) : 1;
         rc = prep_count(pb, 0, 0, (int)((long long)n_phys * 1 / nb0), pb.chrom[0].labels, nullptr);
         if (rc) return rc;
@@ -571,8 +770,11 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
     long long *d_pairbase = nullptr;
     int32_t *d_physof = nullptr;
     uint32_t *d_hist = nullptr;
-    bool tile_in_smem = false, memset_tensor = true;
+    bool tile_in_smem = false, memset_tensor = true, relaxed = false;
     int plan_max_w = 1, nd_max = 1;
+    const bool fused_rng = opt.rand_impl != 0;       // draws generated inside the evaluation kernel (two-phase / relaxed only)
+    long long *d_recbase = nullptr;
+    uint32_t *d_h0 = nullptr;
     const bool want_raw = opt.keep_raw != 0;
     raw_count_ = 0;
     if (!count_only) {
@@ -598,7 +800,7 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
             const size_t nbytes = tw_bytes;
             tw_stage = std::async(std::launch::async, [dst, src, nbytes]() { std::memcpy(dst, src, nbytes); });
             tw_pending = true;
-        } else if (pb.chrom[0].labels_on_device) {
+        } else if (pb.chrom[0].runs ? pb.chrom[0].runs_on_device : pb.chrom[0].labels_on_device) {
             tw_pending = true;                 // small table: copied straight from the caller's buffer, also just before the projection
         } else {
             // host-resident paintings: now, before the label copies occupy the host-to-device copy engine
@@ -618,19 +820,23 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
                 if (s.dhi - s.dlo + 1 > 32) impl = 1;      // the commit kernel keeps one separation per lane
             if (plan.n_slots > kMaxSlots) impl = 1;
         }
+        // relaxed mode (opt-in, "strict" = 0): the evaluation kernel adds straight into the tensor with fp64 atomics
+        relaxed = !opt.strict && impl != 1;
         if (impl == 1) slabs = make_slabs(G, pb.grid_start, pb.binwidth, W0, N);
         for (const SlabDesc &s : slabs) {
             plan_max_w = std::max(plan_max_w, s.b1 - s.b0 + 1);
             nd_max = std::max(nd_max, s.dhi - s.dlo + 1);
         }
-        if (impl != 1) tile_in_smem = commit_tile_bytes(K, plan_max_w) + 7168 <= 200 * 1024;
+        if (impl != 1 && !relaxed) tile_in_smem = commit_tile_bytes(K, plan_max_w) + 7168 <= 200 * 1024;
         memset_tensor = !tile_in_smem;            // smem tiles start from zero and overwrite every cell
         if (memset_tensor) CK(cudaMemsetAsync(d_tensor, 0, tens_elems * sizeof(double), st_));
         d_slabs = d_slabs_.as<SlabDesc>(slabs.size());
         d_pairbase = d_pairbase_.as<long long>((size_t)Cn * N);
         d_physof = d_physof_.as<int32_t>((size_t)Cn * N);
-        d_hist = d_hist_.as<uint32_t>(((size_t)Cn * N + 1) * kLag);
-        if (!d_slabs || !d_pairbase || !d_physof || !d_hist) return FGT_ERR_CUDA;
+        d_hist = d_hist_.as<uint32_t>(((size_t)Cn * N + 2) * kLag + 1);
+        d_recbase = d_recbase_.as<long long>((size_t)Cn * N);
+        if (!d_slabs || !d_pairbase || !d_physof || !d_hist || !d_recbase) return FGT_ERR_CUDA;
+        d_h0 = d_hist + ((size_t)Cn * N + 1) * kLag;       // the generator state at call entry (fused generator)
         CK(cudaMemcpyAsync(d_slabs, slabs.data(), slabs.size() * sizeof(SlabDesc), cudaMemcpyHostToDevice, st_));
         if (impl != 1) {
             d_firstslab = d_firstslab_.as<int32_t>(W0);
@@ -657,7 +863,8 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
             free_b += d_draws_.cap + d_recs_.cap;                // our own grow-only buffers are reusable
             mem_budget_bytes_ = std::min((double)free_b * 0.6, 64e9);
         }
-        budget_pairs = (long long)(mem_budget_bytes_ / 2 / (8.0 + 16.0 * ns_rec));   // two lanes hold a batch each
+        const bool use_fused = fused_rng && impl != 1;
+        budget_pairs = (long long)(mem_budget_bytes_ / 2 / ((use_fused ? 0.0 : 8.0) + (relaxed ? 1.0 : 16.0 * ns_rec)));   // two lanes hold a batch each
     }
     tick("tables ready");
 
@@ -669,7 +876,7 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
     long long run = 0, my_pairs = 0;             // running stream position / pairs of this call
     size_t hist_used = 0;
     // per-range tables go through pinned staging (a pageable async copy would make the host wait for the stream)
-    const size_t stage_need = (size_t)Cn * N * (sizeof(long long) + sizeof(int32_t)) + ((size_t)Cn * N + 1) * kLag * sizeof(uint32_t);
+    const size_t stage_need = (size_t)Cn * N * (2 * sizeof(long long) + sizeof(int32_t)) + ((size_t)Cn * N + 2) * kLag * sizeof(uint32_t);
     if (!count_only && pinned_cap_ < stage_need) {
         if (pinned_) cudaFreeHost(pinned_);
         pinned_ = nullptr; pinned_cap_ = 0;
@@ -677,7 +884,8 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
         pinned_cap_ = stage_need;
     }
     long long *pin_pairbase = (long long *)pinned_;
-    int32_t *pin_physof = (int32_t *)(pin_pairbase + (size_t)Cn * N);
+    long long *pin_recbase = pin_pairbase + (size_t)Cn * N;
+    int32_t *pin_physof = (int32_t *)(pin_recbase + (size_t)Cn * N);
     uint32_t *pin_hist = (uint32_t *)(pin_physof + (size_t)Cn * N);
     std::vector<cudaEvent_t> evs;
     auto new_event = [&]() { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); evs.push_back(e); return e; };
@@ -707,7 +915,12 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
                                  pb.ploidy) * 1009 + pb.num_bins * 4 + pb.mode;
     if (shape_sig != last_shape_sig_) last_first_batch_threads_ = 0;     // only repeat calls of one problem shape speculate
     last_shape_sig_ = shape_sig;
-    if (!count_only && opt.spec_rand && last_first_batch_threads_ >= 256) {
+    if (!count_only && fused_rng && impl != 1) {
+        uint32_t *pin_h0 = pin_hist + ((size_t)Cn * N + 1) * kLag;
+        std::memcpy(pin_h0, h0.x, sizeof h0.x);
+        CK(cudaMemcpyAsync(d_h0, pin_h0, sizeof h0.x, cudaMemcpyHostToDevice, st_));
+    }
+    if (!count_only && opt.spec_rand && last_first_batch_threads_ >= 256 && !(fused_rng && impl != 1)) {
         const long long lo0 = pb.pair_offset ? pb.pair_offset[0] : 0;
         spec_A4 = (2 * lo0) & ~3LL;
         spec_threads = last_first_batch_threads_ & ~255LL;
@@ -724,17 +937,19 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
     }
     auto launch_range = [&](int h, int n0, int n1, cudaEvent_t ready) -> int {
         ChromState &cs = chroms_[h];
+        const bool fused = fused_rng && impl != 1;
         int n = n0;
         while (n < n1) {
             const int b0 = n;
             long long lo = -1, hi = 0, acc_pairs = 0;
-            std::vector<long long> abs_off;
+            std::vector<long long> abs_off, rel_off;
             while (n < n1) {
                 const long long c0 = cs.totals[used[h][n]];
                 if (n > b0 && acc_pairs + c0 > budget_pairs) break;
                 const long long a0 = pb.pair_offset ? pb.pair_offset[(size_t)h * N + n] : run;
                 run += c0; my_pairs += c0;
                 abs_off.push_back(a0);
+                rel_off.push_back(acc_pairs);
                 lo = (lo < 0) ? a0 : std::min(lo, a0);
                 hi = std::max(hi, a0 + c0);
                 acc_pairs += c0;
@@ -745,32 +960,46 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
             DevBuf &draws_buf = bi ? d_draws2_ : d_draws_;
             DevBuf &recs_buf = bi ? d_recs2_ : d_recs_;
             DevBuf &reg_buf = bi ? d_cnt2_ : d_cnt_;
-            const long long A4 = (2 * lo) & ~3LL;
-            const long long nthreads = (2 * hi - A4 + kRun - 1) / kRun;
+            // bulk stream: the batch's draws [A4, 2*hi) are generated into a buffer and indexed relative to it (records too);
+            // fused generator: stream positions stay absolute (the kernel jumps there), records are packed per batch
+            const long long A4 = fused ? 0 : ((2 * lo) & ~3LL);
+            const long long nthreads = fused ? 0 : (2 * hi - A4 + kRun - 1) / kRun;
+            const long long rec_pairs = fused ? acc_pairs : nthreads * (long long)kRun / 2;
             long long *hp = pin_pairbase + (size_t)h * N + b0;
+            long long *hr = pin_recbase + (size_t)h * N + b0;
             int32_t *hq = pin_physof + (size_t)h * N + b0;
-            for (int m = 0; m < Nb; m++) { hp[m] = abs_off[m] - A4 / 2; hq[m] = used[h][b0 + m]; }
-            History hh = apply_jump(poly_pow_E((uint64_t)A4), h0);
-            uint32_t *dh = d_hist + hist_used * kLag;
-            std::memcpy(pin_hist + hist_used * kLag, hh.x, sizeof hh.x);
+            for (int m = 0; m < Nb; m++) {
+                hp[m] = abs_off[m] - A4 / 2;
+                hr[m] = fused ? rel_off[m] : hp[m];
+                hq[m] = used[h][b0 + m];
+            }
             // ---- evaluation stream ----
             if (ready) CK(cudaStreamWaitEvent(st_, ready, 0));
             if (commit_done[bi]) CK(cudaStreamWaitEvent(st_, commit_done[bi], 0));     // this buffer set is free again
-            CK(cudaMemcpyAsync(dh, pin_hist + hist_used * kLag, sizeof hh.x, cudaMemcpyHostToDevice, st_));
-            hist_used++;
+            uint32_t *dh = d_hist + hist_used * kLag;
+            if (!fused) {
+                History hh = apply_jump(poly_pow_E((uint64_t)A4), h0);
+                std::memcpy(pin_hist + hist_used * kLag, hh.x, sizeof hh.x);
+                CK(cudaMemcpyAsync(dh, pin_hist + hist_used * kLag, sizeof hh.x, cudaMemcpyHostToDevice, st_));
+                hist_used++;
+            }
             CK(cudaMemcpyAsync(d_pairbase + (size_t)h * N + b0, hp, Nb * sizeof(long long), cudaMemcpyHostToDevice, st_));
+            CK(cudaMemcpyAsync(d_recbase + (size_t)h * N + b0, hr, Nb * sizeof(long long), cudaMemcpyHostToDevice, st_));
             CK(cudaMemcpyAsync(d_physof + (size_t)h * N + b0, hq, Nb * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
-            uint32_t *d_draws = draws_buf.as<uint32_t>((size_t)nthreads * kRun + 4 + kDrawSlack);
-            if (!d_draws) return FGT_ERR_CUDA;
+            uint32_t *d_draws = nullptr;
             if (!first_eval) { first_eval = new_timed_event(); CK(cudaEventRecord(first_eval, st_)); }
-            long long have = 0;                       // runs already generated speculatively for this very range
-            if (batch_seq == 0 && spec_threads > 0 && A4 == spec_A4 && d_draws == spec_ptr) have = std::min(spec_threads, nthreads & ~255LL);
-            if (batch_seq == 0) last_first_batch_threads_ = nthreads;
-            if (have < nthreads) {
-                span_begin(0, st_);
-                launch_rand_fill(dh, (const uint32_t *)d_level_tab_.p, d_draws, nthreads, st_, have);
-                launches_ += 1;
-                span_end(st_);
+            if (!fused) {
+                d_draws = draws_buf.as<uint32_t>((size_t)nthreads * kRun + 4 + kDrawSlack);
+                if (!d_draws) return FGT_ERR_CUDA;
+                long long have = 0;                       // runs already generated speculatively for this very range
+                if (batch_seq == 0 && spec_threads > 0 && A4 == spec_A4 && d_draws == spec_ptr) have = std::min(spec_threads, nthreads & ~255LL);
+                if (batch_seq == 0) last_first_batch_threads_ = nthreads;
+                if (have < nthreads) {
+                    span_begin(0, st_);
+                    launch_rand_fill(dh, (const uint32_t *)d_level_tab_.p, d_draws, nthreads, st_, have);
+                    launches_ += 1;
+                    span_end(st_);
+                }
             }
             ChromPrep cpd{};
             cpd.nb = cs.nb; cpd.W = cs.W; cpd.n_phys = n_phys;
@@ -779,6 +1008,7 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
             cpd.t = (const int32_t *)cs.t.p; cpd.first = (const int32_t *)cs.first.p;
             cpd.yoff = (const int32_t *)cs.yoff.p; cpd.rowoff = (const long long *)cs.rowoff.p;
             const long long *pbase = d_pairbase + (size_t)h * N + b0;
+            const long long *rbase = d_recbase + (size_t)h * N + b0;
             const int32_t *pphys = d_physof + (size_t)h * N + b0;
             double *tens_b = d_tensor + (size_t)b0 * tens_per_ind;
             cudaEvent_t eval_done = new_event();
@@ -800,14 +1030,18 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
                 span_end(sc);
             } else {
                 const size_t n_ent = (size_t)Nb * slabs.size() * (cs.nb - 1) * nd_max;
-                RegionEnt *d_regions = reg_buf.as<RegionEnt>(n_ent);
-                UpdateRec *d_recs = recs_buf.as<UpdateRec>((size_t)(nthreads * (long long)kRun / 2 + 2) * plan.n_slots);
-                if (!d_regions || !d_recs) return FGT_ERR_CUDA;
-                span_begin(3, st_);
-                CK(cudaMemsetAsync(d_regions, 0, n_ent * sizeof(RegionEnt), st_));
+                RegionEnt *d_regions = nullptr;
+                UpdateRec *d_recs = nullptr;
+                if (!relaxed) {
+                    d_regions = reg_buf.as<RegionEnt>(n_ent);
+                    d_recs = recs_buf.as<UpdateRec>((size_t)(rec_pairs + 2) * plan.n_slots);
+                    if (!d_regions || !d_recs) return FGT_ERR_CUDA;
+                }
                 EvalArgs ea{};
                 ea.cp = cpd; ea.draws = (const uint2 *)d_draws;
-                ea.pair_base = pbase; ea.phys_of = pphys;
+                ea.hist0 = d_h0; ea.jump_tab = fused ? (const uint32_t *)d_jump_tab_.p : nullptr;
+                ea.pair_base = pbase; ea.rec_base = rbase; ea.phys_of = pphys;
+                ea.tensor = tens_b; ea.relaxed = relaxed ? 1 : 0; ea.accepted = d_acc;
                 ea.N = Nb; ea.K = K; ea.G = G; ea.grid_start = pb.grid_start; ea.mode = pb.mode; ea.n_slots = plan.n_slots;
                 ea.bw = pb.binwidth; ea.half_bw = pb.binwidth / 2.0; ea.cutoff = pb.gridweight_max_cutoff;
                 {
@@ -827,22 +1061,35 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
                     long long ds = opt.eval_parts > 0 ? opt.eval_parts : (2 * 148 * 32 + rows_jn - 1) / rows_jn;
                     ea.d_parts = (int)std::min<long long>(8, std::max<long long>(opt.eval_parts > 0 ? 1 : 4, ds));   // 4 also balances the tail of a full-size launch
                 }
-                launch_eval_pairs(ea, st_);
-                span_end(st_);
-                CK(cudaEventRecord(eval_done, st_));
-                CK(cudaStreamWaitEvent(sc, eval_done, 0));
-                span_begin(1, sc);
-                CommitArgs ca{};
-                ca.cp = cpd; ca.pair_base = pbase; ca.phys_of = pphys;
-                ca.N = Nb; ca.K = K; ca.G = G; ca.grid_start = pb.grid_start; ca.n_slots = plan.n_slots;
-                ca.n_slabs = (int)slabs.size();
-                ca.slabs = d_slabs; ca.recs = d_recs; ca.regions = d_regions; ca.nd_max = nd_max;
-                ca.tensor_is_zero = (tile_in_smem && (pb.mode == 3 || h == 0)) ? 1 : 0;
-                ca.tensor = tens_b; ca.accepted = d_acc;
-                ca.task_counter = d_taskctr + batch_seq;
-                launch_commit_ordered(ca, plan_max_w, sc);
-                launches_ += 2;
-                span_end(sc);
+                if (relaxed) {
+                    // the atomics land in the tensor: this launch belongs on the stream that owns the tensors
+                    CK(cudaEventRecord(eval_done, st_));
+                    CK(cudaStreamWaitEvent(sc, eval_done, 0));
+                    span_begin(3, sc);
+                    launch_eval_pairs(ea, sc);
+                    launches_ += 1;
+                    span_end(sc);
+                } else {
+                    span_begin(3, st_);
+                    CK(cudaMemsetAsync(d_regions, 0, n_ent * sizeof(RegionEnt), st_));
+                    launch_eval_pairs(ea, st_);
+                    span_end(st_);
+                    CK(cudaEventRecord(eval_done, st_));
+                    CK(cudaStreamWaitEvent(sc, eval_done, 0));
+                    span_begin(1, sc);
+                    CommitArgs ca{};
+                    ca.cp = cpd; ca.pair_base = pbase; ca.phys_of = pphys;
+                    ca.N = Nb; ca.K = K; ca.G = G; ca.grid_start = pb.grid_start; ca.n_slots = plan.n_slots;
+                    ca.n_slabs = (int)slabs.size();
+                    ca.slabs = d_slabs; ca.recs = d_recs; ca.regions = d_regions; ca.nd_max = nd_max;
+                    ca.tensor_is_zero = (tile_in_smem && (pb.mode == 3 || h == 0)) ? 1 : 0;
+                    ca.match_refine = opt.match_impl == 1 ? 1 : 0;
+                    ca.tensor = tens_b; ca.accepted = d_acc;
+                    ca.task_counter = d_taskctr + batch_seq;
+                    launch_commit_ordered(ca, plan_max_w, sc);
+                    launches_ += 2;
+                    span_end(sc);
+                }
             }
             stx.accum_launches += 1;
             if (project_per_range && (pb.mode == 3 || h == Cn - 1) && !want_raw) {
@@ -871,44 +1118,52 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
     for (int h = 0; h < Cn; h++) {
         ChromState &cs = chroms_[h];
         const fgt_chrom_t &c = pb.chrom[h];
-        // host-resident paintings: upload the chromosome's tables before the label copies fill the copy engine
-        if (!reuse && !c.labels_on_device) {
-            rc = setup_chromosome(pb, h, cs, stx);
-            if (rc) return rc;
-        }
+        const bool use_runs = c.runs != nullptr;
+        const bool in_hbm = use_runs ? c.runs_on_device != 0 : c.labels_on_device != 0;
+        const size_t rows_all = (size_t)n_phys * PM;
         const size_t bytes_per_ind = (size_t)PM * c.nsites * pb.label_bytes;
+        const size_t input_bytes = use_runs ? (size_t)c.run_off[rows_all] * sizeof(fgt_run_t) : bytes_per_ind * n_phys;
         int n_blocks = 1;
         if (!reuse) {
-            if (!c.labels_on_device) n_blocks = (int)std::min<size_t>(n_phys, std::max<size_t>(1, (bytes_per_ind * n_phys) / (48u << 20)));
+            if (!in_hbm) n_blocks = (int)std::min<size_t>(n_phys, std::max<size_t>(1, input_bytes / (48u << 20)));
             else n_blocks = 1;
             if (opt.blocks > 0) n_blocks = std::min(n_phys, opt.blocks);
         }
-        const void *d_lab = c.labels;
+        // host-resident paintings: upload the chromosome's tables before the painting copies fill the copy engine
+        if (!reuse && !in_hbm) {
+            rc = setup_chromosome(pb, h, cs, stx);
+            if (rc) return rc;
+            if (use_runs) { rc = setup_runs(pb, h, n_blocks, cs); if (rc) return rc; }
+        }
+        const void *d_lab = use_runs ? (const void *)c.runs : c.labels;
         std::vector<cudaEvent_t> copy_done(n_blocks, nullptr);
         auto blk_lo = [&](int b) { return (int)((long long)n_phys * b / n_blocks); };
-        if (!reuse && !c.labels_on_device) {
-            void *buf = d_labels_.get(bytes_per_ind * n_phys);
+        // byte range of block b inside the chromosome's painting buffer (dense rows, or the rows' runs)
+        auto blk_off = [&](int p) { return use_runs ? (size_t)c.run_off[(size_t)p * PM] * sizeof(fgt_run_t) : bytes_per_ind * p; };
+        if (!reuse && !in_hbm) {
+            void *buf = d_labels_.get(input_bytes);
             if (!buf) return FGT_ERR_CUDA;
             d_lab = buf;
             if (labels_free) { CK(cudaStreamWaitEvent(st_copy_, labels_free, 0)); CK(cudaStreamWaitEvent(st_copy2_, labels_free, 0)); }
+            const char *src = use_runs ? (const char *)c.runs : (const char *)c.labels;
             for (int b = 0; b < n_blocks; b++) {
                 const int p0 = blk_lo(b), p1 = blk_lo(b + 1);
                 cudaStream_t cstream = (opt.copy_streams > 1 && (b & 1)) ? st_copy2_ : st_copy_;   // two DMA engines
-                CK(cudaMemcpyAsync((char *)buf + bytes_per_ind * p0, (const char *)c.labels + bytes_per_ind * p0,
-                                   bytes_per_ind * (p1 - p0), cudaMemcpyHostToDevice, cstream));
+                CK(cudaMemcpyAsync((char *)buf + blk_off(p0), src + blk_off(p0), blk_off(p1) - blk_off(p0), cudaMemcpyHostToDevice, cstream));
                 copy_done[b] = new_event();
                 CK(cudaEventRecord(copy_done[b], cstream));
             }
-            stx.h2d_bytes += (int64_t)(bytes_per_ind * n_phys);
+            stx.h2d_bytes += (int64_t)input_bytes + (use_runs ? (int64_t)rows_all * 16 : 0);
         }
-        if (!reuse && c.labels_on_device) {
+        if (!reuse && in_hbm) {
             // device-resident paintings: the chunk count streams the labels while the host builds the cM prefix
-            if (!(count_pending_ && count_key_[0] == h && count_key_[1] == blk_lo(0) && count_key_[2] == blk_lo(1))) {
+            if (!use_runs && !(count_pending_ && count_key_[0] == h && count_key_[1] == blk_lo(0) && count_key_[2] == blk_lo(1))) {
                 rc = prep_count(pb, h, blk_lo(0), blk_lo(1), d_lab, copy_done[0]);
                 if (rc) return rc;
             }
             rc = setup_chromosome(pb, h, cs, stx);
             if (rc) return rc;
+            if (use_runs) { rc = setup_runs(pb, h, n_blocks, cs); if (rc) return rc; stx.h2d_bytes += (int64_t)rows_all * 16; }
         }
         int next_n = 0;
         for (int b = 0; b < n_blocks; b++) {
@@ -1116,7 +1371,7 @@ int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_ro
     ChromState &cs = null_cs_;                   // grow-only buffers kept between calls (no cudaMalloc/cudaFree per call)
     long long evals = 0;
     for (int h = 0; h < pb.num_chrom; h++) {
-        rc = prep_chromosome(pb, h, d_rowmap, n_haps, 1, n_haps, true, cs, stx);
+        rc = prep_chromosome(pb, h, d_rowmap, rowmap.data(), n_haps, 1, n_haps, true, cs, stx);
         if (rc) return rc;
         if (Nc >= 2) {
             NullArgs a{};
@@ -1260,7 +1515,7 @@ int Engine::chunk_one(const void *labels, int label_bytes, int nsites, const dou
     CK(cudaMemcpyAsync(d_donor, donor_label_vec, n_donor_labels * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
     ChromState cs;
     fgt_stats_t stx{};
-    rc = prep_chromosome(pb, 0, nullptr, 1, 1, 1, false, cs, stx);
+    rc = prep_chromosome(pb, 0, nullptr, nullptr, 1, 1, 1, false, cs, stx);
     if (rc) return rc;
     int n = (int)cs.n_chunks;
     std::vector<Chunk> hc(n);

@@ -22,6 +22,7 @@ struct DevBuf {
 
 struct ChromState {            // per chromosome device state that must outlive the prep pass
     DevBuf sorted, chunk_base, t, first, yoff, rowoff, cum, inc, etab, chunk_ptr, ps_ptr, pop_ptr;
+    DevBuf run_src, run_rowoff, run_cnt;   // RLE paintings: per row first run / per block chunk offsets / runs per row
     std::vector<DevBuf> sorted_blocks;   // data_read path: one sorted-chunk buffer per block of individuals
     int nb = 0, W = 0;
     std::vector<long long> totals;   // [n_phys] pairs each packed individual samples on this chromosome
@@ -49,7 +50,10 @@ struct Options {
     int null_target = 0;    // NULL task table: accepted pairs per (haplotype pair, slab) a task aims at; 0 = default
     int null_world = 1, null_rank = 0;   // sharded NULL run: this rank folds the label pairs it owns (sum of the ranks = exact)
     int spec_rand = 1;      // generate the first batch's draws while the chunk/bin kernels run
-    int accum_impl = 2;     // 2 = two-phase (evaluate once, ordered commit); 1 = single-phase slab warps     // one-shot: next packed call may reuse the chunk/bin tables of the previous one
+    int accum_impl = 2;     // 2 = two-phase (evaluate once, ordered commit); 1 = single-phase slab warps
+    int rand_impl = 1;      // 1 = glibc stream generated inside the pair-evaluation kernel; 0 = bulk stream in HBM (k_rand_fill)
+    int match_impl = 0;     // commit kernel: 0 = match.any over the cells, 1 = class match + shuffle refinement
+    double cache_mb = 8192; // parsed-file cache budget (host bytes), least recently used entries are dropped
 };
 
 class Engine {
@@ -69,9 +73,15 @@ class Engine {
                   double weight_min, double cutoff, const int32_t *donor_label_vec, int n_donor_labels, double *cpos,
                   double *csize, double *cweight, double *cend, int32_t *cpop);
     fgt_stats_t last_stats{};
+    int prepare_device() {            // CUDA context of the configured device (or the "no device" error): for host code that pins memory
+        int rc = ensure_init();
+        if (rc) return rc;
+        return cudaSetDevice(opt.device) == cudaSuccess ? FGT_OK : FGT_ERR_CUDA;
+    }
 
   private:
     Engine() = default;
+    int data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_stats_t *stats, int64_t *count_only);
     int ensure_init();
     bool fetch_history(History &h);          // current stream state (libc-coupled or private)
     void store_history(const History &h);
@@ -79,10 +89,12 @@ class Engine {
     void vtick(const char *what) const;
     std::chrono::steady_clock::time_point t_call_start_;
     int prep_count(const fgt_problem_t &pb, int h, int p0, int p1, const void *d_lab, cudaEvent_t copy_done);
+    int setup_runs(const fgt_problem_t &pb, int h, int n_blocks, ChromState &cs);
+    long long prep_sig(const fgt_problem_t &pb) const;
     int prep_block(const fgt_problem_t &pb, int h, int p0, int p1, int blk, const void *d_lab, cudaEvent_t copy_done,
                    ChromState &cs, fgt_stats_t &stx);
-    int prep_chromosome(const fgt_problem_t &pb, int h, const int32_t *rowmap_dev, int rows, int rows_per_ind,
-                        int n_groups, bool for_null, ChromState &cs, fgt_stats_t &stx);
+    int prep_chromosome(const fgt_problem_t &pb, int h, const int32_t *rowmap_dev, const int32_t *rowmap_host, int rows,
+                        int rows_per_ind, int n_groups, bool for_null, ChromState &cs, fgt_stats_t &stx);
     std::vector<SlabDesc> make_slabs(int G, int grid_start, double bw, int W, int N) const;
     struct SlabPlan { std::vector<SlabDesc> slabs; std::vector<int32_t> slab_of, first_slab; int n_slots = 0, slab_width = 1; };
     SlabPlan make_slab_plan(int G, int grid_start, double bw, int W, int N) const;
@@ -93,8 +105,12 @@ class Engine {
     cudaStream_t st_copy2_ = nullptr;
     cudaStream_t st_aux_ = nullptr;   // small table uploads that must not queue behind the prep stream
     History private_hist_ = seeded_history(1);
-    std::vector<uint32_t> level_tab_;
-    DevBuf d_level_tab_, d_err_, d_accepted_;
+    std::vector<uint32_t> level_tab_, jump_tab_;
+    DevBuf d_level_tab_, d_jump_tab_, d_err_, d_accepted_, d_recbase_;
+    long long prep_sig_ = 0;          // signature of the problem the kept chunk/bin tables were built from (reuse_prep)
+    void *pin_rows_ = nullptr;        // pinned staging of the per-row run tables of a chromosome
+    size_t pin_rows_cap_ = 0;
+    cudaEvent_t rows_ready_ = nullptr;
     // scratch shared by all chromosomes (stream ordered)
     DevBuf d_labels_, d_cum_, d_inc_, d_counts_, d_rowoff_, d_segoff_, d_cstart_, d_cend_, d_chap_, d_cntmat_, d_runfirst_,
         d_donor_, d_etab_, d_rowmap_;

@@ -147,4 +147,22 @@ inline std::vector<uint32_t> build_level_tables() {
     return tab;
 }
 
+// Jump table of the generator that runs inside the pair-evaluation kernel: coefficient i of
+// E^(digit * 256^level) at tab[(level*256 + digit)*32 + i] (i < 31; word 31 is padding), raw-draw granularity.
+constexpr int kJumpLevelsHost = 6;               // 2^48 raws
+
+inline std::vector<uint32_t> build_jump_table() {
+    std::vector<uint32_t> tab((size_t)kJumpLevelsHost * 256 * 32, 0u);
+    Poly unit = poly_E();
+    for (int lv = 0; lv < kJumpLevelsHost; lv++) {
+        Poly cur = poly_one();
+        for (int d = 0; d < 256; d++) {
+            for (int i = 0; i < kLag; i++) tab[((size_t)lv * 256 + d) * 32 + i] = cur.c[i];
+            cur = poly_mul(cur, unit);
+        }
+        unit = cur;                              // unit^256
+    }
+    return tab;
+}
+
 }  // namespace fgt

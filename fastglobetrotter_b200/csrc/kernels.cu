@@ -333,6 +333,94 @@ void launch_chunk_emit(const void *labels, const int32_t *rowmap, int label_byte
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Chunk builder on run-length-encoded paintings (fgt_run_t): the parse layer already found the maximal
+// runs of equal donor haplotype, so a chunk is a gather of the cM prefix at its run's start (reference
+// C:487-510: start = cursor at the first SNP of the run, end = cursor at the next run's first SNP minus that
+// SNP's own increment, C:501).  One thread per chunk; the row is found by bisecting the row offsets.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_chunks_from_runs(const uint2 *__restrict__ runs, const long long *__restrict__ src_begin, const int32_t *__restrict__ row_off,
+                   int rows, int L, const double *__restrict__ cum, const double *__restrict__ inc,
+                   double *__restrict__ cstart, double *__restrict__ cend, int32_t *__restrict__ chap, int *__restrict__ err) {
+    const int total = row_off[rows];
+    int bad = 0;
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
+        int lo = 0, hi = rows - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (row_off[mid] <= g) lo = mid; else hi = mid - 1;
+        }
+        const int k = g - row_off[lo], cnt = row_off[lo + 1] - row_off[lo];
+        const uint2 *rr = runs + src_begin[lo];
+        const uint2 me = rr[k];
+        if (me.x >= (unsigned)L || (k == 0 && me.x != 0u)) { bad |= kErrBadRuns; continue; }
+        cstart[g] = (k == 0) ? 0.0 : cum[me.x];
+        chap[g] = (int32_t)me.y;
+        if (k + 1 < cnt) {
+            const uint2 nx = rr[k + 1];
+            if (nx.x <= me.x || nx.x >= (unsigned)L || nx.y == me.y) { bad |= kErrBadRuns; continue; }   // runs must be maximal and ascending
+            cend[g] = __dsub_rn(cum[nx.x], inc[nx.x]);
+        } else cend[g] = cum[L - 1];
+    }
+    if (bad) atomicOr(err, bad);
+}
+
+// weight_min >= 1 on runs (never used by the R driver, R:52): a run boundary opens a chunk only if the maximal run
+// that just ended is longer than weight_min SNPs (reference C:446-455); otherwise the open chunk absorbs the next run
+// and keeps its own donor haplotype.  One thread per row, same results as k_chunk_seq on the dense matrix.
+template <bool EMIT>
+__global__ void k_chunk_seq_runs(const uint2 *__restrict__ runs, const long long *__restrict__ src_begin,
+                                 const int32_t *__restrict__ n_runs, int rows, int L, double weight_min,
+                                 int32_t *__restrict__ counts, const int32_t *__restrict__ row_off,
+                                 const double *__restrict__ cum, const double *__restrict__ inc, double *__restrict__ cstart,
+                                 double *__restrict__ cend, int32_t *__restrict__ chap, int *__restrict__ err) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    const uint2 *rr = runs + src_begin[row];
+    const int cnt = n_runs[row];
+    int c = 0;
+    const int base = EMIT ? row_off[row] : 0;
+    if (cnt <= 0 || rr[0].x != 0u) { atomicOr(err, kErrBadRuns); if (!EMIT) counts[row] = 1; return; }
+    if (EMIT) { cstart[base] = 0.0; chap[base] = (int32_t)rr[0].y; }
+    unsigned prev_start = 0;
+    for (int k = 1; k < cnt; k++) {
+        const uint2 r = rr[k];
+        if (r.x <= prev_start || r.x >= (unsigned)L) { atomicOr(err, kErrBadRuns); break; }
+        const double run = (double)(r.x - prev_start);             // SNPs of the maximal run that ends here
+        if (run > weight_min) {
+            c++;
+            if (EMIT) {
+                const double cj = cum[r.x];
+                cstart[base + c] = cj;
+                chap[base + c] = (int32_t)r.y;
+                cend[base + c - 1] = __dsub_rn(cj, inc[r.x]);
+            }
+        }
+        prev_start = r.x;
+    }
+    if (EMIT) cend[base + c] = cum[L - 1];
+    else counts[row] = c + 1;
+}
+
+void launch_chunks_from_runs(const fgt_run_t *runs, const long long *src_begin, const int32_t *row_off, int rows, int total,
+                             int nsites, const double *cum, const double *inc, double *cstart, double *cend, int32_t *chap,
+                             int *err, cudaStream_t st) {
+    if (total <= 0) return;
+    const unsigned grid = (unsigned)std::min<long long>(((long long)total + 255) / 256, 148LL * 8);
+    k_chunks_from_runs<<<grid, 256, 0, st>>>(reinterpret_cast<const uint2 *>(runs), src_begin, row_off, rows, nsites, cum, inc,
+                                             cstart, cend, chap, err);
+}
+
+void launch_chunk_seq_runs(bool emit, const fgt_run_t *runs, const long long *src_begin, const int32_t *n_runs, int rows,
+                           int nsites, double weight_min, int32_t *counts, const int32_t *row_off, const double *cum,
+                           const double *inc, double *cstart, double *cend, int32_t *chap, int *err, cudaStream_t st) {
+    const int grid = (rows + 127) / 128;
+    const uint2 *r2 = reinterpret_cast<const uint2 *>(runs);
+    if (emit) k_chunk_seq_runs<true><<<grid, 128, 0, st>>>(r2, src_begin, n_runs, rows, nsites, weight_min, nullptr, row_off, cum, inc, cstart, cend, chap, err);
+    else k_chunk_seq_runs<false><<<grid, 128, 0, st>>>(r2, src_begin, n_runs, rows, nsites, weight_min, counts, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, err);
+}
+
 // exclusive scan of int32 counts -> out[0..n] (single block; n is "rows", at most a few 10^5)
 __global__ void __launch_bounds__(1024) k_exclusive_scan_i32(const int32_t *__restrict__ in, int32_t *__restrict__ out, int n) {
     __shared__ int wtot[32];
@@ -821,7 +909,7 @@ __device__ __forceinline__ PairEval eval_pair(bool in_range, uint2 r, int t1, un
         const int row = tri_row(lo_l, hi_l, a.K);
         const int slab = a.slab_magic ? (int)__umulhi((unsigned)bb, a.slab_magic) : bb;   // bb / slab_width (exact: both < 2^16; 0 = width 1)
         const int slot = slab - slab0;
-        if ((unsigned)slot >= (unsigned)a.n_slots) { bad |= kErrInternal; return o; }
+        if (!a.relaxed && (unsigned)slot >= (unsigned)a.n_slots) { bad |= kErrInternal; return o; }
         o.cell = row * a.G + bb;
         const int sb0 = slab * a.slab_width;
         const int sw = min(a.slab_width, a.G - sb0);                          // the last slab may be narrower
@@ -833,7 +921,51 @@ __device__ __forceinline__ PairEval eval_pair(bool in_range, uint2 r, int t1, un
     return o;
 }
 
+// ---- glibc rand() inside phase 1 (rand_impl = 1) ---------------------------------------------------------------
+// A warp consumes one contiguous piece of the stream (its separations of row (n, j) follow each other), so it carries
+// its own generator: lanes 0..30 hold the last 31 raw words x[m-31..m-1]; the next 31 follow from
+//     x[m+i] = x[m+i-31] + x[m+i-3]  =  hist[i] + (i < 3 ? hist[i+28] : x[m+i-3])
+// i.e. three interleaved running sums (i mod 3): one shuffle for the three wrapped terms and a stride-3 scan
+// (shuffle-up by 3, 6, 12, 24).  Lane 31 idles.  The warp reaches its start by jump-ahead on the device: the state
+// D raws after the call's entry state is  sum_i c_i * Y[i+j]  with c = E^D mod (E^31 - E^28 - 1), taken one base-256
+// digit of D at a time from a table of E^(digit * 256^level) (built on the host by glibc_rand.h).
+constexpr int kRingRaws = 256;     // per-warp ring of generated draws (uint32, already >> 1)
+constexpr int kJumpLevels = 6;     // base-256 digits of the raw offset: 2^48 raws = 1.4e14 sampled pairs per call
+
+__device__ __forceinline__ uint32_t gen_block31(uint32_t hist, int lane) {
+    const uint32_t t = __shfl_sync(kFull, hist, (lane + 28) & 31);
+    uint32_t a = hist + (lane < 3 ? t : 0u);
+#pragma unroll
+    for (int s = 3; s <= 24; s <<= 1) {
+        const uint32_t u = __shfl_up_sync(kFull, a, s);
+        if (lane >= s) a += u;
+    }
+    return a;
+}
+
+// hist <- history D raws later.  scratch: >= 96 words of the warp's shared memory.
+__device__ __forceinline__ void warp_jump(uint32_t &hist, unsigned long long D, const uint32_t *__restrict__ tab,
+                                          uint32_t *scratch, int lane) {
+    for (int lv = 0; D != 0ull && lv < kJumpLevels; lv++, D >>= 8) {
+        const int digit = (int)(D & 255ull);
+        if (!digit) continue;
+        const uint32_t ext = gen_block31(hist, lane);              // Y[31 + lane]
+        __syncwarp();
+        if (lane < 31) { scratch[lane] = hist; scratch[31 + lane] = ext; }
+        scratch[64 + lane] = tab[((size_t)lv * 256 + digit) * 32 + lane];
+        __syncwarp();
+        const int j = lane < 31 ? lane : 0;
+        uint32_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < 31; i++) acc += scratch[64 + i] * scratch[i + j];
+        hist = acc;
+        __syncwarp();
+    }
+}
+
+template <bool FUSED_RNG, bool RELAXED>
 __global__ void __launch_bounds__(128, 8) k_eval_pairs(const EvalArgs a) {
+    __shared__ __align__(16) uint32_t ring_all[FUSED_RNG ? 4 * kRingRaws : 4];
     const int lane = lane_id();
     const ChromPrep &cp = a.cp;
     const int nb = cp.nb, W = cp.W;
@@ -852,7 +984,9 @@ __global__ void __launch_bounds__(128, 8) k_eval_pairs(const EvalArgs a) {
     const int32_t *yo = cp.yoff + ((size_t)phys * nb + j) * W;
     const double2 *chps = cp.ps_ptr[phys];
     const int32_t *chpop = cp.pop_ptr[phys];
-    const long long row_pair0 = a.pair_base[n] + cp.rowoff[(size_t)phys * (nb + 1) + j];
+    const long long rowoff_j = cp.rowoff[(size_t)phys * (nb + 1) + j];
+    const long long row_pair0 = a.pair_base[n] + rowoff_j;        // stream position (pairs) of the row's first draw
+    const long long row_rec0 = a.rec_base[n] + rowoff_j;          // the same row in the record buffer of this launch
     const int f1 = F[j];
     const unsigned inv1 = mod_magic((unsigned)t1);
     const int ns = a.n_slots;
@@ -861,13 +995,6 @@ __global__ void __launch_bounds__(128, 8) k_eval_pairs(const EvalArgs a) {
     if (nb - 1 - j < dmax) dmax = nb - 1 - j;
     int bad = 0;
     const unsigned lt = (1u << lane) - 1;
-    // The row's draws are consumed strictly front to back (segment d+1 starts where segment d ends), so the 64
-    // draws of the next iteration are fetched while the current one waits for its chunk gathers.
-    uint2 nr0, nr1;
-    auto prefetch = [&](long long p) {
-        nr0 = a.draws[p + lane];                         // may run up to 127 pairs past the batch: the buffer has kDrawSlack
-        nr1 = a.draws[p + 32 + lane];
-    };
     // this warp's share of the separations: d in (d_from, d_to], cut where the row's cumulative pair count crosses
     // part/DS of its total (small ranges of individuals would otherwise leave most of the GPU idle)
     int d_from = 0, d_to = dmax;
@@ -885,7 +1012,23 @@ __global__ void __launch_bounds__(128, 8) k_eval_pairs(const EvalArgs a) {
         d_to = (part == DS - 1) ? dmax : n_hi - 1;
         if (d_from >= d_to) return;
     }
-    prefetch(row_pair0 + yo[d_from]);
+    // The row's draws are consumed strictly front to back (segment d+1 starts where segment d ends).
+    //   bulk stream (k_rand_fill): the 64 draws of the next iteration are fetched while the current one waits for
+    //   its chunk gathers;  fused: the warp generates them into its ring as it goes.
+    uint2 nr0 = make_uint2(0u, 0u), nr1 = make_uint2(0u, 0u);
+    auto prefetch = [&](long long p) {
+        nr0 = a.draws[p + lane];                         // may run up to 127 pairs past the batch: the buffer has kDrawSlack
+        nr1 = a.draws[p + 32 + lane];
+    };
+    uint32_t *ring = ring_all + (FUSED_RNG ? warp_id() * kRingRaws : 0);
+    uint32_t hist = 0;
+    unsigned ring_w = 0, ring_r = 0;                     // raws generated / consumed so far (uniform)
+    if (FUSED_RNG) {
+        if (lane < 31) hist = a.hist0[lane];
+        warp_jump(hist, 2ull * (unsigned long long)(row_pair0 + yo[d_from]), a.jump_tab, ring, lane);
+    } else prefetch(row_pair0 + yo[d_from]);
+    double *tens = RELAXED ? a.tensor + (size_t)n * ((size_t)a.K * (a.K + 1) / 2) * a.G : nullptr;
+    unsigned long long n_relaxed = 0;
     for (int d = d_from + 1; d <= d_to; d++) {
         const int y0 = yo[d - 1];
         const int Y = yo[d] - y0;
@@ -894,37 +1037,62 @@ __global__ void __launch_bounds__(128, 8) k_eval_pairs(const EvalArgs a) {
         const int t2 = T[k], f2 = F[k];
         const unsigned inv2 = mod_magic((unsigned)t2);
         const long long seg = row_pair0 + y0;
-        UpdateRec *reg = a.recs + seg * ns;
+        const long long rseg = row_rec0 + y0;
+        UpdateRec *reg = RELAXED ? nullptr : a.recs + rseg * ns;
         const int slab0 = a.first_slab[d];
         const BinRef binB{chps + f2, chpop + f2};
         int c[kMaxSlots] = {};
         for (int base = 0; base < Y; base += 64) {
             const int q0 = base + lane, q1 = base + 32 + lane;
-            const uint2 r0 = nr0, r1 = nr1;
-            prefetch(seg + min(base + 64, Y));
+            uint2 r0, r1;
+            if (FUSED_RNG) {
+                const unsigned need = 2u * (unsigned)min(64, Y - base);
+                while (ring_w - ring_r < need) {
+                    hist = gen_block31(hist, lane);
+                    if (lane < 31) ring[(ring_w + lane) & (kRingRaws - 1)] = hist >> 1;      // rand() = x >> 1
+                    ring_w += 31;
+                }
+                __syncwarp();
+                const uint2 *r64 = reinterpret_cast<const uint2 *>(ring);
+                r0 = r64[((ring_r >> 1) + lane) & (kRingRaws / 2 - 1)];
+                r1 = r64[((ring_r >> 1) + 32 + lane) & (kRingRaws / 2 - 1)];
+                ring_r += need;
+                __syncwarp();
+            } else {
+                r0 = nr0; r1 = nr1;
+                prefetch(seg + min(base + 64, Y));
+            }
             PairEval e[2];
             e[0] = eval_pair(q0 < Y, r0, t1, inv1, t2, inv2, binA, binB, a, slab0, bad);
             e[1] = eval_pair(q1 < Y, r1, t1, inv1, t2, inv2, binA, binB, a, slab0, bad);
-            // ordered partition of the two steps' updates into the segment's slab regions
+            if (RELAXED) {
+                // relaxed mode (opt-in, "strict" = 0): fp64 atomics straight into the tensor -- additions land in
+                // arbitrary order, so cells agree with the reference to rounding (~1e-16 relative), not bit for bit
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                int pos = 0;
+                for (int h = 0; h < 2; h++)
+                    if (e[h].cell >= 0) { atomicAdd(tens + e[h].cell, e[h].val); n_relaxed++; }
+            } else {
+                // ordered partition of the two steps' updates into the segment's slab regions
 #pragma unroll
-                for (int s = 0; s < kMaxSlots; s++) {
-                    if (s < ns) {
-                        const unsigned m = __ballot_sync(kFull, e[h].slot == s);
-                        if (e[h].slot == s) pos = c[s] + __popc(m & lt);
-                        c[s] += __popc(m);
+                for (int h = 0; h < 2; h++) {
+                    int pos = 0;
+#pragma unroll
+                    for (int s = 0; s < kMaxSlots; s++) {
+                        if (s < ns) {
+                            const unsigned m = __ballot_sync(kFull, e[h].slot == s);
+                            if (e[h].slot == s) pos = c[s] + __popc(m & lt);
+                            c[s] += __popc(m);
+                        }
                     }
-                }
-                if (e[h].slot >= 0) {
-                    UpdateRec rec;
-                    rec.cell = e[h].cell; rec.pad = e[h].local; rec.val = e[h].val;
-                    reg[(long long)e[h].slot * Y + pos] = rec;
+                    if (e[h].slot >= 0) {
+                        UpdateRec rec;
+                        rec.cell = e[h].cell; rec.pad = e[h].local; rec.val = e[h].val;
+                        reg[(long long)e[h].slot * Y + pos] = rec;
+                    }
                 }
             }
         }
-        if (lane < ns) {
+        if (!RELAXED && lane < ns) {
             int v = c[0];
 #pragma unroll
             for (int s = 1; s < kMaxSlots; s++) if (lane == s) v = c[s];
@@ -932,11 +1100,15 @@ __global__ void __launch_bounds__(128, 8) k_eval_pairs(const EvalArgs a) {
             if (v > 0 && slab < a.n_slabs) {
                 // region directory of task (n, slab): entry (j, d - dlo(slab)); empty entries stay zero
                 RegionEnt ent;
-                ent.base = seg * ns + (long long)lane * Y;
+                ent.base = rseg * ns + (long long)lane * Y;
                 ent.cnt = v; ent.pad = 0;
                 a.regions[(((size_t)n * a.n_slabs + slab) * (nb - 1) + j) * a.nd_max + (d - a.slabs[slab].dlo)] = ent;
             }
         }
+    }
+    if (RELAXED) {
+        n_relaxed = warp_sum_u64(n_relaxed);
+        if (lane == 0 && n_relaxed) atomicAdd(a.accepted, n_relaxed);
     }
     if (bad) atomicOr(a.err, bad);
 }
@@ -945,7 +1117,15 @@ void launch_eval_pairs(const EvalArgs &a, cudaStream_t st) {
     long long tasks = (long long)a.N * (a.cp.nb - 1) * a.d_parts;
     if (tasks <= 0) return;
     const int wpb = 4;
-    k_eval_pairs<<<(unsigned)((tasks + wpb - 1) / wpb), wpb * 32, 0, st>>>(a);
+    const unsigned grid = (unsigned)((tasks + wpb - 1) / wpb);
+    const bool fused = a.jump_tab != nullptr;
+    if (a.relaxed) {
+        if (fused) k_eval_pairs<true, true><<<grid, wpb * 32, 0, st>>>(a);
+        else k_eval_pairs<false, true><<<grid, wpb * 32, 0, st>>>(a);
+    } else {
+        if (fused) k_eval_pairs<true, false><<<grid, wpb * 32, 0, st>>>(a);
+        else k_eval_pairs<false, false><<<grid, wpb * 32, 0, st>>>(a);
+    }
 }
 
 // Phase 2: one CTA per (pseudo-individual, slab) folds the slab's records in sequence order
@@ -1114,7 +1294,20 @@ __global__ void __launch_bounds__(32 * (kConsumers + 1)) k_commit_ordered(const 
             // stay in stream order.  Records of other warps share one sentinel key: match.any's cost grows with
             // the number of distinct keys, so every warp's vote gets cheaper as well.
             auto same_cell_mask = [&](int cell) -> unsigned {
-                return __match_any_sync(kFull, cell >= 0 ? (unsigned)cell : 0x80000000u);
+                if (!a.match_refine) return __match_any_sync(kFull, cell >= 0 ? (unsigned)cell : 0x80000000u);
+                // match_impl = 1: match.any costs two cycles per DISTINCT key on the SM's single unit, so match on a
+                // 3-bit class of the cell (bit 0 is the owner bit, constant within a warp) -- at most nine keys with
+                // the sentinel -- and let the few lanes that share a class compare their cells through shuffles.
+                const unsigned cls = cell >= 0 ? (((unsigned)cell >> 1) & 7u) : 8u;
+                const unsigned m = __match_any_sync(kFull, cls);
+                unsigned same = 1u << lane;
+                unsigned rest = cell >= 0 ? (m & ~same) : 0u;
+                while (__any_sync(kFull, rest != 0u)) {
+                    const int src = rest ? (__ffs(rest) - 1) : lane;
+                    const int oc = __shfl_sync(kFull, cell, src);
+                    if (rest) { if (oc == cell) same |= 1u << src; rest &= rest - 1; }
+                }
+                return same;
             };
             struct Staged { int c; int cell[kStageSteps]; double val[kStageSteps]; unsigned g[kStageSteps]; };
             auto fetch = [&]() -> Staged {
@@ -1189,11 +1382,13 @@ void launch_commit_ordered(const CommitArgs &a, int max_slab_width, cudaStream_t
     const size_t ctrl_bytes = 6144 + 1024;
     static_assert(kStages * kStageRecs * sizeof(UpdateRec) == 6144, "ring size");
     const size_t tile_bytes = commit_tile_bytes(a.K, max_slab_width);
-    static bool attr_set = false;
+    static bool attr_set[64] = {};                    // the attribute is per device (one engine per device)
+    int dev = 0;
+    cudaGetDevice(&dev);
     if (tile_bytes + ctrl_bytes <= 200 * 1024) {
-        if (!attr_set) {
+        if (!attr_set[dev & 63]) {
             cudaFuncSetAttribute(k_commit_ordered<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            attr_set = true;
+            attr_set[dev & 63] = true;
         }
         const long long per_sm = std::max<long long>(1, (227 * 1024) / (long long)(ctrl_bytes + tile_bytes + 1024));
         const long long grid = std::min<long long>(tasks, 148 * std::min<long long>(per_sm, 32));
@@ -1804,8 +1999,10 @@ void launch_null_strict(const NullArgs &a, cudaStream_t st) {
     long long tasks = a.n_tasks;
     if (tasks <= 0) return;
     size_t smem = (size_t)wpb * (3 * kNullStage + 2 * kNullQ + kNullGroup + a.max_slab_bins) * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_null_strict, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) { cudaFuncSetAttribute(k_null_strict, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set[dev & 63] = true; }
     k_null_strict<<<(unsigned)((tasks + wpb - 1) / wpb), wpb * 32, smem, st>>>(a);
 }
 

@@ -3,6 +3,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "../../include/fgt_companion.h"
+
 namespace fgt {
 
 // One chunk of a painting after run-length encoding (reference C:514-527), 32 bytes = one
@@ -16,7 +18,7 @@ struct __align__(32) Chunk {
 };
 
 // error bits raised by kernels (mapped to FGT_ERR_* on the host)
-enum : int { kErrMissingDonor = 1, kErrLabelRange = 2, kErrMode3Target = 4, kErrInternal = 8 };
+enum : int { kErrMissingDonor = 1, kErrLabelRange = 2, kErrMode3Target = 4, kErrInternal = 8, kErrBadRuns = 16 };
 
 struct SlabDesc {   // one accumulation task column: a contiguous range of fine bins
     int32_t b0, b1; // owned fine bins [b0, b1] on the FULL grid (before subtracting grid_start)
@@ -63,9 +65,15 @@ constexpr int kMaxSlots = 4;   // slabs a coarse-bin separation can reach (regio
 
 struct EvalArgs {
     ChromPrep cp;
-    const uint2 *draws;
-    const long long *pair_base;   // [N]
+    const uint2 *draws;           // bulk stream (rand_impl = 0): draws[p] = the two rand() outputs of pair p, buffer-relative
+    const uint32_t *hist0;        // fused generator (rand_impl = 1): the 31-word glibc history at pair 0 of `pair_base` ...
+    const uint32_t *jump_tab;     // ... and the jump table [level][digit][32] (NULL selects the bulk stream)
+    const long long *pair_base;   // [N] stream position (in pairs) at which pseudo-individual n starts drawing
+    const long long *rec_base;    // [N] first record slot (in pairs) of n in this launch's record buffer
     const int32_t *phys_of;       // [N]
+    double *tensor;               // relaxed mode only: [N][K(K+1)/2][G], updated with fp64 atomics
+    unsigned long long *accepted; // relaxed mode only (the commit kernel counts otherwise)
+    int32_t relaxed;
     int32_t N, K, G, grid_start, mode, n_slots;
     double bw, half_bw, cutoff;
     double inv_bw;                // RN(1/bw), or 0 when the two-FMA division below is not provably exact for this bw
@@ -89,6 +97,7 @@ struct CommitArgs {
     const UpdateRec *recs;
     const RegionEnt *regions;
     int32_t nd_max, tensor_is_zero;
+    int32_t match_refine;         // 1: class match + shuffle refinement instead of one match.any over the cells
     double *tensor;
     unsigned long long *accepted;
     int *task_counter;            // zeroed before the launch: persistent CTAs claim (individual, slab) tasks from it
@@ -106,6 +115,14 @@ void launch_exclusive_scan_i32(const int32_t *in, int32_t *out /*[n+1]*/, int n,
 void launch_chunk_emit(const void *labels, const int32_t *rowmap, int label_bytes, int nsites, int rows, double weight_min,
                        const int32_t *counts, const int32_t *row_off, const double *cum, const double *inc, double *cstart,
                        double *cend, int32_t *chap, cudaStream_t st);
+// chunks straight from run-length-encoded paintings: row r of the output takes the runs that start at runs[src_begin[r]],
+// row_off[rows+1] are the output chunk offsets (= run counts prefix when weight_min < 1)
+void launch_chunks_from_runs(const fgt_run_t *runs, const long long *src_begin, const int32_t *row_off, int rows, int total,
+                             int nsites, const double *cum, const double *inc, double *cstart, double *cend, int32_t *chap,
+                             int *err, cudaStream_t st);
+void launch_chunk_seq_runs(bool emit, const fgt_run_t *runs, const long long *src_begin, const int32_t *n_runs, int rows,
+                           int nsites, double weight_min, int32_t *counts, const int32_t *row_off, const double *cum,
+                           const double *inc, double *cstart, double *cend, int32_t *chap, int *err, cudaStream_t st);
 void launch_bin_sort(int n_phys, int rows_per_ind, const int32_t *row_off, const double *cstart, const double *cend,
                      const int32_t *chap, const int32_t *donor_label, int n_donor_labels, double cutoff, int K, int mode,
                      int nb, int W, const double *Etab, double divisor, Chunk *sorted, long long n_sorted, const Chunk **chunk_ptr,

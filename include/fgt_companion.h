@@ -66,21 +66,34 @@ void data_read_null(int *ploidy, char **filenameSAMPread, char **filenameRECOMre
 #define FGT_ERR_MODE3_TARGET (-7) /* mode 3 met a target-population chunk (undefined behaviour in
                                      the reference, C:1159-1166 index with label-1 = -1)           */
 
-/* one chromosome of decoded paintings */
+/* one run of a run-length-encoded painting: SNPs [start, next run's start) copy donor haplotype `hap`
+ * (1-based id, as in the samples file).  Runs of a row are maximal (neighbours differ in `hap`), the first
+ * starts at SNP 0.  This is what the reference's chunk builder derives first (C:446-455, C:487-510). */
+typedef struct fgt_run_t {
+    uint32_t start;
+    uint32_t hap;
+} fgt_run_t;
+
+/* one chromosome of decoded paintings: EITHER run-length encoded (preferred: `runs` != NULL) OR a dense
+ * label matrix (`labels`). */
 typedef struct fgt_chrom_t {
     int32_t nsites;          /* SNPs = rows of the recombination map (reference C:357-364)               */
     const double *pos;       /* host, [nsites] basepair positions                                         */
     const double *rate;      /* host, [nsites] recombination rate per bp (Morgans)                        */
-    const void *labels;      /* [n_packed_inds*ploidy*nsamples][nsites] donor haplotype ids (1-based),    */
-                             /* row (ind*ploidy + p)*nsamples + s; uint16 or int32, host or device memory */
+    const void *labels;      /* dense: [n_packed_inds*ploidy*nsamples][nsites] donor haplotype ids        */
+                             /* (1-based), row (ind*ploidy + p)*nsamples + s; uint16 or int32 (problem's  */
+                             /* label_bytes), host or device memory                                       */
     int32_t labels_on_device;
+    int32_t runs_on_device;  /* `runs` is device memory (run_off is always host memory)                   */
+    const int64_t *run_off;  /* RLE: host, [rows+1]; row r owns runs[run_off[r] .. run_off[r+1])          */
+    const fgt_run_t *runs;   /* RLE: [run_off[rows]] runs, host (ideally pinned) or device memory         */
 } fgt_chrom_t;
 
 typedef struct fgt_problem_t {
     int32_t mode;            /* 1 = data_read constants, 3 = data_read_mode3 constants                    */
     int32_t ploidy, nsamples, num_chrom;
     int32_t n_packed_inds;   /* individuals present in every labels matrix                                */
-    int32_t label_bytes;     /* 2 or 4                                                                    */
+    int32_t label_bytes;     /* dense label matrices: 2 or 4 (ignored for RLE chromosomes)                */
     const fgt_chrom_t *chrom;
     int32_t num_inds;        /* pseudo-individuals handled by THIS call (this rank's shard)               */
     const int32_t *ind_rows; /* [i*num_chrom + h] packed individual used for pseudo-individual i          */
@@ -162,6 +175,17 @@ int fgt_chunk_one(const void *labels, int label_bytes, int nsites, const double 
 int fgt_parse_probe(const char *samples_list, const char *recom_list, int ploidy, int n_rec, char **rec_labels,
                     int32_t *num_chrom, int32_t *nsamples, int32_t *nsites, int32_t *rec_index, int32_t *label_bytes,
                     uint64_t *label_sum, void **labels_out, double *pos_out, double *rate_out);
+
+/* host-only: dense label matrix ([rows][nsites], uint16 or int32) -> run-length-encoded rows (fgt_run_t), the
+ * painting format of fgt_chrom_t.  run_off: [rows+1] (may be NULL).  Returns the number of runs; call with
+ * runs == NULL first to size the buffer. */
+int fgt_rle_encode(const void *labels, int label_bytes, int64_t rows, int nsites, int64_t *run_off, fgt_run_t *runs,
+                   int64_t capacity);
+
+/* host-only: convert a whole *.samples.out[.gz] text file into the self-contained binary, chunk-level (run-length
+ * encoded) interchange file "*.fgtrle" (SURVEY 8f.4).  The samples list handed to data_read / data_read_mode3 /
+ * data_read_null may name .fgtrle files instead of text files.  Returns the number of runs written (< 0: error). */
+int64_t fgt_pack_samples(const char *samples_path, int nsites, const char *out_path);
 
 /* host-only self-test of the jump-ahead arithmetic: the 31-word history (oldest first) of the
  * glibc stream n_draws after srand(seed). */

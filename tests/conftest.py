@@ -43,6 +43,15 @@ def lib(built):
     return PackedCompanion(built)
 
 
+@pytest.fixture(params=["rle", "dense"])
+def each_encoding(lib, request):
+    """run a test once with run-length-encoded paintings (the library's preferred format) and once with dense label
+    matrices (chunked on the device by the label-scan kernels)"""
+    lib.encode = request.param
+    yield request.param
+    lib.encode = "rle"
+
+
 @pytest.fixture(scope="session")
 def oracle():
     from oracle.oracle import Oracle

@@ -120,7 +120,7 @@ def test_missing_donor_is_an_error(lib):
 
 @pytest.mark.parametrize("mode", [1, 3])
 @pytest.mark.parametrize("ids_kind", ["identity", "bootstrap"])
-def test_data_read_packed_bit_exact(lib, oracle, small, mode, ids_kind):
+def test_data_read_packed_bit_exact(lib, oracle, small, mode, ids_kind, each_encoding):
     sp = small.spec
     if mode == 3:   # mode 3 has undefined behaviour on target-label chunks: use a data set without them
         sp = synth.SynthSpec(n_chrom=2, n_inds=6, n_snps=4000, K=7, nsamples=5, rate=3e-7, name="m3")
@@ -188,7 +188,7 @@ def test_odd_grids(lib, oracle, small):
         assert np.array_equal(m_g, m_o, equal_nan=True), (bw, G, gs)
 
 
-def test_null_packed_bit_exact(lib, oracle, small):
+def test_null_packed_bit_exact(lib, oracle, small, each_encoding):
     sp = small.spec
     chrom, dl = packed_chrom(small), small.donor_label_vec
     K, G, bw, gs = sp.K, 120, 0.1, 10
@@ -539,7 +539,7 @@ def test_repeatable_at_scale_with_other_kernels_on_the_gpu(lib):
         lib.set_option("accum_impl", 2)
 
 
-def test_odd_row_lengths_and_label_block_offsets(lib, oracle):
+def test_odd_row_lengths_and_label_block_offsets(lib, oracle, each_encoding):
     """the chunk kernels read 16-bit labels as aligned 16-byte groups: odd row lengths, blocks of individuals that start
     at any byte offset (host path, several blocks), a row-mapped NULL call and 32-bit labels must all chunk identically."""
     K, S = 5, 2
@@ -676,7 +676,7 @@ def test_null_sharded_by_label_pair_is_exact(lib, oracle, small):
         lib.set_option("null_rank", 0)
 
 
-def test_weight_min_general_chunking_through_data_read(lib, oracle, small):
+def test_weight_min_general_chunking_through_data_read(lib, oracle, small, each_encoding):
     """weight_min >= 1 (a label change only opens a chunk after a run longer than weight_min SNPs, C:446-455) takes the
     sequential chunk kernels; the whole data_read and data_read_null must still match the oracle bit for bit."""
     sp = small.spec
@@ -743,3 +743,141 @@ def test_randomized_shapes_against_the_oracle(lib, oracle):
             n_o, ev = oracle.data_read_null_packed(ploidy, nsamples, chrom, np.arange(n_inds), bw, G, gs, K, dl, wmin, cutoff)
             n_g, st = lib.data_read_null_packed(ploidy, nsamples, chrom, np.arange(n_inds), bw, G, gs, K, dl, wmin, cutoff)
             assert st["pairs"] == ev and np.array_equal(n_g, n_o), f"null case {case}"
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: generator inside the evaluation kernel, class-match commit, relaxed mode, device-resident runs
+# ---------------------------------------------------------------------------------------------
+def _small_problem(small, oracle, S=4, G=120):
+    sp = small.spec
+    chrom, dl = packed_chrom(small), small.donor_label_vec
+    K = sp.K
+    W = synth.random_weights(K, S)
+    tw = oracle.mutiply_temp_weight(K, S, W.ravel(order="F")).reshape(S * S, K * K).ravel(order="F")
+    return sp, chrom, dl, K, S, G, tw
+
+
+@pytest.mark.parametrize("rand_impl", [0, 1])
+@pytest.mark.parametrize("match_impl", [0, 1])
+def test_generator_and_commit_variants_are_bit_exact(lib, oracle, small, rand_impl, match_impl):
+    """rand_impl: 1 = glibc stream generated by the evaluation warps (device-side jump-ahead), 0 = bulk stream in HBM;
+    match_impl: 1 = class match + shuffle refinement in the ordered commit.  Every combination must give the reference's
+    bits, for split rows (eval_parts) and forced batches as well."""
+    sp, chrom, dl, K, S, G, tw = _small_problem(small, oracle)
+    ids = bootstrap_ids(sp.n_inds, sp.n_chrom, 11)
+    lib.set_option("rand_libc", 0)
+    lib.set_option("rand_impl", rand_impl)
+    lib.set_option("match_impl", match_impl)
+    try:
+        for parts, batch in ((0, 0), (1, 0), (7, 0), (0, 30000)):
+            lib.set_option("eval_parts", parts)
+            lib.set_option("batch_pairs", batch)
+            oracle.srand(77 + parts)
+            m_o, raw_o, pairs_o = oracle.data_read_packed(1, sp.ploidy, sp.nsamples, chrom, ids, 0.1, G, 10, K, dl, 0.0, 1.0, S, tw,
+                                                          want_raw=True)
+            lib.srand(77 + parts)
+            m_g, raw_g, st = lib.data_read_packed(1, sp.ploidy, sp.nsamples, chrom, ids, 0.1, G, 10, K, dl, 0.0, 1.0, S, tw,
+                                                  want_raw=True)
+            assert st["pairs"] == pairs_o
+            assert np.array_equal(raw_g, raw_o), (parts, batch, int((raw_g != raw_o).sum()))
+            assert np.array_equal(m_g, m_o)
+            assert np.array_equal(lib.rand_fill(3), np.array([oracle.rand() for _ in range(3)], dtype=np.int32))
+    finally:
+        for k, v in (("rand_impl", 1), ("match_impl", 0), ("eval_parts", 0), ("batch_pairs", 0)):
+            lib.set_option(k, v)
+
+
+def test_fused_generator_far_into_the_stream(lib, oracle, small):
+    """the device-side jump-ahead of the evaluation warps with large offsets: a sharded-style call whose individuals
+    start billions of pairs into the stream (pair_offset), against the oracle positioned there by host jump-ahead."""
+    sp, chrom, dl, K, S, G, tw = _small_problem(small, oracle)
+    N, Cn = sp.n_inds, sp.n_chrom
+    ids = ind_id_matrix(N, Cn)
+    lib.set_option("rand_libc", 0)
+    cnt = lib.count_pairs_packed(1, sp.ploidy, sp.nsamples, chrom, ids, 0.1, G, 10, K, dl, 0.0, 1.0)     # [Cn, N]
+    base = 3_000_000_000_123                                   # pairs: exercises five base-256 digits of the raw offset
+    offs = base + np.concatenate([[0], np.cumsum(cnt.ravel())])[:-1].reshape(cnt.shape)
+    lib.srand(5)
+    m_g, raw_g, st = lib.data_read_packed(1, sp.ploidy, sp.nsamples, chrom, ids, 0.1, G, 10, K, dl, 0.0, 1.0, S, tw, want_raw=True,
+                                          pair_offset=offs, pairs_total=int(base + cnt.sum()))
+    hist = np.zeros(31, dtype=np.uint32)
+    assert lib.lib.fgt_rand_host_jump(C.c_uint(5), C.c_uint64(2 * base), hist.ctypes.data_as(C.c_void_p)) == 0
+    oracle.set_history(hist)
+    m_o, raw_o, pairs_o = oracle.data_read_packed(1, sp.ploidy, sp.nsamples, chrom, ids, 0.1, G, 10, K, dl, 0.0, 1.0, S, tw, want_raw=True)
+    assert st["pairs"] == pairs_o
+    assert np.array_equal(raw_g, raw_o)
+    assert np.array_equal(m_g, m_o)
+
+
+@pytest.mark.parametrize("mode", [1, 3])
+def test_relaxed_mode_within_tolerance(lib, oracle, small, mode):
+    """strict = 0 (opt-in): fp64 atomics into the tensor.  The same pairs are drawn and accepted, every cell gets the same
+    addends in another order: raw cells and curves agree to 1e-12 relative (north_star's tolerance), not bit for bit."""
+    if mode == 3:
+        sp = synth.SynthSpec(n_chrom=2, n_inds=6, n_snps=4000, K=7, nsamples=5, rate=3e-7, name="m3")
+        chrom = []
+        for h in range(sp.n_chrom):
+            pos, rate, labels = synth.make_chromosome(sp, h)
+            chrom.append({"pos": pos, "rate": rate, "labels": labels})
+        dl, K = sp.donor_label_vec(), sp.K
+        S, G = 4, 120
+        tw = oracle.mutiply_temp_weight(K, S, synth.random_weights(K, S).ravel(order="F")).reshape(S * S, K * K).ravel(order="F")
+    else:
+        sp, chrom, dl, K, S, G, tw = _small_problem(small, oracle)
+    ids = ind_id_matrix(sp.n_inds, sp.n_chrom)
+    oracle.srand(9)
+    m_o, raw_o, pairs_o = oracle.data_read_packed(mode, sp.ploidy, sp.nsamples, chrom, ids, 0.1, G, 10, K, dl, 0.0, 1.0, S, tw, want_raw=True)
+    lib.set_option("rand_libc", 0)
+    lib.set_option("strict", 0)
+    try:
+        lib.srand(9)
+        m_g, raw_g, st = lib.data_read_packed(mode, sp.ploidy, sp.nsamples, chrom, ids, 0.1, G, 10, K, dl, 0.0, 1.0, S, tw, want_raw=True)
+    finally:
+        lib.set_option("strict", 1)
+    assert st["pairs"] == pairs_o
+    assert st["accepted"] >= int(np.count_nonzero(raw_o))
+    assert np.array_equal(raw_g != 0, raw_o != 0)
+    nz = raw_o != 0
+    assert np.max(np.abs(raw_g[nz] - raw_o[nz]) / np.abs(raw_o[nz])) < 1e-12
+    ok = np.isfinite(m_o) & (m_o != 0)
+    assert np.max(np.abs(m_g[ok] - m_o[ok]) / np.abs(m_o[ok])) < 1e-12
+
+
+def test_device_resident_runs_and_bad_runs(lib, oracle, small):
+    """run-length-encoded paintings already in HBM (the benchmark's `value` configuration) give the same bits as host runs;
+    malformed runs (non-maximal, not ascending, first run not at SNP 0) are refused with FGT_ERR_ARG."""
+    import torch
+    from fastglobetrotter_b200.companion import FgtError
+    sp, chrom, dl, K, S, G, tw = _small_problem(small, oracle)
+    ids = ind_id_matrix(sp.n_inds, sp.n_chrom)
+    oracle.srand(3)
+    m_o, raw_o, _ = oracle.data_read_packed(1, sp.ploidy, sp.nsamples, chrom, ids, 0.1, G, 10, K, dl, 0.0, 1.0, S, tw, want_raw=True)
+    lib.set_option("rand_libc", 0)
+    dev_chrom, keep = [], []
+    for c in chrom:
+        off, runs = lib.rle_encode(c["labels"])
+        t = torch.from_numpy(runs.view(np.int32).reshape(-1, 2).copy()).cuda()
+        keep.append(t)
+        dev_chrom.append({"pos": c["pos"], "rate": c["rate"], "runs": (off, int(t.data_ptr()))})
+    torch.cuda.synchronize()
+    lib.srand(3)
+    m_g, raw_g, st = lib.data_read_packed(1, sp.ploidy, sp.nsamples, dev_chrom, ids, 0.1, G, 10, K, dl, 0.0, 1.0, S, tw, want_raw=True)
+    assert np.array_equal(raw_g, raw_o) and np.array_equal(m_g, m_o)
+    n_o, ev = oracle.data_read_null_packed(sp.ploidy, sp.nsamples, chrom, np.arange(sp.n_inds), 0.1, G, 10, K, dl, 0.0, 1.0)
+    n_g, st = lib.data_read_null_packed(sp.ploidy, sp.nsamples, dev_chrom, np.arange(sp.n_inds), 0.1, G, 10, K, dl, 0.0, 1.0)
+    assert st["pairs"] == ev and np.array_equal(n_g, n_o)
+    # malformed runs
+    off, runs = lib.rle_encode(chrom[0]["labels"])
+    for kind in ("not_maximal", "not_ascending", "late_start"):
+        bad = runs.copy()
+        i = int(off[3]) + 1
+        if kind == "not_maximal":
+            bad["hap"][i] = bad["hap"][i - 1]
+        elif kind == "not_ascending":
+            bad["start"][i] = bad["start"][i - 1]
+        else:
+            bad["start"][int(off[3])] = 1
+        bc = [{"pos": chrom[0]["pos"], "rate": chrom[0]["rate"], "runs": (off, bad)}]
+        with pytest.raises(FgtError) as ei:
+            lib.data_read_packed(1, sp.ploidy, sp.nsamples, bc, np.arange(sp.n_inds), 0.1, G, 10, K, dl, 0.0, 1.0, S, tw)
+        assert ei.value.rc == -5, kind
