@@ -300,7 +300,7 @@ class PackedCompanion(Companion):
                     carr[h].runs_on_device = 1
                 else:
                     rr = np.ascontiguousarray(rr)
-                    assert rr.dtype.itemsize == 8
+                    assert rr.dtype.itemsize == 8 or (rr.ndim == 2 and rr.shape[1] == 2 and rr.dtype.itemsize == 4)
                     keep.append(rr)
                     carr[h].runs = rr.ctypes.data
                     carr[h].runs_on_device = 0

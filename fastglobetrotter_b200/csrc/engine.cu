@@ -76,7 +76,7 @@ int Engine::set_option(const char *key, double v) {
     else if (k == "null_slab_bins") opt.null_slab_bins = iv;
     else if (k == "split_ready") opt.split_ready = iv;
     else if (k == "rand_impl") opt.rand_impl = iv;
-    else if (k == "match_impl") opt.match_impl = iv;
+    else if (k == "commit_impl") opt.commit_impl = iv;
     else if (k == "cache_mb") opt.cache_mb = v;
     else return FGT_ERR_ARG;
     return FGT_OK;
@@ -106,7 +106,7 @@ double Engine::get_option(const char *key) {
     if (k == "null_slab_bins") return opt.null_slab_bins;
     if (k == "split_ready") return opt.split_ready;
     if (k == "rand_impl") return opt.rand_impl;
-    if (k == "match_impl") return opt.match_impl;
+    if (k == "commit_impl") return opt.commit_impl;
     if (k == "cache_mb") return opt.cache_mb;
     return NAN;
 }
@@ -526,6 +526,10 @@ int Engine::setup_runs(const fgt_problem_t &pb, int h, int n_blocks, ChromState 
     const int PM = pb.ploidy * pb.nsamples, n_phys = pb.n_packed_inds;
     const size_t rows = (size_t)n_phys * PM;
     if (!c.run_off || n_blocks <= 0) return FGT_ERR_ARG;
+    if (cs.runs_blocks == n_blocks && cs.runs_pm == PM && cs.h_run_off.size() == rows + 1 && cs.run_src.p &&
+        std::memcmp(cs.h_run_off.data(), c.run_off, (rows + 1) * sizeof(int64_t)) == 0)
+        return FGT_OK;                                       // same rows as the previous call: the device tables are still valid
+    cs.runs_blocks = -1;
     const size_t need = rows * sizeof(long long) + (rows + n_blocks) * sizeof(int32_t) + rows * sizeof(int32_t);
     CK(cudaStreamSynchronize(st_aux_));                      // the previous chromosome's upload from this staging area
     if (pin_rows_cap_ < need) {
@@ -563,6 +567,8 @@ int Engine::setup_runs(const fgt_problem_t &pb, int h, int n_blocks, ChromState 
     if (!rows_ready_) CK(cudaEventCreateWithFlags(&rows_ready_, cudaEventDisableTiming));
     CK(cudaEventRecord(rows_ready_, st_aux_));
     CK(cudaStreamWaitEvent(st_prep_, rows_ready_, 0));
+    cs.h_run_off.assign(c.run_off, c.run_off + rows + 1);
+    cs.runs_blocks = n_blocks; cs.runs_pm = PM;
     return FGT_OK;
 }
 
@@ -611,6 +617,18 @@ int Engine::setup_chromosome(const fgt_problem_t &pb, int h, ChromState &cs, fgt
     const int L = c.nsites, n_phys = pb.n_packed_inds;
     if (L <= 0) return FGT_ERR_ARG;
     const int W = (int)std::ceil(pb.binwidth * pb.num_bins) + (pb.mode == 3 ? 1 : 3);   // C:117 / C:1125
+    if (cs.tab_W == W && cs.nb > 0 && cs.cum.p && (int)cs.h_pos.size() == L && cs.t.cap >= (size_t)n_phys * cs.nb * sizeof(int32_t) &&
+        std::memcmp(cs.h_pos.data(), c.pos, L * sizeof(double)) == 0 && std::memcmp(cs.h_rate.data(), c.rate, L * sizeof(double)) == 0) {
+        // same map and window as the previous call: the device tables are still valid (only the per-call state is reset)
+        cs.n_chunks = 0;
+        cs.totals.assign(n_phys, 0);
+        if (!cs.first.as<int32_t>((size_t)n_phys * cs.nb) || !cs.yoff.as<int32_t>((size_t)n_phys * cs.nb * W) ||
+            !cs.rowoff.as<long long>((size_t)n_phys * (cs.nb + 1)) || !cs.chunk_ptr.as<const Chunk *>(n_phys) ||
+            !cs.ps_ptr.as<const double2 *>(n_phys) || !cs.pop_ptr.as<const int32_t *>(n_phys))
+            return FGT_ERR_CUDA;
+        return FGT_OK;
+    }
+    cs.tab_W = -1;
     // the tables are built straight into pinned memory and uploaded without a host wait (the previous chromosome's
     // upload from the same staging area has to be over first)
     const size_t need = ((size_t)2 * L + W) * sizeof(double);
@@ -647,6 +665,9 @@ int Engine::setup_chromosome(const fgt_problem_t &pb, int h, ChromState &cs, fgt
     CK(cudaEventRecord(tab_ready_, st_aux_));
     CK(cudaStreamWaitEvent(st_prep_, tab_ready_, 0));        // chunk emit / bin sort of this chromosome come after this
     stx.h2d_bytes += 2LL * L * sizeof(double);
+    cs.h_pos.assign(c.pos, c.pos + L);
+    cs.h_rate.assign(c.rate, c.rate + L);
+    cs.tab_W = W;
     return FGT_OK;
 }
 
@@ -1083,7 +1104,7 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
                     ca.n_slabs = (int)slabs.size();
                     ca.slabs = d_slabs; ca.recs = d_recs; ca.regions = d_regions; ca.nd_max = nd_max;
                     ca.tensor_is_zero = (tile_in_smem && (pb.mode == 3 || h == 0)) ? 1 : 0;
-                    ca.match_refine = opt.match_impl == 1 ? 1 : 0;
+                    ca.buckets = opt.commit_impl == 1 ? 1 : 0;
                     ca.tensor = tens_b; ca.accepted = d_acc;
                     ca.task_counter = d_taskctr + batch_seq;
                     launch_commit_ordered(ca, plan_max_w, sc);

@@ -986,7 +986,7 @@ __global__ void __launch_bounds__(128, 8) k_eval_pairs(const EvalArgs a) {
     const int32_t *chpop = cp.pop_ptr[phys];
     const long long rowoff_j = cp.rowoff[(size_t)phys * (nb + 1) + j];
     const long long row_pair0 = a.pair_base[n] + rowoff_j;        // stream position (pairs) of the row's first draw
-    const long long row_rec0 = a.rec_base[n] + rowoff_j;          // the same row in the record buffer of this launch
+    UpdateRec *const row_recs = RELAXED ? nullptr : a.recs + (a.rec_base[n] + rowoff_j) * a.n_slots;   // the row's record regions
     const int f1 = F[j];
     const unsigned inv1 = mod_magic((unsigned)t1);
     const int ns = a.n_slots;
@@ -1037,8 +1037,7 @@ __global__ void __launch_bounds__(128, 8) k_eval_pairs(const EvalArgs a) {
         const int t2 = T[k], f2 = F[k];
         const unsigned inv2 = mod_magic((unsigned)t2);
         const long long seg = row_pair0 + y0;
-        const long long rseg = row_rec0 + y0;
-        UpdateRec *reg = RELAXED ? nullptr : a.recs + rseg * ns;
+        UpdateRec *reg = RELAXED ? nullptr : row_recs + (long long)y0 * ns;
         const int slab0 = a.first_slab[d];
         const BinRef binB{chps + f2, chpop + f2};
         int c[kMaxSlots] = {};
@@ -1047,10 +1046,13 @@ __global__ void __launch_bounds__(128, 8) k_eval_pairs(const EvalArgs a) {
             uint2 r0, r1;
             if (FUSED_RNG) {
                 const unsigned need = 2u * (unsigned)min(64, Y - base);
-                while (ring_w - ring_r < need) {
-                    hist = gen_block31(hist, lane);
-                    if (lane < 31) ring[(ring_w + lane) & (kRingRaws - 1)] = hist >> 1;      // rand() = x >> 1
-                    ring_w += 31;
+                while (ring_w - ring_r < need) {         // four blocks of 31 at a time: at most 127 + 124 draws are buffered
+#pragma unroll
+                    for (int blk = 0; blk < 4; blk++) {
+                        hist = gen_block31(hist, lane);
+                        if (lane < 31) ring[(ring_w + 31 * blk + lane) & (kRingRaws - 1)] = hist >> 1;      // rand() = x >> 1
+                    }
+                    ring_w += 124u;
                 }
                 __syncwarp();
                 const uint2 *r64 = reinterpret_cast<const uint2 *>(ring);
@@ -1100,7 +1102,7 @@ __global__ void __launch_bounds__(128, 8) k_eval_pairs(const EvalArgs a) {
             if (v > 0 && slab < a.n_slabs) {
                 // region directory of task (n, slab): entry (j, d - dlo(slab)); empty entries stay zero
                 RegionEnt ent;
-                ent.base = rseg * ns + (long long)lane * Y;
+                ent.base = (long long)(reg - a.recs) + (long long)lane * Y;
                 ent.cnt = v; ent.pad = 0;
                 a.regions[(((size_t)n * a.n_slabs + slab) * (nb - 1) + j) * a.nd_max + (d - a.slabs[slab].dlo)] = ent;
             }
@@ -1174,7 +1176,16 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
 
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
-template <bool TILE_SMEM>
+// BUCKETS (shared-memory tiles only): the ordered fold without match.any.  A consumer warp files its records, in stream
+// order, into 32 per-lane queues keyed by the low bits of the cell index (five ballots give every record its rank among
+// the records of the same key in its 32-record step); lane l then folds queue l front to back.  Records of one cell always
+// share a queue, so every cell still receives its addends in stream order, and different lanes never touch the same cell:
+// no duplicate detection, no shuffle chains.  Queues are only folded when one is about to overflow (or the task ends), so
+// a fold pass covers several hundred records.
+constexpr int kQCap = 32;         // slots per lane queue (a single 32-record step always fits)
+constexpr int kQueueBytes = kConsumers * (kQCap * 32 * (int)(sizeof(double) + sizeof(int32_t)) + 32 * (int)sizeof(int32_t));
+
+template <bool TILE_SMEM, bool BUCKETS>
 __global__ void __launch_bounds__(32 * (kConsumers + 1)) k_commit_ordered(const CommitArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     UpdateRec *ring = reinterpret_cast<UpdateRec *>(smem_raw);                         // [kStages][kStageRecs]
@@ -1183,7 +1194,8 @@ __global__ void __launch_bounds__(32 * (kConsumers + 1)) k_commit_ordered(const 
     int *stage_cnt = reinterpret_cast<int *>(empty + kStages);                         // [kStages]
     int *task_slot = stage_cnt + kStages;                                              // [1] task broadcast
     RegionEnt *dir = reinterpret_cast<RegionEnt *>(smem_raw + 6144 + 256);              // [32] staged directory entries
-    double *tile = reinterpret_cast<double *>(smem_raw + 6144 + 1024);                 // ring 6 KB + 1 KB control
+    unsigned char *qbase = smem_raw + 6144 + 1024;                                     // ring 6 KB + 1 KB control, then the queues
+    double *tile = reinterpret_cast<double *>(qbase + (BUCKETS ? kQueueBytes : 0));
     const int lane = lane_id();
     const int wid = warp_id();
     const int G = a.G;
@@ -1284,32 +1296,16 @@ __global__ void __launch_bounds__(32 * (kConsumers + 1)) k_commit_ordered(const 
             phase = __shfl_sync(kFull, phase, 0);
         } else {
             // ------------------------------ consumer ------------------------------
-            // software pipeline: the records (and match.any masks) of stage s+1 are fetched before stage s is
-            // folded, so barrier / shared-memory / match latency overlaps the ordered read-modify-write chain.
-            // Lanes that share a cell must add in lane order, so every step needs, per lane, the set of lanes with
-            // the same cell: match.any.  (Measured alternatives, both slower on B200: one ballot per index bit --
-            // 13 votes cost more than one match.any; stamping the tile with lane ids to detect collisions first --
-            // duplicates occur in about half the steps of this workload, so the slow path is the common path.)
-            // Several consumer warps read every stage; each folds only the cells it owns, so a cell's additions
-            // stay in stream order.  Records of other warps share one sentinel key: match.any's cost grows with
-            // the number of distinct keys, so every warp's vote gets cheaper as well.
-            auto same_cell_mask = [&](int cell) -> unsigned {
-                if (!a.match_refine) return __match_any_sync(kFull, cell >= 0 ? (unsigned)cell : 0x80000000u);
-                // match_impl = 1: match.any costs two cycles per DISTINCT key on the SM's single unit, so match on a
-                // 3-bit class of the cell (bit 0 is the owner bit, constant within a warp) -- at most nine keys with
-                // the sentinel -- and let the few lanes that share a class compare their cells through shuffles.
-                const unsigned cls = cell >= 0 ? (((unsigned)cell >> 1) & 7u) : 8u;
-                const unsigned m = __match_any_sync(kFull, cls);
-                unsigned same = 1u << lane;
-                unsigned rest = cell >= 0 ? (m & ~same) : 0u;
-                while (__any_sync(kFull, rest != 0u)) {
-                    const int src = rest ? (__ffs(rest) - 1) : lane;
-                    const int oc = __shfl_sync(kFull, cell, src);
-                    if (rest) { if (oc == cell) same |= 1u << src; rest &= rest - 1; }
-                }
-                return same;
-            };
+            // software pipeline: the records of stage s+1 are fetched (and its ring slot released) before stage s is
+            // folded, so barrier / shared-memory latency overlaps the ordered read-modify-write work.
+            // Several consumer warps read every stage; each handles only the cells it owns, so a cell's additions
+            // stay in stream order.
             struct Staged { int c; int cell[kStageSteps]; double val[kStageSteps]; unsigned g[kStageSteps]; };
+            // ownership: BUCKETS -- alternate blocks of 32 tile cells (the low five bits pick the lane queue, so the 32
+            // lanes of a fold pass hit 32 consecutive doubles: conflict free); otherwise odd / even cells
+            auto owned = [&](int local) -> bool {
+                return BUCKETS ? (((unsigned)local >> 5) % kConsumers == (unsigned)wid) : ((unsigned)local % kConsumers == (unsigned)wid);
+            };
             auto fetch = [&]() -> Staged {
                 Staged s;
                 mbar_wait(&full[stage], phase);
@@ -1322,7 +1318,7 @@ __global__ void __launch_bounds__(32 * (kConsumers + 1)) k_commit_ordered(const 
                     for (int h = 0; h < kStageSteps; h++)
                         if (32 * h + lane < s.c) {
                             const UpdateRec r = rg[32 * h + lane];
-                            if ((unsigned)r.pad % kConsumers == (unsigned)wid) { s.cell[h] = TILE_SMEM ? r.pad : r.cell; s.val[h] = r.val; }
+                            if (owned(r.pad)) { s.cell[h] = TILE_SMEM ? r.pad : r.cell; s.val[h] = r.val; }
                         }
                 }
                 // The refill of this stage is a TMA write (async proxy); the reads above are generic-proxy reads.
@@ -1332,35 +1328,91 @@ __global__ void __launch_bounds__(32 * (kConsumers + 1)) k_commit_ordered(const 
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[stage]);     // records are in registers: the stage can be refilled
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
-                if (s.c >= 0) {
+                if (!BUCKETS && s.c >= 0) {
+                    // Lanes that share a cell must add in lane order, so every step needs, per lane, the set of lanes
+                    // with the same cell: match.any (two cycles per distinct key on the SM's single unit; records of
+                    // other warps share one sentinel key)
 #pragma unroll
                     for (int h = 0; h < kStageSteps; h++)
-                        if (32 * h < s.c) s.g[h] = same_cell_mask(s.cell[h]);
+                        if (32 * h < s.c) s.g[h] = __match_any_sync(kFull, s.cell[h] >= 0 ? (unsigned)s.cell[h] : 0x80000000u);
                 }
                 return s;
             };
-            auto fold = [&](int cell, double val, unsigned grp) {
-                const bool leader = (cell >= 0) && ((grp & lt) == 0);
-                double acc = 0.0;
-                if (leader) acc = TILE_SMEM ? tile[cell] : tens[cell];
-                unsigned rest = leader ? (grp & ~(1u << lane)) : 0u;
-                acc = __dadd_rn(acc, val);
-                while (__any_sync(kFull, rest != 0)) {
-                    const int src = rest ? (__ffs(rest) - 1) : lane;
-                    const double v = __shfl_sync(kFull, val, src);
-                    if (rest) { acc = __dadd_rn(acc, v); rest &= rest - 1; }
-                }
-                if (leader) { if (TILE_SMEM) tile[cell] = acc; else tens[cell] = acc; }
+            if (BUCKETS) {
+                double *qval = reinterpret_cast<double *>(qbase) + (size_t)wid * kQCap * 32;                         // [slot][lane]
+                int32_t *qloc = reinterpret_cast<int32_t *>(qbase + kConsumers * kQCap * 32 * sizeof(double)) + (size_t)wid * kQCap * 32;
+                int32_t *qcnt = reinterpret_cast<int32_t *>(qbase + kConsumers * kQCap * 32 * (sizeof(double) + sizeof(int32_t))) + wid * 32;
+                qcnt[lane] = 0;
                 __syncwarp();
-            };
-            Staged cur = fetch();
-            while (cur.c >= 0) {
-                const Staged nxt = fetch();
+                auto flush = [&]() {                      // every lane folds its own queue, front to back
+                    __syncwarp();
+                    const int nq = qcnt[lane];
+                    const int maxq = __reduce_max_sync(kFull, nq);
+                    for (int i = 0; i < maxq; i++) {
+                        if (i < nq) {
+                            const int loc = qloc[i * 32 + lane];
+                            tile[loc] = __dadd_rn(tile[loc], qval[i * 32 + lane]);
+                        }
+                    }
+                    qcnt[lane] = 0;
+                    __syncwarp();
+                };
+                auto insert = [&](int loc, double val) {  // one 32-record step: append every owned record to the queue of its key
+                    const bool valid = loc >= 0;
+                    const unsigned key = (unsigned)loc & 31u;
+                    unsigned M = __ballot_sync(kFull, valid);
+                    if (M == 0u) return;
 #pragma unroll
-                for (int h = 0; h < kStageSteps; h++)
-                    if (32 * h < cur.c) fold(cur.cell[h], cur.val[h], cur.g[h]);
-                if (wid == 0) n_acc += (unsigned long long)cur.c;
-                cur = nxt;
+                    for (int t = 0; t < 5; t++) {
+                        const bool bit = (key >> t) & 1u;
+                        const unsigned bm = __ballot_sync(kFull, valid && bit);
+                        M &= bit ? bm : ~bm;
+                    }
+                    const int rank = __popc(M & lt);     // records of the same key ahead of this one in the step
+                    int base = valid ? qcnt[key] : 0;
+                    if (__any_sync(kFull, valid && base + rank >= kQCap)) { flush(); base = 0; }
+                    if (valid) {
+                        const int slot = base + rank;
+                        qloc[slot * 32 + key] = loc;
+                        qval[slot * 32 + key] = val;
+                        if ((M >> lane) == 1u) qcnt[key] = slot + 1;        // the last record of its key in this step
+                    }
+                    __syncwarp();
+                };
+                Staged cur = fetch();
+                while (cur.c >= 0) {
+                    const Staged nxt = fetch();
+#pragma unroll
+                    for (int h = 0; h < kStageSteps; h++)
+                        if (32 * h < cur.c) insert(cur.cell[h], cur.val[h]);
+                    if (wid == 0) n_acc += (unsigned long long)cur.c;
+                    cur = nxt;
+                }
+                flush();
+            } else {
+                auto fold = [&](int cell, double val, unsigned grp) {
+                    const bool leader = (cell >= 0) && ((grp & lt) == 0);
+                    double acc = 0.0;
+                    if (leader) acc = TILE_SMEM ? tile[cell] : tens[cell];
+                    unsigned rest = leader ? (grp & ~(1u << lane)) : 0u;
+                    acc = __dadd_rn(acc, val);
+                    while (__any_sync(kFull, rest != 0)) {
+                        const int src = rest ? (__ffs(rest) - 1) : lane;
+                        const double v = __shfl_sync(kFull, val, src);
+                        if (rest) { acc = __dadd_rn(acc, v); rest &= rest - 1; }
+                    }
+                    if (leader) { if (TILE_SMEM) tile[cell] = acc; else tens[cell] = acc; }
+                    __syncwarp();
+                };
+                Staged cur = fetch();
+                while (cur.c >= 0) {
+                    const Staged nxt = fetch();
+#pragma unroll
+                    for (int h = 0; h < kStageSteps; h++)
+                        if (32 * h < cur.c) fold(cur.cell[h], cur.val[h], cur.g[h]);
+                    if (wid == 0) n_acc += (unsigned long long)cur.c;
+                    cur = nxt;
+                }
             }
         }
         __syncthreads();
@@ -1387,15 +1439,19 @@ void launch_commit_ordered(const CommitArgs &a, int max_slab_width, cudaStream_t
     cudaGetDevice(&dev);
     if (tile_bytes + ctrl_bytes <= 200 * 1024) {
         if (!attr_set[dev & 63]) {
-            cudaFuncSetAttribute(k_commit_ordered<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(k_commit_ordered<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(k_commit_ordered<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + kQueueBytes);
             attr_set[dev & 63] = true;
         }
-        const long long per_sm = std::max<long long>(1, (227 * 1024) / (long long)(ctrl_bytes + tile_bytes + 1024));
+        const bool buckets = a.buckets != 0;
+        const size_t smem = ctrl_bytes + tile_bytes + (buckets ? kQueueBytes : 0);
+        const long long per_sm = std::max<long long>(1, (227 * 1024) / (long long)(smem + 1024));
         const long long grid = std::min<long long>(tasks, 148 * std::min<long long>(per_sm, 32));
-        k_commit_ordered<true><<<(unsigned)grid, 32 * (kConsumers + 1), ctrl_bytes + tile_bytes, st>>>(a);
+        if (buckets) k_commit_ordered<true, true><<<(unsigned)grid, 32 * (kConsumers + 1), smem, st>>>(a);
+        else k_commit_ordered<true, false><<<(unsigned)grid, 32 * (kConsumers + 1), smem, st>>>(a);
     } else {
         const long long grid = std::min<long long>(tasks, 148 * 16);
-        k_commit_ordered<false><<<(unsigned)grid, 32 * (kConsumers + 1), ctrl_bytes, st>>>(a);
+        k_commit_ordered<false, false><<<(unsigned)grid, 32 * (kConsumers + 1), ctrl_bytes, st>>>(a);
     }
 }
 

@@ -97,7 +97,7 @@ struct CommitArgs {
     const UpdateRec *recs;
     const RegionEnt *regions;
     int32_t nd_max, tensor_is_zero;
-    int32_t match_refine;         // 1: class match + shuffle refinement instead of one match.any over the cells
+    int32_t buckets;              // 1: lane-queue fold (no match.any) for shared-memory tiles; 0: match.any fold
     double *tensor;
     unsigned long long *accepted;
     int *task_counter;            // zeroed before the launch: persistent CTAs claim (individual, slab) tasks from it

@@ -758,16 +758,16 @@ def _small_problem(small, oracle, S=4, G=120):
 
 
 @pytest.mark.parametrize("rand_impl", [0, 1])
-@pytest.mark.parametrize("match_impl", [0, 1])
-def test_generator_and_commit_variants_are_bit_exact(lib, oracle, small, rand_impl, match_impl):
+@pytest.mark.parametrize("commit_impl", [0, 1])
+def test_generator_and_commit_variants_are_bit_exact(lib, oracle, small, rand_impl, commit_impl):
     """rand_impl: 1 = glibc stream generated by the evaluation warps (device-side jump-ahead), 0 = bulk stream in HBM;
-    match_impl: 1 = class match + shuffle refinement in the ordered commit.  Every combination must give the reference's
+    commit_impl: 1 = lane-queue fold (no match.any), 0 = match.any fold in the ordered commit.  Every combination must give the reference's
     bits, for split rows (eval_parts) and forced batches as well."""
     sp, chrom, dl, K, S, G, tw = _small_problem(small, oracle)
     ids = bootstrap_ids(sp.n_inds, sp.n_chrom, 11)
     lib.set_option("rand_libc", 0)
     lib.set_option("rand_impl", rand_impl)
-    lib.set_option("match_impl", match_impl)
+    lib.set_option("commit_impl", commit_impl)
     try:
         for parts, batch in ((0, 0), (1, 0), (7, 0), (0, 30000)):
             lib.set_option("eval_parts", parts)
@@ -783,7 +783,7 @@ def test_generator_and_commit_variants_are_bit_exact(lib, oracle, small, rand_im
             assert np.array_equal(m_g, m_o)
             assert np.array_equal(lib.rand_fill(3), np.array([oracle.rand() for _ in range(3)], dtype=np.int32))
     finally:
-        for k, v in (("rand_impl", 1), ("match_impl", 0), ("eval_parts", 0), ("batch_pairs", 0)):
+        for k, v in (("rand_impl", 1), ("commit_impl", 0), ("eval_parts", 0), ("batch_pairs", 0)):
             lib.set_option(k, v)
 
 
