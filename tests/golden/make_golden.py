@@ -3,7 +3,11 @@
 oracle/build_ref.py from /root/reference) run in this container.  Commit the outputs; the
 GPU box has no /root/reference.
 
-  tutorial_subset.npz  the first 3 target individuals of the reference's tutorial (chr21+chr22),
+  tutorial_full.npz    ALL 100 target individuals of the reference's tutorial (chr21+chr22, BASELINE.json configs[0]):
+                       what the compiled reference computes through data_read, data_read_mode3 (plain and with a
+                       bootstrap id matrix) and data_read_null on the text files committed under tests/golden/tutorial/
+                       (copies of the reference's tutorial inputs: test vectors); outputs as sha256 + strided samples.
+  tutorial_subset.npz  the first 2 target individuals of the reference's tutorial (chr21+chr22),
                        re-packed (uint16 donor-haplotype ids + recombination maps) together with
                        what the reference computes from them through its .C entry points.
   synth_a.npz          outputs of the reference on a synthetic data set that the tests regenerate
@@ -117,6 +121,49 @@ def tutorial_case(ref):
     print("tutorial_subset.npz", {k: v for k, v in out.items() if k.startswith("pairs") or k.endswith("_sum")})
 
 
+FULL_STRIDE = 997
+
+
+def compact_full(out: dict, key: str, a: np.ndarray):
+    out[key + "_sha256"] = digest(a)
+    out[key + "_sample"] = np.ascontiguousarray(a.ravel()[::FULL_STRIDE])
+    out[key + "_shape"] = np.array(a.shape)
+    out[key + "_sum"] = float(a.sum())
+
+
+def tutorial_full_case(ref):
+    """BASELINE.json configs[0] in full: 100 individuals x 10 samples, chr21 + chr22, K = 26, 291 bins, S = 7."""
+    tdir = os.path.join(HERE, "tutorial")
+    prm = parse_paramfile(os.path.join(tdir, "paramfile.txt"))
+    donors = prm["copyvector.popnames"].split()
+    dl, rec = id_file_inputs(os.path.join(tdir, "individual.txt"), donors, prm["target.popname"])
+    N = len(rec)
+    K, S, bw, G, gs = len(donors), 7, 0.1, 291, 10
+    W = synth.random_weights(K, S, seed=13)
+    tw = ref.temp_weights_for_data_read(K, S, W)
+    cwd = os.getcwd()
+    os.chdir(HERE)                     # the list files name their entries relative to the parent of tutorial/
+    out = {}
+    try:
+        for tag, ids in (("", ind_id_matrix(N, 2)), ("_boot", bootstrap_ids(N, 2, 2026))):
+            for mode in (1, 3):
+                if tag and mode == 3:
+                    continue
+                m, raw, pairs = run_ref(ref, mode, 2, ids, "tutorial/samplefile.txt", "tutorial/recomfile.txt", bw, G, gs, K,
+                                        dl, rec, S, tw, N if mode == 1 else 2 * N)
+                out[f"means{mode}{tag}"], out[f"pairs{mode}{tag}"] = m, pairs
+                compact_full(out, f"raw{mode}{tag}", raw)
+                print("tutorial_full", tag, mode, pairs, flush=True)
+            out[f"ids{tag}"] = ids
+        compact_full(out, "null", ref.coancestry_curves_null(2, "tutorial/samplefile.txt", "tutorial/recomfile.txt", bw, G, gs, K,
+                                                             dl, rec, 0.0, 1.0))
+    finally:
+        os.chdir(cwd)
+    out.update(dict(donor_label_vec=dl, K=K, S=S, bw=bw, G=G, gs=gs, N=N, seed=SEED, tw=tw, n_chrom=2, stride=FULL_STRIDE))
+    np.savez_compressed(os.path.join(HERE, "tutorial_full.npz"), **out)
+    print("tutorial_full.npz", {k: v for k, v in out.items() if k.startswith("pairs") or k.endswith("_sum")})
+
+
 def synth_spec():
     return synth.SynthSpec(n_chrom=2, n_inds=5, n_snps=3500, K=8, nsamples=4, self_copy_frac=0.03, n_extra_inds=2, rate=3.5e-7,
                            seed=SEED + 5, name="golden_a")
@@ -145,5 +192,10 @@ def synth_case(ref):
 if __name__ == "__main__":
     assert build_ref.build(), "needs /root/reference"
     ref = Companion(REF_HOOKED)
-    tutorial_case(ref)
-    synth_case(ref)
+    which = sys.argv[1:] or ["subset", "synth", "full"]
+    if "subset" in which:
+        tutorial_case(ref)
+    if "synth" in which:
+        synth_case(ref)
+    if "full" in which:
+        tutorial_full_case(ref)

@@ -193,3 +193,59 @@ def test_on_disk_pack_cache_round_trip(lib, tmp_path, monkeypatch):
             assert np.array_equal(a, b)
     finally:
         lib.set_option("cache", 1)
+
+
+def test_rle_encode_and_interchange_file_round_trip(lib, tmp_path):
+    """fgt_rle_encode (dense matrix -> runs) and the self-contained chunk-level file format: a text samples file is
+    converted to *.fgtrle once, and a samples list naming the .fgtrle file decodes to the very same paintings."""
+    spec = synth.SynthSpec(n_chrom=2, n_inds=4, n_snps=1200, K=5, nsamples=3, n_extra_inds=2, rate=6e-7, name="rle")
+    data = synth.write_dataset(spec, str(tmp_path))
+    lab = data.chrom[0]["labels"]
+    off, runs = lib.rle_encode(lab)
+    assert off[0] == 0 and off[-1] == runs.size and np.all(np.diff(off) >= 1)
+    back = np.zeros_like(lab)
+    for r in range(lab.shape[0]):
+        rr = runs[off[r]:off[r + 1]]
+        assert rr["start"][0] == 0 and np.all(np.diff(rr["start"].astype(np.int64)) > 0) and np.all(rr["hap"][1:] != rr["hap"][:-1])
+        ends = np.append(rr["start"][1:], lab.shape[1])
+        for s, e, hp in zip(rr["start"], ends, rr["hap"]):
+            back[r, s:e] = hp
+    assert np.array_equal(back, lab)
+    text = _probe(lib, data)
+    sfiles = open(data.samples_list).read().split()
+    packed = []
+    for h, sf in enumerate(sfiles):
+        out = str(tmp_path / f"chr{h + 1}.fgtrle")
+        n = lib.pack_samples(sf, spec.n_snps, out)
+        assert n > 0 and os.path.getsize(out) == 48 + sum(len(x) + 1 for x in synth.file_order(spec)[0]) * spec.ploidy + 8 * (len(synth.file_order(spec)[0]) * spec.ploidy * spec.nsamples + 1) + 8 * n
+        packed.append(out)
+    open(data.samples_list, "w").write("\n".join(packed) + "\n")
+    binary = _probe(lib, data)
+    assert binary[:5] == text[:5]
+    for a, b in zip(text[5], binary[5]):
+        assert np.array_equal(a, b)
+
+
+def test_truncated_gzip_is_fatal_and_cache_is_bounded(lib, tmp_path):
+    """a samples file cut in the middle of its gzip stream ends the process with a message (zlib's error is not mistaken
+    for a clean end of file); the per-process cache of decoded files obeys its byte budget ("cache_mb")."""
+    spec = synth.SynthSpec(n_chrom=3, n_inds=3, n_snps=2000, K=4, nsamples=3, rate=6e-7, name="trunc")
+    data = synth.write_dataset(spec, str(tmp_path))
+    ok = _probe(lib, data)
+    lib.set_option("cache_mb", 0.02)                       # ~20 KB: less than one decoded chromosome
+    try:
+        again = _probe(lib, data)                          # entries are evicted as they come in; results unchanged
+        for a, b in zip(ok[5], again[5]):
+            assert np.array_equal(a, b)
+    finally:
+        lib.set_option("cache_mb", 8192)
+    sfile = open(data.samples_list).read().split()[1]
+    raw = open(sfile, "rb").read()
+    open(sfile, "wb").write(raw[: len(raw) // 2])
+    code = ("import sys, ctypes as C; sys.path.insert(0, %r); from fastglobetrotter_b200.companion import PackedCompanion;"
+            "l = PackedCompanion(); l.lib.fgt_parse_probe.restype = C.c_int;"
+            "rec = (C.c_char_p * 3)(b'Target1', b'Target2', b'Target3'); n = C.c_int32();"
+            "l.lib.fgt_parse_probe(%r.encode(), %r.encode(), C.c_int(2), C.c_int(3), rec, C.byref(n), None, None, None, None, None, None, None, None)"
+            ) % (ROOT, data.samples_list, data.recom_list)
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert p.returncode == 1 and "Something wrong with" in p.stdout
