@@ -141,7 +141,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from fastglobetrotter_b200 import build as fbuild
-    from fastglobetrotter_b200 import shard, synth
+    from fastglobetrotter_b200 import synth
     from fastglobetrotter_b200.companion import PackedCompanion
     from fastglobetrotter_b200.synth_torch import make_chromosome_device, make_chromosome_runs_device
 
@@ -192,39 +192,18 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    # persistent exchange buffers (pinned host <-> device) for the two collectives of a sharded call
     if world > 1:
-        n_cnt = W["n_chrom"] * N
-        cnt_pin = torch.empty(n_cnt, dtype=torch.int64, pin_memory=True)
-        cnt_dev = torch.empty(n_cnt, dtype=torch.int64, device=dev)
-        all_dev = torch.empty(world * n_cnt, dtype=torch.int64, device=dev)
-        all_pin = torch.empty(world * n_cnt, dtype=torch.int64, pin_memory=True)
-        m_pin = torch.empty(S * S * G, dtype=torch.float64, pin_memory=True)
-        m_dev = torch.empty(S * S * G, dtype=torch.float64, device=dev)
+        # the library's own process group: rank 0 draws an NCCL id, torch.distributed only carries its 128 bytes
+        uid = [lib.dist_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        lib.dist_init(rank, world, uid[0])
 
     def one_step(chrom):
-        """one data_read pass of this rank's shard; returns (means partial, stats)"""
-        if world == 1:
-            m, _, st = lib.data_read_packed(*common, chrom, *tail, S, tw)
-            return m, st
-        cnt = lib.count_pairs_packed(*common, chrom, *tail)                        # [Cn, N] local
-        cnt_pin.numpy()[:] = cnt.ravel()
-        cnt_dev.copy_(cnt_pin, non_blocking=True)
-        dist.all_gather_into_tensor(all_dev, cnt_dev)                               # the one exchange of draw counts
-        all_pin.copy_(all_dev, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        by_rank = list(all_pin.numpy().reshape(world, W["n_chrom"], N))
-        # reference order: chromosome-major, individual-minor; ranks own consecutive blocks of individuals
-        offs, total = shard.stream_offsets(by_rank)
-        lib.set_option("reuse_prep", 1)
-        m, _, st = lib.data_read_packed(*common, chrom, *tail, S, tw, num_inds_total=world * N, pair_offset=offs[rank],
-                                        pairs_total=total)
-        m_pin.numpy()[:] = m.ravel()
-        m_dev.copy_(m_pin, non_blocking=True)
-        dist.all_reduce(m_dev)                                                       # S^2 x G fp64 curves
-        m_pin.copy_(m_dev, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return m_pin.numpy().reshape(m.shape).copy(), st
+        """one data_read pass of this rank's shard; returns (curves, stats).  With several ranks the call is collective:
+        pair counts are all-gathered and turned into stream offsets on the device, the partial curves all-reduced,
+        all inside the library (include/fgt_companion.h, fgt_dist_init)."""
+        m, _, st = lib.data_read_packed(*common, chrom, *tail, S, tw, num_inds_total=world * N)
+        return m, st
 
     def timed(chrom, steps, warmup):
         lib.srand(1)                             # every timed series draws the same stream: results are comparable bit for bit
@@ -369,6 +348,7 @@ def run_ours(args):
                     out["parity_checked"] = False
     if world > 1:
         dist.barrier()
+        lib.dist_finalize()
         dist.destroy_process_group()
     if out is not None:
         print(json.dumps(out))

@@ -13,8 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "fastGLOBETROTTERCompanion.so")
-SOURCES = ["kernels.cu", "engine.cu", "companion_api.cpp"]
-HEADERS = ["kernels.cuh", "engine.h", "glibc_rand.h", os.path.join("..", "..", "include", "fgt_companion.h")]
+SOURCES = ["kernels.cu", "engine.cu", "companion_api.cpp", "dist.cpp"]
+HEADERS = ["kernels.cuh", "engine.h", "glibc_rand.h", "dist.h", os.path.join("..", "..", "include", "fgt_companion.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -48,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for s, p in procs:
         if p.wait() != 0:
             raise RuntimeError(f"nvcc failed on {s}")
-    subprocess.check_call(["nvcc", "-shared", "-cudart", "static", "-o", OUT, *objs, "-lz", "-lpthread"])
+    subprocess.check_call(["nvcc", "-shared", "-cudart", "static", "-o", OUT, *objs, "-lz", "-lpthread", "-ldl"])
     return OUT
 
 

@@ -206,6 +206,9 @@ class PackedCompanion(Companion):
         L.fgt_rle_encode.restype = C.c_int
         L.fgt_pack_samples.argtypes = [C.c_char_p, C.c_int, C.c_char_p]
         L.fgt_pack_samples.restype = C.c_int64
+        L.fgt_dist_unique_id.restype = C.c_int
+        L.fgt_dist_init.restype = C.c_int
+        L.fgt_dist_finalize.restype = None
         L.fgt_data_read_packed.argtypes = [C.POINTER(fgt_problem_t), _dp, C.POINTER(fgt_stats_t)]
         L.fgt_data_read_packed.restype = C.c_int
         L.fgt_count_pairs_packed.argtypes = [C.POINTER(fgt_problem_t), C.POINTER(C.c_int64)]
@@ -226,6 +229,23 @@ class PackedCompanion(Companion):
         L.fgt_rand_fill.restype = C.c_int
         L.fgt_chunk_one.restype = C.c_int
         L.fgt_version.restype = C.c_char_p
+
+    # -- multi-process sharding (one process per GPU): NCCL communicator inside the library -----------------
+    def dist_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = self.lib.fgt_dist_unique_id(buf)
+        if rc:
+            raise FgtError(rc)
+        return buf.raw
+
+    def dist_init(self, rank: int, world: int, uid: bytes):
+        assert len(uid) == 128
+        rc = self.lib.fgt_dist_init(C.c_int(rank), C.c_int(world), C.create_string_buffer(uid, 128))
+        if rc:
+            raise FgtError(rc)
+
+    def dist_finalize(self):
+        self.lib.fgt_dist_finalize()
 
     def set_option(self, key: str, value: float):
         rc = self.lib.fgt_set_option(key.encode(), float(value))

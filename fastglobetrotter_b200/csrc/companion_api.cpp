@@ -867,7 +867,7 @@ void curves_from_files(int mode, int *ploidy, int *ind_id_vec, char **samp, char
     pb.binwidth = *binwidth; pb.num_bins = *num_bins; pb.grid_start = *grid_start; pb.num_donors = *num_donors;
     pb.donor_label_vec = donor_label_vec; pb.n_donor_labels = max_hap; pb.weight_min = *weight_min;
     pb.gridweight_max_cutoff = *cutoff; pb.num_surrogates = *num_surrogates; pb.temp_weights = temp_weights;
-    int rc = Engine::get().data_read_packed(pb, means, nullptr, nullptr);
+    int rc = Engine::data_read_multi(pb, means, nullptr);           // one device, or the "devices" option's worth of them
     if (rc) fatal_rc(rc);
     if (std::isnan(means[0])) die("NA values. Exiting....\n");     // reference C:660-663 / C:1620
 }
@@ -926,10 +926,54 @@ void data_read_null(int *ploidy, char **filenameSAMPread, char **filenameRECOMre
     if (std::isnan(chrom_ind_res[0])) die("NA values. Exiting....\n");    // reference C:1055
 }
 
+namespace {
+struct ProcDist { bool on = false; int rank = 0, world = 1; NcclComm comm = nullptr; } g_proc;   // one process per device (torchrun)
+}
+
 int fgt_data_read_packed(const fgt_problem_t *prob, double *means, fgt_stats_t *stats) {
     if (!prob || !means) return FGT_ERR_ARG;
     std::lock_guard<std::mutex> lk(g_api_mu);
-    return Engine::get().data_read_packed(*prob, means, stats, nullptr);
+    if (g_proc.on && !prob->pair_offset && prob->num_inds_total > prob->num_inds) {
+        // this process is one shard of a multi-process call: pair counts and curves are exchanged inside the library
+        DistCtx dc;
+        dc.rank = g_proc.rank; dc.world = g_proc.world; dc.comm = g_proc.comm; dc.h0 = nullptr; dc.store_state = true;
+        return Engine::get().data_read_packed(*prob, means, stats, nullptr, &dc);
+    }
+    return Engine::data_read_multi(*prob, means, stats);
+}
+
+int fgt_dist_unique_id(char *out128) {
+    if (!out128) return FGT_ERR_ARG;
+    if (!nccl().loaded) { fprintf(stderr, "fastGLOBETROTTERCompanion(B200): NCCL unavailable (%s)\n", nccl().why); return FGT_ERR_ARG; }
+    NcclUniqueId id;
+    if (nccl().GetUniqueId(&id) != 0) return FGT_ERR_CUDA;
+    std::memcpy(out128, id.internal, sizeof id.internal);
+    return FGT_OK;
+}
+
+int fgt_dist_init(int rank, int world, const char *id128) {
+    if (!id128 || world < 1 || rank < 0 || rank >= world) return FGT_ERR_ARG;
+    std::lock_guard<std::mutex> lk(g_api_mu);
+    if (!nccl().loaded) { fprintf(stderr, "fastGLOBETROTTERCompanion(B200): NCCL unavailable (%s)\n", nccl().why); return FGT_ERR_ARG; }
+    int rc = Engine::get().prepare_device();            // the communicator lives on the configured device ("device" option)
+    if (rc) return rc;
+    if (g_proc.on && g_proc.comm) { nccl().CommDestroy(g_proc.comm); g_proc = ProcDist{}; }
+    NcclUniqueId id;
+    std::memcpy(id.internal, id128, sizeof id.internal);
+    NcclComm c = nullptr;
+    const int nrc = nccl().CommInitRank(&c, world, id, rank);
+    if (nrc != 0) {
+        fprintf(stderr, "fastGLOBETROTTERCompanion(B200): ncclCommInitRank failed (%s)\n", nccl().GetErrorString ? nccl().GetErrorString(nrc) : "?");
+        return FGT_ERR_CUDA;
+    }
+    g_proc.on = world > 1; g_proc.rank = rank; g_proc.world = world; g_proc.comm = c;
+    return FGT_OK;
+}
+
+void fgt_dist_finalize(void) {
+    std::lock_guard<std::mutex> lk(g_api_mu);
+    if (g_proc.comm && nccl().loaded) nccl().CommDestroy(g_proc.comm);
+    g_proc = ProcDist{};
 }
 
 int fgt_count_pairs_packed(const fgt_problem_t *prob, int64_t *out) {
@@ -944,7 +988,7 @@ int fgt_data_read_null_packed(const fgt_problem_t *prob, const int32_t *rec_rows
     return Engine::get().data_read_null_packed(*prob, rec_rows, chrom_ind_res, stats);
 }
 
-int64_t fgt_get_raw_counts(double *out, int64_t capacity) { return Engine::get().get_raw(out, capacity); }
+int64_t fgt_get_raw_counts(double *out, int64_t capacity) { return Engine::get_raw_all(out, capacity); }
 
 int fgt_set_option(const char *key, double value) { return key ? Engine::get().set_option(key, value) : FGT_ERR_ARG; }
 double fgt_get_option(const char *key) { return key ? Engine::get().get_option(key) : NAN; }

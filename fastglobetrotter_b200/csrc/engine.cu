@@ -10,6 +10,8 @@
 #include <cstring>
 #include <cstdlib>
 #include <future>
+#include <mutex>
+#include <thread>
 
 namespace fgt {
 
@@ -42,9 +44,20 @@ void DevBuf::release() {
     p = nullptr; cap = 0;
 }
 
-Engine &Engine::get() {
-    static Engine e;
-    return e;
+static Options &global_options() {
+    static Options o;
+    return o;
+}
+
+Engine::Engine() : opt(global_options()) {}
+
+Engine &Engine::get(int idx) {
+    static Engine *pool = []() {
+        Engine *p = new Engine[kMaxEngines];      // never destroyed: CUDA may already be gone when static destructors run
+        for (int i = 0; i < kMaxEngines; i++) p[i].idx_ = i;
+        return p;
+    }();
+    return pool[(idx >= 0 && idx < kMaxEngines) ? idx : 0];
 }
 
 int Engine::set_option(const char *key, double v) {
@@ -78,6 +91,7 @@ int Engine::set_option(const char *key, double v) {
     else if (k == "rand_impl") opt.rand_impl = iv;
     else if (k == "commit_impl") opt.commit_impl = iv;
     else if (k == "cache_mb") opt.cache_mb = v;
+    else if (k == "devices") opt.devices = std::max(1, std::min(iv, kMaxEngines));
     else return FGT_ERR_ARG;
     return FGT_OK;
 }
@@ -108,6 +122,7 @@ double Engine::get_option(const char *key) {
     if (k == "rand_impl") return opt.rand_impl;
     if (k == "commit_impl") return opt.commit_impl;
     if (k == "cache_mb") return opt.cache_mb;
+    if (k == "devices") return opt.devices;
     return NAN;
 }
 
@@ -122,7 +137,8 @@ int Engine::ensure_init() {
         return FGT_ERR_NO_DEVICE;
     }
     if (opt.device >= n) return FGT_ERR_ARG;
-    CK(cudaSetDevice(opt.device));
+    device_ = (opt.device + idx_) % n;            // engine i of a multi-device call sits on the i-th device after the configured one
+    CK(cudaSetDevice(device_));
     if (!st_) CK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
     if (!st_prep_) CK(cudaStreamCreateWithFlags(&st_prep_, cudaStreamNonBlocking));
     if (!st_copy_) CK(cudaStreamCreateWithFlags(&st_copy_, cudaStreamNonBlocking));
@@ -521,12 +537,12 @@ int Engine::prep_block(const fgt_problem_t &pb, int h, int p0, int p1, int blk, 
 // Per-row tables of a run-length-encoded chromosome, built in pinned memory and uploaded once: where each row's runs
 // start, how many it has, and -- per block of individuals -- the chunk offsets of its rows (for weight_min < 1 a chunk
 // is a run, so nothing has to be counted on the device).
-int Engine::setup_runs(const fgt_problem_t &pb, int h, int n_blocks, ChromState &cs) {
+int Engine::setup_runs(const fgt_problem_t &pb, int h, int n_blocks, int p_lo, int p_hi, ChromState &cs) {
     const fgt_chrom_t &c = pb.chrom[h];
     const int PM = pb.ploidy * pb.nsamples, n_phys = pb.n_packed_inds;
     const size_t rows = (size_t)n_phys * PM;
-    if (!c.run_off || n_blocks <= 0) return FGT_ERR_ARG;
-    if (cs.runs_blocks == n_blocks && cs.runs_pm == PM && cs.h_run_off.size() == rows + 1 && cs.run_src.p &&
+    if (!c.run_off || n_blocks <= 0 || p_lo < 0 || p_hi > n_phys || p_lo >= p_hi) return FGT_ERR_ARG;
+    if (cs.runs_blocks == n_blocks && cs.runs_pm == PM && cs.runs_lo == p_lo && cs.runs_hi == p_hi && cs.h_run_off.size() == rows + 1 && cs.run_src.p &&
         std::memcmp(cs.h_run_off.data(), c.run_off, (rows + 1) * sizeof(int64_t)) == 0)
         return FGT_OK;                                       // same rows as the previous call: the device tables are still valid
     cs.runs_blocks = -1;
@@ -548,7 +564,8 @@ int Engine::setup_runs(const fgt_problem_t &pb, int h, int n_blocks, ChromState 
         cnt[r] = (int32_t)(e0 - b0);
     }
     for (int b = 0; b < n_blocks; b++) {
-        const size_t r0 = (size_t)((long long)n_phys * b / n_blocks) * PM, r1 = (size_t)((long long)n_phys * (b + 1) / n_blocks) * PM;
+        const long long pc = p_hi - p_lo;
+        const size_t r0 = (size_t)(p_lo + pc * b / n_blocks) * PM, r1 = (size_t)(p_lo + pc * (b + 1) / n_blocks) * PM;
         int32_t *base = roff + r0 + b;
         long long acc = 0;
         base[0] = 0;
@@ -568,7 +585,7 @@ int Engine::setup_runs(const fgt_problem_t &pb, int h, int n_blocks, ChromState 
     CK(cudaEventRecord(rows_ready_, st_aux_));
     CK(cudaStreamWaitEvent(st_prep_, rows_ready_, 0));
     cs.h_run_off.assign(c.run_off, c.run_off + rows + 1);
-    cs.runs_blocks = n_blocks; cs.runs_pm = PM;
+    cs.runs_blocks = n_blocks; cs.runs_pm = PM; cs.runs_lo = p_lo; cs.runs_hi = p_hi;
     return FGT_OK;
 }
 
@@ -690,8 +707,8 @@ long long Engine::prep_sig(const fgt_problem_t &pb) const {
     return (long long)(hsh | 1ULL);
 }
 
-int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t *stats, int64_t *count_only) {
-    const int rc = data_read_packed_impl(pb, means, stats, count_only);
+int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t *stats, int64_t *count_only, const DistCtx *dist) {
+    const int rc = data_read_packed_impl(pb, means, stats, count_only, dist);
     if (rc != FGT_OK && rc != FGT_ERR_NO_DEVICE) {
         // an error return may leave work of earlier blocks in flight on the library's streams: drain it before the
         // caller (or the next call) touches the buffers again
@@ -701,7 +718,7 @@ int Engine::data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t
     return rc;
 }
 
-int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_stats_t *stats, int64_t *count_only) {
+int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_stats_t *stats, int64_t *count_only, const DistCtx *dist) {
     int rc = ensure_init();
     if (rc) return rc;
     if ((pb.mode != 1 && pb.mode != 3) || pb.ploidy <= 0 || pb.nsamples <= 0 || pb.num_chrom <= 0 || pb.num_inds <= 0 ||
@@ -711,7 +728,7 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
         const fgt_chrom_t &c = pb.chrom[h];
         if (c.runs ? !c.run_off : (!c.labels || (pb.label_bytes != 2 && pb.label_bytes != 4))) return FGT_ERR_ARG;
     }
-    CK(cudaSetDevice(opt.device));
+    CK(cudaSetDevice(device_));
     fgt_stats_t stx{};
     launches_ = 0;
     cudaEvent_t ev[4];
@@ -724,6 +741,11 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
     const int N = pb.num_inds, Cn = pb.num_chrom, K = pb.num_donors, G = pb.num_bins, S = pb.num_surrogates;
     const int PM = pb.ploidy * pb.nsamples;
     const int n_phys = pb.n_packed_inds;
+    // sharded call: this engine handles `N` of the `num_inds_total` individuals; where its draws start in the shared
+    // stream follows from the other shards' pair counts, exchanged and prefix-summed on the device (dist.h)
+    const bool dist_on = dist && dist->world > 1 && !count_only;
+    const int n_msg = dist_on ? std::max(pb.num_inds_total, N) : 0;      // individuals per shard in the count message (padded)
+    if (dist_on && (pb.pair_offset || !dist->comm || !nccl().loaded)) return FGT_ERR_ARG;
     int *d_err = d_err_.as<int>(4);
     unsigned long long *d_acc = d_accepted_.as<unsigned long long>(2);
     CK(cudaMemsetAsync(d_err, 0, 4 * sizeof(int), st_));
@@ -768,7 +790,8 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
     }
 
     History h0;
-    if (!count_only && !fetch_history(h0)) {
+    if (dist && dist->h0) std::memcpy(h0.x, dist->h0, sizeof h0.x);      // all shards start from one generator state
+    else if (!count_only && !fetch_history(h0)) {
         fprintf(stderr, "fastGLOBETROTTERCompanion(B200): libc rand() is not in its default TYPE_3 state\n");
         return FGT_ERR_RAND;
     }
@@ -858,6 +881,21 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
         d_recbase = d_recbase_.as<long long>((size_t)Cn * N);
         if (!d_slabs || !d_pairbase || !d_physof || !d_hist || !d_recbase) return FGT_ERR_CUDA;
         d_h0 = d_hist + ((size_t)Cn * N + 1) * kLag;       // the generator state at call entry (fused generator)
+        if (dist_on) {
+            if (impl == 1 || !fused_rng) {
+                fprintf(stderr, "fastGLOBETROTTERCompanion(B200): sharded calls need the in-kernel generator (rand_impl=1, accum_impl=2)\n");
+                return FGT_ERR_ARG;
+            }
+            const size_t msg = (size_t)n_msg + 1;
+            if (!d_msg_.as<long long>(msg) || !d_msg_all_.as<long long>(msg * dist->world) || !d_streampos_.as<long long>(2)) return FGT_ERR_CUDA;
+            if (pin_msg_cap_ < msg + 2) {
+                if (pin_msg_) cudaFreeHost(pin_msg_);
+                pin_msg_ = nullptr; pin_msg_cap_ = 0;
+                if (cudaHostAlloc((void **)&pin_msg_, (msg + 2 + 64) * sizeof(long long), cudaHostAllocDefault) != cudaSuccess) return FGT_ERR_CUDA;
+                pin_msg_cap_ = msg + 2 + 64;
+            }
+            CK(cudaMemsetAsync(d_streampos_.p, 0, 2 * sizeof(long long), st_));
+        }
         CK(cudaMemcpyAsync(d_slabs, slabs.data(), slabs.size() * sizeof(SlabDesc), cudaMemcpyHostToDevice, st_));
         if (impl != 1) {
             d_firstslab = d_firstslab_.as<int32_t>(W0);
@@ -1004,7 +1042,8 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
                 CK(cudaMemcpyAsync(dh, pin_hist + hist_used * kLag, sizeof hh.x, cudaMemcpyHostToDevice, st_));
                 hist_used++;
             }
-            CK(cudaMemcpyAsync(d_pairbase + (size_t)h * N + b0, hp, Nb * sizeof(long long), cudaMemcpyHostToDevice, st_));
+            if (!dist_on)        // (sharded calls: k_dist_offsets has already written the stream positions of chromosome h)
+                CK(cudaMemcpyAsync(d_pairbase + (size_t)h * N + b0, hp, Nb * sizeof(long long), cudaMemcpyHostToDevice, st_));
             CK(cudaMemcpyAsync(d_recbase + (size_t)h * N + b0, hr, Nb * sizeof(long long), cudaMemcpyHostToDevice, st_));
             CK(cudaMemcpyAsync(d_physof + (size_t)h * N + b0, hq, Nb * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
             uint32_t *d_draws = nullptr;
@@ -1143,34 +1182,41 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
         const bool in_hbm = use_runs ? c.runs_on_device != 0 : c.labels_on_device != 0;
         const size_t rows_all = (size_t)n_phys * PM;
         const size_t bytes_per_ind = (size_t)PM * c.nsites * pb.label_bytes;
-        const size_t input_bytes = use_runs ? (size_t)c.run_off[rows_all] * sizeof(fgt_run_t) : bytes_per_ind * n_phys;
+        // only the packed individuals this call's pseudo-individuals use are copied, chunked and binned (a shard of a
+        // multi-GPU call, or a bootstrap id matrix that leaves some individuals out)
+        int p_lo = n_phys, p_hi = 0;
+        for (int n = 0; n < N; n++) { p_lo = std::min(p_lo, used[h][n]); p_hi = std::max(p_hi, used[h][n] + 1); }
+        if (reuse) { p_lo = 0; p_hi = n_phys; }
+        const int p_cnt = p_hi - p_lo;
+        const size_t input_bytes = use_runs ? (size_t)(c.run_off[(size_t)p_hi * PM] - c.run_off[(size_t)p_lo * PM]) * sizeof(fgt_run_t)
+                                            : bytes_per_ind * p_cnt;
         int n_blocks = 1;
         if (!reuse) {
-            if (!in_hbm) n_blocks = (int)std::min<size_t>(n_phys, std::max<size_t>(1, input_bytes / (48u << 20)));
+            if (!in_hbm) n_blocks = (int)std::min<size_t>(p_cnt, std::max<size_t>(1, input_bytes / (48u << 20)));
             else n_blocks = 1;
-            if (opt.blocks > 0) n_blocks = std::min(n_phys, opt.blocks);
+            if (opt.blocks > 0) n_blocks = std::min(p_cnt, opt.blocks);
         }
         // host-resident paintings: upload the chromosome's tables before the painting copies fill the copy engine
         if (!reuse && !in_hbm) {
             rc = setup_chromosome(pb, h, cs, stx);
             if (rc) return rc;
-            if (use_runs) { rc = setup_runs(pb, h, n_blocks, cs); if (rc) return rc; }
+            if (use_runs) { rc = setup_runs(pb, h, n_blocks, p_lo, p_hi, cs); if (rc) return rc; }
         }
         const void *d_lab = use_runs ? (const void *)c.runs : c.labels;
         std::vector<cudaEvent_t> copy_done(n_blocks, nullptr);
-        auto blk_lo = [&](int b) { return (int)((long long)n_phys * b / n_blocks); };
+        auto blk_lo = [&](int b) { return p_lo + (int)((long long)p_cnt * b / n_blocks); };
         // byte range of block b inside the chromosome's painting buffer (dense rows, or the rows' runs)
         auto blk_off = [&](int p) { return use_runs ? (size_t)c.run_off[(size_t)p * PM] * sizeof(fgt_run_t) : bytes_per_ind * p; };
         if (!reuse && !in_hbm) {
             void *buf = d_labels_.get(input_bytes);
             if (!buf) return FGT_ERR_CUDA;
-            d_lab = buf;
+            d_lab = (const char *)buf - blk_off(p_lo);       // addressed like the host copy: the buffer holds [p_lo, p_hi) only
             if (labels_free) { CK(cudaStreamWaitEvent(st_copy_, labels_free, 0)); CK(cudaStreamWaitEvent(st_copy2_, labels_free, 0)); }
             const char *src = use_runs ? (const char *)c.runs : (const char *)c.labels;
             for (int b = 0; b < n_blocks; b++) {
                 const int p0 = blk_lo(b), p1 = blk_lo(b + 1);
                 cudaStream_t cstream = (opt.copy_streams > 1 && (b & 1)) ? st_copy2_ : st_copy_;   // two DMA engines
-                CK(cudaMemcpyAsync((char *)buf + blk_off(p0), src + blk_off(p0), blk_off(p1) - blk_off(p0), cudaMemcpyHostToDevice, cstream));
+                CK(cudaMemcpyAsync((char *)buf + (blk_off(p0) - blk_off(p_lo)), src + blk_off(p0), blk_off(p1) - blk_off(p0), cudaMemcpyHostToDevice, cstream));
                 copy_done[b] = new_event();
                 CK(cudaEventRecord(copy_done[b], cstream));
             }
@@ -1184,7 +1230,7 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
             }
             rc = setup_chromosome(pb, h, cs, stx);
             if (rc) return rc;
-            if (use_runs) { rc = setup_runs(pb, h, n_blocks, cs); if (rc) return rc; stx.h2d_bytes += (int64_t)rows_all * 16; }
+            if (use_runs) { rc = setup_runs(pb, h, n_blocks, p_lo, p_hi, cs); if (rc) return rc; stx.h2d_bytes += (int64_t)rows_all * 16; }
         }
         int next_n = 0;
         for (int b = 0; b < n_blocks; b++) {
@@ -1199,6 +1245,26 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
                 if (b == n_blocks - 1) labels_free = ready;
             }
             if (count_only) continue;
+            if (dist_on) {
+                if (b < n_blocks - 1) continue;           // a shard's stream positions need the whole chromosome's counts
+                // one all-gather of the pair counts, offsets computed on the device: nothing waits on the host
+                long long *msg = pin_msg_;
+                CK(cudaStreamSynchronize(st_aux_));       // (the previous chromosome's message has left the staging buffer)
+                msg[0] = N;
+                for (int n = 0; n < N; n++) msg[1 + n] = cs.totals[used[h][n]];
+                for (int n = N; n < n_msg; n++) msg[1 + n] = 0;
+                const size_t mlen = (size_t)n_msg + 1;
+                CK(cudaMemcpyAsync(d_msg_.p, msg, mlen * sizeof(long long), cudaMemcpyHostToDevice, st_aux_));
+                cudaEvent_t msg_up = new_event();
+                CK(cudaEventRecord(msg_up, st_aux_));
+                CK(cudaStreamWaitEvent(st_, msg_up, 0));
+                const int nrc = nccl().AllGather(d_msg_.p, d_msg_all_.p, mlen, kNcclInt64, dist->comm, st_);
+                if (nrc != 0) { fprintf(stderr, "fastGLOBETROTTERCompanion(B200): ncclAllGather failed (%d)\n", nrc); return FGT_ERR_CUDA; }
+                launch_dist_offsets((const long long *)d_msg_all_.p, dist->world, dist->rank, n_msg, (long long *)d_streampos_.p,
+                                    d_pairbase + (size_t)h * N, st_);
+                launches_ += 1;
+                stx.h2d_bytes += (int64_t)(mlen * sizeof(long long));
+            }
             // pseudo-individuals whose packed individual (and all earlier ones in stream order) are ready
             int n_end = next_n;
             if (b == n_blocks - 1) n_end = N;
@@ -1272,12 +1338,23 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
     double *d_rs = d_rs_.as<double>((size_t)N * S * G), *d_ratio = d_ratio_.as<double>((size_t)N * S * S * G);
     double *d_means = d_means_.as<double>((size_t)S * S * G);
     if (!d_rs || !d_ratio || !d_means) return FGT_ERR_CUDA;
-    CK(cudaMemcpyAsync(d_means, means, (size_t)S * S * G * sizeof(double), cudaMemcpyHostToDevice, sc));
+    std::vector<double> part;                      // sharded call: the all-reduced curves before they are added to the caller's
+    if (dist_on) CK(cudaMemsetAsync(d_means, 0, (size_t)S * S * G * sizeof(double), sc));
+    else CK(cudaMemcpyAsync(d_means, means, (size_t)S * S * G * sizeof(double), cudaMemcpyHostToDevice, sc));
     launch_normalise(d_results, N, S, G, pb.num_inds_total > 0 ? pb.num_inds_total : N, d_rs, d_ratio, sc);
     launch_mean_accum(d_ratio, N, S, G, d_means, sc);
     launches_ += 2;
-    CK(cudaMemcpyAsync(means, d_means, (size_t)S * S * G * sizeof(double), cudaMemcpyDeviceToHost, sc));
-    stx.h2d_bytes += (int64_t)S * S * G * 8;
+    if (dist_on) {
+        // the one all-reduce of the S^2 x G partial curves (every shard ends up with the sum)
+        const int nrc = nccl().AllReduce(d_means, d_means, (size_t)S * S * G, kNcclFloat64, kNcclSum, dist->comm, sc);
+        if (nrc != 0) { fprintf(stderr, "fastGLOBETROTTERCompanion(B200): ncclAllReduce failed (%d)\n", nrc); return FGT_ERR_CUDA; }
+        part.resize((size_t)S * S * G);
+        CK(cudaMemcpyAsync(part.data(), d_means, (size_t)S * S * G * sizeof(double), cudaMemcpyDeviceToHost, sc));
+        CK(cudaMemcpyAsync(pin_msg_ + n_msg + 1, d_streampos_.p, sizeof(long long), cudaMemcpyDeviceToHost, sc));   // pairs drawn by ALL shards
+    } else {
+        CK(cudaMemcpyAsync(means, d_means, (size_t)S * S * G * sizeof(double), cudaMemcpyDeviceToHost, sc));
+        stx.h2d_bytes += (int64_t)S * S * G * 8;
+    }
     stx.d2h_bytes += (int64_t)S * S * G * 8;
     CK(cudaEventRecord(ev[2], sc));
     int herr[4];
@@ -1295,8 +1372,12 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
     if (tables_ready) cudaEventDestroy(tables_ready);
     if (herr[0]) { for (auto e2 : evs) cudaEventDestroy(e2); return err_to_code(herr[0]); }
 
+    if (dist_on) {
+        for (size_t i = 0; i < part.size(); i++) means[i] += part[i];       // added into the caller's buffer (C:644)
+        last_total_pairs_ = pin_msg_[n_msg + 1];
+    } else last_total_pairs_ = all_pairs;
     // the stream moves on by two draws per sampled pair of the WHOLE call (all shards), C:136-137
-    store_history(apply_jump(poly_pow_E(2ULL * (uint64_t)all_pairs), h0));
+    if (!dist || dist->store_state) store_history(apply_jump(poly_pow_E(2ULL * (uint64_t)last_total_pairs_), h0));
 
     float ms_eval = 0.f, ms_commit = 0.f, ms_rand_spec = 0.f;
     for (Span &s : spans) {
@@ -1330,6 +1411,114 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
     return FGT_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// One call spread over several GPUs of this process ("devices" option): one host thread and one engine per device, the
+// pseudo-individuals in contiguous blocks (all chromosomes of an individual on one device: its cells must be folded in
+// chromosome order).  The shards exchange their pair counts with one all-gather per chromosome and place their draws on
+// the device; one all-reduce sums the partial curves (dist.h).  Raw tensors stay bit-exact, `means` are summed in
+// another order than the reference's (<= 1e-12 relative).
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct MultiComms {
+    std::mutex mu;
+    int n = 0, first_dev = -1;
+    NcclComm comm[kMaxEngines] = {};
+} g_multi;
+int g_last_multi = 1;       // engines that took part in the most recent data_read call (for fgt_get_raw_counts)
+int g_last_multi_mode = 1;
+}  // namespace
+
+int Engine::data_read_multi(const fgt_problem_t &pb, double *means, fgt_stats_t *stats) {
+    Engine &e0 = Engine::get(0);
+    g_last_multi = 1;
+    int rc = e0.ensure_init();
+    if (rc) return rc;
+    int ndev = 0;
+    cudaGetDeviceCount(&ndev);
+    const int n = std::min(std::min(e0.opt.devices, ndev), std::min(pb.num_inds, kMaxEngines));
+    if (n <= 1 || pb.pair_offset) return e0.data_read_packed(pb, means, stats, nullptr);
+    if (!nccl().loaded) {
+        fprintf(stderr, "fastGLOBETROTTERCompanion(B200): \"devices\" > 1 needs NCCL (%s)\n", nccl().why);
+        return FGT_ERR_ARG;
+    }
+    {
+        std::lock_guard<std::mutex> lk(g_multi.mu);
+        if (g_multi.n != n || g_multi.first_dev != e0.opt.device) {
+            for (int i = 0; i < g_multi.n; i++) if (g_multi.comm[i]) nccl().CommDestroy(g_multi.comm[i]);
+            int devs[kMaxEngines];
+            for (int i = 0; i < n; i++) devs[i] = (e0.opt.device + i) % ndev;
+            const int nrc = nccl().CommInitAll(g_multi.comm, n, devs);
+            if (nrc != 0) {
+                fprintf(stderr, "fastGLOBETROTTERCompanion(B200): ncclCommInitAll failed (%s)\n", nccl().GetErrorString ? nccl().GetErrorString(nrc) : "?");
+                g_multi.n = 0;
+                return FGT_ERR_CUDA;
+            }
+            g_multi.n = n; g_multi.first_dev = e0.opt.device;
+        }
+    }
+    History h0;
+    if (!e0.snapshot_state(h0)) {
+        fprintf(stderr, "fastGLOBETROTTERCompanion(B200): libc rand() is not in its default TYPE_3 state\n");
+        return FGT_ERR_RAND;
+    }
+    const int N = pb.num_inds, Cn = pb.num_chrom;
+    const size_t cells = (size_t)pb.num_surrogates * pb.num_surrogates * pb.num_bins;
+    std::vector<std::vector<double>> part(n, std::vector<double>(cells, 0.0));
+    std::vector<fgt_stats_t> st(n);
+    std::vector<int> rcs(n, 0);
+    std::vector<std::thread> th;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int d = 0; d < n; d++) {
+        th.emplace_back([&, d]() {
+            const int base = N / n, rem = N % n;
+            const int lo = d * base + std::min(d, rem), hi = lo + base + (d < rem ? 1 : 0);
+            fgt_problem_t sub = pb;
+            sub.num_inds = hi - lo;
+            sub.ind_rows = pb.ind_rows + (size_t)lo * Cn;
+            sub.num_inds_total = pb.num_inds_total > 0 ? pb.num_inds_total : N;
+            DistCtx dc;
+            dc.rank = d; dc.world = n; dc.comm = g_multi.comm[d]; dc.h0 = h0.x; dc.store_state = false;
+            rcs[d] = Engine::get(d).data_read_packed(sub, part[d].data(), &st[d], nullptr, &dc);
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int d = 0; d < n; d++) if (rcs[d]) return rcs[d];
+    for (size_t i = 0; i < cells; i++) means[i] += part[0][i];         // every shard holds the all-reduced sum
+    e0.advance_state(h0, Engine::get(0).last_total_pairs_);
+    fgt_stats_t agg{};
+    for (int d = 0; d < n; d++) {
+        agg.pairs += st[d].pairs; agg.accepted += st[d].accepted; agg.chunks += st[d].chunks;
+        agg.kernel_launches += st[d].kernel_launches; agg.h2d_bytes += st[d].h2d_bytes; agg.d2h_bytes += st[d].d2h_bytes;
+        agg.accum_launches += st[d].accum_launches;
+        agg.ms_chunk = std::max(agg.ms_chunk, st[d].ms_chunk); agg.ms_rand = std::max(agg.ms_rand, st[d].ms_rand);
+        agg.ms_accum = std::max(agg.ms_accum, st[d].ms_accum); agg.ms_project = std::max(agg.ms_project, st[d].ms_project);
+    }
+    agg.ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    e0.last_stats = agg;
+    if (stats) *stats = agg;
+    g_last_multi = n;
+    g_last_multi_mode = pb.mode;
+    return FGT_OK;
+}
+
+int64_t Engine::get_raw_all(double *out, int64_t cap) {
+    // raw tensors of the last call: one engine, or the shards of a multi-device call in individual order (mode 1 only:
+    // mode 3 stores its tensors in tabulate-call order, chromosome-major, which interleaves the shards)
+    if (g_last_multi <= 1) return Engine::get(0).get_raw(out, cap);
+    if (g_last_multi_mode != 1) return 0;
+    int64_t total = 0;
+    for (int d = 0; d < g_last_multi; d++) {
+        const int64_t c = Engine::get(d).get_raw(nullptr, 0);
+        if (c <= 0) return 0;
+        if (out) {
+            if (total + c > cap) return FGT_ERR_ARG;
+            Engine::get(d).get_raw(out + total, c);
+        }
+        total += c;
+    }
+    return total;
+}
+
 int64_t Engine::get_raw(double *out, int64_t cap) {
     if (raw_count_ <= 0 || (int64_t)raw_host_.size() < raw_count_) return 0;
     if (out) {
@@ -1348,7 +1537,7 @@ int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_ro
     if (pb.ploidy <= 0 || pb.nsamples <= 0 || pb.num_chrom <= 0 || pb.num_inds <= 0 || pb.n_packed_inds <= 0 ||
         (pb.label_bytes != 2 && pb.label_bytes != 4) || pb.num_bins <= 0 || pb.num_donors <= 0 || !(pb.binwidth > 0))
         return FGT_ERR_ARG;
-    CK(cudaSetDevice(opt.device));
+    CK(cudaSetDevice(device_));
     fgt_stats_t stx{};
     launches_ = 0;
     cudaEvent_t e0, e1, e2;
@@ -1507,7 +1696,7 @@ int Engine::outer_weights(double *tempweights, const double *weights_mat, int S,
     int rc = ensure_init();
     if (rc) return rc;
     if (S <= 0 || K <= 0) return FGT_ERR_ARG;
-    CK(cudaSetDevice(opt.device));
+    CK(cudaSetDevice(device_));
     double *dw = d_rs_.as<double>((size_t)S * K), *dout = d_tw_.as<double>((size_t)S * S * K * K);
     if (!dw || !dout) return FGT_ERR_CUDA;
     CK(cudaMemcpyAsync(dw, weights_mat, (size_t)S * K * sizeof(double), cudaMemcpyHostToDevice, st_));

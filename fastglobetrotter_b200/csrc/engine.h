@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../include/fgt_companion.h"
+#include "dist.h"
 #include "glibc_rand.h"
 #include "kernels.cuh"
 
@@ -27,7 +28,7 @@ struct ChromState {            // per chromosome device state that must outlive 
     // (the R driver calls data_read ~100 times on one data set) skips the rebuild and the upload
     std::vector<double> h_pos, h_rate;
     std::vector<int64_t> h_run_off;
-    int tab_W = -1, runs_blocks = -1, runs_pm = -1;
+    int tab_W = -1, runs_blocks = -1, runs_pm = -1, runs_lo = -1, runs_hi = -1;
     std::vector<DevBuf> sorted_blocks;   // data_read path: one sorted-chunk buffer per block of individuals
     int nb = 0, W = 0;
     std::vector<long long> totals;   // [n_phys] pairs each packed individual samples on this chromosome
@@ -60,19 +61,26 @@ struct Options {
     int commit_impl = 0;    // commit kernel, shared-memory tiles: 0 = match.any fold (measured faster: 1.64 vs 3.4 ms on the bench
                             // workload), 1 = lane-queue fold without match.any (kept for A/B runs; bit-exact as well)
     double cache_mb = 8192; // parsed-file cache budget (host bytes), least recently used entries are dropped
+    int devices = 1;        // GPUs one call of data_read / data_read_mode3 / fgt_data_read_packed is spread over (single process:
+                            // one host thread and one engine per device, individuals in contiguous blocks, exchange over NCCL)
 };
+
+constexpr int kMaxEngines = 16;
 
 class Engine {
   public:
-    static Engine &get();
-    Options opt;
+    static Engine &get(int idx = 0);   // engine 0 serves single-device calls; engines 1.. exist for the "devices" option
+    Options &opt;                      // one set of options for the whole library
     int set_option(const char *key, double v);
     double get_option(const char *key);
     void srand_private(unsigned seed) { private_hist_ = seeded_history(seed); }
 
-    int data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t *stats, int64_t *count_only);
+    int data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t *stats, int64_t *count_only, const DistCtx *dist = nullptr);
+    // the same call spread over opt.devices GPUs of this process (individuals in contiguous blocks, see dist.h)
+    static int data_read_multi(const fgt_problem_t &pb, double *means, fgt_stats_t *stats);
     int data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_rows, double *out, fgt_stats_t *stats);
     int64_t get_raw(double *out, int64_t cap);
+    static int64_t get_raw_all(double *out, int64_t cap);
     int rand_fill_host(int32_t *out, int64_t n);
     int outer_weights(double *tempweights, const double *weights_mat, int S, int K);
     int chunk_one(const void *labels, int label_bytes, int nsites, const double *pos, const double *rate,
@@ -82,12 +90,21 @@ class Engine {
     int prepare_device() {            // CUDA context of the configured device (or the "no device" error): for host code that pins memory
         int rc = ensure_init();
         if (rc) return rc;
-        return cudaSetDevice(opt.device) == cudaSuccess ? FGT_OK : FGT_ERR_CUDA;
+        return cudaSetDevice(device_) == cudaSuccess ? FGT_OK : FGT_ERR_CUDA;
     }
 
+    int device() const { return device_; }
+    long long last_total_pairs_ = 0;   // pairs drawn by the whole call (all shards) -- what the generator state advanced by
+    bool snapshot_state(History &h) { return fetch_history(h); }
+    void advance_state(const History &h0, long long pairs) { store_history(apply_jump(poly_pow_E(2ULL * (uint64_t)pairs), h0)); }
+
   private:
-    Engine() = default;
-    int data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_stats_t *stats, int64_t *count_only);
+    Engine();
+    int idx_ = 0, device_ = 0;
+    int data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_stats_t *stats, int64_t *count_only, const DistCtx *dist);
+    DevBuf d_msg_, d_msg_all_, d_streampos_;      // sharded calls: pair counts (local / gathered), running stream position
+    long long *pin_msg_ = nullptr;                // pinned: [n_max + 1] counts message, then the stream position read-back
+    size_t pin_msg_cap_ = 0;
     int ensure_init();
     bool fetch_history(History &h);          // current stream state (libc-coupled or private)
     void store_history(const History &h);
@@ -95,7 +112,7 @@ class Engine {
     void vtick(const char *what) const;
     std::chrono::steady_clock::time_point t_call_start_;
     int prep_count(const fgt_problem_t &pb, int h, int p0, int p1, const void *d_lab, cudaEvent_t copy_done);
-    int setup_runs(const fgt_problem_t &pb, int h, int n_blocks, ChromState &cs);
+    int setup_runs(const fgt_problem_t &pb, int h, int n_blocks, int p_lo, int p_hi, ChromState &cs);
     long long prep_sig(const fgt_problem_t &pb) const;
     int prep_block(const fgt_problem_t &pb, int h, int p0, int p1, int blk, const void *d_lab, cudaEvent_t copy_done,
                    ChromState &cs, fgt_stats_t &stx);

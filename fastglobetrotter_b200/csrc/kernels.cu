@@ -5,6 +5,7 @@
 // they are never contracted into FMAs (the reference x86-64 binary has none) and the file is
 // additionally compiled with --fmad=false.
 #include "kernels.cuh"
+#include "dist.h"
 #include "glibc_rand.h"
 
 #include <algorithm>
@@ -1455,6 +1456,46 @@ void launch_commit_ordered(const CommitArgs &a, int max_slab_width, cudaStream_t
     }
 }
 
+
+// ---- sharded calls: stream offsets on the device -------------------------------------------------------------------
+// all[r][0] = individuals of shard r, all[r][1 + n] = sampled pairs of its n-th individual on this chromosome (gathered
+// by one all-gather).  The reference draws chromosome-major, individual-minor (C:338, C:419) and the shards own
+// consecutive blocks of individuals, so shard `rank`'s n-th individual starts at
+//     *stream_pos + (pairs of the shards before it) + (pairs of its own earlier individuals);
+// *stream_pos then moves on by the chromosome's total.  One block.
+__global__ void __launch_bounds__(256)
+k_dist_offsets(const long long *__restrict__ all, int world, int rank, int n_max, long long *stream_pos, long long *__restrict__ pair_base) {
+    __shared__ long long sh[2][8];
+    const int stride = n_max + 1;
+    long long before = 0, total = 0;
+    for (long long i = threadIdx.x; i < (long long)world * stride; i += blockDim.x) {
+        const int r = (int)(i / stride), k = (int)(i - (long long)r * stride);
+        if (k == 0) continue;
+        if (k - 1 >= (int)all[(size_t)r * stride]) continue;             // padding behind the shard's individuals
+        const long long v = all[i];
+        total += v;
+        if (r < rank) before += v;
+    }
+    before = (long long)warp_sum_u64((unsigned long long)before);
+    total = (long long)warp_sum_u64((unsigned long long)total);
+    if (lane_id() == 0) { sh[0][warp_id()] = before; sh[1][warp_id()] = total; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long b = 0, t = 0;
+        for (int w = 0; w < 8; w++) { b += sh[0][w]; t += sh[1][w]; }
+        const long long base = *stream_pos + b;
+        const long long *mine = all + (size_t)rank * stride;
+        const int n_local = (int)mine[0];
+        long long run = 0;
+        for (int n = 0; n < n_local; n++) { pair_base[n] = base + run; run += mine[1 + n]; }
+        *stream_pos += t;
+    }
+}
+
+void launch_dist_offsets(const long long *all, int world, int rank, int n_max, long long *stream_pos, long long *pair_base,
+                         cudaStream_t st) {
+    k_dist_offsets<<<1, 256, 0, st>>>(all, world, rank, n_max, stream_pos, pair_base);
+}
 
 // =============================================================================================
 // 5. Projection onto surrogate pairs (reference C:578-595, mode 3: C:1190-1203):

@@ -125,6 +125,19 @@ typedef struct fgt_stats_t {
  * means: host, S*S*num_bins doubles, added into. */
 int fgt_data_read_packed(const fgt_problem_t *prob, double *means, fgt_stats_t *stats);
 
+/* Multi-GPU (individuals shard, two small collectives).  Inside ONE process: set option "devices" = n and
+ * data_read / data_read_mode3 / fgt_data_read_packed spread every call over n GPUs (one host thread and engine per
+ * device, NCCL bound at run time).  With ONE PROCESS PER GPU (torchrun, MPI): rank 0 obtains an id, the launcher
+ * broadcasts its 128 bytes, every rank calls fgt_dist_init after choosing its device (option "device"); afterwards a
+ * call of fgt_data_read_packed whose num_inds_total exceeds num_inds is this rank's shard of a collective call: ranks own
+ * consecutive blocks of individuals in rank order, pair counts are all-gathered and turned into stream offsets on the
+ * device, the S^2 x G partial curves are all-reduced, every rank's `means` receives the sum and every rank's generator
+ * state advances by the pairs of the whole call.  Raw tensors stay bit-exact; `means` agree with the single-GPU result
+ * to <= 1e-12 relative (another summation order over individuals). */
+int fgt_dist_unique_id(char *out128);
+int fgt_dist_init(int rank, int world, const char *id128);
+void fgt_dist_finalize(void);
+
 /* pairs each (h,i) of the problem will draw: out[h*num_inds + i].  Lets shards exchange counts
  * (one all-gather) and derive pair_offset. */
 int fgt_count_pairs_packed(const fgt_problem_t *prob, int64_t *out);
@@ -143,7 +156,8 @@ int64_t fgt_get_raw_counts(double *out, int64_t capacity);
 /* options: "device" (ordinal), "strict" (1 = order-preserving fp64 fold, bit-exact; 0 = fp64
  * atomics), "keep_raw", "rand_libc" (1 = draw from / advance the process' libc rand() state like
  * the reference does; 0 = private stream seeded by fgt_srand), "slab_bins", "cache" (parsed-file cache),
- * "threads" (parser threads), "verbose".  Tuning / test hooks (defaults are the measured optimum): "accum_impl"
+ * "threads" (parser threads), "verbose", "devices" (GPUs per call, single process), "rand_impl" (1 = glibc stream generated
+ * inside the pair-evaluation kernel, 0 = bulk stream in HBM), "commit_impl", "cache_mb".  Tuning / test hooks (defaults are the measured optimum): "accum_impl"
  * (2 = two-phase, 1 = single-phase), "batch_pairs", "blocks", "ranges", "split_ready", "eval_parts", "spec_rand",
  * "copy_streams", "null_slab_bins", "reuse_prep" (one-shot).  "project_impl": 0 = exact projection (bit-identical curves,
  * default), 1 = FP64 tensor cores (curves to ~1e-14).  "null_world" / "null_rank": sharded data_read_null -- this
