@@ -206,6 +206,8 @@ class PackedCompanion(Companion):
         L.fgt_rle_encode.restype = C.c_int
         L.fgt_pack_samples.argtypes = [C.c_char_p, C.c_int, C.c_char_p]
         L.fgt_pack_samples.restype = C.c_int64
+        for nm in ("fgt_null_normalise", "fgt_getlhood_grid", "fgt_getmax", "fgt_bootstrap_means"):
+            getattr(L, nm).restype = C.c_int
         L.fgt_dist_unique_id.restype = C.c_int
         L.fgt_dist_init.restype = C.c_int
         L.fgt_dist_finalize.restype = None
@@ -246,6 +248,50 @@ class PackedCompanion(Companion):
 
     def dist_finalize(self):
         self.lib.fgt_dist_finalize()
+
+    # -- callers of the path (include/fgt_companion.h part 3) -----------------------------------------------
+    def null_normalise(self, temp_weights, null_mat, S, K, G, means=None):
+        tw, nm = _dbls(temp_weights), _dbls(null_mat)
+        m = _dbls(means).copy() if means is not None else None
+        nc = np.zeros(S * S * G, dtype=np.float64)
+        rc = self.lib.fgt_null_normalise(tw.ctypes.data_as(_dp), nm.ctypes.data_as(_dp), C.c_int(S), C.c_int(K), C.c_int(G),
+                                         m.ctypes.data_as(_dp) if m is not None else None, nc.ctypes.data_as(_dp))
+        if rc:
+            raise FgtError(rc)
+        return (m.reshape(S * S, G) if m is not None else None), nc.reshape(S * S, G)
+
+    def getlhood_grid(self, means, times, admixtimes, popfracs, likpenalty=1.0):
+        m = np.ascontiguousarray(means, dtype=np.float64)
+        t, pf = _dbls(times), _dbls(popfracs)
+        a = np.ascontiguousarray(admixtimes, dtype=np.float64)
+        a = a.reshape(-1, 1) if a.ndim == 1 else a
+        out = np.zeros(a.shape[0], dtype=np.float64)
+        rc = self.lib.fgt_getlhood_grid(m.ctypes.data_as(_dp), C.c_int(m.shape[0]), C.c_int(m.shape[1]), t.ctypes.data_as(_dp),
+                                        a.ctypes.data_as(_dp), C.c_int(a.shape[0]), C.c_int(a.shape[1]), pf.ctypes.data_as(_dp),
+                                        C.c_double(likpenalty), out.ctypes.data_as(_dp))
+        if rc:
+            raise FgtError(rc)
+        return out
+
+    def getmax(self, means, times, nparam, popfracs):
+        m = np.ascontiguousarray(means, dtype=np.float64)
+        t, pf = _dbls(times), _dbls(popfracs)
+        par = np.zeros(nparam, dtype=np.float64)
+        val, pen = C.c_double(), C.c_double()
+        rc = self.lib.fgt_getmax(m.ctypes.data_as(_dp), C.c_int(m.shape[0]), C.c_int(m.shape[1]), t.ctypes.data_as(_dp), C.c_int(nparam),
+                                 pf.ctypes.data_as(_dp), par.ctypes.data_as(_dp), C.byref(val), C.byref(pen))
+        if rc:
+            raise FgtError(rc)
+        return par, val.value, pen.value
+
+    def bootstrap_means(self, ind_id_vecs, S, G):
+        ids = np.ascontiguousarray(ind_id_vecs, dtype=np.int32)
+        ids = ids.reshape(1, -1) if ids.ndim == 1 else ids
+        out = np.zeros((ids.shape[0], S * S * G), dtype=np.float64)
+        rc = self.lib.fgt_bootstrap_means(ids.ctypes.data_as(_ip), C.c_int(ids.shape[0]), out.ctypes.data_as(_dp))
+        if rc:
+            raise FgtError(rc)
+        return out.reshape(ids.shape[0], S * S, G)
 
     def set_option(self, key: str, value: float):
         rc = self.lib.fgt_set_option(key.encode(), float(value))

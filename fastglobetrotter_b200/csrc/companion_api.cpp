@@ -921,7 +921,7 @@ void data_read_null(int *ploidy, char **filenameSAMPread, char **filenameRECOMre
     pb.binwidth = *binwidth; pb.num_bins = *num_bins; pb.grid_start = *grid_start; pb.num_donors = *num_donors;
     pb.donor_label_vec = donor_label_vec; pb.n_donor_labels = max_hap; pb.weight_min = *weight_min;
     pb.gridweight_max_cutoff = *gridweightMAX_cutoff; pb.num_surrogates = 1;
-    int rc = Engine::get().data_read_null_packed(pb, rec_rows.data(), chrom_ind_res, nullptr);
+    int rc = Engine::data_read_null_multi(pb, rec_rows.data(), chrom_ind_res, nullptr);
     if (rc) fatal_rc(rc);
     if (std::isnan(chrom_ind_res[0])) die("NA values. Exiting....\n");    // reference C:1055
 }
@@ -985,7 +985,37 @@ int fgt_count_pairs_packed(const fgt_problem_t *prob, int64_t *out) {
 int fgt_data_read_null_packed(const fgt_problem_t *prob, const int32_t *rec_rows, double *chrom_ind_res, fgt_stats_t *stats) {
     if (!prob || !rec_rows || !chrom_ind_res) return FGT_ERR_ARG;
     std::lock_guard<std::mutex> lk(g_api_mu);
-    return Engine::get().data_read_null_packed(*prob, rec_rows, chrom_ind_res, stats);
+    return Engine::data_read_null_multi(*prob, rec_rows, chrom_ind_res, stats);
+}
+
+// ---- callers of the path: opt-in entry points -----------------------------------------------------------
+int fgt_null_normalise(const double *temp_weights, const double *null_mat, int num_surrogates, int num_donors, int num_bins,
+                       double *means, double *null_curves_out) {
+    std::lock_guard<std::mutex> lk(g_api_mu);
+    return Engine::get().null_normalise(temp_weights, null_mat, num_surrogates, num_donors, num_bins, means, null_curves_out);
+}
+
+void null_normalise(double *temp_weights, double *null_mat, int *num_surrogates, int *num_donors, int *num_bins, double *means) {
+    // .C flavour of the above: every argument a pointer, `means` replaced in place, fatal errors end the process
+    int rc = fgt_null_normalise(temp_weights, null_mat, *num_surrogates, *num_donors, *num_bins, means, nullptr);
+    if (rc) fatal_rc(rc);
+}
+
+int fgt_getlhood_grid(const double *means, int n_curves, int n_times, const double *times, const double *admixtimes, int n_cand,
+                      int nparam, const double *popfracs, double likpenalty, double *lhood_out) {
+    std::lock_guard<std::mutex> lk(g_api_mu);
+    return Engine::get().getlhood_grid(means, n_curves, n_times, times, admixtimes, n_cand, nparam, popfracs, likpenalty, lhood_out);
+}
+
+int fgt_getmax(const double *means, int n_curves, int n_times, const double *times, int nparam, const double *popfracs, double *par_out,
+               double *value_out, double *likpenalty_out) {
+    std::lock_guard<std::mutex> lk(g_api_mu);
+    return Engine::get().getmax(means, n_curves, n_times, times, nparam, popfracs, par_out, value_out, likpenalty_out);
+}
+
+int fgt_bootstrap_means(const int32_t *ind_id_vec, int n_replicates, double *means_out) {
+    std::lock_guard<std::mutex> lk(g_api_mu);
+    return Engine::get().bootstrap_means(ind_id_vec, n_replicates, means_out);
 }
 
 int64_t fgt_get_raw_counts(double *out, int64_t capacity) { return Engine::get_raw_all(out, capacity); }

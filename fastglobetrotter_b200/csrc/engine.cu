@@ -91,6 +91,7 @@ int Engine::set_option(const char *key, double v) {
     else if (k == "rand_impl") opt.rand_impl = iv;
     else if (k == "commit_impl") opt.commit_impl = iv;
     else if (k == "cache_mb") opt.cache_mb = v;
+    else if (k == "keep_partials") opt.keep_partials = iv;
     else if (k == "devices") opt.devices = std::max(1, std::min(iv, kMaxEngines));
     else return FGT_ERR_ARG;
     return FGT_OK;
@@ -122,6 +123,7 @@ double Engine::get_option(const char *key) {
     if (k == "rand_impl") return opt.rand_impl;
     if (k == "commit_impl") return opt.commit_impl;
     if (k == "cache_mb") return opt.cache_mb;
+    if (k == "keep_partials") return opt.keep_partials;
     if (k == "devices") return opt.devices;
     return NAN;
 }
@@ -909,6 +911,15 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
             raw_count_ = (int64_t)slots * K * K * G;
         }
     }
+    // keep_partials: only a plain run (every individual once, in order) leaves curves that bootstrap replicates can recombine
+    bool keep_part = false;
+    part_valid_ = false;
+    if (!count_only && opt.keep_partials && !dist_on && N == n_phys) {
+        keep_part = true;
+        for (int h = 0; h < Cn && keep_part; h++)
+            for (int n = 0; n < N; n++) if (used[h][n] != n) { keep_part = false; break; }
+        if (keep_part && !d_partials_.as<double>((size_t)Cn * N * S * S * G)) return FGT_ERR_CUDA;
+    }
     cudaEvent_t tables_ready = nullptr;
     if (!count_only) { cudaEventCreateWithFlags(&tables_ready, cudaEventDisableTiming); CK(cudaEventRecord(tables_ready, st_)); }
     if (tables_ready) CK(cudaStreamWaitEvent(st_commit_, tables_ready, 0));
@@ -1288,6 +1299,19 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
             for (int n = 0; n < N; n++) count_only[(size_t)h * N + n] = cs.totals[used[h][n]];
             continue;
         }
+        if (keep_part) {
+            // the projected curves of every individual after this chromosome (mode 1: cumulative tensor; mode 3: this chromosome's)
+            double *dst = (double *)d_partials_.p + (size_t)h * N * S * S * G;
+            CK(cudaMemsetAsync(dst, 0, (size_t)N * S * S * G * sizeof(double), sc));
+            if (tw_pending) {
+                const double *tw_src = pb.temp_weights;
+                if (tw_stage.valid()) { tw_stage.get(); tw_src = pin_tw_; }
+                CK(cudaMemcpyAsync(d_tw, tw_src, tw_bytes, cudaMemcpyHostToDevice, sc));
+                tw_pending = false;
+            }
+            launch_project(d_tensor, N, K, G, S, d_tw, d_pairkh, dst, sc);
+            launches_ += 1;
+        }
         if (pb.mode == 3 && !(project_per_range && !want_raw)) {
             span_begin(2, sc);
             if (want_raw) { launch_expand_raw(d_tensor, N, K, G, d_raw + (size_t)h * N * K * K * G, sc); launches_++; }
@@ -1372,6 +1396,7 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
     if (tables_ready) cudaEventDestroy(tables_ready);
     if (herr[0]) { for (auto e2 : evs) cudaEventDestroy(e2); return err_to_code(herr[0]); }
 
+    if (keep_part) { part_valid_ = true; part_Cn_ = Cn; part_N_ = N; part_S_ = S; part_G_ = G; part_mode_ = pb.mode; }
     if (dist_on) {
         for (size_t i = 0; i < part.size(); i++) means[i] += part[i];       // added into the caller's buffer (C:644)
         last_total_pairs_ = pin_msg_[n_msg + 1];
@@ -1501,6 +1526,160 @@ int Engine::data_read_multi(const fgt_problem_t &pb, double *means, fgt_stats_t 
     return FGT_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Callers of the path, opt-in: bootstrap replicates from kept partial curves, R's null normalisation,
+// the date likelihood over a grid and the date fit.  Small problems: plain allocate / launch / copy back.
+// ---------------------------------------------------------------------------------------------
+int Engine::bootstrap_means(const int32_t *ids, int n_rep, double *means_out) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!part_valid_ || !ids || !means_out || n_rep <= 0) return FGT_ERR_ARG;
+    CK(cudaSetDevice(device_));
+    const int N = part_N_, Cn = part_Cn_, S = part_S_, G = part_G_;
+    const size_t cells = (size_t)S * S * G;
+    for (long long i = 0; i < (long long)n_rep * N * Cn; i++) if (ids[i] < 0 || ids[i] >= N) return FGT_ERR_ARG;
+    int32_t *d_ids = d_physof_.as<int32_t>((size_t)N * Cn);
+    double *d_res = d_results_.as<double>((size_t)N * cells), *d_rs = d_rs_.as<double>((size_t)N * S * G);
+    double *d_ratio = d_ratio_.as<double>((size_t)N * cells), *d_means = d_means_.as<double>(cells);
+    if (!d_ids || !d_res || !d_rs || !d_ratio || !d_means) return FGT_ERR_CUDA;
+    for (int r = 0; r < n_rep; r++) {
+        CK(cudaMemcpyAsync(d_ids, ids + (size_t)r * N * Cn, (size_t)N * Cn * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
+        launch_bootstrap_combine((const double *)d_partials_.p, Cn, N, cells, part_mode_ == 1 ? 1 : 0, d_ids, N, d_res, st_);
+        launch_normalise(d_res, N, S, G, N, d_rs, d_ratio, st_);
+        CK(cudaMemsetAsync(d_means, 0, cells * sizeof(double), st_));
+        launch_mean_accum(d_ratio, N, S, G, d_means, st_);
+        CK(cudaMemcpyAsync(means_out + (size_t)r * cells, d_means, cells * sizeof(double), cudaMemcpyDeviceToHost, st_));
+        CK(cudaStreamSynchronize(st_));
+    }
+    CK(cudaGetLastError());
+    return FGT_OK;
+}
+
+int Engine::null_normalise(const double *tw, const double *null_mat, int S, int K, int G, double *means, double *null_curves) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!tw || !null_mat || S <= 0 || S > 64 || K <= 0 || G <= 0 || (!means && !null_curves)) return FGT_ERR_ARG;
+    CK(cudaSetDevice(device_));
+    const size_t cells = (size_t)S * S * G, ntw = (size_t)S * S * K * K, nn = (size_t)K * K * G;
+    double *d_tw = d_tw_.as<double>(ntw), *d_null = d_tensor_.as<double>(nn), *d_scr = d_results_.as<double>(cells);
+    double *d_nc = d_ratio_.as<double>(cells), *d_m = d_means_.as<double>(cells);
+    if (!d_tw || !d_null || !d_scr || !d_nc || !d_m) return FGT_ERR_CUDA;
+    CK(cudaMemcpyAsync(d_tw, tw, ntw * sizeof(double), cudaMemcpyHostToDevice, st_));
+    CK(cudaMemcpyAsync(d_null, null_mat, nn * sizeof(double), cudaMemcpyHostToDevice, st_));
+    if (means) CK(cudaMemcpyAsync(d_m, means, cells * sizeof(double), cudaMemcpyHostToDevice, st_));
+    launch_null_normalise(d_tw, d_null, S, K, G, d_scr, d_nc, means ? d_m : nullptr, st_);
+    if (means) CK(cudaMemcpyAsync(means, d_m, cells * sizeof(double), cudaMemcpyDeviceToHost, st_));
+    if (null_curves) CK(cudaMemcpyAsync(null_curves, d_nc, cells * sizeof(double), cudaMemcpyDeviceToHost, st_));
+    CK(cudaStreamSynchronize(st_));
+    CK(cudaGetLastError());
+    return FGT_OK;
+}
+
+int Engine::getlhood_grid(const double *means, int R, int T, const double *times, const double *cand, int n_cand, int nparam,
+                          const double *popfracs, double likpenalty, double *lhood) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    const int S = (int)(std::sqrt((double)R) + 0.5);
+    if (!means || !times || !cand || !popfracs || !lhood || R <= 0 || S * S != R || T < 3 || n_cand <= 0 || (nparam != 1 && nparam != 2))
+        return FGT_ERR_ARG;
+    CK(cudaSetDevice(device_));
+    double *d_m = d_results_.as<double>((size_t)R * T), *d_t = d_rs_.as<double>((size_t)T + S);
+    double *d_c = d_ratio_.as<double>((size_t)n_cand * nparam + n_cand);
+    void *d_fit = d_tensor_.get(getlhood_scratch_bytes(R, n_cand));
+    if (!d_m || !d_t || !d_c || !d_fit) return FGT_ERR_CUDA;
+    double *d_pf = d_t + T, *d_lh = d_c + (size_t)n_cand * nparam;
+    CK(cudaMemcpyAsync(d_m, means, (size_t)R * T * sizeof(double), cudaMemcpyHostToDevice, st_));
+    CK(cudaMemcpyAsync(d_t, times, (size_t)T * sizeof(double), cudaMemcpyHostToDevice, st_));
+    CK(cudaMemcpyAsync(d_pf, popfracs, (size_t)S * sizeof(double), cudaMemcpyHostToDevice, st_));
+    CK(cudaMemcpyAsync(d_c, cand, (size_t)n_cand * nparam * sizeof(double), cudaMemcpyHostToDevice, st_));
+    launch_getlhood(d_m, R, T, d_t, d_c, n_cand, nparam, d_pf, likpenalty, d_fit, d_lh, st_);
+    CK(cudaMemcpyAsync(lhood, d_lh, (size_t)n_cand * sizeof(double), cudaMemcpyDeviceToHost, st_));
+    CK(cudaStreamSynchronize(st_));
+    CK(cudaGetLastError());
+    return FGT_OK;
+}
+
+// getmax, fastGLOBETROTTER.R:491-520: likelihood on the grid 10^seq(0,3,.25) (13 dates, or the 91 ordered pairs), then a
+// Nelder-Mead search in sqrt(date - 1) started at the best grid point (R's optim defaults: reflection 1, contraction 0.5,
+// expansion 2, relative tolerance sqrt(eps), 500 iterations).  Every likelihood evaluation runs on the device.
+int Engine::getmax(const double *means, int R, int T, const double *times, int nparam, const double *popfracs, double *par, double *value,
+                   double *likpenalty_out) {
+    if (!par || (nparam != 1 && nparam != 2)) return FGT_ERR_ARG;
+    std::vector<double> x(13);
+    for (int i = 0; i < 13; i++) x[i] = std::pow(10.0, 0.25 * i);
+    std::vector<double> grid;
+    if (nparam == 1) grid = x;
+    else
+        for (int i = 0; i < 13; i++)
+            for (int j = i; j < 13; j++) { grid.push_back(x[i]); grid.push_back(x[j]); }       // cbind(rep(x,13:1), rep(x,13)[-to.remove])
+    const int n_cand = (int)grid.size() / nparam;
+    double pen = 1.0;
+    int rc = getlhood_grid(means, R, T, times, grid.data(), 1, nparam, popfracs, 1.0, &pen);
+    if (rc) return rc;
+    std::vector<double> lh(n_cand);
+    rc = getlhood_grid(means, R, T, times, grid.data(), n_cand, nparam, popfracs, pen, lh.data());
+    if (rc) return rc;
+    double maxlik = 0.0;
+    std::vector<double> init(nparam);
+    for (int j = 0; j < nparam; j++) init[j] = std::sqrt(grid[j]);
+    for (int i = 0; i < n_cand; i++)
+        if (lh[i] > maxlik) { maxlik = lh[i]; for (int j = 0; j < nparam; j++) init[j] = std::sqrt(grid[(size_t)i * nparam + j]); }
+    int evals = 0, bad = 0;
+    auto f = [&](const std::vector<double> &p) {
+        double a[2], v = 0.0;
+        for (int j = 0; j < nparam; j++) a[j] = 1.0 + p[j] * p[j];
+        if (getlhood_grid(means, R, T, times, a, 1, nparam, popfracs, pen, &v)) bad = 1;
+        evals++;
+        return -v;
+    };
+    // Nelder-Mead (the structure of R's nmmin)
+    const int n = nparam;
+    const double alpha = 1.0, beta = 0.5, gamma = 2.0, reltol = 1.4901161193847656e-08;
+    std::vector<std::vector<double>> P(n + 1, init);
+    std::vector<double> F(n + 1);
+    double size = 0.0;
+    for (int i = 0; i < n; i++) size = std::max(size, 0.1 * std::fabs(init[i]));
+    if (size == 0.0) size = 0.1;
+    for (int j = 1; j <= n; j++) P[j][j - 1] += size;
+    for (int j = 0; j <= n; j++) F[j] = f(P[j]);
+    for (int iter = 0; iter < 500 && !bad; iter++) {
+        int L = 0, H = 0;
+        for (int j = 1; j <= n; j++) { if (F[j] < F[L]) L = j; if (F[j] > F[H]) H = j; }
+        if (F[H] <= F[L] + reltol * (std::fabs(F[L]) + reltol)) break;
+        std::vector<double> C(n, 0.0);
+        for (int j = 0; j <= n; j++) if (j != H) for (int i = 0; i < n; i++) C[i] += P[j][i] / n;
+        std::vector<double> Rp(n), Ep(n);
+        for (int i = 0; i < n; i++) Rp[i] = (1.0 + alpha) * C[i] - alpha * P[H][i];
+        const double fr = f(Rp);
+        if (fr < F[L]) {
+            for (int i = 0; i < n; i++) Ep[i] = gamma * Rp[i] + (1.0 - gamma) * C[i];
+            const double fe = f(Ep);
+            if (fe < fr) { P[H] = Ep; F[H] = fe; } else { P[H] = Rp; F[H] = fr; }
+        } else {
+            if (fr < F[H]) { P[H] = Rp; F[H] = fr; }
+            // second highest
+            double second = -1e300;
+            for (int j = 0; j <= n; j++) if (j != H && F[j] > second) second = F[j];
+            if (fr >= second) {
+                for (int i = 0; i < n; i++) Ep[i] = (1.0 - beta) * P[H][i] + beta * C[i];
+                const double fc = f(Ep);
+                if (fc < F[H]) { P[H] = Ep; F[H] = fc; }
+                else if (fr >= F[H]) {
+                    for (int j = 0; j <= n; j++)
+                        if (j != L) { for (int i = 0; i < n; i++) P[j][i] = beta * (P[j][i] - P[L][i]) + P[L][i]; F[j] = f(P[j]); }
+                }
+            }
+        }
+    }
+    if (bad) return FGT_ERR_CUDA;
+    int L = 0;
+    for (int j = 1; j <= n; j++) if (F[j] < F[L]) L = j;
+    for (int j = 0; j < nparam; j++) par[j] = 1.0 + P[L][j] * P[L][j];
+    if (value) *value = F[L];
+    if (likpenalty_out) *likpenalty_out = pen;
+    return FGT_OK;
+}
+
 int64_t Engine::get_raw_all(double *out, int64_t cap) {
     // raw tensors of the last call: one engine, or the shards of a multi-device call in individual order (mode 1 only:
     // mode 3 stores its tensors in tabulate-call order, chromosome-major, which interleaves the shards)
@@ -1531,12 +1710,52 @@ int64_t Engine::get_raw(double *out, int64_t cap) {
 // ---------------------------------------------------------------------------------------------
 // NULL-individual curves
 // ---------------------------------------------------------------------------------------------
-int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_rows, double *out, fgt_stats_t *stats) {
+// The NULL tensor over several GPUs of this process ("devices" option): every engine folds the label pairs it owns (the
+// same owner on every chromosome, so no cell's additions are re-associated) into a zero-initialised copy, the copies have
+// disjoint supports and are added to the caller's buffer on the host: bit-identical to one GPU.
+int Engine::data_read_null_multi(const fgt_problem_t &pb, const int32_t *rec_rows, double *out, fgt_stats_t *stats) {
+    Engine &e0 = Engine::get(0);
+    int rc = e0.ensure_init();
+    if (rc) return rc;
+    int ndev = 0;
+    cudaGetDeviceCount(&ndev);
+    const int n = std::min(std::min(e0.opt.devices, ndev), kMaxEngines);
+    if (n <= 1 || e0.opt.null_world > 1) return e0.data_read_null_packed(pb, rec_rows, out, stats);
+    const size_t cells = (size_t)pb.num_donors * pb.num_donors * pb.num_bins;
+    std::vector<std::vector<double>> part(n);
+    std::vector<fgt_stats_t> st(n);
+    std::vector<int> rcs(n, 0);
+    std::vector<std::thread> th;
+    for (int d = 0; d < n; d++) {
+        part[d].assign(out, out + cells);                       // every shard continues from the caller's values on its own cells
+        th.emplace_back([&, d]() { rcs[d] = Engine::get(d).data_read_null_packed(pb, rec_rows, part[d].data(), &st[d], n, d); });
+    }
+    for (auto &t : th) t.join();
+    for (int d = 0; d < n; d++) if (rcs[d]) return rcs[d];
+    std::fill(out, out + cells, 0.0);
+    for (int d = 0; d < n; d++)
+        for (size_t i = 0; i < cells; i++) out[i] += part[d][i];      // disjoint supports: exact
+    fgt_stats_t agg = st[0];
+    for (int d = 1; d < n; d++) {
+        agg.accepted += st[d].accepted; agg.kernel_launches += st[d].kernel_launches;
+        agg.h2d_bytes += st[d].h2d_bytes; agg.d2h_bytes += st[d].d2h_bytes;
+        agg.ms_accum = std::max(agg.ms_accum, st[d].ms_accum); agg.ms_total = std::max(agg.ms_total, st[d].ms_total);
+    }
+    e0.last_stats = agg;
+    if (stats) *stats = agg;
+    return FGT_OK;
+}
+
+int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_rows, double *out, fgt_stats_t *stats, int shard_world,
+                                  int shard_rank) {
+    const int null_world = shard_world > 0 ? shard_world : opt.null_world, null_rank = shard_world > 0 ? shard_rank : opt.null_rank;
     int rc = ensure_init();
     if (rc) return rc;
     if (pb.ploidy <= 0 || pb.nsamples <= 0 || pb.num_chrom <= 0 || pb.num_inds <= 0 || pb.n_packed_inds <= 0 ||
-        (pb.label_bytes != 2 && pb.label_bytes != 4) || pb.num_bins <= 0 || pb.num_donors <= 0 || !(pb.binwidth > 0))
+        pb.num_bins <= 0 || pb.num_donors <= 0 || !(pb.binwidth > 0) || !pb.chrom)
         return FGT_ERR_ARG;
+    for (int h = 0; h < pb.num_chrom; h++)
+        if (pb.chrom[h].runs ? !pb.chrom[h].run_off : (!pb.chrom[h].labels || (pb.label_bytes != 2 && pb.label_bytes != 4))) return FGT_ERR_ARG;
     CK(cudaSetDevice(device_));
     fgt_stats_t stx{};
     launches_ = 0;
@@ -1565,18 +1784,18 @@ int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_ro
     if (!d_out) return FGT_ERR_CUDA;
     std::vector<double> own_init;
     const double *init_src = out;
-    if (opt.null_world > 1) {
+    if (null_world > 1) {
         // sharded run: this rank returns only the label pairs it owns (continuing from the caller's values there), zeros
         // elsewhere, so that the ranks' outputs have disjoint supports and their sum is exact
         own_init.assign(out, out + (size_t)K * K * G);
         for (int la = 0; la < K; la++)
             for (int lb = 0; lb < K; lb++)
-                if ((la * 31 + lb * 17) % opt.null_world != opt.null_rank)
+                if ((la * 31 + lb * 17) % null_world != null_rank)
                     std::fill(own_init.begin() + ((size_t)la * K + lb) * G, own_init.begin() + ((size_t)la * K + lb + 1) * G, 0.0);
         init_src = own_init.data();
     }
     CK(cudaMemcpyAsync(d_out, init_src, (size_t)K * K * G * sizeof(double), cudaMemcpyHostToDevice, st_));
-    if (opt.null_world > 1) CK(cudaStreamSynchronize(st_));      // own_init is a local
+    if (null_world > 1) CK(cudaStreamSynchronize(st_));      // own_init is a local
     CK(cudaEventRecord(e1, st_));
     ChromState &cs = null_cs_;                   // grow-only buffers kept between calls (no cudaMalloc/cudaFree per call)
     long long evals = 0;
@@ -1607,7 +1826,7 @@ int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_ro
                     // sharded NULL run: a rank folds the label pairs it owns, on every chromosome (the owner of a cell must
                     // not change between chromosomes, or its additions would be re-associated); the ranks' outputs have
                     // disjoint supports, so their sum is exact
-                    if (opt.null_world > 1 && (la * 31 + lb * 17) % opt.null_world != opt.null_rank) continue;
+                    if (null_world > 1 && (la * 31 + lb * 17) % null_world != null_rank) continue;
                     const double scan = ca * std::ceil(std::max(cb, 1.0) / 32.0);          // steps per haplotype pair
                     const double recs = ca * cb * 0.7;                                      // accepted pairs per haplotype pair
                     int ns = opt.null_slab_bins > 0 ? (G + opt.null_slab_bins - 1) / opt.null_slab_bins

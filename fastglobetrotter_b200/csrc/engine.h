@@ -61,6 +61,8 @@ struct Options {
     int commit_impl = 0;    // commit kernel, shared-memory tiles: 0 = match.any fold (measured faster: 1.64 vs 3.4 ms on the bench
                             // workload), 1 = lane-queue fold without match.any (kept for A/B runs; bit-exact as well)
     double cache_mb = 8192; // parsed-file cache budget (host bytes), least recently used entries are dropped
+    int keep_partials = 0;  // keep the projected curves of every (individual, chromosome) of a data_read call on the device, so that
+                            // bootstrap replicates can be formed from them without re-sampling (fgt_bootstrap_means; identity ids only)
     int devices = 1;        // GPUs one call of data_read / data_read_mode3 / fgt_data_read_packed is spread over (single process:
                             // one host thread and one engine per device, individuals in contiguous blocks, exchange over NCCL)
 };
@@ -78,7 +80,16 @@ class Engine {
     int data_read_packed(const fgt_problem_t &pb, double *means, fgt_stats_t *stats, int64_t *count_only, const DistCtx *dist = nullptr);
     // the same call spread over opt.devices GPUs of this process (individuals in contiguous blocks, see dist.h)
     static int data_read_multi(const fgt_problem_t &pb, double *means, fgt_stats_t *stats);
-    int data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_rows, double *out, fgt_stats_t *stats);
+    int data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_rows, double *out, fgt_stats_t *stats, int shard_world = 0,
+                              int shard_rank = 0);
+    static int data_read_null_multi(const fgt_problem_t &pb, const int32_t *rec_rows, double *out, fgt_stats_t *stats);
+    // callers of the path: opt-in entry points, see include/fgt_companion.h part 3
+    int null_normalise(const double *tw, const double *null_mat, int S, int K, int G, double *means, double *null_curves);
+    int getlhood_grid(const double *means, int R, int T, const double *times, const double *cand, int n_cand, int nparam,
+                      const double *popfracs, double likpenalty, double *lhood);
+    int getmax(const double *means, int R, int T, const double *times, int nparam, const double *popfracs, double *par, double *value,
+               double *likpenalty_out);
+    int bootstrap_means(const int32_t *ids, int n_rep, double *means_out);
     int64_t get_raw(double *out, int64_t cap);
     static int64_t get_raw_all(double *out, int64_t cap);
     int rand_fill_host(int32_t *out, int64_t n);
@@ -102,6 +113,9 @@ class Engine {
     Engine();
     int idx_ = 0, device_ = 0;
     int data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_stats_t *stats, int64_t *count_only, const DistCtx *dist);
+    DevBuf d_partials_;                           // keep_partials: [Cn][N][S*S][G] projected curves of the last data_read call
+    int part_Cn_ = 0, part_N_ = 0, part_S_ = 0, part_G_ = 0, part_mode_ = 0;
+    bool part_valid_ = false;
     DevBuf d_msg_, d_msg_all_, d_streampos_;      // sharded calls: pair counts (local / gathered), running stream position
     long long *pin_msg_ = nullptr;                // pinned: [n_max + 1] counts message, then the stream position read-back
     size_t pin_msg_cap_ = 0;

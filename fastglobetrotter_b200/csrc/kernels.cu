@@ -2104,3 +2104,181 @@ void launch_null_strict(const NullArgs &a, cudaStream_t st) {
 }
 
 }  // namespace fgt
+
+// =============================================================================================
+// 8. Callers of the path, as opt-in extra entry points: the R script stays unchanged unless a user
+//    switches to them.  Tolerance-level by nature (R's %*% is BLAS, lm() is Householder QR).
+// =============================================================================================
+namespace fgt {
+
+// ---- 8a. null normalisation, fastGLOBETROTTER.R:1216-1249 -------------------------------------
+// results = tempweights %*% null  ([S^2 x K^2] . [K^2 x G]); tw is in data_read's layout [(k*K+l)*S^2 + mn].
+__global__ void __launch_bounds__(256)
+k_weights_times_null(const double *__restrict__ tw, const double *__restrict__ nul, int SS, int KK, int G, double *__restrict__ out) {
+    const int b = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int mn = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (b >= G || mn >= SS) return;
+    double acc = 0.0;
+    for (int p = 0; p < KK; p++) acc = __dadd_rn(acc, __dmul_rn(tw[(size_t)p * SS + mn], nul[(size_t)p * G + b]));
+    out[(size_t)mn * G + b] = acc;
+}
+
+// per bin: symmetrise, expectation from the margins, divide (R:1223-1248); one thread per bin, S <= 64
+__global__ void __launch_bounds__(128)
+k_null_normalise(const double *__restrict__ res, int S, int G, double *__restrict__ nullcurves, double *__restrict__ means) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= G) return;
+    double s2[64], s3[64];
+    for (int k = 0; k < S; k++) { s2[k] = 0.0; s3[k] = 0.0; }
+    double tot = 0.0;
+    auto sym = [&](int k, int l) { return __dmul_rn(__dadd_rn(res[(size_t)(k * S + l) * G + b], res[(size_t)(l * S + k) * G + b]), 0.5); };
+    for (int k = 0; k < S; k++)
+        for (int l = 0; l < S; l++) {
+            const double r = sym(k, l);
+            tot = __dadd_rn(tot, r); s2[k] = __dadd_rn(s2[k], r); s3[l] = __dadd_rn(s3[l], r);
+        }
+    for (int k = 0; k < S; k++)
+        for (int l = 0; l < S; l++) {
+            const double e_kl = __ddiv_rn(__dmul_rn(s2[k], s3[l]), tot), e_lk = __ddiv_rn(__dmul_rn(s2[l], s3[k]), tot);
+            const double ex = __dmul_rn(__dadd_rn(e_kl, e_lk), 0.5);
+            const double nc = __ddiv_rn(sym(k, l), ex);
+            const size_t o = (size_t)(k * S + l) * G + b;
+            if (nullcurves) nullcurves[o] = nc;
+            if (means) means[o] = __ddiv_rn(means[o], nc);
+        }
+}
+
+void launch_null_normalise(const double *tw, const double *nul, int S, int K, int G, double *scratch, double *nullcurves, double *means,
+                           cudaStream_t st) {
+    dim3 grid((G + 31) / 32, (S * S + 7) / 8);
+    k_weights_times_null<<<grid, 256, 0, st>>>(tw, nul, S * S, K * K, G, scratch);
+    k_null_normalise<<<(G + 127) / 128, 128, 0, st>>>(scratch, S, G, nullcurves, means);
+}
+
+// ---- 8b. date likelihood, fastGLOBETROTTER.R:441-489 (getlhood) over a grid of candidate dates --------------------
+// one thread per (candidate, curve): ordinary least squares of the curve on 1 + exp(-t*a/100) (+ a second date), the way
+// lm() resolves it (a column whose part orthogonal to the earlier ones is below 1e-7 of its norm gets an NA coefficient)
+struct FitOut { double lh, c1, c2, sd3; };
+
+__global__ void __launch_bounds__(128)
+k_getlhood_fit(const double *__restrict__ means, int R, int T, const double *__restrict__ times, const double *__restrict__ cand,
+               int n_cand, int nparam, FitOut *__restrict__ out) {
+    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= (long long)n_cand * R) return;
+    const int c = (int)(id / R), i = (int)(id - (long long)c * R);
+    const double a1 = cand[(size_t)c * nparam], a2 = nparam == 2 ? cand[(size_t)c * nparam + 1] : 0.0;
+    const double *y = means + (size_t)i * T;
+    double sy = 0, s1 = 0, s2 = 0, n1 = 0, n2 = 0;
+    for (int t = 0; t < T; t++) {
+        const double p1 = exp(-times[t] * a1 / 100.0), p2 = nparam == 2 ? exp(-times[t] * a2 / 100.0) : 0.0;
+        sy += y[t]; s1 += p1; s2 += p2; n1 += p1 * p1; n2 += p2 * p2;
+    }
+    const double yb = sy / T, b1m = s1 / T, b2m = s2 / T;
+    double c11 = 0, c12 = 0, c22 = 0, c1y = 0, c2y = 0;
+    for (int t = 0; t < T; t++) {
+        const double p1 = exp(-times[t] * a1 / 100.0) - b1m, p2 = (nparam == 2 ? exp(-times[t] * a2 / 100.0) : 0.0) - b2m, yc = y[t] - yb;
+        c11 += p1 * p1; c12 += p1 * p2; c22 += p2 * p2; c1y += p1 * yc; c2y += p2 * yc;
+    }
+    const double tol2 = 1e-14;                 // (1e-7)^2, lm()'s rank tolerance on column norms
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    double coef1 = nan, coef2 = nan;
+    const bool ok1 = c11 >= tol2 * n1 && n1 > 0.0;
+    bool ok2 = false;
+    if (ok1) {
+        if (nparam == 2) {
+            const double q22 = c22 - c12 * c12 / c11;             // squared norm of the second column's orthogonal part
+            ok2 = q22 >= tol2 * n2 && n2 > 0.0;
+            if (ok2) {
+                coef2 = (c2y - c12 * c1y / c11) / q22;
+                coef1 = (c1y - coef2 * c12) / c11;
+            } else coef1 = c1y / c11;
+        } else coef1 = c1y / c11;
+    } else if (nparam == 2 && c22 >= tol2 * n2 && n2 > 0.0) { coef2 = c2y / c22; ok2 = true; }
+    const double u1 = ok1 ? coef1 : 0.0, u2 = ok2 ? coef2 : 0.0;
+    double ss = 0.0;
+    const int h0 = T / 2;                      // R: res[floor(T/2):T] (1-based, inclusive) -> 0-based from floor(T/2)-1
+    const int from = h0 - 1 < 0 ? 0 : h0 - 1;
+    double sa = 0.0, saa = 0.0;
+    int na = 0;
+    for (int t = 0; t < T; t++) {
+        const double p1 = exp(-times[t] * a1 / 100.0) - b1m, p2 = (nparam == 2 ? exp(-times[t] * a2 / 100.0) : 0.0) - b2m;
+        const double r = (y[t] - yb) - u1 * p1 - u2 * p2;
+        ss += r * r;
+        if (t >= from) { const double ar = fabs(r); sa += ar; saa += ar * ar; na++; }
+    }
+    FitOut o;
+    o.lh = -0.5 * T * log(ss / T);
+    o.c1 = coef1; o.c2 = coef2;
+    const double var = na > 1 ? (saa - sa * sa / na) / (na - 1) : nan;
+    o.sd3 = 3.0 * sqrt(var > 0.0 ? var : 0.0);
+    out[id] = o;
+}
+
+// one thread per candidate: the sum over curves and the penalty rules of R:455-488 (diagonal curves carry popfracs)
+__global__ void k_getlhood_reduce(const FitOut *__restrict__ fit, int R, int n_cand, int nparam, const double *__restrict__ cand,
+                                  const double *__restrict__ popfracs, double likpenalty, double *__restrict__ lhood) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cand) return;
+    const int S = (int)(sqrt((double)R) + 0.5);
+    double lh = 0.0, ts0 = 0.0, ts1 = 0.0;
+    bool neg = false;
+    for (int i = 0; i < R; i++) {
+        const FitOut f = fit[(size_t)c * R + i];
+        if (i % (S + 1) == 0 && i / (S + 1) < S) {             // seq.to.capture: the (k,k) curves
+            const double pf = popfracs[i / S];                 // popfracs[((i-1)/sqrt(R)+1)] with R's 1-based i: k
+            if (nparam == 2) {
+                const double a1 = cand[(size_t)c * 2], a2 = cand[(size_t)c * 2 + 1];
+                const bool na3 = isnan(f.c2);
+                if (a1 != a2 && !na3) {
+                    const bool s1 = f.c1 > 0, s2 = f.c2 > 0, z1 = f.c1 == 0, z2 = f.c2 == 0;
+                    const int sg1 = z1 ? 0 : (s1 ? 1 : -1), sg2 = z2 ? 0 : (s2 ? 1 : -1);
+                    if (sg1 != sg2 && fmin(f.c1, f.c2) < -f.sd3) neg = true;
+                    ts0 += pf * fabs(f.c1); ts1 += pf * fabs(f.c2);
+                }
+                if (na3) neg = true;
+            } else ts0 += pf * fabs(f.c1);
+        }
+        lh += f.lh;
+    }
+    double mx = nparam == 2 ? fmax(ts0, ts1) : ts0;
+    if (isnan(ts0) || isnan(ts1)) { mx = 0.0; neg = true; }
+    lhood[c] = (neg || mx > 2.0) ? lh / likpenalty : lh;
+}
+
+void launch_getlhood(const double *means, int R, int T, const double *times, const double *cand, int n_cand, int nparam,
+                     const double *popfracs, double likpenalty, void *fit_scratch, double *lhood, cudaStream_t st) {
+    const long long n = (long long)n_cand * R;
+    if (n <= 0) return;
+    k_getlhood_fit<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(means, R, T, times, cand, n_cand, nparam, (FitOut *)fit_scratch);
+    k_getlhood_reduce<<<(n_cand + 63) / 64, 64, 0, st>>>((const FitOut *)fit_scratch, R, n_cand, nparam, cand, popfracs, likpenalty, lhood);
+}
+size_t getlhood_scratch_bytes(int R, int n_cand) { return (size_t)R * n_cand * sizeof(FitOut); }
+
+// ---- 8c. bootstrap replicates from per-(individual, chromosome) projected curves ---------------------
+// part[h][p][mn][b]: projection of packed individual p's tensor after chromosome h (mode 1: cumulative over chromosomes,
+// so chromosome h's own share is part[h] - part[h-1]; mode 3: chromosome h alone).  A replicate's pseudo-individual i uses
+// individual ids[i*Cn + h] on chromosome h (R:2058-2059).
+__global__ void __launch_bounds__(256)
+k_bootstrap_combine(const double *__restrict__ part, int Cn, int Np, size_t cells, int cumulative, const int32_t *__restrict__ ids,
+                    int N, double *__restrict__ results) {
+    const int i = blockIdx.y;                                   // pseudo-individual of this replicate
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < cells; e += (size_t)gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        for (int h = 0; h < Cn; h++) {
+            const int p = ids[(size_t)i * Cn + h];
+            double v = part[((size_t)h * Np + p) * cells + e];
+            if (cumulative && h > 0) v = __dsub_rn(v, part[((size_t)(h - 1) * Np + p) * cells + e]);
+            acc = __dadd_rn(acc, v);
+        }
+        results[(size_t)i * cells + e] = acc;
+    }
+}
+
+void launch_bootstrap_combine(const double *part, int Cn, int Np, size_t cells, int cumulative, const int32_t *ids, int N, double *results,
+                              cudaStream_t st) {
+    if (N <= 0) return;
+    dim3 grid((unsigned)std::min<size_t>((cells + 255) / 256, 64), N);
+    k_bootstrap_combine<<<grid, 256, 0, st>>>(part, Cn, Np, cells, cumulative, ids, N, results);
+}
+
+}  // namespace fgt

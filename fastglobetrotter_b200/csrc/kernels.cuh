@@ -141,6 +141,15 @@ void launch_mean_accum(const double *ratio, int N, int S, int G, double *means, 
 void launch_outer_weights(const double *w, int S, int K, double *out, cudaStream_t st);
 void launch_expand_raw(const double *tensor, int N, int K, int G, double *out_full, cudaStream_t st);
 
+// callers of the path, opt-in entry points
+void launch_null_normalise(const double *tw, const double *nul, int S, int K, int G, double *scratch /*[S*S*G]*/, double *nullcurves,
+                           double *means, cudaStream_t st);
+void launch_getlhood(const double *means, int R, int T, const double *times, const double *cand, int n_cand, int nparam,
+                     const double *popfracs, double likpenalty, void *fit_scratch, double *lhood, cudaStream_t st);
+size_t getlhood_scratch_bytes(int R, int n_cand);
+void launch_bootstrap_combine(const double *part, int Cn, int Np, size_t cells, int cumulative, const int32_t *ids, int N, double *results,
+                              cudaStream_t st);
+
 // NULL-individual path
 struct NullTask { int32_t lA, lB, b_lo, b_hi; };   // one ordered fold: label pair x range of fine bins
 struct NullArgs {

@@ -205,6 +205,39 @@ int64_t fgt_pack_samples(const char *samples_path, int nsites, const char *out_p
  * glibc stream n_draws after srand(seed). */
 int fgt_rand_host_jump(unsigned seed, uint64_t n_draws, uint32_t *hist_out);
 
+/* ------------------------------------------------------------------------------------
+ * Part 3 -- callers of the path, opt-in.  fastGLOBETROTTER.R runs unchanged without them; a user who wants
+ * the steps around the curves on the GPU as well switches the corresponding R lines to these.  They are
+ * tolerance-level by nature: R's %*% is BLAS and lm() is Householder QR.
+ * ------------------------------------------------------------------------------------ */
+
+/* replaces fastGLOBETROTTER.R:1216-1249 (also R:1427-1457, 1773-1803, 2078-2109, 2222-2253): results = tempweights %*% null,
+ * symmetrise, expectation from the margins, null curves = results / expectation, means = means / null curves.
+ * temp_weights: as handed to data_read ([(k*K+l)*S*S + m*S+n]); null_mat: [K*K][G] row-major -- the chrom_ind_res buffer of
+ * data_read_null (after R's removal of the target rows/columns, if any, with K reduced accordingly); means: [S*S][G]
+ * row-major (the `means` buffer of data_read), divided in place (may be NULL); null_curves_out: [S*S][G] or NULL. */
+int fgt_null_normalise(const double *temp_weights, const double *null_mat, int num_surrogates, int num_donors, int num_bins,
+                       double *means, double *null_curves_out);
+/* .C flavour: .C("null_normalise", as.double(tempweights), as.double(t(null)), S, K, G, means = as.double(t(means))) */
+void null_normalise(double *temp_weights, double *null_mat, int *num_surrogates, int *num_donors, int *num_bins, double *means);
+
+/* replaces getlhood (fastGLOBETROTTER.R:441-489) evaluated for a whole list of candidate dates at once: means [n_curves][n_times]
+ * row-major (n_curves = S*S), admixtimes [n_cand][nparam] (nparam 1 or 2), popfracs [S]; lhood_out [n_cand]. */
+int fgt_getlhood_grid(const double *means, int n_curves, int n_times, const double *times, const double *admixtimes, int n_cand,
+                      int nparam, const double *popfracs, double likpenalty, double *lhood_out);
+/* replaces getmax(..., returnall=F) (R:491-520): grid 10^seq(0,3,.25) then Nelder-Mead in sqrt(date-1); par_out [nparam] dates,
+ * value_out the minimised -lhood, likpenalty_out the penalty getmax derives from the first grid point. */
+int fgt_getmax(const double *means, int n_curves, int n_times, const double *times, int nparam, const double *popfracs, double *par_out,
+               double *value_out, double *likpenalty_out);
+
+/* Bootstrap replicates formed on the device from per-(individual, chromosome) partial curves (BASELINE north_star; the
+ * relaxed shortcut of SURVEY 8e): after ONE plain data_read / data_read_mode3 call made with option "keep_partials" = 1
+ * (every individual once, in order), each replicate's curves are recombined from the kept projections instead of re-drawing
+ * the sampled pairs: ind_id_vec [n_replicates][num_inds*num_chrom] as R:2058-2059 builds it, means_out [n_replicates][S*S*G].
+ * NOT bit-comparable with the reference, which draws fresh pairs for every replicate; statistically the replicates resample
+ * individuals per chromosome exactly like R's. */
+int fgt_bootstrap_means(const int32_t *ind_id_vec, int n_replicates, double *means_out);
+
 const char *fgt_version(void);
 
 #ifdef __cplusplus

@@ -136,3 +136,21 @@ def test_one_process_per_gpu_with_the_library_process_group(oracle):
         assert np.max(np.abs(out[r][1][ok] - m_o[ok]) / np.abs(m_o[ok])) < 1e-12
         assert np.array_equal(out[r][4], want_next)          # every rank's generator advanced by the whole call's pairs
     assert np.array_equal(out[0][1], out[1][1])              # the all-reduce leaves the same bits on both ranks
+
+
+@needs2
+def test_null_tensor_over_two_gpus_is_bit_exact(lib, oracle):
+    """data_read_null with "devices" = 2: every engine folds the label pairs it owns, the partial tensors have disjoint
+    supports and their sum is the single-GPU (= reference) tensor bit for bit, including the add-into-caller semantics."""
+    spec, chrom = _problem(n_inds=6, n_chrom=2)
+    K, G = spec.K, 110
+    dl = spec.donor_label_vec()
+    init = np.random.default_rng(3).random(K * K * G)
+    n_o, ev = oracle.data_read_null_packed(2, spec.nsamples, chrom, np.arange(6), 0.1, G, 10, K, dl, 0.0, 1.0, init=init)
+    lib.set_option("devices", 2)
+    try:
+        n_g, st = lib.data_read_null_packed(2, spec.nsamples, chrom, np.arange(6), 0.1, G, 10, K, dl, 0.0, 1.0, init=init)
+    finally:
+        lib.set_option("devices", 1)
+    assert st["pairs"] == ev
+    assert np.array_equal(n_g, n_o)
