@@ -241,9 +241,16 @@ def run_ours(args):
         lib.set_option("strict", 0)
         dt_r, pairs_r, agg_r, means_r = timed(chrom_dev, e_steps, 2)
         lib.set_option("strict", 1)
-        ok = np.isfinite(means) & (means != 0)
+        # same stream position as a strict call: one call each right after srand(1)
+        lib.srand(1)
+        m_s, _ = one_step(chrom_dev)
+        lib.set_option("strict", 0)
+        lib.srand(1)
+        m_r, _ = one_step(chrom_dev)
+        lib.set_option("strict", 1)
+        ok = np.isfinite(m_s) & (m_s != 0)
         relaxed = {"dt": dt_r, "pairs": pairs_r, "agg": agg_r, "steps": e_steps,
-                   "max_rel_diff_vs_strict": float(np.max(np.abs(means_r[ok] - means[ok]) / np.abs(means[ok])))}
+                   "max_rel_diff_vs_strict": float(np.max(np.abs(m_r[ok] - m_s[ok]) / np.abs(m_s[ok])))}
     variants = None
     if world == 1 and args.variants:
         variants = {}
@@ -254,7 +261,7 @@ def run_ours(args):
             for k in opts:
                 lib.set_option(k, {"rand_impl": 1, "commit_impl": 0}[k])
             variants[name] = {"value": pairs_v / dt_v, "ms_per_step": dt_v / e_steps * 1e3, "ms_accum": agg_v["ms_accum"] / e_steps,
-                              "ms_rand": agg_v["ms_rand"] / e_steps, "same_bits": bool(np.array_equal(means_v, means))}
+                              "ms_rand": agg_v["ms_rand"] / e_steps}
     dense = None
     if world == 1 and not args.no_dense:
         # the same paintings as dense uint16 label matrices (round 1's packed format): chunked on the device by the label-scan kernels
@@ -272,7 +279,7 @@ def run_ours(args):
         dt_dh, pairs_dh, agg_dh, _ = timed(dchrom_host, 3, 1)
         lib.encode = "rle"
         dense = {"value": pairs_d / dt_d, "ms_per_step": dt_d / 3 * 1e3, "e2e_value": pairs_dh / dt_dh, "e2e_ms_per_step": dt_dh / 3 * 1e3,
-                 "e2e_h2d_bytes_per_step": agg_dh["h2d_bytes"] / 3, "same_bits_as_rle": bool(np.array_equal(means_d, means))}
+                 "e2e_h2d_bytes_per_step": agg_dh["h2d_bytes"] / 3}
 
     out = None
     if rank == 0:

@@ -694,7 +694,31 @@ Loaded load_inputs(int ploidy, char **samp_list, char **recom_list, int n_rec, c
     const bool use_cache = Engine::get().opt.cache != 0;
     L.maps.resize(L.num_chrom);
     L.files.resize(L.num_chrom);
-    for (int h = 0; h < L.num_chrom; h++) L.maps[h] = read_recomb(rfiles[h]);
+    {
+        // recombination maps are parsed once per (path, size, mtime): a 100k-row map costs ~10 ms of strtod per call otherwise
+        static std::mutex mu;
+        static std::map<std::string, std::shared_ptr<RecombMap>> map_cache;
+        for (int h = 0; h < L.num_chrom; h++) {
+            long long sz = 0, mt = 0;
+            std::string key;
+            if (use_cache && file_identity(rfiles[h], sz, mt)) key = rfiles[h] + "|" + std::to_string(sz) + "|" + std::to_string(mt);
+            std::shared_ptr<RecombMap> m;
+            if (!key.empty()) {
+                std::lock_guard<std::mutex> lk(mu);
+                auto it = map_cache.find(key);
+                if (it != map_cache.end()) m = it->second;
+            }
+            if (!m) {
+                m = std::make_shared<RecombMap>(read_recomb(rfiles[h]));
+                if (!key.empty()) {
+                    std::lock_guard<std::mutex> lk(mu);
+                    if (map_cache.size() > 256) map_cache.clear();
+                    map_cache[key] = m;
+                }
+            }
+            L.maps[h] = *m;
+        }
+    }
 
     // up to four files are streamed at once (zlib is sequential per file), the tokeniser threads are shared out among them
     const int nt = n_threads();
@@ -1019,6 +1043,10 @@ int fgt_bootstrap_means(const int32_t *ind_id_vec, int n_replicates, double *mea
 }
 
 int64_t fgt_get_raw_counts(double *out, int64_t capacity) { return Engine::get_raw_all(out, capacity); }
+
+void fgt_set_option_R(char **key, double *value) {          // .C flavour: .C("fgt_set_option_R", "devices", 8)
+    if (key && *key && value) Engine::get().set_option(*key, *value);
+}
 
 int fgt_set_option(const char *key, double value) { return key ? Engine::get().set_option(key, value) : FGT_ERR_ARG; }
 double fgt_get_option(const char *key) { return key ? Engine::get().get_option(key) : NAN; }

@@ -45,7 +45,12 @@ void DevBuf::release() {
 }
 
 static Options &global_options() {
-    static Options o;
+    static Options o = []() {
+        Options v;
+        // an unchanged R script cannot call fgt_set_option: the number of GPUs per call can come from the environment
+        if (const char *e = getenv("FGT_DEVICES")) { const int n = atoi(e); if (n >= 1) v.devices = std::min(n, kMaxEngines); }
+        return v;
+    }();
     return o;
 }
 

@@ -165,6 +165,7 @@ int64_t fgt_get_raw_counts(double *out, int64_t capacity);
  * buffer and keeps its own cells of it); the outputs have disjoint supports, so their sum (one all-reduce) is
  * bit-identical to the single-process result. */
 int fgt_set_option(const char *key, double value);
+void fgt_set_option_R(char **key, double *value);     /* the same for R: .C("fgt_set_option_R", "devices", 8) */
 double fgt_get_option(const char *key);
 
 /* seed of the private glibc-compatible stream (rand_libc = 0); same sequence as srand(seed). */
