@@ -506,6 +506,115 @@ def other_paths(lib, chrom_dev, common, tail, S, tw, N, dl, K, G, W, steps=3, nu
     return res
 
 
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs[2..4]: biobank-shaped runs (device-generated run-length-encoded paintings), one JSON line each.
+# Not part of the default run (the headline stays on configs[1]); `python bench.py --config 3|4|5 [--scale f --chrom-frac f]`.
+# ------------------------------------------------------------------------------------------------
+BIG = {
+    3: dict(name="configs[2]: 22 autosomes, 1,000 target haps (500 diploid inds) x 10 samples, 500k SNPs/chr, K=50, 500 bins, "
+                 "one chromosome-bootstrap replicate (R:2058-2059 id matrix), data_read (mode 1)",
+            n_chrom=22, n_inds=500, n_snps=500_000, K=50, S=10, mode=1, kind="curves", boot=True),
+    4: dict(name="configs[3]: 22 chr, K=100 surrogates, full NULL-individual curve set (data_read_null over the first 100 "
+                 "individuals, one sample each), 100k SNPs/chr (~600 chunks per painting)",
+            n_chrom=22, n_inds=100, n_snps=100_000, K=100, S=10, mode=1, kind="null", boot=False),
+    5: dict(name="configs[4]: one GPU's shard (1/8) of the biobank run: 1,250 of 10,000 diploid inds x 10 samples, 1M SNPs/chr, "
+                 "K=150, 500 bins, data_read_mode3 (mode-3 dataflow)",
+            n_chrom=22, n_inds=1250, n_snps=1_000_000, K=150, S=10, mode=3, kind="curves", boot=False),
+}
+
+
+def run_big(args):
+    import torch
+    from fastglobetrotter_b200 import build as fbuild, synth
+    from fastglobetrotter_b200.companion import PackedCompanion
+    from fastglobetrotter_b200.synth_torch import make_chromosome_runs_device
+    cfg = dict(BIG[args.config])
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    lib = PackedCompanion(fbuild.build())
+    lib.set_option("rand_libc", 0)
+    for kv in filter(None, os.environ.get("FGT_OPTS", "").split(",")):
+        k, v = kv.split("=")
+        lib.set_option(k.strip(), float(v))
+    n_chrom = max(1, int(round(cfg["n_chrom"] * args.chrom_frac)))
+    n_inds = max(2, int(round(cfg["n_inds"] * args.scale)))
+    K, S, G, mode = cfg["K"], cfg["S"], 500, cfg["mode"]
+    spec = synth.SynthSpec(n_chrom=n_chrom, n_inds=n_inds, ploidy=2, nsamples=10, n_snps=cfg["n_snps"], K=K, haps_per_pop=20,
+                           seed=20261019 + args.config, name=f"cfg{args.config}")
+    t0 = time.perf_counter()
+    chrom, keep, n_runs = [], [], 0
+    for h in range(n_chrom):
+        pos, rate, run_off, runs = make_chromosome_runs_device(spec, h, dev)
+        keep.append(runs)
+        n_runs += int(run_off[-1])
+        chrom.append({"pos": pos, "rate": rate, "runs": (run_off, int(runs.data_ptr()))})
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t0
+    dl = spec.donor_label_vec()
+    if mode == 3:
+        dl = np.where(dl == 0, 1, dl).astype(np.int32)
+    tw = lib.temp_weights_for_data_read(K, S, synth.random_weights(K, S))
+    rng = np.random.default_rng(5)
+    if cfg["boot"]:
+        ids = np.ascontiguousarray(np.sort(rng.integers(0, n_inds, size=(n_chrom, n_inds)), axis=1).T.ravel().astype(np.int32))
+    else:
+        ids = np.repeat(np.arange(n_inds, dtype=np.int32), n_chrom)
+    peak, peak_src = peaks()
+    sampler = ClockSampler(0)
+    out = {"metric": METRIC, "unit": UNIT, "n_gpus": 1, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic (device-generated run-length-encoded paintings)", "steps": args.steps, "warmup": 1}
+    lib.srand(1)
+    if cfg["kind"] == "curves":
+        call = lambda: lib.data_read_packed(mode, 2, 10, chrom, ids, 0.1, G, 10, K, dl, 0.0, 1.0, S, tw)
+        call()                                                 # warm-up (buffers, tables)
+        torch.cuda.synchronize()
+        sampler.start()
+        t0 = time.perf_counter()
+        pairs = acc = 0
+        ms_accum = launches = chunks = 0
+        for _ in range(args.steps):
+            m, _, st = call()
+            pairs += st["pairs"]; acc += st["accepted"]; ms_accum += st["ms_accum"]; launches += st["accum_launches"]; chunks += st["chunks"]
+        dt = time.perf_counter() - t0
+        clocks = sampler.stop()
+        P = K * (K + 1) // 2
+        alg = 16.0 * pairs + 32.0 * chunks + 8.0 * P * G * n_inds * (n_chrom if mode == 3 else 1) * args.steps
+        kern_s = ms_accum * 1e-3
+        out.update({"value": pairs / dt, "ms_per_step": dt / args.steps * 1e3,
+                    "config": {"workload": cfg["name"], "run_at": f"{n_inds} individuals x {n_chrom} chromosomes (scale {args.scale}, chromosome fraction {args.chrom_frac})",
+                               "pairs_per_step": pairs / args.steps, "accepted_fraction": acc / max(1, pairs), "runs": n_runs,
+                               "paintings_bytes": 8 * n_runs, "generation_s": t_gen, "options": os.environ.get("FGT_OPTS", "")},
+                    "roofline": {"bound": "hbm", "kernel": "k_eval_pairs (+ k_route) + k_commit_ordered (all batches of the call)", "achieved": alg / kern_s / 1e9,
+                                 "peak": peak, "unit": "GB/s", "frac": alg / kern_s / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                                 "kernel_ms": kern_s * 1e3 / args.steps, "accum_launches_per_step": launches / args.steps},
+                    "gpu_launches": None, "clocks": clocks, "means_checksum": float(np.nansum(m))})
+    else:
+        rows = np.arange(min(100, n_inds), dtype=np.int32)
+        call = lambda: lib.data_read_null_packed(2, 10, chrom, rows, 0.1, G, 10, K, dl, 0.0, 1.0)
+        call()
+        torch.cuda.synchronize()
+        sampler.start()
+        t0 = time.perf_counter()
+        ev = acc = 0
+        for _ in range(args.steps):
+            t, st = call()
+            ev += st["pairs"]; acc += st["accepted"]
+        dt = time.perf_counter() - t0
+        clocks = sampler.stop()
+        out.update({"metric": "null_chunk_pair_evaluations_per_sec", "unit": "chunk-pair evaluations/s", "value": ev / dt,
+                    "ms_per_step": dt / args.steps * 1e3,
+                    "config": {"workload": cfg["name"], "run_at": f"{rows.size} individuals x {n_chrom} chromosomes (chromosome fraction {args.chrom_frac})",
+                               "evaluations_per_step": ev / args.steps, "accepted_fraction": acc / max(1, ev), "runs": n_runs,
+                               "options": os.environ.get("FGT_OPTS", "")},
+                    "roofline": {"bound": "hbm", "kernel": "k_null_strict", "achieved": 16.0 * acc / dt / 1e9, "peak": peak, "unit": "GB/s",
+                                 "frac": 16.0 * acc / dt / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                                 "note": "16 B per accepted update (SURVEY 8d); the tensor lives in shared memory, not HBM"},
+                    "clocks": clocks, "checksum": float(np.nansum(t))})
+    print(json.dumps(out))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -538,7 +647,15 @@ def main():
     ap.add_argument("--no-dense", action="store_true", help="skip the dense-label-matrix comparison numbers")
     ap.add_argument("--variants", action="store_true", help="also time the kernel variants (bulk rand stream, lane-queue commit)")
     ap.add_argument("--cpu-sample-inds", type=int, default=16)
+    ap.add_argument("--config", type=int, default=0, choices=[0, 3, 4, 5], help="run one of BASELINE.json configs[2..4] (numbered 3..5) instead of the headline")
+    ap.add_argument("--scale", type=float, default=1.0, help="--config: fraction of the configuration's individuals to run")
+    ap.add_argument("--chrom-frac", type=float, default=1.0, help="--config: fraction of the 22 chromosomes to run")
     args = ap.parse_args()
+    if args.config and args.impl != "reference":
+        if args.steps == 10:
+            args.steps = 1
+        run_big(args)
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -95,6 +95,7 @@ int Engine::set_option(const char *key, double v) {
     else if (k == "split_ready") opt.split_ready = iv;
     else if (k == "rand_impl") opt.rand_impl = iv;
     else if (k == "commit_impl") opt.commit_impl = iv;
+    else if (k == "route_impl") opt.route_impl = iv;
     else if (k == "cache_mb") opt.cache_mb = v;
     else if (k == "keep_partials") opt.keep_partials = iv;
     else if (k == "devices") opt.devices = std::max(1, std::min(iv, kMaxEngines));
@@ -127,6 +128,7 @@ double Engine::get_option(const char *key) {
     if (k == "split_ready") return opt.split_ready;
     if (k == "rand_impl") return opt.rand_impl;
     if (k == "commit_impl") return opt.commit_impl;
+    if (k == "route_impl") return opt.route_impl;
     if (k == "cache_mb") return opt.cache_mb;
     if (k == "keep_partials") return opt.keep_partials;
     if (k == "devices") return opt.devices;
@@ -822,7 +824,7 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
     int32_t *d_physof = nullptr;
     uint32_t *d_hist = nullptr;
     bool tile_in_smem = false, memset_tensor = true, relaxed = false;
-    int plan_max_w = 1, nd_max = 1;
+    int plan_max_w = 1, nd_max = 1, row_blocks = 1, rows_per_block = 0;
     const bool fused_rng = opt.rand_impl != 0;       // draws generated inside the evaluation kernel (two-phase / relaxed only)
     long long *d_recbase = nullptr;
     uint32_t *d_h0 = nullptr;
@@ -879,7 +881,24 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
             nd_max = std::max(nd_max, s.dhi - s.dlo + 1);
         }
         if (impl != 1 && !relaxed) tile_in_smem = commit_tile_bytes(K, plan_max_w) + 7168 <= 200 * 1024;
-        memset_tensor = !tile_in_smem;            // smem tiles start from zero and overwrite every cell
+        // large K: the slab tile does not fit shared memory -> route every slab's records to blocks of tensor rows whose
+        // tiles do (k_route), instead of folding into the global tensor.  route_impl: 0 = never (global-tensor commit),
+        // 1 = when the whole tile does not fit, 2 = whenever the tile exceeds the size that keeps three CTAs on an SM.
+        if (impl != 1 && !relaxed && opt.route_impl > 0) {
+            const size_t want = 56 * 1024;
+            const bool need = !tile_in_smem || (opt.route_impl >= 2 && commit_tile_bytes(K, plan_max_w) > want);
+            if (need) {
+                long long rpb = std::max<long long>(1, (long long)(want / ((size_t)plan_max_w * sizeof(double))));
+                long long nblk = ((long long)P + rpb - 1) / rpb;
+                if (nblk > 32) { nblk = 32; rpb = ((long long)P + 31) / 32; }
+                nblk = ((long long)P + rpb - 1) / rpb;
+                if (nblk > 1 && (size_t)rpb * plan_max_w * sizeof(double) + 7168 <= 200 * 1024 && (long long)P * plan_max_w < (1LL << 28)) {
+                    row_blocks = (int)nblk; rows_per_block = (int)rpb; tile_in_smem = false;
+                }
+            }
+        }
+        const bool smem_commit = tile_in_smem || row_blocks > 1;
+        memset_tensor = !smem_commit;             // smem tiles start from zero and overwrite every cell
         if (memset_tensor) CK(cudaMemsetAsync(d_tensor, 0, tens_elems * sizeof(double), st_));
         d_slabs = d_slabs_.as<SlabDesc>(slabs.size());
         d_pairbase = d_pairbase_.as<long long>((size_t)Cn * N);
@@ -939,7 +958,8 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
             mem_budget_bytes_ = std::min((double)free_b * 0.6, 64e9);
         }
         const bool use_fused = fused_rng && impl != 1;
-        budget_pairs = (long long)(mem_budget_bytes_ / 2 / ((use_fused ? 0.0 : 8.0) + (relaxed ? 1.0 : 16.0 * ns_rec)));   // two lanes hold a batch each
+        budget_pairs = (long long)(mem_budget_bytes_ / 2 / ((use_fused ? 0.0 : 8.0) + (relaxed ? 1.0 : 16.0 * ns_rec) + (row_blocks > 1 ? 16.0 : 0.0)));   // two lanes hold a batch each
+        budget_pairs = std::min<long long>(budget_pairs, 1900000000LL);      // (routed offsets are 32-bit)
     }
     tick("tables ready");
 
@@ -1149,16 +1169,35 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
                     span_begin(3, st_);
                     CK(cudaMemsetAsync(d_regions, 0, n_ent * sizeof(RegionEnt), st_));
                     launch_eval_pairs(ea, st_);
-                    span_end(st_);
-                    CK(cudaEventRecord(eval_done, st_));
-                    CK(cudaStreamWaitEvent(sc, eval_done, 0));
-                    span_begin(1, sc);
                     CommitArgs ca{};
                     ca.cp = cpd; ca.pair_base = pbase; ca.phys_of = pphys;
                     ca.N = Nb; ca.K = K; ca.G = G; ca.grid_start = pb.grid_start; ca.n_slots = plan.n_slots;
                     ca.n_slabs = (int)slabs.size();
                     ca.slabs = d_slabs; ca.recs = d_recs; ca.regions = d_regions; ca.nd_max = nd_max;
-                    ca.tensor_is_zero = (tile_in_smem && (pb.mode == 3 || h == 0)) ? 1 : 0;
+                    ca.tensor_is_zero = ((tile_in_smem || row_blocks > 1) && (pb.mode == 3 || h == 0)) ? 1 : 0;
+                    if (row_blocks > 1) {
+                        // large K: count, scan, stable scatter of every slab's records by block of tensor rows (evaluation stream)
+                        const size_t n_rt = (size_t)Nb * slabs.size() * row_blocks;
+                        int32_t *d_rcnt = d_rcnt_[bi].as<int32_t>(n_rt + 1), *d_roff = d_roff_[bi].as<int32_t>(n_rt + 1);
+                        UpdateRec *d_routed = d_routed_[bi].as<UpdateRec>((size_t)rec_pairs + 2);
+                        RegionEnt *d_rdir = d_rdir_[bi].as<RegionEnt>(n_rt);
+                        if (!d_rcnt || !d_roff || !d_routed || !d_rdir) return FGT_ERR_CUDA;
+                        RouteArgs ra{};
+                        ra.recs = d_recs; ra.regions = d_regions; ra.slabs = d_slabs;
+                        ra.N = Nb; ra.n_slabs = (int)slabs.size(); ra.nb = cs.nb; ra.nd_max = nd_max;
+                        ra.row_blocks = row_blocks; ra.rows_per_block = rows_per_block;
+                        ra.counts = d_rcnt; ra.offs = d_roff; ra.routed = d_routed; ra.routed_dir = d_rdir;
+                        launch_route(ra, false, st_);
+                        launch_exclusive_scan_i32(d_rcnt, d_roff, (int)n_rt, st_);
+                        launch_route(ra, true, st_);
+                        launches_ += 3;
+                        ca.recs = d_routed; ca.regions = d_rdir;
+                        ca.row_blocks = row_blocks; ca.rows_per_block = rows_per_block;
+                    }
+                    span_end(st_);
+                    CK(cudaEventRecord(eval_done, st_));
+                    CK(cudaStreamWaitEvent(sc, eval_done, 0));
+                    span_begin(1, sc);
                     ca.buckets = opt.commit_impl == 1 ? 1 : 0;
                     ca.tensor = tens_b; ca.accepted = d_acc;
                     ca.task_counter = d_taskctr + batch_seq;

@@ -58,6 +58,8 @@ struct Options {
     int spec_rand = 1;      // generate the first batch's draws while the chunk/bin kernels run
     int accum_impl = 2;     // 2 = two-phase (evaluate once, ordered commit); 1 = single-phase slab warps
     int rand_impl = 1;      // 1 = glibc stream generated inside the pair-evaluation kernel; 0 = bulk stream in HBM (k_rand_fill)
+    int route_impl = 1;     // large K: 1 = route records to row blocks when the slab tile does not fit shared memory, 0 = fold into the
+                            // global tensor instead, 2 = also route tiles that fit but leave fewer than three CTAs per SM
     int commit_impl = 0;    // commit kernel, shared-memory tiles: 0 = match.any fold (measured faster: 1.64 vs 3.4 ms on the bench
                             // workload), 1 = lane-queue fold without match.any (kept for A/B runs; bit-exact as well)
     double cache_mb = 8192; // parsed-file cache budget (host bytes), least recently used entries are dropped
@@ -113,6 +115,7 @@ class Engine {
     Engine();
     int idx_ = 0, device_ = 0;
     int data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_stats_t *stats, int64_t *count_only, const DistCtx *dist);
+    DevBuf d_rcnt_[2], d_roff_[2], d_routed_[2], d_rdir_[2];   // large K: routed records per batch lane (k_route)
     DevBuf d_partials_;                           // keep_partials: [Cn][N][S*S][G] projected curves of the last data_read call
     int part_Cn_ = 0, part_N_ = 0, part_S_ = 0, part_G_ = 0, part_mode_ = 0;
     bool part_valid_ = false;

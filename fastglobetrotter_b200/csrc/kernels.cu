@@ -1201,7 +1201,8 @@ __global__ void __launch_bounds__(32 * (kConsumers + 1)) k_commit_ordered(const 
     const int wid = warp_id();
     const int G = a.G;
     const int P = a.K * (a.K + 1) / 2;
-    const int total_tasks = a.N * a.n_slabs;
+    const int RB = a.row_blocks > 0 ? a.row_blocks : 1;      // row blocks per slab tile (large K: records routed per block first)
+    const int total_tasks = a.N * a.n_slabs * RB;
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], kConsumers); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -1220,17 +1221,20 @@ __global__ void __launch_bounds__(32 * (kConsumers + 1)) k_commit_ordered(const 
         __syncthreads();
         const int task = *task_slot;
         if (task >= total_tasks) break;
-        const int slab_i = task / a.N;
-        const int n = task - slab_i * a.N;
+        const int sr = task / a.N;                          // (slab, row block), heavy slabs first
+        const int n = task - sr * a.N;
+        const int slab_i = sr / RB, rb = sr - slab_i * RB;
         const SlabDesc sl = a.slabs[slab_i];
-        double *tens = a.tensor + (size_t)n * (size_t)P * G;
+        const int row0 = RB > 1 ? rb * a.rows_per_block : 0;                   // the tile holds tensor rows [row0, row0 + rows)
+        const int rows = RB > 1 ? min(a.rows_per_block, P - row0) : P;
+        double *tens = a.tensor + (size_t)n * (size_t)P * G + (size_t)row0 * G;
         const int sbw = sl.b1 - sl.b0 + 1;
         const int boff = sl.b0 - a.grid_start;
         if (TILE_SMEM) {
             if (a.tensor_is_zero) {
-                for (int idx = threadIdx.x; idx < P * sbw; idx += blockDim.x) tile[idx] = 0.0;
+                for (int idx = threadIdx.x; idx < rows * sbw; idx += blockDim.x) tile[idx] = 0.0;
             } else {
-                for (int idx = threadIdx.x; idx < P * sbw; idx += blockDim.x) {
+                for (int idx = threadIdx.x; idx < rows * sbw; idx += blockDim.x) {
                     const int row = idx / sbw, off = idx - row * sbw;
                     tile[idx] = tens[(size_t)row * G + boff + off];
                 }
@@ -1240,8 +1244,9 @@ __global__ void __launch_bounds__(32 * (kConsumers + 1)) k_commit_ordered(const 
 
         if (wid == kConsumers) {
             // ------------------------------ producer ------------------------------
-            const long long n_ent = (long long)(a.cp.nb - 1) * a.nd_max;
-            const RegionEnt *ents = a.regions + ((size_t)n * a.n_slabs + slab_i) * n_ent;
+            // routed records (row blocks): one contiguous region per task; otherwise the slab's (j, d) region directory
+            const long long n_ent = RB > 1 ? 1 : (long long)(a.cp.nb - 1) * a.nd_max;
+            const RegionEnt *ents = a.regions + (((size_t)n * a.n_slabs + slab_i) * RB + rb) * n_ent;
             RegionEnt cur, nxt;
             cur.base = 0; cur.cnt = 0; cur.pad = 0;
             if (lane < n_ent) cur = ents[lane];
@@ -1418,7 +1423,7 @@ __global__ void __launch_bounds__(32 * (kConsumers + 1)) k_commit_ordered(const 
         }
         __syncthreads();
         if (TILE_SMEM) {
-            for (int idx = threadIdx.x; idx < P * sbw; idx += blockDim.x) {
+            for (int idx = threadIdx.x; idx < rows * sbw; idx += blockDim.x) {
                 const int row = idx / sbw, o2 = idx - row * sbw;
                 tens[(size_t)row * G + boff + o2] = tile[idx];
             }
@@ -1430,11 +1435,12 @@ __global__ void __launch_bounds__(32 * (kConsumers + 1)) k_commit_ordered(const 
 size_t commit_tile_bytes(int K, int slab_width) { return (size_t)K * (K + 1) / 2 * slab_width * sizeof(double); }
 
 void launch_commit_ordered(const CommitArgs &a, int max_slab_width, cudaStream_t st) {
-    long long tasks = (long long)a.N * a.n_slabs;
+    const int RB = a.row_blocks > 0 ? a.row_blocks : 1;
+    long long tasks = (long long)a.N * a.n_slabs * RB;
     if (tasks <= 0) return;
     const size_t ctrl_bytes = 6144 + 1024;
     static_assert(kStages * kStageRecs * sizeof(UpdateRec) == 6144, "ring size");
-    const size_t tile_bytes = commit_tile_bytes(a.K, max_slab_width);
+    const size_t tile_bytes = RB > 1 ? (size_t)a.rows_per_block * max_slab_width * sizeof(double) : commit_tile_bytes(a.K, max_slab_width);
     static bool attr_set[64] = {};                    // the attribute is per device (one engine per device)
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1456,6 +1462,89 @@ void launch_commit_ordered(const CommitArgs &a, int max_slab_width, cudaStream_t
     }
 }
 
+
+// ---- large K: route the records of every (individual, slab) to row blocks ---------------------------------------------
+// A slab tile of K(K+1)/2 rows does not fit shared memory for K >~ 70.  Instead of folding into the global tensor (one DRAM
+// read-modify-write per record on a latency-bound chain), the slab's record stream is split, in stream order, by BLOCK OF
+// TENSOR ROWS: a counting pass, a scan, and a stable scatter that rewrites every record's tile index relative to its row
+// block.  Phase 2 then runs its shared-memory path on (individual, slab, row block) tasks whose tiles fit.
+// One warp per (individual, slab) walks the slab's region directory in order, 32 records per step.
+template <bool SCATTER>
+__global__ void __launch_bounds__(128)
+k_route(const RouteArgs a) {
+    __shared__ int32_t cnt_all[4][32];
+    const int lane = lane_id(), wid = warp_id();
+    const long long task = (long long)blockIdx.x * 4 + wid;
+    if (task >= (long long)a.N * a.n_slabs) return;
+    const int n = (int)(task / a.n_slabs), slab_i = (int)(task - (long long)n * a.n_slabs);
+    const int RB = a.row_blocks;
+    int32_t *cnt = cnt_all[wid];
+    cnt[lane] = 0;
+    __syncwarp();
+    const long long n_ent = (long long)(a.nb - 1) * a.nd_max;
+    const RegionEnt *ents = a.regions + ((size_t)n * a.n_slabs + slab_i) * n_ent;
+    const SlabDesc sl = a.slabs[slab_i];
+    const int sw = sl.b1 - sl.b0 + 1;
+    const unsigned sw_magic = sw > 1 ? (unsigned)(((1ULL << 32) + sw - 1) / sw) : 0u;      // local / sw (local < 2^16 * sw guaranteed by the host)
+    const unsigned rpb_magic = a.rows_per_block > 1 ? (unsigned)(((1ULL << 32) + a.rows_per_block - 1) / a.rows_per_block) : 0u;
+    const size_t tbase = ((size_t)n * a.n_slabs + slab_i) * RB;
+    const unsigned lt = (1u << lane) - 1;
+    for (long long e0 = 0; e0 < n_ent; e0 += 32) {
+        RegionEnt ent;
+        ent.base = 0; ent.cnt = 0; ent.pad = 0;
+        if (e0 + lane < n_ent) ent = ents[e0 + lane];
+        unsigned live = __ballot_sync(kFull, ent.cnt > 0);
+        while (live) {
+            const int i = __ffs(live) - 1;
+            live &= live - 1;
+            const long long base = __shfl_sync(kFull, ent.base, i);
+            const int c = __shfl_sync(kFull, ent.cnt, i);
+            for (int off = 0; off < c; off += 32) {
+                const bool v = off + lane < c;
+                UpdateRec r;
+                r.cell = 0; r.pad = 0; r.val = 0.0;
+                if (v) r = a.recs[base + off + lane];
+                const unsigned row = sw_magic ? __umulhi((unsigned)r.pad, sw_magic) : (unsigned)r.pad;
+                const unsigned rb = rpb_magic ? __umulhi(row, rpb_magic) : row;
+                if (!SCATTER) {
+                    if (v) atomicAdd(&cnt[rb], 1);
+                } else {
+                    // stable: rank among the step's records of the same row block, behind those filed before
+                    const unsigned m = __match_any_sync(kFull, v ? rb : 0xffffffffu);
+                    const int rank = __popc(m & lt);
+                    const int fill = v ? cnt[rb] : 0;
+                    __syncwarp();
+                    if (v) {
+                        UpdateRec o;
+                        o.cell = r.cell;
+                        o.pad = (int)(((unsigned)row - rb * (unsigned)a.rows_per_block) * (unsigned)sw + ((unsigned)r.pad - row * (unsigned)sw));
+                        o.val = r.val;
+                        a.routed[a.offs[tbase + rb] + fill + rank] = o;
+                        if ((m >> lane) == 1u) cnt[rb] = fill + rank + 1;
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (lane < RB) {
+        if (!SCATTER) a.counts[tbase + lane] = cnt[lane];
+        else {
+            RegionEnt o;
+            o.base = a.offs[tbase + lane]; o.cnt = cnt[lane]; o.pad = 0;
+            a.routed_dir[tbase + lane] = o;
+        }
+    }
+}
+
+void launch_route(const RouteArgs &a, bool scatter, cudaStream_t st) {
+    const long long tasks = (long long)a.N * a.n_slabs;
+    if (tasks <= 0) return;
+    const unsigned grid = (unsigned)((tasks + 3) / 4);
+    if (scatter) k_route<true><<<grid, 128, 0, st>>>(a);
+    else k_route<false><<<grid, 128, 0, st>>>(a);
+}
 
 // ---- sharded calls: stream offsets on the device -------------------------------------------------------------------
 // all[r][0] = individuals of shard r, all[r][1 + n] = sampled pairs of its n-th individual on this chromosome (gathered

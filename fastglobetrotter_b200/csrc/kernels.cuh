@@ -98,10 +98,23 @@ struct CommitArgs {
     const RegionEnt *regions;
     int32_t nd_max, tensor_is_zero;
     int32_t buckets;              // 1: lane-queue fold (no match.any) for shared-memory tiles; 0: match.any fold
+    int32_t row_blocks;           // > 1: tasks are (individual, slab, block of rows_per_block tensor rows) over ROUTED records:
+    int32_t rows_per_block;       //      `regions` then holds one entry per task and `recs` the routed buffer (see k_route)
     double *tensor;
     unsigned long long *accepted;
     int *task_counter;            // zeroed before the launch: persistent CTAs claim (individual, slab) tasks from it
 };
+struct RouteArgs {               // large K: split every (individual, slab) record stream by block of tensor rows (k_route)
+    const UpdateRec *recs;        // phase-1 records ...
+    const RegionEnt *regions;     // ... and their directory [N*n_slabs][nb-1][nd_max]
+    const SlabDesc *slabs;
+    int32_t N, n_slabs, nb, nd_max, row_blocks, rows_per_block;
+    int32_t *counts;              // [N*n_slabs*row_blocks] records per task (counting pass)
+    const int32_t *offs;          // [N*n_slabs*row_blocks + 1] exclusive scan of counts (scatter pass)
+    UpdateRec *routed;            // records in (individual, slab, row block) order, tile index relative to the row block
+    RegionEnt *routed_dir;        // [N*n_slabs*row_blocks] one region per task
+};
+void launch_route(const RouteArgs &a, bool scatter, cudaStream_t st);
 void launch_eval_pairs(const EvalArgs &a, cudaStream_t st);
 void launch_commit_ordered(const CommitArgs &a, int max_slab_width, cudaStream_t st);
 size_t commit_tile_bytes(int K, int slab_width);

@@ -387,32 +387,42 @@ def test_pipeline_options_do_not_change_results(lib, oracle, small):
         lib.set_option("blocks", 0); lib.set_option("ranges", 8); lib.set_option("split_ready", 1)
 
 
-def test_large_K_uses_the_global_tensor_path(lib, oracle):
-    """K = 80 donor groups: the slab tile (3240 rows x 10 bins x 8 B) no longer fits in shared memory, so the
-    commit kernel folds straight into the global tensor (TILE_SMEM = false).  Also K = 50 (tile in smem, 2 CTAs/SM)."""
-    for K, haps in ((80, 3), (50, 4)):
-        spec = synth.SynthSpec(n_chrom=2, n_inds=3, n_snps=3000, K=K, haps_per_pop=haps, nsamples=3, rate=4e-7, seed=31 + K)
-        chrom = []
-        for h in range(spec.n_chrom):
-            pos, rate, labels = synth.make_chromosome(spec, h)
-            chrom.append({"pos": pos, "rate": rate, "labels": labels})
-        dl = spec.donor_label_vec()
-        S, G, bw, gs = 2, 60, 0.1, 10
-        tw = np.random.default_rng(K).random(K * K * S * S)
-        ids = ind_id_matrix(spec.n_inds, spec.n_chrom)
-        oracle.srand(3)
-        m_o, raw_o, pairs = oracle.data_read_packed(1, spec.ploidy, spec.nsamples, chrom, ids, bw, G, gs, K, dl, 0.0, 1.0, S, tw,
-                                                    want_raw=True)
-        lib.set_option("rand_libc", 0)
-        lib.srand(3)
-        m_g, raw_g, st = lib.data_read_packed(1, spec.ploidy, spec.nsamples, chrom, ids, bw, G, gs, K, dl, 0.0, 1.0, S, tw,
-                                              want_raw=True)
-        assert st["pairs"] == pairs
-        assert np.array_equal(raw_g, raw_o), K
-        assert np.array_equal(m_g, m_o), K
-        lib.srand(3)
-        m_g2, _, _ = lib.data_read_packed(1, spec.ploidy, spec.nsamples, chrom, ids, bw, G, gs, K, dl, 0.0, 1.0, S, tw)
-        assert np.array_equal(m_g2, m_o), K          # per-range projection path (no raw requested)
+@pytest.mark.parametrize("route_impl", [0, 1, 2])
+def test_large_K_commit_paths(lib, oracle, route_impl):
+    """K = 80 and 120 donor groups: the slab tile (3240 / 7260 rows x 10 bins x 8 B) no longer fits in shared memory.
+    route_impl = 1 (default): every slab's records are routed, in stream order, to blocks of tensor rows whose tiles fit
+    (k_route: count, scan, stable scatter) and committed through the shared-memory path; 0: folded straight into the global
+    tensor; 2: tiles that fit but crowd the SM are routed as well (K = 50).  Modes 1 and 3, several chromosomes and batches."""
+    lib.set_option("route_impl", route_impl)
+    try:
+        for K, haps, mode in ((80, 3, 1), (50, 4, 1), (120, 2, 3)):
+            spec = synth.SynthSpec(n_chrom=2, n_inds=3, n_snps=3000, K=K, haps_per_pop=haps, nsamples=3, rate=4e-7, seed=31 + K)
+            chrom = []
+            for h in range(spec.n_chrom):
+                pos, rate, labels = synth.make_chromosome(spec, h)
+                chrom.append({"pos": pos, "rate": rate, "labels": labels})
+            dl = spec.donor_label_vec()
+            S, G, bw, gs = 2, 60, 0.1, 10
+            tw = np.random.default_rng(K).random(K * K * S * S)
+            ids = ind_id_matrix(spec.n_inds, spec.n_chrom)
+            oracle.srand(3)
+            m_o, raw_o, pairs = oracle.data_read_packed(mode, spec.ploidy, spec.nsamples, chrom, ids, bw, G, gs, K, dl, 0.0, 1.0, S, tw,
+                                                        want_raw=True)
+            lib.set_option("rand_libc", 0)
+            for batch in (0, 20000):
+                lib.set_option("batch_pairs", batch)
+                lib.srand(3)
+                m_g, raw_g, st = lib.data_read_packed(mode, spec.ploidy, spec.nsamples, chrom, ids, bw, G, gs, K, dl, 0.0, 1.0, S, tw,
+                                                      want_raw=True)
+                assert st["pairs"] == pairs
+                assert np.array_equal(raw_g, raw_o), (K, batch, int((raw_g != raw_o).sum()))
+                assert np.array_equal(m_g, m_o), (K, batch)
+            lib.srand(3)
+            m_g2, _, _ = lib.data_read_packed(mode, spec.ploidy, spec.nsamples, chrom, ids, bw, G, gs, K, dl, 0.0, 1.0, S, tw)
+            assert np.array_equal(m_g2, m_o), K          # per-range projection path (no raw requested)
+    finally:
+        lib.set_option("route_impl", 1)
+        lib.set_option("batch_pairs", 0)
 
 
 def _run_both(lib, oracle, mode, ploidy, nsamples, chrom, ids, bw, G, gs, K, dl, wmin, cutoff, S, tw, seed=7):
