@@ -1178,19 +1178,21 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
                     if (row_blocks > 1) {
                         // large K: count, scan, stable scatter of every slab's records by block of tensor rows (evaluation stream)
                         const size_t n_rt = (size_t)Nb * slabs.size() * row_blocks;
-                        int32_t *d_rcnt = d_rcnt_[bi].as<int32_t>(n_rt + 1), *d_roff = d_roff_[bi].as<int32_t>(n_rt + 1);
+                        const int jch = std::max(1, (cs.nb - 1 + 31) / 32);
+                        const size_t n_cnt = n_rt * jch;
+                        int32_t *d_rcnt = d_rcnt_[bi].as<int32_t>(n_cnt + 1 + 2 * (n_cnt / 1024 + 2)), *d_roff = d_roff_[bi].as<int32_t>(n_cnt + 1);
                         UpdateRec *d_routed = d_routed_[bi].as<UpdateRec>((size_t)rec_pairs + 2);
                         RegionEnt *d_rdir = d_rdir_[bi].as<RegionEnt>(n_rt);
                         if (!d_rcnt || !d_roff || !d_routed || !d_rdir) return FGT_ERR_CUDA;
                         RouteArgs ra{};
                         ra.recs = d_recs; ra.regions = d_regions; ra.slabs = d_slabs;
                         ra.N = Nb; ra.n_slabs = (int)slabs.size(); ra.nb = cs.nb; ra.nd_max = nd_max;
-                        ra.row_blocks = row_blocks; ra.rows_per_block = rows_per_block;
+                        ra.row_blocks = row_blocks; ra.rows_per_block = rows_per_block; ra.j_chunks = jch;
                         ra.counts = d_rcnt; ra.offs = d_roff; ra.routed = d_routed; ra.routed_dir = d_rdir;
                         launch_route(ra, false, st_);
-                        launch_exclusive_scan_i32(d_rcnt, d_roff, (int)n_rt, st_);
+                        launch_exclusive_scan_i32_large(d_rcnt, d_roff, (long long)n_cnt, d_rcnt + n_cnt + 1, st_);
                         launch_route(ra, true, st_);
-                        launches_ += 3;
+                        launches_ += 7;
                         ca.recs = d_routed; ca.regions = d_rdir;
                         ca.row_blocks = row_blocks; ca.rows_per_block = rows_per_block;
                     }

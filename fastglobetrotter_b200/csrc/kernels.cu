@@ -1468,31 +1468,42 @@ void launch_commit_ordered(const CommitArgs &a, int max_slab_width, cudaStream_t
 // read-modify-write per record on a latency-bound chain), the slab's record stream is split, in stream order, by BLOCK OF
 // TENSOR ROWS: a counting pass, a scan, and a stable scatter that rewrites every record's tile index relative to its row
 // block.  Phase 2 then runs its shared-memory path on (individual, slab, row block) tasks whose tiles fit.
-// One warp per (individual, slab) walks the slab's region directory in order, 32 records per step.
+// One warp per (individual, slab, chunk of 32 coarse bins j) walks its part of the slab's region directory in order, 32
+// records per step; counts are kept per (individual, slab, row block, j chunk) in exactly the order the routed buffer is
+// laid out, so one exclusive scan gives every warp of the scatter pass its own write positions and the passes are fully
+// parallel while each row block's records stay in stream order.
+constexpr int kRouteJ = 32;       // coarse bins per routing task
+
 template <bool SCATTER>
 __global__ void __launch_bounds__(128)
 k_route(const RouteArgs a) {
     __shared__ int32_t cnt_all[4][32];
     const int lane = lane_id(), wid = warp_id();
+    const int JC = a.j_chunks;
     const long long task = (long long)blockIdx.x * 4 + wid;
-    if (task >= (long long)a.N * a.n_slabs) return;
-    const int n = (int)(task / a.n_slabs), slab_i = (int)(task - (long long)n * a.n_slabs);
+    if (task >= (long long)a.N * a.n_slabs * JC) return;
+    const int jc = (int)(task % JC);
+    const long long ns_i = task / JC;
+    const int n = (int)(ns_i / a.n_slabs), slab_i = (int)(ns_i - (long long)n * a.n_slabs);
     const int RB = a.row_blocks;
     int32_t *cnt = cnt_all[wid];
     cnt[lane] = 0;
     __syncwarp();
     const long long n_ent = (long long)(a.nb - 1) * a.nd_max;
     const RegionEnt *ents = a.regions + ((size_t)n * a.n_slabs + slab_i) * n_ent;
+    const long long e_lo = (long long)jc * kRouteJ * a.nd_max, e_hi = min(n_ent, (long long)(jc + 1) * kRouteJ * a.nd_max);
     const SlabDesc sl = a.slabs[slab_i];
     const int sw = sl.b1 - sl.b0 + 1;
-    const unsigned sw_magic = sw > 1 ? (unsigned)(((1ULL << 32) + sw - 1) / sw) : 0u;      // local / sw (local < 2^16 * sw guaranteed by the host)
+    const unsigned sw_magic = sw > 1 ? (unsigned)(((1ULL << 32) + sw - 1) / sw) : 0u;      // local / sw (local * sw < 2^32, checked on the host)
     const unsigned rpb_magic = a.rows_per_block > 1 ? (unsigned)(((1ULL << 32) + a.rows_per_block - 1) / a.rows_per_block) : 0u;
-    const size_t tbase = ((size_t)n * a.n_slabs + slab_i) * RB;
+    const size_t tbase = ((size_t)n * a.n_slabs + slab_i) * RB;                              // counter (tbase + rb) * JC + jc
     const unsigned lt = (1u << lane) - 1;
-    for (long long e0 = 0; e0 < n_ent; e0 += 32) {
+    int32_t my_off = 0;
+    if (SCATTER && lane < RB) my_off = a.offs[(tbase + lane) * JC + jc];
+    for (long long e0 = e_lo; e0 < e_hi; e0 += 32) {
         RegionEnt ent;
         ent.base = 0; ent.cnt = 0; ent.pad = 0;
-        if (e0 + lane < n_ent) ent = ents[e0 + lane];
+        if (e0 + lane < e_hi) ent = ents[e0 + lane];
         unsigned live = __ballot_sync(kFull, ent.cnt > 0);
         while (live) {
             const int i = __ffs(live) - 1;
@@ -1509,17 +1520,18 @@ k_route(const RouteArgs a) {
                 if (!SCATTER) {
                     if (v) atomicAdd(&cnt[rb], 1);
                 } else {
-                    // stable: rank among the step's records of the same row block, behind those filed before
+                    // stable: rank among the step's records of the same row block, behind those this warp filed before
                     const unsigned m = __match_any_sync(kFull, v ? rb : 0xffffffffu);
                     const int rank = __popc(m & lt);
                     const int fill = v ? cnt[rb] : 0;
+                    const int dst0 = __shfl_sync(kFull, my_off, v ? (int)rb : 0);
                     __syncwarp();
                     if (v) {
                         UpdateRec o;
                         o.cell = r.cell;
                         o.pad = (int)(((unsigned)row - rb * (unsigned)a.rows_per_block) * (unsigned)sw + ((unsigned)r.pad - row * (unsigned)sw));
                         o.val = r.val;
-                        a.routed[a.offs[tbase + rb] + fill + rank] = o;
+                        a.routed[(long long)dst0 + fill + rank] = o;
                         if ((m >> lane) == 1u) cnt[rb] = fill + rank + 1;
                     }
                     __syncwarp();
@@ -1528,22 +1540,71 @@ k_route(const RouteArgs a) {
         }
     }
     __syncwarp();
-    if (lane < RB) {
-        if (!SCATTER) a.counts[tbase + lane] = cnt[lane];
-        else {
-            RegionEnt o;
-            o.base = a.offs[tbase + lane]; o.cnt = cnt[lane]; o.pad = 0;
-            a.routed_dir[tbase + lane] = o;
-        }
+    if (!SCATTER && lane < RB) a.counts[(tbase + lane) * JC + jc] = cnt[lane];
+}
+
+// one region per commit task (individual, slab, row block): the j chunks of a row block are adjacent in the routed buffer
+__global__ void k_route_dir(const int32_t *__restrict__ offs, long long n_tasks, int JC, RegionEnt *__restrict__ dir) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tasks) return;
+    RegionEnt o;
+    o.base = offs[t * JC];
+    o.cnt = offs[(t + 1) * JC] - offs[t * JC];
+    o.pad = 0;
+    dir[t] = o;
+}
+
+// exclusive scan of n int32 (n up to a few 10^6): per-block sums, scan of the sums, per-block scan
+__global__ void __launch_bounds__(1024) k_scan_block_sums(const int32_t *__restrict__ in, long long n, int32_t *__restrict__ sums) {
+    __shared__ int wtot[32];
+    const long long i = (long long)blockIdx.x * 1024 + threadIdx.x;
+    int v = i < n ? in[i] : 0;
+    v = warp_sum(v);
+    if (lane_id() == 0) wtot[warp_id()] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int s = wtot[threadIdx.x];
+        s = warp_sum(s);
+        if (threadIdx.x == 0) sums[blockIdx.x] = s;
     }
+}
+__global__ void __launch_bounds__(1024) k_scan_apply(const int32_t *__restrict__ in, long long n, const int32_t *__restrict__ block_off,
+                                                      int32_t *__restrict__ out) {
+    __shared__ int wtot[32];
+    const long long i = (long long)blockIdx.x * 1024 + threadIdx.x;
+    const int v = i < n ? in[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(kFull, x, o);
+        if (lane_id() >= o) x += y;
+    }
+    if (lane_id() == 31) wtot[warp_id()] = x;
+    __syncthreads();
+    int base = block_off[blockIdx.x];
+    for (int w = 0; w < warp_id(); w++) base += wtot[w];
+    if (i < n) out[i] = base + x - v;
+    if (i == n - 1) out[n] = base + x;
+}
+
+void launch_exclusive_scan_i32_large(const int32_t *in, int32_t *out, long long n, int32_t *scratch /*[2 * (n/1024 + 2)]*/, cudaStream_t st) {
+    if (n <= 0) return;
+    const long long nblk = (n + 1023) / 1024;
+    int32_t *sums = scratch, *sums_off = scratch + nblk + 1;
+    k_scan_block_sums<<<(unsigned)nblk, 1024, 0, st>>>(in, n, sums);
+    k_exclusive_scan_i32<<<1, 1024, 0, st>>>(sums, sums_off, (int)nblk);
+    k_scan_apply<<<(unsigned)nblk, 1024, 0, st>>>(in, n, sums_off, out);
 }
 
 void launch_route(const RouteArgs &a, bool scatter, cudaStream_t st) {
-    const long long tasks = (long long)a.N * a.n_slabs;
+    const long long tasks = (long long)a.N * a.n_slabs * a.j_chunks;
     if (tasks <= 0) return;
     const unsigned grid = (unsigned)((tasks + 3) / 4);
-    if (scatter) k_route<true><<<grid, 128, 0, st>>>(a);
-    else k_route<false><<<grid, 128, 0, st>>>(a);
+    if (scatter) {
+        k_route<true><<<grid, 128, 0, st>>>(a);
+        const long long nt = (long long)a.N * a.n_slabs * a.row_blocks;
+        k_route_dir<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(a.offs, nt, a.j_chunks, a.routed_dir);
+    } else k_route<false><<<grid, 128, 0, st>>>(a);
 }
 
 // ---- sharded calls: stream offsets on the device -------------------------------------------------------------------

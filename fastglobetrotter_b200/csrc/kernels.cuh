@@ -109,12 +109,14 @@ struct RouteArgs {               // large K: split every (individual, slab) reco
     const RegionEnt *regions;     // ... and their directory [N*n_slabs][nb-1][nd_max]
     const SlabDesc *slabs;
     int32_t N, n_slabs, nb, nd_max, row_blocks, rows_per_block;
-    int32_t *counts;              // [N*n_slabs*row_blocks] records per task (counting pass)
-    const int32_t *offs;          // [N*n_slabs*row_blocks + 1] exclusive scan of counts (scatter pass)
+    int32_t j_chunks;             // ceil((nb-1) / 32): routing tasks per (individual, slab)
+    int32_t *counts;              // [N*n_slabs*row_blocks*j_chunks] records per (task, row block) (counting pass)
+    const int32_t *offs;          // [... + 1] exclusive scan of counts (scatter pass)
     UpdateRec *routed;            // records in (individual, slab, row block) order, tile index relative to the row block
     RegionEnt *routed_dir;        // [N*n_slabs*row_blocks] one region per task
 };
 void launch_route(const RouteArgs &a, bool scatter, cudaStream_t st);
+void launch_exclusive_scan_i32_large(const int32_t *in, int32_t *out, long long n, int32_t *scratch /*[2 * (n/1024 + 2)]*/, cudaStream_t st);
 void launch_eval_pairs(const EvalArgs &a, cudaStream_t st);
 void launch_commit_ordered(const CommitArgs &a, int max_slab_width, cudaStream_t st);
 size_t commit_tile_bytes(int K, int slab_width);
