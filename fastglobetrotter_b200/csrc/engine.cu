@@ -1408,7 +1408,6 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
     double *d_rs = d_rs_.as<double>((size_t)N * S * G), *d_ratio = d_ratio_.as<double>((size_t)N * S * S * G);
     double *d_means = d_means_.as<double>((size_t)S * S * G);
     if (!d_rs || !d_ratio || !d_means) return FGT_ERR_CUDA;
-    std::vector<double> part;                      // sharded call: the all-reduced curves before they are added to the caller's
     if (dist_on) CK(cudaMemsetAsync(d_means, 0, (size_t)S * S * G * sizeof(double), sc));
     else CK(cudaMemcpyAsync(d_means, means, (size_t)S * S * G * sizeof(double), cudaMemcpyHostToDevice, sc));
     launch_normalise(d_results, N, S, G, pb.num_inds_total > 0 ? pb.num_inds_total : N, d_rs, d_ratio, sc);
@@ -1418,8 +1417,14 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
         // the one all-reduce of the S^2 x G partial curves (every shard ends up with the sum)
         const int nrc = nccl().AllReduce(d_means, d_means, (size_t)S * S * G, kNcclFloat64, kNcclSum, dist->comm, sc);
         if (nrc != 0) { fprintf(stderr, "fastGLOBETROTTERCompanion(B200): ncclAllReduce failed (%d)\n", nrc); return FGT_ERR_CUDA; }
-        part.resize((size_t)S * S * G);
-        CK(cudaMemcpyAsync(part.data(), d_means, (size_t)S * S * G * sizeof(double), cudaMemcpyDeviceToHost, sc));
+        const size_t cells = (size_t)S * S * G;
+        if (pin_part_cap_ < cells) {                 // pinned: a pageable read-back would stall the stream for ~0.1 ms
+            if (pin_part_) cudaFreeHost(pin_part_);
+            pin_part_ = nullptr; pin_part_cap_ = 0;
+            if (cudaHostAlloc((void **)&pin_part_, cells * sizeof(double), cudaHostAllocDefault) != cudaSuccess) return FGT_ERR_CUDA;
+            pin_part_cap_ = cells;
+        }
+        CK(cudaMemcpyAsync(pin_part_, d_means, cells * sizeof(double), cudaMemcpyDeviceToHost, sc));
         CK(cudaMemcpyAsync(pin_msg_ + n_msg + 1, d_streampos_.p, sizeof(long long), cudaMemcpyDeviceToHost, sc));   // pairs drawn by ALL shards
     } else {
         CK(cudaMemcpyAsync(means, d_means, (size_t)S * S * G * sizeof(double), cudaMemcpyDeviceToHost, sc));
@@ -1444,7 +1449,7 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
 
     if (keep_part) { part_valid_ = true; part_Cn_ = Cn; part_N_ = N; part_S_ = S; part_G_ = G; part_mode_ = pb.mode; }
     if (dist_on) {
-        for (size_t i = 0; i < part.size(); i++) means[i] += part[i];       // added into the caller's buffer (C:644)
+        for (size_t i = 0; i < (size_t)S * S * G; i++) means[i] += pin_part_[i];       // added into the caller's buffer (C:644)
         last_total_pairs_ = pin_msg_[n_msg + 1];
     } else last_total_pairs_ = all_pairs;
     // the stream moves on by two draws per sampled pair of the WHOLE call (all shards), C:136-137

@@ -120,6 +120,8 @@ class Engine {
     int part_Cn_ = 0, part_N_ = 0, part_S_ = 0, part_G_ = 0, part_mode_ = 0;
     bool part_valid_ = false;
     DevBuf d_msg_, d_msg_all_, d_streampos_;      // sharded calls: pair counts (local / gathered), running stream position
+    double *pin_part_ = nullptr;                  // pinned: the all-reduced curves of a sharded call
+    size_t pin_part_cap_ = 0;
     long long *pin_msg_ = nullptr;                // pinned: [n_max + 1] counts message, then the stream position read-back
     size_t pin_msg_cap_ = 0;
     int ensure_init();

@@ -249,3 +249,17 @@ def test_truncated_gzip_is_fatal_and_cache_is_bounded(lib, tmp_path):
             ) % (ROOT, data.samples_list, data.recom_list)
     p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert p.returncode == 1 and "Something wrong with" in p.stdout
+
+
+def test_option_setters_for_R_and_environment(lib):
+    """fgt_set_option_R is the .C flavour (every argument a pointer); FGT_DEVICES presets the "devices" option at first use."""
+    key = (C.c_char_p * 1)(b"cache_mb")
+    val = C.c_double(123.0)
+    lib.lib.fgt_set_option_R(key, C.byref(val))
+    assert lib.get_option("cache_mb") == 123.0
+    lib.set_option("cache_mb", 8192)
+    code = ("import sys; sys.path.insert(0, %r); from fastglobetrotter_b200.companion import PackedCompanion;"
+            "print(int(PackedCompanion().get_option('devices')))") % ROOT
+    env = dict(os.environ, FGT_DEVICES="4")
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    assert p.returncode == 0 and p.stdout.strip() == "4"
