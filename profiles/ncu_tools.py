@@ -33,8 +33,11 @@ def src(rep, kernel, top=25):
             if not r or r[0]=='' : continue
             try: ln=int(r[0])
             except: continue
-            inst=int(r[ci["Instructions Executed"]].replace("-","0") or 0); samp=int(r[ci["# Samples"]].replace("-","0") or 0)
-            st={k:int(r[ci[k]].replace("-","0") or 0) for k in hdr if k.startswith('stall_') and 'Not Issued' not in k}
+            try:
+                inst=int(r[ci["Instructions Executed"]].replace("-","0") or 0); samp=int(r[ci["# Samples"]].replace("-","0") or 0)
+                st={k:int(r[ci[k]].replace("-","0") or 0) for k in hdr if k.startswith('stall_') and 'Not Issued' not in k}
+            except (ValueError, IndexError):
+                continue
             lines.append((ln,r[1].strip()[:80],inst,samp,st)); tot_inst+=inst; tot_samp+=samp
         print("total inst",tot_inst,"samples",tot_samp)
         for ln,s,inst,samp,st in sorted(lines,key=lambda x:-x[3])[:top]:
