@@ -524,29 +524,21 @@ int Engine::prep_block(const fgt_problem_t &pb, int h, int p0, int p1, int blk, 
     size_t cm = (size_t)np * PM * nb;
     int32_t *d_cnt = d_cntmat_.as<int32_t>(cm), *d_rf = d_runfirst_.as<int32_t>(cm);
     if (!d_cnt || !d_rf) return FGT_ERR_CUDA;
-    long long *d_tot = d_totals_.as<long long>(2 * (size_t)np);
+    long long *d_tot = d_totals_.as<long long>(np);
     if (!d_tot) return FGT_ERR_CUDA;
-    if (pin_tot_cap_ < 2 * (size_t)np) {
-        if (pin_tot_) cudaFreeHost(pin_tot_);
-        pin_tot_ = nullptr; pin_tot_cap_ = 0;
-        if (cudaHostAlloc((void **)&pin_tot_, (2 * (size_t)np + 64) * sizeof(long long), cudaHostAllocDefault) != cudaSuccess) return FGT_ERR_CUDA;
-        pin_tot_cap_ = 2 * (size_t)np + 64;
-    }
     CK(cudaMemsetAsync(d_cnt, 0, cm * sizeof(int32_t), sp));
     launch_bin_sort(np, PM, row_off_dev, d_cstart, d_cend, d_chap, (const int32_t *)d_donor_.p, pb.n_donor_labels,
                     pb.gridweight_max_cutoff, K, pb.mode, nb, W, (const double *)cs.etab.p, pb.mode == 3 ? 8.0 : 10.0, d_sorted,
                     total_chunks, (const Chunk **)cs.chunk_ptr.p + p0, (const double2 **)cs.ps_ptr.p + p0,
                     (const int32_t **)cs.pop_ptr.p + p0, (int32_t *)cs.t.p + (size_t)p0 * nb, (int32_t *)cs.first.p + (size_t)p0 * nb,
                     (int32_t *)cs.yoff.p + (size_t)p0 * nb * W, (long long *)cs.rowoff.p + (size_t)p0 * (nb + 1), d_cnt, d_rf,
-                    (int *)d_err_.p, d_tot, sp, (int32_t *)cs.yoff4.p + (size_t)p0 * nb * W,
-                    (long long *)cs.rowoff4.p + (size_t)p0 * (nb + 1), d_tot + np);
+                    (int *)d_err_.p, d_tot, sp);
     launches_ += 2;
-    CK(cudaMemcpyAsync(pin_tot_, d_tot, 2 * (size_t)np * sizeof(long long), cudaMemcpyDeviceToHost, sp));
+    CK(cudaMemcpyAsync(cs.totals.data() + p0, d_tot, np * sizeof(long long), cudaMemcpyDeviceToHost, sp));
     if (use_runs) CK(cudaMemcpyAsync(pin_small_ + 1, d_err_.p, sizeof(int), cudaMemcpyDeviceToHost, sp));
     vtick("  prep: emit + bin sort enqueued");
     CK(cudaStreamSynchronize(sp));
-    for (int q = 0; q < np; q++) { cs.totals[p0 + q] = pin_tot_[q]; cs.totals4[p0 + q] = pin_tot_[np + q]; }
-    stx.d2h_bytes += (int64_t)np * 16;
+    stx.d2h_bytes += (int64_t)np * 8;
     if (use_runs && (pin_small_[1] & kErrBadRuns)) return FGT_ERR_ARG;     // malformed runs: nothing is accumulated
     return FGT_OK;
 }
@@ -656,9 +648,7 @@ int Engine::setup_chromosome(const fgt_problem_t &pb, int h, ChromState &cs, fgt
         // same map and window as the previous call: the device tables are still valid (only the per-call state is reset)
         cs.n_chunks = 0;
         cs.totals.assign(n_phys, 0);
-        cs.totals4.assign(n_phys, 0);
         if (!cs.first.as<int32_t>((size_t)n_phys * cs.nb) || !cs.yoff.as<int32_t>((size_t)n_phys * cs.nb * W) ||
-            !cs.yoff4.as<int32_t>((size_t)n_phys * cs.nb * W) || !cs.rowoff4.as<long long>((size_t)n_phys * (cs.nb + 1)) ||
             !cs.rowoff.as<long long>((size_t)n_phys * (cs.nb + 1)) || !cs.chunk_ptr.as<const Chunk *>(n_phys) ||
             !cs.ps_ptr.as<const double2 *>(n_phys) || !cs.pop_ptr.as<const int32_t *>(n_phys))
             return FGT_ERR_CUDA;
@@ -690,11 +680,9 @@ int Engine::setup_chromosome(const fgt_problem_t &pb, int h, ChromState &cs, fgt
     if (!d_cum || !d_inc || !d_etab) return FGT_ERR_CUDA;
     if (!cs.t.as<int32_t>((size_t)n_phys * nb) || !cs.first.as<int32_t>((size_t)n_phys * nb) ||
         !cs.yoff.as<int32_t>((size_t)n_phys * nb * W) || !cs.rowoff.as<long long>((size_t)n_phys * (nb + 1)) ||
-        !cs.yoff4.as<int32_t>((size_t)n_phys * nb * W) || !cs.rowoff4.as<long long>((size_t)n_phys * (nb + 1)) ||
         !cs.chunk_ptr.as<const Chunk *>(n_phys) || !cs.ps_ptr.as<const double2 *>(n_phys) || !cs.pop_ptr.as<const int32_t *>(n_phys))
         return FGT_ERR_CUDA;
     cs.totals.assign(n_phys, 0);
-    cs.totals4.assign(n_phys, 0);
     // on their own stream: the prep stream may already be streaming labels through the chunk count
     CK(cudaMemcpyAsync(d_cum, cum, L * sizeof(double), cudaMemcpyHostToDevice, st_aux_));
     CK(cudaMemcpyAsync(d_inc, inc, L * sizeof(double), cudaMemcpyHostToDevice, st_aux_));
@@ -970,7 +958,7 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
             mem_budget_bytes_ = std::min((double)free_b * 0.6, 64e9);
         }
         const bool use_fused = fused_rng && impl != 1;
-        budget_pairs = (long long)(mem_budget_bytes_ / 2 / ((use_fused ? 0.0 : 8.0) + (relaxed ? 1.0 : 12.3 * ns_rec) + (row_blocks > 1 ? 12.3 : 0.0)));   // two lanes hold a batch each
+        budget_pairs = (long long)(mem_budget_bytes_ / 2 / ((use_fused ? 0.0 : 8.0) + (relaxed ? 1.0 : 16.0 * ns_rec) + (row_blocks > 1 ? 16.0 : 0.0)));   // two lanes hold a batch each
         budget_pairs = std::min<long long>(budget_pairs, 1900000000LL);      // (routed offsets are 32-bit)
     }
     tick("tables ready");
@@ -1048,7 +1036,7 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
         int n = n0;
         while (n < n1) {
             const int b0 = n;
-            long long lo = -1, hi = 0, acc_pairs = 0, acc_slots = 0;
+            long long lo = -1, hi = 0, acc_pairs = 0;
             std::vector<long long> abs_off, rel_off;
             while (n < n1) {
                 const long long c0 = cs.totals[used[h][n]];
@@ -1056,11 +1044,10 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
                 const long long a0 = pb.pair_offset ? pb.pair_offset[(size_t)h * N + n] : run;
                 run += c0; my_pairs += c0;
                 abs_off.push_back(a0);
-                rel_off.push_back(acc_slots);                    // records: padded slots, packed per batch
+                rel_off.push_back(acc_pairs);
                 lo = (lo < 0) ? a0 : std::min(lo, a0);
                 hi = std::max(hi, a0 + c0);
                 acc_pairs += c0;
-                acc_slots += cs.totals4[used[h][n]];
                 n++;
             }
             const int Nb = n - b0;
@@ -1072,13 +1059,13 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
             // fused generator: stream positions stay absolute (the kernel jumps there), records are packed per batch
             const long long A4 = fused ? 0 : ((2 * lo) & ~3LL);
             const long long nthreads = fused ? 0 : (2 * hi - A4 + kRun - 1) / kRun;
-            const long long rec_pairs = acc_slots;               // record slots per region slot (pairs padded to multiples of 4 per segment)
+            const long long rec_pairs = fused ? acc_pairs : nthreads * (long long)kRun / 2;
             long long *hp = pin_pairbase + (size_t)h * N + b0;
             long long *hr = pin_recbase + (size_t)h * N + b0;
             int32_t *hq = pin_physof + (size_t)h * N + b0;
             for (int m = 0; m < Nb; m++) {
                 hp[m] = abs_off[m] - A4 / 2;
-                hr[m] = rel_off[m];
+                hr[m] = fused ? rel_off[m] : hp[m];
                 hq[m] = used[h][b0 + m];
             }
             // ---- evaluation stream ----
@@ -1116,7 +1103,6 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
             cpd.ps_ptr = (const double2 *const *)cs.ps_ptr.p; cpd.pop_ptr = (const int32_t *const *)cs.pop_ptr.p;
             cpd.t = (const int32_t *)cs.t.p; cpd.first = (const int32_t *)cs.first.p;
             cpd.yoff = (const int32_t *)cs.yoff.p; cpd.rowoff = (const long long *)cs.rowoff.p;
-            cpd.yoff4 = (const int32_t *)cs.yoff4.p; cpd.rowoff4 = (const long long *)cs.rowoff4.p;
             const long long *pbase = d_pairbase + (size_t)h * N + b0;
             const long long *rbase = d_recbase + (size_t)h * N + b0;
             const int32_t *pphys = d_physof + (size_t)h * N + b0;
@@ -1141,10 +1127,10 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
             } else {
                 const size_t n_ent = (size_t)Nb * slabs.size() * (cs.nb - 1) * nd_max;
                 RegionEnt *d_regions = nullptr;
-                RecQuad *d_recs = nullptr;
+                UpdateRec *d_recs = nullptr;
                 if (!relaxed) {
                     d_regions = reg_buf.as<RegionEnt>(n_ent);
-                    d_recs = recs_buf.as<RecQuad>((size_t)(rec_pairs * plan.n_slots) / 4 + 8);
+                    d_recs = recs_buf.as<UpdateRec>((size_t)(rec_pairs + 2) * plan.n_slots);
                     if (!d_regions || !d_recs) return FGT_ERR_CUDA;
                 }
                 EvalArgs ea{};
@@ -1152,7 +1138,6 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
                 ea.hist0 = d_h0; ea.jump_tab = fused ? (const uint32_t *)d_jump_tab_.p : nullptr;
                 ea.pair_base = pbase; ea.rec_base = rbase; ea.phys_of = pphys;
                 ea.tensor = tens_b; ea.relaxed = relaxed ? 1 : 0; ea.accepted = d_acc;
-                ea.idx_is_cell = (tile_in_smem || row_blocks > 1) ? 0 : 1;
                 ea.N = Nb; ea.K = K; ea.G = G; ea.grid_start = pb.grid_start; ea.mode = pb.mode; ea.n_slots = plan.n_slots;
                 ea.bw = pb.binwidth; ea.half_bw = pb.binwidth / 2.0; ea.cutoff = pb.gridweight_max_cutoff;
                 {
@@ -1196,7 +1181,7 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
                         const int jch = std::max(1, (cs.nb - 1 + 31) / 32);
                         const size_t n_cnt = n_rt * jch;
                         int32_t *d_rcnt = d_rcnt_[bi].as<int32_t>(n_cnt + 1 + 2 * (n_cnt / 1024 + 2)), *d_roff = d_roff_[bi].as<int32_t>(n_cnt + 1);
-                        RecQuad *d_routed = d_routed_[bi].as<RecQuad>(((size_t)acc_pairs + 3 * n_cnt) / 4 + 8);
+                        UpdateRec *d_routed = d_routed_[bi].as<UpdateRec>((size_t)rec_pairs + 2);
                         RegionEnt *d_rdir = d_rdir_[bi].as<RegionEnt>(n_rt);
                         if (!d_rcnt || !d_roff || !d_routed || !d_rdir) return FGT_ERR_CUDA;
                         RouteArgs ra{};

@@ -23,8 +23,6 @@ struct DevBuf {
 
 struct ChromState {            // per chromosome device state that must outlive the prep pass
     DevBuf sorted, chunk_base, t, first, yoff, rowoff, cum, inc, etab, chunk_ptr, ps_ptr, pop_ptr;
-    DevBuf yoff4, rowoff4;                 // the sampling schedule's prefixes over counts padded to multiples of 4 (record regions)
-    std::vector<long long> totals4;        // [n_phys] padded record slots (per region slot) of each packed individual
     DevBuf run_src, run_rowoff, run_cnt;   // RLE paintings: per row first run / per block chunk offsets / runs per row
     // host copies of what the device tables above were built from: a repeat call with the same map / the same rows
     // (the R driver calls data_read ~100 times on one data set) skips the rebuild and the upload
@@ -122,8 +120,6 @@ class Engine {
     int part_Cn_ = 0, part_N_ = 0, part_S_ = 0, part_G_ = 0, part_mode_ = 0;
     bool part_valid_ = false;
     DevBuf d_msg_, d_msg_all_, d_streampos_;      // sharded calls: pair counts (local / gathered), running stream position
-    long long *pin_tot_ = nullptr;                // pinned: per-individual pair totals / padded record slots of a block
-    size_t pin_tot_cap_ = 0;
     double *pin_part_ = nullptr;                  // pinned: the all-reduced curves of a sharded call
     size_t pin_part_cap_ = 0;
     long long *pin_msg_ = nullptr;                // pinned: [n_max + 1] counts message, then the stream position read-back

@@ -479,8 +479,7 @@ k_bin_sort(int rows_per_ind, const int32_t *__restrict__ row_off, const double *
            double divisor, Chunk *__restrict__ sorted, long long n_sorted, const Chunk **__restrict__ chunk_ptr,
            const double2 **__restrict__ ps_ptr, const int32_t **__restrict__ pop_ptr, int32_t *__restrict__ t_out,
            int32_t *__restrict__ first_out, int32_t *__restrict__ yoff, long long *__restrict__ rowoff,
-           int32_t *__restrict__ cntmat, int32_t *__restrict__ runfirst, int *__restrict__ err, long long *__restrict__ totals,
-           int32_t *__restrict__ yoff4, long long *__restrict__ rowoff4, long long *__restrict__ totals4) {
+           int32_t *__restrict__ cntmat, int32_t *__restrict__ runfirst, int *__restrict__ err, long long *__restrict__ totals) {
     const int p = blockIdx.x;
     const int r0 = p * rows_per_ind;
     const int c0 = row_off[r0];
@@ -575,20 +574,13 @@ k_bin_sort(int rows_per_ind, const int32_t *__restrict__ row_off, const double *
     // phase 5: pairs per row of the (j,k) sampling schedule
     for (int j = threadIdx.x; j < nb; j += blockDim.x) {
         int32_t *yo = yoff + ((size_t)p * nb + j) * W;
-        int32_t *yo4 = yoff4 ? yoff4 + ((size_t)p * nb + j) * W : nullptr;
         int t1 = t[j];
-        int acc = 0, acc4 = 0;
+        int acc = 0;
         yo[0] = 0;
-        if (yo4) yo4[0] = 0;
         for (int d = 1; d < W; d++) {
             int k = j + d;
-            if (j < nb - 1 && k < nb) {
-                const int Y = pairs_to_sample(t1, t[k], Etab[d], divisor);
-                acc += Y;
-                acc4 += (Y + 3) & ~3;                     // record regions are multiples of four records (48-byte quads)
-            }
+            if (j < nb - 1 && k < nb) acc += pairs_to_sample(t1, t[k], Etab[d], divisor);
             yo[d] = acc;
-            if (yo4) yo4[d] = acc4;
         }
     }
     __syncthreads();
@@ -611,26 +603,6 @@ k_bin_sort(int rows_per_ind, const int32_t *__restrict__ row_off, const double *
             ro[nb] = carry;
             if (totals) totals[p] = carry;
         }
-        if (yoff4) {                                    // the same prefix over the padded counts
-            long long carry4 = 0;
-            long long *ro4 = rowoff4 + (size_t)p * (nb + 1);
-            for (int j0 = 0; j0 < nb; j0 += 32) {
-                const int j = j0 + (int)threadIdx.x;
-                const long long v = j < nb ? (long long)yoff4[((size_t)p * nb + j) * W + (W - 1)] : 0;
-                long long x = v;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const long long y = __shfl_up_sync(kFull, x, o);
-                    if ((int)threadIdx.x >= o) x += y;
-                }
-                if (j < nb) ro4[j] = carry4 + x - v;
-                carry4 += __shfl_sync(kFull, x, 31);
-            }
-            if (threadIdx.x == 0) {
-                ro4[nb] = carry4;
-                if (totals4) totals4[p] = carry4;
-            }
-        }
     }
 }
 
@@ -639,10 +611,10 @@ void launch_bin_sort(int n_phys, int rows_per_ind, const int32_t *row_off, const
                      int nb, int W, const double *Etab, double divisor, Chunk *sorted, long long n_sorted, const Chunk **chunk_ptr,
                      const double2 **ps_ptr, const int32_t **pop_ptr, int32_t *t,
                      int32_t *first, int32_t *yoff, long long *rowoff, int32_t *cntmat, int32_t *runfirst, int *err,
-                     long long *totals, cudaStream_t st, int32_t *yoff4, long long *rowoff4, long long *totals4) {
+                     long long *totals, cudaStream_t st) {
     k_bin_sort<<<n_phys, 1024, 0, st>>>(rows_per_ind, row_off, cstart, cend, chap, donor_label, n_donor_labels, cutoff, K,
                                       mode, nb, W, Etab, divisor, sorted, n_sorted, chunk_ptr, ps_ptr, pop_ptr, t, first, yoff, rowoff, cntmat,
-                                      runfirst, err, totals, yoff4, rowoff4, totals4);
+                                      runfirst, err, totals);
 }
 
 // =============================================================================================
@@ -1015,9 +987,7 @@ __global__ void __launch_bounds__(128, 8) k_eval_pairs(const EvalArgs a) {
     const int32_t *chpop = cp.pop_ptr[phys];
     const long long rowoff_j = cp.rowoff[(size_t)phys * (nb + 1) + j];
     const long long row_pair0 = a.pair_base[n] + rowoff_j;        // stream position (pairs) of the row's first draw
-    // the row's record regions: slot `ns * (padded pairs before the segment) + slot * Y4` of the launch's buffer (multiples of 4)
-    const long long row_rec0 = RELAXED ? 0 : (a.rec_base[n] + cp.rowoff4[(size_t)phys * (nb + 1) + j]) * a.n_slots;
-    const int32_t *yo4 = cp.yoff4 + ((size_t)phys * nb + j) * W;
+    UpdateRec *const row_recs = RELAXED ? nullptr : a.recs + (a.rec_base[n] + rowoff_j) * a.n_slots;   // the row's record regions
     const int f1 = F[j];
     const unsigned inv1 = mod_magic((unsigned)t1);
     const int ns = a.n_slots;
@@ -1068,9 +1038,7 @@ __global__ void __launch_bounds__(128, 8) k_eval_pairs(const EvalArgs a) {
         const int t2 = T[k], f2 = F[k];
         const unsigned inv2 = mod_magic((unsigned)t2);
         const long long seg = row_pair0 + y0;
-        const int y04 = RELAXED ? 0 : yo4[d - 1];
-        const int Y4 = RELAXED ? 0 : yo4[d] - y04;                  // slots per region: Y rounded up to a multiple of 4
-        const long long reg = row_rec0 + (long long)y04 * ns;       // first slot of the segment's regions
+        UpdateRec *reg = RELAXED ? nullptr : row_recs + (long long)y0 * ns;
         const int slab0 = a.first_slab[d];
         const BinRef binB{chps + f2, chpop + f2};
         int c[kMaxSlots] = {};
@@ -1120,10 +1088,9 @@ __global__ void __launch_bounds__(128, 8) k_eval_pairs(const EvalArgs a) {
                         }
                     }
                     if (e[h].slot >= 0) {
-                        const long long r = reg + (long long)e[h].slot * Y4 + pos;
-                        RecQuad *q = a.recs + (r >> 2);
-                        q->val[r & 3] = e[h].val;
-                        q->idx[r & 3] = a.idx_is_cell ? e[h].cell : e[h].local;
+                        UpdateRec rec;
+                        rec.cell = e[h].cell; rec.pad = e[h].local; rec.val = e[h].val;
+                        reg[(long long)e[h].slot * Y + pos] = rec;
                     }
                 }
             }
@@ -1133,12 +1100,10 @@ __global__ void __launch_bounds__(128, 8) k_eval_pairs(const EvalArgs a) {
 #pragma unroll
             for (int s = 1; s < kMaxSlots; s++) if (lane == s) v = c[s];
             const int slab = slab0 + lane;
-            const long long rbase = reg + (long long)lane * Y4;
-            for (int e2 = v; e2 < ((v + 3) & ~3); e2++) a.recs[(rbase + e2) >> 2].idx[(rbase + e2) & 3] = -1;   // unused slots of the last quad
             if (v > 0 && slab < a.n_slabs) {
                 // region directory of task (n, slab): entry (j, d - dlo(slab)); empty entries stay zero
                 RegionEnt ent;
-                ent.base = rbase;
+                ent.base = (long long)(reg - a.recs) + (long long)lane * Y;
                 ent.cnt = v; ent.pad = 0;
                 a.regions[(((size_t)n * a.n_slabs + slab) * (nb - 1) + j) * a.nd_max + (d - a.slabs[slab].dlo)] = ent;
             }
@@ -1224,8 +1189,8 @@ constexpr int kQueueBytes = kConsumers * (kQCap * 32 * (int)(sizeof(double) + si
 template <bool TILE_SMEM, bool BUCKETS>
 __global__ void __launch_bounds__(32 * (kConsumers + 1)) k_commit_ordered(const CommitArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    RecQuad *ring = reinterpret_cast<RecQuad *>(smem_raw);                             // [kStages][kStageRecs / 4] quads (4608 of the 6144 bytes)
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + 4608);
+    UpdateRec *ring = reinterpret_cast<UpdateRec *>(smem_raw);                         // [kStages][kStageRecs]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kStages * kStageRecs * sizeof(UpdateRec));
     uint64_t *empty = full + kStages;
     int *stage_cnt = reinterpret_cast<int *>(empty + kStages);                         // [kStages]
     int *task_slot = stage_cnt + kStages;                                              // [1] task broadcast
@@ -1299,15 +1264,15 @@ __global__ void __launch_bounds__(32 * (kConsumers + 1)) k_commit_ordered(const 
                         while (m) {
                             const int i = __ffs(m) - 1;
                             m &= m - 1;
-                            const int c = (dir[i].cnt + 3) & ~3;         // whole quads: the slots behind the region's last record hold index -1
-                            const RecQuad *src = a.recs + (dir[i].base >> 2);
+                            const int c = dir[i].cnt;
+                            const UpdateRec *src = a.recs + dir[i].base;
                             int off = 0;
-                            while (off < c) {              // stages are packed: a stage takes pieces (whole quads) of consecutive regions
+                            while (off < c) {              // stages are packed: a stage takes pieces of consecutive regions
                                 if (!open) { mbar_wait(&empty[stage], phase ^ 1); fence_proxy_async_smem(); open = true; fill = 0; }
                                 const int piece = min(c - off, kStageRecs - fill);
-                                const unsigned bytes = (unsigned)(piece >> 2) * (unsigned)sizeof(RecQuad);
+                                const unsigned bytes = (unsigned)piece * (unsigned)sizeof(UpdateRec);
                                 mbar_expect_tx(&full[stage], bytes);
-                                bulk_g2s(&ring[(stage * kStageRecs + fill) >> 2], src + (off >> 2), bytes, &full[stage]);
+                                bulk_g2s(&ring[stage * kStageRecs + fill], src + off, bytes, &full[stage]);
                                 fill += piece; off += piece;
                                 if (fill == kStageRecs) {
                                     stage_cnt[stage] = fill;
@@ -1341,7 +1306,7 @@ __global__ void __launch_bounds__(32 * (kConsumers + 1)) k_commit_ordered(const 
             // folded, so barrier / shared-memory latency overlaps the ordered read-modify-write work.
             // Several consumer warps read every stage; each handles only the cells it owns, so a cell's additions
             // stay in stream order.
-            struct Staged { int c, n; int cell[kStageSteps]; double val[kStageSteps]; unsigned g[kStageSteps]; };
+            struct Staged { int c; int cell[kStageSteps]; double val[kStageSteps]; unsigned g[kStageSteps]; };
             // ownership: BUCKETS -- alternate blocks of 32 tile cells (the low five bits pick the lane queue, so the 32
             // lanes of a fold pass hit 32 consecutive doubles: conflict free); otherwise odd / even cells
             auto owned = [&](int local) -> bool {
@@ -1353,17 +1318,14 @@ __global__ void __launch_bounds__(32 * (kConsumers + 1)) k_commit_ordered(const 
                 s.c = stage_cnt[stage];
 #pragma unroll
                 for (int h = 0; h < kStageSteps; h++) { s.cell[h] = -1; s.val[h] = 0.0; s.g[h] = 0; }
-                s.n = 0;
                 if (s.c >= 0) {
-                    const RecQuad *rg = ring + ((stage * kStageRecs) >> 2);
+                    const UpdateRec *rg = ring + stage * kStageRecs;
 #pragma unroll
-                    for (int h = 0; h < kStageSteps; h++) {
-                        const int slot = 32 * h + lane;
-                        int idx = -1;
-                        if (slot < s.c) idx = rg[slot >> 2].idx[slot & 3];
-                        if (32 * h < s.c) s.n += __popc(__ballot_sync(kFull, idx >= 0));
-                        if (idx >= 0 && owned(idx)) { s.cell[h] = idx; s.val[h] = rg[slot >> 2].val[slot & 3]; }
-                    }
+                    for (int h = 0; h < kStageSteps; h++)
+                        if (32 * h + lane < s.c) {
+                            const UpdateRec r = rg[32 * h + lane];
+                            if (owned(r.pad)) { s.cell[h] = TILE_SMEM ? r.pad : r.cell; s.val[h] = r.val; }
+                        }
                 }
                 // The refill of this stage is a TMA write (async proxy); the reads above are generic-proxy reads.
                 // Without the cross-proxy fence the bulk copy can land before these loads have sampled the
@@ -1429,7 +1391,7 @@ __global__ void __launch_bounds__(32 * (kConsumers + 1)) k_commit_ordered(const 
 #pragma unroll
                     for (int h = 0; h < kStageSteps; h++)
                         if (32 * h < cur.c) insert(cur.cell[h], cur.val[h]);
-                    if (wid == 0) n_acc += (unsigned long long)cur.n;
+                    if (wid == 0) n_acc += (unsigned long long)cur.c;
                     cur = nxt;
                 }
                 flush();
@@ -1454,7 +1416,7 @@ __global__ void __launch_bounds__(32 * (kConsumers + 1)) k_commit_ordered(const 
 #pragma unroll
                     for (int h = 0; h < kStageSteps; h++)
                         if (32 * h < cur.c) fold(cur.cell[h], cur.val[h], cur.g[h]);
-                    if (wid == 0) n_acc += (unsigned long long)cur.n;
+                    if (wid == 0) n_acc += (unsigned long long)cur.c;
                     cur = nxt;
                 }
             }
@@ -1477,7 +1439,7 @@ void launch_commit_ordered(const CommitArgs &a, int max_slab_width, cudaStream_t
     long long tasks = (long long)a.N * a.n_slabs * RB;
     if (tasks <= 0) return;
     const size_t ctrl_bytes = 6144 + 1024;
-    static_assert(kStages * (kStageRecs / 4) * sizeof(RecQuad) == 4608, "ring size");
+    static_assert(kStages * kStageRecs * sizeof(UpdateRec) == 6144, "ring size");
     const size_t tile_bytes = RB > 1 ? (size_t)a.rows_per_block * max_slab_width * sizeof(double) : commit_tile_bytes(a.K, max_slab_width);
     static bool attr_set[64] = {};                    // the attribute is per device (one engine per device)
     int dev = 0;
@@ -1550,14 +1512,10 @@ k_route(const RouteArgs a) {
             const int c = __shfl_sync(kFull, ent.cnt, i);
             for (int off = 0; off < c; off += 32) {
                 const bool v = off + lane < c;
-                int local = 0;
-                double val = 0.0;
-                if (v) {
-                    const long long r = base + off + lane;
-                    const RecQuad *q = a.recs + (r >> 2);
-                    local = q->idx[r & 3]; val = q->val[r & 3];
-                }
-                const unsigned row = sw_magic ? __umulhi((unsigned)local, sw_magic) : (unsigned)local;
+                UpdateRec r;
+                r.cell = 0; r.pad = 0; r.val = 0.0;
+                if (v) r = a.recs[base + off + lane];
+                const unsigned row = sw_magic ? __umulhi((unsigned)r.pad, sw_magic) : (unsigned)r.pad;
                 const unsigned rb = rpb_magic ? __umulhi(row, rpb_magic) : row;
                 if (!SCATTER) {
                     if (v) atomicAdd(&cnt[rb], 1);
@@ -1569,10 +1527,11 @@ k_route(const RouteArgs a) {
                     const int dst0 = __shfl_sync(kFull, my_off, v ? (int)rb : 0);
                     __syncwarp();
                     if (v) {
-                        const long long dst = (long long)dst0 + fill + rank;
-                        RecQuad *q = a.routed + (dst >> 2);
-                        q->val[dst & 3] = val;
-                        q->idx[dst & 3] = (int)(((unsigned)row - rb * (unsigned)a.rows_per_block) * (unsigned)sw + ((unsigned)local - row * (unsigned)sw));
+                        UpdateRec o;
+                        o.cell = r.cell;
+                        o.pad = (int)(((unsigned)row - rb * (unsigned)a.rows_per_block) * (unsigned)sw + ((unsigned)r.pad - row * (unsigned)sw));
+                        o.val = r.val;
+                        a.routed[(long long)dst0 + fill + rank] = o;
                         if ((m >> lane) == 1u) cnt[rb] = fill + rank + 1;
                     }
                     __syncwarp();
@@ -1581,15 +1540,7 @@ k_route(const RouteArgs a) {
         }
     }
     __syncwarp();
-    if (lane < RB) {
-        // every (row block, j chunk) piece of the routed buffer is a whole number of quads; unused slots hold index -1
-        if (!SCATTER) a.counts[(tbase + lane) * JC + jc] = (cnt[lane] + 3) & ~3;
-        else
-            for (int e2 = cnt[lane]; e2 < ((cnt[lane] + 3) & ~3); e2++) {
-                const long long dst = (long long)my_off + e2;
-                a.routed[dst >> 2].idx[dst & 3] = -1;
-            }
-    }
+    if (!SCATTER && lane < RB) a.counts[(tbase + lane) * JC + jc] = cnt[lane];
 }
 
 // one region per commit task (individual, slab, row block): the j chunks of a row block are adjacent in the routed buffer

@@ -36,8 +36,6 @@ struct ChromPrep {  // per chromosome, per call: everything the accumulation ker
     const int32_t *first;   // [n_phys][nb] exclusive prefix of t          (start_bin)
     const int32_t *yoff;    // [n_phys][nb][W]: yoff[..][d] = sum_{delta=1..d} Y(j, j+delta)
     const long long *rowoff; // [n_phys][nb+1] exclusive prefix over j of the row totals
-    const int32_t *yoff4;   // the same prefixes over Y rounded up to multiples of four: where the record regions of a segment lie
-    const long long *rowoff4;
 };
 
 struct AccumArgs {
@@ -58,12 +56,7 @@ struct AccumArgs {
 // Phase 1 evaluates every sampled pair once (no ordering constraint, full occupancy) and files the
 // accepted updates, in sequence order, into per-(segment, slab) record regions; phase 2 lets one warp
 // per (individual, slab) fold the records of its slab in the reference's order.
-// Update records travel in QUADS of 48 bytes: four values (fp64) followed by their four cell indices (int32).  A record costs
-// 12 bytes (the value and ONE index: the slab-tile index, or the tensor index when phase 2 folds into global memory), and every
-// TMA bulk copy of whole quads is a multiple of 16 bytes.  Record r of a buffer is element r & 3 of quad r >> 2; a region is a
-// whole number of quads and its unused trailing slots hold index -1.
-struct __align__(16) RecQuad { double val[4]; int32_t idx[4]; };
-static_assert(sizeof(RecQuad) == 48, "quad size");
+struct __align__(16) UpdateRec { int32_t cell; int32_t pad; double val; };   // cell: index in the individual's tensor; pad: index in the slab tile
 
 struct __align__(16) RegionEnt { long long base; int32_t cnt; int32_t pad; };   // one record region: first record, count
 
@@ -76,8 +69,7 @@ struct EvalArgs {
     const uint32_t *hist0;        // fused generator (rand_impl = 1): the 31-word glibc history at pair 0 of `pair_base` ...
     const uint32_t *jump_tab;     // ... and the jump table [level][digit][32] (NULL selects the bulk stream)
     const long long *pair_base;   // [N] stream position (in pairs) at which pseudo-individual n starts drawing
-    const long long *rec_base;    // [N] first record slot (in padded pairs, a multiple of 4) of n in this launch's record buffer
-    int32_t idx_is_cell;          // records carry the tensor index (global-memory commit) instead of the slab-tile index
+    const long long *rec_base;    // [N] first record slot (in pairs) of n in this launch's record buffer
     const int32_t *phys_of;       // [N]
     double *tensor;               // relaxed mode only: [N][K(K+1)/2][G], updated with fp64 atomics
     unsigned long long *accepted; // relaxed mode only (the commit kernel counts otherwise)
@@ -86,7 +78,7 @@ struct EvalArgs {
     double bw, half_bw, cutoff;
     double inv_bw;                // RN(1/bw), or 0 when the two-FMA division below is not provably exact for this bw
     const int32_t *first_slab;    // [W] first slab reachable from separation d
-    RecQuad *recs;                // segment (n,j,d) owns n_slots regions of Y4 = roundup4(Y) record slots each (yoff4 / rowoff4 / rec_base)
+    UpdateRec *recs;              // [(pairs) * n_slots]: segment (n,j,d) owns n_slots regions of Y records each
     RegionEnt *regions;           // [N*n_slabs][nb-1][nd_max] region directory, slab-major (zero = empty)
     const SlabDesc *slabs;
     int32_t n_slabs, nd_max;
@@ -102,8 +94,8 @@ struct CommitArgs {
     const int32_t *phys_of;
     int32_t N, K, G, grid_start, n_slots, n_slabs;
     const SlabDesc *slabs;        // dlo/dhi = separations whose reach includes the slab
-    const RecQuad *recs;
-    const RegionEnt *regions;     // base: first record slot of the region (a multiple of 4), cnt: records in it
+    const UpdateRec *recs;
+    const RegionEnt *regions;
     int32_t nd_max, tensor_is_zero;
     int32_t buckets;              // 1: lane-queue fold (no match.any) for shared-memory tiles; 0: match.any fold
     int32_t row_blocks;           // > 1: tasks are (individual, slab, block of rows_per_block tensor rows) over ROUTED records:
@@ -113,14 +105,14 @@ struct CommitArgs {
     int *task_counter;            // zeroed before the launch: persistent CTAs claim (individual, slab) tasks from it
 };
 struct RouteArgs {               // large K: split every (individual, slab) record stream by block of tensor rows (k_route)
-    const RecQuad *recs;          // phase-1 records ...
+    const UpdateRec *recs;        // phase-1 records ...
     const RegionEnt *regions;     // ... and their directory [N*n_slabs][nb-1][nd_max]
     const SlabDesc *slabs;
     int32_t N, n_slabs, nb, nd_max, row_blocks, rows_per_block;
     int32_t j_chunks;             // ceil((nb-1) / 32): routing tasks per (individual, slab)
     int32_t *counts;              // [N*n_slabs*row_blocks*j_chunks] records per (task, row block) (counting pass)
     const int32_t *offs;          // [... + 1] exclusive scan of counts (scatter pass)
-    RecQuad *routed;              // records in (individual, slab, row block) order, tile index relative to the row block
+    UpdateRec *routed;            // records in (individual, slab, row block) order, tile index relative to the row block
     RegionEnt *routed_dir;        // [N*n_slabs*row_blocks] one region per task
 };
 void launch_route(const RouteArgs &a, bool scatter, cudaStream_t st);
@@ -151,8 +143,7 @@ void launch_bin_sort(int n_phys, int rows_per_ind, const int32_t *row_off, const
                      int nb, int W, const double *Etab, double divisor, Chunk *sorted, long long n_sorted, const Chunk **chunk_ptr,
                      const double2 **ps_ptr, const int32_t **pop_ptr, int32_t *t,
                      int32_t *first, int32_t *yoff, long long *rowoff, int32_t *cntmat, int32_t *runfirst, int *err,
-                     long long *totals, cudaStream_t st, int32_t *yoff4 = nullptr, long long *rowoff4 = nullptr,
-                     long long *totals4 = nullptr);
+                     long long *totals, cudaStream_t st);
 void launch_rand_fill(const uint32_t *base_hist, const uint32_t *level_tab, uint32_t *out, long long n_threads,
                       cudaStream_t st, long long first_thread = 0);
 void launch_accum_strict(const AccumArgs &a, cudaStream_t st);
