@@ -83,6 +83,9 @@ int Engine::set_option(const char *key, double v) {
     else if (k == "accum_impl") opt.accum_impl = iv;
     else if (k == "spec_rand") opt.spec_rand = iv;
     else if (k == "null_target") opt.null_target = iv;
+    else if (k == "null_impl") opt.null_impl = iv;
+    else if (k == "null_batch") opt.null_batch = v;
+    else if (k == "null_tasks") opt.null_tasks = iv;
     else if (k == "null_world") opt.null_world = std::max(1, iv);
     else if (k == "null_rank") opt.null_rank = std::max(0, iv);
     else if (k == "project_impl") opt.project_impl = iv;
@@ -116,6 +119,9 @@ double Engine::get_option(const char *key) {
     if (k == "reuse_prep") return opt.reuse_prep;
     if (k == "accum_impl") return opt.accum_impl;
     if (k == "spec_rand") return opt.spec_rand;
+    if (k == "null_impl") return opt.null_impl;
+    if (k == "null_batch") return opt.null_batch;
+    if (k == "null_tasks") return opt.null_tasks;
     if (k == "null_world") return opt.null_world;
     if (k == "null_rank") return opt.null_rank;
     if (k == "project_impl") return opt.project_impl;
@@ -1797,6 +1803,186 @@ int Engine::data_read_null_multi(const fgt_problem_t &pb, const int32_t *rec_row
     return FGT_OK;
 }
 
+// Who folds label pair (la, lb) in a sharded NULL run.  The owner of a cell must not change between chromosomes (its additions
+// would be re-associated).  Two-phase path: whole rows of A labels (the evaluation work is split as well); k_null_strict: label pairs.
+static inline bool null_owner(bool two_phase, int la, int lb, int world, int rank) {
+    if (world <= 1) return true;
+    return two_phase ? (la % world == rank) : ((la * 31 + lb * 17) % world == rank);
+}
+
+// Two-phase NULL accumulation of one chromosome (kernels.cu, "NULL path, two phases"): plan the commit tasks from the per-haplotype
+// label counts, then per batch of haplotype pairs: count, scan, scatter, ordered commit.
+int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::vector<int32_t> &laboff, int Nc, int null_world, int null_rank,
+                           double *d_out, unsigned long long *d_acc, fgt_stats_t &stx) {
+    const int K = pb.num_donors, G = pb.num_bins, P = pb.ploidy, NH = Nc * P;
+    auto cl = [&](int hp, int l) { return (long long)(laboff[(size_t)hp * (K + 2) + l + 1] - laboff[(size_t)hp * (K + 2) + l]); };
+    std::vector<int32_t> own;
+    for (int la = 0; la < K; la++) if (null_owner(true, la, 0, null_world, null_rank)) own.push_back(la);
+    if (own.empty()) return FGT_OK;
+    // evaluated chunk pairs per label pair: sum over haplotypes A of c[A][la] * (chunks labelled lb in the haplotypes of later individuals)
+    std::vector<long long> suffix((size_t)(Nc + 1) * K, 0);
+    for (int n = Nc - 1; n >= 0; n--)
+        for (int l = 0; l < K; l++) {
+            long long c = suffix[(size_t)(n + 1) * K + l];
+            for (int p = 0; p < P; p++) c += cl(n * P + p, l);
+            suffix[(size_t)n * K + l] = c;
+        }
+    std::vector<double> est((size_t)K * K, 0.0);
+    double total_est = 0;
+    for (int la : own)
+        for (int hA = 0; hA < (Nc - 1) * P; hA++) {
+            const long long ca = cl(hA, la);
+            if (!ca) continue;
+            const long long *sf = &suffix[(size_t)(hA / P + 1) * K];
+            for (int lb = 0; lb < K; lb++) est[(size_t)la * K + lb] += (double)ca * (double)sf[lb];
+        }
+    for (double e : est) total_est += e;
+    if (total_est <= 0) return FGT_OK;
+    {   // the warps of a CTA claim the A labels of a haplotype pair heaviest first
+        std::vector<double> row_est(K, 0.0);
+        for (int la : own) for (int lb = 0; lb < K; lb++) row_est[la] += est[(size_t)la * K + lb];
+        std::stable_sort(own.begin(), own.end(), [&](int x, int y) { return row_est[x] > row_est[y]; });
+    }
+    // bin ranges per label pair: hot pairs are cut into up to 32 ranges so that no commit task is much heavier than the rest
+    const int want_tasks = opt.null_tasks > 0 ? opt.null_tasks : 4096;
+    int rmax = std::min(32, G);
+    std::vector<NullPairPlan> plan((size_t)K * K);
+    std::vector<NullRowPlan> rows(K);
+    std::vector<int32_t> perm;
+    std::vector<CommitTile> tab;
+    int n_tasks = 0, max_tb = 1, max_w = 1;
+    for (int attempt = 0; attempt < 8; attempt++) {
+        const double target = std::max(total_est / want_tasks, 1.0);
+        n_tasks = 0; max_tb = 1; max_w = 1;
+        struct Cost { double c; int32_t nat; CommitTile t; };
+        std::vector<Cost> tl;
+        for (int la = 0; la < K; la++) {
+            rows[la].task0 = n_tasks; rows[la].ntb = 0;
+            const bool mine = null_owner(true, la, 0, null_world, null_rank);
+            for (int lb = 0; lb < K; lb++) {
+                NullPairPlan &pp = plan[(size_t)la * K + lb];
+                pp.tb0 = rows[la].ntb; pp.w = G; pp.magic = G > 1 ? (uint32_t)((0x100000000ULL + G - 1) / G) : 0u; pp.pad = 0;
+                if (!mine) continue;
+                const double e = est[(size_t)la * K + lb];
+                int R = (int)std::ceil(e / target);
+                R = std::max(1, std::min(R, rmax));
+                const int w = (G + R - 1) / R;
+                const int nr = (G + w - 1) / w;
+                pp.w = w; pp.magic = w > 1 ? (uint32_t)((0x100000000ULL + w - 1) / w) : 0u;
+                max_w = std::max(max_w, w);
+                for (int r = 0; r < nr; r++) {
+                    CommitTile t{la * K + lb, 1, r * w, std::min(w, G - r * w)};
+                    tl.push_back({e / nr, n_tasks + rows[la].ntb + r, t});
+                }
+                rows[la].ntb += nr;
+            }
+            n_tasks += rows[la].ntb;
+            max_tb = std::max(max_tb, rows[la].ntb);
+        }
+        if (max_tb <= 4096) {
+            std::stable_sort(tl.begin(), tl.end(), [](const Cost &x, const Cost &y) { return x.c > y.c; });
+            perm.resize(tl.size()); tab.resize(tl.size());
+            for (size_t q = 0; q < tl.size(); q++) { perm[q] = tl[q].nat; tab[q] = tl[q].t; }
+            break;
+        }
+        rmax = std::max(1, rmax / 2);
+    }
+    if (max_tb > 4096 || n_tasks <= 0) return FGT_ERR_ARG;
+    // haplotype pairs in the reference's order, with an upper bound of the records each can produce
+    std::vector<int2> tiles;
+    std::vector<long long> bound;
+    std::vector<long long> ownA(NH, 0), nlab(NH, 0);
+    for (int hp = 0; hp < NH; hp++) {
+        nlab[hp] = laboff[(size_t)hp * (K + 2) + K];
+        for (int la : own) ownA[hp] += cl(hp, la);
+    }
+    for (int hA = 0; hA < (Nc - 1) * P; hA++)
+        for (int hB = (hA / P + 1) * P; hB < NH; hB++)
+            if (ownA[hA] > 0 && nlab[hB] > 0) { tiles.push_back(make_int2(hA, hB)); bound.push_back(ownA[hA] * nlab[hB]); }
+    if (tiles.empty()) return FGT_OK;
+    // batch size: records of a batch are addressed with 32 bits; the buffer takes a share of the free memory
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    free_b += d_recs_.cap + d_ncnt_.cap + d_noff_.cap;
+    long long batch_evals = opt.null_batch > 0 ? (long long)opt.null_batch : (long long)std::min(1.5e9, (double)free_b * 0.5 / sizeof(UpdateRec));
+    long long max_bound = 0;
+    for (long long b : bound) max_bound = std::max(max_bound, b);
+    batch_evals = std::max(batch_evals, max_bound);
+    if (batch_evals >= (1LL << 31) - 64) return FGT_ERR_ARG;
+    const long long max_tiles = std::max<long long>(1, 100000000LL / n_tasks);     // count / offset tables of at most 400 MB each
+    // device tables
+    int2 *d_tiles = d_ntiles_.as<int2>(tiles.size());
+    int32_t *d_own = d_nown_.as<int32_t>(own.size());
+    NullPairPlan *d_plan = d_nplan_.as<NullPairPlan>(plan.size());
+    NullRowPlan *d_rows = d_nrows_.as<NullRowPlan>(rows.size());
+    int32_t *d_perm = d_nperm_.as<int32_t>(perm.size());
+    CommitTile *d_tab = d_ntab_.as<CommitTile>(tab.size());
+    RegionEnt *d_dir = d_ndir_.as<RegionEnt>(tab.size());
+    int *d_ctr = d_taskctr_.as<int>(1024);
+    if (!d_tiles || !d_own || !d_plan || !d_rows || !d_perm || !d_tab || !d_dir || !d_ctr) return FGT_ERR_CUDA;
+    CK(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, st_));
+    CK(cudaMemcpyAsync(d_own, own.data(), own.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
+    CK(cudaMemcpyAsync(d_plan, plan.data(), plan.size() * sizeof(NullPairPlan), cudaMemcpyHostToDevice, st_));
+    CK(cudaMemcpyAsync(d_rows, rows.data(), rows.size() * sizeof(NullRowPlan), cudaMemcpyHostToDevice, st_));
+    CK(cudaMemcpyAsync(d_perm, perm.data(), perm.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
+    CK(cudaMemcpyAsync(d_tab, tab.data(), tab.size() * sizeof(CommitTile), cudaMemcpyHostToDevice, st_));
+    NullEvalArgs ea{};
+    ea.chunks = (const Chunk *)cs.sorted.p; ea.hap_base = (const int32_t *)cs.chunk_base.p; ea.lab_off = (const int32_t *)cs.yoff.p;
+    ea.own = d_own; ea.n_own = (int)own.size();
+    ea.K = K; ea.G = G; ea.grid_start = pb.grid_start;
+    ea.bw = pb.binwidth; ea.half_bw = pb.binwidth / 2.0;
+    {
+        uint64_t bits;
+        std::memcpy(&bits, &pb.binwidth, sizeof bits);
+        const bool all_ones = (bits & 0xFFFFFFFFFFFFFULL) == 0xFFFFFFFFFFFFFULL;
+        const bool normal = std::isnormal(pb.binwidth) && pb.binwidth > 1e-100 && pb.binwidth < 1e100;
+        ea.inv_bw = (!all_ones && normal) ? 1.0 / pb.binwidth : 0.0;
+    }
+    ea.plan = d_plan; ea.rows = d_rows; ea.max_tb = max_tb; ea.n_tasks = n_tasks;
+    long long most = 1;
+    for (long long c : nlab) most = std::max(most, c);
+    ea.stage_cap = null_stage_cap((int)std::min<long long>(most, 1 << 20));
+    if (null_eval_smem(K, max_tb, ea.stage_cap) > 200 * 1024) ea.stage_cap = 0;          // many labels: B is read through L1 instead
+    if (null_eval_smem(K, max_tb, ea.stage_cap) > 200 * 1024) return FGT_ERR_ARG;
+    ea.tile_counter = d_ctr + 1;
+    size_t t0 = 0;
+    while (t0 < tiles.size()) {
+        size_t t1 = t0;
+        long long sum = 0;
+        while (t1 < tiles.size() && (t1 == t0 || (sum + bound[t1] <= batch_evals && (long long)(t1 - t0) < max_tiles))) sum += bound[t1++];
+        const long long T = (long long)(t1 - t0);
+        const long long n_cnt = (long long)n_tasks * T;
+        int32_t *d_cnt = d_ncnt_.as<int32_t>((size_t)n_cnt + 1 + 2 * ((size_t)n_cnt / 1024 + 2));
+        int32_t *d_off = d_noff_.as<int32_t>((size_t)n_cnt + 1);
+        UpdateRec *d_recs = d_recs_.as<UpdateRec>((size_t)sum + 2);
+        if (!d_cnt || !d_off || !d_recs) return FGT_ERR_CUDA;
+        ea.tiles = d_tiles + t0; ea.n_tiles = (int)T;
+        ea.la_groups = (int)std::max<long long>(1, std::min<long long>((long long)own.size(), (148 * 8 + T - 1) / T));
+        ea.recs = d_recs;
+        // counts per (tile, task) -> [task][tile] -> exclusive scan = first record of every (task, tile) -> back to [tile][task]
+        CK(cudaMemsetAsync(d_ctr, 0, 4 * sizeof(int), st_));
+        ea.counts = d_cnt; ea.offs = nullptr;
+        launch_null_eval(ea, false, st_);
+        launch_transpose_i32(d_cnt, T, n_tasks, d_off, st_);
+        launch_exclusive_scan_i32_large(d_off, d_cnt, n_cnt, d_cnt + n_cnt + 1, st_);
+        launch_transpose_i32(d_cnt, n_tasks, T, d_off, st_);
+        CK(cudaMemsetAsync(d_ctr + 1, 0, sizeof(int), st_));
+        ea.counts = nullptr; ea.offs = d_off;
+        launch_null_eval(ea, true, st_);
+        launch_null_dir(d_cnt, d_perm, n_tasks, T, d_dir, st_);
+        CommitArgs ca{};
+        ca.N = 1; ca.K = K; ca.G = G; ca.grid_start = pb.grid_start;
+        ca.recs = d_recs; ca.regions = d_dir; ca.tensor_is_zero = 0; ca.buckets = 0;
+        ca.tensor = d_out; ca.accepted = d_acc; ca.task_counter = d_ctr;
+        ca.task_tab = d_tab; ca.n_task_tab = n_tasks; ca.max_tile_cells = max_w;
+        launch_commit_ordered(ca, max_w, st_);
+        launches_ += 10;
+        stx.accum_launches += 1;
+        t0 = t1;
+    }
+    return FGT_OK;
+}
+
 int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_rows, double *out, fgt_stats_t *stats, int shard_world,
                                   int shard_rank) {
     const int null_world = shard_world > 0 ? shard_world : opt.null_world, null_rank = shard_world > 0 ? shard_rank : opt.null_rank;
@@ -1833,6 +2019,12 @@ int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_ro
     CK(cudaMemcpyAsync(d_rowmap, rowmap.data(), n_haps * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
     double *d_out = d_tensor_.as<double>((size_t)K * K * G);
     if (!d_out) return FGT_ERR_CUDA;
+    // null_impl: 2 = two phases (every chunk pair evaluated once), 1 = k_null_strict (windowed enumeration per task), 0 = choose per
+    // call.  Measured on B200 (profiles/r2_null.md): the two-phase path wins up to K ~ 50 (tutorial, K = 26: 3.5x; K = 30: 1.7x, 7x on a
+    // 400k-SNP chromosome; K = 50: 1.3x), the windowed kernel from K ~ 100 on (its K*K*slabs tasks fill the GPU and it skips the
+    // pairs outside the distance window; the two-phase path pays per batch for K*K commit tasks)
+    bool two_phase = opt.null_impl == 2 && K <= 4096 && G < 65536;
+    if (opt.null_impl == 0 && G < 65536) two_phase = K <= 64;
     std::vector<double> own_init;
     const double *init_src = out;
     if (null_world > 1) {
@@ -1841,7 +2033,7 @@ int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_ro
         own_init.assign(out, out + (size_t)K * K * G);
         for (int la = 0; la < K; la++)
             for (int lb = 0; lb < K; lb++)
-                if ((la * 31 + lb * 17) % null_world != null_rank)
+                if (!null_owner(two_phase, la, lb, null_world, null_rank))
                     std::fill(own_init.begin() + ((size_t)la * K + lb) * G, own_init.begin() + ((size_t)la * K + lb + 1) * G, 0.0);
         init_src = own_init.data();
     }
@@ -1864,6 +2056,10 @@ int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_ro
             std::vector<int32_t> laboff((size_t)n_haps * (K + 2));
             CK(cudaMemcpyAsync(laboff.data(), cs.yoff.p, laboff.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st_));
             CK(cudaStreamSynchronize(st_));
+            if (two_phase) {
+                rc = null_two_phase(pb, cs, laboff, Nc, null_world, null_rank, d_out, d_acc, stx);
+                if (rc) return rc;
+            } else {
             std::vector<double> cnt_mean(K, 0.0);
             for (int hp = 0; hp < n_haps; hp++)
                 for (int l = 0; l < K; l++) cnt_mean[l] += (double)(laboff[(size_t)hp * (K + 2) + l + 1] - laboff[(size_t)hp * (K + 2) + l]) / n_haps;
@@ -1877,7 +2073,7 @@ int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_ro
                     // sharded NULL run: a rank folds the label pairs it owns, on every chromosome (the owner of a cell must
                     // not change between chromosomes, or its additions would be re-associated); the ranks' outputs have
                     // disjoint supports, so their sum is exact
-                    if (null_world > 1 && (la * 31 + lb * 17) % null_world != null_rank) continue;
+                    if (null_world > 1 && !null_owner(false, la, lb, null_world, null_rank)) continue;
                     const double scan = ca * std::ceil(std::max(cb, 1.0) / 32.0);          // steps per haplotype pair
                     const double recs = ca * cb * 0.7;                                      // accepted pairs per haplotype pair
                     int ns = opt.null_slab_bins > 0 ? (G + opt.null_slab_bins - 1) / opt.null_slab_bins
@@ -1900,6 +2096,7 @@ int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_ro
             launch_null_strict(a, st_);
             launches_ += 1;
             stx.accum_launches += 1;
+            }
             // evaluated pairs (reference loop count): sum over hap pairs of |A|*|B|
             std::vector<int32_t> ro(n_haps + 1);
             CK(cudaMemcpyAsync(ro.data(), cs.chunk_base.p, (n_haps + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st_));

@@ -54,6 +54,10 @@ struct Options {
     int copy_streams = 1;   // 2 = alternate the label block copies between two streams (two DMA engines)
     int project_impl = 0;   // 0 = exact (separately rounded multiply and add, bit-identical curves); 1 = FP64 tensor cores (~1e-14)
     int null_target = 0;    // NULL task table: accepted pairs per (haplotype pair, slab) a task aims at; 0 = default
+    int null_impl = 0;      // NULL path: 2 = two phases (every chunk pair evaluated once into records, ordered commit), 1 = k_null_strict,
+                            // 0 = two phases up to 64 donor groups, k_null_strict above
+    double null_batch = 0;  // null_impl 2: chunk-pair evaluations per batch of haplotype pairs (0 = from free device memory)
+    int null_tasks = 0;     // null_impl 2: commit tasks aimed at (0 = default)
     int null_world = 1, null_rank = 0;   // sharded NULL run: this rank folds the label pairs it owns (sum of the ranks = exact)
     int spec_rand = 1;      // generate the first batch's draws while the chunk/bin kernels run
     int accum_impl = 2;     // 2 = two-phase (evaluate once, ordered commit); 1 = single-phase slab warps
@@ -160,6 +164,9 @@ class Engine {
         d_ratio_, d_means_, d_raw_, d_totals_, d_recs_, d_cnt_, d_draws2_, d_recs2_, d_cnt2_, d_taskctr_, d_firstslab_;
     std::vector<ChromState> chroms_;
     ChromState null_cs_;              // NULL path: chunk buffers of the chromosome being folded
+    DevBuf d_ntiles_, d_nown_, d_nplan_, d_nrows_, d_nperm_, d_ntab_, d_ncnt_, d_noff_, d_ndir_;   // two-phase NULL path
+    int null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::vector<int32_t> &laboff, int Nc, int null_world, int null_rank,
+                       double *d_out, unsigned long long *d_acc, fgt_stats_t &stx);
     std::vector<double> raw_host_;
     int64_t raw_count_ = 0;
     int launches_ = 0;

@@ -1202,7 +1202,8 @@ __global__ void __launch_bounds__(32 * (kConsumers + 1)) k_commit_ordered(const 
     const int G = a.G;
     const int P = a.K * (a.K + 1) / 2;
     const int RB = a.row_blocks > 0 ? a.row_blocks : 1;      // row blocks per slab tile (large K: records routed per block first)
-    const int total_tasks = a.N * a.n_slabs * RB;
+    const bool tabbed = a.task_tab != nullptr;               // explicit task table (NULL path): one tile and one record region per entry
+    const int total_tasks = tabbed ? a.n_task_tab : a.N * a.n_slabs * RB;
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], kConsumers); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -1221,15 +1222,21 @@ __global__ void __launch_bounds__(32 * (kConsumers + 1)) k_commit_ordered(const 
         __syncthreads();
         const int task = *task_slot;
         if (task >= total_tasks) break;
-        const int sr = task / a.N;                          // (slab, row block), heavy slabs first
-        const int n = task - sr * a.N;
-        const int slab_i = sr / RB, rb = sr - slab_i * RB;
-        const SlabDesc sl = a.slabs[slab_i];
-        const int row0 = RB > 1 ? rb * a.rows_per_block : 0;                   // the tile holds tensor rows [row0, row0 + rows)
-        const int rows = RB > 1 ? min(a.rows_per_block, P - row0) : P;
+        int n = 0, slab_i = 0, rb = 0, row0, rows, sbw, boff;
+        if (tabbed) {
+            const CommitTile td = a.task_tab[task];         // heavy tasks first (host order)
+            row0 = td.row0; rows = td.rows; sbw = td.bins; boff = td.b0;
+        } else {
+            const int sr = task / a.N;                      // (slab, row block), heavy slabs first
+            n = task - sr * a.N;
+            slab_i = sr / RB; rb = sr - slab_i * RB;
+            const SlabDesc sl = a.slabs[slab_i];
+            row0 = RB > 1 ? rb * a.rows_per_block : 0;      // the tile holds tensor rows [row0, row0 + rows)
+            rows = RB > 1 ? min(a.rows_per_block, P - row0) : P;
+            sbw = sl.b1 - sl.b0 + 1;
+            boff = sl.b0 - a.grid_start;
+        }
         double *tens = a.tensor + (size_t)n * (size_t)P * G + (size_t)row0 * G;
-        const int sbw = sl.b1 - sl.b0 + 1;
-        const int boff = sl.b0 - a.grid_start;
         if (TILE_SMEM) {
             if (a.tensor_is_zero) {
                 for (int idx = threadIdx.x; idx < rows * sbw; idx += blockDim.x) tile[idx] = 0.0;
@@ -1245,8 +1252,8 @@ __global__ void __launch_bounds__(32 * (kConsumers + 1)) k_commit_ordered(const 
         if (wid == kConsumers) {
             // ------------------------------ producer ------------------------------
             // routed records (row blocks): one contiguous region per task; otherwise the slab's (j, d) region directory
-            const long long n_ent = RB > 1 ? 1 : (long long)(a.cp.nb - 1) * a.nd_max;
-            const RegionEnt *ents = a.regions + (((size_t)n * a.n_slabs + slab_i) * RB + rb) * n_ent;
+            const long long n_ent = (RB > 1 || tabbed) ? 1 : (long long)(a.cp.nb - 1) * a.nd_max;
+            const RegionEnt *ents = tabbed ? a.regions + task : a.regions + (((size_t)n * a.n_slabs + slab_i) * RB + rb) * n_ent;
             RegionEnt cur, nxt;
             cur.base = 0; cur.cnt = 0; cur.pad = 0;
             if (lane < n_ent) cur = ents[lane];
@@ -1436,11 +1443,12 @@ size_t commit_tile_bytes(int K, int slab_width) { return (size_t)K * (K + 1) / 2
 
 void launch_commit_ordered(const CommitArgs &a, int max_slab_width, cudaStream_t st) {
     const int RB = a.row_blocks > 0 ? a.row_blocks : 1;
-    long long tasks = (long long)a.N * a.n_slabs * RB;
+    long long tasks = a.task_tab ? (long long)a.n_task_tab : (long long)a.N * a.n_slabs * RB;
     if (tasks <= 0) return;
     const size_t ctrl_bytes = 6144 + 1024;
     static_assert(kStages * kStageRecs * sizeof(UpdateRec) == 6144, "ring size");
-    const size_t tile_bytes = RB > 1 ? (size_t)a.rows_per_block * max_slab_width * sizeof(double) : commit_tile_bytes(a.K, max_slab_width);
+    const size_t tile_bytes = a.task_tab ? (size_t)a.max_tile_cells * sizeof(double)
+                              : RB > 1 ? (size_t)a.rows_per_block * max_slab_width * sizeof(double) : commit_tile_bytes(a.K, max_slab_width);
     static bool attr_set[64] = {};                    // the attribute is per device (one engine per device)
     int dev = 0;
     cudaGetDevice(&dev);
@@ -2251,6 +2259,236 @@ void launch_null_strict(const NullArgs &a, cudaStream_t st) {
     cudaGetDevice(&dev);
     if (!attr_set[dev & 63]) { cudaFuncSetAttribute(k_null_strict, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set[dev & 63] = true; }
     k_null_strict<<<(unsigned)((tasks + wpb - 1) / wpb), wpb * 32, smem, st>>>(a);
+}
+
+// ---- NULL path, two phases (null_impl = 2) ------------------------------------------------------------------------
+// Phase 1 evaluates every chunk pair of every haplotype pair exactly ONCE (k_null_strict lets every (label pair, slab)
+// task re-walk all haplotype pairs) and files the accepted updates as 16-byte records; phase 2 is k_commit_ordered over
+// an explicit task table: task = (label of A, label of B, range of fine bins) = a few hundred cells in shared memory, one
+// contiguous record region per task.
+//
+// Order.  The reference adds in (n, p, g, m, i, j) order; only the relative order of the additions into ONE cell matters.
+// A work item is (haplotype pair "tile", label of A): one warp walks the A chunks with that label in order and, per A
+// chunk, the B chunks in label-grouped order (k_null_group is stable, so within a label of B that is the reference's j
+// order).  Records of a task are laid out tile-major (tiles in (n, p, g, m) order), inside a tile in the warp's (i, j)
+// order: every cell sees its addends in the reference's order.
+//
+// Positions.  A counting pass (same evaluation, shared-memory counters) fills counts[task][tile]; one exclusive scan
+// turns that into every (task, tile) region's first record, and a task's tiles are adjacent, so phase 2 needs one
+// RegionEnt per task.  The scatter pass ranks the accepted pairs of a 32-pair step without match.any (two cycles per distinct
+// key on the SM's single unit): B is grouped by label, so the task numbers met in one step lie close together and the
+// lanes of one task are found with one ballot per bit of (task - smallest task of the step).
+struct NullStep { unsigned key; int cell, local; double val; };   // key = bin range of the lane's pair inside its label pair, ~0u = rejected
+
+constexpr int kNullWarps = 4;          // warps per CTA of k_null_eval (few: the CTA waits for its slowest warp before the next haplotype pair)
+constexpr int kNullStageB = 2048;      // most chunks of B staged in shared memory (32 bytes each); longer haplotypes are read from global memory
+constexpr int kNullMaxRanges = 64;     // most bin ranges of one label pair (shared-memory counters per warp)
+
+__device__ __forceinline__ NullStep null_eval_pair(const NullEvalArgs &a, const Chunk &A, double posB, double halfB, double wB, int cell0,
+                                                    unsigned magic, int w, bool valid) {
+    NullStep o;
+    o.key = ~0u; o.cell = -1; o.local = 0; o.val = 0.0;
+    if (!valid) return o;
+    const double dist = fabs(__dsub_rn(A.pos, posB));                       // reference C:1015
+    double qd;
+    if (a.inv_bw != 0.0) {                                                  // dist / bw, correctly rounded (see eval_pair)
+        const double q0 = __dmul_rn(dist, a.inv_bw);
+        qd = __fma_rn(__fma_rn(-q0, a.bw, dist), a.inv_bw, q0);
+    } else qd = __ddiv_rn(dist, a.bw);
+    const double fl = floor(qd);
+    const double frac = __dmul_rn(__dsub_rn(qd, fl), a.bw);                 // reference C:1016-1017
+    int bfull = __double2int_rz(fl);
+    bool ok = true;
+    if (frac <= a.half_bw) {}
+    else if (frac > a.half_bw) bfull += 1;
+    else ok = false;
+    const int bb = bfull - a.grid_start;
+    const double mind = __dadd_rn(__dmul_rn(A.size, 0.5), halfB);           // reference C:1019-1020
+    if (ok && (unsigned)bb < (unsigned)a.G && dist >= mind) {
+        const int r = magic ? (int)__umulhi((unsigned)bb, magic) : bb;      // bb / w (exact below 2^16; magic 0: w = 1)
+        o.key = (unsigned)r;
+        o.local = bb - r * w;
+        o.cell = cell0 + bb;
+        o.val = __dmul_rn(A.w, wB);
+    }
+    return o;
+}
+
+// Persistent CTAs: a CTA claims a haplotype pair, stages the B haplotype once, and its warps claim the A labels of the pair
+// (heaviest first) from a shared counter, so that uneven label sizes leave no warp idle behind a slow neighbour.  A warp then
+// takes the labels of B one after the other: the chunk pairs of one (label of A, label of B) are numbered q = i * |B group| + j
+// and handed to the lanes 32 at a time (all lanes busy however small the groups are), so that at any time a warp writes to
+// the few record regions of ONE label pair -- their sectors fill up and leave L2 whole.
+template <bool SCATTER>
+__global__ void __launch_bounds__(32 * kNullWarps) k_null_eval(const NullEvalArgs a) {
+    extern __shared__ __align__(16) unsigned char nev_sm[];
+    const int cap = a.stage_cap;
+    double2 *sBph = reinterpret_cast<double2 *>(nev_sm);                      // [cap] (position, half size)
+    double *sBw = reinterpret_cast<double *>(sBph + cap);                     // [cap] weight
+    int32_t *ctl = reinterpret_cast<int32_t *>(sBw + cap);                    // [0] tile, [1] next label
+    int32_t *cnt = ctl + 4 + warp_id() * kNullMaxRanges;
+    const int K = a.K;
+    const int lane = lane_id();
+    const unsigned lt = (1u << lane) - 1;
+    const long long NT = a.n_tasks;
+    while (true) {
+        __syncthreads();                                    // everybody is done with the staged haplotype
+        if (threadIdx.x == 0) { ctl[0] = atomicAdd(a.tile_counter, 1); ctl[1] = 0; }
+        __syncthreads();
+        // work unit = (haplotype pair, group of A labels): the labels are dealt round robin over la_groups groups, so that a batch
+        // of few (long) haplotype pairs still fills the GPU
+        const int unit = ctl[0];
+        if (unit >= a.n_tiles * a.la_groups) break;
+        const int tile = unit / a.la_groups, grp = unit - tile * a.la_groups;
+        const int2 hh = a.tiles[tile];
+        const int32_t *oA = a.lab_off + (size_t)hh.x * (K + 2);
+        const int32_t *oB = a.lab_off + (size_t)hh.y * (K + 2);
+        const int nB = oB[K];                               // labelled chunks of B (labels 1..K), grouped by label
+        const Chunk *CB = a.chunks + a.hap_base[hh.y];
+        const bool staged = nB <= cap;
+        if (staged) {
+            for (int j = threadIdx.x; j < nB; j += blockDim.x) {
+                const Chunk B = ldg_chunk(CB + j);
+                sBph[j] = make_double2(B.pos, __dmul_rn(B.size, 0.5));
+                sBw[j] = B.w;
+            }
+        }
+        __syncthreads();
+        while (true) {
+            int qi = 0;
+            if (lane == 0) qi = atomicAdd(&ctl[1], 1);
+            qi = __shfl_sync(kFull, qi, 0) * a.la_groups + grp;
+            if (qi >= a.n_own) break;
+            const int la = a.own[qi];
+            const int a0 = oA[la], cntA = oA[la + 1] - a0;
+            if (cntA <= 0) {
+                if (!SCATTER) {                             // the counts of this (tile, label) must still be written: zeros
+                    const NullRowPlan rp = a.rows[la];
+                    int32_t *g0 = a.counts + (size_t)tile * NT + rp.task0;
+                    for (int t = lane; t < rp.ntb; t += 32) g0[t] = 0;
+                }
+                continue;
+            }
+            const Chunk *CA = a.chunks + a.hap_base[hh.x] + a0;
+            const NullPairPlan *row = a.plan + (size_t)la * K;
+            const int task0 = a.rows[la].task0;
+            int32_t *grow = (SCATTER ? const_cast<int32_t *>(a.offs) : a.counts) + (size_t)tile * NT + task0;   // [tile][task]
+            for (int lb = 0; lb < K; lb++) {
+                const NullPairPlan pp = row[lb];
+                const int b0 = oB[lb], cntB = oB[lb + 1] - b0;
+                const int nr = (a.G + pp.w - 1) / pp.w;
+                int32_t *gcnt = grow + pp.tb0;
+                __syncwarp();
+                for (int t = lane; t < nr; t += 32) cnt[t] = (SCATTER && cntB > 0) ? gcnt[t] : 0;
+                __syncwarp();
+                if (cntB > 0) {
+                    const int npairs = cntA * cntB;
+                    const unsigned bmagic = cntB > 1 ? (unsigned)((0x100000000ULL + cntB - 1) / cntB) : 0u;   // q / cntB for q < 2^16 ...
+                    const bool small = npairs < 65536;                                                         // ... else a real division
+                    const int cell0 = (la * K + lb) * a.G;
+                    for (int q0 = 0; q0 < npairs; q0 += 64) {
+                        NullStep e[2];
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const int q = q0 + 32 * h + lane;
+                            const bool valid = q < npairs;
+                            int i = 0, j = 0;
+                            if (valid) {
+                                i = cntB == 1 ? q : (small ? (int)__umulhi((unsigned)q, bmagic) : q / cntB);
+                                j = q - i * cntB;
+                            }
+                            const Chunk A = ldg_chunk(CA + i);
+                            double posB, halfB, wB;
+                            if (staged) { const double2 ph = sBph[b0 + j]; posB = ph.x; halfB = ph.y; wB = sBw[b0 + j]; }
+                            else { const Chunk B = ldg_chunk(CB + b0 + j); posB = B.pos; halfB = __dmul_rn(B.size, 0.5); wB = B.w; }
+                            e[h] = null_eval_pair(a, A, posB, halfB, wB, cell0, pp.magic, pp.w, valid);
+                        }
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const bool acc = e[h].key != ~0u;
+                            if (!SCATTER) {
+                                if (acc) atomicAdd(&cnt[e[h].key], 1);
+                            } else {
+                                // stable rank inside the step: the lanes of the same bin range, in lane order (= (i, j) order)
+                                if (!__any_sync(kFull, acc)) continue;
+                                const unsigned M = nr > 1 ? __match_any_sync(kFull, e[h].key) : __ballot_sync(kFull, acc);
+                                const int first = __ffs(M) - 1;
+                                int base = 0;
+                                if (acc && lane == first) base = atomicAdd(&cnt[e[h].key], __popc(M));   // one lane per range of the step
+                                base = __shfl_sync(kFull, base, first);
+                                if (acc) {
+                                    UpdateRec rec;
+                                    rec.cell = e[h].cell; rec.pad = e[h].local; rec.val = e[h].val;
+                                    a.recs[base + __popc(M & lt)] = rec;
+                                }
+                            }
+                        }
+                    }
+                }
+                if (!SCATTER) {
+                    __syncwarp();
+                    for (int t = lane; t < nr; t += 32) gcnt[t] = cnt[t];
+                }
+            }
+        }
+    }
+}
+
+// [rows][cols] int32 -> [cols][rows]
+__global__ void __launch_bounds__(256) k_transpose_i32(const int32_t *__restrict__ in, long long rows, long long cols, int32_t *__restrict__ out) {
+    __shared__ int32_t t[32][33];
+    const long long c0 = (long long)blockIdx.x * 32, r0 = (long long)blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int k = ty; k < 32; k += 8)
+        if (r0 + k < rows && c0 + tx < cols) t[k][tx] = in[(r0 + k) * cols + c0 + tx];
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8)
+        if (c0 + k < cols && r0 + tx < rows) out[(c0 + k) * rows + r0 + tx] = t[tx][k];
+}
+void launch_transpose_i32(const int32_t *in, long long rows, long long cols, int32_t *out, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return;
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+    k_transpose_i32<<<grid, 256, 0, st>>>(in, rows, cols, out);
+}
+
+// one record region per commit task: commit task c folds natural task perm[c], whose tiles are adjacent in the record buffer
+__global__ void k_null_dir(const int32_t *__restrict__ offs, const int32_t *__restrict__ perm, int n_tasks, long long T,
+                           RegionEnt *__restrict__ dir) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_tasks) return;
+    const long long t = perm[c];
+    RegionEnt o;
+    o.base = offs[t * T];
+    o.cnt = offs[(t + 1) * T] - offs[t * T];
+    o.pad = 0;
+    dir[c] = o;
+}
+
+int null_stage_cap(int max_chunks) { return std::min(kNullStageB, (max_chunks + 7) & ~7); }
+size_t null_eval_smem(int K, int max_tb, int stage_cap) {
+    (void)K; (void)max_tb;
+    return (size_t)stage_cap * (sizeof(double2) + sizeof(double)) + 16 + (size_t)kNullWarps * kNullMaxRanges * sizeof(int32_t);
+}
+void launch_null_eval(const NullEvalArgs &a, bool scatter, cudaStream_t st) {
+    if (a.n_tiles <= 0 || a.n_own <= 0) return;
+    const size_t smem = null_eval_smem(a.K, a.max_tb, a.stage_cap);
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+        cudaFuncSetAttribute(k_null_eval<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_null_eval<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set[dev & 63] = true;
+    }
+    const long long per_sm = std::max<long long>(1, std::min<long long>(2048 / (32 * kNullWarps), (227 * 1024) / (long long)(smem + 1024)));
+    const unsigned grid = (unsigned)std::min<long long>((long long)a.n_tiles * a.la_groups, 148 * per_sm);
+    if (scatter) k_null_eval<true><<<grid, 32 * kNullWarps, smem, st>>>(a);
+    else k_null_eval<false><<<grid, 32 * kNullWarps, smem, st>>>(a);
+}
+
+void launch_null_dir(const int32_t *offs, const int32_t *perm, int n_tasks, long long T, RegionEnt *dir, cudaStream_t st) {
+    if (n_tasks <= 0) return;
+    k_null_dir<<<(n_tasks + 255) / 256, 256, 0, st>>>(offs, perm, n_tasks, T, dir);
 }
 
 }  // namespace fgt

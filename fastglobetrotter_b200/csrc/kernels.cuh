@@ -103,7 +103,11 @@ struct CommitArgs {
     double *tensor;
     unsigned long long *accepted;
     int *task_counter;            // zeroed before the launch: persistent CTAs claim (individual, slab) tasks from it
+    const struct CommitTile *task_tab;   // optional explicit task table (NULL path): tile = rows [row0, row0+rows) x bins [b0, b0+bins) of
+    int32_t n_task_tab;                  // `tensor` (individual 0), one RegionEnt per task, heavy tasks first
+    int32_t max_tile_cells;              // largest tile of the table (sizes the shared memory)
 };
+struct CommitTile { int32_t row0, rows, b0, bins; };
 struct RouteArgs {               // large K: split every (individual, slab) record stream by block of tensor rows (k_route)
     const UpdateRec *recs;        // phase-1 records ...
     const RegionEnt *regions;     // ... and their directory [N*n_slabs][nb-1][nd_max]
@@ -182,5 +186,37 @@ void launch_null_group(int n_haps, const int32_t *row_off /*[n_haps+1]*/, const 
                        const int32_t *chap, const int32_t *donor_label, int n_donor_labels, double cutoff, int K,
                        Chunk *grouped, int32_t *lab_off, int *err, cudaStream_t st);
 void launch_null_strict(const NullArgs &a, cudaStream_t st);
+
+// two-phase NULL path (null_impl = 2): evaluate every chunk pair once into records, fold them with k_commit_ordered
+struct NullPairPlan { int32_t tb0, w; uint32_t magic; int32_t pad; };   // per (label of A, label of B): first counter of the pair's bin
+                                                                        // ranges within the row of A, bins per range, ceil(2^32 / w) (0: w = 1)
+struct NullRowPlan { int32_t task0, ntb; };                             // per label of A: its first task (natural numbering), its tasks
+struct NullEvalArgs {
+    const Chunk *chunks;          // per haplotype, grouped by population label (k_null_group)
+    const int32_t *hap_base;      // [n_haps+1]
+    const int32_t *lab_off;       // [n_haps][K+2]
+    const int2 *tiles;            // [n_tiles] haplotype pairs (A, B) of this batch in the reference's (n, p, g, m) order
+    int32_t n_tiles;
+    const int32_t *own;           // [n_own] labels of A (0-based) this engine folds (all of them unless the call is sharded)
+    int32_t n_own;
+    int32_t la_groups;            // work units per haplotype pair (groups of A labels)
+    int32_t K, G, grid_start;
+    double bw, half_bw, inv_bw;
+    const NullPairPlan *plan;     // [K][K]
+    const NullRowPlan *rows;      // [K]
+    int32_t max_tb;               // largest ntb (shared-memory counters per warp)
+    int32_t stage_cap;            // null_stage_cap(most labelled chunks of a haplotype)
+    int32_t n_tasks;              // tasks of this engine (natural numbering: rows of A in label order)
+    int32_t *counts;              // counting pass: [n_tiles][n_tasks]
+    const int32_t *offs;          // scatter pass: [n_tiles][n_tasks] first record of (tile, task): the exclusive scan of the counts in
+                                  // [task][tile] order, transposed back
+    UpdateRec *recs;
+    int *tile_counter;            // zeroed before every launch: persistent CTAs claim haplotype pairs from it
+};
+int null_stage_cap(int max_chunks);   // chunks of B a CTA stages in shared memory (multiple of 8)
+size_t null_eval_smem(int K, int max_tb, int stage_cap);
+void launch_transpose_i32(const int32_t *in, long long rows, long long cols, int32_t *out, cudaStream_t st);
+void launch_null_eval(const NullEvalArgs &a, bool scatter, cudaStream_t st);
+void launch_null_dir(const int32_t *offs, const int32_t *perm, int n_tasks, long long T, RegionEnt *dir, cudaStream_t st);
 
 }  // namespace fgt

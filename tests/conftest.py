@@ -52,6 +52,20 @@ def each_encoding(lib, request):
     lib.encode = "rle"
 
 
+@pytest.fixture(params=["windowed", "two_phase", "two_phase_batched"])
+def each_null_impl(lib, request):
+    """run a NULL test with k_null_strict (null_impl 1), with the two-phase path (null_impl 2: every chunk pair evaluated once
+    into records, ordered commit), and with the two-phase path forced into many small batches and many narrow commit tasks"""
+    lib.set_option("null_impl", 1 if request.param == "windowed" else 2)
+    if request.param == "two_phase_batched":
+        lib.set_option("null_batch", 3000)
+        lib.set_option("null_tasks", 100000)
+    yield request.param
+    lib.set_option("null_impl", 0)
+    lib.set_option("null_batch", 0)
+    lib.set_option("null_tasks", 0)
+
+
 @pytest.fixture(scope="session")
 def oracle():
     from oracle.oracle import Oracle

@@ -136,7 +136,7 @@ def test_config3_slice_22_chromosomes_K50_with_bootstrap_ids(lib, oracle):
     assert total > 3_000_000
 
 
-def test_config4_slice_K100_curves_and_full_null(lib, oracle):
+def test_config4_slice_K100_curves_and_full_null(lib, oracle, each_null_impl):
     """configs[3] scaled: K = 100 surrogates/donor groups (tile too large for shared memory: global-tensor commit path),
     500 bins, three chromosomes; data_read and the complete NULL-individual tensor (100 x 100 x 500) over 5 individuals."""
     spec = synth.SynthSpec(n_chrom=3, n_inds=5, ploidy=2, nsamples=5, n_snps=9000, K=100, haps_per_pop=4, rate=1.4e-7, seed=404, name="cfg4")

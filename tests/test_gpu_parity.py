@@ -188,7 +188,7 @@ def test_odd_grids(lib, oracle, small):
         assert np.array_equal(m_g, m_o, equal_nan=True), (bw, G, gs)
 
 
-def test_null_packed_bit_exact(lib, oracle, small, each_encoding):
+def test_null_packed_bit_exact(lib, oracle, small, each_encoding, each_null_impl):
     sp = small.spec
     chrom, dl = packed_chrom(small), small.donor_label_vec
     K, G, bw, gs = sp.K, 120, 0.1, 10
@@ -476,7 +476,7 @@ def test_edge_shapes(lib, oracle):
               S, tw)
 
 
-def test_null_edge_shapes(lib, oracle):
+def test_null_edge_shapes(lib, oracle, each_null_impl):
     K = 4
     spec = synth.SynthSpec(n_chrom=2, n_inds=3, ploidy=1, nsamples=2, n_snps=1200, K=K, rate=1.5e-6, self_copy_frac=0.1, seed=2)
     chrom = []
@@ -660,8 +660,9 @@ def test_twenty_two_chromosomes_bootstrap(lib, oracle, mode):
         lib.set_option("blocks", 0)
 
 
-def test_null_sharded_by_label_pair_is_exact(lib, oracle, small):
-    """data_read_null over `world` ranks: each folds the label pairs it owns (the same owner on every chromosome), the
+def test_null_sharded_by_label_pair_is_exact(lib, oracle, small, each_null_impl):
+    """data_read_null over `world` ranks: each folds the label pairs it owns (two-phase path: whole rows of A labels, so the
+    evaluation is split as well; the same owner on every chromosome), the
     partial tensors have disjoint supports and their sum is the oracle's tensor bit for bit -- also when the caller's
     buffer starts non-zero (every rank gets it and keeps only its own cells of it)."""
     sp = small.spec
