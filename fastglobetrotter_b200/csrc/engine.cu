@@ -86,6 +86,7 @@ int Engine::set_option(const char *key, double v) {
     else if (k == "null_impl") opt.null_impl = iv;
     else if (k == "null_batch") opt.null_batch = v;
     else if (k == "null_tasks") opt.null_tasks = iv;
+    else if (k == "null_overlap") opt.null_overlap = iv;
     else if (k == "null_world") opt.null_world = std::max(1, iv);
     else if (k == "null_rank") opt.null_rank = std::max(0, iv);
     else if (k == "project_impl") opt.project_impl = iv;
@@ -122,6 +123,7 @@ double Engine::get_option(const char *key) {
     if (k == "null_impl") return opt.null_impl;
     if (k == "null_batch") return opt.null_batch;
     if (k == "null_tasks") return opt.null_tasks;
+    if (k == "null_overlap") return opt.null_overlap;
     if (k == "null_world") return opt.null_world;
     if (k == "null_rank") return opt.null_rank;
     if (k == "project_impl") return opt.project_impl;
@@ -1901,12 +1903,20 @@ int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::v
             if (ownA[hA] > 0 && nlab[hB] > 0) { tiles.push_back(make_int2(hA, hB)); bound.push_back(ownA[hA] * nlab[hB]); }
     if (tiles.empty()) return FGT_OK;
     // batch size: records of a batch are addressed with 32 bits; the buffer takes a share of the free memory
-    size_t free_b = 0, total_b = 0;
-    cudaMemGetInfo(&free_b, &total_b);
-    free_b += d_recs_.cap + d_ncnt_.cap + d_noff_.cap;
-    long long batch_evals = opt.null_batch > 0 ? (long long)opt.null_batch : (long long)std::min(1.5e9, (double)free_b * 0.5 / sizeof(UpdateRec));
-    long long max_bound = 0;
-    for (long long b : bound) max_bound = std::max(max_bound, b);
+    vtick("null: plan made");
+    if (mem_budget_bytes_ <= 0) {                                // cudaMemGetInfo costs milliseconds: ask once
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        free_b += d_draws_.cap + d_recs_.cap;
+        mem_budget_bytes_ = std::min((double)free_b * 0.6, 64e9);
+    }
+    long long batch_evals = opt.null_batch > 0 ? (long long)opt.null_batch : (long long)std::min(1.5e9, mem_budget_bytes_ * 0.8 / sizeof(UpdateRec));
+    long long max_bound = 0, total_bound = 0;
+    for (long long b : bound) { max_bound = std::max(max_bound, b); total_bound += b; }
+    {   // equal batches instead of full ones and a remainder (every batch pays for a pass over all commit tasks)
+        const long long nbat = (total_bound + batch_evals - 1) / batch_evals;
+        batch_evals = std::min(batch_evals, (total_bound + nbat - 1) / nbat + max_bound);
+    }
     batch_evals = std::max(batch_evals, max_bound);
     if (batch_evals >= (1LL << 31) - 64) return FGT_ERR_ARG;
     const long long max_tiles = std::max<long long>(1, 100000000LL / n_tasks);     // count / offset tables of at most 400 MB each
@@ -1917,9 +1927,8 @@ int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::v
     NullRowPlan *d_rows = d_nrows_.as<NullRowPlan>(rows.size());
     int32_t *d_perm = d_nperm_.as<int32_t>(perm.size());
     CommitTile *d_tab = d_ntab_.as<CommitTile>(tab.size());
-    RegionEnt *d_dir = d_ndir_.as<RegionEnt>(tab.size());
     int *d_ctr = d_taskctr_.as<int>(1024);
-    if (!d_tiles || !d_own || !d_plan || !d_rows || !d_perm || !d_tab || !d_dir || !d_ctr) return FGT_ERR_CUDA;
+    if (!d_tiles || !d_own || !d_plan || !d_rows || !d_perm || !d_tab || !d_ctr) return FGT_ERR_CUDA;
     CK(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, st_));
     CK(cudaMemcpyAsync(d_own, own.data(), own.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
     CK(cudaMemcpyAsync(d_plan, plan.data(), plan.size() * sizeof(NullPairPlan), cudaMemcpyHostToDevice, st_));
@@ -1945,22 +1954,37 @@ int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::v
     if (null_eval_smem(K, max_tb, ea.stage_cap) > 200 * 1024) ea.stage_cap = 0;          // many labels: B is read through L1 instead
     if (null_eval_smem(K, max_tb, ea.stage_cap) > 200 * 1024) return FGT_ERR_ARG;
     ea.tile_counter = d_ctr + 1;
+    // Two lanes of batches: batch b is folded on the commit stream while batch b+1 is counted and scattered on the evaluation
+    // stream (the two kinds of kernel stall on different things); both persistent grids are capped so that they fit an SM together.
+    const bool overlap = opt.null_overlap != 0;
+    cudaStream_t sc = overlap ? st_commit_ : st_;
+    for (int e = 0; e < 3; e++)
+        if (!null_ev_[e]) CK(cudaEventCreateWithFlags(&null_ev_[e], cudaEventDisableTiming));
+    if (overlap) {                                   // the caller's values and this chromosome's tables are in place
+        CK(cudaEventRecord(null_ev_[2], st_));
+        CK(cudaStreamWaitEvent(sc, null_ev_[2], 0));
+        ea.max_ctas_per_sm = 8;
+    }
     size_t t0 = 0;
+    int nb = 0;
+    bool lane_used[2] = {false, false};
     while (t0 < tiles.size()) {
         size_t t1 = t0;
         long long sum = 0;
         while (t1 < tiles.size() && (t1 == t0 || (sum + bound[t1] <= batch_evals && (long long)(t1 - t0) < max_tiles))) sum += bound[t1++];
+        const int ln = overlap ? (nb & 1) : 0;
         const long long T = (long long)(t1 - t0);
         const long long n_cnt = (long long)n_tasks * T;
-        int32_t *d_cnt = d_ncnt_.as<int32_t>((size_t)n_cnt + 1 + 2 * ((size_t)n_cnt / 1024 + 2));
-        int32_t *d_off = d_noff_.as<int32_t>((size_t)n_cnt + 1);
-        UpdateRec *d_recs = d_recs_.as<UpdateRec>((size_t)sum + 2);
-        if (!d_cnt || !d_off || !d_recs) return FGT_ERR_CUDA;
+        int32_t *d_cnt = (ln ? d_ncnt2_ : d_ncnt_).as<int32_t>((size_t)n_cnt + 1 + 2 * ((size_t)n_cnt / 1024 + 2));
+        int32_t *d_off = (ln ? d_noff2_ : d_noff_).as<int32_t>((size_t)n_cnt + 1);
+        RegionEnt *d_dir = (ln ? d_ndir2_ : d_ndir_).as<RegionEnt>(tab.size());
+        UpdateRec *d_recs = (ln ? d_recs2_ : d_recs_).as<UpdateRec>((size_t)sum + 2);
+        if (!d_cnt || !d_off || !d_recs || !d_dir) return FGT_ERR_CUDA;
         ea.tiles = d_tiles + t0; ea.n_tiles = (int)T;
         ea.la_groups = (int)std::max<long long>(1, std::min<long long>((long long)own.size(), (148 * 8 + T - 1) / T));
         ea.recs = d_recs;
         // counts per (tile, task) -> [task][tile] -> exclusive scan = first record of every (task, tile) -> back to [tile][task]
-        CK(cudaMemsetAsync(d_ctr, 0, 4 * sizeof(int), st_));
+        CK(cudaMemsetAsync(d_ctr + 1, 0, sizeof(int), st_));
         ea.counts = d_cnt; ea.offs = nullptr;
         launch_null_eval(ea, false, st_);
         launch_transpose_i32(d_cnt, T, n_tasks, d_off, st_);
@@ -1968,18 +1992,31 @@ int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::v
         launch_transpose_i32(d_cnt, n_tasks, T, d_off, st_);
         CK(cudaMemsetAsync(d_ctr + 1, 0, sizeof(int), st_));
         ea.counts = nullptr; ea.offs = d_off;
+        if (overlap && lane_used[ln]) CK(cudaStreamWaitEvent(st_, null_ev_[ln], 0));     // the lane's records and directory are free again
         launch_null_eval(ea, true, st_);
         launch_null_dir(d_cnt, d_perm, n_tasks, T, d_dir, st_);
+        if (overlap) {
+            CK(cudaEventRecord(null_ev_[2], st_));
+            CK(cudaStreamWaitEvent(sc, null_ev_[2], 0));
+        }
+        int *ctr = d_ctr + 2 + ln;
+        CK(cudaMemsetAsync(ctr, 0, sizeof(int), sc));
         CommitArgs ca{};
         ca.N = 1; ca.K = K; ca.G = G; ca.grid_start = pb.grid_start;
         ca.recs = d_recs; ca.regions = d_dir; ca.tensor_is_zero = 0; ca.buckets = 0;
-        ca.tensor = d_out; ca.accepted = d_acc; ca.task_counter = d_ctr;
+        ca.tensor = d_out; ca.accepted = d_acc; ca.task_counter = ctr;
         ca.task_tab = d_tab; ca.n_task_tab = n_tasks; ca.max_tile_cells = max_w;
-        launch_commit_ordered(ca, max_w, st_);
+        ca.max_ctas_per_sm = overlap ? 10 : 0;
+        launch_commit_ordered(ca, max_w, sc);
+        if (overlap) { CK(cudaEventRecord(null_ev_[ln], sc)); lane_used[ln] = true; }
         launches_ += 10;
         stx.accum_launches += 1;
+        if (opt.verbose) { char msg[96]; snprintf(msg, sizeof msg, "null: batch of %lld haplotype pairs launched (bound %lld records)", T, sum); vtick(msg); }
         t0 = t1;
+        nb++;
     }
+    if (overlap)                                     // the tensor and this chromosome's tables are the evaluation stream's again
+        for (int ln = 0; ln < 2; ln++) if (lane_used[ln]) CK(cudaStreamWaitEvent(st_, null_ev_[ln], 0));
     return FGT_OK;
 }
 
@@ -1994,6 +2031,7 @@ int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_ro
     for (int h = 0; h < pb.num_chrom; h++)
         if (pb.chrom[h].runs ? !pb.chrom[h].run_off : (!pb.chrom[h].labels || (pb.label_bytes != 2 && pb.label_bytes != 4))) return FGT_ERR_ARG;
     CK(cudaSetDevice(device_));
+    t_call_start_ = std::chrono::steady_clock::now();
     fgt_stats_t stx{};
     launches_ = 0;
     cudaEvent_t e0, e1, e2;
@@ -2056,6 +2094,7 @@ int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_ro
             std::vector<int32_t> laboff((size_t)n_haps * (K + 2));
             CK(cudaMemcpyAsync(laboff.data(), cs.yoff.p, laboff.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st_));
             CK(cudaStreamSynchronize(st_));
+            vtick("null: chunks grouped, label counts on the host");
             if (two_phase) {
                 rc = null_two_phase(pb, cs, laboff, Nc, null_world, null_rank, d_out, d_acc, stx);
                 if (rc) return rc;
@@ -2115,12 +2154,14 @@ int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_ro
         }
     }
     CK(cudaEventRecord(e2, st_));
+    vtick("null: all chromosomes launched");
     CK(cudaMemcpyAsync(out, d_out, (size_t)K * K * G * sizeof(double), cudaMemcpyDeviceToHost, st_));
     int herr[4];
     unsigned long long hacc[2];
     CK(cudaMemcpyAsync(herr, d_err, sizeof herr, cudaMemcpyDeviceToHost, st_));
     CK(cudaMemcpyAsync(hacc, d_acc, sizeof hacc, cudaMemcpyDeviceToHost, st_));
     CK(cudaStreamSynchronize(st_));
+    vtick("null: done");
     CK(cudaGetLastError());
     if ((herr[0] & kErrMissingDonor) && Nc >= 2) return FGT_ERR_MISSING_DONOR;
     stx.pairs = evals;

@@ -1460,7 +1460,8 @@ void launch_commit_ordered(const CommitArgs &a, int max_slab_width, cudaStream_t
         }
         const bool buckets = a.buckets != 0;
         const size_t smem = ctrl_bytes + tile_bytes + (buckets ? kQueueBytes : 0);
-        const long long per_sm = std::max<long long>(1, (227 * 1024) / (long long)(smem + 1024));
+        long long per_sm = std::max<long long>(1, (227 * 1024) / (long long)(smem + 1024));
+        if (a.max_ctas_per_sm > 0) per_sm = std::min<long long>(per_sm, a.max_ctas_per_sm);
         const long long grid = std::min<long long>(tasks, 148 * std::min<long long>(per_sm, 32));
         if (buckets) k_commit_ordered<true, true><<<(unsigned)grid, 32 * (kConsumers + 1), smem, st>>>(a);
         else k_commit_ordered<true, false><<<(unsigned)grid, 32 * (kConsumers + 1), smem, st>>>(a);
@@ -2480,7 +2481,8 @@ void launch_null_eval(const NullEvalArgs &a, bool scatter, cudaStream_t st) {
         cudaFuncSetAttribute(k_null_eval<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set[dev & 63] = true;
     }
-    const long long per_sm = std::max<long long>(1, std::min<long long>(2048 / (32 * kNullWarps), (227 * 1024) / (long long)(smem + 1024)));
+    long long per_sm = std::max<long long>(1, std::min<long long>(2048 / (32 * kNullWarps), (227 * 1024) / (long long)(smem + 1024)));
+    if (a.max_ctas_per_sm > 0) per_sm = std::min<long long>(per_sm, a.max_ctas_per_sm);
     const unsigned grid = (unsigned)std::min<long long>((long long)a.n_tiles * a.la_groups, 148 * per_sm);
     if (scatter) k_null_eval<true><<<grid, 32 * kNullWarps, smem, st>>>(a);
     else k_null_eval<false><<<grid, 32 * kNullWarps, smem, st>>>(a);

@@ -106,6 +106,7 @@ struct CommitArgs {
     const struct CommitTile *task_tab;   // optional explicit task table (NULL path): tile = rows [row0, row0+rows) x bins [b0, b0+bins) of
     int32_t n_task_tab;                  // `tensor` (individual 0), one RegionEnt per task, heavy tasks first
     int32_t max_tile_cells;              // largest tile of the table (sizes the shared memory)
+    int32_t max_ctas_per_sm;             // > 0: cap of the persistent grid (leaves room for a kernel of another stream)
 };
 struct CommitTile { int32_t row0, rows, b0, bins; };
 struct RouteArgs {               // large K: split every (individual, slab) record stream by block of tensor rows (k_route)
@@ -212,6 +213,7 @@ struct NullEvalArgs {
                                   // [task][tile] order, transposed back
     UpdateRec *recs;
     int *tile_counter;            // zeroed before every launch: persistent CTAs claim haplotype pairs from it
+    int32_t max_ctas_per_sm;      // > 0: cap of the persistent grid
 };
 int null_stage_cap(int max_chunks);   // chunks of B a CTA stages in shared memory (multiple of 8)
 size_t null_eval_smem(int K, int max_tb, int stage_cap);

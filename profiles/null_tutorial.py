@@ -14,12 +14,15 @@ prm = parse_paramfile(os.path.join(tdir, "paramfile.txt"))
 dl, rec = id_file_inputs(os.path.join(tdir, "individual.txt"), prm["copyvector.popnames"].split(), prm["target.popname"])
 K, bw, G, gs, stride = int(gold["K"]), float(gold["bw"]), int(gold["G"]), int(gold["gs"]), int(gold["stride"])
 os.chdir(GOLDEN)
+if os.environ.get("DEVICES"): lib.set_option("devices", int(os.environ["DEVICES"]))   # one process, several GPUs
 for impl in [int(x) for x in os.environ.get("IMPLS", "1,2,0").split(",")]:
     lib.set_option("null_impl", impl)
     for rep in range(3):
+        lib.set_option("verbose", 1 if (rep == 2 and os.environ.get("VERBOSE")) else 0)
         t0 = time.perf_counter()
         nul = lib.coancestry_curves_null(2, "tutorial/samplefile.txt", "tutorial/recomfile.txt", bw, G, gs, K, dl, rec, 0.0, 1.0)
         dt = time.perf_counter() - t0
+    lib.set_option("verbose", 0)
     st = lib.last_stats()
     gu.assert_matches(gold, "null", nul, stride)
     print(f"null_impl={impl}: call {dt*1e3:.1f} ms, kernels {st['ms_accum']:.1f} ms, {st['pairs']/1e9:.2f} G evaluations, {st['pairs']/dt/1e9:.1f} G/s, accepted {st['accepted']/st['pairs']:.3f}, == reference", flush=True)
