@@ -476,7 +476,7 @@ def file_parity_and_e2e(lib, files, means_ref, sample_inds, ref_ms_per_call):
     return same, out
 
 
-def other_paths(lib, chrom_dev, common, tail, S, tw, N, dl, K, G, W, steps=3, null_inds=40):
+def other_paths(lib, chrom_dev, common, tail, S, tw, N, dl, K, G, W, steps=3, null_inds=100):
     """the two other entry points of the path on the same device-resident synthetic paintings (outside the timed region of
     the headline): data_read_mode3 (window +1, Y/8, no target-label skip, projection per chromosome) in the headline's
     unit, and data_read_null (exhaustive chunk x chunk across the first `null_inds` individuals) in chunk-pair
@@ -501,8 +501,14 @@ def other_paths(lib, chrom_dev, common, tail, S, tw, N, dl, K, G, W, steps=3, nu
     _, st = lib.data_read_null_packed(W["ploidy"], W["nsamples"], chrom_dev, rows, W["bw"], G, W["grid_start"], K, dl, W["weight_min"],
                                       W["cutoff"])
     dt = time.perf_counter() - t0
+    peak, peak_src = peaks()
     res["data_read_null"] = {"value": st["pairs"] / dt, "unit": "chunk-pair evaluations/s", "ms": dt * 1e3, "individuals": int(rows.size),
-                             "pair_evaluations": st["pairs"]}
+                             "pair_evaluations": st["pairs"], "accepted_fraction": st["accepted"] / max(1, st["pairs"]),
+                             "impl": "two phases (k_null_eval count/scatter + k_commit_ordered)" if lib.get_option("null_impl") == 2 or
+                                     (lib.get_option("null_impl") == 0 and K <= 64) else "windowed (k_null_strict)",
+                             "roofline": {"bound": "hbm", "achieved": 16.0 * st["accepted"] / dt / 1e9, "peak": peak, "unit": "GB/s",
+                                          "frac": 16.0 * st["accepted"] / dt / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                                          "note": "16 B per accepted update (SURVEY 8d) over the whole call (count, scan, scatter, commit)"}}
     return res
 
 

@@ -83,6 +83,7 @@ int Engine::set_option(const char *key, double v) {
     else if (k == "accum_impl") opt.accum_impl = iv;
     else if (k == "spec_rand") opt.spec_rand = iv;
     else if (k == "null_target") opt.null_target = iv;
+    else if (k == "commit_ctas") opt.commit_ctas = iv;
     else if (k == "null_impl") opt.null_impl = iv;
     else if (k == "null_batch") opt.null_batch = v;
     else if (k == "null_tasks") opt.null_tasks = iv;
@@ -120,6 +121,7 @@ double Engine::get_option(const char *key) {
     if (k == "reuse_prep") return opt.reuse_prep;
     if (k == "accum_impl") return opt.accum_impl;
     if (k == "spec_rand") return opt.spec_rand;
+    if (k == "commit_ctas") return opt.commit_ctas;
     if (k == "null_impl") return opt.null_impl;
     if (k == "null_batch") return opt.null_batch;
     if (k == "null_tasks") return opt.null_tasks;
@@ -1209,6 +1211,7 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
                     CK(cudaStreamWaitEvent(sc, eval_done, 0));
                     span_begin(1, sc);
                     ca.buckets = opt.commit_impl == 1 ? 1 : 0;
+                    ca.max_ctas_per_sm = opt.commit_ctas;
                     ca.tensor = tens_b; ca.accepted = d_acc;
                     ca.task_counter = d_taskctr + batch_seq;
                     launch_commit_ordered(ca, plan_max_w, sc);

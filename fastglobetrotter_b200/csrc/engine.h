@@ -54,6 +54,7 @@ struct Options {
     int copy_streams = 1;   // 2 = alternate the label block copies between two streams (two DMA engines)
     int project_impl = 0;   // 0 = exact (separately rounded multiply and add, bit-identical curves); 1 = FP64 tensor cores (~1e-14)
     int null_target = 0;    // NULL task table: accepted pairs per (haplotype pair, slab) a task aims at; 0 = default
+    int commit_ctas = 0;    // > 0: cap of the commit kernel's persistent CTAs per SM (room for the next range's evaluation kernel)
     int null_impl = 0;      // NULL path: 2 = two phases (every chunk pair evaluated once into records, ordered commit), 1 = k_null_strict,
                             // 0 = two phases up to 64 donor groups, k_null_strict above
     double null_batch = 0;  // null_impl 2: chunk-pair evaluations per batch of haplotype pairs (0 = from free device memory)

@@ -254,6 +254,34 @@ def test_file_entry_points_vs_compiled_reference(lib, ref_libs, small, tmp_path,
         assert np.array_equal(n_ref, n_lib)
 
 
+@pytest.mark.skipif(not have_ref(), reason="compiled reference (oracle/_ref) not present")
+def test_donor_panel_beyond_16_bit_ids(lib, ref_libs, tmp_path):
+    """a donor panel of 68,000 haplotypes: ids above 65535 travel as 32-bit runs whatever the other chromosomes hold (the parse
+    layer once picked a label width per file); data_read, data_read_mode3 and data_read_null on the text files against the
+    compiled reference."""
+    ref, _ = ref_libs
+    sp = synth.SynthSpec(n_chrom=3, n_inds=4, n_snps=1800, K=4, nsamples=3, haps_per_pop=17000, rate=5e-7, self_copy_frac=0.0, name="wide")
+    data = synth.write_dataset(sp, str(tmp_path))
+    assert max(int(c["labels"].max()) for c in data.chrom) > 65535 and len(data.donor_label_vec) >= 68000
+    K, S, G, bw, gs = sp.K, 2, 80, 0.1, 10
+    W = synth.random_weights(K, S)
+    tw = ref.temp_weights_for_data_read(K, S, W)
+    ids = ind_id_matrix(sp.n_inds, sp.n_chrom)
+    args = (sp.ploidy, ids, data.samples_list, data.recom_list, bw, G, gs, K, data.donor_label_vec, data.rec_labels, 0.0, 1.0)
+    lib.set_option("rand_libc", 1)
+    try:
+        for name in ("coancestry_curves", "coancestry_curves_mode3"):
+            srand(77)
+            m_ref = getattr(ref, name)(*args, tw, S)
+            srand(77)
+            m_lib = getattr(lib, name)(*args, tw, S)
+            assert np.array_equal(m_ref, m_lib), name
+    finally:
+        lib.set_option("rand_libc", 0)
+    nargs = (sp.ploidy, data.samples_list, data.recom_list, bw, G, gs, K, data.donor_label_vec, data.rec_labels, 0.0, 1.0)
+    assert np.array_equal(ref.coancestry_curves_null(*nargs), lib.coancestry_curves_null(*nargs))
+
+
 def test_sharded_offsets_reproduce_single_call(lib, oracle, small):
     """two 'ranks' (emulated sequentially on one GPU) with exchanged pair counts reproduce the raw
     tensors of the unsharded call bit-for-bit; means agree to 1e-12 (different summation order over
