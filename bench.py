@@ -348,7 +348,7 @@ def run_ours(args):
                 if files0 is not None:
                     same, fe = file_parity_and_e2e(lib, files0, means_ref, args.cpu_sample_inds, cb.get("ms_per_call"))
                     out["parity_checked"] = same
-                    out["parity"] = ("curves of .C data_read on the cpu_baseline leg's files == compiled reference, bit for bit"
+                    out["parity"] = ("curves of .C data_read (16 individuals) and the NULL tensor of .C data_read_null (8 individuals) on the cpu_baseline leg's files == compiled reference, bit for bit"
                                      if same else "MISMATCH between the GPU library and the compiled reference on the cpu_baseline files")
                     out["file_e2e"] = fe
                 else:
@@ -473,6 +473,21 @@ def file_parity_and_e2e(lib, files, means_ref, sample_inds, ref_ms_per_call):
            "value_first_call": pairs / cold, "value_cached": pairs / cached, "reference_ms_per_call": ref_ms_per_call,
            "speedup_first_call": ref_ms_per_call / (cold * 1e3) if ref_ms_per_call else None,
            "speedup_cached": ref_ms_per_call / (cached * 1e3) if ref_ms_per_call else None}
+    # the NULL curves of the first 8 of those individuals: compiled reference vs the GPU library, same files, bit for bit
+    try:
+        from oracle import build_ref
+        from fastglobetrotter_b200.companion import Companion
+        ref = Companion(build_ref.HOOKED)
+        nn = min(8, sample_inds)
+        nargs = (W["ploidy"], sl, rl, W["bw"], G, W["grid_start"], K, dl, rec[:nn], W["weight_min"], W["cutoff"])
+        t0 = time.perf_counter(); n_ref = ref.coancestry_curves_null(*nargs); t_ref = time.perf_counter() - t0
+        lib.coancestry_curves_null(*nargs)
+        t0 = time.perf_counter(); n_gpu = lib.coancestry_curves_null(*nargs); t_gpu = time.perf_counter() - t0
+        out["null"] = {"individuals": nn, "pair_evaluations": lib.last_stats()["pairs"], "reference_ms": t_ref * 1e3, "cached_call_ms": t_gpu * 1e3,
+                       "parity_checked": bool(np.array_equal(n_ref, n_gpu))}
+        same = same and out["null"]["parity_checked"]
+    except Exception as e:                                   # the headline must not die on the side check
+        out["null"] = {"error": repr(e)}
     return same, out
 
 
@@ -504,8 +519,8 @@ def other_paths(lib, chrom_dev, common, tail, S, tw, N, dl, K, G, W, steps=3, nu
     peak, peak_src = peaks()
     res["data_read_null"] = {"value": st["pairs"] / dt, "unit": "chunk-pair evaluations/s", "ms": dt * 1e3, "individuals": int(rows.size),
                              "pair_evaluations": st["pairs"], "accepted_fraction": st["accepted"] / max(1, st["pairs"]),
-                             "impl": "two phases (k_null_eval count/scatter + k_commit_ordered)" if lib.get_option("null_impl") == 2 or
-                                     (lib.get_option("null_impl") == 0 and K <= 64) else "windowed (k_null_strict)",
+                             "impl": f"null_impl={int(lib.get_option('null_impl'))} (0 = automatic: two phases unless K >= 100 on long chromosomes); "
+                                     f"{st['kernel_launches']} kernel launches",
                              "roofline": {"bound": "hbm", "achieved": 16.0 * st["accepted"] / dt / 1e9, "peak": peak, "unit": "GB/s",
                                           "frac": 16.0 * st["accepted"] / dt / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                                           "note": "16 B per accepted update (SURVEY 8d) over the whole call (count, scan, scatter, commit)"}}
@@ -614,7 +629,7 @@ def run_big(args):
                     "config": {"workload": cfg["name"], "run_at": f"{rows.size} individuals x {n_chrom} chromosomes (chromosome fraction {args.chrom_frac})",
                                "evaluations_per_step": ev / args.steps, "accepted_fraction": acc / max(1, ev), "runs": n_runs,
                                "options": os.environ.get("FGT_OPTS", "")},
-                    "roofline": {"bound": "hbm", "kernel": "k_null_strict", "achieved": 16.0 * acc / dt / 1e9, "peak": peak, "unit": "GB/s",
+                    "roofline": {"bound": "hbm", "kernel": "data_read_null (automatic choice: k_null_eval count/scatter + k_commit_ordered, or k_null_strict)", "achieved": 16.0 * acc / dt / 1e9, "peak": peak, "unit": "GB/s",
                                  "frac": 16.0 * acc / dt / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                                  "note": "16 B per accepted update (SURVEY 8d); the tensor lives in shared memory, not HBM"},
                     "clocks": clocks, "checksum": float(np.nansum(t))})

@@ -88,6 +88,7 @@ int Engine::set_option(const char *key, double v) {
     else if (k == "null_batch") opt.null_batch = v;
     else if (k == "null_tasks") opt.null_tasks = iv;
     else if (k == "null_overlap") opt.null_overlap = iv;
+    else if (k == "null_block") opt.null_block = iv;
     else if (k == "null_world") opt.null_world = std::max(1, iv);
     else if (k == "null_rank") opt.null_rank = std::max(0, iv);
     else if (k == "project_impl") opt.project_impl = iv;
@@ -126,6 +127,7 @@ double Engine::get_option(const char *key) {
     if (k == "null_batch") return opt.null_batch;
     if (k == "null_tasks") return opt.null_tasks;
     if (k == "null_overlap") return opt.null_overlap;
+    if (k == "null_block") return opt.null_block;
     if (k == "null_world") return opt.null_world;
     if (k == "null_rank") return opt.null_rank;
     if (k == "project_impl") return opt.project_impl;
@@ -1951,8 +1953,33 @@ int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::v
         ea.inv_bw = (!all_ones && normal) ? 1.0 / pb.binwidth : 0.0;
     }
     ea.plan = d_plan; ea.rows = d_rows; ea.max_tb = max_tb; ea.n_tasks = n_tasks;
-    long long most = 1;
-    for (long long c : nlab) most = std::max(most, c);
+    long long most = 1, all_lab = 0;
+    for (long long c : nlab) { most = std::max(most, c); all_lab += c; }
+    // small label groups (large K): the labels of B in blocks of consecutive labels holding at most 32 bin ranges
+    const bool blocks = opt.null_block >= 0 ? opt.null_block != 0 : (double)all_lab / NH / K < 24.0;
+    if (blocks) {
+        std::vector<int32_t> bstart(K + 1, 0);
+        std::vector<int2> blk;
+        for (int la = 0; la < K; la++) {
+            bstart[la] = (int32_t)blk.size();
+            if (!null_owner(true, la, 0, null_world, null_rank)) continue;
+            int lb0 = 0, acc = 0;
+            for (int lb = 0; lb < K; lb++) {
+                const int nr = (G + plan[(size_t)la * K + lb].w - 1) / plan[(size_t)la * K + lb].w;
+                if (lb > lb0 && acc + nr > 32) { blk.push_back(make_int2(lb0, lb)); lb0 = lb; acc = 0; }
+                acc += nr;
+            }
+            blk.push_back(make_int2(lb0, K));
+        }
+        bstart[K] = (int32_t)blk.size();
+        int32_t *d_bs = d_nblks_.as<int32_t>(bstart.size());
+        int2 *d_blk = d_nblk_.as<int2>(blk.size() + 1);
+        if (!d_bs || !d_blk) return FGT_ERR_CUDA;
+        CK(cudaMemcpyAsync(d_bs, bstart.data(), bstart.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
+        CK(cudaMemcpyAsync(d_blk, blk.data(), blk.size() * sizeof(int2), cudaMemcpyHostToDevice, st_));
+        CK(cudaStreamSynchronize(st_));            // the two vectors are locals
+        ea.blk_start = d_bs; ea.blk = d_blk;
+    }
     ea.stage_cap = null_stage_cap((int)std::min<long long>(most, 1 << 20));
     if (null_eval_smem(K, max_tb, ea.stage_cap) > 200 * 1024) ea.stage_cap = 0;          // many labels: B is read through L1 instead
     if (null_eval_smem(K, max_tb, ea.stage_cap) > 200 * 1024) return FGT_ERR_ARG;
@@ -2061,11 +2088,25 @@ int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_ro
     double *d_out = d_tensor_.as<double>((size_t)K * K * G);
     if (!d_out) return FGT_ERR_CUDA;
     // null_impl: 2 = two phases (every chunk pair evaluated once), 1 = k_null_strict (windowed enumeration per task), 0 = choose per
-    // call.  Measured on B200 (profiles/r2_null.md): the two-phase path wins up to K ~ 50 (tutorial, K = 26: 3.5x; K = 30: 1.7x, 7x on a
-    // 400k-SNP chromosome; K = 50: 1.3x), the windowed kernel from K ~ 100 on (its K*K*slabs tasks fill the GPU and it skips the
-    // pairs outside the distance window; the two-phase path pays per batch for K*K commit tasks)
+    // call.  Measured on B200 (profiles/r2_null.md): the two-phase path evaluates ALL chunk pairs and wins wherever a good share of
+    // them lies inside the distance window (tutorial, K = 26: 3.8x; 100k-SNP chromosomes: 2.0x at K = 30, 1.8x at K = 100, 2.4x at
+    // K = 150) and whenever K is small (K = 30, 400k SNPs: 6.9x -- few label pairs leave k_null_strict's task table shallow); the
+    // windowed kernel wins on long chromosomes with many labels (K = 100, 300k SNPs: 1.1x; K = 150, 1M SNPs: 2.2x), where it skips the
+    // ~90 % of pairs outside the window and its K*K*slabs tasks fill the GPU.
     bool two_phase = opt.null_impl == 2 && K <= 4096 && G < 65536;
-    if (opt.null_impl == 0 && G < 65536) two_phase = K <= 64;
+    if (opt.null_impl == 0 && K <= 4096 && G < 65536) {
+        // the share of chunk pairs inside the distance window, from the chromosomes' genetic lengths
+        double len_cm = 0;
+        for (int h = 0; h < pb.num_chrom; h++) {
+            const fgt_chrom_t &c = pb.chrom[h];
+            double cm = 0;
+            for (int i = 0; i + 1 < c.nsites; i++) cm += (c.pos[i + 1] - c.pos[i]) * c.rate[i] * 100.0;
+            len_cm += cm / pb.num_chrom;
+        }
+        const double window = (pb.grid_start + G) * pb.binwidth;
+        const double in_window = len_cm > 0 ? std::min(1.0, 2.0 * window / len_cm) : 1.0;
+        two_phase = !(K >= 100 && in_window < 0.3);
+    }
     std::vector<double> own_init;
     const double *init_src = out;
     if (null_world > 1) {

@@ -2286,7 +2286,7 @@ constexpr int kNullStageB = 2048;      // most chunks of B staged in shared memo
 constexpr int kNullMaxRanges = 64;     // most bin ranges of one label pair (shared-memory counters per warp)
 
 __device__ __forceinline__ NullStep null_eval_pair(const NullEvalArgs &a, const Chunk &A, double posB, double halfB, double wB, int cell0,
-                                                    unsigned magic, int w, bool valid) {
+                                                    unsigned magic, int w, int koff, bool valid) {
     NullStep o;
     o.key = ~0u; o.cell = -1; o.local = 0; o.val = 0.0;
     if (!valid) return o;
@@ -2307,7 +2307,7 @@ __device__ __forceinline__ NullStep null_eval_pair(const NullEvalArgs &a, const 
     const double mind = __dadd_rn(__dmul_rn(A.size, 0.5), halfB);           // reference C:1019-1020
     if (ok && (unsigned)bb < (unsigned)a.G && dist >= mind) {
         const int r = magic ? (int)__umulhi((unsigned)bb, magic) : bb;      // bb / w (exact below 2^16; magic 0: w = 1)
-        o.key = (unsigned)r;
+        o.key = (unsigned)(koff + r);
         o.local = bb - r * w;
         o.cell = cell0 + bb;
         o.val = __dmul_rn(A.w, wB);
@@ -2320,7 +2320,10 @@ __device__ __forceinline__ NullStep null_eval_pair(const NullEvalArgs &a, const 
 // takes the labels of B one after the other: the chunk pairs of one (label of A, label of B) are numbered q = i * |B group| + j
 // and handed to the lanes 32 at a time (all lanes busy however small the groups are), so that at any time a warp writes to
 // the few record regions of ONE label pair -- their sectors fill up and leave L2 whole.
-template <bool SCATTER>
+// BLOCKS (small label groups, large K): the labels of B are taken in blocks of consecutive labels with at most 32 bin ranges
+// between them, so that a step of 32 pairs is full even when a label group holds a handful of chunks; the lanes then look up
+// their own label's plan.
+template <bool SCATTER, bool BLOCKS>
 __global__ void __launch_bounds__(32 * kNullWarps) k_null_eval(const NullEvalArgs a) {
     extern __shared__ __align__(16) unsigned char nev_sm[];
     const int cap = a.stage_cap;
@@ -2329,6 +2332,8 @@ __global__ void __launch_bounds__(32 * kNullWarps) k_null_eval(const NullEvalArg
     int32_t *ctl = reinterpret_cast<int32_t *>(sBw + cap);                    // [0] tile, [1] next label
     int32_t *cnt = ctl + 4 + warp_id() * kNullMaxRanges;
     const int K = a.K;
+    uint2 *prow = reinterpret_cast<uint2 *>(ctl + 4 + kNullWarps * kNullMaxRanges) + (size_t)warp_id() * K;   // BLOCKS: the row's plan, packed
+    uint16_t *sBlab = reinterpret_cast<uint16_t *>(reinterpret_cast<uint2 *>(ctl + 4 + kNullWarps * kNullMaxRanges) + (size_t)kNullWarps * K);   // BLOCKS: [cap]
     const int lane = lane_id();
     const unsigned lt = (1u << lane) - 1;
     const long long NT = a.n_tasks;
@@ -2352,6 +2357,7 @@ __global__ void __launch_bounds__(32 * kNullWarps) k_null_eval(const NullEvalArg
                 const Chunk B = ldg_chunk(CB + j);
                 sBph[j] = make_double2(B.pos, __dmul_rn(B.size, 0.5));
                 sBw[j] = B.w;
+                if (BLOCKS) sBlab[j] = (uint16_t)(B.pop - 1);
             }
         }
         __syncthreads();
@@ -2372,12 +2378,25 @@ __global__ void __launch_bounds__(32 * kNullWarps) k_null_eval(const NullEvalArg
             }
             const Chunk *CA = a.chunks + a.hap_base[hh.x] + a0;
             const NullPairPlan *row = a.plan + (size_t)la * K;
-            const int task0 = a.rows[la].task0;
+            const NullRowPlan rpl = a.rows[la];
+            const int task0 = rpl.task0;
             int32_t *grow = (SCATTER ? const_cast<int32_t *>(a.offs) : a.counts) + (size_t)tile * NT + task0;   // [tile][task]
-            for (int lb = 0; lb < K; lb++) {
+            int blk0 = 0, nblk = K;
+            if (BLOCKS) {
+                blk0 = a.blk_start[la]; nblk = a.blk_start[la + 1] - blk0;
+                __syncwarp();
+                for (int lb = lane; lb < K; lb += 32) {
+                    const NullPairPlan pp = row[lb];
+                    prow[lb] = make_uint2(pp.magic, (unsigned)pp.tb0 | ((unsigned)pp.w << 16));
+                }
+                __syncwarp();
+            }
+            for (int bi = 0; bi < nblk; bi++) {
+                int lb = bi, lb1 = bi + 1;
+                if (BLOCKS) { const int2 bk = a.blk[blk0 + bi]; lb = bk.x; lb1 = bk.y; }
                 const NullPairPlan pp = row[lb];
-                const int b0 = oB[lb], cntB = oB[lb + 1] - b0;
-                const int nr = (a.G + pp.w - 1) / pp.w;
+                const int b0 = oB[lb], cntB = oB[lb1] - b0;              // chunks of B in this label (block of labels)
+                const int nr = BLOCKS ? ((lb1 < K ? row[lb1].tb0 : rpl.ntb) - pp.tb0) : (a.G + pp.w - 1) / pp.w;
                 int32_t *gcnt = grow + pp.tb0;
                 __syncwarp();
                 for (int t = lane; t < nr; t += 32) cnt[t] = (SCATTER && cntB > 0) ? gcnt[t] : 0;
@@ -2385,8 +2404,8 @@ __global__ void __launch_bounds__(32 * kNullWarps) k_null_eval(const NullEvalArg
                 if (cntB > 0) {
                     const int npairs = cntA * cntB;
                     const unsigned bmagic = cntB > 1 ? (unsigned)((0x100000000ULL + cntB - 1) / cntB) : 0u;   // q / cntB for q < 2^16 ...
-                    const bool small = npairs < 65536;                                                         // ... else a real division
-                    const int cell0 = (la * K + lb) * a.G;
+                    const bool small = npairs < 65536 && cntB < 65536;                                          // ... else a real division
+                    const int cell0u = (la * K + lb) * a.G;
                     for (int q0 = 0; q0 < npairs; q0 += 64) {
                         NullStep e[2];
 #pragma unroll
@@ -2400,9 +2419,18 @@ __global__ void __launch_bounds__(32 * kNullWarps) k_null_eval(const NullEvalArg
                             }
                             const Chunk A = ldg_chunk(CA + i);
                             double posB, halfB, wB;
-                            if (staged) { const double2 ph = sBph[b0 + j]; posB = ph.x; halfB = ph.y; wB = sBw[b0 + j]; }
-                            else { const Chunk B = ldg_chunk(CB + b0 + j); posB = B.pos; halfB = __dmul_rn(B.size, 0.5); wB = B.w; }
-                            e[h] = null_eval_pair(a, A, posB, halfB, wB, cell0, pp.magic, pp.w, valid);
+                            int labB = lb;
+                            if (staged) {
+                                const double2 ph = sBph[b0 + j]; posB = ph.x; halfB = ph.y; wB = sBw[b0 + j];
+                                if (BLOCKS) labB = sBlab[b0 + j];
+                            } else {
+                                const Chunk B = ldg_chunk(CB + b0 + j); posB = B.pos; halfB = __dmul_rn(B.size, 0.5); wB = B.w;
+                                if (BLOCKS) labB = B.pop - 1;
+                            }
+                            if (BLOCKS) {
+                                const uint2 pl = prow[labB];
+                                e[h] = null_eval_pair(a, A, posB, halfB, wB, (la * K + labB) * a.G, pl.x, (int)(pl.y >> 16), (int)(pl.y & 0xffffu) - pp.tb0, valid);
+                            } else e[h] = null_eval_pair(a, A, posB, halfB, wB, cell0u, pp.magic, pp.w, 0, valid);
                         }
 #pragma unroll
                         for (int h = 0; h < 2; h++) {
@@ -2467,8 +2495,9 @@ __global__ void k_null_dir(const int32_t *__restrict__ offs, const int32_t *__re
 
 int null_stage_cap(int max_chunks) { return std::min(kNullStageB, (max_chunks + 7) & ~7); }
 size_t null_eval_smem(int K, int max_tb, int stage_cap) {
-    (void)K; (void)max_tb;
-    return (size_t)stage_cap * (sizeof(double2) + sizeof(double)) + 16 + (size_t)kNullWarps * kNullMaxRanges * sizeof(int32_t);
+    (void)max_tb;       // blocks: + the packed plan of a row per warp and the staged labels of B
+    return (size_t)stage_cap * (sizeof(double2) + sizeof(double)) + 16 + (size_t)kNullWarps * kNullMaxRanges * sizeof(int32_t) +
+           (size_t)kNullWarps * K * sizeof(uint2) + (size_t)stage_cap * sizeof(uint16_t);
 }
 void launch_null_eval(const NullEvalArgs &a, bool scatter, cudaStream_t st) {
     if (a.n_tiles <= 0 || a.n_own <= 0) return;
@@ -2477,15 +2506,22 @@ void launch_null_eval(const NullEvalArgs &a, bool scatter, cudaStream_t st) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_set[dev & 63]) {
-        cudaFuncSetAttribute(k_null_eval<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(k_null_eval<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_null_eval<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_null_eval<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_null_eval<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_null_eval<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set[dev & 63] = true;
     }
     long long per_sm = std::max<long long>(1, std::min<long long>(2048 / (32 * kNullWarps), (227 * 1024) / (long long)(smem + 1024)));
     if (a.max_ctas_per_sm > 0) per_sm = std::min<long long>(per_sm, a.max_ctas_per_sm);
     const unsigned grid = (unsigned)std::min<long long>((long long)a.n_tiles * a.la_groups, 148 * per_sm);
-    if (scatter) k_null_eval<true><<<grid, 32 * kNullWarps, smem, st>>>(a);
-    else k_null_eval<false><<<grid, 32 * kNullWarps, smem, st>>>(a);
+    if (a.blk) {
+        if (scatter) k_null_eval<true, true><<<grid, 32 * kNullWarps, smem, st>>>(a);
+        else k_null_eval<false, true><<<grid, 32 * kNullWarps, smem, st>>>(a);
+    } else {
+        if (scatter) k_null_eval<true, false><<<grid, 32 * kNullWarps, smem, st>>>(a);
+        else k_null_eval<false, false><<<grid, 32 * kNullWarps, smem, st>>>(a);
+    }
 }
 
 void launch_null_dir(const int32_t *offs, const int32_t *perm, int n_tasks, long long T, RegionEnt *dir, cudaStream_t st) {

@@ -205,6 +205,8 @@ struct NullEvalArgs {
     double bw, half_bw, inv_bw;
     const NullPairPlan *plan;     // [K][K]
     const NullRowPlan *rows;      // [K]
+    const int32_t *blk_start;     // blocks of B labels (small label groups): row la takes blk[blk_start[la] .. blk_start[la+1])
+    const int2 *blk;              // (first label, label behind the last) of a block: at most 32 bin ranges; NULL = one label at a time
     int32_t max_tb;               // largest ntb (shared-memory counters per warp)
     int32_t stage_cap;            // null_stage_cap(most labelled chunks of a haplotype)
     int32_t n_tasks;              // tasks of this engine (natural numbering: rows of A in label order)

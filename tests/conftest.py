@@ -52,16 +52,21 @@ def each_encoding(lib, request):
     lib.encode = "rle"
 
 
-@pytest.fixture(params=["windowed", "two_phase", "two_phase_batched"])
+@pytest.fixture(params=["windowed", "two_phase", "two_phase_batched", "two_phase_blocks"])
 def each_null_impl(lib, request):
     """run a NULL test with k_null_strict (null_impl 1), with the two-phase path (null_impl 2: every chunk pair evaluated once
-    into records, ordered commit), and with the two-phase path forced into many small batches and many narrow commit tasks"""
+    into records, ordered commit), with the two-phase path forced into many small batches and many narrow commit tasks, and with
+    the labels of B taken in blocks (the large-K variant of phase 1)"""
     lib.set_option("null_impl", 1 if request.param == "windowed" else 2)
     if request.param == "two_phase_batched":
         lib.set_option("null_batch", 3000)
         lib.set_option("null_tasks", 100000)
+    lib.set_option("null_block", {"two_phase": 0, "two_phase_blocks": 1}.get(request.param, -1))
+    if request.param == "two_phase_blocks":
+        lib.set_option("null_tasks", 400)          # label pairs with one and with several bin ranges inside a block
     yield request.param
     lib.set_option("null_impl", 0)
+    lib.set_option("null_block", -1)
     lib.set_option("null_batch", 0)
     lib.set_option("null_tasks", 0)
 
