@@ -89,6 +89,8 @@ int Engine::set_option(const char *key, double v) {
     else if (k == "null_tasks") opt.null_tasks = iv;
     else if (k == "null_overlap") opt.null_overlap = iv;
     else if (k == "null_block") opt.null_block = iv;
+    else if (k == "null_kernel") opt.null_kernel = iv;
+    else if (k == "null_window") opt.null_window = iv;
     else if (k == "null_world") opt.null_world = std::max(1, iv);
     else if (k == "null_rank") opt.null_rank = std::max(0, iv);
     else if (k == "project_impl") opt.project_impl = iv;
@@ -128,6 +130,8 @@ double Engine::get_option(const char *key) {
     if (k == "null_tasks") return opt.null_tasks;
     if (k == "null_overlap") return opt.null_overlap;
     if (k == "null_block") return opt.null_block;
+    if (k == "null_kernel") return opt.null_kernel;
+    if (k == "null_window") return opt.null_window;
     if (k == "null_world") return opt.null_world;
     if (k == "null_rank") return opt.null_rank;
     if (k == "project_impl") return opt.project_impl;
@@ -1820,7 +1824,7 @@ static inline bool null_owner(bool two_phase, int la, int lb, int world, int ran
 // Two-phase NULL accumulation of one chromosome (kernels.cu, "NULL path, two phases"): plan the commit tasks from the per-haplotype
 // label counts, then per batch of haplotype pairs: count, scan, scatter, ordered commit.
 int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::vector<int32_t> &laboff, int Nc, int null_world, int null_rank,
-                           double *d_out, unsigned long long *d_acc, fgt_stats_t &stx) {
+                           double *d_out, unsigned long long *d_acc, fgt_stats_t &stx, double in_window) {
     const int K = pb.num_donors, G = pb.num_bins, P = pb.ploidy, NH = Nc * P;
     auto cl = [&](int hp, int l) { return (long long)(laboff[(size_t)hp * (K + 2) + l + 1] - laboff[(size_t)hp * (K + 2) + l]); };
     std::vector<int32_t> own;
@@ -1915,9 +1919,15 @@ int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::v
         free_b += d_draws_.cap + d_recs_.cap;
         mem_budget_bytes_ = std::min((double)free_b * 0.6, 64e9);
     }
-    long long batch_evals = opt.null_batch > 0 ? (long long)opt.null_batch : (long long)std::min(1.5e9, mem_budget_bytes_ * 0.8 / sizeof(UpdateRec));
+    // Batches are sized by the records they are EXPECTED to produce (the chunk pairs times the share inside the distance window, with
+    // a margin); the counting pass then tells the exact number before the record buffer is sized, and a batch that would not fit
+    // 32-bit offsets is halved and counted again.
+    const double est_frac = std::max(0.05, std::min(1.0, in_window * 1.3 + 0.02));
+    for (long long &b : bound) b = std::max<long long>(1, (long long)std::ceil((double)b * est_frac));
+    long long batch_evals = opt.null_batch > 0 ? (long long)opt.null_batch : (long long)std::min(1.2e9, mem_budget_bytes_ * 0.8 / sizeof(UpdateRec));
     long long max_bound = 0, total_bound = 0;
     for (long long b : bound) { max_bound = std::max(max_bound, b); total_bound += b; }
+    if (!null_pin_ && cudaHostAlloc((void **)&null_pin_, 64, cudaHostAllocDefault) != cudaSuccess) return FGT_ERR_CUDA;
     {   // equal batches instead of full ones and a remainder (every batch pays for a pass over all commit tasks)
         const long long nbat = (total_bound + batch_evals - 1) / batch_evals;
         batch_evals = std::min(batch_evals, (total_bound + nbat - 1) / nbat + max_bound);
@@ -1956,7 +1966,11 @@ int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::v
     long long most = 1, all_lab = 0;
     for (long long c : nlab) { most = std::max(most, c); all_lab += c; }
     // small label groups (large K): the labels of B in blocks of consecutive labels holding at most 32 bin ranges
-    const bool blocks = opt.null_block >= 0 ? opt.null_block != 0 : (double)all_lab / NH / K < 24.0;
+    const bool window_on = opt.null_kernel == 2 && (opt.null_window >= 0 ? (opt.null_window != 0) : (in_window < 0.9));
+    const double group = (double)all_lab / NH / K;           // chunks of one label on a haplotype, on average
+    // (the windowed enumeration works one label at a time: with half the pairs outside the window it beats the blocks down to ~12
+    // chunks per group -- K = 100, 300k SNPs: 435 ms against 994 ms in blocks and 888 ms for k_null_strict)
+    const bool blocks = opt.null_block >= 0 ? opt.null_block != 0 : (group < 24.0 && !(window_on && group >= 12.0));
     if (blocks) {
         std::vector<int32_t> bstart(K + 1, 0);
         std::vector<int2> blk;
@@ -1984,6 +1998,11 @@ int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::v
     if (null_eval_smem(K, max_tb, ea.stage_cap) > 200 * 1024) ea.stage_cap = 0;          // many labels: B is read through L1 instead
     if (null_eval_smem(K, max_tb, ea.stage_cap) > 200 * 1024) return FGT_ERR_ARG;
     ea.tile_counter = d_ctr + 1;
+    if (opt.null_kernel == 2) {
+        ea.unit_counter = reinterpret_cast<unsigned long long *>(d_ctr + 8);
+        ea.window = window_on ? 1 : 0;
+        ea.dwin = (pb.grid_start + G + 1) * pb.binwidth;
+    }
     // Two lanes of batches: batch b is folded on the commit stream while batch b+1 is counted and scattered on the evaluation
     // stream (the two kinds of kernel stall on different things); both persistent grids are capped so that they fit an SM together.
     const bool overlap = opt.null_overlap != 0;
@@ -1998,29 +2017,44 @@ int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::v
     size_t t0 = 0;
     int nb = 0;
     bool lane_used[2] = {false, false};
+    size_t forced_t1 = 0;                            // a batch that overflowed is retried up to here
     while (t0 < tiles.size()) {
         size_t t1 = t0;
         long long sum = 0;
-        while (t1 < tiles.size() && (t1 == t0 || (sum + bound[t1] <= batch_evals && (long long)(t1 - t0) < max_tiles))) sum += bound[t1++];
+        while (t1 < tiles.size() && (t1 == t0 || (sum + bound[t1] <= batch_evals && (long long)(t1 - t0) < max_tiles)) && (!forced_t1 || t1 < forced_t1))
+            sum += bound[t1++];
+        forced_t1 = 0;
         const int ln = overlap ? (nb & 1) : 0;
         const long long T = (long long)(t1 - t0);
         const long long n_cnt = (long long)n_tasks * T;
         int32_t *d_cnt = (ln ? d_ncnt2_ : d_ncnt_).as<int32_t>((size_t)n_cnt + 1 + 2 * ((size_t)n_cnt / 1024 + 2));
         int32_t *d_off = (ln ? d_noff2_ : d_noff_).as<int32_t>((size_t)n_cnt + 1);
         RegionEnt *d_dir = (ln ? d_ndir2_ : d_ndir_).as<RegionEnt>(tab.size());
-        UpdateRec *d_recs = (ln ? d_recs2_ : d_recs_).as<UpdateRec>((size_t)sum + 2);
-        if (!d_cnt || !d_off || !d_recs || !d_dir) return FGT_ERR_CUDA;
+        if (!d_cnt || !d_off || !d_dir) return FGT_ERR_CUDA;
         ea.tiles = d_tiles + t0; ea.n_tiles = (int)T;
         ea.la_groups = (int)std::max<long long>(1, std::min<long long>((long long)own.size(), (148 * 8 + T - 1) / T));
-        ea.recs = d_recs;
         // counts per (tile, task) -> [task][tile] -> exclusive scan = first record of every (task, tile) -> back to [tile][task]
         CK(cudaMemsetAsync(d_ctr + 1, 0, sizeof(int), st_));
-        ea.counts = d_cnt; ea.offs = nullptr;
+        CK(cudaMemsetAsync(d_ctr + 8, 0, 2 * sizeof(unsigned long long), st_));
+        ea.counts = d_cnt; ea.offs = nullptr; ea.recs = nullptr;
         launch_null_eval(ea, false, st_);
+        launch_sum_i32(d_cnt, n_cnt, reinterpret_cast<unsigned long long *>(d_ctr + 10), st_);
+        CK(cudaMemcpyAsync(null_pin_, d_ctr + 10, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st_));
+        CK(cudaStreamSynchronize(st_));
+        const unsigned long long n_recs = *null_pin_;
+        if (n_recs >= (1ULL << 31) - 64) {           // the estimate was too low for this batch: half of it, counted again
+            if (T <= 1) return FGT_ERR_ARG;
+            forced_t1 = t0 + (size_t)(T / 2);
+            continue;
+        }
+        UpdateRec *d_recs = (ln ? d_recs2_ : d_recs_).as<UpdateRec>((size_t)std::max<unsigned long long>(n_recs, (unsigned long long)std::min<long long>(sum, batch_evals)) + 2);
+        if (!d_recs) return FGT_ERR_CUDA;
+        ea.recs = d_recs;
         launch_transpose_i32(d_cnt, T, n_tasks, d_off, st_);
         launch_exclusive_scan_i32_large(d_off, d_cnt, n_cnt, d_cnt + n_cnt + 1, st_);
         launch_transpose_i32(d_cnt, n_tasks, T, d_off, st_);
         CK(cudaMemsetAsync(d_ctr + 1, 0, sizeof(int), st_));
+        CK(cudaMemsetAsync(d_ctr + 8, 0, sizeof(unsigned long long), st_));
         ea.counts = nullptr; ea.offs = d_off;
         if (overlap && lane_used[ln]) CK(cudaStreamWaitEvent(st_, null_ev_[ln], 0));     // the lane's records and directory are free again
         launch_null_eval(ea, true, st_);
@@ -2087,26 +2121,24 @@ int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_ro
     CK(cudaMemcpyAsync(d_rowmap, rowmap.data(), n_haps * sizeof(int32_t), cudaMemcpyHostToDevice, st_));
     double *d_out = d_tensor_.as<double>((size_t)K * K * G);
     if (!d_out) return FGT_ERR_CUDA;
-    // null_impl: 2 = two phases (every chunk pair evaluated once), 1 = k_null_strict (windowed enumeration per task), 0 = choose per
-    // call.  Measured on B200 (profiles/r2_null.md): the two-phase path evaluates ALL chunk pairs and wins wherever a good share of
-    // them lies inside the distance window (tutorial, K = 26: 3.8x; 100k-SNP chromosomes: 2.0x at K = 30, 1.8x at K = 100, 2.4x at
-    // K = 150) and whenever K is small (K = 30, 400k SNPs: 6.9x -- few label pairs leave k_null_strict's task table shallow); the
-    // windowed kernel wins on long chromosomes with many labels (K = 100, 300k SNPs: 1.1x; K = 150, 1M SNPs: 2.2x), where it skips the
-    // ~90 % of pairs outside the window and its K*K*slabs tasks fill the GPU.
+    // null_impl: 2 = two phases (every chunk pair evaluated once), 1 = k_null_strict (round 1: one warp per label pair and slab walks all
+    // haplotype pairs), 0 = two phases whenever its tables allow (K <= 4096, G < 65536).  Measured on B200 (profiles/r2_null.md), two
+    // phases against k_null_strict: tutorial 3.9x, K = 30 2.0x (100k SNPs) / 26x (400k), K = 100 1.8x / 2.2x (300k), K = 150 2.5x /
+    // 3.2x (1M SNPs): with the windowed enumeration and batches sized by expected records it wins on every shape tried.
     bool two_phase = opt.null_impl == 2 && K <= 4096 && G < 65536;
-    if (opt.null_impl == 0 && K <= 4096 && G < 65536) {
-        // the share of chunk pairs inside the distance window, from the chromosomes' genetic lengths
-        double len_cm = 0;
-        for (int h = 0; h < pb.num_chrom; h++) {
-            const fgt_chrom_t &c = pb.chrom[h];
-            double cm = 0;
-            for (int i = 0; i + 1 < c.nsites; i++) cm += (c.pos[i + 1] - c.pos[i]) * c.rate[i] * 100.0;
-            len_cm += cm / pb.num_chrom;
-        }
+    // the share of chunk pairs inside the distance window, from the chromosomes' genetic lengths
+    std::vector<double> in_window(pb.num_chrom, 1.0);
+    double mean_in_window = 0;
+    for (int h = 0; h < pb.num_chrom; h++) {
+        const fgt_chrom_t &c = pb.chrom[h];
+        double cm = 0;
+        if (c.pos && c.rate) for (int i = 0; i + 1 < c.nsites; i++) cm += (c.pos[i + 1] - c.pos[i]) * c.rate[i] * 100.0;
         const double window = (pb.grid_start + G) * pb.binwidth;
-        const double in_window = len_cm > 0 ? std::min(1.0, 2.0 * window / len_cm) : 1.0;
-        two_phase = !(K >= 100 && in_window < 0.3);
+        in_window[h] = cm > 0 ? std::min(1.0, 2.0 * window / cm) : 1.0;
+        mean_in_window += in_window[h] / pb.num_chrom;
     }
+    if (opt.null_impl == 0 && K <= 4096 && G < 65536) two_phase = true;
+    (void)mean_in_window;
     std::vector<double> own_init;
     const double *init_src = out;
     if (null_world > 1) {
@@ -2140,7 +2172,7 @@ int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_ro
             CK(cudaStreamSynchronize(st_));
             vtick("null: chunks grouped, label counts on the host");
             if (two_phase) {
-                rc = null_two_phase(pb, cs, laboff, Nc, null_world, null_rank, d_out, d_acc, stx);
+                rc = null_two_phase(pb, cs, laboff, Nc, null_world, null_rank, d_out, d_acc, stx, in_window[h]);
                 if (rc) return rc;
             } else {
             std::vector<double> cnt_mean(K, 0.0);

@@ -56,10 +56,12 @@ struct Options {
     int null_target = 0;    // NULL task table: accepted pairs per (haplotype pair, slab) a task aims at; 0 = default
     int commit_ctas = 0;    // > 0: cap of the commit kernel's persistent CTAs per SM (room for the next range's evaluation kernel)
     int null_impl = 0;      // NULL path: 2 = two phases (every chunk pair evaluated once into records, ordered commit), 1 = k_null_strict,
-                            // 0 = two phases unless K >= 100 and under 30 % of the chunk pairs lie inside the distance window
+                            // 0 = two phases whenever its tables allow (K <= 4096, G < 65536)
     double null_batch = 0;  // null_impl 2: chunk-pair evaluations per batch of haplotype pairs (0 = from free device memory)
     int null_tasks = 0;     // null_impl 2: commit tasks aimed at (0 = default)
     int null_block = -1;    // null_impl 2: take the labels of B in blocks (small label groups); -1 = when a label group averages < 24 chunks
+    int null_kernel = 2;    // null_impl 2, phase 1: 2 = warps on their own (per-warp staging, optional windowed enumeration), 1 = CTA-wide staging of B
+    int null_window = -1;   // null_kernel 2: windowed enumeration; -1 = when under 90 % of the chunk pairs lie inside the distance window
     int null_overlap = 1;   // null_impl 2: fold batch b on the commit stream while batch b+1 is evaluated (two record buffers)
     int null_world = 1, null_rank = 0;   // sharded NULL run: this rank folds the label pairs it owns (sum of the ranks = exact)
     int spec_rand = 1;      // generate the first batch's draws while the chunk/bin kernels run
@@ -168,9 +170,10 @@ class Engine {
     std::vector<ChromState> chroms_;
     ChromState null_cs_;              // NULL path: chunk buffers of the chromosome being folded
     DevBuf d_ntiles_, d_nown_, d_nplan_, d_nrows_, d_nperm_, d_ntab_, d_ncnt_, d_noff_, d_ndir_, d_ncnt2_, d_noff2_, d_ndir2_, d_nblk_, d_nblks_;   // two-phase NULL path (two lanes of batches)
+    unsigned long long *null_pin_ = nullptr;      // pinned: the record total of a batch
     cudaEvent_t null_ev_[3] = {nullptr, nullptr, nullptr};   // commit of lane 0 / lane 1 done, evaluation side ready
     int null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::vector<int32_t> &laboff, int Nc, int null_world, int null_rank,
-                       double *d_out, unsigned long long *d_acc, fgt_stats_t &stx);
+                       double *d_out, unsigned long long *d_acc, fgt_stats_t &stx, double in_window);
     std::vector<double> raw_host_;
     int64_t raw_count_ = 0;
     int launches_ = 0;

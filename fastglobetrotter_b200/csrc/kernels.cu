@@ -2463,6 +2463,208 @@ __global__ void __launch_bounds__(32 * kNullWarps) k_null_eval(const NullEvalArg
     }
 }
 
+// ---- phase 1, second form (null_kernel = 2): every warp on its own -------------------------------------------------------
+// A warp claims (haplotype pair, label of A) units from one global counter (no CTA barrier, no idle warps at the end of a
+// haplotype pair) and stages what it needs in ITS OWN slice of shared memory: the chunks of A with that label once per unit, the
+// chunks of the current label (block of labels) of B once per label pair -- a 1/|A group| overhead that removes the limit on the
+// haplotype length (the CTA-wide staging above falls back to global loads beyond 2048 chunks: every long chromosome of real data).
+// Optional windowed enumeration (one label of B at a time): every lane bisects, for its A chunk, the index range of the position-sorted
+// B group within the largest distance the grid holds; a warp scan numbers the candidates of 32 A chunks in (i, j) order and the
+// steps take 32 candidates each -- on chromosomes much longer than the window most chunk pairs are never touched.
+constexpr int kNullGrp = 128;                               // chunks of a group staged per warp (larger groups: global loads)
+constexpr int kNullWarpBytes = kNullGrp * (16 + 8) * 2 + kNullMaxRanges * 4 + kNullGrp * 2;   // B, A, counters, labels of B
+
+template <bool SCATTER>
+__device__ __forceinline__ void null_file(const NullEvalArgs &a, int32_t *cnt, const NullStep &e, int nr, unsigned lt, int lane) {
+    const bool acc = e.key != ~0u;
+    if (!SCATTER) {
+        if (acc) atomicAdd(&cnt[e.key], 1);
+    } else {
+        // stable rank inside the step: the lanes of the same bin range, in lane order (= (i, j) order)
+        if (!__any_sync(kFull, acc)) return;
+        const unsigned M = nr > 1 ? __match_any_sync(kFull, e.key) : __ballot_sync(kFull, acc);
+        const int first = __ffs(M) - 1;
+        int base = 0;
+        if (acc && lane == first) base = atomicAdd(&cnt[e.key], __popc(M));   // one lane per range of the step
+        base = __shfl_sync(kFull, base, first);
+        if (acc) {
+            UpdateRec rec;
+            rec.cell = e.cell; rec.pad = e.local; rec.val = e.val;
+            a.recs[base + __popc(M & lt)] = rec;
+        }
+    }
+}
+
+template <bool SCATTER, bool BLOCKS>
+__global__ void __launch_bounds__(32 * kNullWarps) k_null_eval2(const NullEvalArgs a) {
+    extern __shared__ __align__(16) unsigned char nev2_sm[];
+    unsigned char *wb = nev2_sm + (size_t)warp_id() * kNullWarpBytes;
+    double2 *sBph = reinterpret_cast<double2 *>(wb);                                      // [kNullGrp] (position, half size)
+    double2 *sAph = sBph + kNullGrp;
+    double *sBw = reinterpret_cast<double *>(sAph + kNullGrp);
+    double *sAw = sBw + kNullGrp;
+    int32_t *cnt = reinterpret_cast<int32_t *>(sAw + kNullGrp);
+    uint16_t *sBlab = reinterpret_cast<uint16_t *>(cnt + kNullMaxRanges);
+    const int K = a.K;
+    uint2 *prow = reinterpret_cast<uint2 *>(nev2_sm + (size_t)kNullWarps * kNullWarpBytes) + (size_t)warp_id() * K;   // BLOCKS
+    const int lane = lane_id();
+    const unsigned lt = (1u << lane) - 1;
+    const long long NT = a.n_tasks;
+    const long long n_units = (long long)a.n_tiles * a.n_own;
+    while (true) {
+        long long unit = 0;
+        if (lane == 0) unit = atomicAdd(a.unit_counter, 1ULL);
+        unit = __shfl_sync(kFull, unit, 0);
+        if (unit >= n_units) break;
+        const int tile = (int)(unit / a.n_own);
+        const int la = a.own[unit - (long long)tile * a.n_own];
+        const int2 hh = a.tiles[tile];
+        const int32_t *oA = a.lab_off + (size_t)hh.x * (K + 2);
+        const int32_t *oB = a.lab_off + (size_t)hh.y * (K + 2);
+        const Chunk *CB = a.chunks + a.hap_base[hh.y];
+        const NullRowPlan rpl = a.rows[la];
+        int32_t *grow = (SCATTER ? const_cast<int32_t *>(a.offs) : a.counts) + (size_t)tile * NT + rpl.task0;   // [tile][task]
+        const int a0 = oA[la], cntA = oA[la + 1] - a0;
+        if (cntA <= 0 || oB[K] <= 0) {
+            if (!SCATTER) for (int t = lane; t < rpl.ntb; t += 32) grow[t] = 0;
+            continue;
+        }
+        const Chunk *CA = a.chunks + a.hap_base[hh.x] + a0;
+        const NullPairPlan *row = a.plan + (size_t)la * K;
+        const bool stagedA = cntA <= kNullGrp;
+        __syncwarp();
+        if (stagedA)
+            for (int i = lane; i < cntA; i += 32) {
+                const Chunk A = ldg_chunk(CA + i);
+                sAph[i] = make_double2(A.pos, __dmul_rn(A.size, 0.5)); sAw[i] = A.w;
+            }
+        int blk0 = 0, nblk = K;
+        if (BLOCKS) {
+            blk0 = a.blk_start[la]; nblk = a.blk_start[la + 1] - blk0;
+            for (int lb = lane; lb < K; lb += 32) {
+                const NullPairPlan pp = row[lb];
+                prow[lb] = make_uint2(pp.magic, (unsigned)pp.tb0 | ((unsigned)pp.w << 16));
+            }
+        }
+        for (int bi = 0; bi < nblk; bi++) {
+            int lb = bi, lb1 = bi + 1;
+            if (BLOCKS) { const int2 bk = a.blk[blk0 + bi]; lb = bk.x; lb1 = bk.y; }
+            const NullPairPlan pp = row[lb];
+            const int b0 = oB[lb], cntB = oB[lb1] - b0;              // chunks of B in this label (block of labels)
+            const int nr = BLOCKS ? ((lb1 < K ? row[lb1].tb0 : rpl.ntb) - pp.tb0) : (a.G + pp.w - 1) / pp.w;
+            int32_t *gcnt = grow + pp.tb0;
+            const bool stagedB = cntB <= kNullGrp;
+            __syncwarp();                                            // the previous label's steps are done with the staged group
+            for (int t = lane; t < nr; t += 32) cnt[t] = (SCATTER && cntB > 0) ? gcnt[t] : 0;
+            if (stagedB)
+                for (int j = lane; j < cntB; j += 32) {
+                    const Chunk B = ldg_chunk(CB + b0 + j);
+                    sBph[j] = make_double2(B.pos, __dmul_rn(B.size, 0.5)); sBw[j] = B.w;
+                    if (BLOCKS) sBlab[j] = (uint16_t)(B.pop - 1);
+                }
+            __syncwarp();
+            if (cntB > 0) {
+                const int cell0u = (la * K + lb) * a.G;
+                auto eval = [&](int i, int j, bool valid) -> NullStep {
+                    Chunk A;                                          // (pos, size, w) of A as eval needs them: size = 2 * half
+                    double halfA;
+                    if (stagedA) { const double2 ph = sAph[i]; A.pos = ph.x; halfA = ph.y; A.w = sAw[i]; }
+                    else { const Chunk g = ldg_chunk(CA + i); A.pos = g.pos; halfA = __dmul_rn(g.size, 0.5); A.w = g.w; }
+                    A.size = __dadd_rn(halfA, halfA);                 // exact: null_eval_pair halves it again
+                    double posB, halfB, wB;
+                    int labB = lb;
+                    if (stagedB) {
+                        const double2 ph = sBph[j]; posB = ph.x; halfB = ph.y; wB = sBw[j];
+                        if (BLOCKS) labB = sBlab[j];
+                    } else {
+                        const Chunk B = ldg_chunk(CB + b0 + j); posB = B.pos; halfB = __dmul_rn(B.size, 0.5); wB = B.w;
+                        if (BLOCKS) labB = B.pop - 1;
+                    }
+                    if (BLOCKS) {
+                        const uint2 pl = prow[labB];
+                        return null_eval_pair(a, A, posB, halfB, wB, (la * K + labB) * a.G, pl.x, (int)(pl.y >> 16), (int)(pl.y & 0xffffu) - pp.tb0, valid);
+                    }
+                    return null_eval_pair(a, A, posB, halfB, wB, cell0u, pp.magic, pp.w, 0, valid);
+                };
+                if (!BLOCKS && a.window && stagedA && stagedB) {
+                    // windowed enumeration: 32 A chunks at a time, every lane the index range of B within the largest distance of the grid
+                    for (int i0 = 0; i0 < cntA; i0 += 32) {
+                        const int i = i0 + lane;
+                        int lo = 0, n = 0;
+                        if (i < cntA) {
+                            const double xa = sAph[i].x;
+                            const double x0 = xa - a.dwin, x1 = xa + a.dwin;
+                            int l = 0, h = cntB;
+                            while (l < h) { const int m = (l + h) >> 1; if (sBph[m].x < x0) l = m + 1; else h = m; }
+                            lo = l; h = cntB;
+                            while (l < h) { const int m = (l + h) >> 1; if (sBph[m].x <= x1) l = m + 1; else h = m; }
+                            n = l - lo;
+                        }
+                        int incl = n;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int y = __shfl_up_sync(kFull, incl, o);
+                            if (lane >= o) incl += y;
+                        }
+                        const int T = __shfl_sync(kFull, incl, 31);
+                        const int off = incl - n;
+                        for (int t0 = 0; t0 < T; t0 += 32) {
+                            const int t = t0 + lane;
+                            int u = 0;                                 // owner: the last lane whose first candidate is <= t
+#pragma unroll
+                            for (int sft = 16; sft >= 1; sft >>= 1) {
+                                const int c = u + sft;
+                                const int v = __shfl_sync(kFull, off, c & 31);
+                                if (c < 32 && v <= t) u = c;
+                            }
+                            const int lo_u = __shfl_sync(kFull, lo, u), off_u = __shfl_sync(kFull, off, u);
+                            const bool valid = t < T;
+                            const NullStep e = eval(valid ? i0 + u : 0, valid ? lo_u + (t - off_u) : 0, valid);
+                            null_file<SCATTER>(a, cnt, e, nr, lt, lane);
+                        }
+                    }
+                } else {
+                    const int npairs = cntA * cntB;
+                    const unsigned bmagic = cntB > 1 ? (unsigned)((0x100000000ULL + cntB - 1) / cntB) : 0u;   // q / cntB for q < 2^16 ...
+                    const bool small = npairs < 65536 && cntB < 65536;                                          // ... else a real division
+                    for (int q0 = 0; q0 < npairs; q0 += 64) {
+                        NullStep e[2];
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const int q = q0 + 32 * h + lane;
+                            const bool valid = q < npairs;
+                            int i = 0, j = 0;
+                            if (valid) {
+                                i = cntB == 1 ? q : (small ? (int)__umulhi((unsigned)q, bmagic) : q / cntB);
+                                j = q - i * cntB;
+                            }
+                            e[h] = eval(i, j, valid);
+                        }
+                        null_file<SCATTER>(a, cnt, e[0], nr, lt, lane);
+                        if (q0 + 32 < npairs) null_file<SCATTER>(a, cnt, e[1], nr, lt, lane);
+                    }
+                }
+            }
+            if (!SCATTER) {
+                __syncwarp();
+                for (int t = lane; t < nr; t += 32) gcnt[t] = cnt[t];
+            }
+        }
+    }
+}
+
+// sum of n int32 counts as a 64-bit total (the records of a batch, before its buffer is sized)
+__global__ void __launch_bounds__(256) k_sum_i32(const int32_t *__restrict__ in, long long n, unsigned long long *__restrict__ total) {
+    unsigned long long s = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) s += (unsigned long long)in[i];
+    s = warp_sum_u64(s);
+    if (lane_id() == 0 && s) atomicAdd(total, s);
+}
+void launch_sum_i32(const int32_t *in, long long n, unsigned long long *total, cudaStream_t st) {
+    if (n <= 0) return;
+    k_sum_i32<<<(unsigned)std::min<long long>((n + 255) / 256, 148 * 8), 256, 0, st>>>(in, n, total);
+}
+
 // [rows][cols] int32 -> [cols][rows]
 __global__ void __launch_bounds__(256) k_transpose_i32(const int32_t *__restrict__ in, long long rows, long long cols, int32_t *__restrict__ out) {
     __shared__ int32_t t[32][33];
@@ -2510,11 +2712,29 @@ void launch_null_eval(const NullEvalArgs &a, bool scatter, cudaStream_t st) {
         cudaFuncSetAttribute(k_null_eval<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(k_null_eval<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(k_null_eval<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_null_eval2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_null_eval2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_null_eval2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_null_eval2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set[dev & 63] = true;
     }
     long long per_sm = std::max<long long>(1, std::min<long long>(2048 / (32 * kNullWarps), (227 * 1024) / (long long)(smem + 1024)));
     if (a.max_ctas_per_sm > 0) per_sm = std::min<long long>(per_sm, a.max_ctas_per_sm);
     const unsigned grid = (unsigned)std::min<long long>((long long)a.n_tiles * a.la_groups, 148 * per_sm);
+    if (a.unit_counter) {                              // second form: warps on their own
+        const size_t smem2 = (size_t)kNullWarps * kNullWarpBytes + (a.blk ? (size_t)kNullWarps * a.K * sizeof(uint2) : 0);
+        long long ps = std::max<long long>(1, std::min<long long>(2048 / (32 * kNullWarps), (227 * 1024) / (long long)(smem2 + 1024)));
+        if (a.max_ctas_per_sm > 0) ps = std::min<long long>(ps, a.max_ctas_per_sm);
+        const unsigned g2 = (unsigned)std::min<long long>(((long long)a.n_tiles * a.n_own + kNullWarps - 1) / kNullWarps, 148 * ps);
+        if (a.blk) {
+            if (scatter) k_null_eval2<true, true><<<g2, 32 * kNullWarps, smem2, st>>>(a);
+            else k_null_eval2<false, true><<<g2, 32 * kNullWarps, smem2, st>>>(a);
+        } else {
+            if (scatter) k_null_eval2<true, false><<<g2, 32 * kNullWarps, smem2, st>>>(a);
+            else k_null_eval2<false, false><<<g2, 32 * kNullWarps, smem2, st>>>(a);
+        }
+        return;
+    }
     if (a.blk) {
         if (scatter) k_null_eval<true, true><<<grid, 32 * kNullWarps, smem, st>>>(a);
         else k_null_eval<false, true><<<grid, 32 * kNullWarps, smem, st>>>(a);

@@ -215,10 +215,14 @@ struct NullEvalArgs {
                                   // [task][tile] order, transposed back
     UpdateRec *recs;
     int *tile_counter;            // zeroed before every launch: persistent CTAs claim haplotype pairs from it
+    unsigned long long *unit_counter;   // != NULL: second form of the kernel (k_null_eval2, warps on their own); zeroed before every launch
+    int32_t window;               // second form: windowed enumeration (one label of B at a time)
+    double dwin;                  // largest distance that can land on the grid (a safe superset)
     int32_t max_ctas_per_sm;      // > 0: cap of the persistent grid
 };
 int null_stage_cap(int max_chunks);   // chunks of B a CTA stages in shared memory (multiple of 8)
 size_t null_eval_smem(int K, int max_tb, int stage_cap);
+void launch_sum_i32(const int32_t *in, long long n, unsigned long long *total /*zeroed*/, cudaStream_t st);
 void launch_transpose_i32(const int32_t *in, long long rows, long long cols, int32_t *out, cudaStream_t st);
 void launch_null_eval(const NullEvalArgs &a, bool scatter, cudaStream_t st);
 void launch_null_dir(const int32_t *offs, const int32_t *perm, int n_tasks, long long T, RegionEnt *dir, cudaStream_t st);
