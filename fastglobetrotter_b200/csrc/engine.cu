@@ -89,7 +89,6 @@ int Engine::set_option(const char *key, double v) {
     else if (k == "null_tasks") opt.null_tasks = iv;
     else if (k == "null_overlap") opt.null_overlap = iv;
     else if (k == "null_block") opt.null_block = iv;
-    else if (k == "null_kernel") opt.null_kernel = iv;
     else if (k == "null_window") opt.null_window = iv;
     else if (k == "null_world") opt.null_world = std::max(1, iv);
     else if (k == "null_rank") opt.null_rank = std::max(0, iv);
@@ -130,7 +129,6 @@ double Engine::get_option(const char *key) {
     if (k == "null_tasks") return opt.null_tasks;
     if (k == "null_overlap") return opt.null_overlap;
     if (k == "null_block") return opt.null_block;
-    if (k == "null_kernel") return opt.null_kernel;
     if (k == "null_window") return opt.null_window;
     if (k == "null_world") return opt.null_world;
     if (k == "null_rank") return opt.null_rank;
@@ -1962,11 +1960,11 @@ int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::v
         const bool normal = std::isnormal(pb.binwidth) && pb.binwidth > 1e-100 && pb.binwidth < 1e100;
         ea.inv_bw = (!all_ones && normal) ? 1.0 / pb.binwidth : 0.0;
     }
-    ea.plan = d_plan; ea.rows = d_rows; ea.max_tb = max_tb; ea.n_tasks = n_tasks;
-    long long most = 1, all_lab = 0;
-    for (long long c : nlab) { most = std::max(most, c); all_lab += c; }
+    ea.plan = d_plan; ea.rows = d_rows; ea.n_tasks = n_tasks;
+    long long all_lab = 0;
+    for (long long c : nlab) all_lab += c;
     // small label groups (large K): the labels of B in blocks of consecutive labels holding at most 32 bin ranges
-    const bool window_on = opt.null_kernel == 2 && (opt.null_window >= 0 ? (opt.null_window != 0) : (in_window < 0.9));
+    const bool window_on = opt.null_window >= 0 ? (opt.null_window != 0) : (in_window < 0.9);
     const double group = (double)all_lab / NH / K;           // chunks of one label on a haplotype, on average
     // (the windowed enumeration works one label at a time: with half the pairs outside the window it beats the blocks down to ~12
     // chunks per group -- K = 100, 300k SNPs: 435 ms against 994 ms in blocks and 888 ms for k_null_strict)
@@ -1994,15 +1992,10 @@ int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::v
         CK(cudaStreamSynchronize(st_));            // the two vectors are locals
         ea.blk_start = d_bs; ea.blk = d_blk;
     }
-    ea.stage_cap = null_stage_cap((int)std::min<long long>(most, 1 << 20));
-    if (null_eval_smem(K, max_tb, ea.stage_cap) > 200 * 1024) ea.stage_cap = 0;          // many labels: B is read through L1 instead
-    if (null_eval_smem(K, max_tb, ea.stage_cap) > 200 * 1024) return FGT_ERR_ARG;
-    ea.tile_counter = d_ctr + 1;
-    if (opt.null_kernel == 2) {
-        ea.unit_counter = reinterpret_cast<unsigned long long *>(d_ctr + 8);
-        ea.window = window_on ? 1 : 0;
-        ea.dwin = (pb.grid_start + G + 1) * pb.binwidth;
-    }
+    if (null_eval_smem(K, blocks) > 200 * 1024) return FGT_ERR_ARG;
+    ea.unit_counter = reinterpret_cast<unsigned long long *>(d_ctr + 8);
+    ea.window = window_on ? 1 : 0;
+    ea.dwin = (pb.grid_start + G + 1) * pb.binwidth;
     // Two lanes of batches: batch b is folded on the commit stream while batch b+1 is counted and scattered on the evaluation
     // stream (the two kinds of kernel stall on different things); both persistent grids are capped so that they fit an SM together.
     const bool overlap = opt.null_overlap != 0;
@@ -2032,9 +2025,7 @@ int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::v
         RegionEnt *d_dir = (ln ? d_ndir2_ : d_ndir_).as<RegionEnt>(tab.size());
         if (!d_cnt || !d_off || !d_dir) return FGT_ERR_CUDA;
         ea.tiles = d_tiles + t0; ea.n_tiles = (int)T;
-        ea.la_groups = (int)std::max<long long>(1, std::min<long long>((long long)own.size(), (148 * 8 + T - 1) / T));
         // counts per (tile, task) -> [task][tile] -> exclusive scan = first record of every (task, tile) -> back to [tile][task]
-        CK(cudaMemsetAsync(d_ctr + 1, 0, sizeof(int), st_));
         CK(cudaMemsetAsync(d_ctr + 8, 0, 2 * sizeof(unsigned long long), st_));
         ea.counts = d_cnt; ea.offs = nullptr; ea.recs = nullptr;
         launch_null_eval(ea, false, st_);
@@ -2053,7 +2044,6 @@ int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::v
         launch_transpose_i32(d_cnt, T, n_tasks, d_off, st_);
         launch_exclusive_scan_i32_large(d_off, d_cnt, n_cnt, d_cnt + n_cnt + 1, st_);
         launch_transpose_i32(d_cnt, n_tasks, T, d_off, st_);
-        CK(cudaMemsetAsync(d_ctr + 1, 0, sizeof(int), st_));
         CK(cudaMemsetAsync(d_ctr + 8, 0, sizeof(unsigned long long), st_));
         ea.counts = nullptr; ea.offs = d_off;
         if (overlap && lane_used[ln]) CK(cudaStreamWaitEvent(st_, null_ev_[ln], 0));     // the lane's records and directory are free again
@@ -2125,7 +2115,8 @@ int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_ro
     // haplotype pairs), 0 = two phases whenever its tables allow (K <= 4096, G < 65536).  Measured on B200 (profiles/r2_null.md), two
     // phases against k_null_strict: tutorial 3.9x, K = 30 2.0x (100k SNPs) / 26x (400k), K = 100 1.8x / 2.2x (300k), K = 150 2.5x /
     // 3.2x (1M SNPs): with the windowed enumeration and batches sized by expected records it wins on every shape tried.
-    bool two_phase = opt.null_impl == 2 && K <= 4096 && G < 65536;
+    const bool tables_ok = K <= 4096 && G < 65536 && (long long)K * K * G < (1LL << 31);     // 16-bit packed plans, 32-bit cell numbers
+    bool two_phase = opt.null_impl == 2 && tables_ok;
     // the share of chunk pairs inside the distance window, from the chromosomes' genetic lengths
     std::vector<double> in_window(pb.num_chrom, 1.0);
     double mean_in_window = 0;
@@ -2137,7 +2128,7 @@ int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_ro
         in_window[h] = cm > 0 ? std::min(1.0, 2.0 * window / cm) : 1.0;
         mean_in_window += in_window[h] / pb.num_chrom;
     }
-    if (opt.null_impl == 0 && K <= 4096 && G < 65536) two_phase = true;
+    if (opt.null_impl == 0 && tables_ok) two_phase = true;
     (void)mean_in_window;
     std::vector<double> own_init;
     const double *init_src = out;

@@ -60,8 +60,7 @@ struct Options {
     double null_batch = 0;  // null_impl 2: chunk-pair evaluations per batch of haplotype pairs (0 = from free device memory)
     int null_tasks = 0;     // null_impl 2: commit tasks aimed at (0 = default)
     int null_block = -1;    // null_impl 2: take the labels of B in blocks (small label groups); -1 = when a label group averages < 24 chunks
-    int null_kernel = 2;    // null_impl 2, phase 1: 2 = warps on their own (per-warp staging, optional windowed enumeration), 1 = CTA-wide staging of B
-    int null_window = -1;   // null_kernel 2: windowed enumeration; -1 = when under 90 % of the chunk pairs lie inside the distance window
+    int null_window = -1;   // null_impl 2: windowed enumeration of phase 1; -1 = when under 90 % of the chunk pairs lie inside the distance window
     int null_overlap = 1;   // null_impl 2: fold batch b on the commit stream while batch b+1 is evaluated (two record buffers)
     int null_world = 1, null_rank = 0;   // sharded NULL run: this rank folds the label pairs it owns (sum of the ranks = exact)
     int spec_rand = 1;      // generate the first batch's draws while the chunk/bin kernels run

@@ -2281,8 +2281,7 @@ void launch_null_strict(const NullArgs &a, cudaStream_t st) {
 // lanes of one task are found with one ballot per bit of (task - smallest task of the step).
 struct NullStep { unsigned key; int cell, local; double val; };   // key = bin range of the lane's pair inside its label pair, ~0u = rejected
 
-constexpr int kNullWarps = 4;          // warps per CTA of k_null_eval (few: the CTA waits for its slowest warp before the next haplotype pair)
-constexpr int kNullStageB = 2048;      // most chunks of B staged in shared memory (32 bytes each); longer haplotypes are read from global memory
+constexpr int kNullWarps = 4;          // warps per CTA of k_null_eval2
 constexpr int kNullMaxRanges = 64;     // most bin ranges of one label pair (shared-memory counters per warp)
 
 __device__ __forceinline__ NullStep null_eval_pair(const NullEvalArgs &a, const Chunk &A, double posB, double halfB, double wB, int cell0,
@@ -2315,159 +2314,16 @@ __device__ __forceinline__ NullStep null_eval_pair(const NullEvalArgs &a, const 
     return o;
 }
 
-// Persistent CTAs: a CTA claims a haplotype pair, stages the B haplotype once, and its warps claim the A labels of the pair
-// (heaviest first) from a shared counter, so that uneven label sizes leave no warp idle behind a slow neighbour.  A warp then
-// takes the labels of B one after the other: the chunk pairs of one (label of A, label of B) are numbered q = i * |B group| + j
-// and handed to the lanes 32 at a time (all lanes busy however small the groups are), so that at any time a warp writes to
-// the few record regions of ONE label pair -- their sectors fill up and leave L2 whole.
-// BLOCKS (small label groups, large K): the labels of B are taken in blocks of consecutive labels with at most 32 bin ranges
-// between them, so that a step of 32 pairs is full even when a label group holds a handful of chunks; the lanes then look up
-// their own label's plan.
-template <bool SCATTER, bool BLOCKS>
-__global__ void __launch_bounds__(32 * kNullWarps) k_null_eval(const NullEvalArgs a) {
-    extern __shared__ __align__(16) unsigned char nev_sm[];
-    const int cap = a.stage_cap;
-    double2 *sBph = reinterpret_cast<double2 *>(nev_sm);                      // [cap] (position, half size)
-    double *sBw = reinterpret_cast<double *>(sBph + cap);                     // [cap] weight
-    int32_t *ctl = reinterpret_cast<int32_t *>(sBw + cap);                    // [0] tile, [1] next label
-    int32_t *cnt = ctl + 4 + warp_id() * kNullMaxRanges;
-    const int K = a.K;
-    uint2 *prow = reinterpret_cast<uint2 *>(ctl + 4 + kNullWarps * kNullMaxRanges) + (size_t)warp_id() * K;   // BLOCKS: the row's plan, packed
-    uint16_t *sBlab = reinterpret_cast<uint16_t *>(reinterpret_cast<uint2 *>(ctl + 4 + kNullWarps * kNullMaxRanges) + (size_t)kNullWarps * K);   // BLOCKS: [cap]
-    const int lane = lane_id();
-    const unsigned lt = (1u << lane) - 1;
-    const long long NT = a.n_tasks;
-    while (true) {
-        __syncthreads();                                    // everybody is done with the staged haplotype
-        if (threadIdx.x == 0) { ctl[0] = atomicAdd(a.tile_counter, 1); ctl[1] = 0; }
-        __syncthreads();
-        // work unit = (haplotype pair, group of A labels): the labels are dealt round robin over la_groups groups, so that a batch
-        // of few (long) haplotype pairs still fills the GPU
-        const int unit = ctl[0];
-        if (unit >= a.n_tiles * a.la_groups) break;
-        const int tile = unit / a.la_groups, grp = unit - tile * a.la_groups;
-        const int2 hh = a.tiles[tile];
-        const int32_t *oA = a.lab_off + (size_t)hh.x * (K + 2);
-        const int32_t *oB = a.lab_off + (size_t)hh.y * (K + 2);
-        const int nB = oB[K];                               // labelled chunks of B (labels 1..K), grouped by label
-        const Chunk *CB = a.chunks + a.hap_base[hh.y];
-        const bool staged = nB <= cap;
-        if (staged) {
-            for (int j = threadIdx.x; j < nB; j += blockDim.x) {
-                const Chunk B = ldg_chunk(CB + j);
-                sBph[j] = make_double2(B.pos, __dmul_rn(B.size, 0.5));
-                sBw[j] = B.w;
-                if (BLOCKS) sBlab[j] = (uint16_t)(B.pop - 1);
-            }
-        }
-        __syncthreads();
-        while (true) {
-            int qi = 0;
-            if (lane == 0) qi = atomicAdd(&ctl[1], 1);
-            qi = __shfl_sync(kFull, qi, 0) * a.la_groups + grp;
-            if (qi >= a.n_own) break;
-            const int la = a.own[qi];
-            const int a0 = oA[la], cntA = oA[la + 1] - a0;
-            if (cntA <= 0) {
-                if (!SCATTER) {                             // the counts of this (tile, label) must still be written: zeros
-                    const NullRowPlan rp = a.rows[la];
-                    int32_t *g0 = a.counts + (size_t)tile * NT + rp.task0;
-                    for (int t = lane; t < rp.ntb; t += 32) g0[t] = 0;
-                }
-                continue;
-            }
-            const Chunk *CA = a.chunks + a.hap_base[hh.x] + a0;
-            const NullPairPlan *row = a.plan + (size_t)la * K;
-            const NullRowPlan rpl = a.rows[la];
-            const int task0 = rpl.task0;
-            int32_t *grow = (SCATTER ? const_cast<int32_t *>(a.offs) : a.counts) + (size_t)tile * NT + task0;   // [tile][task]
-            int blk0 = 0, nblk = K;
-            if (BLOCKS) {
-                blk0 = a.blk_start[la]; nblk = a.blk_start[la + 1] - blk0;
-                __syncwarp();
-                for (int lb = lane; lb < K; lb += 32) {
-                    const NullPairPlan pp = row[lb];
-                    prow[lb] = make_uint2(pp.magic, (unsigned)pp.tb0 | ((unsigned)pp.w << 16));
-                }
-                __syncwarp();
-            }
-            for (int bi = 0; bi < nblk; bi++) {
-                int lb = bi, lb1 = bi + 1;
-                if (BLOCKS) { const int2 bk = a.blk[blk0 + bi]; lb = bk.x; lb1 = bk.y; }
-                const NullPairPlan pp = row[lb];
-                const int b0 = oB[lb], cntB = oB[lb1] - b0;              // chunks of B in this label (block of labels)
-                const int nr = BLOCKS ? ((lb1 < K ? row[lb1].tb0 : rpl.ntb) - pp.tb0) : (a.G + pp.w - 1) / pp.w;
-                int32_t *gcnt = grow + pp.tb0;
-                __syncwarp();
-                for (int t = lane; t < nr; t += 32) cnt[t] = (SCATTER && cntB > 0) ? gcnt[t] : 0;
-                __syncwarp();
-                if (cntB > 0) {
-                    const int npairs = cntA * cntB;
-                    const unsigned bmagic = cntB > 1 ? (unsigned)((0x100000000ULL + cntB - 1) / cntB) : 0u;   // q / cntB for q < 2^16 ...
-                    const bool small = npairs < 65536 && cntB < 65536;                                          // ... else a real division
-                    const int cell0u = (la * K + lb) * a.G;
-                    for (int q0 = 0; q0 < npairs; q0 += 64) {
-                        NullStep e[2];
-#pragma unroll
-                        for (int h = 0; h < 2; h++) {
-                            const int q = q0 + 32 * h + lane;
-                            const bool valid = q < npairs;
-                            int i = 0, j = 0;
-                            if (valid) {
-                                i = cntB == 1 ? q : (small ? (int)__umulhi((unsigned)q, bmagic) : q / cntB);
-                                j = q - i * cntB;
-                            }
-                            const Chunk A = ldg_chunk(CA + i);
-                            double posB, halfB, wB;
-                            int labB = lb;
-                            if (staged) {
-                                const double2 ph = sBph[b0 + j]; posB = ph.x; halfB = ph.y; wB = sBw[b0 + j];
-                                if (BLOCKS) labB = sBlab[b0 + j];
-                            } else {
-                                const Chunk B = ldg_chunk(CB + b0 + j); posB = B.pos; halfB = __dmul_rn(B.size, 0.5); wB = B.w;
-                                if (BLOCKS) labB = B.pop - 1;
-                            }
-                            if (BLOCKS) {
-                                const uint2 pl = prow[labB];
-                                e[h] = null_eval_pair(a, A, posB, halfB, wB, (la * K + labB) * a.G, pl.x, (int)(pl.y >> 16), (int)(pl.y & 0xffffu) - pp.tb0, valid);
-                            } else e[h] = null_eval_pair(a, A, posB, halfB, wB, cell0u, pp.magic, pp.w, 0, valid);
-                        }
-#pragma unroll
-                        for (int h = 0; h < 2; h++) {
-                            const bool acc = e[h].key != ~0u;
-                            if (!SCATTER) {
-                                if (acc) atomicAdd(&cnt[e[h].key], 1);
-                            } else {
-                                // stable rank inside the step: the lanes of the same bin range, in lane order (= (i, j) order)
-                                if (!__any_sync(kFull, acc)) continue;
-                                const unsigned M = nr > 1 ? __match_any_sync(kFull, e[h].key) : __ballot_sync(kFull, acc);
-                                const int first = __ffs(M) - 1;
-                                int base = 0;
-                                if (acc && lane == first) base = atomicAdd(&cnt[e[h].key], __popc(M));   // one lane per range of the step
-                                base = __shfl_sync(kFull, base, first);
-                                if (acc) {
-                                    UpdateRec rec;
-                                    rec.cell = e[h].cell; rec.pad = e[h].local; rec.val = e[h].val;
-                                    a.recs[base + __popc(M & lt)] = rec;
-                                }
-                            }
-                        }
-                    }
-                }
-                if (!SCATTER) {
-                    __syncwarp();
-                    for (int t = lane; t < nr; t += 32) gcnt[t] = cnt[t];
-                }
-            }
-        }
-    }
-}
-
-// ---- phase 1, second form (null_kernel = 2): every warp on its own -------------------------------------------------------
-// A warp claims (haplotype pair, label of A) units from one global counter (no CTA barrier, no idle warps at the end of a
-// haplotype pair) and stages what it needs in ITS OWN slice of shared memory: the chunks of A with that label once per unit, the
-// chunks of the current label (block of labels) of B once per label pair -- a 1/|A group| overhead that removes the limit on the
-// haplotype length (the CTA-wide staging above falls back to global loads beyond 2048 chunks: every long chromosome of real data).
+// ---- phase 1: persistent warps, every warp on its own ---------------------------------------------------------------------
+// A warp claims (haplotype pair, label of A) units from one global counter, heaviest labels first (no CTA barrier, no idle warps at
+// the end of a haplotype pair) and stages what it needs in ITS OWN slice of shared memory: the chunks of A with that label once
+// per unit, the chunks of the current label (block of labels) of B once per label pair -- a 1/|A group| overhead, and no limit on
+// the haplotype length (an earlier form staged the whole B haplotype per CTA and fell back to global loads beyond 2048 chunks:
+// every long chromosome of real data).  The chunk pairs of one (label of A, label of B) are dealt to the lanes 32 at a time in
+// (i, j) order, so that at any time a warp writes to the few record regions of ONE label pair -- their sectors fill up and leave
+// L2 whole.  BLOCKS (small label groups, large K): the labels of B in blocks of consecutive labels with at most 32 bin ranges
+// between them, so that a step is full even when a label group holds a handful of chunks; the lanes then look up their own
+// label's plan.
 // Optional windowed enumeration (one label of B at a time): every lane bisects, for its A chunk, the index range of the position-sorted
 // B group within the largest distance the grid holds; a warp scan numbers the candidates of 32 A chunks in (i, j) order and the
 // steps take 32 candidates each -- on chromosomes much longer than the window most chunk pairs are never touched.
@@ -2624,19 +2480,19 @@ __global__ void __launch_bounds__(32 * kNullWarps) k_null_eval2(const NullEvalAr
                         }
                     }
                 } else {
-                    const int npairs = cntA * cntB;
+                    const long long npairs = (long long)cntA * cntB;   // (two haplotypes of 50k chunks with one label: beyond 32 bits)
                     const unsigned bmagic = cntB > 1 ? (unsigned)((0x100000000ULL + cntB - 1) / cntB) : 0u;   // q / cntB for q < 2^16 ...
                     const bool small = npairs < 65536 && cntB < 65536;                                          // ... else a real division
-                    for (int q0 = 0; q0 < npairs; q0 += 64) {
+                    for (long long q0 = 0; q0 < npairs; q0 += 64) {
                         NullStep e[2];
 #pragma unroll
                         for (int h = 0; h < 2; h++) {
-                            const int q = q0 + 32 * h + lane;
+                            const long long q = q0 + 32 * h + lane;
                             const bool valid = q < npairs;
                             int i = 0, j = 0;
                             if (valid) {
-                                i = cntB == 1 ? q : (small ? (int)__umulhi((unsigned)q, bmagic) : q / cntB);
-                                j = q - i * cntB;
+                                i = cntB == 1 ? (int)q : (small ? (int)__umulhi((unsigned)q, bmagic) : (int)(q / cntB));
+                                j = (int)(q - (long long)i * cntB);
                             }
                             e[h] = eval(i, j, valid);
                         }
@@ -2695,54 +2551,31 @@ __global__ void k_null_dir(const int32_t *__restrict__ offs, const int32_t *__re
     dir[c] = o;
 }
 
-int null_stage_cap(int max_chunks) { return std::min(kNullStageB, (max_chunks + 7) & ~7); }
-size_t null_eval_smem(int K, int max_tb, int stage_cap) {
-    (void)max_tb;       // blocks: + the packed plan of a row per warp and the staged labels of B
-    return (size_t)stage_cap * (sizeof(double2) + sizeof(double)) + 16 + (size_t)kNullWarps * kNullMaxRanges * sizeof(int32_t) +
-           (size_t)kNullWarps * K * sizeof(uint2) + (size_t)stage_cap * sizeof(uint16_t);
-}
 void launch_null_eval(const NullEvalArgs &a, bool scatter, cudaStream_t st) {
     if (a.n_tiles <= 0 || a.n_own <= 0) return;
-    const size_t smem = null_eval_smem(a.K, a.max_tb, a.stage_cap);
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_set[dev & 63]) {
-        cudaFuncSetAttribute(k_null_eval<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(k_null_eval<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(k_null_eval<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(k_null_eval<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(k_null_eval2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(k_null_eval2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(k_null_eval2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(k_null_eval2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set[dev & 63] = true;
     }
+    const size_t smem = (size_t)kNullWarps * kNullWarpBytes + (a.blk ? (size_t)kNullWarps * a.K * sizeof(uint2) : 0);
     long long per_sm = std::max<long long>(1, std::min<long long>(2048 / (32 * kNullWarps), (227 * 1024) / (long long)(smem + 1024)));
     if (a.max_ctas_per_sm > 0) per_sm = std::min<long long>(per_sm, a.max_ctas_per_sm);
-    const unsigned grid = (unsigned)std::min<long long>((long long)a.n_tiles * a.la_groups, 148 * per_sm);
-    if (a.unit_counter) {                              // second form: warps on their own
-        const size_t smem2 = (size_t)kNullWarps * kNullWarpBytes + (a.blk ? (size_t)kNullWarps * a.K * sizeof(uint2) : 0);
-        long long ps = std::max<long long>(1, std::min<long long>(2048 / (32 * kNullWarps), (227 * 1024) / (long long)(smem2 + 1024)));
-        if (a.max_ctas_per_sm > 0) ps = std::min<long long>(ps, a.max_ctas_per_sm);
-        const unsigned g2 = (unsigned)std::min<long long>(((long long)a.n_tiles * a.n_own + kNullWarps - 1) / kNullWarps, 148 * ps);
-        if (a.blk) {
-            if (scatter) k_null_eval2<true, true><<<g2, 32 * kNullWarps, smem2, st>>>(a);
-            else k_null_eval2<false, true><<<g2, 32 * kNullWarps, smem2, st>>>(a);
-        } else {
-            if (scatter) k_null_eval2<true, false><<<g2, 32 * kNullWarps, smem2, st>>>(a);
-            else k_null_eval2<false, false><<<g2, 32 * kNullWarps, smem2, st>>>(a);
-        }
-        return;
-    }
+    const unsigned grid = (unsigned)std::min<long long>(((long long)a.n_tiles * a.n_own + kNullWarps - 1) / kNullWarps, 148 * per_sm);
     if (a.blk) {
-        if (scatter) k_null_eval<true, true><<<grid, 32 * kNullWarps, smem, st>>>(a);
-        else k_null_eval<false, true><<<grid, 32 * kNullWarps, smem, st>>>(a);
+        if (scatter) k_null_eval2<true, true><<<grid, 32 * kNullWarps, smem, st>>>(a);
+        else k_null_eval2<false, true><<<grid, 32 * kNullWarps, smem, st>>>(a);
     } else {
-        if (scatter) k_null_eval<true, false><<<grid, 32 * kNullWarps, smem, st>>>(a);
-        else k_null_eval<false, false><<<grid, 32 * kNullWarps, smem, st>>>(a);
+        if (scatter) k_null_eval2<true, false><<<grid, 32 * kNullWarps, smem, st>>>(a);
+        else k_null_eval2<false, false><<<grid, 32 * kNullWarps, smem, st>>>(a);
     }
 }
+size_t null_eval_smem(int K, bool blocks) { return (size_t)kNullWarps * kNullWarpBytes + (blocks ? (size_t)kNullWarps * K * sizeof(uint2) : 0); }
 
 void launch_null_dir(const int32_t *offs, const int32_t *perm, int n_tasks, long long T, RegionEnt *dir, cudaStream_t st) {
     if (n_tasks <= 0) return;

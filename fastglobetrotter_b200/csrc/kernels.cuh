@@ -200,28 +200,23 @@ struct NullEvalArgs {
     int32_t n_tiles;
     const int32_t *own;           // [n_own] labels of A (0-based) this engine folds (all of them unless the call is sharded)
     int32_t n_own;
-    int32_t la_groups;            // work units per haplotype pair (groups of A labels)
     int32_t K, G, grid_start;
     double bw, half_bw, inv_bw;
     const NullPairPlan *plan;     // [K][K]
     const NullRowPlan *rows;      // [K]
     const int32_t *blk_start;     // blocks of B labels (small label groups): row la takes blk[blk_start[la] .. blk_start[la+1])
     const int2 *blk;              // (first label, label behind the last) of a block: at most 32 bin ranges; NULL = one label at a time
-    int32_t max_tb;               // largest ntb (shared-memory counters per warp)
-    int32_t stage_cap;            // null_stage_cap(most labelled chunks of a haplotype)
     int32_t n_tasks;              // tasks of this engine (natural numbering: rows of A in label order)
     int32_t *counts;              // counting pass: [n_tiles][n_tasks]
     const int32_t *offs;          // scatter pass: [n_tiles][n_tasks] first record of (tile, task): the exclusive scan of the counts in
                                   // [task][tile] order, transposed back
     UpdateRec *recs;
-    int *tile_counter;            // zeroed before every launch: persistent CTAs claim haplotype pairs from it
-    unsigned long long *unit_counter;   // != NULL: second form of the kernel (k_null_eval2, warps on their own); zeroed before every launch
-    int32_t window;               // second form: windowed enumeration (one label of B at a time)
+    unsigned long long *unit_counter;   // zeroed before every launch: persistent warps claim (haplotype pair, label of A) units from it
+    int32_t window;               // windowed enumeration (one label of B at a time)
     double dwin;                  // largest distance that can land on the grid (a safe superset)
     int32_t max_ctas_per_sm;      // > 0: cap of the persistent grid
 };
-int null_stage_cap(int max_chunks);   // chunks of B a CTA stages in shared memory (multiple of 8)
-size_t null_eval_smem(int K, int max_tb, int stage_cap);
+size_t null_eval_smem(int K, bool blocks);
 void launch_sum_i32(const int32_t *in, long long n, unsigned long long *total /*zeroed*/, cudaStream_t st);
 void launch_transpose_i32(const int32_t *in, long long rows, long long cols, int32_t *out, cudaStream_t st);
 void launch_null_eval(const NullEvalArgs &a, bool scatter, cudaStream_t st);

@@ -161,8 +161,8 @@ int64_t fgt_get_raw_counts(double *out, int64_t capacity);
  * (2 = two-phase, 1 = single-phase), "batch_pairs", "blocks", "ranges", "split_ready", "eval_parts", "spec_rand",
  * "copy_streams", "null_slab_bins", "commit_ctas", "reuse_prep" (one-shot).  "null_impl": data_read_null as 2 = two phases (every
  * chunk pair evaluated once into records, ordered commit), 1 = windowed kernel (one warp per label pair and slab), 0 = two phases
- * whenever its tables allow (K <= 4096, default); "null_tasks", "null_batch", "null_overlap", "null_block", "null_window", "null_kernel"
- * are its tuning hooks.
+ * whenever its tables allow (K <= 4096, default); "null_tasks", "null_batch", "null_overlap", "null_block", "null_window" are its
+ * tuning hooks.
  * "project_impl": 0 = exact projection (bit-identical curves,
  * default), 1 = FP64 tensor cores (curves to ~1e-14).  "null_world" / "null_rank": sharded data_read_null -- this
  * process folds only the tensor rows (two phases: rows of A labels; windowed kernel: label pairs) it owns and returns zeros elsewhere (every rank is given the caller's initial

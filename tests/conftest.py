@@ -52,7 +52,7 @@ def each_encoding(lib, request):
     lib.encode = "rle"
 
 
-@pytest.fixture(params=["windowed", "two_phase", "two_phase_batched", "two_phase_blocks", "two_phase_cta_staged", "two_phase_window"])
+@pytest.fixture(params=["windowed", "two_phase", "two_phase_batched", "two_phase_blocks", "two_phase_window"])
 def each_null_impl(lib, request):
     """run a NULL test with k_null_strict (null_impl 1), with the two-phase path (null_impl 2: every chunk pair evaluated once
     into records, ordered commit), with the two-phase path forced into many small batches and many narrow commit tasks, and with
@@ -64,12 +64,10 @@ def each_null_impl(lib, request):
     lib.set_option("null_block", {"two_phase": 0, "two_phase_blocks": 1}.get(request.param, -1))
     if request.param == "two_phase_blocks":
         lib.set_option("null_tasks", 400)          # label pairs with one and with several bin ranges inside a block
-    lib.set_option("null_kernel", 1 if request.param == "two_phase_cta_staged" else 2)
     lib.set_option("null_window", {"two_phase_window": 1, "two_phase": 0}.get(request.param, -1))
     yield request.param
     lib.set_option("null_impl", 0)
     lib.set_option("null_block", -1)
-    lib.set_option("null_kernel", 2)
     lib.set_option("null_window", -1)
     lib.set_option("null_batch", 0)
     lib.set_option("null_tasks", 0)
