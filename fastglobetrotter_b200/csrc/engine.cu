@@ -89,6 +89,7 @@ int Engine::set_option(const char *key, double v) {
     else if (k == "null_tasks") opt.null_tasks = iv;
     else if (k == "null_overlap") opt.null_overlap = iv;
     else if (k == "null_block") opt.null_block = iv;
+    else if (k == "null_min_batches") opt.null_min_batches = std::max(1, iv);
     else if (k == "null_window") opt.null_window = iv;
     else if (k == "null_world") opt.null_world = std::max(1, iv);
     else if (k == "null_rank") opt.null_rank = std::max(0, iv);
@@ -129,6 +130,7 @@ double Engine::get_option(const char *key) {
     if (k == "null_tasks") return opt.null_tasks;
     if (k == "null_overlap") return opt.null_overlap;
     if (k == "null_block") return opt.null_block;
+    if (k == "null_min_batches") return opt.null_min_batches;
     if (k == "null_window") return opt.null_window;
     if (k == "null_world") return opt.null_world;
     if (k == "null_rank") return opt.null_rank;
@@ -1816,7 +1818,8 @@ int Engine::data_read_null_multi(const fgt_problem_t &pb, const int32_t *rec_row
 // would be re-associated).  Two-phase path: whole rows of A labels (the evaluation work is split as well); k_null_strict: label pairs.
 static inline bool null_owner(bool two_phase, int la, int lb, int world, int rank) {
     if (world <= 1) return true;
-    return two_phase ? (la % world == rank) : ((la * 31 + lb * 17) % world == rank);
+    (void)two_phase;                        // (the two-phase path deals whole rows of A labels by expected work: null_row_owner_)
+    return (la * 31 + lb * 17) % world == rank;
 }
 
 // Two-phase NULL accumulation of one chromosome (kernels.cu, "NULL path, two phases"): plan the commit tasks from the per-haplotype
@@ -1826,7 +1829,8 @@ int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::v
     const int K = pb.num_donors, G = pb.num_bins, P = pb.ploidy, NH = Nc * P;
     auto cl = [&](int hp, int l) { return (long long)(laboff[(size_t)hp * (K + 2) + l + 1] - laboff[(size_t)hp * (K + 2) + l]); };
     std::vector<int32_t> own;
-    for (int la = 0; la < K; la++) if (null_owner(true, la, 0, null_world, null_rank)) own.push_back(la);
+    auto mine_row = [&](int la) { return null_world <= 1 || null_row_owner_[la] == null_rank; };
+    for (int la = 0; la < K; la++) if (mine_row(la)) own.push_back(la);
     if (own.empty()) return FGT_OK;
     // evaluated chunk pairs per label pair: sum over haplotypes A of c[A][la] * (chunks labelled lb in the haplotypes of later individuals)
     std::vector<long long> suffix((size_t)(Nc + 1) * K, 0);
@@ -1867,7 +1871,7 @@ int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::v
         std::vector<Cost> tl;
         for (int la = 0; la < K; la++) {
             rows[la].task0 = n_tasks; rows[la].ntb = 0;
-            const bool mine = null_owner(true, la, 0, null_world, null_rank);
+            const bool mine = mine_row(la);
             for (int lb = 0; lb < K; lb++) {
                 NullPairPlan &pp = plan[(size_t)la * K + lb];
                 pp.tb0 = rows[la].ntb; pp.w = G; pp.magic = G > 1 ? (uint32_t)((0x100000000ULL + G - 1) / G) : 0u; pp.pad = 0;
@@ -1920,6 +1924,7 @@ int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::v
     // Batches are sized by the records they are EXPECTED to produce (the chunk pairs times the share inside the distance window, with
     // a margin); the counting pass then tells the exact number before the record buffer is sized, and a batch that would not fit
     // 32-bit offsets is halved and counted again.
+    const bool overlap_batches = opt.null_overlap != 0;
     const double est_frac = std::max(0.05, std::min(1.0, in_window * 1.3 + 0.02));
     for (long long &b : bound) b = std::max<long long>(1, (long long)std::ceil((double)b * est_frac));
     long long batch_evals = opt.null_batch > 0 ? (long long)opt.null_batch : (long long)std::min(1.2e9, mem_budget_bytes_ * 0.8 / sizeof(UpdateRec));
@@ -1927,7 +1932,8 @@ int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::v
     for (long long b : bound) { max_bound = std::max(max_bound, b); total_bound += b; }
     if (!null_pin_ && cudaHostAlloc((void **)&null_pin_, 64, cudaHostAllocDefault) != cudaSuccess) return FGT_ERR_CUDA;
     {   // equal batches instead of full ones and a remainder (every batch pays for a pass over all commit tasks)
-        const long long nbat = (total_bound + batch_evals - 1) / batch_evals;
+        long long nbat = (total_bound + batch_evals - 1) / batch_evals;
+        if (opt.null_batch <= 0 && overlap_batches) nbat = std::max(nbat, std::min<long long>(opt.null_min_batches, total_bound / 100000000LL));   // batches to overlap
         batch_evals = std::min(batch_evals, (total_bound + nbat - 1) / nbat + max_bound);
     }
     batch_evals = std::max(batch_evals, max_bound);
@@ -1974,7 +1980,7 @@ int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::v
         std::vector<int2> blk;
         for (int la = 0; la < K; la++) {
             bstart[la] = (int32_t)blk.size();
-            if (!null_owner(true, la, 0, null_world, null_rank)) continue;
+            if (!mine_row(la)) continue;
             int lb0 = 0, acc = 0;
             for (int lb = 0; lb < K; lb++) {
                 const int nr = (G + plan[(size_t)la * K + lb].w - 1) / plan[(size_t)la * K + lb].w;
@@ -2132,7 +2138,7 @@ int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_ro
     (void)mean_in_window;
     std::vector<double> own_init;
     const double *init_src = out;
-    if (null_world > 1) {
+    if (null_world > 1 && !two_phase) {
         // sharded run: this rank returns only the label pairs it owns (continuing from the caller's values there), zeros
         // elsewhere, so that the ranks' outputs have disjoint supports and their sum is exact
         own_init.assign(out, out + (size_t)K * K * G);
@@ -2143,13 +2149,15 @@ int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_ro
         init_src = own_init.data();
     }
     CK(cudaMemcpyAsync(d_out, init_src, (size_t)K * K * G * sizeof(double), cudaMemcpyHostToDevice, st_));
-    if (null_world > 1) CK(cudaStreamSynchronize(st_));      // own_init is a local
+    if (null_world > 1 && !two_phase) CK(cudaStreamSynchronize(st_));      // own_init is a local
     CK(cudaEventRecord(e1, st_));
     ChromState &cs = null_cs_;                   // grow-only buffers kept between calls (no cudaMalloc/cudaFree per call)
     long long evals = 0;
     for (int h = 0; h < pb.num_chrom; h++) {
         rc = prep_chromosome(pb, h, d_rowmap, rowmap.data(), n_haps, 1, n_haps, true, cs, stx);
         if (rc) return rc;
+        if (Nc < 2 && two_phase && null_world > 1 && h == 0 && null_rank != 0)       // nothing to fold: rank 0 returns the caller's values
+            CK(cudaMemsetAsync(d_out, 0, (size_t)K * K * G * sizeof(double), st_));
         if (Nc >= 2) {
             NullArgs a{};
             a.chunks = (const Chunk *)cs.sorted.p; a.hap_base = (const int32_t *)cs.chunk_base.p;
@@ -2162,6 +2170,33 @@ int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_ro
             CK(cudaMemcpyAsync(laboff.data(), cs.yoff.p, laboff.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st_));
             CK(cudaStreamSynchronize(st_));
             vtick("null: chunks grouped, label counts on the host");
+            if (two_phase && null_world > 1 && h == 0) {
+                // Sharded two-phase run: rows of A labels are dealt to the ranks by their expected work on the first chromosome
+                // (longest processing time first), the same on every rank (same counts, same rule) and for every chromosome of
+                // the call -- a cell's owner must not change, or its additions would be re-associated.  The rows of the other ranks
+                // are zeroed: outputs have disjoint supports, their sum is exact.
+                std::vector<double> row_est(K, 0.0);
+                std::vector<long long> later(Nc + 1, 0);
+                for (int n = Nc - 1; n >= 0; n--) {
+                    later[n] = later[n + 1];
+                    for (int p = 0; p < P; p++) later[n] += laboff[(size_t)(n * P + p) * (K + 2) + K];
+                }
+                for (int hA = 0; hA < (Nc - 1) * P; hA++)
+                    for (int la = 0; la < K; la++)
+                        row_est[la] += (double)(laboff[(size_t)hA * (K + 2) + la + 1] - laboff[(size_t)hA * (K + 2) + la]) * (double)later[hA / P + 1];
+                std::vector<int> order(K);
+                for (int la = 0; la < K; la++) order[la] = la;
+                std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return row_est[x] > row_est[y]; });
+                std::vector<double> load(null_world, 0.0);
+                null_row_owner_.assign(K, 0);
+                for (int la : order) {
+                    int best = 0;
+                    for (int r = 1; r < null_world; r++) if (load[r] < load[best]) best = r;
+                    null_row_owner_[la] = best; load[best] += row_est[la];
+                }
+                for (int la = 0; la < K; la++)
+                    if (null_row_owner_[la] != null_rank) CK(cudaMemsetAsync(d_out + (size_t)la * K * G, 0, (size_t)K * G * sizeof(double), st_));
+            }
             if (two_phase) {
                 rc = null_two_phase(pb, cs, laboff, Nc, null_world, null_rank, d_out, d_acc, stx, in_window[h]);
                 if (rc) return rc;

@@ -61,6 +61,7 @@ struct Options {
     int null_tasks = 0;     // null_impl 2: commit tasks aimed at (0 = default)
     int null_block = -1;    // null_impl 2: take the labels of B in blocks (small label groups); -1 = when a label group averages < 24 chunks
     int null_window = -1;   // null_impl 2: windowed enumeration of phase 1; -1 = when under 90 % of the chunk pairs lie inside the distance window
+    int null_min_batches = 4; // null_impl 2: batches per chromosome aimed at when the work allows (so that commit and evaluation overlap)
     int null_overlap = 1;   // null_impl 2: fold batch b on the commit stream while batch b+1 is evaluated (two record buffers)
     int null_world = 1, null_rank = 0;   // sharded NULL run: this rank folds the label pairs it owns (sum of the ranks = exact)
     int spec_rand = 1;      // generate the first batch's draws while the chunk/bin kernels run
@@ -169,6 +170,7 @@ class Engine {
     std::vector<ChromState> chroms_;
     ChromState null_cs_;              // NULL path: chunk buffers of the chromosome being folded
     DevBuf d_ntiles_, d_nown_, d_nplan_, d_nrows_, d_nperm_, d_ntab_, d_ncnt_, d_noff_, d_ndir_, d_ncnt2_, d_noff2_, d_ndir2_, d_nblk_, d_nblks_;   // two-phase NULL path (two lanes of batches)
+    std::vector<int> null_row_owner_;             // sharded two-phase NULL run: rank that folds each row of A labels
     unsigned long long *null_pin_ = nullptr;      // pinned: the record total of a batch
     cudaEvent_t null_ev_[3] = {nullptr, nullptr, nullptr};   // commit of lane 0 / lane 1 done, evaluation side ready
     int null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::vector<int32_t> &laboff, int Nc, int null_world, int null_rank,
