@@ -784,6 +784,55 @@ def test_randomized_shapes_against_the_oracle(lib, oracle):
             assert st["pairs"] == ev and np.array_equal(n_g, n_o), f"null case {case}"
 
 
+def test_null_two_phase_variants_fuzz(lib, oracle):
+    """differential fuzz of the two-phase NULL path: 24 random shapes x random choices of windowed / dense enumeration, labels of B
+    one at a time / in blocks, few / many commit tasks, one / many batches, one or three shards -- label groups longer than the
+    128 chunks a warp stages, single-label panels and empty labels included.  The NULL tensor must equal the oracle's bit for bit."""
+    rng = np.random.default_rng(int(os.environ.get("FGT_FUZZ_SEED", "20261022")))
+    names = ("null_impl", "null_window", "null_block", "null_tasks", "null_batch", "null_overlap", "null_world", "null_rank")
+    try:
+        for case in range(24):
+            ploidy = int(rng.choice([1, 2]))
+            n_inds = int(rng.integers(2, 5))
+            n_chrom = int(rng.integers(1, 3))
+            K = int(rng.choice([1, 2, 3, 5, 9, 17, 40]))
+            n_snps = int(rng.choice([300, 1500, 5000] if K > 3 else [1500, 5000, 9000]))       # few labels x long haplotypes: groups > 128
+            bw = float(rng.choice([0.05, 0.1, 0.25, 1.0]))
+            G = int(rng.integers(3, 200))
+            gs = int(rng.integers(0, 12))
+            spec = synth.SynthSpec(n_chrom=n_chrom, n_inds=n_inds, ploidy=ploidy, nsamples=2, n_snps=n_snps, K=K,
+                                   haps_per_pop=int(rng.integers(1, 4)), rate=float(rng.choice([3e-7, 1e-6, 5e-6])),
+                                   mean_chunk_cm=float(rng.choice([0.05, 0.25, 1.0])), self_copy_frac=float(rng.choice([0.0, 0.2])),
+                                   seed=3000 + case)
+            chrom = []
+            for h in range(n_chrom):
+                pos, rt, labels = synth.make_chromosome(spec, h)
+                chrom.append({"pos": pos, "rate": rt, "labels": labels})
+            dl = spec.donor_label_vec()
+            if K > 2 and rng.random() < 0.3:
+                dl = np.where(dl == K, K - 1, dl).astype(np.int32)                              # a label nobody carries
+            rows = rng.permutation(n_inds) if rng.random() < 0.3 else np.arange(n_inds)
+            init = rng.random(K * K * G) if rng.random() < 0.3 else None
+            n_o, ev = oracle.data_read_null_packed(ploidy, 2, chrom, rows, bw, G, gs, K, dl, 0.0, 1.0, init=init)
+            opts = {"null_impl": 2, "null_window": int(rng.choice([0, 1])), "null_block": int(rng.choice([0, 1])),
+                    "null_tasks": int(rng.choice([1, 60, 4096, 200000])), "null_batch": int(rng.choice([0, 0, 5000, 50000])),
+                    "null_overlap": int(rng.choice([0, 1]))}
+            world = int(rng.choice([1, 1, 3]))
+            total = np.zeros_like(n_o)
+            for rank in range(world):
+                for k, v in opts.items():
+                    lib.set_option(k, v)
+                lib.set_option("null_world", world)
+                lib.set_option("null_rank", rank)
+                part, st = lib.data_read_null_packed(ploidy, 2, chrom, rows, bw, G, gs, K, dl, 0.0, 1.0, init=init)
+                assert st["pairs"] == ev, (case, opts)
+                total = total + part if world > 1 else part
+            assert np.array_equal(total, n_o), f"case {case}: ploidy={ploidy} N={n_inds} chr={n_chrom} L={n_snps} K={K} bw={bw} G={G} gs={gs} world={world} {opts}"
+    finally:
+        for k in names:
+            lib.set_option(k, {"null_window": -1, "null_block": -1, "null_overlap": 1, "null_world": 1}.get(k, 0))
+
+
 # ---------------------------------------------------------------------------------------------
 # round 2: generator inside the evaluation kernel, class-match commit, relaxed mode, device-resident runs
 # ---------------------------------------------------------------------------------------------
