@@ -90,6 +90,7 @@ int Engine::set_option(const char *key, double v) {
     else if (k == "null_overlap") opt.null_overlap = iv;
     else if (k == "null_block") opt.null_block = iv;
     else if (k == "null_min_batches") opt.null_min_batches = std::max(1, iv);
+    else if (k == "null_taper") opt.null_taper = iv;
     else if (k == "null_window") opt.null_window = iv;
     else if (k == "null_world") opt.null_world = std::max(1, iv);
     else if (k == "null_rank") opt.null_rank = std::max(0, iv);
@@ -131,6 +132,7 @@ double Engine::get_option(const char *key) {
     if (k == "null_overlap") return opt.null_overlap;
     if (k == "null_block") return opt.null_block;
     if (k == "null_min_batches") return opt.null_min_batches;
+    if (k == "null_taper") return opt.null_taper;
     if (k == "null_window") return opt.null_window;
     if (k == "null_world") return opt.null_world;
     if (k == "null_rank") return opt.null_rank;
@@ -2011,16 +2013,22 @@ int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::v
     if (overlap) {                                   // the caller's values and this chromosome's tables are in place
         CK(cudaEventRecord(null_ev_[2], st_));
         CK(cudaStreamWaitEvent(sc, null_ev_[2], 0));
-        ea.max_ctas_per_sm = 8;
     }
     size_t t0 = 0;
     int nb = 0;
     bool lane_used[2] = {false, false};
     size_t forced_t1 = 0;                            // a batch that overflowed is retried up to here
+    long long left_bound = total_bound;              // expected records of the haplotype pairs not yet in a batch
     while (t0 < tiles.size()) {
         size_t t1 = t0;
         long long sum = 0;
-        while (t1 < tiles.size() && (t1 == t0 || (sum + bound[t1] <= batch_evals && (long long)(t1 - t0) < max_tiles)) && (!forced_t1 || t1 < forced_t1))
+        // the last commit runs with nothing beside it: the work left is dealt out in shrinking batches (a half, a third of a batch)
+        long long cap_now = batch_evals;
+        if (overlap && opt.null_batch <= 0 && opt.null_taper) {
+            if (left_bound <= batch_evals * 3 / 2) cap_now = std::max<long long>(left_bound * 3 / 5, 1);
+            if (left_bound <= batch_evals / 2) cap_now = batch_evals;
+        }
+        while (t1 < tiles.size() && (t1 == t0 || (sum + bound[t1] <= cap_now && (long long)(t1 - t0) < max_tiles)) && (!forced_t1 || t1 < forced_t1))
             sum += bound[t1++];
         forced_t1 = 0;
         const int ln = overlap ? (nb & 1) : 0;
@@ -2031,6 +2039,7 @@ int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::v
         RegionEnt *d_dir = (ln ? d_ndir2_ : d_ndir_).as<RegionEnt>(tab.size());
         if (!d_cnt || !d_off || !d_dir) return FGT_ERR_CUDA;
         ea.tiles = d_tiles + t0; ea.n_tiles = (int)T;
+        ea.max_ctas_per_sm = (overlap && nb > 0) ? 8 : 0;            // a commit of the previous batch shares the SMs
         // counts per (tile, task) -> [task][tile] -> exclusive scan = first record of every (task, tile) -> back to [tile][task]
         CK(cudaMemsetAsync(d_ctr + 8, 0, 2 * sizeof(unsigned long long), st_));
         ea.counts = d_cnt; ea.offs = nullptr; ea.recs = nullptr;
@@ -2066,12 +2075,13 @@ int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::v
         ca.recs = d_recs; ca.regions = d_dir; ca.tensor_is_zero = 0; ca.buckets = 0;
         ca.tensor = d_out; ca.accepted = d_acc; ca.task_counter = ctr;
         ca.task_tab = d_tab; ca.n_task_tab = n_tasks; ca.max_tile_cells = max_w;
-        ca.max_ctas_per_sm = overlap ? 10 : 0;
+        ca.max_ctas_per_sm = (overlap && t1 < tiles.size()) ? 10 : 0;   // the next batch's evaluation shares the SMs
         launch_commit_ordered(ca, max_w, sc);
         if (overlap) { CK(cudaEventRecord(null_ev_[ln], sc)); lane_used[ln] = true; }
         launches_ += 10;
         stx.accum_launches += 1;
         if (opt.verbose) { char msg[96]; snprintf(msg, sizeof msg, "null: batch of %lld haplotype pairs launched (bound %lld records)", T, sum); vtick(msg); }
+        left_bound -= sum;
         t0 = t1;
         nb++;
     }
