@@ -629,7 +629,7 @@ def run_big(args):
                     "config": {"workload": cfg["name"], "run_at": f"{rows.size} individuals x {n_chrom} chromosomes (chromosome fraction {args.chrom_frac})",
                                "evaluations_per_step": ev / args.steps, "accepted_fraction": acc / max(1, ev), "runs": n_runs,
                                "options": os.environ.get("FGT_OPTS", "")},
-                    "roofline": {"bound": "hbm", "kernel": "data_read_null (automatic choice: k_null_eval count/scatter + k_commit_ordered, or k_null_strict)", "achieved": 16.0 * acc / dt / 1e9, "peak": peak, "unit": "GB/s",
+                    "roofline": {"bound": "hbm", "kernel": "data_read_null (two phases: k_null_eval2 count/scatter + k_commit_ordered)", "achieved": 16.0 * acc / dt / 1e9, "peak": peak, "unit": "GB/s",
                                  "frac": 16.0 * acc / dt / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                                  "note": "16 B per accepted update (SURVEY 8d); the tensor lives in shared memory, not HBM"},
                     "clocks": clocks, "checksum": float(np.nansum(t))})
