@@ -1009,6 +1009,8 @@ int fgt_count_pairs_packed(const fgt_problem_t *prob, int64_t *out) {
 int fgt_data_read_null_packed(const fgt_problem_t *prob, const int32_t *rec_rows, double *chrom_ind_res, fgt_stats_t *stats) {
     if (!prob || !rec_rows || !chrom_ind_res) return FGT_ERR_ARG;
     std::lock_guard<std::mutex> lk(g_api_mu);
+    if (g_proc.on)      // one process per GPU: this rank folds its rows of the tensor, the partial tensors are all-reduced inside the library
+        return Engine::get().data_read_null_packed(*prob, rec_rows, chrom_ind_res, stats, g_proc.world, g_proc.rank, g_proc.comm);
     return Engine::data_read_null_multi(*prob, rec_rows, chrom_ind_res, stats);
 }
 

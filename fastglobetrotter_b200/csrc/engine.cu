@@ -2091,7 +2091,7 @@ int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::v
 }
 
 int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_rows, double *out, fgt_stats_t *stats, int shard_world,
-                                  int shard_rank) {
+                                  int shard_rank, NcclComm reduce_comm) {
     const int null_world = shard_world > 0 ? shard_world : opt.null_world, null_rank = shard_world > 0 ? shard_rank : opt.null_rank;
     int rc = ensure_init();
     if (rc) return rc;
@@ -2264,6 +2264,11 @@ int Engine::data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_ro
                 evals += c * suffix[n + 1];
             }
         }
+    }
+    if (reduce_comm && null_world > 1) {
+        // one process per GPU: the shards' tensors have disjoint supports -- one all-reduce(sum) leaves the whole tensor on every rank, exact
+        if (!nccl().loaded) return FGT_ERR_ARG;
+        if (nccl().AllReduce(d_out, d_out, (size_t)K * K * G, kNcclFloat64, kNcclSum, reduce_comm, st_) != 0) return FGT_ERR_CUDA;
     }
     CK(cudaEventRecord(e2, st_));
     vtick("null: all chromosomes launched");

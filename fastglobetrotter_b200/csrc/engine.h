@@ -93,7 +93,7 @@ class Engine {
     // the same call spread over opt.devices GPUs of this process (individuals in contiguous blocks, see dist.h)
     static int data_read_multi(const fgt_problem_t &pb, double *means, fgt_stats_t *stats);
     int data_read_null_packed(const fgt_problem_t &pb, const int32_t *rec_rows, double *out, fgt_stats_t *stats, int shard_world = 0,
-                              int shard_rank = 0);
+                              int shard_rank = 0, NcclComm reduce_comm = nullptr);   // reduce_comm: all-reduce the partial tensors on the device
     static int data_read_null_multi(const fgt_problem_t &pb, const int32_t *rec_rows, double *out, fgt_stats_t *stats);
     // callers of the path: opt-in entry points, see include/fgt_companion.h part 3
     int null_normalise(const double *tw, const double *null_mat, int S, int K, int G, double *means, double *null_curves);

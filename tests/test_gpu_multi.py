@@ -101,8 +101,11 @@ def _rank_main(rank, world, uid_q, res_q, ids, seed):
     m, raw, st = lib.data_read_packed(1, 2, spec.nsamples, chrom, my_ids, 0.1, G, 10, K, dl, 0.0, 1.0, S, tw, want_raw=True,
                                       num_inds_total=N)
     nxt = lib.rand_fill(3)
+    # the NULL tensor over the same process group: every rank passes the whole problem, folds its rows, gets the all-reduced tensor
+    init = np.random.default_rng(5).random(K * K * G)
+    nul, nst = lib.data_read_null_packed(2, spec.nsamples, chrom, np.arange(N), 0.1, G, 10, K, dl, 0.0, 1.0, init=init)
     lib.dist_finalize()
-    res_q.put((rank, m, raw, st["pairs"], nxt))
+    res_q.put((rank, m, raw, st["pairs"], nxt, nul, nst["pairs"]))
 
 
 @needs2
@@ -128,6 +131,10 @@ def test_one_process_per_gpu_with_the_library_process_group(oracle):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    n_o, ev = oracle.data_read_null_packed(2, spec.nsamples, chrom, np.arange(N), 0.1, G, 10, K, dl, 0.0, 1.0,
+                                           init=np.random.default_rng(5).random(K * K * G))
+    for r in (0, 1):
+        assert out[r][6] == ev and np.array_equal(out[r][5], n_o), r          # disjoint supports: the all-reduce is exact
     raw = np.concatenate([out[0][2], out[1][2]], axis=0)
     assert out[0][3] + out[1][3] == pairs_o
     assert np.array_equal(raw, raw_o)
