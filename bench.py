@@ -281,6 +281,28 @@ def run_ours(args):
         dense = {"value": pairs_d / dt_d, "ms_per_step": dt_d / 3 * 1e3, "e2e_value": pairs_dh / dt_dh, "e2e_ms_per_step": dt_dh / 3 * 1e3,
                  "e2e_h2d_bytes_per_step": agg_dh["h2d_bytes"] / 3}
 
+    null_dist = None
+    if world > 1 and not os.environ.get("FGT_BENCH_NO_NULL"):
+        # ONE data_read_null job (the first 100 recipients of rank 0's paintings) over all ranks: every rank passes the whole problem,
+        # folds its rows of the K x K x G tensor, one ncclAllReduce inside the library -- strong scaling of the NULL path
+        nchrom = []
+        for h in range(W["n_chrom"]):
+            pos, rate, run_off, runs = make_chromosome_runs_device(spec, h, dev, ind_offset=0)
+            keep.append(runs)
+            nchrom.append({"pos": pos, "rate": rate, "runs": (run_off, int(runs.data_ptr()))})
+        rows = np.arange(min(100, N), dtype=np.int32)
+        nargs = (W["ploidy"], W["nsamples"], nchrom, rows, W["bw"], G, W["grid_start"], K, dl, W["weight_min"], W["cutoff"])
+        lib.data_read_null_packed(*nargs)
+        barrier()
+        t0 = time.perf_counter()
+        nul, nst = lib.data_read_null_packed(*nargs)
+        barrier()
+        dt_n = time.perf_counter() - t0
+        tn = torch.tensor([dt_n], dtype=torch.float64, device=dev)
+        dist.all_reduce(tn, op=dist.ReduceOp.MAX)
+        null_dist = {"value": nst["pairs"] / float(tn[0]), "unit": "chunk-pair evaluations/s", "ms": float(tn[0]) * 1e3, "n_gpus": world,
+                     "scaling": "strong", "individuals": int(rows.size), "pair_evaluations": nst["pairs"], "checksum": float(np.sum(nul))}
+
     out = None
     if rank == 0:
         peak, peak_src = peaks()
@@ -341,6 +363,8 @@ def run_ours(args):
             out["dense_label_input"] = dense
         if world == 1:
             out["other_paths"] = other_paths(lib, chrom_dev, common, tail, S, tw, N, dl, K, G, W)
+        elif null_dist is not None:
+            out["other_paths"] = {"data_read_null": null_dist}
         if not args.no_cpu_baseline and world == 1:
             with tempfile.TemporaryDirectory() as tmp:
                 cb, files0, means_ref = cpu_baseline(sample_inds=args.cpu_sample_inds, procs=1, steps=3, warmup=0, tmp=tmp)

@@ -1859,7 +1859,7 @@ int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::v
         std::stable_sort(own.begin(), own.end(), [&](int x, int y) { return row_est[x] > row_est[y]; });
     }
     // bin ranges per label pair: hot pairs are cut into up to 32 ranges so that no commit task is much heavier than the rest
-    const int want_tasks = opt.null_tasks > 0 ? opt.null_tasks : 4096;
+    const int want_tasks = opt.null_tasks > 0 ? opt.null_tasks : std::max(1024, 4096 / std::max(1, null_world));   // per shard: the count tables scale with it
     int rmax = std::min(32, G);
     std::vector<NullPairPlan> plan((size_t)K * K);
     std::vector<NullRowPlan> rows(K);
