@@ -91,6 +91,8 @@ int Engine::set_option(const char *key, double v) {
     else if (k == "null_block") opt.null_block = iv;
     else if (k == "null_min_batches") opt.null_min_batches = std::max(1, iv);
     else if (k == "null_taper") opt.null_taper = iv;
+    else if (k == "null_eval_ctas") opt.null_eval_ctas = iv;
+    else if (k == "null_commit_ctas") opt.null_commit_ctas = iv;
     else if (k == "null_window") opt.null_window = iv;
     else if (k == "null_world") opt.null_world = std::max(1, iv);
     else if (k == "null_rank") opt.null_rank = std::max(0, iv);
@@ -133,6 +135,8 @@ double Engine::get_option(const char *key) {
     if (k == "null_block") return opt.null_block;
     if (k == "null_min_batches") return opt.null_min_batches;
     if (k == "null_taper") return opt.null_taper;
+    if (k == "null_eval_ctas") return opt.null_eval_ctas;
+    if (k == "null_commit_ctas") return opt.null_commit_ctas;
     if (k == "null_window") return opt.null_window;
     if (k == "null_world") return opt.null_world;
     if (k == "null_rank") return opt.null_rank;
@@ -1859,7 +1863,7 @@ int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::v
         std::stable_sort(own.begin(), own.end(), [&](int x, int y) { return row_est[x] > row_est[y]; });
     }
     // bin ranges per label pair: hot pairs are cut into up to 32 ranges so that no commit task is much heavier than the rest
-    const int want_tasks = opt.null_tasks > 0 ? opt.null_tasks : std::max(1024, 4096 / std::max(1, null_world));   // per shard: the count tables scale with it
+    const int want_tasks = opt.null_tasks > 0 ? opt.null_tasks : 4096;     // per shard: enough tasks to fill the GPU's commit CTAs
     int rmax = std::min(32, G);
     std::vector<NullPairPlan> plan((size_t)K * K);
     std::vector<NullRowPlan> rows(K);
@@ -2017,6 +2021,8 @@ int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::v
     size_t t0 = 0;
     int nb = 0;
     bool lane_used[2] = {false, false};
+    std::vector<cudaEvent_t> vb_events;              // verbose: per batch, events around the count pass, the scatter pass and the commit
+    std::vector<long long> vb_recs;
     size_t forced_t1 = 0;                            // a batch that overflowed is retried up to here
     long long left_bound = total_bound;              // expected records of the haplotype pairs not yet in a batch
     while (t0 < tiles.size()) {
@@ -2039,11 +2045,14 @@ int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::v
         RegionEnt *d_dir = (ln ? d_ndir2_ : d_ndir_).as<RegionEnt>(tab.size());
         if (!d_cnt || !d_off || !d_dir) return FGT_ERR_CUDA;
         ea.tiles = d_tiles + t0; ea.n_tiles = (int)T;
-        ea.max_ctas_per_sm = (overlap && nb > 0) ? 8 : 0;            // a commit of the previous batch shares the SMs
+        ea.max_ctas_per_sm = (overlap && nb > 0) ? opt.null_eval_ctas : 0;            // a commit of the previous batch shares the SMs
         // counts per (tile, task) -> [task][tile] -> exclusive scan = first record of every (task, tile) -> back to [tile][task]
         CK(cudaMemsetAsync(d_ctr + 8, 0, 2 * sizeof(unsigned long long), st_));
         ea.counts = d_cnt; ea.offs = nullptr; ea.recs = nullptr;
+        cudaEvent_t ev_t[6] = {};
+        if (opt.verbose) { for (auto &e : ev_t) cudaEventCreate(&e); cudaEventRecord(ev_t[0], st_); }
         launch_null_eval(ea, false, st_);
+        if (opt.verbose) cudaEventRecord(ev_t[1], st_);
         launch_sum_i32(d_cnt, n_cnt, reinterpret_cast<unsigned long long *>(d_ctr + 10), st_);
         CK(cudaMemcpyAsync(null_pin_, d_ctr + 10, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st_));
         CK(cudaStreamSynchronize(st_));
@@ -2062,7 +2071,9 @@ int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::v
         CK(cudaMemsetAsync(d_ctr + 8, 0, sizeof(unsigned long long), st_));
         ea.counts = nullptr; ea.offs = d_off;
         if (overlap && lane_used[ln]) CK(cudaStreamWaitEvent(st_, null_ev_[ln], 0));     // the lane's records and directory are free again
+        if (opt.verbose) cudaEventRecord(ev_t[2], st_);
         launch_null_eval(ea, true, st_);
+        if (opt.verbose) cudaEventRecord(ev_t[3], st_);
         launch_null_dir(d_cnt, d_perm, n_tasks, T, d_dir, st_);
         if (overlap) {
             CK(cudaEventRecord(null_ev_[2], st_));
@@ -2075,8 +2086,10 @@ int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::v
         ca.recs = d_recs; ca.regions = d_dir; ca.tensor_is_zero = 0; ca.buckets = 0;
         ca.tensor = d_out; ca.accepted = d_acc; ca.task_counter = ctr;
         ca.task_tab = d_tab; ca.n_task_tab = n_tasks; ca.max_tile_cells = max_w;
-        ca.max_ctas_per_sm = (overlap && t1 < tiles.size()) ? 10 : 0;   // the next batch's evaluation shares the SMs
+        ca.max_ctas_per_sm = (overlap && t1 < tiles.size()) ? opt.null_commit_ctas : 0;   // the next batch's evaluation shares the SMs
+        if (opt.verbose) cudaEventRecord(ev_t[4], sc);
         launch_commit_ordered(ca, max_w, sc);
+        if (opt.verbose) { cudaEventRecord(ev_t[5], sc); for (auto &e : ev_t) vb_events.push_back(e); vb_recs.push_back((long long)n_recs); }
         if (overlap) { CK(cudaEventRecord(null_ev_[ln], sc)); lane_used[ln] = true; }
         launches_ += 10;
         stx.accum_launches += 1;
@@ -2087,6 +2100,20 @@ int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::v
     }
     if (overlap)                                     // the tensor and this chromosome's tables are the evaluation stream's again
         for (int ln = 0; ln < 2; ln++) if (lane_used[ln]) CK(cudaStreamWaitEvent(st_, null_ev_[ln], 0));
+    if (opt.verbose && !vb_events.empty()) {
+        cudaStreamSynchronize(st_);
+        for (size_t b = 0; b * 6 < vb_events.size(); b++) {
+            float c = 0, sca = 0, com = 0, c0 = 0, c1 = 0;
+            cudaEventElapsedTime(&c, vb_events[b * 6], vb_events[b * 6 + 1]);
+            cudaEventElapsedTime(&sca, vb_events[b * 6 + 2], vb_events[b * 6 + 3]);
+            cudaEventElapsedTime(&com, vb_events[b * 6 + 4], vb_events[b * 6 + 5]);
+            cudaEventElapsedTime(&c0, vb_events[0], vb_events[b * 6 + 4]);
+            cudaEventElapsedTime(&c1, vb_events[0], vb_events[b * 6 + 5]);
+            fprintf(stderr, "[fgt] dev %d null batch %zu: %lld records, count %.2f ms, scatter %.2f ms, commit %.2f ms (from %.2f to %.2f ms)\n",
+                    device_, b, vb_recs[b], c, sca, com, c0, c1);
+        }
+        for (cudaEvent_t e : vb_events) cudaEventDestroy(e);
+    }
     return FGT_OK;
 }
 

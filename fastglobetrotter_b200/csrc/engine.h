@@ -62,6 +62,7 @@ struct Options {
     int null_block = -1;    // null_impl 2: take the labels of B in blocks (small label groups); -1 = when a label group averages < 24 chunks
     int null_window = -1;   // null_impl 2: windowed enumeration of phase 1; -1 = when under 90 % of the chunk pairs lie inside the distance window
     int null_min_batches = 4; // null_impl 2: batches per chromosome aimed at when the work allows (so that commit and evaluation overlap)
+    int null_eval_ctas = 8, null_commit_ctas = 10;   // null_impl 2: persistent CTAs per SM of the two sides while they overlap
     int null_taper = 1;     // null_impl 2: shrinking last batches (the last commit has nothing to overlap with)
     int null_overlap = 1;   // null_impl 2: fold batch b on the commit stream while batch b+1 is evaluated (two record buffers)
     int null_world = 1, null_rank = 0;   // sharded NULL run: this rank folds the label pairs it owns (sum of the ranks = exact)
