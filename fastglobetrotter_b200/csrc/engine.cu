@@ -84,6 +84,7 @@ int Engine::set_option(const char *key, double v) {
     else if (k == "spec_rand") opt.spec_rand = iv;
     else if (k == "null_target") opt.null_target = iv;
     else if (k == "commit_ctas") opt.commit_ctas = iv;
+    else if (k == "commit_consumers") opt.commit_consumers = iv;
     else if (k == "null_impl") opt.null_impl = iv;
     else if (k == "null_batch") opt.null_batch = v;
     else if (k == "null_tasks") opt.null_tasks = iv;
@@ -91,6 +92,7 @@ int Engine::set_option(const char *key, double v) {
     else if (k == "null_block") opt.null_block = iv;
     else if (k == "null_min_batches") opt.null_min_batches = std::max(1, iv);
     else if (k == "null_taper") opt.null_taper = iv;
+    else if (k == "null_consumers") opt.null_consumers = iv;
     else if (k == "null_eval_ctas") opt.null_eval_ctas = iv;
     else if (k == "null_commit_ctas") opt.null_commit_ctas = iv;
     else if (k == "null_window") opt.null_window = iv;
@@ -128,6 +130,7 @@ double Engine::get_option(const char *key) {
     if (k == "accum_impl") return opt.accum_impl;
     if (k == "spec_rand") return opt.spec_rand;
     if (k == "commit_ctas") return opt.commit_ctas;
+    if (k == "commit_consumers") return opt.commit_consumers;
     if (k == "null_impl") return opt.null_impl;
     if (k == "null_batch") return opt.null_batch;
     if (k == "null_tasks") return opt.null_tasks;
@@ -135,6 +138,7 @@ double Engine::get_option(const char *key) {
     if (k == "null_block") return opt.null_block;
     if (k == "null_min_batches") return opt.null_min_batches;
     if (k == "null_taper") return opt.null_taper;
+    if (k == "null_consumers") return opt.null_consumers;
     if (k == "null_eval_ctas") return opt.null_eval_ctas;
     if (k == "null_commit_ctas") return opt.null_commit_ctas;
     if (k == "null_window") return opt.null_window;
@@ -1224,6 +1228,7 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
                     span_begin(1, sc);
                     ca.buckets = opt.commit_impl == 1 ? 1 : 0;
                     ca.max_ctas_per_sm = opt.commit_ctas;
+                    ca.consumers = opt.commit_consumers;
                     ca.tensor = tens_b; ca.accepted = d_acc;
                     ca.task_counter = d_taskctr + batch_seq;
                     launch_commit_ordered(ca, plan_max_w, sc);
@@ -2086,7 +2091,8 @@ int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::v
         ca.recs = d_recs; ca.regions = d_dir; ca.tensor_is_zero = 0; ca.buckets = 0;
         ca.tensor = d_out; ca.accepted = d_acc; ca.task_counter = ctr;
         ca.task_tab = d_tab; ca.n_task_tab = n_tasks; ca.max_tile_cells = max_w;
-        ca.max_ctas_per_sm = (overlap && t1 < tiles.size()) ? opt.null_commit_ctas : 0;   // the next batch's evaluation shares the SMs
+        ca.max_ctas_per_sm = (overlap && t1 < tiles.size()) ? opt.null_commit_ctas : 0;
+        ca.consumers = opt.null_consumers;   // the next batch's evaluation shares the SMs
         if (opt.verbose) cudaEventRecord(ev_t[4], sc);
         launch_commit_ordered(ca, max_w, sc);
         if (opt.verbose) { cudaEventRecord(ev_t[5], sc); for (auto &e : ev_t) vb_events.push_back(e); vb_recs.push_back((long long)n_recs); }

@@ -917,7 +917,7 @@ __device__ __forceinline__ PairEval eval_pair(bool in_range, uint2 r, int t1, un
         o.local = row * sw + (bb - sb0);
         o.slot = slot;
         // gridweight = min(size, cutoff), as stored by the chunk builder (reference C:527)
-        o.val = __dmul_rn(fmin(A.size, a.cutoff), fmin(B.size, a.cutoff));     // sizes are never NaN: fmin == (size > cutoff ? cutoff : size)
+        o.val = __dmul_rn(A.size > a.cutoff ? a.cutoff : A.size, B.size > a.cutoff ? a.cutoff : B.size);   // reference C:527 (sizes are never NaN)
     }
     return o;
 }
@@ -936,11 +936,10 @@ constexpr int kJumpLevels = 6;     // base-256 digits of the raw offset: 2^48 ra
 __device__ __forceinline__ uint32_t gen_block31(uint32_t hist, int lane) {
     const uint32_t t = __shfl_sync(kFull, hist, (lane + 28) & 31);
     uint32_t a = hist + (lane < 3 ? t : 0u);
+    // shfl.up hands back its own in-range predicate: one shuffle and one predicated add per level
 #pragma unroll
-    for (int s = 3; s <= 24; s <<= 1) {
-        const uint32_t u = __shfl_up_sync(kFull, a, s);
-        if (lane >= s) a += u;
-    }
+    for (int s = 3; s <= 24; s <<= 1)
+        asm volatile("{\n.reg .pred p;\n.reg .b32 u;\nshfl.sync.up.b32 u|p, %0, %1, 0, 0xffffffff;\n@p add.u32 %0, %0, u;\n}\n" : "+r"(a) : "r"(s));
     return a;
 }
 
@@ -1078,16 +1077,21 @@ __global__ void __launch_bounds__(128, 8) k_eval_pairs(const EvalArgs a) {
                 // ordered partition of the two steps' updates into the segment's slab regions
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
-                    int pos = 0;
-#pragma unroll
-                    for (int s = 0; s < kMaxSlots; s++) {
-                        if (s < ns) {
-                            const unsigned m = __ballot_sync(kFull, e[h].slot == s);
-                            if (e[h].slot == s) pos = c[s] + __popc(m & lt);
-                            c[s] += __popc(m);
-                        }
-                    }
-                    if (e[h].slot >= 0) {
+                    // three ballots (accepted, slot bit 0, slot bit 1) give the lane mask of every slot: no branch on the
+                    // number of slots in use (slots nobody holds have empty masks)
+                    static_assert(kMaxSlots == 4, "two slot bits");
+                    const int sl = e[h].slot;
+                    const unsigned bv = __ballot_sync(kFull, sl >= 0);
+                    const unsigned b0 = __ballot_sync(kFull, (sl & 1) != 0);
+                    const unsigned b1 = __ballot_sync(kFull, (sl & 2) != 0);
+                    const unsigned lo = bv & ~b1, hi = bv & b1;
+                    const unsigned m0 = lo & ~b0, m1 = lo & b0, m2 = hi & ~b0, m3 = hi & b0;
+                    const bool s0 = (sl & 1) != 0, s1 = (sl & 2) != 0;
+                    const unsigned mine = s1 ? (s0 ? m3 : m2) : (s0 ? m1 : m0);
+                    const int cs = s1 ? (s0 ? c[3] : c[2]) : (s0 ? c[1] : c[0]);
+                    const int pos = cs + __popc(mine & lt);
+                    c[0] += __popc(m0); c[1] += __popc(m1); c[2] += __popc(m2); c[3] += __popc(m3);
+                    if (sl >= 0) {
                         UpdateRec rec;
                         rec.cell = e[h].cell; rec.pad = e[h].local; rec.val = e[h].val;
                         reg[(long long)e[h].slot * Y + pos] = rec;
@@ -1186,8 +1190,11 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 constexpr int kQCap = 32;         // slots per lane queue (a single 32-record step always fits)
 constexpr int kQueueBytes = kConsumers * (kQCap * 32 * (int)(sizeof(double) + sizeof(int32_t)) + 32 * (int)sizeof(int32_t));
 
-template <bool TILE_SMEM, bool BUCKETS>
-__global__ void __launch_bounds__(32 * (kConsumers + 1)) k_commit_ordered(const CommitArgs a) {
+// NC consumer warps per CTA.  With two, both warps read and match every record and fold only the cells they own (records of the
+// other warp share one sentinel key); with one (the default of both callers) no record is matched twice: the match.any unit is
+// the binding resource, and the second warp's sentinel keys cost more than sharing the fold chains saves.
+template <bool TILE_SMEM, bool BUCKETS, int NC = kConsumers>
+__global__ void __launch_bounds__(32 * (NC + 1)) k_commit_ordered(const CommitArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     UpdateRec *ring = reinterpret_cast<UpdateRec *>(smem_raw);                         // [kStages][kStageRecs]
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kStages * kStageRecs * sizeof(UpdateRec));
@@ -1205,7 +1212,7 @@ __global__ void __launch_bounds__(32 * (kConsumers + 1)) k_commit_ordered(const 
     const bool tabbed = a.task_tab != nullptr;               // explicit task table (NULL path): one tile and one record region per entry
     const int total_tasks = tabbed ? a.n_task_tab : a.N * a.n_slabs * RB;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], kConsumers); }
+        for (int s = 0; s < kStages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NC); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     // ring position: carried across tasks (the end marker of a task occupies a stage like any other)
@@ -1249,7 +1256,7 @@ __global__ void __launch_bounds__(32 * (kConsumers + 1)) k_commit_ordered(const 
         }
         __syncthreads();
 
-        if (wid == kConsumers) {
+        if (wid == NC) {
             // ------------------------------ producer ------------------------------
             // routed records (row blocks): one contiguous region per task; otherwise the slab's (j, d) region directory
             const long long n_ent = (RB > 1 || tabbed) ? 1 : (long long)(a.cp.nb - 1) * a.nd_max;
@@ -1317,7 +1324,8 @@ __global__ void __launch_bounds__(32 * (kConsumers + 1)) k_commit_ordered(const 
             // ownership: BUCKETS -- alternate blocks of 32 tile cells (the low five bits pick the lane queue, so the 32
             // lanes of a fold pass hit 32 consecutive doubles: conflict free); otherwise odd / even cells
             auto owned = [&](int local) -> bool {
-                return BUCKETS ? (((unsigned)local >> 5) % kConsumers == (unsigned)wid) : ((unsigned)local % kConsumers == (unsigned)wid);
+                if (NC == 1) return true;
+                return BUCKETS ? (((unsigned)local >> 5) % NC == (unsigned)wid) : ((unsigned)local % NC == (unsigned)wid);
             };
             auto fetch = [&]() -> Staged {
                 Staged s;
@@ -1455,6 +1463,7 @@ void launch_commit_ordered(const CommitArgs &a, int max_slab_width, cudaStream_t
     if (tile_bytes + ctrl_bytes <= 200 * 1024) {
         if (!attr_set[dev & 63]) {
             cudaFuncSetAttribute(k_commit_ordered<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(k_commit_ordered<true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             cudaFuncSetAttribute(k_commit_ordered<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + kQueueBytes);
             attr_set[dev & 63] = true;
         }
@@ -1464,7 +1473,11 @@ void launch_commit_ordered(const CommitArgs &a, int max_slab_width, cudaStream_t
         if (a.max_ctas_per_sm > 0) per_sm = std::min<long long>(per_sm, a.max_ctas_per_sm);
         const long long grid = std::min<long long>(tasks, 148 * std::min<long long>(per_sm, 32));
         if (buckets) k_commit_ordered<true, true><<<(unsigned)grid, 32 * (kConsumers + 1), smem, st>>>(a);
-        else k_commit_ordered<true, false><<<(unsigned)grid, 32 * (kConsumers + 1), smem, st>>>(a);
+        else if (a.consumers == 1) {
+            const long long per_sm1 = a.max_ctas_per_sm > 0 ? std::min<long long>(a.max_ctas_per_sm, 32) : std::min<long long>(32, std::max<long long>(1, (227 * 1024) / (long long)(smem + 1024)));
+            const long long grid1 = std::min<long long>(tasks, 148 * per_sm1);
+            k_commit_ordered<true, false, 1><<<(unsigned)grid1, 64, smem, st>>>(a);
+        } else k_commit_ordered<true, false><<<(unsigned)grid, 32 * (kConsumers + 1), smem, st>>>(a);
     } else {
         const long long grid = std::min<long long>(tasks, 148 * 16);
         k_commit_ordered<false, false><<<(unsigned)grid, 32 * (kConsumers + 1), ctrl_bytes, st>>>(a);
