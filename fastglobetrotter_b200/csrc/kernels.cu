@@ -1092,9 +1092,10 @@ __global__ void __launch_bounds__(128, 8) k_eval_pairs(const EvalArgs a) {
                     const int pos = cs + __popc(mine & lt);
                     c[0] += __popc(m0); c[1] += __popc(m1); c[2] += __popc(m2); c[3] += __popc(m3);
                     if (sl >= 0) {
-                        UpdateRec rec;
-                        rec.cell = e[h].cell; rec.pad = e[h].local; rec.val = e[h].val;
-                        reg[(long long)e[h].slot * Y + pos] = rec;
+                        // one 16-byte store per record
+                        const long long vb = __double_as_longlong(e[h].val);
+                        *reinterpret_cast<int4 *>(&reg[(long long)sl * Y + pos]) =
+                            make_int4(e[h].cell, e[h].local, (int)(vb & 0xffffffffLL), (int)(vb >> 32));
                     }
                 }
             }
@@ -1697,11 +1698,16 @@ k_project(const double *__restrict__ tensor, int K, int G, int S, const double *
             int mn = m0 + ty + TY * u, i = i0 + tx + 16 * v;
             acc[u][v] = (mn < SS && i < G) ? out[(size_t)mn * G + i] : 0.0;
         }
+    // A slice is PKK x PTM = 4 * blockDim.x weights: thread t loads rows prA, prA + 4, prA + 8, prA + 12 of column cA (one
+    // division per thread, outside the loop over slices)
+    const int prA = threadIdx.x / PTM, cA = threadIdx.x - prA * PTM;
+    const bool okA = m0 + cA < SS;
+    const double *twA = tw + m0 + cA;
     for (int p0 = 0; p0 < P; p0 += PKK) {
-        for (int e = threadIdx.x; e < PKK * PTM; e += blockDim.x) {
-            const int pr = e / PTM, c = e - pr * PTM;
-            const int p = p0 + pr;
-            sA[pr][c] = (p < P && m0 + c < SS) ? tw[(size_t)pair_kh[p] * SS + m0 + c] : 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int p = p0 + prA + 4 * q;
+            sA[prA + 4 * q][cA] = (p < P && okA) ? twA[(size_t)pair_kh[p] * SS] : 0.0;
         }
         for (int e = threadIdx.x; e < PKK * PT; e += blockDim.x) {
             const int pr = e / PT, c = e % PT;

@@ -19,11 +19,11 @@ for oset in os.environ.get("OPTSETS", "").split(";") or [""]:
     kv = [x.split("=") for x in oset.split(",") if x]
     for k, v in kv:
         defaults.setdefault(k, lib.get_option(k)); lib.set_option(k, float(v))
-    acc, tot = [], []
+    acc, tot, prj = [], [], []
     for rep in range(8):
         lib.srand(11); torch.cuda.synchronize(); t0 = time.perf_counter()
         m, _, st = lib.data_read_packed(MODE, 2, 10, chrom, ids, 0.1, G, 10, K, dl, 0.0, 1.0, S, tw)
         torch.cuda.synchronize(); t1 = time.perf_counter()
-        if rep >= 3: acc.append(st["ms_accum"]); tot.append((t1 - t0) * 1e3)
-    print(f"{oset or 'default':40s} ms_accum {np.mean(acc):.3f} (min {np.min(acc):.3f})  call {np.mean(tot):.3f} ms  pairs {st['pairs']}  sha {hashlib.sha256(np.ascontiguousarray(m).tobytes()).hexdigest()[:12]}", flush=True)
+        if rep >= 3: acc.append(st["ms_accum"]); tot.append((t1 - t0) * 1e3); prj.append(st.get("ms_project", 0.0))
+    print(f"{oset or 'default':40s} ms_accum {np.mean(acc):.3f} (min {np.min(acc):.3f})  call {np.mean(tot):.3f} ms  project {np.mean(prj):.3f}  pairs {st['pairs']}  sha {hashlib.sha256(np.ascontiguousarray(m).tobytes()).hexdigest()[:12]}", flush=True)
     for k, v in defaults.items(): lib.set_option(k, v)
