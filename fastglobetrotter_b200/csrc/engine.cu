@@ -85,6 +85,8 @@ int Engine::set_option(const char *key, double v) {
     else if (k == "null_target") opt.null_target = iv;
     else if (k == "commit_ctas") opt.commit_ctas = iv;
     else if (k == "commit_consumers") opt.commit_consumers = iv;
+    else if (k == "commit_tags") opt.commit_tags = iv;
+    else if (k == "null_tags") opt.null_tags = iv;
     else if (k == "null_impl") opt.null_impl = iv;
     else if (k == "null_batch") opt.null_batch = v;
     else if (k == "null_tasks") opt.null_tasks = iv;
@@ -131,6 +133,8 @@ double Engine::get_option(const char *key) {
     if (k == "spec_rand") return opt.spec_rand;
     if (k == "commit_ctas") return opt.commit_ctas;
     if (k == "commit_consumers") return opt.commit_consumers;
+    if (k == "commit_tags") return opt.commit_tags;
+    if (k == "null_tags") return opt.null_tags;
     if (k == "null_impl") return opt.null_impl;
     if (k == "null_batch") return opt.null_batch;
     if (k == "null_tasks") return opt.null_tasks;
@@ -1228,7 +1232,7 @@ int Engine::data_read_packed_impl(const fgt_problem_t &pb, double *means, fgt_st
                     span_begin(1, sc);
                     ca.buckets = opt.commit_impl == 1 ? 1 : 0;
                     ca.max_ctas_per_sm = opt.commit_ctas;
-                    ca.consumers = opt.commit_consumers;
+                    ca.consumers = opt.commit_consumers; ca.tags = opt.commit_tags;
                     ca.tensor = tens_b; ca.accepted = d_acc;
                     ca.task_counter = d_taskctr + batch_seq;
                     launch_commit_ordered(ca, plan_max_w, sc);
@@ -2092,7 +2096,7 @@ int Engine::null_two_phase(const fgt_problem_t &pb, ChromState &cs, const std::v
         ca.tensor = d_out; ca.accepted = d_acc; ca.task_counter = ctr;
         ca.task_tab = d_tab; ca.n_task_tab = n_tasks; ca.max_tile_cells = max_w;
         ca.max_ctas_per_sm = (overlap && t1 < tiles.size()) ? opt.null_commit_ctas : 0;
-        ca.consumers = opt.null_consumers;   // the next batch's evaluation shares the SMs
+        ca.consumers = opt.null_consumers; ca.tags = opt.null_tags;   // the next batch's evaluation shares the SMs
         if (opt.verbose) cudaEventRecord(ev_t[4], sc);
         launch_commit_ordered(ca, max_w, sc);
         if (opt.verbose) { cudaEventRecord(ev_t[5], sc); for (auto &e : ev_t) vb_events.push_back(e); vb_recs.push_back((long long)n_recs); }

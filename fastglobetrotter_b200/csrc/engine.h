@@ -54,7 +54,10 @@ struct Options {
     int copy_streams = 1;   // 2 = alternate the label block copies between two streams (two DMA engines)
     int project_impl = 0;   // 0 = exact (separately rounded multiply and add, bit-identical curves); 1 = FP64 tensor cores (~1e-14)
     int null_target = 0;    // NULL task table: accepted pairs per (haplotype pair, slab) a task aims at; 0 = default
-    int commit_consumers = 1; // data_read: consumer warps per commit CTA (1: no record is matched by a warp that does not own it; accumulation 3.41 -> 3.30 ms)
+    int commit_consumers = 4; // data_read: consumer warps per commit CTA: 4 = step-wise (two sets of two warps, folds handed over through named
+                            // barriers; accumulation 3.30 -> 2.64 ms with commit_tags), 1 / 2 = one / two warps that fold whole stages
+    int commit_tags = 1;    // commit_consumers = 4: tag arrays resolve steps of distinct cells and of couples without match.any
+    int null_tags = 0;      // the same for the NULL path's commit (null_consumers = 4); its small tiles make most steps fall back
     int commit_ctas = 0;    // > 0: cap of the commit kernel's persistent CTAs per SM (room for the next range's evaluation kernel)
     int null_impl = 0;      // NULL path: 2 = two phases (every chunk pair evaluated once into records, ordered commit), 1 = k_null_strict,
                             // 0 = two phases whenever its tables allow (K <= 4096, G < 65536)
@@ -64,7 +67,7 @@ struct Options {
     int null_window = -1;   // null_impl 2: windowed enumeration of phase 1; -1 = when under 90 % of the chunk pairs lie inside the distance window
     int null_min_batches = 4; // null_impl 2: batches per chromosome aimed at when the work allows (so that commit and evaluation overlap)
     int null_eval_ctas = 8, null_commit_ctas = 16;   // null_impl 2: persistent CTAs per SM of the two sides while they overlap
-    int null_consumers = 1; // null_impl 2: consumer warps per commit CTA (1 or 2; bench chromosome 93 -> 86 ms with 1)
+    int null_consumers = 1; // null_impl 2: consumer warps per commit CTA (1, 2 or 4; bench chromosome 93 / 86 / 105 ms with 2 / 1 / 4)
     int null_taper = 1;     // null_impl 2: shrinking last batches (the last commit has nothing to overlap with)
     int null_overlap = 1;   // null_impl 2: fold batch b on the commit stream while batch b+1 is evaluated (two record buffers)
     int null_world = 1, null_rank = 0;   // sharded NULL run: this rank folds the label pairs it owns (sum of the ranks = exact)

@@ -1145,8 +1145,10 @@ void launch_eval_pairs(const EvalArgs &a, cudaStream_t st) {
 // the slab tile, which lives in shared memory when it fits (TILE_SMEM), so the ordered
 // read-modify-write chain runs at shared-memory latency and global latency is off the critical path.
 constexpr int kStages = 3;        // ring depth
+constexpr int kStagesStepwise = 4; // ring depth of the step-wise variant (even: each set of consumers walks every other slot; 6 measured equal)
 constexpr int kStageRecs = 128;   // records per ring stage (four consumer steps); stages are packed across regions
 constexpr int kStageSteps = kStageRecs / 32;
+constexpr int kTagSlots = 512;    // STEPWISE: slots of a tag array (two arrays per consumer warp, one byte per slot)
 constexpr int kConsumers = 2;     // consumer warps per CTA; each owns the tile cells with local % kConsumers == warp
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -1194,17 +1196,30 @@ constexpr int kQueueBytes = kConsumers * (kQCap * 32 * (int)(sizeof(double) + si
 // NC consumer warps per CTA.  With two, both warps read and match every record and fold only the cells they own (records of the
 // other warp share one sentinel key); with one (the default of both callers) no record is matched twice: the match.any unit is
 // the binding resource, and the second warp's sentinel keys cost more than sharing the fold chains saves.
-template <bool TILE_SMEM, bool BUCKETS, int NC = kConsumers>
+//
+// STEPWISE (shared-memory tiles, NC = 4): two sets of two consumer warps; set q takes the stages k = q (mod 2) of the record
+// stream, its warp h the steps 2h and 2h+1 (32 records each) of the stage.  Waiting for the stage, reading the records,
+// releasing the stage and finding the lanes that share a cell run in four warps at once, a stage ahead of the folds; only
+// the folds are serial -- the turn travels w0 -> w1 -> w2 -> w3 -> w0 through named barriers (one hand-over per 64 records), so
+// the steps are folded in stream order.  With one consumer warp the whole per-stage chain (wait, loads, fence, four
+// matches, four folds: ~2 000 cycles) is one warp's latency and the SM's match.any unit is the binding resource.
+template <bool TILE_SMEM, bool BUCKETS, int NC = kConsumers, bool STEPWISE = false>
 __global__ void __launch_bounds__(32 * (NC + 1)) k_commit_ordered(const CommitArgs a) {
+    static_assert(!STEPWISE || (TILE_SMEM && !BUCKETS && NC == kStageSteps), "step-wise consumers: one warp per step of a stage");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    UpdateRec *ring = reinterpret_cast<UpdateRec *>(smem_raw);                         // [kStages][kStageRecs]
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kStages * kStageRecs * sizeof(UpdateRec));
-    uint64_t *empty = full + kStages;
-    int *stage_cnt = reinterpret_cast<int *>(empty + kStages);                         // [kStages]
-    int *task_slot = stage_cnt + kStages;                                              // [1] task broadcast
-    RegionEnt *dir = reinterpret_cast<RegionEnt *>(smem_raw + 6144 + 256);              // [32] staged directory entries
-    unsigned char *qbase = smem_raw + 6144 + 1024;                                     // ring 6 KB + 1 KB control, then the queues
+    constexpr int RS = STEPWISE ? kStagesStepwise : kStages;    // ring depth
+    static_assert(kStagesStepwise % 2 == 0, "each set of step-wise consumers walks every other ring slot");
+    constexpr int kRing = RS * kStageRecs * (int)sizeof(UpdateRec);
+    UpdateRec *ring = reinterpret_cast<UpdateRec *>(smem_raw);                         // [RS][kStageRecs]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kRing);
+    uint64_t *empty = full + RS;
+    int *stage_cnt = reinterpret_cast<int *>(empty + RS);                              // [RS]
+    int *task_slot = stage_cnt + RS;                                                   // [1] task broadcast
+    RegionEnt *dir = reinterpret_cast<RegionEnt *>(smem_raw + kRing + 256);             // [32] staged directory entries
+    unsigned char *qbase = smem_raw + kRing + 1024;                                    // ring + 1 KB control, then the queues
+    static_assert(2 * RS * 8 + RS * 4 + 4 <= 256, "control block layout");
     double *tile = reinterpret_cast<double *>(qbase + (BUCKETS ? kQueueBytes : 0));
+    volatile unsigned char *tags = (STEPWISE && a.tag_off > 0) ? reinterpret_cast<unsigned char *>(tile) + a.tag_off : nullptr;
     const int lane = lane_id();
     const int wid = warp_id();
     const int G = a.G;
@@ -1213,14 +1228,15 @@ __global__ void __launch_bounds__(32 * (NC + 1)) k_commit_ordered(const CommitAr
     const bool tabbed = a.task_tab != nullptr;               // explicit task table (NULL path): one tile and one record region per entry
     const int total_tasks = tabbed ? a.n_task_tab : a.N * a.n_slabs * RB;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NC); }
+        for (int s = 0; s < RS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], STEPWISE ? 2 : NC); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     // ring position: carried across tasks (the end marker of a task occupies a stage like any other)
-    int stage = 0;
+    int stage = (STEPWISE && warp_id() < NC) ? warp_id() >> 1 : 0;   // STEPWISE consumers start at their set's first stage
     unsigned phase = 0;
     unsigned long long n_acc = 0;
     const unsigned lt = (1u << lane) - 1;
+    bool first_turn = warp_id() == 0;                        // STEPWISE: the very first turn (warp 0's) waits for nobody
 
     // Persistent CTA: tasks (heavy slabs first) are claimed from a global counter, so the grid never has
     // blocks waiting and kernels of other streams (the next range's evaluation) can share the SMs.
@@ -1262,57 +1278,66 @@ __global__ void __launch_bounds__(32 * (NC + 1)) k_commit_ordered(const CommitAr
             // routed records (row blocks): one contiguous region per task; otherwise the slab's (j, d) region directory
             const long long n_ent = (RB > 1 || tabbed) ? 1 : (long long)(a.cp.nb - 1) * a.nd_max;
             const RegionEnt *ents = tabbed ? a.regions + task : a.regions + (((size_t)n * a.n_slabs + slab_i) * RB + rb) * n_ent;
+            // All 32 lanes work: lane l holds entry e0 + l; a prefix sum over the batch's counts gives every region its place in
+            // the task's record stream, and for every stage the batch touches each lane issues its own piece (at most one per
+            // stage and lane).  Lane 0 alone opens a stage (waits for it to be empty) and closes it (count, arrive).
+            // [one lane walking the regions one by one -- ~130 dependent instructions per stage -- was what bounded a CTA
+            //  once the consumers had become fast]
             RegionEnt cur, nxt;
             cur.base = 0; cur.cnt = 0; cur.pad = 0;
             if (lane < n_ent) cur = ents[lane];
-            int fill = 0;                                  // records already placed in the open stage (lane 0's view)
+            int fill = 0;                                  // records already placed in the open stage
             bool open = false;
             for (long long e0 = 0; e0 < n_ent; e0 += 32) {
                 nxt.base = 0; nxt.cnt = 0; nxt.pad = 0;
                 if (e0 + 32 + lane < n_ent) nxt = ents[e0 + 32 + lane];     // in flight while this batch is issued
-                const unsigned live = __ballot_sync(kFull, cur.cnt > 0);
-                if (live) {
-                    dir[lane] = cur;
-                    __syncwarp();
-                    if (lane == 0) {
-                        unsigned m = live;
-                        while (m) {
-                            const int i = __ffs(m) - 1;
-                            m &= m - 1;
-                            const int c = dir[i].cnt;
-                            const UpdateRec *src = a.recs + dir[i].base;
-                            int off = 0;
-                            while (off < c) {              // stages are packed: a stage takes pieces of consecutive regions
-                                if (!open) { mbar_wait(&empty[stage], phase ^ 1); fence_proxy_async_smem(); open = true; fill = 0; }
-                                const int piece = min(c - off, kStageRecs - fill);
-                                const unsigned bytes = (unsigned)piece * (unsigned)sizeof(UpdateRec);
-                                mbar_expect_tx(&full[stage], bytes);
-                                bulk_g2s(&ring[stage * kStageRecs + fill], src + off, bytes, &full[stage]);
-                                fill += piece; off += piece;
-                                if (fill == kStageRecs) {
-                                    stage_cnt[stage] = fill;
-                                    mbar_arrive(&full[stage]);
-                                    open = false;
-                                    if (++stage == kStages) { stage = 0; phase ^= 1; }
-                                }
-                            }
-                        }
+                const long long c = cur.cnt > 0 ? (long long)cur.cnt : 0;
+                long long incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const long long t = __shfl_up_sync(kFull, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                const long long total = __shfl_sync(kFull, incl, 31);
+                const long long start = incl - c;          // this lane's region inside the batch: [start, start + c)
+                const UpdateRec *src = a.recs + cur.base;
+                long long done = 0;                        // records of the batch already placed
+                while (done < total) {
+                    if (!open) {
+                        if (lane == 0) { mbar_wait(&empty[stage], phase ^ 1); fence_proxy_async_smem(); }
+                        __syncwarp();
+                        open = true; fill = 0;
                     }
-                    __syncwarp();
+                    const long long take = min((long long)(kStageRecs - fill), total - done);   // records this stage takes now
+                    const long long lo = max(start, done), hi = min(start + c, done + take);
+                    if (hi > lo) {
+                        const unsigned bytes = (unsigned)(hi - lo) * (unsigned)sizeof(UpdateRec);
+                        mbar_expect_tx(&full[stage], bytes);
+                        bulk_g2s(&ring[stage * kStageRecs + fill + (int)(lo - done)], src + (lo - start), bytes, &full[stage]);
+                    }
+                    fill += (int)take; done += take;
+                    __syncwarp();                          // every piece of the stage is announced before lane 0 arrives
+                    if (fill == kStageRecs) {
+                        if (lane == 0) { stage_cnt[stage] = fill; mbar_arrive(&full[stage]); }
+                        open = false;
+                        if (++stage == RS) { stage = 0; phase ^= 1; }
+                    }
                 }
                 cur = nxt;
             }
-            if (lane == 0) {
-                if (open) {                                // last, partially filled stage
-                    stage_cnt[stage] = fill;
-                    mbar_arrive(&full[stage]);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
-                }
-                mbar_wait(&empty[stage], phase ^ 1);       // end marker: occupies one stage
-                stage_cnt[stage] = -1;
-                mbar_arrive(&full[stage]);
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            if (open) {                                    // last, partially filled stage
+                if (lane == 0) { stage_cnt[stage] = fill; mbar_arrive(&full[stage]); }
+                if (++stage == RS) { stage = 0; phase ^= 1; }
             }
+            for (int mk = 0; mk < (STEPWISE ? 2 : 1); mk++) {   // end marker: occupies one stage (one per set of consumer warps)
+                if (lane == 0) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    stage_cnt[stage] = -1;
+                    mbar_arrive(&full[stage]);
+                }
+                if (++stage == RS) { stage = 0; phase ^= 1; }
+            }
+            __syncwarp();
             stage = __shfl_sync(kFull, stage, 0);
             phase = __shfl_sync(kFull, phase, 0);
         } else {
@@ -1349,7 +1374,7 @@ __global__ void __launch_bounds__(32 * (NC + 1)) k_commit_ordered(const CommitAr
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[stage]);     // records are in registers: the stage can be refilled
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                if (++stage == RS) { stage = 0; phase ^= 1; }
                 if (!BUCKETS && s.c >= 0) {
                     // Lanes that share a cell must add in lane order, so every step needs, per lane, the set of lanes
                     // with the same cell: match.any (two cycles per distinct key on the SM's single unit; records of
@@ -1360,7 +1385,117 @@ __global__ void __launch_bounds__(32 * (NC + 1)) k_commit_ordered(const CommitAr
                 }
                 return s;
             };
-            if (BUCKETS) {
+            if (STEPWISE) {
+                // Two sets of two warps: set q takes the stages k = q (mod 2) of the stream, its warp h the steps 2h and 2h+1 of
+                // the stage.  The turn travels w0 -> w1 (stage k) -> w2 -> w3 (stage k+1) -> w0 ...: one hand-over per 64 records.
+                // kind 0: 32 distinct cells; 1: cells shared by at most two lanes, g = the partner lane (own lane: none);
+                // 2: g = match.any mask
+                struct Step { int cell; double val; unsigned g; int kind; };
+                struct Two { int c; Step s[2]; };
+                const int half = wid & 1;
+                volatile unsigned char *tA = tags ? tags + wid * 2 * kTagSlots : nullptr, *tB = tA + kTagSlots;
+                auto classify = [&](Step &s) {
+                    // Lanes that share a cell must add in lane order.  match.any would give every lane the lanes with its
+                    // cell, at ~30 + 2 cycles per distinct key on the SM's single unit -- the binding resource of the earlier
+                    // forms of this kernel.  Measured on the bench workload: 41 % of the steps have 32 distinct cells, 56 % have
+                    // nothing worse than pairs, 3 % a cell shared by three or more lanes.  Two private tag arrays per warp (a
+                    // byte per slot, slot = cell mod kTagSlots) sort the first two classes out without match.any:
+                    //   round 1: every lane writes its number at its slot and re-reads: the last writer "wins" the slot;
+                    //   round 2: the lanes that lost write their number into the second array and re-read: a loser that does
+                    //            not find itself is one of several losers of its slot -> the step falls back to match.any.
+                    // Otherwise every slot holds one lane or one (winner, loser) couple; the two find each other through the
+                    // tags (the winner checks with a shuffle that its candidate really lost THIS step's slot -- the second
+                    // array may hold an older step's number), and are a pair iff their cells (not only their slots) agree.
+                    const bool valid = s.cell >= 0;
+                    const int slot = s.cell & (kTagSlots - 1);
+                    s.kind = 2;
+                    if (tA) {
+                        if (valid) tA[slot] = (unsigned char)lane;
+                        __syncwarp();
+                        const int t = valid ? tA[slot] : lane;
+                        const bool lost = valid && t != lane;
+                        if (!__any_sync(kFull, lost)) s.kind = 0;
+                        else {
+                            if (lost) tB[slot] = (unsigned char)lane;
+                            __syncwarp();
+                            const int u = valid ? tB[slot] : lane;
+                            const bool bad = lost && u != lane;
+                            const int cand = (lost ? t : u) & 31;
+                            const int c_cell = __shfl_sync(kFull, s.cell, cand);
+                            const int c_lost = __shfl_sync(kFull, (int)lost, cand);
+                            bool paired;
+                            if (lost) paired = c_cell == s.cell;              // the winner of my slot is this step's by construction
+                            else paired = valid && c_lost && c_cell == s.cell;  // my candidate lost this step, to my very cell
+                            if (!__any_sync(kFull, bad)) { s.kind = 1; s.g = (unsigned)(paired ? cand : lane); }
+                        }
+                        __syncwarp();                              // the arrays are free for the next step
+                    }
+                    if (s.kind == 2) s.g = __match_any_sync(kFull, (unsigned)s.cell);
+                };
+                auto fetch2 = [&]() -> Two {
+                    Two t;
+                    mbar_wait(&full[stage], phase);
+                    t.c = stage_cnt[stage];
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        t.s[h].cell = -1; t.s[h].val = 0.0; t.s[h].g = 0; t.s[h].kind = 0;
+                        const int idx = 32 * (2 * half + h) + lane;
+                        if (idx < t.c) {
+                            const UpdateRec r = ring[stage * kStageRecs + idx];
+                            t.s[h].cell = r.pad; t.s[h].val = r.val;
+                        }
+                    }
+                    fence_proxy_async_smem();                  // generic-proxy reads before the async-proxy refill (see below)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[stage]);
+                    stage += 2;                                // the next stage of this set
+                    if (stage >= RS) { stage -= RS; phase ^= 1; }
+#pragma unroll
+                    for (int h = 0; h < 2; h++)
+                        if (32 * (2 * half + h) < t.c) classify(t.s[h]);
+                    return t;
+                };
+                auto fold1 = [&](const Step &s, double pv) {
+                    if (s.kind == 0) {
+                        if (s.cell >= 0) tile[s.cell] = __dadd_rn(tile[s.cell], s.val);
+                    } else if (s.kind == 1) {
+                        const int partner = (int)s.g;
+                        if (s.cell >= 0 && partner >= lane) {              // the lower lane of a couple adds both, in lane order
+                            double acc = __dadd_rn(tile[s.cell], s.val);
+                            if (partner != lane) acc = __dadd_rn(acc, pv);
+                            tile[s.cell] = acc;
+                        }
+                    } else {
+                        const bool leader = (s.cell >= 0) && ((s.g & lt) == 0);
+                        double acc = leader ? tile[s.cell] : 0.0;
+                        unsigned rest = leader ? (s.g & ~(1u << lane)) : 0u;
+                        acc = __dadd_rn(acc, s.val);
+                        while (__any_sync(kFull, rest != 0)) {
+                            const int src = rest ? (__ffs(rest) - 1) : lane;
+                            const double v = __shfl_sync(kFull, s.val, src);
+                            if (rest) { acc = __dadd_rn(acc, v); rest &= rest - 1; }
+                        }
+                        if (leader) tile[s.cell] = acc;
+                    }
+                };
+                const int bar_wait = 1 + wid, bar_next = 1 + ((wid + 1) & (kStageSteps - 1));
+                Two cur = fetch2();
+                while (cur.c >= 0) {
+                    const Two nxt = fetch2();
+                    // a couple's other addend, fetched before the turn
+                    const double pv0 = __shfl_sync(kFull, cur.s[0].val, cur.s[0].kind == 1 ? (int)cur.s[0].g : lane);
+                    const double pv1 = __shfl_sync(kFull, cur.s[1].val, cur.s[1].kind == 1 ? (int)cur.s[1].g : lane);
+                    // the turn: named barrier 1 + w counts this warp's 32 threads and the 32 of its predecessor's bar.arrive
+                    // (a hardware barrier hand-over; an mbarrier token costs about twice the latency, polling a flag far more)
+                    if (!first_turn) asm volatile("bar.sync %0, 64;\n" ::"r"(bar_wait) : "memory");
+                    first_turn = false;
+                    if (32 * (2 * half) < cur.c) fold1(cur.s[0], pv0);
+                    if (32 * (2 * half + 1) < cur.c) { __syncwarp(); fold1(cur.s[1], pv1); }
+                    asm volatile("bar.arrive %0, 64;\n" ::"r"(bar_next) : "memory");
+                    if (half == 0) n_acc += (unsigned long long)cur.c;
+                    cur = nxt;
+                }
+            } else if (BUCKETS) {
                 double *qval = reinterpret_cast<double *>(qbase) + (size_t)wid * kQCap * 32;                         // [slot][lane]
                 int32_t *qloc = reinterpret_cast<int32_t *>(qbase + kConsumers * kQCap * 32 * sizeof(double)) + (size_t)wid * kQCap * 32;
                 int32_t *qcnt = reinterpret_cast<int32_t *>(qbase + kConsumers * kQCap * 32 * (sizeof(double) + sizeof(int32_t))) + wid * 32;
@@ -1445,7 +1580,7 @@ __global__ void __launch_bounds__(32 * (NC + 1)) k_commit_ordered(const CommitAr
             }
         }
     }
-    if (wid == 0 && lane == 0 && n_acc) atomicAdd(a.accepted, n_acc);
+    if ((STEPWISE ? (wid < NC && (wid & 1) == 0) : wid == 0) && lane == 0 && n_acc) atomicAdd(a.accepted, n_acc);
 }
 
 size_t commit_tile_bytes(int K, int slab_width) { return (size_t)K * (K + 1) / 2 * slab_width * sizeof(double); }
@@ -1461,10 +1596,11 @@ void launch_commit_ordered(const CommitArgs &a, int max_slab_width, cudaStream_t
     static bool attr_set[64] = {};                    // the attribute is per device (one engine per device)
     int dev = 0;
     cudaGetDevice(&dev);
-    if (tile_bytes + ctrl_bytes <= 200 * 1024) {
+    if (tile_bytes + ctrl_bytes + 6144 <= 200 * 1024) {
         if (!attr_set[dev & 63]) {
             cudaFuncSetAttribute(k_commit_ordered<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             cudaFuncSetAttribute(k_commit_ordered<true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaFuncSetAttribute(k_commit_ordered<true, false, kStageSteps, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             cudaFuncSetAttribute(k_commit_ordered<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + kQueueBytes);
             attr_set[dev & 63] = true;
         }
@@ -1474,7 +1610,21 @@ void launch_commit_ordered(const CommitArgs &a, int max_slab_width, cudaStream_t
         if (a.max_ctas_per_sm > 0) per_sm = std::min<long long>(per_sm, a.max_ctas_per_sm);
         const long long grid = std::min<long long>(tasks, 148 * std::min<long long>(per_sm, 32));
         if (buckets) k_commit_ordered<true, true><<<(unsigned)grid, 32 * (kConsumers + 1), smem, st>>>(a);
-        else if (a.consumers == 1) {
+        else if (a.consumers == kStageSteps) {
+            CommitArgs b = a;
+            const size_t ctrl4 = (size_t)kStagesStepwise * kStageRecs * sizeof(UpdateRec) + 1024;
+            size_t smem4 = ctrl4 + tile_bytes;
+            b.tag_off = 0;
+            if (a.tags) {                                   // the consumer warps' tag arrays behind the tile
+                b.tag_off = (int32_t)((tile_bytes + 15) & ~(size_t)15);
+                smem4 = ctrl4 + (size_t)b.tag_off + (size_t)kStageSteps * 2 * kTagSlots;
+                if (smem4 > 200 * 1024) { b.tag_off = 0; smem4 = ctrl4 + tile_bytes; }
+            }
+            long long per_sm4 = std::min<long long>(64 / (kStageSteps + 1), std::max<long long>(1, (227 * 1024) / (long long)(smem4 + 1024)));
+            if (a.max_ctas_per_sm > 0) per_sm4 = std::min<long long>(per_sm4, a.max_ctas_per_sm);
+            const long long grid4 = std::min<long long>(tasks, 148 * per_sm4);
+            k_commit_ordered<true, false, kStageSteps, true><<<(unsigned)grid4, 32 * (kStageSteps + 1), smem4, st>>>(b);
+        } else if (a.consumers == 1) {
             const long long per_sm1 = a.max_ctas_per_sm > 0 ? std::min<long long>(a.max_ctas_per_sm, 32) : std::min<long long>(32, std::max<long long>(1, (227 * 1024) / (long long)(smem + 1024)));
             const long long grid1 = std::min<long long>(tasks, 148 * per_sm1);
             k_commit_ordered<true, false, 1><<<(unsigned)grid1, 64, smem, st>>>(a);

@@ -107,7 +107,10 @@ struct CommitArgs {
     int32_t n_task_tab;                  // `tensor` (individual 0), one RegionEnt per task, heavy tasks first
     int32_t max_tile_cells;              // largest tile of the table (sizes the shared memory)
     int32_t max_ctas_per_sm;             // > 0: cap of the persistent grid (leaves room for a kernel of another stream)
-    int32_t consumers;                   // 1: one consumer warp per CTA (shared-memory tiles, match.any fold); otherwise two
+    int32_t consumers;                   // 1: one consumer warp per CTA (shared-memory tiles, match.any fold); 4: one warp per step of a
+                                         // stage, folds serialised by named barriers (STEPWISE); otherwise two
+    int32_t tags;                        // consumers == 4: tag arrays, match.any only for steps in which three or more lanes share a slot
+    int32_t tag_off;                     // (set by the launcher) byte offset of the tag arrays behind the tile, 0 = none
 };
 struct CommitTile { int32_t row0, rows, b0, bins; };
 struct RouteArgs {               // large K: split every (individual, slab) record stream by block of tensor rows (k_route)

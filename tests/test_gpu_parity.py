@@ -17,6 +17,9 @@ from fastglobetrotter_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
+DEFAULT_COMMIT_CONSUMERS, DEFAULT_COMMIT_TAGS = 4, 1     # engine.h: Options::commit_consumers / commit_tags
+
+
 def packed_chrom(data):
     sp = data.spec
     per = sp.ploidy * sp.nsamples
@@ -872,6 +875,48 @@ def test_generator_and_commit_variants_are_bit_exact(lib, oracle, small, rand_im
             assert np.array_equal(lib.rand_fill(3), np.array([oracle.rand() for _ in range(3)], dtype=np.int32))
     finally:
         for k, v in (("rand_impl", 1), ("commit_impl", 0), ("eval_parts", 0), ("batch_pairs", 0)):
+            lib.set_option(k, v)
+
+
+@pytest.mark.parametrize("consumers,tags", [(1, 0), (2, 0), (4, 0), (4, 1)])
+def test_commit_consumer_variants_are_bit_exact(lib, oracle, small, consumers, tags):
+    """commit_consumers: 1 / 2 = one / two consumer warps that fold whole stages (match.any on every step), 4 = one warp per step of
+    a stage with the folds handed from warp to warp through named barriers; commit_tags = 1 adds the tag arrays that resolve steps of
+    distinct cells and of couples without match.any.  Two shapes: few cells (K=7: most steps hold cells shared by three or more
+    lanes -> the match.any fall-back) and many cells (K=24: distinct cells, couples and slot aliases; modes 1 and 3), forced
+    batches, and the NULL path's commit (small tiles) with the same variants."""
+    lib.set_option("rand_libc", 0)
+    lib.set_option("commit_consumers", consumers); lib.set_option("commit_tags", tags)
+    lib.set_option("null_consumers", consumers); lib.set_option("null_tags", tags)
+    try:
+        sp, chrom, dl, K, S, G, tw = _small_problem(small, oracle)
+        ids = bootstrap_ids(sp.n_inds, sp.n_chrom, 5)
+        for mode, batch in ((1, 0), (1, 40000)):
+            lib.set_option("batch_pairs", batch)
+            oracle.srand(3 + mode)
+            m_o, raw_o, pairs_o = oracle.data_read_packed(mode, sp.ploidy, sp.nsamples, chrom, ids, 0.1, G, 10, K, dl, 0.0, 1.0, S, tw,
+                                                          want_raw=True)
+            lib.srand(3 + mode)
+            m_g, raw_g, st = lib.data_read_packed(mode, sp.ploidy, sp.nsamples, chrom, ids, 0.1, G, 10, K, dl, 0.0, 1.0, S, tw,
+                                                  want_raw=True)
+            assert st["pairs"] == pairs_o
+            assert np.array_equal(raw_g, raw_o), (mode, batch, int((raw_g != raw_o).sum()))
+            assert np.array_equal(m_g, m_o, equal_nan=True)
+        lib.set_option("batch_pairs", 0)
+        n_o, ev = oracle.data_read_null_packed(sp.ploidy, sp.nsamples, chrom, np.arange(sp.n_inds), 0.1, G, 10, K, dl, 0.0, 1.0)
+        n_g, stn = lib.data_read_null_packed(sp.ploidy, sp.nsamples, chrom, np.arange(sp.n_inds), 0.1, G, 10, K, dl, 0.0, 1.0)
+        assert stn["pairs"] == ev and np.array_equal(n_g, n_o)
+        # many cells
+        K2, S2, G2 = 24, 3, 200
+        spec = synth.SynthSpec(n_chrom=1, n_inds=3, ploidy=2, nsamples=6, n_snps=9000, K=K2, rate=5e-7, seed=consumers * 10 + tags)
+        pos, rate, labels = synth.make_chromosome(spec, 0)
+        tw2 = np.random.default_rng(4).random(K2 * K2 * S2 * S2)
+        for mode in (1, 3):
+            _run_both(lib, oracle, mode, 2, 6, [{"pos": pos, "rate": rate, "labels": labels}], np.arange(3), 0.1, G2, 10, K2,
+                      spec.donor_label_vec(), 0.0, 1.0, S2, tw2, seed=21 + mode)
+    finally:
+        for k, v in (("commit_consumers", DEFAULT_COMMIT_CONSUMERS), ("commit_tags", DEFAULT_COMMIT_TAGS), ("null_consumers", 1),
+                     ("null_tags", 0), ("batch_pairs", 0)):
             lib.set_option(k, v)
 
 
