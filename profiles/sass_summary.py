@@ -3,7 +3,7 @@ import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(ROOT, "fastglobetrotter_b200", "fastGLOBETROTTERCompanion.so")
 out = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
-ops = ["UBLKCP", "SYNCS", "MATCH", "DMMA", "FENCE.VIEW.ASYNC", "SHFL", "VOTE", "REDG.E.ADD.F64", "REDUX", "DADD", "DMUL", "DFMA", "UTMALDG", "UTCHMMA", "LDTM"]
+ops = ["UBLKCP", "SYNCS", "MATCH", "BAR.ARV", "BAR.SYNC", "DMMA", "FENCE.VIEW.ASYNC", "SHFL", "VOTE", "REDG.E.ADD.F64", "REDUX", "DADD", "DMUL", "DFMA", "UTMALDG", "UTCHMMA", "LDTM"]
 cur, cnt, tot = None, collections.defaultdict(collections.Counter), collections.Counter()
 for ln in out.split("\n"):
     m = re.search(r"Function : (\S+)", ln)
