@@ -159,7 +159,10 @@ int64_t fgt_get_raw_counts(double *out, int64_t capacity);
  * "threads" (parser threads), "verbose", "devices" (GPUs per call, single process), "rand_impl" (1 = glibc stream generated
  * inside the pair-evaluation kernel, 0 = bulk stream in HBM), "commit_impl", "cache_mb".  Tuning / test hooks (defaults are the measured optimum): "accum_impl"
  * (2 = two-phase, 1 = single-phase), "batch_pairs", "blocks", "ranges", "split_ready", "eval_parts", "spec_rand",
- * "copy_streams", "null_slab_bins", "commit_ctas", "reuse_prep" (one-shot).  "null_impl": data_read_null as 2 = two phases (every
+ * "copy_streams", "null_slab_bins", "commit_ctas", "reuse_prep" (one-shot); "commit_consumers" (consumer warps of a commit CTA: 4 = step-wise,
+ * folds handed from warp to warp through named barriers, default; 1 / 2 = one / two warps that fold whole stages) with "commit_tags"
+ * (1 = tag arrays resolve steps of distinct cells and of couples without match.any, default), "null_consumers" / "null_tags" for the commit of
+ * data_read_null -- every setting gives the same bits.  "null_impl": data_read_null as 2 = two phases (every
  * chunk pair evaluated once into records, ordered commit), 1 = windowed kernel (one warp per label pair and slab), 0 = two phases
  * whenever its tables allow (K <= 4096, default); "null_tasks", "null_batch", "null_overlap", "null_block", "null_window" are its
  * tuning hooks.
