@@ -1193,9 +1193,9 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 constexpr int kQCap = 32;         // slots per lane queue (a single 32-record step always fits)
 constexpr int kQueueBytes = kConsumers * (kQCap * 32 * (int)(sizeof(double) + sizeof(int32_t)) + 32 * (int)sizeof(int32_t));
 
-// NC consumer warps per CTA.  With two, both warps read and match every record and fold only the cells they own (records of the
-// other warp share one sentinel key); with one (the default of both callers) no record is matched twice: the match.any unit is
-// the binding resource, and the second warp's sentinel keys cost more than sharing the fold chains saves.
+// NC consumer warps per CTA (not STEPWISE).  With two, both warps read and match every record and fold only the cells they own
+// (records of the other warp share one sentinel key); with one (the NULL path's default) no record is matched twice: the match.any
+// unit is the binding resource of these forms, and the second warp's sentinel keys cost more than sharing the fold chains saves.
 //
 // STEPWISE (shared-memory tiles, NC = 4): two sets of two consumer warps; set q takes the stages k = q (mod 2) of the record
 // stream, its warp h the steps 2h and 2h+1 (32 records each) of the stage.  Waiting for the stage, reading the records,
@@ -1205,7 +1205,7 @@ constexpr int kQueueBytes = kConsumers * (kQCap * 32 * (int)(sizeof(double) + si
 // matches, four folds: ~2 000 cycles) is one warp's latency and the SM's match.any unit is the binding resource.
 template <bool TILE_SMEM, bool BUCKETS, int NC = kConsumers, bool STEPWISE = false>
 __global__ void __launch_bounds__(32 * (NC + 1)) k_commit_ordered(const CommitArgs a) {
-    static_assert(!STEPWISE || (TILE_SMEM && !BUCKETS && NC == kStageSteps), "step-wise consumers: one warp per step of a stage");
+    static_assert(!STEPWISE || (TILE_SMEM && !BUCKETS && NC == kStageSteps), "step-wise consumers: two sets of two warps");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int RS = STEPWISE ? kStagesStepwise : kStages;    // ring depth
     static_assert(kStagesStepwise % 2 == 0, "each set of step-wise consumers walks every other ring slot");
@@ -1215,8 +1215,7 @@ __global__ void __launch_bounds__(32 * (NC + 1)) k_commit_ordered(const CommitAr
     uint64_t *empty = full + RS;
     int *stage_cnt = reinterpret_cast<int *>(empty + RS);                              // [RS]
     int *task_slot = stage_cnt + RS;                                                   // [1] task broadcast
-    RegionEnt *dir = reinterpret_cast<RegionEnt *>(smem_raw + kRing + 256);             // [32] staged directory entries
-    unsigned char *qbase = smem_raw + kRing + 1024;                                    // ring + 1 KB control, then the queues
+    unsigned char *qbase = smem_raw + kRing + 1024;                                    // ring + 1 KB control (barriers, counts), then the queues
     static_assert(2 * RS * 8 + RS * 4 + 4 <= 256, "control block layout");
     double *tile = reinterpret_cast<double *>(qbase + (BUCKETS ? kQueueBytes : 0));
     volatile unsigned char *tags = (STEPWISE && a.tag_off > 0) ? reinterpret_cast<unsigned char *>(tile) + a.tag_off : nullptr;

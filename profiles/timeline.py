@@ -1,10 +1,11 @@
-"""Print the engine's verbose host/device timeline for one data_read on the bench workload (device-resident paintings)."""
+"""Print the engine's verbose host/device timeline for one data_read on the bench workload (device-resident paintings;
+RLE=1: run-length-encoded rows, the bench's default input)."""
 import sys, os
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch
 from fastglobetrotter_b200 import synth, build as fbuild
 from fastglobetrotter_b200.companion import PackedCompanion
-from fastglobetrotter_b200.synth_torch import make_chromosome_device
+from fastglobetrotter_b200.synth_torch import make_chromosome_device, make_chromosome_runs_device
 lib = PackedCompanion(fbuild.build()); lib.set_option("rand_libc", 0)
 dev = torch.device("cuda", 0)
 N, L, K, G, S = 100, 100_000, 30, 500, 10
@@ -13,7 +14,10 @@ MODE = int(os.environ.get('MODE', 1))
 spec = synth.SynthSpec(n_chrom=1, n_inds=N, n_snps=L, K=K, nsamples=10, seed=20261021)
 pos, rate, lab = make_chromosome_device(spec, 0, dev)
 chrom = [{"pos": pos, "rate": rate, "labels": (lab.data_ptr(), 2, lab.shape[0])}]
-if os.environ.get("HOST"):
+if os.environ.get("RLE"):
+    pos, rate, run_off, runs = make_chromosome_runs_device(spec, 0, dev)
+    chrom = [{"pos": pos, "rate": rate, "runs": (run_off, int(runs.data_ptr()))}]
+elif os.environ.get("HOST"):
     hl = torch.empty(lab.shape, dtype=torch.int16, pin_memory=True); hl.copy_(lab)
     chrom = [{"pos": pos, "rate": rate, "labels": hl.numpy().view(np.uint16)}]
 for k, v in [kv.split("=") for kv in os.environ.get("OPTS", "").split(",") if kv]:
