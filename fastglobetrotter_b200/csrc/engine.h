@@ -67,7 +67,7 @@ struct Options {
     int null_window = -1;   // null_impl 2: windowed enumeration of phase 1; -1 = when under 90 % of the chunk pairs lie inside the distance window
     int null_min_batches = 4; // null_impl 2: batches per chromosome aimed at when the work allows (so that commit and evaluation overlap)
     int null_eval_ctas = 8, null_commit_ctas = 16;   // null_impl 2: persistent CTAs per SM of the two sides while they overlap
-    int null_consumers = 1; // null_impl 2: consumer warps per commit CTA (1, 2 or 4; bench chromosome 93 / 86 / 105 ms with 2 / 1 / 4)
+    int null_consumers = 1; // null_impl 2: consumer warps per commit CTA (1, 2 or 4; bench chromosome 93 / 86 / 110 ms with 2 / 1 / 4)
     int null_taper = 1;     // null_impl 2: shrinking last batches (the last commit has nothing to overlap with)
     int null_overlap = 1;   // null_impl 2: fold batch b on the commit stream while batch b+1 is evaluated (two record buffers)
     int null_world = 1, null_rank = 0;   // sharded NULL run: this rank folds the label pairs it owns (sum of the ranks = exact)

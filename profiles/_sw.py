@@ -12,7 +12,7 @@ pos, rate, run_off, runs = make_chromosome_runs_device(spec, 0, dev)
 chrom = [{"pos": pos, "rate": rate, "runs": (run_off, int(runs.data_ptr()))}]
 dl = spec.donor_label_vec(); rows = np.arange(N, dtype=np.int32)
 ref = None
-for nc, ec, cc in ((1,8,16),(4,8,12),(4,8,8),(4,8,6),(4,6,10),(4,10,8),(1,8,16)):
+for nc, ec, cc in ((1,8,16),(4,8,12),(4,8,8),(4,8,6),(1,8,16)):
     lib.set_option("null_consumers", nc); lib.set_option("null_eval_ctas", ec); lib.set_option("null_commit_ctas", cc)
     for rep in range(3):
         torch.cuda.synchronize(); t0 = time.perf_counter()
