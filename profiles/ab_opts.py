@@ -13,6 +13,9 @@ MODE = int(os.environ.get('MODE', 1))
 spec = synth.SynthSpec(n_chrom=1, n_inds=N, n_snps=L, K=K, nsamples=10, seed=20261021)
 pos, rate, run_off, runs = make_chromosome_runs_device(spec, 0, dev)
 chrom = [{"pos": pos, "rate": rate, "runs": (run_off, int(runs.data_ptr()))}]
+if os.environ.get("HOST"):         # the e2e leg of bench.py: the runs in pinned host memory, copied by the library inside the call
+    hr = torch.empty(runs.shape, dtype=runs.dtype, pin_memory=True); hr.copy_(runs); torch.cuda.synchronize()
+    chrom = [{"pos": pos, "rate": rate, "runs": (run_off, hr.numpy().view(np.uint32).reshape(-1, 2))}]
 dl = spec.donor_label_vec(); tw = lib.temp_weights_for_data_read(K, S, synth.random_weights(K, S)); ids = np.arange(N).astype(np.int32)
 defaults = {}
 for oset in os.environ.get("OPTSETS", "").split(";") or [""]:
