@@ -1444,7 +1444,7 @@ __global__ void __launch_bounds__(32 * (NC + 1)) k_commit_ordered(const CommitAr
                             t.s[h].cell = r.pad; t.s[h].val = r.val;
                         }
                     }
-                    fence_proxy_async_smem();                  // generic-proxy reads before the async-proxy refill (see below)
+                    fence_proxy_async_smem();                  // generic-proxy reads before the async-proxy refill (see fetch() of the other consumer forms)
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty[stage]);
                     stage += 2;                                // the next stage of this set
